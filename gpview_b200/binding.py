@@ -1,0 +1,259 @@
+"""ctypes binding of libgpview_b200.so (include/gpview_b200.h).  Harness only -- see gpview_b200/__init__.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgpview_b200.so")
+
+GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS = 1, 2, 4
+
+
+class GpvError(RuntimeError):
+    pass
+
+
+class CMesh(C.Structure):
+    _fields_ = [("n_tri", C.c_int64), ("tris", C.POINTER(C.c_float)), ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
+                ("max_model_size", C.c_float), ("n_verts", C.c_int64)]
+
+
+class CGrid(C.Structure):
+    _fields_ = [("num_div", C.c_int * 3), ("grid_size", C.c_float * 3), ("grid_size2", C.c_float * 3), ("ext1", C.c_float * 3),
+                ("ext2", C.c_float * 3), ("n2", C.c_int)]
+
+
+class CParams(C.Structure):
+    _fields_ = [("voxel_count", C.c_int), ("voxel_count2", C.c_int), ("flags", C.c_int), ("z0", C.c_int), ("z1", C.c_int)]
+
+
+class CResult(C.Structure):
+    _fields_ = [("grid", CGrid), ("z0", C.c_int), ("z1", C.c_int), ("cells", C.c_int64), ("n_boundary", C.c_int64), ("n23", C.c_int64),
+                ("d_level1_inout", C.c_void_p), ("d_prefix", C.c_void_p), ("d_boundary_index", C.c_void_p), ("d_level2_inout", C.c_void_p),
+                ("d_level1_normal", C.c_void_p), ("d_level2_normal", C.c_void_p), ("d_cell_off", C.c_void_p), ("d_cell_tris", C.c_void_p),
+                ("d_col_off", C.c_void_p), ("d_col_count", C.c_void_p), ("d_col_tris", C.c_void_p)] + [(k, C.c_int64) for k in (
+                    "l1_inside", "l1_boundary", "l2_inside", "l2_boundary", "l1_box_tests", "l1_box_hits", "l2_box_tests", "l2_ray_tests",
+                    "tri_total", "fill_crossings", "fill_ill_conditioned", "kernel_launches")]
+
+
+class CHostStreams(C.Structure):
+    _fields_ = [("level1_inout", C.c_void_p), ("prefix", C.c_void_p), ("boundary_index", C.c_void_p), ("level2_inout", C.c_void_p),
+                ("level1_normal", C.c_void_p), ("level2_normal", C.c_void_p), ("level2_capacity", C.c_int64), ("boundary_capacity", C.c_int64)]
+
+
+# every symbol include/gpview_b200.h declares (tests/test_abi_symbols.py checks the header against this and the .so)
+NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh",
+                  "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
+                  "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
+                  "gpv_save", "gpv_measure_fp32_peak", "gpv_measure_copy_peak"]
+COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libgpview_b200.so in-tree (nvcc, sm_100a, -fmad=false).  Cross-compiles without a GPU."""
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "csrc")] + ([] if verbose else ["-s"]))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GpvError("libgpview_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                           "there is no fallback implementation")
+        L = C.CDLL(LIB_PATH)
+        fp = C.POINTER(C.c_float)
+        vp = C.c_void_p
+        L.gpv_last_error.restype = C.c_char_p
+        L.gpv_device_count.restype = C.c_int
+        L.gpv_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.gpv_destroy.argtypes = [vp]; L.gpv_destroy.restype = None
+        for n in ("gpv_load_obj", "gpv_load_off", "gpv_load_mesh"):
+            getattr(L, n).argtypes = [C.c_char_p, C.POINTER(CMesh)]
+        L.gpv_mesh_from_triangles.argtypes = [fp, C.c_int64, C.POINTER(CMesh)]
+        L.gpv_free_mesh.argtypes = [C.POINTER(CMesh)]; L.gpv_free_mesh.restype = None
+        L.gpv_make_grid.argtypes = [fp, fp, C.c_float, C.c_int, C.c_int, C.POINTER(CGrid)]
+        L.gpv_alloc_host.argtypes = [C.c_int64]; L.gpv_alloc_host.restype = vp
+        L.gpv_free_host.argtypes = [vp]; L.gpv_free_host.restype = None
+        L.gpv_alloc_device.argtypes = [C.c_int64]; L.gpv_alloc_device.restype = vp
+        L.gpv_free_device.argtypes = [vp]; L.gpv_free_device.restype = None
+        L.gpv_memcpy_h2d.argtypes = [vp, vp, C.c_int64, vp]
+        L.gpv_memcpy_d2h.argtypes = [vp, vp, C.c_int64, vp]
+        L.gpv_stream_sync.argtypes = [vp]
+        L.gpv_voxelize_device.argtypes = [vp, vp, C.c_int64, fp, fp, C.c_float, C.POINTER(CParams), vp, C.POINTER(CResult)]
+        L.gpv_voxelize_host.argtypes = [vp, C.POINTER(CMesh), C.POINTER(CParams), vp, C.POINTER(CResult), C.POINTER(CHostStreams)]
+        L.gpv_save.argtypes = [C.POINTER(CMesh), C.POINTER(CResult), C.POINTER(CHostStreams), C.c_int, C.c_char_p]
+        L.gpv_measure_fp32_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
+        L.gpv_measure_copy_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc:
+        raise GpvError(lib().gpv_last_error().decode(errors="replace"))
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Mesh:
+    """Host mesh in the reference's flat layout (Object::CreateFlatTriangleData) with its padded bbox."""
+
+    def __init__(self, cmesh):
+        self.c = cmesh
+        self.ntri = int(cmesh.n_tri)
+        self.bbox_min = np.array(list(cmesh.bbox_min), np.float32)
+        self.bbox_max = np.array(list(cmesh.bbox_max), np.float32)
+        self.max_model_size = np.float32(cmesh.max_model_size)
+
+    @property
+    def tris(self):
+        return np.ctypeslib.as_array(self.c.tris, shape=(self.ntri * 9,)).reshape(-1, 9)
+
+    def set_bbox(self, bmin, bmax, max_model_size):
+        for a in range(3):
+            self.c.bbox_min[a] = float(bmin[a]); self.c.bbox_max[a] = float(bmax[a])
+        self.c.max_model_size = float(max_model_size)
+        self.bbox_min = np.array(list(self.c.bbox_min), np.float32); self.bbox_max = np.array(list(self.c.bbox_max), np.float32)
+        self.max_model_size = np.float32(self.c.max_model_size)
+
+    def __del__(self):
+        try:
+            lib().gpv_free_mesh(C.byref(self.c))
+        except Exception:
+            pass
+
+
+def load_mesh(path):
+    m = CMesh()
+    _check(lib().gpv_load_mesh(os.fsencode(path), C.byref(m)))
+    return Mesh(m)
+
+
+def mesh_from_triangles(tris):
+    t = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+    m = CMesh()
+    _check(lib().gpv_mesh_from_triangles(_fp(t), len(t), C.byref(m)))
+    return Mesh(m)
+
+
+def grid_for(bmin, bmax, max_model_size, l1, l2):
+    g = CGrid()
+    bmin = np.ascontiguousarray(bmin, np.float32); bmax = np.ascontiguousarray(bmax, np.float32)
+    _check(lib().gpv_make_grid(_fp(bmin), _fp(bmax), float(max_model_size), l1, l2, C.byref(g)))
+    return g
+
+
+class Params:
+    def __init__(self, l1=8, l2=4, flags=0, z0=0, z1=0):
+        self.c = CParams(l1, l2, flags, z0, z1)
+
+
+class Result:
+    """Device-resident result of one voxelization (views are valid until the next call on the same Context)."""
+
+    def __init__(self, cres, ctx):
+        self.c, self.ctx = cres, ctx
+        g = cres.grid
+        self.num_div = np.array(list(g.num_div), np.int32)
+        self.grid_size = np.array(list(g.grid_size), np.float32)
+        self.grid_size2 = np.array(list(g.grid_size2), np.float32)
+        self.n2, self.cells, self.nb, self.n23 = int(g.n2), int(cres.cells), int(cres.n_boundary), int(cres.n23)
+        self.z0, self.z1 = int(cres.z0), int(cres.z1)
+        self.counts = [int(cres.l1_inside), int(cres.l1_boundary), int(cres.l2_inside), int(cres.l2_boundary)]
+        self.stats = {k: int(getattr(cres, k)) for k in ("l1_box_tests", "l1_box_hits", "l2_box_tests", "tri_total", "fill_crossings",
+                                                         "fill_ill_conditioned", "kernel_launches")}
+
+    def _d2h(self, ptr, n, dtype):
+        out = np.empty(int(n), dtype)
+        if n and ptr:
+            _check(lib().gpv_memcpy_d2h(out.ctypes.data, ptr, out.nbytes, None))
+            _check(lib().gpv_stream_sync(None))
+        return out
+
+    def level1_inout(self): return self._d2h(self.c.d_level1_inout, self.cells, np.uint8)
+    def prefix(self): return self._d2h(self.c.d_prefix, self.cells, np.int32)
+    def boundary_index(self): return self._d2h(self.c.d_boundary_index, self.nb, np.int32)
+    def level2_inout(self): return self._d2h(self.c.d_level2_inout, self.nb * self.n23, np.uint8)
+    def level1_normal(self): return self._d2h(self.c.d_level1_normal, self.cells * 3, np.uint8)
+    def level2_normal(self): return self._d2h(self.c.d_level2_normal, self.nb * self.n23 * 3, np.uint8)
+    def cell_off(self): return self._d2h(self.c.d_cell_off, self.nb + 1, np.uint32)
+    def cell_tris(self): return self._d2h(self.c.d_cell_tris, int(self.c.tri_total), np.int32)
+    def col_off(self): return self._d2h(self.c.d_col_off, int(self.num_div[0]) * int(self.num_div[1]) + 1, np.uint32)
+    def col_count(self): return self._d2h(self.c.d_col_count, int(self.num_div[0]) * int(self.num_div[1]), np.int32)
+
+    def col_lists(self):
+        off, cnt = self.col_off(), self.col_count()
+        flat = self._d2h(self.c.d_col_tris, int(off[-1]), np.int32)
+        return [flat[o:o + c] for o, c in zip(off[:-1], cnt)]
+
+
+class Context:
+    """One per host thread and device (gpv_ctx)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().gpv_create(device, C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().gpv_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, mesh):
+        """Copy the mesh's flat triangles to the device; returns a device pointer owned by the caller (free_device)."""
+        L = lib()
+        d = L.gpv_alloc_device(mesh.ntri * 36)
+        if not d:
+            raise GpvError("device allocation failed")
+        _check(L.gpv_memcpy_h2d(d, C.cast(mesh.c.tris, C.c_void_p), mesh.ntri * 36, None))
+        _check(L.gpv_stream_sync(None))
+        return d
+
+    def free_device(self, d):
+        lib().gpv_free_device(d)
+
+    def voxelize_device(self, d_tris, mesh, params, stream=None):
+        r = CResult()
+        _check(lib().gpv_voxelize_device(self.h, d_tris, mesh.ntri, _fp(mesh.bbox_min), _fp(mesh.bbox_max), float(mesh.max_model_size),
+                                         C.byref(params.c), stream, C.byref(r)))
+        return Result(r, self)
+
+    def voxelize(self, mesh, params):
+        """Convenience: upload, voxelize, free the upload (results stay on the device)."""
+        d = self.upload(mesh)
+        try:
+            return self.voxelize_device(d, mesh, params)
+        finally:
+            self.free_device(d)
+
+    def voxelize_host(self, mesh, params, host, stream=None):
+        r = CResult()
+        _check(lib().gpv_voxelize_host(self.h, C.byref(mesh.c), C.byref(params.c), stream, C.byref(r), C.byref(host)))
+        return Result(r, self)
+
+    def fp32_peak(self):
+        v = C.c_double()
+        _check(lib().gpv_measure_fp32_peak(self.h, None, C.byref(v)))
+        return v.value
+
+    def copy_peak(self):
+        v = C.c_double()
+        _check(lib().gpv_measure_copy_peak(self.h, None, C.byref(v)))
+        return v.value
+
+
+def save(mesh, result, host, obj_id, directory):
+    _check(lib().gpv_save(C.byref(mesh.c), C.byref(result.c), C.byref(host), obj_id, os.fsencode(directory)))

@@ -1,0 +1,523 @@
+// gpview_b200/csrc/gpv_abi.cu -- C ABI (include/gpview_b200.h): context, device pipeline orchestration, compat tier.
+//
+// Pipeline of gpv_voxelize_device (what Object::PerformVoxelization, src/Object.cpp:3077-3430, does between
+// CreateFlatTriangleData and SaveVoxelization, re-designed for one B200):
+//
+//   k_tables, k_repack
+//   k_bin<count>            K1 count sweep: cellCount, colCount(over), l1Tests/l1Hits
+//   k_cross<count>          K2a count sweep: crossCount
+//   k_scan<CELLS>           K3: prefix, boundaryIndex, bTriOff, bmask, nBoundary, triTotal
+//   k_scan<OFFS> x2         column-list offsets, crossing-list offsets
+//   ---- one 64-byte read-back (sizes of the variable-length buffers) ----
+//   k_bin<fill>, k_cross<fill>
+//   k_sort_segments x2      canonical ascending cell lists; sorted + de-duplicated column lists
+//   k_fill_sweep            K2b: final Level-1 bytes + inside count
+//   k_l1_normals            (GPV_NORMALS)
+//   k_l2                    K4: Level-2 bytes + counts
+//   k_l2_normals            (GPV_NORMALS)
+#include "../../include/gpview_b200.h"
+#include "gpv_internal.h"
+#include "gpv_kernels.cuh"
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace gpv {
+
+static thread_local std::string g_err;
+int fail(const std::string& msg) { g_err = msg; return 1; }
+
+#define GPV_CUDA(call)                                                                                              \
+	do {                                                                                                            \
+		cudaError_t e_ = (call);                                                                                    \
+		if (e_ != cudaSuccess) return gpv::fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+	} while (0)
+
+struct DevBuf {
+	void* p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes)
+	{
+		if (bytes <= cap) return 0;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 256; // grow-only pool with slack so that repeated models do not reallocate
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess) return gpv::fail(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+		cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+} // namespace gpv
+
+struct gpv_ctx {
+	int device = 0;
+	int smCount = 0;
+	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch;
+	gpv::Totals* hTotals = nullptr; // pinned
+};
+
+using namespace gpv;
+
+extern "C" const char* gpv_last_error(void) { return g_err.c_str(); }
+
+extern "C" int gpv_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+extern "C" int gpv_create(int device, gpv_ctx** out)
+{
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) return fail("no CUDA device: libgpview_b200 has no CPU fallback");
+	if (device < 0 || device >= n) return fail("gpv_create: bad device index");
+	GPV_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	GPV_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) return fail(std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+	                                  "; libgpview_b200 carries sm_100a code only");
+	gpv_ctx* c = new gpv_ctx();
+	c->device = device;
+	c->smCount = prop.multiProcessorCount;
+	GPV_CUDA(cudaHostAlloc((void**)&c->hTotals, sizeof(Totals), cudaHostAllocDefault));
+	if (c->totals.ensure(sizeof(Totals))) { delete c; return 1; }
+	*out = c;
+	return 0;
+}
+
+extern "C" void gpv_destroy(gpv_ctx* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
+		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch };
+	for (DevBuf* b : all) b->release();
+	if (c->hTotals) cudaFreeHost(c->hTotals);
+	delete c;
+}
+
+extern "C" void* gpv_alloc_host(int64_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault) != cudaSuccess) { fail("cudaHostAlloc failed"); return nullptr; }
+	return p;
+}
+extern "C" void gpv_free_host(void* p) { if (p) cudaFreeHost(p); }
+extern "C" void* gpv_alloc_device(int64_t bytes)
+{
+	void* p = nullptr;
+	if (cudaMalloc(&p, (size_t)(bytes > 0 ? bytes : 1)) != cudaSuccess) { fail("cudaMalloc failed"); return nullptr; }
+	return p;
+}
+extern "C" void gpv_free_device(void* p) { if (p) cudaFree(p); }
+extern "C" int gpv_memcpy_h2d(void* dst, const void* src, int64_t bytes, void* stream)
+{
+	GPV_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+	return 0;
+}
+extern "C" int gpv_memcpy_d2h(void* dst, const void* src, int64_t bytes, void* stream)
+{
+	GPV_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+	return 0;
+}
+extern "C" int gpv_stream_sync(void* stream)
+{
+	GPV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+	return 0;
+}
+
+static int run_scan_offsets(gpv_ctx* c, cudaStream_t st, const int* in, long long n, unsigned* off, unsigned* totalOut, int64_t& launches)
+{
+	long long tiles = (n + kScanTile - 1) / kScanTile;
+	if (c->desc.ensure((size_t)(tiles + 1) * 8 + 16)) return 1;
+	GPV_CUDA(cudaMemsetAsync(c->desc.p, 0, (size_t)(tiles + 1) * 8 + 16, st));
+	ScanIO io{};
+	io.in = in; io.n = n;
+	io.desc = c->desc.as<unsigned long long>() + 1; io.tileCounter = c->desc.as<unsigned>();
+	io.off = off; io.totalOut = totalOut;
+	k_scan<MODE_OFFS><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
+	launches++;
+	return 0;
+}
+
+extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tri, const float bmin[3], const float bmax[3], float max_model_size,
+                                   const gpv_params* prm, void* stream, gpv_result* out)
+{
+	if (!c) return fail("gpv_voxelize_device: null ctx");
+	if (n_tri <= 0 || n_tri > 0x7fffffff) return fail("gpv_voxelize_device: triangle count out of range");
+	memset(out, 0, sizeof *out);
+	GPV_CUDA(cudaSetDevice(c->device));
+	cudaStream_t st = (cudaStream_t)stream;
+	const bool wantL2 = !(prm->flags & GPV_NO_LEVEL2) && prm->voxel_count2 > 0;
+	const bool wantN = (prm->flags & GPV_NORMALS) != 0;
+	if (gpv_make_grid(bmin, bmax, max_model_size, prm->voxel_count, wantL2 ? prm->voxel_count2 : 1, &out->grid)) return 1;
+	const gpv_grid& gg = out->grid;
+	if (gg.n2 > 32) return fail("voxel_count2 > 32 is not supported (Level-2 z parity is kept in one 32-bit word)");
+	GridP g{};
+	g.nx = gg.num_div[0]; g.ny = gg.num_div[1]; g.nz = gg.num_div[2];
+	g.z0 = 0; g.z1 = g.nz;
+	if (prm->z1 > 0) { g.z0 = prm->z0; g.z1 = prm->z1; }
+	if (g.z0 < 0 || g.z1 > g.nz || g.z0 >= g.z1) return fail("gpv_voxelize_device: bad z-slab");
+	g.minx = bmin[0]; g.miny = bmin[1]; g.minz = bmin[2]; g.maxx = bmax[0]; g.maxy = bmax[1]; g.maxz = bmax[2];
+	g.gsx = gg.grid_size[0]; g.gsy = gg.grid_size[1]; g.gsz = gg.grid_size[2];
+	g.h1x = gg.ext1[0]; g.h1y = gg.ext1[1]; g.h1z = gg.ext1[2];
+	g.h2x = gg.ext2[0]; g.h2y = gg.ext2[1]; g.h2z = gg.ext2[2];
+	g.n2 = gg.n2;
+	const long long ncol = (long long)g.nx * g.ny;
+	const long long cells = ncol * (g.z1 - g.z0);
+	if (ncol * g.nz > 0x7fffffffLL) return fail("grid exceeds 2^31 cells: boundary_index is int32 (file contract); shard finer");
+	const int nTri = (int)n_tri;
+	int64_t launches = 0;
+
+	// ---- fixed-size buffers
+	if (c->tri48.ensure((size_t)nTri * 48) || c->ray48.ensure((size_t)nTri * 48) || c->tabX.ensure((size_t)g.nx * 4) || c->tabY.ensure((size_t)g.ny * 4) ||
+	    c->tabZ.ensure((size_t)g.nz * 4) || c->cellCount.ensure((size_t)cells * 4 + 32) || c->colCount.ensure((size_t)ncol * 4 + 32) ||
+	    c->crossCount.ensure((size_t)ncol * 4 + 32) || c->prefix.ensure((size_t)(cells + 1) * 4 + 32) || c->bmask.ensure((size_t)cells / 8 + 64) ||
+	    c->boundaryIndex.ensure((size_t)cells * 4 + 32) || c->bTriOff.ensure((size_t)(cells + 1) * 4 + 32) || c->colOff.ensure((size_t)(ncol + 1) * 4 + 32) ||
+	    c->crossOff.ensure((size_t)(ncol + 1) * 4 + 32) || c->l1State.ensure((size_t)cells + 32))
+		return 1;
+	Totals* dT = c->totals.as<Totals>();
+	GPV_CUDA(cudaMemsetAsync(dT, 0, sizeof(Totals), st));
+	GPV_CUDA(cudaMemsetAsync(c->cellCount.p, 0, (size_t)cells * 4, st));
+	GPV_CUDA(cudaMemsetAsync(c->colCount.p, 0, (size_t)ncol * 4, st));
+	GPV_CUDA(cudaMemsetAsync(c->crossCount.p, 0, (size_t)ncol * 4, st));
+
+	float *cx = c->tabX.as<float>(), *cy = c->tabY.as<float>(), *cz = c->tabZ.as<float>();
+	float4 *tri48 = c->tri48.as<float4>(), *ray48 = c->ray48.as<float4>();
+	{
+		int m = g.nx > g.ny ? g.nx : g.ny; m = m > g.nz ? m : g.nz;
+		k_tables<<<(m + 255) / 256, 256, 0, st>>>(g, cx, cy, cz);
+		k_repack<<<(nTri + 255) / 256, 256, 0, st>>>(d_tris, nTri, tri48, ray48);
+		launches += 2;
+	}
+	const int binBlocks = (nTri + kBinThreads - 1) / kBinThreads;
+	BinOut bo{};
+	bo.cellCount = c->cellCount.as<int>(); bo.colCount = c->colCount.as<int>(); bo.totals = dT;
+	k_bin<false><<<binBlocks, kBinThreads, 0, st>>>(tri48, nTri, g, cx, cy, cz, bo);
+	k_cross<false><<<binBlocks, kBinThreads, 0, st>>>(ray48, nTri, g, cx, cy, c->crossCount.as<int>(), nullptr, nullptr, dT);
+	launches += 2;
+	{ // K3 boundary compaction
+		long long tiles = (cells + kScanTile - 1) / kScanTile;
+		if (c->desc.ensure((size_t)(tiles + 1) * 8 + 16)) return 1;
+		GPV_CUDA(cudaMemsetAsync(c->desc.p, 0, (size_t)(tiles + 1) * 8 + 16, st));
+		ScanIO io{};
+		io.in = c->cellCount.as<int>(); io.n = cells;
+		io.desc = c->desc.as<unsigned long long>() + 1; io.tileCounter = c->desc.as<unsigned>();
+		io.prefix = c->prefix.as<int>(); io.boundaryIndex = c->boundaryIndex.as<int>(); io.bTriOff = c->bTriOff.as<unsigned>();
+		io.bmask = c->bmask.as<unsigned char>(); io.globalBase = (long long)g.z0 * ncol; io.totals = dT;
+		k_scan<MODE_CELLS><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
+		launches++;
+	}
+	if (run_scan_offsets(c, st, c->colCount.as<int>(), ncol, c->colOff.as<unsigned>(), &dT->colTotalOver, launches)) return 1;
+	if (run_scan_offsets(c, st, c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, launches)) return 1;
+
+	// ---- the one size read-back
+	GPV_CUDA(cudaMemcpyAsync(c->hTotals, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
+	GPV_CUDA(cudaStreamSynchronize(st));
+	GPV_CUDA(cudaGetLastError());
+	const Totals T1 = *c->hTotals;
+	if (T1.l1Hits > 0x7ffffff0ull) return fail("more than 2^31 (cell, triangle) pairs in one slab: shard finer");
+	const long long nB = T1.nBoundary;
+	const long long n23 = (long long)g.n2 * g.n2 * g.n2;
+	if (c->cellTris.ensure((size_t)T1.triTotal * 4 + 32) || c->colTris.ensure((size_t)T1.colTotalOver * 4 + 32) || c->crossTri.ensure((size_t)T1.crossTotal * 4 + 32))
+		return 1;
+	if (wantL2 && c->l2State.ensure((size_t)(nB * n23) + 32)) return 1;
+	if (wantN && (c->l1Normal.ensure((size_t)cells * 3 + 32) || (wantL2 && c->l2Normal.ensure((size_t)(nB * n23) * 3 + 32)))) return 1;
+
+	bo.prefix = c->prefix.as<int>(); bo.bTriOff = c->bTriOff.as<unsigned>(); bo.cellTris = c->cellTris.as<int>();
+	bo.colOff = c->colOff.as<unsigned>(); bo.colTris = c->colTris.as<int>();
+	k_bin<true><<<binBlocks, kBinThreads, 0, st>>>(tri48, nTri, g, cx, cy, cz, bo);
+	k_cross<true><<<binBlocks, kBinThreads, 0, st>>>(ray48, nTri, g, cx, cy, c->crossCount.as<int>(), c->crossOff.as<unsigned>(), c->crossTri.as<int>(), dT);
+	launches += 2;
+	if (nB > 0) {
+		k_sort_segments<false><<<(unsigned)((nB * 32 + 255) / 256), 256, 0, st>>>(c->bTriOff.as<unsigned>(), (int)nB, c->cellTris.as<int>(), nullptr);
+		launches++;
+	}
+	k_sort_segments<true><<<(unsigned)((ncol * 32 + 255) / 256), 256, 0, st>>>(c->colOff.as<unsigned>(), (int)ncol, c->colTris.as<int>(), c->colCount.as<int>());
+	launches++;
+	{
+		dim3 grid((g.nx + 31) / 32, g.ny, (g.z1 - g.z0 + 127) / 128), block(32, 4);
+		k_fill_sweep<<<grid, block, 0, st>>>(ray48, g, cx, cy, cz, c->crossOff.as<unsigned>(), c->crossTri.as<int>(), c->bmask.as<unsigned char>(),
+		                                     c->l1State.as<unsigned char>(), dT);
+		launches++;
+	}
+	if (wantN) {
+		GPV_CUDA(cudaMemsetAsync(c->l1Normal.p, 127, (size_t)cells * 3, st));
+		if (nB > 0) {
+			k_l1_normals<<<(unsigned)((nB + 127) / 128), 128, 0, st>>>(tri48, c->boundaryIndex.as<int>(), c->bTriOff.as<unsigned>(), c->cellTris.as<int>(), (int)nB,
+			                                                         (long long)g.z0 * ncol, c->l1Normal.as<unsigned char>());
+			launches++;
+		}
+	}
+	L2IO lio{};
+	if (wantL2 && nB > 0) {
+		lio.tri48 = tri48; lio.ray48 = ray48; lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
+		lio.cellTris = c->cellTris.as<int>(); lio.colOff = c->colOff.as<unsigned>(); lio.colCount = c->colCount.as<int>(); lio.colTris = c->colTris.as<int>();
+		lio.cx = cx; lio.cy = cy; lio.cz = cz; lio.l2State = c->l2State.as<unsigned char>(); lio.nBoundary = (int)nB; lio.totals = dT;
+		const int rows = g.n2 * g.n2, G = rows >= kL2Threads ? 1 : kL2Threads / rows;
+		const size_t smem = (size_t)G * 3 * g.n2 * 4 + (size_t)G * rows * 4 + (size_t)G * 16;
+		k_l2<<<(unsigned)((nB + G - 1) / G), kL2Threads, smem, st>>>(g, lio);
+		launches++;
+		if (wantN) {
+			k_l2_normals<<<(unsigned)((nB * n23 + 255) / 256), 256, 0, st>>>(g, lio, c->l2Normal.as<unsigned char>());
+			launches++;
+		}
+	}
+	GPV_CUDA(cudaMemcpyAsync(c->hTotals, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
+	GPV_CUDA(cudaStreamSynchronize(st));
+	GPV_CUDA(cudaGetLastError());
+	const Totals T2 = *c->hTotals;
+
+	out->z0 = g.z0; out->z1 = g.z1;
+	out->cells = cells; out->n_boundary = nB; out->n23 = n23;
+	out->d_level1_inout = c->l1State.as<uint8_t>();
+	out->d_prefix = c->prefix.as<int32_t>();
+	out->d_boundary_index = c->boundaryIndex.as<int32_t>();
+	out->d_level2_inout = wantL2 ? c->l2State.as<uint8_t>() : nullptr;
+	out->d_level1_normal = wantN ? c->l1Normal.as<uint8_t>() : nullptr;
+	out->d_level2_normal = (wantN && wantL2) ? c->l2Normal.as<uint8_t>() : nullptr;
+	out->d_cell_off = c->bTriOff.as<uint32_t>(); out->d_cell_tris = c->cellTris.as<int32_t>();
+	out->d_col_off = c->colOff.as<uint32_t>(); out->d_col_count = c->colCount.as<int32_t>(); out->d_col_tris = c->colTris.as<int32_t>();
+	out->l1_inside = (int64_t)T2.l1Inside; out->l1_boundary = nB;
+	out->l2_inside = (int64_t)T2.l2Inside; out->l2_boundary = (int64_t)T2.l2Boundary;
+	out->l1_box_tests = (int64_t)T2.l1Tests; out->l1_box_hits = (int64_t)T2.l1Hits;
+	out->tri_total = T2.triTotal;
+	out->l2_box_tests = wantL2 ? (int64_t)T2.triTotal * n23 : 0; // reference-equivalent: n2^3 x sum of cell list lengths (cu:428)
+	out->l2_ray_tests = 0;
+	out->fill_crossings = (int64_t)T2.crossPairs; out->fill_ill_conditioned = (int64_t)T2.nIll;
+	out->kernel_launches = launches;
+	return 0;
+}
+
+extern "C" int gpv_voxelize_host(gpv_ctx* c, const gpv_mesh* mesh, const gpv_params* prm, void* stream, gpv_result* out, gpv_host_streams* h)
+{
+	if (!c || !mesh || !mesh->tris) return fail("gpv_voxelize_host: null argument");
+	GPV_CUDA(cudaSetDevice(c->device));
+	cudaStream_t st = (cudaStream_t)stream;
+	if (c->scratch.ensure((size_t)mesh->n_tri * 36)) return 1;
+	GPV_CUDA(cudaMemcpyAsync(c->scratch.p, mesh->tris, (size_t)mesh->n_tri * 36, cudaMemcpyHostToDevice, st));
+	if (gpv_voxelize_device(c, c->scratch.as<float>(), mesh->n_tri, mesh->bbox_min, mesh->bbox_max, mesh->max_model_size, prm, stream, out)) return 1;
+	const size_t cells = (size_t)out->cells, l2n = (size_t)(out->n_boundary * out->n23);
+	if (h->level2_inout && out->d_level2_inout && (int64_t)l2n > h->level2_capacity) return fail("gpv_voxelize_host: level2 host buffer too small");
+	if (h->boundary_index && out->n_boundary > h->boundary_capacity) return fail("gpv_voxelize_host: boundary_index host buffer too small");
+	if (h->level1_inout) GPV_CUDA(cudaMemcpyAsync(h->level1_inout, out->d_level1_inout, cells, cudaMemcpyDeviceToHost, st));
+	if (h->prefix) GPV_CUDA(cudaMemcpyAsync(h->prefix, out->d_prefix, cells * 4, cudaMemcpyDeviceToHost, st));
+	if (h->boundary_index && out->n_boundary) GPV_CUDA(cudaMemcpyAsync(h->boundary_index, out->d_boundary_index, (size_t)out->n_boundary * 4, cudaMemcpyDeviceToHost, st));
+	if (h->level2_inout && out->d_level2_inout && l2n) GPV_CUDA(cudaMemcpyAsync(h->level2_inout, out->d_level2_inout, l2n, cudaMemcpyDeviceToHost, st));
+	if (h->level1_normal && out->d_level1_normal) GPV_CUDA(cudaMemcpyAsync(h->level1_normal, out->d_level1_normal, cells * 3, cudaMemcpyDeviceToHost, st));
+	if (h->level2_normal && out->d_level2_normal && l2n) GPV_CUDA(cudaMemcpyAsync(h->level2_normal, out->d_level2_normal, l2n * 3, cudaMemcpyDeviceToHost, st));
+	GPV_CUDA(cudaStreamSynchronize(st));
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ roofline probes
+// non-FMA FP32 issue rate: independent FMUL/FADD chains, 8 accumulators per thread
+__global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters)
+{
+	float a0 = threadIdx.x * 1e-3f + 1.f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+	const float m = 1.0000001f, d = 1e-7f;
+	for (int i = 0; i < iters; i++) {
+		a0 = a0 * m; a1 = a1 + d; a2 = a2 * m; a3 = a3 + d; a4 = a4 * m; a5 = a5 + d; a6 = a6 * m; a7 = a7 + d;
+		a0 = a0 + d; a1 = a1 * m; a2 = a2 + d; a3 = a3 * m; a4 = a4 + d; a5 = a5 * m; a6 = a6 + d; a7 = a7 * m;
+	}
+	if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
+}
+
+extern "C" int gpv_measure_fp32_peak(gpv_ctx* c, void* stream, double* ops)
+{
+	GPV_CUDA(cudaSetDevice(c->device));
+	cudaStream_t st = (cudaStream_t)stream;
+	if (c->scratch.ensure(1024)) return 1;
+	cudaEvent_t e0, e1;
+	GPV_CUDA(cudaEventCreate(&e0)); GPV_CUDA(cudaEventCreate(&e1));
+	const int iters = 4096, blocks = c->smCount * 16;
+	k_fp32_peak<<<blocks, 256, 0, st>>>(c->scratch.as<float>(), 64);
+	double best = 0;
+	for (int rep = 0; rep < 5; rep++) {
+		GPV_CUDA(cudaEventRecord(e0, st));
+		k_fp32_peak<<<blocks, 256, 0, st>>>(c->scratch.as<float>(), iters);
+		GPV_CUDA(cudaEventRecord(e1, st));
+		GPV_CUDA(cudaEventSynchronize(e1));
+		float ms = 0;
+		GPV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+		double v = (double)blocks * 256 * iters * 16 / (ms * 1e-3);
+		if (v > best) best = v;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	*ops = best;
+	return 0;
+}
+
+extern "C" int gpv_measure_copy_peak(gpv_ctx* c, void* stream, double* gbs)
+{
+	GPV_CUDA(cudaSetDevice(c->device));
+	cudaStream_t st = (cudaStream_t)stream;
+	const size_t bytes = (size_t)1 << 30;
+	if (c->scratch.ensure(2 * bytes)) return 1;
+	cudaEvent_t e0, e1;
+	GPV_CUDA(cudaEventCreate(&e0)); GPV_CUDA(cudaEventCreate(&e1));
+	char* p = c->scratch.as<char>();
+	double best = 0;
+	for (int rep = 0; rep < 6; rep++) {
+		GPV_CUDA(cudaEventRecord(e0, st));
+		GPV_CUDA(cudaMemcpyAsync(p + bytes, p, bytes, cudaMemcpyDeviceToDevice, st));
+		GPV_CUDA(cudaEventRecord(e1, st));
+		GPV_CUDA(cudaEventSynchronize(e1));
+		float ms = 0;
+		GPV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+		double v = 2.0 * bytes / (ms * 1e-3) / 1e9;
+		if (rep && v > best) best = v;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	*gbs = best;
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ compatibility tier
+// The reference's three operator entry points (cu:507-540), same signatures and launch semantics (asynchronous on the
+// default stream, always return 1, errors surface at the caller's CUDACheckErrors), strict-IEEE arithmetic.
+namespace gpv {
+
+__global__ void __launch_bounds__(128) k_compat_l1(const float* __restrict__ tris, int nTri, float* inOut, int* count, int* triIndex,
+                                                   gpv_float3 mn, gpv_float3 mx, gpv_float3 ext, gpv_int3 nd, int bufLen)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nTri) return;
+	const float* v = tris + (size_t)t * 9;
+	float a0 = v[0], a1 = v[1], a2 = v[2], b0 = v[3], b1 = v[4], b2 = v[5], c0 = v[6], c1 = v[7], c2 = v[8];
+	int x0 = cell_of(a0, mn.x, mx.x, nd.x), x1 = cell_of(b0, mn.x, mx.x, nd.x), x2 = cell_of(c0, mn.x, mx.x, nd.x);
+	int y0 = cell_of(a1, mn.y, mx.y, nd.y), y1 = cell_of(b1, mn.y, mx.y, nd.y), y2 = cell_of(c1, mn.y, mx.y, nd.y);
+	int z0 = cell_of(a2, mn.z, mx.z, nd.z), z1 = cell_of(b2, mn.z, mx.z, nd.z), z2 = cell_of(c2, mn.z, mx.z, nd.z);
+	int lox = max(0, min(x0, min(x1, x2))), hix = max(x0, max(x1, x2));
+	int loy = max(0, min(y0, min(y1, y2))), hiy = max(y0, max(y1, y2));
+	int loz = max(0, min(z0, min(z1, z2))), hiz = max(z0, max(z1, z2));
+	for (int p = lox; p <= hix && p < nd.x; p++) for (int q = loy; q <= hiy && q < nd.y; q++) for (int r = loz; r <= hiz && r < nd.z; r++) {
+		float mx_ = (float)((p + 0.5) * (double)ext.x * 2 + (double)mn.x); // cu:382-384
+		float my_ = (float)((q + 0.5) * (double)ext.y * 2 + (double)mn.y);
+		float mz_ = (float)((r + 0.5) * (double)ext.z * 2 + (double)mn.z);
+		if (tri_box_overlap(mx_, my_, mz_, ext.x, ext.y, ext.z, a0, a1, a2, b0, b1, b2, c0, c1, c2)) {
+			int index = r * nd.y * nd.x + q * nd.x + p;
+			inOut[index] = 2;
+			int slot = atomicAdd(count + index, 1);
+			if (slot < bufLen) triIndex[(size_t)index * bufLen + slot] = t; // the reference writes unconditionally (App. B4)
+		}
+	}
+}
+
+__device__ __forceinline__ void compat_l2_centre(int loc, gpv_int3 n2, const float* mid, int b, gpv_float3 e1, gpv_float3 e2, float& cxv, float& cyv, float& czv)
+{
+	int r = loc / (n2.x * n2.y), pq = loc - r * n2.x * n2.y, q = pq / n2.x, p = pq % n2.x;
+	cxv = (float)(2 * p + 1) * e2.x + mid[b * 3 + 0] - e1.x; // cu:423-425
+	cyv = (float)(2 * q + 1) * e2.y + mid[b * 3 + 1] - e1.y;
+	czv = (float)(2 * r + 1) * e2.z + mid[b * 3 + 2] - e1.z;
+}
+
+__global__ void __launch_bounds__(256) k_compat_l2_sat(const float* __restrict__ tris, float* l2InOut, float* l2Normal, const float* __restrict__ mid,
+                                                       const int* __restrict__ l2Index, const int* __restrict__ triCount, const int* __restrict__ triFlatIndex,
+                                                       const int* __restrict__ triFlat, int nB, gpv_int3 n2, gpv_float3 e1, gpv_float3 e2)
+{
+	const long long n23 = (long long)n2.x * n2.y * n2.z;
+	long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= nB * n23) return;
+	int b = (int)(v / n23), loc = (int)(v - (long long)b * n23);
+	int cell = l2Index[b], nT = triCount[cell], first = triFlatIndex[cell];
+	float cxv, cyv, czv;
+	compat_l2_centre(loc, n2, mid, b, e1, e2, cxv, cyv, czv);
+	float ax = l2Normal[v * 4], ay = l2Normal[v * 4 + 1], az = l2Normal[v * 4 + 2], an = l2Normal[v * 4 + 3];
+	bool hit = false;
+	for (int k = 0; k < nT; k++) {
+		const float* d = tris + (size_t)triFlat[first + k] * 9;
+		if (tri_box_overlap(cxv, cyv, czv, e2.x, e2.y, e2.z, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8])) {
+			hit = true;
+			float ux = d[3] - d[0], uy = d[4] - d[1], uz = d[5] - d[2], wx = d[6] - d[0], wy = d[7] - d[1], wz = d[8] - d[2];
+			ax += uy * wz - uz * wy; ay += uz * wx - ux * wz; az += ux * wy - uy * wx; an += 1; // cu:40-46, 311-318
+		}
+	}
+	if (hit) { l2InOut[v] = 2; l2Normal[v * 4] = ax; l2Normal[v * 4 + 1] = ay; l2Normal[v * 4 + 2] = az; l2Normal[v * 4 + 3] = an; }
+}
+
+__global__ void __launch_bounds__(256) k_compat_l2_ray(const float* __restrict__ tris, float* l2InOut, const float* __restrict__ mid, const int* __restrict__ l2Index,
+                                                       const int* __restrict__ xyCount, const int* __restrict__ xyFlatIndex, const int* __restrict__ xyFlat, int nB,
+                                                       gpv_int3 nd, gpv_int3 n2, gpv_float3 e1, gpv_float3 e2)
+{
+	const long long n23 = (long long)n2.x * n2.y * n2.z;
+	long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= nB * n23) return;
+	int b = (int)(v / n23), loc = (int)(v - (long long)b * n23);
+	int xy = l2Index[b] % (nd.x * nd.y), nT = xyCount[xy], first = xyFlatIndex[xy];
+	float cxv, cyv, czv;
+	compat_l2_centre(loc, n2, mid, b, e1, e2, cxv, cyv, czv);
+	int n = 0;
+	for (int k = 0; k < nT; k++) {
+		const float* d = tris + (size_t)xyFlat[first + k] * 9;
+		RayTri s; RayCol rc;
+		ray_tri_setup(s, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8]);
+		n += s.ok && ray_column(s, cxv, cyv, rc) && ray_cell(s, rc, czv);
+	}
+	if (n % 2 == 1) l2InOut[v] = 1; // cu:497-501
+}
+
+__global__ void __launch_bounds__(256) k_max_reduce(const float* __restrict__ in, long long n, float* out)
+{
+	__shared__ float s[8];
+	float m = -3.402823466e+38f;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, in[i]);
+	for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+	if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+	__syncthreads();
+	if (threadIdx.x < 8) {
+		m = s[threadIdx.x];
+		for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+		if (threadIdx.x == 0) out[blockIdx.x] = m;
+	}
+}
+
+} // namespace gpv
+
+extern "C" int CUDAClassifyTessellation(float* tris, int nTri, float* inOut, int* count, int* triIndex, gpv_float3 mn, gpv_float3 mx, gpv_float3 ext,
+                                        gpv_int3 nd, int bufLen)
+{
+	if (nTri > 0) k_compat_l1<<<(nTri + 127) / 128, 128>>>(tris, nTri, inOut, count, triIndex, mn, mx, ext, nd, bufLen);
+	return 1;
+}
+
+extern "C" int CUDAClassifyTessellationLevel2(float* tris, float* l2InOut, float* l2Normal, float* mid, int* l2Index, int* triCount, int* triFlatIndex,
+                                              int* triFlat, int nB, gpv_int3 n2, gpv_float3 e1, gpv_float3 e2)
+{
+	long long total = (long long)nB * n2.x * n2.y * n2.z;
+	if (total > 0) k_compat_l2_sat<<<(unsigned)((total + 255) / 256), 256>>>(tris, l2InOut, l2Normal, mid, l2Index, triCount, triFlatIndex, triFlat, nB, n2, e1, e2);
+	return 1;
+}
+
+extern "C" int CUDAClassifyInOutLevel2(float* tris, float* l2InOut, float* mid, int* l2Index, int* xyCount, int* xyFlatIndex, int* xyFlat, int nB,
+                                       gpv_int3 nd, gpv_int3 n2, gpv_float3 e1, gpv_float3 e2)
+{
+	long long total = (long long)nB * n2.x * n2.y * n2.z;
+	if (total > 0) k_compat_l2_ray<<<(unsigned)((total + 255) / 256), 256>>>(tris, l2InOut, mid, l2Index, xyCount, xyFlatIndex, xyFlat, nB, nd, n2, e1, e2);
+	return 1;
+}
+
+extern "C" float THRUSTDeviceFindMax(float* data, int w, int h)
+{
+	long long n = (long long)w * h;
+	if (n <= 0) return 0.f;
+	float* part = nullptr;
+	const int blocks = 256;
+	if (cudaMalloc(&part, (blocks + 1) * sizeof(float)) != cudaSuccess) return 0.f;
+	k_max_reduce<<<blocks, 256>>>(data, n, part);
+	k_max_reduce<<<1, 256>>>(part, blocks, part + blocks);
+	float r = 0.f;
+	cudaMemcpy(&r, part + blocks, sizeof(float), cudaMemcpyDeviceToHost);
+	cudaFree(part);
+	return r;
+}

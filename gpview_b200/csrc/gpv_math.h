@@ -1,0 +1,227 @@
+// gpview_b200/csrc/gpv_math.h -- intersection arithmetic of the voxelizer path, shared by every kernel.
+//
+// Bit-exactness contract (DESIGN.md "Numerics"): every binary32 operation below is a separate IEEE-754 round-to-nearest
+// operation in the reference's operand order.  The translation unit that includes this header MUST be compiled with
+// FMA contraction disabled (nvcc -fmad=false; g++ -ffp-contract=off for the CPU-side unit probes in tests/).
+// The functions are __host__ __device__ only so that tests/ can exercise the very same source on the CPU against the
+// oracle; the product never calls them on the host.
+//
+// Reference arithmetic restated here:
+//   SAT  tri/box : TriBoxOverlapCUDA  cuda/CUDAClassifyTessellation.cu:234-309 (== src/TriBoxIntersection.cpp:135-210)
+//   ray  tri/+Z  : TriRayIntersectCUDA cuda/CUDAClassifyTessellation.cu:102-155 (== src/TriRayIntersection.cpp:78-131)
+//   cell index   : cuda/CUDAClassifyTessellation.cu:333-361
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GPV_HD __host__ __device__ __forceinline__
+#else
+#define GPV_HD inline
+#endif
+
+namespace gpv {
+
+// fl32(1e-6): the reference compares floats against the DOUBLE literal 0.000001 (cu:76).  For a float x:
+//   (double)x < 1e-6  <=>  x <= kEps      (double)x > -1e-6  <=>  x >= -kEps      (double)x > 1e-6  <=>  x > kEps
+constexpr float kEps = 9.99999997475242707878e-07f;
+constexpr float kFltMax = 3.402823466e+38f;
+
+// ---- separating-axis helper: `if (min>rad || max<-rad) return 0;` of every AXISTEST macro (cu:182-231)
+GPV_HD bool axis_separates(float pa, float pb, float rad)
+{
+	float mn = fminf(pa, pb), mx = fmaxf(pa, pb); // pa,pb are never NaN for finite input; min/max == the macro's if/else
+	return mn > rad || mx < -rad;
+}
+
+// ---- full 13-predicate SAT in the reference's order (used by Level-1 binning, where nothing can be hoisted)
+GPV_HD bool tri_box_overlap(float cx, float cy, float cz, float hx, float hy, float hz,
+                            float t0x, float t0y, float t0z, float t1x, float t1y, float t1z, float t2x, float t2y, float t2z)
+{
+	// translate so the box centre is the origin (cu:251-253); edges are formed AFTER the translation (cu:256-258)
+	float v0x = t0x - cx, v0y = t0y - cy, v0z = t0z - cz;
+	float v1x = t1x - cx, v1y = t1y - cy, v1z = t1z - cz;
+	float v2x = t2x - cx, v2y = t2y - cy, v2z = t2z - cz;
+	// cheap predicates first (legal: the result is an AND of side-effect-free predicates)
+	{
+		float mn = fminf(v0x, fminf(v1x, v2x)), mx = fmaxf(v0x, fmaxf(v1x, v2x));
+		if (mn > hx || mx < -hx) return false;
+		mn = fminf(v0y, fminf(v1y, v2y)); mx = fmaxf(v0y, fmaxf(v1y, v2y));
+		if (mn > hy || mx < -hy) return false;
+		mn = fminf(v0z, fminf(v1z, v2z)); mx = fmaxf(v0z, fmaxf(v1z, v2z));
+		if (mn > hz || mx < -hz) return false;
+	}
+	float e0x = v1x - v0x, e0y = v1y - v0y, e0z = v1z - v0z;
+	float e1x = v2x - v1x, e1y = v2y - v1y, e1z = v2z - v1z;
+	// plane of the triangle against the box (cu:304-306, planeBoxOverlapCUDA cu:157-179)
+	{
+		float nx = e0y * e1z - e0z * e1y, ny = e0z * e1x - e0x * e1z, nz = e0x * e1y - e0y * e1x;
+		float mnx = (nx > 0.0f) ? (-hx - v0x) : (hx - v0x), mxx = (nx > 0.0f) ? (hx - v0x) : (-hx - v0x);
+		float mny = (ny > 0.0f) ? (-hy - v0y) : (hy - v0y), mxy = (ny > 0.0f) ? (hy - v0y) : (-hy - v0y);
+		float mnz = (nz > 0.0f) ? (-hz - v0z) : (hz - v0z), mxz = (nz > 0.0f) ? (hz - v0z) : (-hz - v0z);
+		if (nx * mnx + ny * mny + nz * mnz > 0.0f) return false;
+		if (!(nx * mxx + ny * mxy + nz * mxz >= 0.0f)) return false;
+	}
+	float e2x = v0x - v2x, e2y = v0y - v2y, e2z = v0z - v2z;
+	float fex, fey, fez;
+	// edge 0: X01 Y02 Z12 (cu:262-267)
+	fex = fabsf(e0x); fey = fabsf(e0y); fez = fabsf(e0z);
+	if (axis_separates(e0z * v0y - e0y * v0z, e0z * v2y - e0y * v2z, fez * hy + fey * hz)) return false;
+	if (axis_separates(-e0z * v0x + e0x * v0z, -e0z * v2x + e0x * v2z, fez * hx + fex * hz)) return false;
+	if (axis_separates(e0y * v1x - e0x * v1y, e0y * v2x - e0x * v2y, fey * hx + fex * hy)) return false;
+	// edge 1: X01 Y02 Z0 (cu:269-274)
+	fex = fabsf(e1x); fey = fabsf(e1y); fez = fabsf(e1z);
+	if (axis_separates(e1z * v0y - e1y * v0z, e1z * v2y - e1y * v2z, fez * hy + fey * hz)) return false;
+	if (axis_separates(-e1z * v0x + e1x * v0z, -e1z * v2x + e1x * v2z, fez * hx + fex * hz)) return false;
+	if (axis_separates(e1y * v0x - e1x * v0y, e1y * v1x - e1x * v1y, fey * hx + fex * hy)) return false;
+	// edge 2: X2 Y1 Z12 (cu:276-281)
+	fex = fabsf(e2x); fey = fabsf(e2y); fez = fabsf(e2z);
+	if (axis_separates(e2z * v0y - e2y * v0z, e2z * v1y - e2y * v1z, fez * hy + fey * hz)) return false;
+	if (axis_separates(-e2z * v0x + e2x * v0z, -e2z * v1x + e2x * v1z, fez * hx + fex * hz)) return false;
+	if (axis_separates(e2y * v1x - e2x * v1y, e2y * v2x - e2x * v2y, fey * hx + fex * hy)) return false;
+	return true;
+}
+
+// ---- Level-2 SAT, hoisted along x.  A row of sub-voxels shares (cy,cz); everything that touches only y/z components is
+// computed once per (row, triangle): the translated y/z coordinates, the y/z edge components, the three X-axis tests,
+// the y/z AABB tests and the x component of the normal.  Exact: those sub-expressions do not involve cx at all.
+struct SatRow {
+	float v0y, v0z, v1y, v1z, v2y, v2z;
+	float e0y, e0z, e1y, e1z, e2y, e2z;
+	float nx;                 // e0y*e1z - e0z*e1y
+	float py0, py1, pz0, pz1; // plane-box candidates: (-hy - v0y, hy - v0y), (-hz - v0z, hz - v0z)
+};
+
+// returns false when a p-independent predicate already separates the triangle from every box of the row
+GPV_HD bool sat_row_setup(SatRow& s, float cy, float cz, float hy, float hz,
+                          float t0y, float t0z, float t1y, float t1z, float t2y, float t2z)
+{
+	s.v0y = t0y - cy; s.v0z = t0z - cz; s.v1y = t1y - cy; s.v1z = t1z - cz; s.v2y = t2y - cy; s.v2z = t2z - cz;
+	{
+		float mn = fminf(s.v0y, fminf(s.v1y, s.v2y)), mx = fmaxf(s.v0y, fmaxf(s.v1y, s.v2y));
+		if (mn > hy || mx < -hy) return false;
+		mn = fminf(s.v0z, fminf(s.v1z, s.v2z)); mx = fmaxf(s.v0z, fmaxf(s.v1z, s.v2z));
+		if (mn > hz || mx < -hz) return false;
+	}
+	s.e0y = s.v1y - s.v0y; s.e0z = s.v1z - s.v0z;
+	s.e1y = s.v2y - s.v1y; s.e1z = s.v2z - s.v1z;
+	s.e2y = s.v0y - s.v2y; s.e2z = s.v0z - s.v2z;
+	// X01(e0), X01(e1), X2(e2): a = e.z, b = e.y, rad = |e.z|*hy + |e.y|*hz
+	if (axis_separates(s.e0z * s.v0y - s.e0y * s.v0z, s.e0z * s.v2y - s.e0y * s.v2z, fabsf(s.e0z) * hy + fabsf(s.e0y) * hz)) return false;
+	if (axis_separates(s.e1z * s.v0y - s.e1y * s.v0z, s.e1z * s.v2y - s.e1y * s.v2z, fabsf(s.e1z) * hy + fabsf(s.e1y) * hz)) return false;
+	if (axis_separates(s.e2z * s.v0y - s.e2y * s.v0z, s.e2z * s.v1y - s.e2y * s.v1z, fabsf(s.e2z) * hy + fabsf(s.e2y) * hz)) return false;
+	s.nx = s.e0y * s.e1z - s.e0z * s.e1y;
+	s.py0 = -hy - s.v0y; s.py1 = hy - s.v0y; s.pz0 = -hz - s.v0z; s.pz1 = hz - s.v0z;
+	return true;
+}
+
+// the remaining predicates for one box of the row (box centre x = cx)
+GPV_HD bool sat_row_test(const SatRow& s, float cx, float hx, float hy, float hz, float t0x, float t1x, float t2x)
+{
+	float v0x = t0x - cx, v1x = t1x - cx, v2x = t2x - cx;
+	{
+		float mn = fminf(v0x, fminf(v1x, v2x)), mx = fmaxf(v0x, fmaxf(v1x, v2x));
+		if (mn > hx || mx < -hx) return false;
+	}
+	float e0x = v1x - v0x, e1x = v2x - v1x;
+	{
+		float ny = s.e0z * e1x - e0x * s.e1z, nz = e0x * s.e1y - s.e0y * e1x;
+		float mnx = (s.nx > 0.0f) ? (-hx - v0x) : (hx - v0x), mxx = (s.nx > 0.0f) ? (hx - v0x) : (-hx - v0x);
+		float mny = (ny > 0.0f) ? s.py0 : s.py1, mxy = (ny > 0.0f) ? s.py1 : s.py0;
+		float mnz = (nz > 0.0f) ? s.pz0 : s.pz1, mxz = (nz > 0.0f) ? s.pz1 : s.pz0;
+		if (s.nx * mnx + ny * mny + nz * mnz > 0.0f) return false;
+		if (!(s.nx * mxx + ny * mxy + nz * mxz >= 0.0f)) return false;
+	}
+	float e2x = v0x - v2x;
+	float fex;
+	// edge 0: Y02, Z12
+	fex = fabsf(e0x);
+	if (axis_separates(-s.e0z * v0x + e0x * s.v0z, -s.e0z * v2x + e0x * s.v2z, fabsf(s.e0z) * hx + fex * hz)) return false;
+	if (axis_separates(s.e0y * v1x - e0x * s.v1y, s.e0y * v2x - e0x * s.v2y, fabsf(s.e0y) * hx + fex * hy)) return false;
+	// edge 1: Y02, Z0
+	fex = fabsf(e1x);
+	if (axis_separates(-s.e1z * v0x + e1x * s.v0z, -s.e1z * v2x + e1x * s.v2z, fabsf(s.e1z) * hx + fex * hz)) return false;
+	if (axis_separates(s.e1y * v0x - e1x * s.v0y, s.e1y * v1x - e1x * s.v1y, fabsf(s.e1y) * hx + fex * hy)) return false;
+	// edge 2: Y1, Z12
+	fex = fabsf(e2x);
+	if (axis_separates(-s.e2z * v0x + e2x * s.v0z, -s.e2z * v1x + e2x * s.v1z, fabsf(s.e2z) * hx + fex * hz)) return false;
+	if (axis_separates(s.e2y * v1x - e2x * s.v1y, s.e2y * v2x - e2x * s.v2y, fabsf(s.e2y) * hx + fex * hy)) return false;
+	return true;
+}
+
+// ---- Moller-Trumbore for the fixed direction D = (0,0,1), split by what each part depends on.
+// Exact for finite intermediates: the dropped terms are products with D's zero components, i.e. additions of +-0.
+struct RayTri { // per triangle
+	float v1x, v1y, v1z, e1x, e1y, e1z, e2x, e2y, e2z, det, inv;
+	bool ok; // false: |det| inside the epsilon band, or not finite -- the ray test can never return 1
+};
+GPV_HD void ray_tri_setup(RayTri& s, float t0x, float t0y, float t0z, float t1x, float t1y, float t1z, float t2x, float t2y, float t2z)
+{
+	s.v1x = t0x; s.v1y = t0y; s.v1z = t0z;
+	s.e1x = t1x - t0x; s.e1y = t1y - t0y; s.e1z = t1z - t0z;
+	s.e2x = t2x - t0x; s.e2y = t2y - t0y; s.e2z = t2z - t0z;
+	s.det = s.e1x * (-s.e2y) + s.e1y * s.e2x; // P = D x e2 = (-e2y, e2x, 0)
+	float ad = fabsf(s.det);
+	s.ok = ad > kEps && ad <= kFltMax;
+	s.inv = 1.f / s.det;
+}
+struct RayCol { float c0, c1, c2; }; // per (triangle, xy origin)
+GPV_HD bool ray_column(const RayTri& s, float ox, float oy, RayCol& c)
+{
+	float Tx = ox - s.v1x, Ty = oy - s.v1y;
+	float u = (Tx * (-s.e2y) + Ty * s.e2x) * s.inv;
+	if (u < 0.f || u > 1.f) return false;
+	float Q2 = Tx * s.e1y - Ty * s.e1x;
+	float v = Q2 * s.inv;
+	if (v < 0.f || u + v > 1.f) return false;
+	c.c0 = Ty * s.e1z; c.c1 = Tx * s.e1z; c.c2 = s.e2z * Q2;
+	return true;
+}
+GPV_HD bool ray_cell(const RayTri& s, const RayCol& c, float oz)
+{
+	float Tz = oz - s.v1z;
+	float Q0 = c.c0 - Tz * s.e1y;
+	float Q1 = Tz * s.e1x - c.c1;
+	float t = (s.e2x * Q0 + s.e2y * Q1 + c.c2) * s.inv;
+	return t > kEps;
+}
+
+// ---- certified candidate columns for the +Z parity fill of one triangle (DESIGN.md "Certified fill").
+// kind 0: no column can be hit; 1: candidates [i0,i1]x[j0,j1]; 2: ill-conditioned -> every column must be tested.
+GPV_HD int fill_candidates(const RayTri& s, float minx, float miny, float gsx, float gsy, int nx, int ny, int& i0, int& i1, int& j0, int& j1)
+{
+	if (!s.ok) return 0;
+	float ax = fabsf(s.e1x), ay = fabsf(s.e1y), bx = fabsf(s.e2x), by = fabsf(s.e2y);
+	float B = fmaxf(fmaxf(ax * by + ay * bx, 2.f * (bx * by)), 2.f * (ax * ay));
+	if (!(fabsf(s.det) >= 1.6e-5f * B)) return 2;
+	float rx = 1.04f * (ax + bx) + 1e-30f, ry = 1.04f * (ay + by) + 1e-30f;
+	float lo = floorf((s.v1x - rx - minx) / gsx) - 1.f, hi = floorf((s.v1x + rx - minx) / gsx) + 1.f;
+	if (!(lo == lo) || !(hi == hi)) return 2;
+	i0 = lo < 0.f ? 0 : (lo > 2e9f ? 2000000000 : (int)lo);
+	i1 = hi > (float)(nx - 1) ? nx - 1 : (int)hi;
+	lo = floorf((s.v1y - ry - miny) / gsy) - 1.f; hi = floorf((s.v1y + ry - miny) / gsy) + 1.f;
+	if (!(lo == lo) || !(hi == hi)) return 2;
+	j0 = lo < 0.f ? 0 : (lo > 2e9f ? 2000000000 : (int)lo);
+	j1 = hi > (float)(ny - 1) ? ny - 1 : (int)hi;
+	return (i0 <= i1 && j0 <= j1) ? 1 : 0;
+}
+
+// ---- vertex -> Level-1 cell index (cu:333-361): int(((v-min)/(max-min))*n), with the max-edge fix-up
+GPV_HD int cell_of(float v, float mn, float mx, int n)
+{
+	int b = (int)((v - mn) / (mx - mn) * (float)n);
+	if (b == n && v == mx) b--;
+	return b;
+}
+
+// ---- reference uchar encodings (src/Object.cpp:2940-2942, :3031-3034)
+GPV_HD unsigned char encode_normal(float n) { return (unsigned char)(n * 85.33333587646484375f + 127.0f); } // float(256.0/3.0)
+
+// VectorNormalize (includes/FloatVector.h:333-342)
+GPV_HD void normalize3(float& x, float& y, float& z)
+{
+	float mag = sqrtf(x * x + y * y + z * z);
+	if (mag != 0) { x /= mag; y /= mag; z /= mag; }
+}
+
+} // namespace gpv

@@ -1,0 +1,162 @@
+/* include/gpview_b200.h -- C ABI of libgpview_b200.so, the B200-native replacement of GPView's hybrid two-level
+ * voxelizer hot path.  Plain pointers and sizes only; no CUDA, torch or C++ types in any signature.
+ *
+ * Two tiers:
+ *   1. COMPATIBILITY TIER -- the reference's own operator boundary, same names, argument meaning and error behaviour:
+ *        CUDAClassifyTessellation / CUDAClassifyTessellationLevel2 / CUDAClassifyInOutLevel2
+ *        (declared includes/CUDAUtilities.h:87-89, defined cuda/CUDAClassifyTessellation.cu:507,518,531)
+ *      plus THRUSTDeviceFindMax (includes/CUDAUtilities.h:70; cuda/THRUSTUtilities.cu:44), the only other device symbol the
+ *      reference's Object.cpp/CUDAUtilities.cpp link against.  The reference's unmodified Object.cpp links against this
+ *      library.
+ *   2. NATIVE TIER -- gpv_*: owns the whole path (Object::PerformVoxelization, src/Object.cpp:3077-3430, minus GL): loaders
+ *      with Object::ReadObject / ReadOFFObject semantics, grid sizing, the six-kernel device pipeline, and the
+ *      Object::SaveVoxelization file contract.
+ *
+ * Error behaviour: native functions return 0 on success, non-zero on failure, message via gpv_last_error() (per thread).
+ * There is NO CPU fallback: every compute entry point fails if no sm_100 device is usable.
+ * Threading: one gpv_ctx per host thread; a ctx is bound to one CUDA device.
+ */
+#ifndef GPVIEW_B200_H
+#define GPVIEW_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ compatibility tier (device pointers, caller-owned) */
+/* layout-identical to CUDA's float3 / int3 (vector_types.h), which is what the reference passes by value */
+typedef struct { float x, y, z; } gpv_float3;
+typedef struct { int x, y, z; } gpv_int3;
+
+/* replaces cuda/CUDAClassifyTessellation.cu:507-515.  inOut[cell]=2.0f on a hit, count[cell]++ (always), triIndex[cell*buf+slot]=t
+ * only while slot < triBufferLen (the reference writes out of bounds, App. B4).  Returns 1 like the reference. */
+int CUDAClassifyTessellation(float* trianglesCUDAData, int numTriangles, float* inOutCUDAData, int* voxelTriCountCUDAData,
+                             int* voxelTriIndexCUDAData, gpv_float3 objBoxMin, gpv_float3 objBoxMax, gpv_float3 boxExtents,
+                             gpv_int3 numDiv, int triBufferLen);
+/* replaces cuda/CUDAClassifyTessellation.cu:518-527 */
+int CUDAClassifyTessellationLevel2(float* trianglesCUDAData, float* level2InOutCUDAData, float* level2NormalCUDAData,
+                                   float* level1MidPointCUDAData, int* level2IndexCUDAData, int* voxelTriCountCUDAData,
+                                   int* level1TriFlatIndexCUDAData, int* level1TriFlatCUDAData, int numBoundary,
+                                   gpv_int3 numDiv2, gpv_float3 boxExtentsLevel1, gpv_float3 boxExtentsLevel2);
+/* replaces cuda/CUDAClassifyTessellation.cu:531-540 */
+int CUDAClassifyInOutLevel2(float* trianglesCUDAData, float* level2InOutCUDAData, float* level1MidPointCUDAData,
+                            int* level2IndexCUDAData, int* level1XYTriCountCUDAData, int* level1XYTriFlatIndexCUDAData,
+                            int* level1XYTriFlatCUDAData, int numBoundary, gpv_int3 numDiv, gpv_int3 numDiv2,
+                            gpv_float3 boxExtentsLevel1, gpv_float3 boxExtentsLevel2);
+/* replaces cuda/THRUSTUtilities.cu:44-61 (hand-written max reduction, no Thrust) */
+float THRUSTDeviceFindMax(float* dataCUDAPointer, int w, int h);
+
+/* ------------------------------------------------------------------ native tier */
+typedef struct gpv_ctx gpv_ctx;
+
+typedef struct {
+	int64_t n_tri;
+	float* tris;               /* n_tri*9 floats: v0xyz v1xyz v2xyz, file face order (Object::CreateFlatTriangleData, src/Object.cpp:3496) */
+	float bbox_min[3], bbox_max[3]; /* padded bounding box (src/Object.cpp:572-583) */
+	float max_model_size;      /* largest padded extent (src/Object.cpp:583) */
+	int64_t n_verts;
+} gpv_mesh;
+
+typedef struct {
+	int num_div[3];            /* Level-1 resolution (src/Object.cpp:3098-3106) */
+	float grid_size[3];        /* Level-1 cell size  (:3107-3109) */
+	float grid_size2[3];       /* Level-2 cell size  (:3128-3130) */
+	float ext1[3], ext2[3];    /* half extents (:2551-2552) */
+	int n2;                    /* Level-2 resolution per boundary cell (GLParameters::voxelCount2) */
+} gpv_grid;
+
+/* flags */
+#define GPV_NORMALS      1     /* also produce Level1Normal / Level2Normal streams */
+#define GPV_NO_LEVEL2    2     /* GLParameters::level2Voxels == false */
+#define GPV_KEEP_LISTS   4     /* keep CSR cell lists / column lists readable after the call (gpv_result list pointers) */
+
+typedef struct {
+	int voxel_count;           /* GLParameters::voxelCount  (Level-1 cells along the longest axis; reference default 8) */
+	int voxel_count2;          /* GLParameters::voxelCount2 (Level-2 cells per boundary cell axis; reference default 4) */
+	int flags;
+	int z0, z1;                /* z-slab [z0,z1) owned by this call; z1 <= 0 means the whole grid */
+} gpv_params;
+
+/* Result of one voxelization.  All d_* pointers are DEVICE memory owned by the ctx, valid until the next call on the ctx.
+ * Streams are in the reference's file layout; for a slab they cover only the slab's cells / boundary cells
+ * (contiguous ranges of the whole-grid streams; prefix sums and Level-2 blocks are slab-local, boundary_index is global). */
+typedef struct {
+	gpv_grid grid;
+	int z0, z1;
+	int64_t cells;             /* (z1-z0)*ny*nx */
+	int64_t n_boundary;        /* boundary cells in the slab */
+	int64_t n23;               /* n2^3 */
+	uint8_t* d_level1_inout;   /* cells bytes: 0 outside / 127 inside / 254 boundary  (ObjNLevel1InOut.raw) */
+	int32_t* d_prefix;         /* cells+1 int32: exclusive boundary prefix sum (ObjNLevel1BoundaryPrefixSum.raw), [cells] = n_boundary */
+	int32_t* d_boundary_index; /* n_boundary int32: global linear index of each boundary cell, ascending */
+	uint8_t* d_level2_inout;   /* n_boundary*n23 bytes (ObjNLevel2InOut.raw) */
+	uint8_t* d_level1_normal;  /* cells*3 bytes or NULL */
+	uint8_t* d_level2_normal;  /* n_boundary*n23*3 bytes or NULL */
+	/* CSR lists (GPV_KEEP_LISTS): ascending triangle ids */
+	uint32_t* d_cell_off;      /* n_boundary+1, indexed by slab-local boundary rank */
+	int32_t* d_cell_tris;
+	uint32_t* d_col_off;       /* nx*ny+1 (slack between columns: use d_col_count) */
+	int32_t* d_col_count;      /* nx*ny */
+	int32_t* d_col_tris;
+	/* counts (src/Object.cpp:3353-3378) */
+	int64_t l1_inside, l1_boundary, l2_inside, l2_boundary;
+	/* reference-equivalent work */
+	int64_t l1_box_tests, l1_box_hits, l2_box_tests, l2_ray_tests, tri_total, fill_crossings, fill_ill_conditioned;
+	int64_t kernel_launches;   /* kernels launched by this call */
+} gpv_result;
+
+/* host copies of the streams (caller-allocated; any pointer may be NULL to skip that stream) */
+typedef struct {
+	uint8_t* level1_inout; int32_t* prefix; int32_t* boundary_index; uint8_t* level2_inout;
+	uint8_t* level1_normal; uint8_t* level2_normal;
+	int64_t level2_capacity;   /* bytes available behind level2_inout (level2_normal must hold 3x) */
+	int64_t boundary_capacity; /* entries available behind boundary_index */
+} gpv_host_streams;
+
+const char* gpv_last_error(void);
+int gpv_device_count(void);
+
+/* context: device buffers are pooled (grow-only) inside the ctx */
+int gpv_create(int device, gpv_ctx** out);
+void gpv_destroy(gpv_ctx* ctx);
+
+/* loaders with the reference's semantics (Object::ReadObject src/Object.cpp:395-584, Object::ReadOFFObject :171-317);
+ * gpv_load_mesh dispatches on the last three characters like main() (src/GPView.cpp:1642-1659) */
+int gpv_load_obj(const char* path, gpv_mesh* out);
+int gpv_load_off(const char* path, gpv_mesh* out);
+int gpv_load_mesh(const char* path, gpv_mesh* out);
+int gpv_mesh_from_triangles(const float* tris, int64_t n_tri, gpv_mesh* out); /* bbox over the given vertices + padding */
+void gpv_free_mesh(gpv_mesh* m);
+
+/* grid sizing of Object::PerformVoxelization (src/Object.cpp:3094-3134) */
+int gpv_make_grid(const float bbox_min[3], const float bbox_max[3], float max_model_size, int voxel_count, int voxel_count2, gpv_grid* out);
+
+/* pinned host memory for the callers' staging buffers */
+void* gpv_alloc_host(int64_t bytes);
+void gpv_free_host(void* p);
+void* gpv_alloc_device(int64_t bytes);
+void gpv_free_device(void* p);
+int gpv_memcpy_h2d(void* dst, const void* src, int64_t bytes, void* stream);
+int gpv_memcpy_d2h(void* dst, const void* src, int64_t bytes, void* stream);
+int gpv_stream_sync(void* stream);
+
+/* the hot path.  d_tris: DEVICE pointer to n_tri*9 floats.  stream: a cudaStream_t (NULL = default stream).
+ * Asynchronous except for one internal size read-back; counts in `out` are final on return (the call ends with a stream sync). */
+int gpv_voxelize_device(gpv_ctx* ctx, const float* d_tris, int64_t n_tri, const float bbox_min[3], const float bbox_max[3],
+                        float max_model_size, const gpv_params* params, void* stream, gpv_result* out);
+/* same, from HOST triangles into HOST streams: H2D + pipeline + D2H (the reference-facing call: what
+ * Object::PerformVoxelization does between CreateFlatTriangleData and SaveVoxelization) */
+int gpv_voxelize_host(gpv_ctx* ctx, const gpv_mesh* mesh, const gpv_params* params, void* stream, gpv_result* out, gpv_host_streams* host);
+
+/* Object::SaveVoxelization (src/Object.cpp:2934-3075): the six ObjN*.{txt,raw} files into `dir` from host streams */
+int gpv_save(const gpv_mesh* mesh, const gpv_result* res, const gpv_host_streams* host, int obj_id, const char* dir);
+
+/* micro-benchmarks used for the roofline denominators (bench.py): achieved non-FMA FP32 lane-ops/s and copy GB/s */
+int gpv_measure_fp32_peak(gpv_ctx* ctx, void* stream, double* ops_per_s);
+int gpv_measure_copy_peak(gpv_ctx* ctx, void* stream, double* gb_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

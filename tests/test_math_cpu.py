@@ -1,0 +1,163 @@
+"""The product's intersection arithmetic (gpview_b200/csrc/gpv_math.h, compiled for the host by tests/cpu_probe) must
+agree bit-for-bit with the oracle -- and, in the build container, with the reference's own object code -- on random and
+adversarial inputs: touching, degenerate, axis-aligned, coplanar, sliver and far-away triangles."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import HAVE_REF, ROOT
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def probe():
+    so = os.path.join(HERE, "cpu_probe", "math_probe.so")
+    src = os.path.join(HERE, "cpu_probe", "math_probe.cpp")
+    hdr = os.path.join(ROOT, "gpview_b200", "csrc", "gpv_math.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", so, src])
+    L = C.CDLL(so)
+    fp, bp = C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+    for n in ("probe_sat_full", "probe_sat_row"):
+        getattr(L, n).argtypes = [C.c_int64, fp, fp, fp, bp]
+    L.probe_ray.argtypes = [C.c_int64, fp, fp, bp]
+    L.probe_column.argtypes = [C.c_int64, fp, fp, bp]
+    L.probe_candidates.argtypes = [C.c_int64, fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    L.probe_cell_of.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
+    L.probe_encode_normal.argtypes = [C.c_float]
+    return L
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _bp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def sat_cases(rng, n):
+    """boxes + triangles with many near-boundary situations"""
+    c = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    h = rng.uniform(0.05, 0.6, (n, 3)).astype(np.float32)
+    t = (c[:, None, :] + rng.normal(0, 0.7, (n, 3, 3)) * rng.uniform(0.1, 2.0, (n, 1, 1))).astype(np.float32)
+    k = n // 8
+    # vertices exactly on box faces / corners
+    t[:k, 0, :] = c[:k] + h[:k] * rng.choice([-1, 1], (k, 3))
+    # axis-aligned triangles lying in a face plane of the box
+    t[k:2 * k, :, 0] = (c[k:2 * k, 0] + h[k:2 * k, 0])[:, None]
+    # degenerate: two equal vertices, or all collinear
+    t[2 * k:3 * k, 1] = t[2 * k:3 * k, 0]
+    t[3 * k:4 * k, 2] = (t[3 * k:4 * k, 0] + (t[3 * k:4 * k, 1] - t[3 * k:4 * k, 0]) * np.float32(2.0)).astype(np.float32)
+    # big triangles swallowing the box, tiny triangles inside the box
+    t[4 * k:5 * k] = (c[4 * k:5 * k, None, :] + rng.normal(0, 20, (k, 3, 3))).astype(np.float32)
+    t[5 * k:6 * k] = (c[5 * k:6 * k, None, :] + rng.normal(0, 0.01, (k, 3, 3))).astype(np.float32)
+    return c, h, t.reshape(n, 9)
+
+
+def test_sat_matches_oracle(probe, oracle):
+    rng = np.random.default_rng(1)
+    n = 400000
+    c, h, t = sat_cases(rng, n)
+    want = oracle.tribox_batch(c, h, t)
+    full = np.zeros(n, np.uint8); row = np.zeros(n, np.uint8)
+    probe.probe_sat_full(n, _fp(c), _fp(h), _fp(t), _bp(full))
+    probe.probe_sat_row(n, _fp(c), _fp(h), _fp(t), _bp(row))
+    assert 0.05 < want.mean() < 0.95
+    assert np.array_equal(full, want)
+    assert np.array_equal(row, want)
+
+
+def ray_cases(rng, n):
+    o = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    t = rng.uniform(-2.5, 2.5, (n, 3, 3)).astype(np.float32)
+    k = n // 8
+    # origin exactly under a vertex / an edge midpoint (inclusive-edge semantics, App. A.5)
+    o[:k, :2] = t[:k, 0, :2]
+    o[k:2 * k, :2] = ((t[k:2 * k, 0, :2] + t[k:2 * k, 1, :2]) * np.float32(0.5)).astype(np.float32)
+    # vertical and near-vertical triangles (det ~ 0), huge coordinates (noise-level determinants)
+    t[2 * k:3 * k, 2, :2] = t[2 * k:3 * k, 0, :2]
+    t[3 * k:4 * k] = (t[3 * k:4 * k] * np.float32(1000)).astype(np.float32)
+    o[3 * k:4 * k] = (o[3 * k:4 * k] * np.float32(1000)).astype(np.float32)
+    # slivers: third vertex almost on the line through the first two
+    a = rng.uniform(0, 1, (k, 1)).astype(np.float32)
+    t[4 * k:5 * k, 2] = (t[4 * k:5 * k, 0] + (t[4 * k:5 * k, 1] - t[4 * k:5 * k, 0]) * a + rng.normal(0, 1e-6, (k, 3))).astype(np.float32)
+    # origin on the triangle's plane (t ~ 0)
+    o[5 * k:6 * k] = ((t[5 * k:6 * k, 0] + t[5 * k:6 * k, 1] + t[5 * k:6 * k, 2]) / np.float32(3)).astype(np.float32)
+    return o, t.reshape(n, 9)
+
+
+def test_ray_split_matches_general_form(probe, oracle):
+    rng = np.random.default_rng(2)
+    n = 400000
+    o, t = ray_cases(rng, n)
+    want = oracle.triray_batch(o, t)
+    got = np.zeros(n, np.uint8)
+    probe.probe_ray(n, _fp(o), _fp(t), _bp(got))
+    assert 0.01 < want.mean() < 0.6
+    assert np.array_equal(got, want)
+    assert np.array_equal(oracle.triray_batch(o, t, specialised=True), want)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference object code only exists in the build container")
+def test_oracle_predicates_match_reference_object_code(oracle):
+    from oracle import refbind
+    rng = np.random.default_rng(3)
+    n = 200000
+    c, h, t = sat_cases(rng, n)
+    assert np.array_equal(oracle.tribox_batch(c, h, t), refbind.tribox_batch(c, h, t))
+    o, t2 = ray_cases(rng, n)
+    assert np.array_equal(oracle.triray_batch(o, t2), refbind.triray_batch(o, t2))
+
+
+def test_certified_candidates_cover_brute_force(probe):
+    """For every triangle, every grid column whose +Z ray passes the column part of Moller-Trumbore must lie inside the
+    candidate rectangle (or the triangle is flagged ill-conditioned = test every column)."""
+    rng = np.random.default_rng(4)
+    nx = ny = 48
+    gs = np.float32(0.125)
+    mn = np.float32(-3.0)
+    cx = (mn + (np.arange(nx) + 0.5) * gs).astype(np.float32)
+    n = 3000
+    t = rng.uniform(-3, 3, (n, 3, 3)).astype(np.float32)
+    k = n // 6
+    a = rng.uniform(-1, 2, (k, 1)).astype(np.float32)
+    t[:k, 2] = (t[:k, 0] + (t[:k, 1] - t[:k, 0]) * a + rng.normal(0, 3e-6, (k, 3))).astype(np.float32)          # slivers
+    t[k:2 * k] = (t[k:2 * k] * np.float32(300)).astype(np.float32)                                              # large coordinates
+    t[2 * k:3 * k, 2, :2] = (t[2 * k:3 * k, 0, :2] + rng.normal(0, 1e-5, (k, 2))).astype(np.float32)            # near-vertical
+    t[3 * k:4 * k] = (t[3 * k:4 * k, :1] + rng.normal(0, 0.05, (k, 3, 3))).astype(np.float32)                   # small
+    t = t.reshape(n, 9)
+    cand = np.zeros((n, 5), np.int32)
+    probe.probe_candidates(n, _fp(t), mn, mn, gs, gs, nx, ny, cand.ctypes.data_as(C.POINTER(C.c_int32)))
+    jj, ii = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    oxy = np.stack([cx[ii.reshape(-1)], cx[jj.reshape(-1)]], -1).astype(np.float32)
+    kinds = np.bincount(cand[:, 0], minlength=3)
+    assert kinds[1] > n // 2 and kinds[2] > 0
+    for q in range(n):
+        tt = np.repeat(t[q:q + 1], nx * ny, 0)
+        hit = np.zeros(nx * ny, np.uint8)
+        probe.probe_column(nx * ny, _fp(oxy), _fp(np.ascontiguousarray(tt)), _bp(hit))
+        hit = hit.reshape(ny, nx).astype(bool)
+        kind, i0, i1, j0, j1 = cand[q]
+        if kind == 2:
+            continue
+        if kind == 0:
+            assert not hit.any(), q
+            continue
+        outside = np.ones((ny, nx), bool)
+        outside[j0:j1 + 1, i0:i1 + 1] = False
+        assert not (hit & outside).any(), (q, cand[q], np.argwhere(hit & outside)[:4])
+
+
+def test_cell_of_and_normal_encoding(probe):
+    assert probe.probe_cell_of(C.c_float(1.0), C.c_float(0.0), C.c_float(1.0), 8) == 7      # max-edge fix-up (cu:336)
+    assert probe.probe_cell_of(C.c_float(0.0), C.c_float(0.0), C.c_float(1.0), 8) == 0
+    assert probe.probe_cell_of(C.c_float(0.5), C.c_float(0.0), C.c_float(1.0), 8) == 4
+    for x in np.linspace(-1, 1, 101).astype(np.float32):
+        want = int(np.uint8(np.float32(np.float32(x * np.float32(256.0 / 3.0)) + np.float32(127.0))))
+        assert probe.probe_encode_normal(C.c_float(float(x))) == want
