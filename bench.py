@@ -1,0 +1,406 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the voxelizer hot path (BASELINE.json: cessna Level-1 256 + Level-2 16^3).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--l1 256 --l2 16 --mesh cessna|sphere|torus|cad]
+
+One "step" = one full voxelization of the model (Level-1 SAT binning, parity fill, boundary compaction, Level-2
+refinement), triangles resident in HBM when the timed region starts, outputs resident in HBM when it ends.
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (k_l2): algorithmic tri-box FLOPs (124 per reference-equivalent test) over
+                its CUDA-event time, against the non-FMA FP32 issue rate measured live by gpv_measure_fp32_peak
+  roofline_hbm  the same launch's output bytes against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own TriBoxOverlap object code (oracle/_ref) -- or the oracle port when _ref is absent --
+                inside the Level-2 loop nest on a bounded sample of boundary cells, all host threads
+  e2e           the same metric through gpv_voxelize_host: pinned HOST triangles in, HOST streams out, copies timed
+N > 1 (torchrun): the grid is cut into z-slabs balanced by boundary-cell count, one rank per GPU; the Level-1 passes are
+replicated (cheap), Level-2 is sharded, slab pieces are gathered on rank 0 over NCCL inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FLOPS_PER_TRIBOX = 124  # 66 MUL + 58 ADD/SUB, SURVEY.md 8(a8)
+
+
+def make_mesh_file(name, tmp):
+    from gpview_b200 import meshgen
+    p = os.path.join(tmp, name + ".obj")
+    if name == "cessna":
+        z = np.load(os.path.join(ROOT, "tests", "golden", "cessna_mesh.npz"))
+        meshgen.write_obj(p, z["V"], z["F"])
+    elif name == "sphere":
+        meshgen.write_obj(p, *meshgen.uv_sphere(1000, 502))
+    elif name == "torus":
+        meshgen.write_obj(p, *meshgen.torus(1000, 500))
+    elif name == "cad":
+        meshgen.write_obj(p, *meshgen.cad_body(2500, 2001))
+    else:
+        raise SystemExit("unknown mesh " + name)
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.p = gpu, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs"), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per k_l2 launch from the committed ncu --set full summary (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
+def cpu_baseline(mesh_path, l1, l2, threads, target_seconds=12.0):
+    """Time the reference's TriBoxOverlap (oracle/_ref, kind 'reference') in the Level-2 loop nest of
+    cuda/CUDAClassifyTessellation.cu:428-445 on a bounded sample of boundary cells; falls back to the oracle port."""
+    try:
+        from oracle import refbind
+        if not refbind.available():
+            raise RuntimeError("no _ref")
+        o = refbind.RefObject(mesh_path)
+        o.setup(l1, l2)
+        o.l1_tribox()
+        o.compact()
+        nb = o.nboundary()
+        s, n = o.time_l2_tribox(0, min(nb, 256), threads)  # calibrate
+        per_cell = s / max(1, min(nb, 256))
+        cells = int(max(256, min(nb, target_seconds / max(per_cell, 1e-9))))
+        s, n = o.time_l2_tribox(0, cells, threads)
+        o.close()
+        kind = "reference"
+    except Exception:
+        from oracle import oraclebind as O
+        m = O.OracleMesh(mesh_path)
+        r = m.voxelize(l1, l2, O.FILL_COLLIST | O.NO_L2 | O.NO_NORMALS, threads)
+        nb = r.nb
+        s, n = r.time_l2_tribox(0, min(nb, 256), threads)
+        per_cell = s / max(1, min(nb, 256))
+        cells = int(max(256, min(nb, target_seconds / max(per_cell, 1e-9))))
+        s, n = r.time_l2_tribox(0, cells, threads)
+        kind = "port"
+    return {"value": n / s / 1e9, "unit": "G tri-box tests/s", "cores": threads, "kind": kind,
+            "sample": "Level-2 SAT loop nest over the first %d of %d boundary cells (%d tests, %.2f s)" % (cells, nb, n, s)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU TriBoxOverlap path on this box's host cores (all threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(prefix="gpvbench")
+    path = make_mesh_file(args.mesh, tmp)
+    from oracle import refbind
+    kind = "reference" if refbind.available() else "port"
+    if kind == "reference":
+        o = refbind.RefObject(path)
+        o.setup(args.l1, args.l2)
+        o.l1_tribox()
+        o.compact()
+        nb = o.nboundary()
+        timer = lambda c: o.time_l2_tribox(0, c, threads)
+    else:
+        from oracle import oraclebind as O
+        r = O.OracleMesh(path).voxelize(args.l1, args.l2, O.FILL_COLLIST | O.NO_L2 | O.NO_NORMALS, threads)
+        nb = r.nb
+        timer = lambda c: r.time_l2_tribox(0, c, threads)
+    s, n = timer(min(nb, 256))
+    cells = int(max(256, min(nb, 1.0 / max(s / max(1, min(nb, 256)), 1e-9))))  # ~1 s per step
+    for _ in range(args.warmup):
+        timer(cells)
+    tot_s, tot_n = 0.0, 0
+    for _ in range(args.steps):
+        s, n = timer(cells)
+        tot_s += s; tot_n += n
+    v = tot_n / tot_s / 1e9
+    sample = "Level-2 SAT loop nest (cuda/CUDAClassifyTessellation.cu:428-445) over %d of %d boundary cells per step" % (cells, nb)
+    print(json.dumps({"impl": "reference", "metric": "G tri-box tests/s", "value": v, "unit": "G tri-box tests/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
+                      "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if args.mesh != "cessna" else "cessna.obj fixture",
+                      "config": workload_config(args), "cpu_baseline": {"value": v, "unit": "G tri-box tests/s", "cores": threads, "kind": kind, "sample": sample},
+                      "e2e": {"value": v, "unit": "G tri-box tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def workload_config(args):
+    return {"workload": "%s Level1 %d + Level2 %d^3 (BASELINE.json configs[1] when cessna/256/16), .raw streams, occupancy only"
+                        % (args.mesh, args.l1, args.l2), "l1": args.l1, "l2": args.l2, "mesh": args.mesh,
+            "cache": "L2 flushed between timed steps (256 MiB memset); outputs (>=221 MB at 256/16) exceed L2"}
+
+
+def slab_cuts(per_layer_cost, R):
+    """cut z into R contiguous slabs of ~equal cost (deterministic; every rank computes the same cuts)"""
+    c = np.concatenate([[0], np.cumsum(per_layer_cost.astype(np.float64))])
+    nz = len(per_layer_cost)
+    cuts = [0]
+    for r in range(1, R):
+        z = int(np.searchsorted(c, c[-1] * r / R))
+        z = min(max(z, cuts[-1] + 1), nz - (R - r))
+        cuts.append(z)
+    cuts.append(nz)
+    return cuts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mesh", default="cessna")
+    ap.add_argument("--l1", type=int, default=256)
+    ap.add_argument("--l2", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import gpview_b200 as gpv
+    from gpview_b200 import binding as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- libgpview_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tmp = tempfile.mkdtemp(prefix="gpvbench")
+    path = make_mesh_file(args.mesh, tmp)
+    mesh = gpv.load_mesh(path)
+    ctx = gpv.Context(local)
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+    d_tris = ctx.upload(mesh)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    # ---- z-slab plan (N > 1): replicated Level-1 pre-pass gives per-layer Level-2 cost; cuts are deterministic
+    z0, z1 = 0, 0
+    whole = ctx.voxelize_device(d_tris, mesh, gpv.Params(args.l1, args.l2, gpv.GPV_NO_LEVEL2), sptr)
+    nz = int(whole.num_div[2]); plane = int(whole.num_div[0]) * int(whole.num_div[1])
+    total_tests = None
+    if world > 1:
+        bi = whole.boundary_index()
+        off = whole.cell_off().astype(np.int64)
+        cost = np.bincount(bi // plane, weights=(off[1:] - off[:-1]) + 8.0, minlength=nz)
+        cuts = slab_cuts(cost, world)
+        z0, z1 = cuts[rank], cuts[rank + 1]
+    params = gpv.Params(args.l1, args.l2, gpv.GPV_PROFILE, z0, z1)  # CUDA events around every kernel, on the launching stream
+    phase_acc = {}
+
+    def wrap(ptr, nbytes):
+        class P:
+            pass
+        p = P()
+        p.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(p, device="cuda")
+
+    gathered = {}
+
+    def gather(res):
+        """slab pieces -> rank 0 (concatenation only): sizes by all_gather, payload by batched send/recv"""
+        sizes = torch.tensor([res.cells, res.nb], device="cuda", dtype=torch.int64)
+        allsz = [torch.empty_like(sizes) for _ in range(world)]
+        dist.all_gather(allsz, sizes)
+        allsz = torch.stack(allsz).cpu().numpy()
+        n23 = res.n23
+        streams = [("l1", res.c.d_level1_inout, 1, 0), ("pre", res.c.d_prefix, 4, 0), ("l2", res.c.d_level2_inout, n23, 1)]
+        ops = []
+        for name, ptr, unit, which in streams:
+            mine = wrap(ptr, int(allsz[rank][which]) * unit) if int(allsz[rank][which]) else torch.empty(0, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                tot = int(allsz[:, which].sum()) * unit
+                if name not in gathered or gathered[name].numel() < tot:
+                    gathered[name] = torch.empty(tot, dtype=torch.uint8, device="cuda")
+                o = 0
+                for r in range(world):
+                    nby = int(allsz[r][which]) * unit
+                    if r == 0:
+                        gathered[name][o:o + nby].copy_(mine, non_blocking=True)
+                    elif nby:
+                        ops.append(dist.P2POp(dist.irecv, gathered[name][o:o + nby], r))
+                    o += nby
+            elif mine.numel():
+                ops.append(dist.P2POp(dist.isend, mine, 0))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if rank == 0:  # slab-local prefix sums -> global: add the boundary counts of the lower slabs
+            o = 0; base = 0
+            pre = gathered["pre"].view(torch.int32)
+            for r in range(world):
+                ncell = int(allsz[r][0])
+                if base:
+                    pre[o:o + ncell] += base
+                o += ncell; base += int(allsz[r][1])
+
+    def step():
+        res = ctx.voxelize_device(d_tris, mesh, params, sptr)
+        if world > 1:
+            gather(res)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)
+        barrier()
+        ev[k][0].record(stream)
+        res = step()
+        ev[k][1].record(stream)
+        launches += res.stats["kernel_launches"]
+        for ph, v in res.phase_ms.items():
+            phase_acc[ph] = phase_acc.get(ph, 0.0) + v
+    barrier()
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device="cuda", dtype=torch.float64)
+    tests_local = torch.tensor([res.stats["l2_box_tests"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tests_local)
+    total_ms = float(ms.item())
+    tests = float(tests_local.item()) + res.stats["l1_box_tests"]  # Level-1 tests are replicated: counted once
+    ms_per_step = total_ms / args.steps
+    value = tests / (ms_per_step * 1e-3) / 1e9
+
+    # ---- dominant kernel timed alone (its own CUDA events, L2 flushed): Level-2 refinement
+    roof = roof_hbm = None
+    e2e = None
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and world == 1:
+        kt = {"k_l2_ms": phase_acc["l2"] / args.steps}
+        fp32_peak = ctx.fp32_peak()
+        hbm_peak, hbm_src = measured_peaks()
+        traffic = ncu_traffic()
+        flops = FLOPS_PER_TRIBOX * res.stats["l2_box_tests"]
+        ach = flops / (kt["k_l2_ms"] * 1e-3) / 1e12
+        roof = {"kernel": "k_l2 (Level-2 refinement: parity rays + hoisted SAT)", "bound": "fp32", "achieved": ach, "peak": fp32_peak / 1e12,
+                "unit": "TFLOP/s", "frac": ach / (fp32_peak / 1e12), "traffic": traffic.get("k_l2_dram_bytes"),
+                "peak_source": "non-FMA FP32 issue rate measured live (gpv_measure_fp32_peak: independent FMUL/FADD chains); "
+                               "MEASURED_PEAKS.json has no FP32 entry",
+                "algorithmic": "%d reference-equivalent tri-box tests x 124 FLOP; the kernel hoists the x-independent part of each test "
+                               "per sub-voxel row and exits early, so frac can exceed what executed-instruction counts suggest" % res.stats["l2_box_tests"],
+                "kernel_ms": kt["k_l2_ms"], "share_of_step": kt["k_l2_ms"] / ms_per_step}
+        out_bytes = res.nb * res.n23
+        roof_hbm = {"kernel": "k_l2", "bound": "hbm", "achieved": out_bytes / (kt["k_l2_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": out_bytes / (kt["k_l2_ms"] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("k_l2_dram_bytes"), "peak_source": hbm_src,
+                    "algorithmic": "1 B per Level-2 voxel written (%d B)" % out_bytes}
+        # ---- e2e: pinned host triangles in, host streams out, through gpv_voxelize_host
+        L = gpv.lib()
+        cells, nb, n23 = res.cells, res.nb, res.n23
+        hb = {k: L.gpv_alloc_host(n) for k, n in (("l1", cells), ("pre", cells * 4), ("bi", nb * 4 + 64), ("l2", nb * n23 + 64))}
+        pinned_tris = L.gpv_alloc_host(mesh.ntri * 36)
+        C.memmove(pinned_tris, C.cast(mesh.c.tris, C.c_void_p), mesh.ntri * 36)
+        pm = B.CMesh(mesh.c.n_tri, C.cast(pinned_tris, C.POINTER(C.c_float)), mesh.c.bbox_min, mesh.c.bbox_max, mesh.c.max_model_size, mesh.c.n_verts)
+        hs = B.CHostStreams(hb["l1"], hb["pre"], hb["bi"], hb["l2"], None, None, nb * n23 + 64, nb + 16)
+        r2 = B.CResult()
+        def e2e_step():
+            rc = L.gpv_voxelize_host(ctx.h, C.byref(pm), C.byref(params.c), sptr, C.byref(r2), C.byref(hs))
+            if rc:
+                raise SystemExit(L.gpv_last_error().decode())
+        for _ in range(args.warmup):
+            e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = 0.0
+        for k in range(args.steps):
+            flush.fill_(k & 0xff)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_step()  # returns after the last D2H has landed (stream sync inside)
+            t_e2e += time.perf_counter() - t0
+        e2e_ms = 1e3 * t_e2e / args.steps
+        got = np.ctypeslib.as_array(C.cast(hb["l2"], C.POINTER(C.c_uint8)), shape=(nb * n23,))
+        assert int((got == 254).sum()) == res.counts[3], "e2e host stream does not match the device counts"
+        e2e = {"value": tests / (e2e_ms * 1e-3) / 1e9, "unit": "G tri-box tests/s", "ms_per_model": e2e_ms,
+               "h2d_bytes_per_step": mesh.ntri * 36, "d2h_bytes_per_step": int(cells + cells * 4 + nb * 4 + nb * n23),
+               "timing": "host wall clock around gpv_voxelize_host (pinned buffers both ways; the call ends with a stream sync)"}
+        for p in hb.values():
+            L.gpv_free_host(p)
+        L.gpv_free_host(pinned_tris)
+
+    if rank == 0:
+        line = {"metric": "G tri-box tests/s", "value": value, "unit": "G tri-box tests/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "ms_per_model": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "cessna.obj fixture (reference sample mesh)" if args.mesh == "cessna" else "synthetic",
+                "config": dict(workload_config(args), parallelism="z-slabs x%d, Level-1 replicated, NCCL gather to rank 0" % world if world > 1 else "1 GPU",
+                               tri_box_tests_per_model=int(tests), triangles=mesh.ntri, grid=[int(x) for x in res.num_div]),
+                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_hbm": roof_hbm,
+                "phase_ms": {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0},
+                "counts": {"l1_inside": whole.counts[0], "l1_boundary": whole.counts[1]}}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(path, args.l1, args.l2, os.cpu_count() or 1)
+        print(json.dumps(line))
+    ctx.free_device(d_tris)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

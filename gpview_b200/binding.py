@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgpview_b200.so")
 
-GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS = 1, 2, 4
+GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE = 1, 2, 4, 8
 
 
 class GpvError(RuntimeError):
@@ -35,7 +35,10 @@ class CResult(C.Structure):
                 ("d_level1_normal", C.c_void_p), ("d_level2_normal", C.c_void_p), ("d_cell_off", C.c_void_p), ("d_cell_tris", C.c_void_p),
                 ("d_col_off", C.c_void_p), ("d_col_count", C.c_void_p), ("d_col_tris", C.c_void_p)] + [(k, C.c_int64) for k in (
                     "l1_inside", "l1_boundary", "l2_inside", "l2_boundary", "l1_box_tests", "l1_box_hits", "l2_box_tests", "l2_ray_tests",
-                    "tri_total", "fill_crossings", "fill_ill_conditioned", "kernel_launches")]
+                    "tri_total", "fill_crossings", "fill_ill_conditioned", "kernel_launches")] + [("phase_ms", C.c_float * 16)]
+
+
+PHASES = ["setup", "bin_count", "cross_count", "scan", "host_gap", "bin_fill", "cross_fill", "sort", "fill_sweep", "l1_normals", "l2", "l2_normals"]
 
 
 class CHostStreams(C.Structure):
@@ -168,6 +171,7 @@ class Result:
         self.counts = [int(cres.l1_inside), int(cres.l1_boundary), int(cres.l2_inside), int(cres.l2_boundary)]
         self.stats = {k: int(getattr(cres, k)) for k in ("l1_box_tests", "l1_box_hits", "l2_box_tests", "tri_total", "fill_crossings",
                                                          "fill_ill_conditioned", "kernel_launches")}
+        self.phase_ms = dict(zip(PHASES, [float(x) for x in cres.phase_ms]))
 
     def _d2h(self, ptr, n, dtype):
         out = np.empty(int(n), dtype)

@@ -60,6 +60,8 @@ struct gpv_ctx {
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
 	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch;
 	gpv::Totals* hTotals = nullptr; // pinned
+	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {};
+	bool haveEvents = false;
 };
 
 using namespace gpv;
@@ -103,6 +105,7 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch };
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
+	if (c->haveEvents) for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
 	delete c;
 }
 
@@ -178,6 +181,14 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	if (ncol * g.nz > 0x7fffffffLL) return fail("grid exceeds 2^31 cells: boundary_index is int32 (file contract); shard finer");
 	const int nTri = (int)n_tri;
 	int64_t launches = 0;
+	const bool prof = (prm->flags & GPV_PROFILE) != 0;
+	if (prof && !c->haveEvents) {
+		for (cudaEvent_t& e : c->ev) GPV_CUDA(cudaEventCreate(&e));
+		c->haveEvents = true;
+	}
+	// phase boundaries: ev[k] is recorded when phase k starts, ev[GPV_PHASE_COUNT] when the last one ends
+	bool marked[GPV_PHASE_COUNT + 1] = {};
+	auto mark = [&](int phase) { if (prof) { cudaEventRecord(c->ev[phase], st); marked[phase] = true; } };
 
 	// ---- fixed-size buffers
 	if (c->tri48.ensure((size_t)nTri * 48) || c->ray48.ensure((size_t)nTri * 48) || c->tabX.ensure((size_t)g.nx * 4) || c->tabY.ensure((size_t)g.ny * 4) ||
@@ -187,6 +198,7 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	    c->crossOff.ensure((size_t)(ncol + 1) * 4 + 32) || c->l1State.ensure((size_t)cells + 32))
 		return 1;
 	Totals* dT = c->totals.as<Totals>();
+	mark(GPV_PHASE_SETUP);
 	GPV_CUDA(cudaMemsetAsync(dT, 0, sizeof(Totals), st));
 	GPV_CUDA(cudaMemsetAsync(c->cellCount.p, 0, (size_t)cells * 4, st));
 	GPV_CUDA(cudaMemsetAsync(c->colCount.p, 0, (size_t)ncol * 4, st));
@@ -203,9 +215,12 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	const int binBlocks = (nTri + kBinThreads - 1) / kBinThreads;
 	BinOut bo{};
 	bo.cellCount = c->cellCount.as<int>(); bo.colCount = c->colCount.as<int>(); bo.totals = dT;
+	mark(GPV_PHASE_BIN_COUNT);
 	k_bin<false><<<binBlocks, kBinThreads, 0, st>>>(tri48, nTri, g, cx, cy, cz, bo);
+	mark(GPV_PHASE_CROSS_COUNT);
 	k_cross<false><<<binBlocks, kBinThreads, 0, st>>>(ray48, nTri, g, cx, cy, c->crossCount.as<int>(), nullptr, nullptr, dT);
 	launches += 2;
+	mark(GPV_PHASE_SCAN);
 	{ // K3 boundary compaction
 		long long tiles = (cells + kScanTile - 1) / kScanTile;
 		if (c->desc.ensure((size_t)(tiles + 1) * 8 + 16)) return 1;
@@ -222,6 +237,7 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	if (run_scan_offsets(c, st, c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, launches)) return 1;
 
 	// ---- the one size read-back
+	mark(GPV_PHASE_HOST_GAP);
 	GPV_CUDA(cudaMemcpyAsync(c->hTotals, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
 	GPV_CUDA(cudaStreamSynchronize(st));
 	GPV_CUDA(cudaGetLastError());
@@ -236,21 +252,26 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 
 	bo.prefix = c->prefix.as<int>(); bo.bTriOff = c->bTriOff.as<unsigned>(); bo.cellTris = c->cellTris.as<int>();
 	bo.colOff = c->colOff.as<unsigned>(); bo.colTris = c->colTris.as<int>();
+	mark(GPV_PHASE_BIN_FILL);
 	k_bin<true><<<binBlocks, kBinThreads, 0, st>>>(tri48, nTri, g, cx, cy, cz, bo);
+	mark(GPV_PHASE_CROSS_FILL);
 	k_cross<true><<<binBlocks, kBinThreads, 0, st>>>(ray48, nTri, g, cx, cy, c->crossCount.as<int>(), c->crossOff.as<unsigned>(), c->crossTri.as<int>(), dT);
 	launches += 2;
+	mark(GPV_PHASE_SORT);
 	if (nB > 0) {
 		k_sort_segments<false><<<(unsigned)((nB * 32 + 255) / 256), 256, 0, st>>>(c->bTriOff.as<unsigned>(), (int)nB, c->cellTris.as<int>(), nullptr);
 		launches++;
 	}
 	k_sort_segments<true><<<(unsigned)((ncol * 32 + 255) / 256), 256, 0, st>>>(c->colOff.as<unsigned>(), (int)ncol, c->colTris.as<int>(), c->colCount.as<int>());
 	launches++;
+	mark(GPV_PHASE_FILL_SWEEP);
 	{
 		dim3 grid((g.nx + 31) / 32, g.ny, (g.z1 - g.z0 + 127) / 128), block(32, 4);
 		k_fill_sweep<<<grid, block, 0, st>>>(ray48, g, cx, cy, cz, c->crossOff.as<unsigned>(), c->crossTri.as<int>(), c->bmask.as<unsigned char>(),
 		                                     c->l1State.as<unsigned char>(), dT);
 		launches++;
 	}
+	mark(GPV_PHASE_L1_NORMALS);
 	if (wantN) {
 		GPV_CUDA(cudaMemsetAsync(c->l1Normal.p, 127, (size_t)cells * 3, st));
 		if (nB > 0) {
@@ -260,6 +281,7 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 		}
 	}
 	L2IO lio{};
+	mark(GPV_PHASE_L2);
 	if (wantL2 && nB > 0) {
 		lio.tri48 = tri48; lio.ray48 = ray48; lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
 		lio.cellTris = c->cellTris.as<int>(); lio.colOff = c->colOff.as<unsigned>(); lio.colCount = c->colCount.as<int>(); lio.colTris = c->colTris.as<int>();
@@ -268,11 +290,13 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 		const size_t smem = (size_t)G * 3 * g.n2 * 4 + (size_t)G * rows * 4 + (size_t)G * 16;
 		k_l2<<<(unsigned)((nB + G - 1) / G), kL2Threads, smem, st>>>(g, lio);
 		launches++;
+		mark(GPV_PHASE_L2_NORMALS);
 		if (wantN) {
 			k_l2_normals<<<(unsigned)((nB * n23 + 255) / 256), 256, 0, st>>>(g, lio, c->l2Normal.as<unsigned char>());
 			launches++;
 		}
 	}
+	mark(GPV_PHASE_COUNT);
 	GPV_CUDA(cudaMemcpyAsync(c->hTotals, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
 	GPV_CUDA(cudaStreamSynchronize(st));
 	GPV_CUDA(cudaGetLastError());
@@ -296,6 +320,15 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	out->l2_ray_tests = 0;
 	out->fill_crossings = (int64_t)T2.crossPairs; out->fill_ill_conditioned = (int64_t)T2.nIll;
 	out->kernel_launches = launches;
+	if (prof) {
+		for (int k = 0; k < GPV_PHASE_COUNT; k++) {
+			if (!marked[k]) continue;
+			int nxt = k + 1;
+			while (nxt < GPV_PHASE_COUNT && !marked[nxt]) nxt++;
+			float ms = 0.f;
+			if (cudaEventElapsedTime(&ms, c->ev[k], c->ev[nxt]) == cudaSuccess) out->phase_ms[k] = ms;
+		}
+	}
 	return 0;
 }
 

@@ -70,6 +70,7 @@ typedef struct {
 #define GPV_NORMALS      1     /* also produce Level1Normal / Level2Normal streams */
 #define GPV_NO_LEVEL2    2     /* GLParameters::level2Voxels == false */
 #define GPV_KEEP_LISTS   4     /* keep CSR cell lists / column lists readable after the call (gpv_result list pointers) */
+#define GPV_PROFILE      8     /* record a CUDA event pair around every kernel of the pipeline -> gpv_result.phase_ms */
 
 typedef struct {
 	int voxel_count;           /* GLParameters::voxelCount  (Level-1 cells along the longest axis; reference default 8) */
@@ -104,7 +105,12 @@ typedef struct {
 	/* reference-equivalent work */
 	int64_t l1_box_tests, l1_box_hits, l2_box_tests, l2_ray_tests, tri_total, fill_crossings, fill_ill_conditioned;
 	int64_t kernel_launches;   /* kernels launched by this call */
+	/* GPV_PROFILE: device time of each phase in ms (CUDA events on the caller's stream), indexed by GPV_PHASE_* */
+	float phase_ms[16];
 } gpv_result;
+
+enum { GPV_PHASE_SETUP = 0, GPV_PHASE_BIN_COUNT, GPV_PHASE_CROSS_COUNT, GPV_PHASE_SCAN, GPV_PHASE_HOST_GAP, GPV_PHASE_BIN_FILL,
+       GPV_PHASE_CROSS_FILL, GPV_PHASE_SORT, GPV_PHASE_FILL_SWEEP, GPV_PHASE_L1_NORMALS, GPV_PHASE_L2, GPV_PHASE_L2_NORMALS, GPV_PHASE_COUNT };
 
 /* host copies of the streams (caller-allocated; any pointer may be NULL to skip that stream) */
 typedef struct {
