@@ -3,8 +3,9 @@
 // Pipeline of gpv_voxelize_device (what Object::PerformVoxelization, src/Object.cpp:3077-3430, does between
 // CreateFlatTriangleData and SaveVoxelization, re-designed for one B200):
 //
-//   k_tables, k_repack
-//   k_bin<count>            K1 count sweep: cellCount, colCount(over), l1Tests/l1Hits
+//   k_tables, k_prepare     48 B triangle / ray records, footprints, work-item counts
+//   k_scan<OFFS> x2         balanced work spaces of the two triangle-parallel sweeps
+//   k_bin<count>            K1 count sweep: cellCount, colCount(over), l1Hits
 //   k_cross<count>          K2a count sweep: crossCount
 //   k_scan<CELLS>           K3: prefix, boundaryIndex, bTriOff, bmask, nBoundary, triTotal
 //   k_scan<OFFS> x2         column-list offsets, crossing-list offsets
@@ -58,7 +59,7 @@ struct gpv_ctx {
 	int device = 0;
 	int smCount = 0;
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
-	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch;
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff;
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
@@ -102,7 +103,7 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff };
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
 	if (c->haveEvents) for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -139,7 +140,8 @@ extern "C" int gpv_stream_sync(void* stream)
 	return 0;
 }
 
-static int run_scan_offsets(gpv_ctx* c, cudaStream_t st, const int* in, long long n, unsigned* off, unsigned* totalOut, int64_t& launches)
+static int run_scan_offsets(gpv_ctx* c, cudaStream_t st, const int* in, long long n, unsigned* off, unsigned* totalOut, unsigned long long* totalOut64,
+                            int64_t& launches)
 {
 	long long tiles = (n + kScanTile - 1) / kScanTile;
 	if (c->desc.ensure((size_t)(tiles + 1) * 8 + 16)) return 1;
@@ -147,7 +149,7 @@ static int run_scan_offsets(gpv_ctx* c, cudaStream_t st, const int* in, long lon
 	ScanIO io{};
 	io.in = in; io.n = n;
 	io.desc = c->desc.as<unsigned long long>() + 1; io.tileCounter = c->desc.as<unsigned>();
-	io.off = off; io.totalOut = totalOut;
+	io.off = off; io.totalOut = totalOut; io.totalOut64 = totalOut64;
 	k_scan<MODE_OFFS><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
 	launches++;
 	return 0;
@@ -179,6 +181,7 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	const long long ncol = (long long)g.nx * g.ny;
 	const long long cells = ncol * (g.z1 - g.z0);
 	if (ncol * g.nz > 0x7fffffffLL) return fail("grid exceeds 2^31 cells: boundary_index is int32 (file contract); shard finer");
+	if (g.nx > 32767 || g.ny > 32767 || g.nz > 32767) return fail("grid axis exceeds 32767 cells (footprints are packed in 16-bit fields)");
 	const int nTri = (int)n_tri;
 	int64_t launches = 0;
 	const bool prof = (prm->flags & GPV_PROFILE) != 0;
@@ -195,7 +198,9 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	    c->tabZ.ensure((size_t)g.nz * 4) || c->cellCount.ensure((size_t)cells * 4 + 32) || c->colCount.ensure((size_t)ncol * 4 + 32) ||
 	    c->crossCount.ensure((size_t)ncol * 4 + 32) || c->prefix.ensure((size_t)(cells + 1) * 4 + 32) || c->bmask.ensure((size_t)cells / 8 + 64) ||
 	    c->boundaryIndex.ensure((size_t)cells * 4 + 32) || c->bTriOff.ensure((size_t)(cells + 1) * 4 + 32) || c->colOff.ensure((size_t)(ncol + 1) * 4 + 32) ||
-	    c->crossOff.ensure((size_t)(ncol + 1) * 4 + 32) || c->l1State.ensure((size_t)cells + 32))
+	    c->crossOff.ensure((size_t)(ncol + 1) * 4 + 32) || c->l1State.ensure((size_t)cells + 32) || c->crossFp.ensure((size_t)nTri * 16) ||
+	    c->binCnt.ensure((size_t)nTri * 4 + 32) || c->binOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->crossCnt.ensure((size_t)nTri * 4 + 32) ||
+	    c->crossWorkOff.ensure((size_t)(nTri + 1) * 4 + 32))
 		return 1;
 	Totals* dT = c->totals.as<Totals>();
 	mark(GPV_PHASE_SETUP);
@@ -209,16 +214,18 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	{
 		int m = g.nx > g.ny ? g.nx : g.ny; m = m > g.nz ? m : g.nz;
 		k_tables<<<(m + 255) / 256, 256, 0, st>>>(g, cx, cy, cz);
-		k_repack<<<(nTri + 255) / 256, 256, 0, st>>>(d_tris, nTri, tri48, ray48);
+		k_prepare<<<(nTri + 255) / 256, 256, 0, st>>>(d_tris, nTri, g, tri48, ray48, c->crossFp.as<int4>(), c->binCnt.as<int>(), c->crossCnt.as<int>(), dT);
 		launches += 2;
 	}
-	const int binBlocks = (nTri + kBinThreads - 1) / kBinThreads;
+	// balanced work spaces: exclusive scans of the per-triangle item counts; totals stay on the device (persistent grids read them)
+	if (run_scan_offsets(c, st, c->binCnt.as<int>(), nTri, c->binOff.as<unsigned>(), nullptr, &dT->binWork, launches)) return 1;
+	if (run_scan_offsets(c, st, c->crossCnt.as<int>(), nTri, c->crossWorkOff.as<unsigned>(), nullptr, &dT->crossWork, launches)) return 1;
 	BinOut bo{};
 	bo.cellCount = c->cellCount.as<int>(); bo.colCount = c->colCount.as<int>(); bo.totals = dT;
 	mark(GPV_PHASE_BIN_COUNT);
-	k_bin<false><<<binBlocks, kBinThreads, 0, st>>>(tri48, nTri, g, cx, cy, cz, bo);
+	k_bin<false><<<kWorkGrid, kWorkThreads, 0, st>>>(tri48, nTri, c->binOff.as<unsigned>(), g, cx, cy, cz, bo);
 	mark(GPV_PHASE_CROSS_COUNT);
-	k_cross<false><<<binBlocks, kBinThreads, 0, st>>>(ray48, nTri, g, cx, cy, c->crossCount.as<int>(), nullptr, nullptr, dT);
+	k_cross<false><<<kWorkGrid, kWorkThreads, 0, st>>>(ray48, c->crossFp.as<int4>(), nTri, c->crossWorkOff.as<unsigned>(), g, cx, cy, c->crossCount.as<int>(), nullptr, nullptr, dT);
 	launches += 2;
 	mark(GPV_PHASE_SCAN);
 	{ // K3 boundary compaction
@@ -233,8 +240,8 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 		k_scan<MODE_CELLS><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
 		launches++;
 	}
-	if (run_scan_offsets(c, st, c->colCount.as<int>(), ncol, c->colOff.as<unsigned>(), &dT->colTotalOver, launches)) return 1;
-	if (run_scan_offsets(c, st, c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, launches)) return 1;
+	if (run_scan_offsets(c, st, c->colCount.as<int>(), ncol, c->colOff.as<unsigned>(), &dT->colTotalOver, nullptr, launches)) return 1;
+	if (run_scan_offsets(c, st, c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, nullptr, launches)) return 1;
 
 	// ---- the one size read-back
 	mark(GPV_PHASE_HOST_GAP);
@@ -243,6 +250,7 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	GPV_CUDA(cudaGetLastError());
 	const Totals T1 = *c->hTotals;
 	if (T1.l1Hits > 0x7ffffff0ull) return fail("more than 2^31 (cell, triangle) pairs in one slab: shard finer");
+	if (T1.binWork > 0xfffffff0ull || T1.crossWork > 0xfffffff0ull) return fail("more than 2^32 (triangle, cell) work items: work offsets are 32-bit");
 	const long long nB = T1.nBoundary;
 	const long long n23 = (long long)g.n2 * g.n2 * g.n2;
 	if (c->cellTris.ensure((size_t)T1.triTotal * 4 + 32) || c->colTris.ensure((size_t)T1.colTotalOver * 4 + 32) || c->crossTri.ensure((size_t)T1.crossTotal * 4 + 32))
@@ -253,9 +261,10 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	bo.prefix = c->prefix.as<int>(); bo.bTriOff = c->bTriOff.as<unsigned>(); bo.cellTris = c->cellTris.as<int>();
 	bo.colOff = c->colOff.as<unsigned>(); bo.colTris = c->colTris.as<int>();
 	mark(GPV_PHASE_BIN_FILL);
-	k_bin<true><<<binBlocks, kBinThreads, 0, st>>>(tri48, nTri, g, cx, cy, cz, bo);
+	k_bin<true><<<kWorkGrid, kWorkThreads, 0, st>>>(tri48, nTri, c->binOff.as<unsigned>(), g, cx, cy, cz, bo);
 	mark(GPV_PHASE_CROSS_FILL);
-	k_cross<true><<<binBlocks, kBinThreads, 0, st>>>(ray48, nTri, g, cx, cy, c->crossCount.as<int>(), c->crossOff.as<unsigned>(), c->crossTri.as<int>(), dT);
+	k_cross<true><<<kWorkGrid, kWorkThreads, 0, st>>>(ray48, c->crossFp.as<int4>(), nTri, c->crossWorkOff.as<unsigned>(), g, cx, cy, c->crossCount.as<int>(), c->crossOff.as<unsigned>(),
+	                                                   c->crossTri.as<int>(), dT);
 	launches += 2;
 	mark(GPV_PHASE_SORT);
 	if (nB > 0) {
@@ -314,7 +323,7 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	out->d_col_off = c->colOff.as<uint32_t>(); out->d_col_count = c->colCount.as<int32_t>(); out->d_col_tris = c->colTris.as<int32_t>();
 	out->l1_inside = (int64_t)T2.l1Inside; out->l1_boundary = nB;
 	out->l2_inside = (int64_t)T2.l2Inside; out->l2_boundary = (int64_t)T2.l2Boundary;
-	out->l1_box_tests = (int64_t)T2.l1Tests; out->l1_box_hits = (int64_t)T2.l1Hits;
+	out->l1_box_tests = (int64_t)T2.binWork; out->l1_box_hits = (int64_t)T2.l1Hits; // sum of clipped footprints = the reference's loop nest (cu:374-378)
 	out->tri_total = T2.triTotal;
 	out->l2_box_tests = wantL2 ? (int64_t)T2.triTotal * n23 : 0; // reference-equivalent: n2^3 x sum of cell list lengths (cu:428)
 	out->l2_ray_tests = 0;

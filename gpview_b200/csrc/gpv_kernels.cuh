@@ -3,7 +3,7 @@
 // Compiled ONLY with  nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false  (see DESIGN.md "Numerics").
 // Kernel inventory (SURVEY.md 2.3 "new kernels"):
 //   k_tables        per-axis Level-1 cell-centre tables (kills all FP64 / int->float work in the inner loops)
-//   k_repack        36 B flat triangles -> 48 B float4x3 records (TMA-able) + 48 B +Z ray records
+//   k_prepare       36 B flat triangles -> 48 B float4x3 records (TMA-able, footprint in the w lanes) + 48 B +Z ray records
 //   k_bin<FILL>     K1  triangle -> Level-1 cell SAT binning (count / fill sweeps), TMA-staged triangle tiles
 //   k_cross<FILL>   K2a certified (column, triangle) crossing detection for the parity fill
 //   k_fill_sweep    K2b +Z parity sweep per Level-1 column, coalesced along x, final Level-1 state bytes
@@ -30,34 +30,39 @@ struct GridP {
 
 // device-side totals block (one per context), read back once per model
 struct Totals {
-	unsigned long long l1Tests, l1Hits, colPairsOver, crossPairs, nIll, l1Inside, l2Inside, l2Boundary, l2BoxTests, l2RayTests;
+	unsigned long long binWork, crossWork; // totals of the two balanced work spaces (exclusive scans of binCnt / crossCnt)
+	unsigned long long l1Hits, crossPairs, nIll, l1Inside, l2Inside, l2Boundary;
 	unsigned int nBoundary, triTotal, colTotalOver, crossTotal;
 };
 
-constexpr int kBinThreads = 128;  // triangles per tile
-constexpr int kBigFootprint = 32; // cells; larger footprints are spread over the warp
+constexpr int kWorkThreads = 128;                        // threads per CTA of the balanced triangle-work kernels
+constexpr int kWorkItems = 8;                            // work items per thread and work block
+constexpr int kWorkBlock = kWorkThreads * kWorkItems;    // 1024 (triangle, cell) items per work block
+constexpr int kTileTris = 128;                           // triangle records staged per TMA tile (6 KB + 2 KB)
+constexpr int kWorkGrid = 148 * 8;                       // persistent grid: 8 CTAs per SM, work blocks strided over it
 
-// ------------------------------------------------------------------------------------------------ TMA tile load
-// One elected thread issues a 1-D bulk async copy (TMA, SASS UBLKCP) of `bytes` (multiple of 16) from global to shared
-// memory; completion is signalled on an mbarrier that every thread of the CTA then waits on.
-__device__ __forceinline__ void tma_load_tile(void* smemDst, const void* gmemSrc, uint32_t bytes, uint64_t* bar, int tid)
+// ------------------------------------------------------------------------------------------------ TMA staging
+// 1-D bulk async copies (TMA, SASS UBLKCP) from global to shared memory, completion on an mbarrier (SYNCS).
+__device__ __forceinline__ void mbar_init(uint64_t* bar)
 {
-	uint32_t barAddr = (uint32_t)__cvta_generic_to_shared(bar);
-	uint32_t dstAddr = (uint32_t)__cvta_generic_to_shared(smemDst);
-	if (tid == 0) {
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-	if (tid == 0) {
-		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(bytes) : "memory");
-		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-		             ::"r"(dstAddr), "l"(gmemSrc), "r"(bytes), "r"(barAddr) : "memory");
-	}
-	uint32_t done = 0;
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smemDst, const void* gmemSrc, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	uint32_t done = 0, addr = (uint32_t)__cvta_generic_to_shared(bar);
 	while (!done) {
-		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-		             : "=r"(done) : "r"(barAddr) : "memory");
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
 	}
 }
 
@@ -72,10 +77,17 @@ __global__ void k_tables(GridP g, float* cx, float* cy, float* cz)
 	if (i < g.nz) cz[i] = (float)((i + 0.5) * (double)g.h1z * 2 + (double)g.minz);
 }
 
-// ------------------------------------------------------------------------------------------------ k_repack
-// flat float[9] per triangle (src/Object.cpp:3496-3527 layout) -> tri48 (v0|v1|v2 as float4, w = 0) and ray48
-// (v1xyz e1xyz e2xyz det inv ok), both 16-byte aligned records so that tiles can be moved by TMA bulk copies.
-__global__ void __launch_bounds__(256) k_repack(const float* __restrict__ flat, long long nTri, float4* __restrict__ tri48, float4* __restrict__ ray48)
+// ------------------------------------------------------------------------------------------------ k_prepare
+// flat float[9] per triangle (src/Object.cpp:3496-3527 layout) ->
+//   tri48  v0|v1|v2 as float4; the three w lanes carry the clipped Level-1 footprint (cu:333-378) as packed 16-bit fields
+//          w0 = lox | loy<<16, w1 = loz | dx<<16, w2 = dy | dz<<16
+//   ray48  v1xyz e1xyz e2xyz det inv ok  (gpv::RayTri)
+//   crossFp i0 | j0<<16, di | dj<<16, kind, -   certified candidate columns of the +Z parity fill (gpv::fill_candidates)
+//   binCnt / crossCnt  number of (triangle, cell) / (triangle, column) work items
+// All records are 16-byte aligned so that contiguous triangle ranges can be moved by TMA bulk copies.
+__global__ void __launch_bounds__(256) k_prepare(const float* __restrict__ flat, long long nTri, GridP g, float4* __restrict__ tri48,
+                                                 float4* __restrict__ ray48, int4* __restrict__ crossFp, int* __restrict__ binCnt,
+                                                 int* __restrict__ crossCnt, Totals* totals)
 {
 	__shared__ float s[256 * 9];
 	long long base = (long long)blockIdx.x * 256;
@@ -83,16 +95,36 @@ __global__ void __launch_bounds__(256) k_repack(const float* __restrict__ flat, 
 	for (int i = threadIdx.x; i < n * 9; i += 256) s[i] = flat[base * 9 + i]; // coalesced
 	__syncthreads();
 	int t = threadIdx.x;
-	if (t >= n) return;
-	const float* v = s + t * 9;
-	tri48[(base + t) * 3 + 0] = make_float4(v[0], v[1], v[2], 0.f);
-	tri48[(base + t) * 3 + 1] = make_float4(v[3], v[4], v[5], 0.f);
-	tri48[(base + t) * 3 + 2] = make_float4(v[6], v[7], v[8], 0.f);
-	RayTri r;
-	ray_tri_setup(r, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
-	ray48[(base + t) * 3 + 0] = make_float4(r.v1x, r.v1y, r.v1z, r.e1x);
-	ray48[(base + t) * 3 + 1] = make_float4(r.e1y, r.e1z, r.e2x, r.e2y);
-	ray48[(base + t) * 3 + 2] = make_float4(r.e2z, r.det, r.inv, r.ok ? 1.f : 0.f);
+	unsigned long long ill = 0;
+	if (t < n) {
+		const float* v = s + t * 9;
+		// vertex -> cell, footprint min/max (cu:333-371); loops are clipped to < numDiv (cu:374-378) and to >= 0
+		int x0 = cell_of(v[0], g.minx, g.maxx, g.nx), x1 = cell_of(v[3], g.minx, g.maxx, g.nx), x2 = cell_of(v[6], g.minx, g.maxx, g.nx);
+		int y0 = cell_of(v[1], g.miny, g.maxy, g.ny), y1 = cell_of(v[4], g.miny, g.maxy, g.ny), y2 = cell_of(v[7], g.miny, g.maxy, g.ny);
+		int w0 = cell_of(v[2], g.minz, g.maxz, g.nz), w1 = cell_of(v[5], g.minz, g.maxz, g.nz), w2 = cell_of(v[8], g.minz, g.maxz, g.nz);
+		int lox = max(0, min(x0, min(x1, x2))), hix = min(g.nx - 1, max(x0, max(x1, x2)));
+		int loy = max(0, min(y0, min(y1, y2))), hiy = min(g.ny - 1, max(y0, max(y1, y2)));
+		int loz = max(0, min(w0, min(w1, w2))), hiz = min(g.nz - 1, max(w0, max(w1, w2)));
+		int dx = max(0, hix - lox + 1), dy = max(0, hiy - loy + 1), dz = max(0, hiz - loz + 1);
+		if (dx == 0 || dy == 0 || dz == 0) { dx = dy = dz = 0; lox = loy = loz = 0; }
+		tri48[(base + t) * 3 + 0] = make_float4(v[0], v[1], v[2], __int_as_float(lox | (loy << 16)));
+		tri48[(base + t) * 3 + 1] = make_float4(v[3], v[4], v[5], __int_as_float(loz | (dx << 16)));
+		tri48[(base + t) * 3 + 2] = make_float4(v[6], v[7], v[8], __int_as_float(dy | (dz << 16)));
+		binCnt[base + t] = dx * dy * dz;
+		RayTri r;
+		ray_tri_setup(r, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+		ray48[(base + t) * 3 + 0] = make_float4(r.v1x, r.v1y, r.v1z, r.e1x);
+		ray48[(base + t) * 3 + 1] = make_float4(r.e1y, r.e1z, r.e2x, r.e2y);
+		ray48[(base + t) * 3 + 2] = make_float4(r.e2z, r.det, r.inv, r.ok ? 1.f : 0.f);
+		int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
+		int kind = fill_candidates(r, g.minx, g.miny, g.gsx, g.gsy, g.nx, g.ny, i0, i1, j0, j1);
+		if (kind == 2) { i0 = 0; j0 = 0; i1 = g.nx - 1; j1 = g.ny - 1; ill = 1; }
+		int di = kind ? i1 - i0 + 1 : 0, dj = kind ? j1 - j0 + 1 : 0;
+		crossFp[base + t] = make_int4(i0 | (j0 << 16), di | (dj << 16), kind, 0);
+		crossCnt[base + t] = di * dj;
+	}
+	ill = __reduce_add_sync(0xffffffffu, (unsigned)ill);
+	if ((threadIdx.x & 31) == 0 && ill) atomicAdd(&totals->nIll, ill);
 }
 
 __device__ __forceinline__ void load_ray(RayTri& r, const float4* __restrict__ ray48, int t)
@@ -108,10 +140,67 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
 	return v;
 }
 
+// ------------------------------------------------------------------------------------------------ balanced triangle work
+// The (triangle, cell) items of all triangles form one flat index space (off = exclusive scan of the per-triangle item
+// counts).  Work block w owns items [w*1024, (w+1)*1024); work blocks are strided over a persistent grid.  The triangles
+// a work block touches are a CONTIGUOUS range, staged tile by tile (<= 128 records) into shared memory by TMA; each
+// thread finds the owner of its item by binary search in the tile's offsets (shared memory) and decodes the cell from the
+// item's rank inside the footprint.  This removes the footprint skew (cessna-256: mean 64, max 6,762 cells per triangle;
+// an ill-conditioned triangle of the parity fill has nx*ny candidate columns) that a triangle-per-thread map suffers from.
+struct WorkSmem {
+	float4 rec[kTileTris * 3];
+	int4 fp[kTileTris];
+	unsigned off[kTileTris + 1];
+	int t0;
+	uint64_t bar;
+};
+
+template <bool HAS_FP, class F>
+__device__ __forceinline__ void for_each_work_item(WorkSmem& sm, const unsigned* __restrict__ off, int nTri, const unsigned long long* totalPtr,
+                                                   const float4* __restrict__ rec48, const int4* __restrict__ fp, F&& f)
+{
+	const int tid = threadIdx.x;
+	if (tid == 0) mbar_init(&sm.bar);
+	__syncthreads();
+	const unsigned long long total = *totalPtr;
+	uint32_t parity = 0;
+	for (unsigned long long wb = blockIdx.x; wb * kWorkBlock < total; wb += gridDim.x) {
+		const unsigned long long B0 = wb * kWorkBlock, B1 = min(total, B0 + kWorkBlock);
+		if (tid == 0) { // largest t with off[t] <= B0   (off[0] = 0 <= B0 < total = off[nTri])
+			int lo = 0, hi = nTri;
+			while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (off[mid] <= B0) lo = mid; else hi = mid; }
+			sm.t0 = lo;
+		}
+		__syncthreads();
+		int t = sm.t0;
+		for (;;) {
+			const int nt = min(kTileTris, nTri - t);
+			for (int i = tid; i <= nt; i += kWorkThreads) sm.off[i] = off[t + i];
+			if (tid == 0) {
+				mbar_expect(&sm.bar, (uint32_t)nt * (HAS_FP ? 64u : 48u));
+				tma_bulk_g2s(sm.rec, rec48 + (size_t)t * 3, (uint32_t)nt * 48u, &sm.bar);
+				if (HAS_FP) tma_bulk_g2s(sm.fp, fp + t, (uint32_t)nt * 16u, &sm.bar);
+			}
+			mbar_wait(&sm.bar, parity);
+			parity ^= 1;
+			__syncthreads();
+			const unsigned long long cb = max(B0, (unsigned long long)sm.off[0]), ce = min(B1, (unsigned long long)sm.off[nt]);
+			const bool last = sm.off[nt] >= B1 || t + nt >= nTri;
+			for (unsigned long long c = cb + tid; c < ce; c += kWorkThreads) {
+				int lo = 0, hi = nt; // largest k in [0,nt) with off[k] <= c
+				while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm.off[mid] <= c) lo = mid; else hi = mid; }
+				f(t + lo, sm.rec + lo * 3, sm.fp + lo, (unsigned)(c - sm.off[lo]));
+			}
+			__syncthreads();
+			if (last) break;
+			t += nt;
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ k_bin
 // K1.  Replaces CUDAClassifyTessellationKernel (cu:320-401) + the host CSR flatten (src/Object.cpp:2137-2180).
-// One thread owns one triangle of a 128-triangle tile (staged by TMA); footprints larger than kBigFootprint cells are
-// spread over the 32 lanes of the warp (cessna-256: mean 64, max 6,762 cells per triangle).  Two sweeps:
+// One thread = one (triangle, Level-1 cell) SAT test (cu:374-395).  Two sweeps over the same balanced work space:
 //   FILL=false  cellCount[cell]++ (slab cells only), colCount[col]++ (every hit: column lists are de-duplicated later)
 //   FILL=true   cellTris[bTriOff[prefix[cell]] + slot], colTris[colOff[col] + slot]   (slots by atomic decrement)
 struct BinOut {
@@ -126,88 +215,34 @@ struct BinOut {
 };
 
 template <bool FILL>
-__device__ __forceinline__ void bin_emit(const GridP& g, const BinOut& o, int p, int q, int r, int t)
+__global__ void __launch_bounds__(kWorkThreads) k_bin(const float4* __restrict__ tri48, int nTri, const unsigned* __restrict__ binOff, GridP g,
+                                                      const float* __restrict__ cx, const float* __restrict__ cy, const float* __restrict__ cz, BinOut o)
 {
-	int col = q * g.nx + p;
-	if (!FILL) {
-		atomicAdd(o.colCount + col, 1);
-		if (r >= g.z0 && r < g.z1) atomicAdd(o.cellCount + ((size_t)(r - g.z0) * g.ny * g.nx + col), 1);
-	} else {
-		int slot = atomicSub(o.colCount + col, 1) - 1;
-		o.colTris[o.colOff[col] + slot] = t;
-		if (r >= g.z0 && r < g.z1) {
-			size_t li = (size_t)(r - g.z0) * g.ny * g.nx + col;
-			int s2 = atomicSub(o.cellCount + li, 1) - 1;
-			o.cellTris[o.bTriOff[o.prefix[li]] + s2] = t;
-		}
-	}
-}
-
-template <bool FILL>
-__global__ void __launch_bounds__(kBinThreads) k_bin(const float4* __restrict__ tri48, int nTri, GridP g,
-                                                     const float* __restrict__ cx, const float* __restrict__ cy, const float* __restrict__ cz, BinOut o)
-{
-	__shared__ __align__(128) float4 sTri[kBinThreads * 3];
-	__shared__ __align__(8) uint64_t bar;
-	const int tid = threadIdx.x, lane = tid & 31;
-	const int base = blockIdx.x * kBinThreads;
-	const int n = min(kBinThreads, nTri - base);
-	tma_load_tile(sTri, tri48 + (size_t)base * 3, (uint32_t)n * 48u, &bar, tid);
-
-	float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
-	int lox = 0, loy = 0, loz = 0, dx = 0, dy = 0, dz = 0;
-	const bool valid = tid < n;
-	if (valid) {
-		a = sTri[tid * 3]; b = sTri[tid * 3 + 1]; c = sTri[tid * 3 + 2];
-		// vertex -> cell, footprint min/max (cu:333-371); loops are clipped to < numDiv (cu:374-378) and to >= 0
-		int x0 = cell_of(a.x, g.minx, g.maxx, g.nx), x1 = cell_of(b.x, g.minx, g.maxx, g.nx), x2 = cell_of(c.x, g.minx, g.maxx, g.nx);
-		int y0 = cell_of(a.y, g.miny, g.maxy, g.ny), y1 = cell_of(b.y, g.miny, g.maxy, g.ny), y2 = cell_of(c.y, g.miny, g.maxy, g.ny);
-		int w0 = cell_of(a.z, g.minz, g.maxz, g.nz), w1 = cell_of(b.z, g.minz, g.maxz, g.nz), w2 = cell_of(c.z, g.minz, g.maxz, g.nz);
-		lox = max(0, min(x0, min(x1, x2))); int hix = min(g.nx - 1, max(x0, max(x1, x2)));
-		loy = max(0, min(y0, min(y1, y2))); int hiy = min(g.ny - 1, max(y0, max(y1, y2)));
-		loz = max(0, min(w0, min(w1, w2))); int hiz = min(g.nz - 1, max(w0, max(w1, w2)));
-		dx = max(0, hix - lox + 1); dy = max(0, hiy - loy + 1); dz = max(0, hiz - loz + 1);
-	}
-	const long long ncell = (long long)dx * dy * dz;
-	unsigned long long tests = 0, hits = 0;
-
-	// big footprints: all 32 lanes walk the cells of one triangle, p fastest (adjacent atomics)
-	unsigned big = __ballot_sync(0xffffffffu, ncell > kBigFootprint);
-	while (big) {
-		int src = __ffs(big) - 1;
-		big &= big - 1;
-		float t0x = __shfl_sync(0xffffffffu, a.x, src), t0y = __shfl_sync(0xffffffffu, a.y, src), t0z = __shfl_sync(0xffffffffu, a.z, src);
-		float t1x = __shfl_sync(0xffffffffu, b.x, src), t1y = __shfl_sync(0xffffffffu, b.y, src), t1z = __shfl_sync(0xffffffffu, b.z, src);
-		float t2x = __shfl_sync(0xffffffffu, c.x, src), t2y = __shfl_sync(0xffffffffu, c.y, src), t2z = __shfl_sync(0xffffffffu, c.z, src);
-		int slx = __shfl_sync(0xffffffffu, lox, src), sly = __shfl_sync(0xffffffffu, loy, src), slz = __shfl_sync(0xffffffffu, loz, src);
-		int sdx = __shfl_sync(0xffffffffu, dx, src), sdy = __shfl_sync(0xffffffffu, dy, src);
-		long long tot = __shfl_sync(0xffffffffu, ncell, src);
-		int t = base + (tid - lane) + src;
-		for (long long i = lane; i < tot; i += 32) {
-			int p = slx + (int)(i % sdx);
-			long long rest = i / sdx;
-			int q = sly + (int)(rest % sdy), r = slz + (int)(rest / sdy);
-			tests++;
-			if (tri_box_overlap(cx[p], cy[q], cz[r], g.h1x, g.h1y, g.h1z, t0x, t0y, t0z, t1x, t1y, t1z, t2x, t2y, t2z)) {
-				hits++;
-				bin_emit<FILL>(g, o, p, q, r, t);
+	__shared__ __align__(128) WorkSmem sm;
+	unsigned long long hits = 0;
+	for_each_work_item<false>(sm, binOff, nTri, &o.totals->binWork, tri48, nullptr, [&](int t, const float4* rec, const int4*, unsigned local) {
+		const float4 a = rec[0], b = rec[1], c = rec[2];
+		const unsigned w0 = __float_as_uint(a.w), w1 = __float_as_uint(b.w), w2 = __float_as_uint(c.w);
+		const unsigned dx = w1 >> 16, dy = w2 & 0xffffu;
+		const unsigned rest = local / dx;
+		const int p = (int)((w0 & 0xffffu) + (local - rest * dx)), q = (int)((w0 >> 16) + rest % dy), r = (int)((w1 & 0xffffu) + rest / dy);
+		if (!tri_box_overlap(cx[p], cy[q], cz[r], g.h1x, g.h1y, g.h1z, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z)) return;
+		hits++;
+		const int col = q * g.nx + p;
+		if (!FILL) {
+			atomicAdd(o.colCount + col, 1);
+			if (r >= g.z0 && r < g.z1) atomicAdd(o.cellCount + ((size_t)(r - g.z0) * g.ny * g.nx + col), 1);
+		} else {
+			o.colTris[o.colOff[col] + atomicSub(o.colCount + col, 1) - 1] = t;
+			if (r >= g.z0 && r < g.z1) {
+				const size_t li = (size_t)(r - g.z0) * g.ny * g.nx + col;
+				o.cellTris[o.bTriOff[o.prefix[li]] + atomicSub(o.cellCount + li, 1) - 1] = t;
 			}
 		}
-	}
-	// small footprints: the owning lane walks its own cells
-	if (valid && ncell <= kBigFootprint) {
-		int t = base + tid;
-		for (int r = loz; r < loz + dz; r++) for (int q = loy; q < loy + dy; q++) for (int p = lox; p < lox + dx; p++) {
-			tests++;
-			if (tri_box_overlap(cx[p], cy[q], cz[r], g.h1x, g.h1y, g.h1z, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z)) {
-				hits++;
-				bin_emit<FILL>(g, o, p, q, r, t);
-			}
-		}
-	}
+	});
 	if (!FILL) {
-		tests = warp_sum(tests); hits = warp_sum(hits);
-		if (lane == 0) { atomicAdd(&o.totals->l1Tests, tests); atomicAdd(&o.totals->l1Hits, hits); }
+		hits = warp_sum(hits);
+		if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&o.totals->l1Hits, hits);
 	}
 }
 
@@ -215,71 +250,33 @@ __global__ void __launch_bounds__(kBinThreads) k_bin(const float4* __restrict__ 
 // K2a.  For every triangle, the Level-1 columns whose +Z ray passes the det/u/v part of Moller-Trumbore (constant along
 // the column, App. A.6).  Candidate columns come from gpv::fill_candidates (certified superset of what the reference's
 // brute force Object::ClassifyInOutCPU, src/Object.cpp:716-779, can hit); ill-conditioned triangles test every column.
+// One thread = one (triangle, candidate column) test over the balanced work space.
 template <bool FILL>
-__global__ void __launch_bounds__(kBinThreads) k_cross(const float4* __restrict__ ray48, int nTri, GridP g,
-                                                       const float* __restrict__ cx, const float* __restrict__ cy,
-                                                       int* crossCount, const unsigned* __restrict__ crossOff, int* crossTri, Totals* totals)
+__global__ void __launch_bounds__(kWorkThreads) k_cross(const float4* __restrict__ ray48, const int4* __restrict__ crossFp, int nTri,
+                                                        const unsigned* __restrict__ workOff, GridP g, const float* __restrict__ cx,
+                                                        const float* __restrict__ cy, int* crossCount, const unsigned* __restrict__ crossOff,
+                                                        int* crossTri, Totals* totals)
 {
-	__shared__ __align__(128) float4 sRay[kBinThreads * 3];
-	__shared__ __align__(8) uint64_t bar;
-	const int tid = threadIdx.x, lane = tid & 31;
-	const int base = blockIdx.x * kBinThreads;
-	const int n = min(kBinThreads, nTri - base);
-	tma_load_tile(sRay, ray48 + (size_t)base * 3, (uint32_t)n * 48u, &bar, tid);
-
-	RayTri s;
-	int i0 = 0, j0 = 0, di = 0, dj = 0, kind = 0;
-	if (tid < n) {
-		float4 a = sRay[tid * 3], b = sRay[tid * 3 + 1], c = sRay[tid * 3 + 2];
-		s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;
-		s.e2z = c.x; s.det = c.y; s.inv = c.z; s.ok = c.w != 0.f;
-		int i1, j1;
-		kind = fill_candidates(s, g.minx, g.miny, g.gsx, g.gsy, g.nx, g.ny, i0, i1, j0, j1);
-		if (kind == 2) { i0 = 0; j0 = 0; i1 = g.nx - 1; j1 = g.ny - 1; }
-		if (kind) { di = i1 - i0 + 1; dj = j1 - j0 + 1; }
-	} else { s.ok = false; s.v1x = s.v1y = s.v1z = s.e1x = s.e1y = s.e1z = s.e2x = s.e2y = s.e2z = s.det = s.inv = 0.f; }
-	const long long ncol = (long long)di * dj;
+	__shared__ __align__(128) WorkSmem sm;
 	unsigned long long found = 0;
-
-	unsigned big = __ballot_sync(0xffffffffu, ncol > kBigFootprint);
-	while (big) {
-		int src = __ffs(big) - 1;
-		big &= big - 1;
-		RayTri w;
-		w.v1x = __shfl_sync(0xffffffffu, s.v1x, src); w.v1y = __shfl_sync(0xffffffffu, s.v1y, src);
-		w.e1x = __shfl_sync(0xffffffffu, s.e1x, src); w.e1y = __shfl_sync(0xffffffffu, s.e1y, src); w.e1z = __shfl_sync(0xffffffffu, s.e1z, src);
-		w.e2x = __shfl_sync(0xffffffffu, s.e2x, src); w.e2y = __shfl_sync(0xffffffffu, s.e2y, src); w.e2z = __shfl_sync(0xffffffffu, s.e2z, src);
-		w.inv = __shfl_sync(0xffffffffu, s.inv, src);
-		int si0 = __shfl_sync(0xffffffffu, i0, src), sj0 = __shfl_sync(0xffffffffu, j0, src), sdi = __shfl_sync(0xffffffffu, di, src);
-		long long tot = __shfl_sync(0xffffffffu, ncol, src);
-		int t = base + (tid - lane) + src;
-		for (long long k = lane; k < tot; k += 32) {
-			int i = si0 + (int)(k % sdi), j = sj0 + (int)(k / sdi);
-			RayCol rc;
-			if (ray_column(w, cx[i], cy[j], rc)) {
-				found++;
-				int col = j * g.nx + i;
-				if (!FILL) atomicAdd(crossCount + col, 1);
-				else crossTri[crossOff[col] + atomicSub(crossCount + col, 1) - 1] = t;
-			}
-		}
-	}
-	if (kind && ncol <= kBigFootprint) {
-		int t = base + tid;
-		for (int j = j0; j < j0 + dj; j++) for (int i = i0; i < i0 + di; i++) {
-			RayCol rc;
-			if (ray_column(s, cx[i], cy[j], rc)) {
-				found++;
-				int col = j * g.nx + i;
-				if (!FILL) atomicAdd(crossCount + col, 1);
-				else crossTri[crossOff[col] + atomicSub(crossCount + col, 1) - 1] = t;
-			}
-		}
-	}
+	for_each_work_item<true>(sm, workOff, nTri, &totals->crossWork, ray48, crossFp, [&](int t, const float4* rec, const int4* fp, unsigned local) {
+		const float4 a = rec[0], b = rec[1], c = rec[2];
+		RayTri s;
+		s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;
+		s.e2z = c.x; s.det = c.y; s.inv = c.z; s.ok = true;
+		const unsigned f0 = (unsigned)fp->x, f1 = (unsigned)fp->y;
+		const unsigned di = f1 & 0xffffu, jj = local / di;
+		const int i = (int)((f0 & 0xffffu) + (local - jj * di)), j = (int)((f0 >> 16) + jj);
+		RayCol rc;
+		if (!ray_column(s, cx[i], cy[j], rc)) return;
+		found++;
+		const int col = j * g.nx + i;
+		if (!FILL) atomicAdd(crossCount + col, 1);
+		else crossTri[crossOff[col] + atomicSub(crossCount + col, 1) - 1] = t;
+	});
 	if (!FILL) {
 		found = warp_sum(found);
-		unsigned long long ill = warp_sum((unsigned long long)(kind == 2));
-		if (lane == 0) { atomicAdd(&totals->crossPairs, found); if (ill) atomicAdd(&totals->nIll, ill); }
+		if ((threadIdx.x & 31) == 0 && found) atomicAdd(&totals->crossPairs, found);
 	}
 }
 
@@ -340,7 +337,7 @@ struct ScanIO {
 	// MODE_CELLS
 	int* prefix; int* boundaryIndex; unsigned* bTriOff; unsigned char* bmask; long long globalBase; Totals* totals;
 	// MODE_OFFS
-	unsigned* off; unsigned* totalOut;
+	unsigned* off; unsigned* totalOut; unsigned long long* totalOut64; // either total pointer may be null
 };
 
 __device__ __forceinline__ unsigned long long ld_desc(const unsigned long long* p)
@@ -460,7 +457,11 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(ScanIO io)
 			if (first + k < io.n) io.off[first + k] = (unsigned)run;
 			run += item[k];
 		}
-		if (first <= io.n - 1 && io.n - 1 < first + kScanItems) { io.off[io.n] = (unsigned)run; *io.totalOut = (unsigned)run; }
+		if (first <= io.n - 1 && io.n - 1 < first + kScanItems) {
+			io.off[io.n] = (unsigned)run;
+			if (io.totalOut) *io.totalOut = (unsigned)run;
+			if (io.totalOut64) *io.totalOut64 = run;
+		}
 	}
 }
 
