@@ -59,7 +59,7 @@ struct gpv_ctx {
 	int device = 0;
 	int smCount = 0;
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
-	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff;
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16;
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
@@ -103,7 +103,7 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16 };
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
 	if (c->haveEvents) for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -198,7 +198,7 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	    c->tabZ.ensure((size_t)g.nz * 4) || c->cellCount.ensure((size_t)cells * 4 + 32) || c->colCount.ensure((size_t)ncol * 4 + 32) ||
 	    c->crossCount.ensure((size_t)ncol * 4 + 32) || c->prefix.ensure((size_t)(cells + 1) * 4 + 32) || c->bmask.ensure((size_t)cells / 8 + 64) ||
 	    c->boundaryIndex.ensure((size_t)cells * 4 + 32) || c->bTriOff.ensure((size_t)(cells + 1) * 4 + 32) || c->colOff.ensure((size_t)(ncol + 1) * 4 + 32) ||
-	    c->crossOff.ensure((size_t)(ncol + 1) * 4 + 32) || c->l1State.ensure((size_t)cells + 32) || c->crossFp.ensure((size_t)nTri * 16) ||
+	    c->crossOff.ensure((size_t)(ncol + 1) * 4 + 32) || c->l1State.ensure((size_t)cells + 32) || c->crossFp.ensure((size_t)nTri * 16) || c->plane16.ensure((size_t)nTri * 16) ||
 	    c->binCnt.ensure((size_t)nTri * 4 + 32) || c->binOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->crossCnt.ensure((size_t)nTri * 4 + 32) ||
 	    c->crossWorkOff.ensure((size_t)(nTri + 1) * 4 + 32))
 		return 1;
@@ -214,7 +214,7 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	{
 		int m = g.nx > g.ny ? g.nx : g.ny; m = m > g.nz ? m : g.nz;
 		k_tables<<<(m + 255) / 256, 256, 0, st>>>(g, cx, cy, cz);
-		k_prepare<<<(nTri + 255) / 256, 256, 0, st>>>(d_tris, nTri, g, tri48, ray48, c->crossFp.as<int4>(), c->binCnt.as<int>(), c->crossCnt.as<int>(), dT);
+		k_prepare<<<(nTri + 255) / 256, 256, 0, st>>>(d_tris, nTri, g, tri48, ray48, c->plane16.as<float4>(), c->crossFp.as<int4>(), c->binCnt.as<int>(), c->crossCnt.as<int>(), dT);
 		launches += 2;
 	}
 	// balanced work spaces: exclusive scans of the per-triangle item counts; totals stay on the device (persistent grids read them)
@@ -292,11 +292,11 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	L2IO lio{};
 	mark(GPV_PHASE_L2);
 	if (wantL2 && nB > 0) {
-		lio.tri48 = tri48; lio.ray48 = ray48; lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
+		lio.tri48 = tri48; lio.ray48 = ray48; lio.plane16 = c->plane16.as<float4>(); lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
 		lio.cellTris = c->cellTris.as<int>(); lio.colOff = c->colOff.as<unsigned>(); lio.colCount = c->colCount.as<int>(); lio.colTris = c->colTris.as<int>();
 		lio.cx = cx; lio.cy = cy; lio.cz = cz; lio.l2State = c->l2State.as<unsigned char>(); lio.nBoundary = (int)nB; lio.totals = dT;
 		const int rows = g.n2 * g.n2, G = rows >= kL2Threads ? 1 : kL2Threads / rows;
-		const size_t smem = (size_t)G * 3 * g.n2 * 4 + (size_t)G * rows * 4 + (size_t)G * 16;
+		const size_t smem = (size_t)G * 3 * g.n2 * 4 + (size_t)G * rows * 8 + (size_t)G * 16 + 8 + (kL2Threads / 32) * 64 * 8;
 		k_l2<<<(unsigned)((nB + G - 1) / G), kL2Threads, smem, st>>>(g, lio);
 		launches++;
 		mark(GPV_PHASE_L2_NORMALS);

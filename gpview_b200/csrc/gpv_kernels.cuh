@@ -82,12 +82,13 @@ __global__ void k_tables(GridP g, float* cx, float* cy, float* cz)
 //   tri48  v0|v1|v2 as float4; the three w lanes carry the clipped Level-1 footprint (cu:333-378) as packed 16-bit fields
 //          w0 = lox | loy<<16, w1 = loz | dx<<16, w2 = dy | dz<<16
 //   ray48  v1xyz e1xyz e2xyz det inv ok  (gpv::RayTri)
+//   plane16 normalised plane record of the certified Level-2 plane culling (gpv::PlaneRec)
 //   crossFp i0 | j0<<16, di | dj<<16, kind, -   certified candidate columns of the +Z parity fill (gpv::fill_candidates)
 //   binCnt / crossCnt  number of (triangle, cell) / (triangle, column) work items
 // All records are 16-byte aligned so that contiguous triangle ranges can be moved by TMA bulk copies.
 __global__ void __launch_bounds__(256) k_prepare(const float* __restrict__ flat, long long nTri, GridP g, float4* __restrict__ tri48,
-                                                 float4* __restrict__ ray48, int4* __restrict__ crossFp, int* __restrict__ binCnt,
-                                                 int* __restrict__ crossCnt, Totals* totals)
+                                                 float4* __restrict__ ray48, float4* __restrict__ plane16, int4* __restrict__ crossFp,
+                                                 int* __restrict__ binCnt, int* __restrict__ crossCnt, Totals* totals)
 {
 	__shared__ float s[256 * 9];
 	long long base = (long long)blockIdx.x * 256;
@@ -115,7 +116,9 @@ __global__ void __launch_bounds__(256) k_prepare(const float* __restrict__ flat,
 		ray_tri_setup(r, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
 		ray48[(base + t) * 3 + 0] = make_float4(r.v1x, r.v1y, r.v1z, r.e1x);
 		ray48[(base + t) * 3 + 1] = make_float4(r.e1y, r.e1z, r.e2x, r.e2y);
-		ray48[(base + t) * 3 + 2] = make_float4(r.e2z, r.det, r.inv, r.ok ? 1.f : 0.f);
+		ray48[(base + t) * 3 + 2] = make_float4(r.e2z, r.det, r.inv, r.ok ? (r.well ? 2.f : 1.f) : 0.f);
+		PlaneRec pl = plane_rec_setup(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], g.gsx, g.gsy, g.gsz, g.h2x, g.h2y, g.h2z);
+		plane16[base + t] = make_float4(pl.sx, pl.ny, pl.nz, pl.R);
 		int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
 		int kind = fill_candidates(r, g.minx, g.miny, g.gsx, g.gsy, g.nx, g.ny, i0, i1, j0, j1);
 		if (kind == 2) { i0 = 0; j0 = 0; i1 = g.nx - 1; j1 = g.ny - 1; ill = 1; }
@@ -131,7 +134,7 @@ __device__ __forceinline__ void load_ray(RayTri& r, const float4* __restrict__ r
 {
 	float4 a = __ldg(ray48 + (size_t)t * 3), b = __ldg(ray48 + (size_t)t * 3 + 1), c = __ldg(ray48 + (size_t)t * 3 + 2);
 	r.v1x = a.x; r.v1y = a.y; r.v1z = a.z; r.e1x = a.w; r.e1y = b.x; r.e1z = b.y; r.e2x = b.z; r.e2y = b.w;
-	r.e2z = c.x; r.det = c.y; r.inv = c.z; r.ok = c.w != 0.f;
+	r.e2z = c.x; r.det = c.y; r.inv = c.z; r.ok = c.w != 0.f; r.well = c.w == 2.f;
 }
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(kWorkThreads) k_cross(const float4* __restrict
 		const float4 a = rec[0], b = rec[1], c = rec[2];
 		RayTri s;
 		s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;
-		s.e2z = c.x; s.det = c.y; s.inv = c.z; s.ok = true;
+		s.e2z = c.x; s.det = c.y; s.inv = c.z; s.ok = true; s.well = false;
 		const unsigned f0 = (unsigned)fp->x, f1 = (unsigned)fp->y;
 		const unsigned di = f1 & 0xffffu, jj = local / di;
 		const int i = (int)((f0 & 0xffffu) + (local - jj * di)), j = (int)((f0 >> 16) + jj);
@@ -304,7 +307,10 @@ __global__ void __launch_bounds__(128) k_fill_sweep(const float4* __restrict__ r
 			RayCol rc;
 			if (!ray_column(s, ox, oy, rc)) continue; // cannot happen (listed because it passed); keeps c0..c2 defined
 			unsigned m = 0;
-			for (int kk = 0; kk < kn; kk++) m |= (unsigned)ray_cell(s, rc, cz[kbase + kk]) << kk;
+			const int run = ray_z_run(s, rc, s.well, cz[kbase], cz[kbase + kn - 1]); // whole chunk below / above the crossing?
+			if (run == 0) continue;
+			if (run == 1) m = kn == 32 ? 0xffffffffu : ((1u << kn) - 1);
+			else for (int kk = 0; kk < kn; kk++) m |= (unsigned)ray_cell(s, rc, cz[kbase + kk]) << kk;
 			par ^= m;
 		}
 		const size_t plane = (size_t)g.ny * g.nx;
@@ -543,7 +549,7 @@ __global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restric
 // (n2 = 16: 128-bit; rows of a CTA are contiguous in Level2InOut.raw).
 // Sub-voxel centre (cu:423-425 / 472-474): ((2p+1)*ext2 + mid) - ext1, all f32.
 struct L2IO {
-	const float4* tri48; const float4* ray48;
+	const float4* tri48; const float4* ray48; const float4* plane16;
 	const int* boundaryIndex; const unsigned* bTriOff; const int* cellTris;
 	const unsigned* colOff; const int* colCount; const int* colTris;
 	const float* cx; const float* cy; const float* cz;
@@ -562,6 +568,8 @@ __global__ void __launch_bounds__(kL2Threads) k_l2(GridP g, L2IO io)
 	float* sC = reinterpret_cast<float*>(smemRaw);                   // [G][3][n2] sub-voxel centres
 	unsigned* sPar = reinterpret_cast<unsigned*>(sC + G * 3 * n2);    // [G][rows] parity bits along z per xy-column
 	int* sInfo = reinterpret_cast<int*>(sPar + G * rows);             // [G][4] triOff, triCnt, colOff, colCnt
+	unsigned* sSat = reinterpret_cast<unsigned*>(sInfo + G * 4);      // [G][rows] SAT hit bits along x per row
+	uint2* sQueue = reinterpret_cast<uint2*>(sSat + G * rows + ((G * 3 * n2) & 1)); // [8 warps][64] (item|plo|phi, triangle), 8-byte aligned
 	const int tid = threadIdx.x;
 	const long long b0 = (long long)blockIdx.x * G;
 
@@ -602,33 +610,81 @@ __global__ void __launch_bounds__(kL2Threads) k_l2(GridP g, L2IO io)
 			load_ray(s, io.ray48, io.colTris[inf[2] + k]);
 			RayCol rc;
 			if (!s.ok || !ray_column(s, ox, oy, rc)) continue;
-			for (int r = 0; r < n2; r++) par ^= (unsigned)ray_cell(s, rc, c[2 * n2 + r]) << r;
+			const int run = ray_z_run(s, rc, s.well, c[2 * n2], c[3 * n2 - 1]); // the whole cell below / above the crossing?
+			if (run == 0) continue;
+			if (run == 1) par ^= n2 == 32 ? 0xffffffffu : ((1u << n2) - 1);
+			else for (int r = 0; r < n2; r++) par ^= (unsigned)ray_cell(s, rc, c[2 * n2 + r]) << r;
 		}
 		sPar[item] = par;
 	}
 	__syncthreads();
 
-	// ---- phase 2: SAT per row of n2 sub-voxels, then the row's file bytes
+	// ---- phase 2a: SAT.  Cheap pass: every (row, triangle) pair gets the certified plane interval (gpv::plane_row_interval,
+	// ~12 instructions); pairs that can still hit are compacted into a per-warp queue (ballot/popc) and the expensive part
+	// -- the hoisted row set-up plus the exact test of the few sub-voxels inside the interval -- runs on full warps of
+	// queue entries, whatever rows and triangles they came from.  Hits are OR-ed into the row's bit mask in shared memory.
+	for (int item = tid; item < G * rows; item += kL2Threads) sSat[item] = 0;
+	__syncthreads();
+	{
+		const int lane = tid & 31;
+		uint2* queue = sQueue + (tid >> 5) * 64;
+		const float inv2h = 1.f / (2.f * g.h2x);
+		auto heavy = [&](uint2 e) {
+			const int item = (int)(e.x & 0xffffu), plo = (int)((e.x >> 16) & 0xffu), phi = (int)(e.x >> 24);
+			const int gi = item / rows, row = item - gi * rows, r = row / n2, q = row - r * n2;
+			const float* c = sC + gi * 3 * n2;
+			const float4 A = __ldg(io.tri48 + (size_t)e.y * 3), B = __ldg(io.tri48 + (size_t)e.y * 3 + 1), C = __ldg(io.tri48 + (size_t)e.y * 3 + 2);
+			SatRow s;
+			if (!sat_row_setup(s, c[n2 + q], c[2 * n2 + r], g.h2y, g.h2z, A.y, A.z, B.y, B.z, C.y, C.z)) return;
+			unsigned bits = 0;
+			for (int p = plo; p <= phi; p++) bits |= (unsigned)sat_row_test(s, c[p], g.h2x, g.h2y, g.h2z, A.x, B.x, C.x) << p;
+			if (bits) atomicOr(sSat + item, bits);
+		};
+		for (int itemBase = 0; itemBase < G * rows; itemBase += kL2Threads) { // one round unless n2 = 32
+			const int item = itemBase + tid;
+			int triOff = 0, triCnt = 0;
+			float c0 = 0.f, cy2 = 0.f, cz2 = 0.f, slack = 0.f;
+			if (item < G * rows) {
+				const int gi = item / rows, row = item - gi * rows, r = row / n2, q = row - r * n2;
+				const float* c = sC + gi * 3 * n2;
+				c0 = c[0]; cy2 = c[n2 + q]; cz2 = c[2 * n2 + r];
+				slack = 9.5367431640625e-07f * (fabsf(c0) + 2.f * g.gsx); // 16u(|mid_x| + gs_x) >= |(c_p - c_0) - 2*h2x*p|
+				triOff = sInfo[gi * 4]; triCnt = sInfo[gi * 4 + 1];        // 0 for cells past the end
+			}
+			const int maxCnt = __reduce_max_sync(0xffffffffu, triCnt);
+			int qn = 0;
+			for (int k = 0; k < maxCnt; k++) {
+				bool alive = false;
+				int plo = 0, phi = -1, t = 0;
+				if (k < triCnt) {
+					t = io.cellTris[triOff + k];
+					const float4 A = __ldg(io.tri48 + (size_t)t * 3), pl = __ldg(io.plane16 + t);
+					PlaneRec P; P.sx = pl.x; P.ny = pl.y; P.nz = pl.z; P.R = pl.w;
+					alive = plane_row_interval(P, A.x - c0, A.y - cy2, A.z - cz2, inv2h, slack, n2, plo, phi);
+				}
+				const unsigned m = __ballot_sync(0xffffffffu, alive);
+				if (alive) queue[qn + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)item | ((unsigned)plo << 16) | ((unsigned)phi << 24), (unsigned)t);
+				qn += __popc(m);
+				__syncwarp();
+				if (qn >= 32) {
+					qn -= 32;
+					heavy(queue[qn + lane]);
+					__syncwarp();
+				}
+			}
+			if (lane < qn) heavy(queue[lane]);
+			__syncwarp();
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 2b: the row's file bytes
 	unsigned long long nIn = 0, nBd = 0;
 	for (int item = tid; item < G * rows; item += kL2Threads) {
 		int gi = item / rows, row = item - gi * rows, r = row / n2, q = row - r * n2;
 		long long b = b0 + gi;
 		if (b >= io.nBoundary) continue;
-		const float* c = sC + gi * 3 * n2;
-		const float cy2 = c[n2 + q], cz2 = c[2 * n2 + r];
-		const int* inf = sInfo + gi * 4;
-		unsigned sat = 0;
-		const unsigned full = n2 == 32 ? 0xffffffffu : ((1u << n2) - 1);
-		for (int k = 0; k < inf[1] && sat != full; k++) {
-			int t = io.cellTris[inf[0] + k];
-			float4 A = __ldg(io.tri48 + (size_t)t * 3), B = __ldg(io.tri48 + (size_t)t * 3 + 1), C = __ldg(io.tri48 + (size_t)t * 3 + 2);
-			SatRow s;
-			if (!sat_row_setup(s, cy2, cz2, g.h2y, g.h2z, A.y, A.z, B.y, B.z, C.y, C.z)) continue;
-			for (int p = 0; p < n2; p++) {
-				if ((sat >> p) & 1) continue;
-				if (sat_row_test(s, c[p], g.h2x, g.h2y, g.h2z, A.x, B.x, C.x)) sat |= 1u << p;
-			}
-		}
+		const unsigned sat = sSat[item];
 		unsigned par = 0;
 		const unsigned* pr = sPar + gi * rows + q * n2;
 		for (int p = 0; p < n2; p++) par |= ((pr[p] >> r) & 1u) << p;

@@ -149,11 +149,64 @@ GPV_HD bool sat_row_test(const SatRow& s, float cx, float hx, float hy, float hz
 	return true;
 }
 
+// ---- certified plane culling for the Level-2 SAT (DESIGN.md "Certified plane culling").
+// The plane predicate of the SAT (planeBoxOverlapCUDA, cu:157-179) passes only if |N.(t0 - c)| <= r with N = e0 x e1 and
+// r = sum |N_q| h_q -- in exact arithmetic.  In the reference's f32 arithmetic the two dot products it compares with 0 differ
+// from -r -/+ N.(t0-c) by at most 488 u M^3 (u = 2^-24, M = bound on every translated coordinate of the triangle seen from
+// any sub-voxel centre of a Level-1 cell the triangle overlaps); our own f32 evaluation of the left side adds < 500 u M^3.
+// With E = 2048 u M^3 = 2^-13 M^3:   |N.(t0 - c)| > r + E   ==>   the reference's plane predicate FAILS.
+// Along a row of sub-voxels (fixed cy, cz) N.(t0 - c_p) = D0 - Nx * s_p with s_p = c_p - c_0, so the sub-voxels that can
+// pass form an index interval.  The record is normalised by Nx so that the interval needs no division per row:
+//   x = 1: (1, Ny/Nx, Nz/Nx, (r+E)/|Nx|)      x = 0: Nx too small to normalise, (0, Ny, Nz, r+E): whole row or nothing
+//   w = +inf: no culling (degenerate magnitudes)
+struct PlaneRec { float sx, ny, nz, R; };
+
+GPV_HD PlaneRec plane_rec_setup(float t0x, float t0y, float t0z, float t1x, float t1y, float t1z, float t2x, float t2y, float t2z,
+                                float gsx, float gsy, float gsz, float hx, float hy, float hz)
+{
+	PlaneRec p;
+	float e0x = t1x - t0x, e0y = t1y - t0y, e0z = t1z - t0z, e1x = t2x - t1x, e1y = t2y - t1y, e1z = t2z - t1z;
+	float Nx = e0y * e1z - e0z * e1y, Ny = e0z * e1x - e0x * e1z, Nz = e0x * e1y - e0y * e1x;
+	float ex = fmaxf(t0x, fmaxf(t1x, t2x)) - fminf(t0x, fminf(t1x, t2x));
+	float ey = fmaxf(t0y, fmaxf(t1y, t2y)) - fminf(t0y, fminf(t1y, t2y));
+	float ez = fmaxf(t0z, fmaxf(t1z, t2z)) - fminf(t0z, fminf(t1z, t2z));
+	float amax = fmaxf(fmaxf(fabsf(t0x), fmaxf(fabsf(t1x), fabsf(t2x))), fmaxf(fmaxf(fabsf(t0y), fmaxf(fabsf(t1y), fabsf(t2y))),
+	                                                                            fmaxf(fabsf(t0z), fmaxf(fabsf(t1z), fabsf(t2z)))));
+	float gmax = fmaxf(gsx, fmaxf(gsy, gsz));
+	float M = 1.01f * fmaxf(ex + gsx, fmaxf(ey + gsy, ez + gsz)) + 1e-6f * (amax + gmax);
+	float E = M * M * M * 1.220703125e-4f; // 2^-13
+	float R = fabsf(Nx) * hx + fabsf(Ny) * hy + fabsf(Nz) * hz + E;
+	p.sx = 0.f; p.ny = Ny; p.nz = Nz; p.R = R;
+	if (!(M > 1e-9f && M < 1e9f) || !(R <= kFltMax)) { p.R = INFINITY; return p; }
+	float inv = 1.f / Nx;
+	float ny = Ny * inv, nz = Nz * inv, Rn = R * fabsf(inv) * 1.000001f;
+	if (fabsf(Nx) > 1e-30f && fabsf(inv) <= kFltMax && fabsf(ny) <= kFltMax && fabsf(nz) <= kFltMax && Rn <= kFltMax) { p.sx = 1.f; p.ny = ny; p.nz = nz; p.R = Rn; }
+	return p;
+}
+
+// Index interval [plo,phi] of the sub-voxels of one row that can pass the plane predicate; false = none can.
+//   v0x0 = t0x - c_x[0], v0y = t0y - cy, v0z = t0z - cz (the translated first vertex at p = 0);
+//   inv2h = 1/(2*h2x); slack >= 6u(|mid_x| + gs_x) bounds |(c_p - c_0) - 2*h2x*p| (f32 rounding of the centre formula).
+GPV_HD bool plane_row_interval(const PlaneRec& pl, float v0x0, float v0y, float v0z, float inv2h, float slack, int n2, int& plo, int& phi)
+{
+	plo = 0; phi = n2 - 1;
+	if (!(pl.R <= kFltMax)) return true;
+	float D = pl.sx * v0x0 + pl.ny * v0y + pl.nz * v0z;
+	if (pl.sx == 0.f) return !(fabsf(D) > pl.R);
+	// floor/ceil already round outwards; the f32 error of the two bounds (<= 3u(|D|+R)) is inside the E budget folded into R
+	float lo = floorf((D - pl.R - slack) * inv2h), hi = ceilf((D + pl.R + slack) * inv2h);
+	if (!(lo == lo) || !(hi == hi)) return true;
+	if (lo > 0.f) plo = lo > (float)n2 ? n2 : (int)lo;
+	if (hi < (float)(n2 - 1)) phi = hi < -1.f ? -1 : (int)hi;
+	return plo <= phi;
+}
+
 // ---- Moller-Trumbore for the fixed direction D = (0,0,1), split by what each part depends on.
 // Exact for finite intermediates: the dropped terms are products with D's zero components, i.e. additions of +-0.
 struct RayTri { // per triangle
 	float v1x, v1y, v1z, e1x, e1y, e1z, e2x, e2y, e2z, det, inv;
-	bool ok; // false: |det| inside the epsilon band, or not finite -- the ray test can never return 1
+	bool ok;   // false: |det| inside the epsilon band, or not finite -- the ray test can never return 1
+	bool well; // det is well conditioned: whole z-runs can be decided by gpv::ray_z_run
 };
 GPV_HD void ray_tri_setup(RayTri& s, float t0x, float t0y, float t0z, float t1x, float t1y, float t1z, float t2x, float t2y, float t2z)
 {
@@ -163,6 +216,10 @@ GPV_HD void ray_tri_setup(RayTri& s, float t0x, float t0y, float t0z, float t1x,
 	s.det = s.e1x * (-s.e2y) + s.e1y * s.e2x; // P = D x e2 = (-e2y, e2x, 0)
 	float ad = fabsf(s.det);
 	s.ok = ad > kEps && ad <= kFltMax;
+	{
+		float S = fabsf(s.e1x * s.e2y) + fabsf(s.e1y * s.e2x);
+		s.well = s.ok && ad >= 9.765625e-4f * S && S <= kFltMax; // 2^-10
+	}
 	s.inv = 1.f / s.det;
 }
 struct RayCol { float c0, c1, c2; }; // per (triangle, xy origin)
@@ -184,6 +241,31 @@ GPV_HD bool ray_cell(const RayTri& s, const RayCol& c, float oz)
 	float Q1 = Tz * s.e1x - c.c1;
 	float t = (s.e2x * Q0 + s.e2y * Q1 + c.c2) * s.inv;
 	return t > kEps;
+}
+
+// ---- certified classification of a whole run of cells along one column (DESIGN.md "Certified z-runs").
+// For a (triangle, column) pair that passed ray_column, t as a function of the origin height is  t = alpha - Tz * (D/det') in
+// exact arithmetic on the f32 inputs, D the exact 2-D determinant.  When det' is well conditioned (|det'| >= 2^-10 * S,
+// S = |e1x*e2y| + |e1y*e2x|, flagged per triangle) the slope lies in [0.998, 1.002], so t falls monotonically with height.
+// ray_cell's f32 result differs from that exact t by at most bnd (16u times the magnitudes of its intermediates; the
+// actual rounding count is <= 5u per term).  Evaluating ray_cell ONCE at the lowest centre therefore decides the whole run:
+//   t0 + 2 bnd <= eps            -> no cell of the run is hit
+//   t0 - 2 bnd - 1.01 span > eps -> every cell of the run is hit
+// returns 0 / 1 for those, 2 when the cells must be evaluated one by one.
+GPV_HD int ray_z_run(const RayTri& s, const RayCol& c, bool wellConditioned, float ozLo, float ozHi)
+{
+	if (!wellConditioned) return 2;
+	const float TzLo = ozLo - s.v1z, TzHi = ozHi - s.v1z;
+	const float Tm = fmaxf(fabsf(TzLo), fabsf(TzHi));
+	const float Q0 = c.c0 - TzLo * s.e1y, Q1 = TzLo * s.e1x - c.c1;
+	const float t0 = (s.e2x * Q0 + s.e2y * Q1 + c.c2) * s.inv; // == what ray_cell computes at ozLo
+	const float span = (ozHi - ozLo) * 1.01f;
+	const float bnd = 9.5367431640625e-07f * (fabsf(s.inv) * (fabsf(s.e2x) * (fabsf(c.c0) + Tm * fabsf(s.e1y)) + fabsf(s.e2y) * (fabsf(c.c1) + Tm * fabsf(s.e1x)) + fabsf(c.c2)) +
+	                                          fabsf(t0) + span) + 1e-30f;
+	if (!(bnd <= kFltMax) || !(t0 == t0)) return 2;
+	if (t0 + 2.f * bnd <= kEps) return 0;
+	if (t0 - 2.f * bnd - span > kEps) return 1;
+	return 2;
 }
 
 // ---- certified candidate columns for the +Z parity fill of one triangle (DESIGN.md "Certified fill").

@@ -54,3 +54,69 @@ void probe_column(int64_t n, const float* oxy, const float* t, uint8_t* out)
 int probe_cell_of(float v, float mn, float mx, int n) { return cell_of(v, mn, mx, n); }
 int probe_encode_normal(float x) { return encode_normal(x); }
 }
+
+// ---- certified plane culling: for one Level-1 cell (centre mid, size gs, n2 sub-voxels per axis) and one triangle, walk
+// every row (q,r): returns the number of sub-voxels whose PLANE predicate (reference arithmetic) passes outside the
+// certified interval (must be 0), and counts how many sub-voxels the interval keeps / how many pass the plane / full SAT.
+static bool plane_pred_ref(float cx, float cy, float cz, float hx, float hy, float hz, const float* T)
+{
+	float v0x = T[0] - cx, v0y = T[1] - cy, v0z = T[2] - cz, v1x = T[3] - cx, v1y = T[4] - cy, v1z = T[5] - cz, v2x = T[6] - cx, v2y = T[7] - cy, v2z = T[8] - cz;
+	float e0x = v1x - v0x, e0y = v1y - v0y, e0z = v1z - v0z, e1x = v2x - v1x, e1y = v2y - v1y, e1z = v2z - v1z;
+	float nx = e0y * e1z - e0z * e1y, ny = e0z * e1x - e0x * e1z, nz = e0x * e1y - e0y * e1x;
+	float mnx = (nx > 0.0f) ? (-hx - v0x) : (hx - v0x), mxx = (nx > 0.0f) ? (hx - v0x) : (-hx - v0x);
+	float mny = (ny > 0.0f) ? (-hy - v0y) : (hy - v0y), mxy = (ny > 0.0f) ? (hy - v0y) : (-hy - v0y);
+	float mnz = (nz > 0.0f) ? (-hz - v0z) : (hz - v0z), mxz = (nz > 0.0f) ? (hz - v0z) : (-hz - v0z);
+	if (nx * mnx + ny * mny + nz * mnz > 0.0f) return false;
+	return nx * mxx + ny * mxy + nz * mxz >= 0.0f;
+}
+extern "C" void probe_plane_cull(int64_t n, const float* mid3, const float* gs3, int n2, const float* tri9, int64_t* out4)
+{
+	int64_t violations = 0, kept = 0, planePass = 0, satPass = 0;
+	for (int64_t i = 0; i < n; i++) {
+		const float *mid = mid3 + i * 3, *gs = gs3 + i * 3, *T = tri9 + i * 9;
+		float h1[3], h2[3], c[3][32];
+		for (int a = 0; a < 3; a++) {
+			h1[a] = gs[a] / 2.0; float g2 = gs[a] / (n2 * 1.0); h2[a] = g2 / 2.0;
+			for (int p = 0; p < n2; p++) c[a][p] = (float)(2 * p + 1) * h2[a] + mid[a] - h1[a];
+		}
+		PlaneRec pl = plane_rec_setup(T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8], gs[0], gs[1], gs[2], h2[0], h2[1], h2[2]);
+		float inv2h = 1.f / (2.f * h2[0]);
+		float slack = 9.5367431640625e-07f * (fabsf(mid[0]) + gs[0]); // 16u(|mid|+gs)
+		for (int r = 0; r < n2; r++) for (int q = 0; q < n2; q++) {
+			int plo, phi;
+			bool any = plane_row_interval(pl, T[0] - c[0][0], T[1] - c[1][q], T[2] - c[2][r], inv2h, slack, n2, plo, phi);
+			if (!any) { plo = 0; phi = -1; }
+			for (int p = 0; p < n2; p++) {
+				bool pp = plane_pred_ref(c[0][p], c[1][q], c[2][r], h2[0], h2[1], h2[2], T);
+				bool in = p >= plo && p <= phi;
+				kept += in; planePass += pp;
+				if (pp && !in) violations++;
+				if (pp && tri_box_overlap(c[0][p], c[1][q], c[2][r], h2[0], h2[1], h2[2], T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8])) satPass++;
+			}
+		}
+	}
+	out4[0] = violations; out4[1] = kept; out4[2] = planePass; out4[3] = satPass;
+}
+
+// ---- certified z-runs: for each (triangle, origin xy, run of nz centres z0 + k*dz) compare gpv::ray_z_run with the per-cell truth.
+// out3: [0] violations, [1] runs decided without per-cell work, [2] runs that passed the column test
+extern "C" void probe_z_run(int64_t n, const float* oxy, const float* zrun /* z0, dz per item */, int nz, const float* tri9, int64_t* out3)
+{
+	int64_t bad = 0, decided = 0, passed = 0;
+	for (int64_t i = 0; i < n; i++) {
+		const float* T = tri9 + i * 9;
+		RayTri s; RayCol rc;
+		ray_tri_setup(s, T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8]);
+		if (!s.ok || !ray_column(s, oxy[i * 2], oxy[i * 2 + 1], rc)) continue;
+		passed++;
+		float zs[64];
+		for (int k = 0; k < nz; k++) zs[k] = zrun[i * 2] + (float)k * zrun[i * 2 + 1];
+		int cls = ray_z_run(s, rc, s.well, zs[0], zs[nz - 1]);
+		int hits = 0;
+		for (int k = 0; k < nz; k++) hits += ray_cell(s, rc, zs[k]);
+		if (cls == 0 && hits != 0) bad++;
+		if (cls == 1 && hits != nz) bad++;
+		if (cls != 2) decided++;
+	}
+	out3[0] = bad; out3[1] = decided; out3[2] = passed;
+}

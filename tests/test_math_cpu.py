@@ -161,3 +161,66 @@ def test_cell_of_and_normal_encoding(probe):
     for x in np.linspace(-1, 1, 101).astype(np.float32):
         want = int(np.uint8(np.float32(np.float32(x * np.float32(256.0 / 3.0)) + np.float32(127.0))))
         assert probe.probe_encode_normal(C.c_float(float(x))) == want
+
+
+def test_certified_plane_culling_never_drops_a_passing_subvoxel(probe, oracle):
+    """The Level-2 kernel skips sub-voxels outside gpv::plane_row_interval.  Sweep cells x triangles over nine orders of
+    magnitude of coordinates / cell sizes / triangle sizes, slivers and axis-parallel planes included: no sub-voxel whose
+    plane predicate passes in the reference's f32 arithmetic may fall outside the interval."""
+    probe.probe_plane_cull.argtypes = [C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+    rng = np.random.default_rng(7)
+    total = np.zeros(4, np.int64)
+    for n2 in (2, 4, 8, 16):
+        n = 60000 if n2 < 16 else 25000
+        gs = (10.0 ** rng.uniform(-3, 1, (n, 1)) * rng.uniform(0.7, 1.3, (n, 3))).astype(np.float32)
+        off = 10.0 ** rng.uniform(-2, 4, (n, 1)) * rng.choice([-1, 1], (n, 3)) * rng.uniform(0, 1, (n, 3))
+        mid = (off * (rng.uniform(0, 1, (n, 1)) < 0.7)).astype(np.float32)
+        size = 10.0 ** rng.uniform(-2, 2, (n, 1, 1)) * gs[:, None, :]
+        ctr = mid[:, None, :] + rng.uniform(-0.7, 0.7, (n, 1, 3)) * gs[:, None, :]
+        tri = (ctr + rng.normal(0, 1, (n, 3, 3)) * size).astype(np.float32)
+        k = n // 6
+        tri[:k, :, 0] = tri[:k, :1, 0] + (rng.normal(0, 1e-4, (k, 3)) * gs[:k, :1]).astype(np.float32)         # plane ~ perpendicular to x
+        tri[k:2 * k, :, 2] = tri[k:2 * k, :1, 2]                                                              # Nx = Ny = 0 exactly
+        a = rng.uniform(0, 1, (k, 1))
+        tri[2 * k:3 * k, 2] = (tri[2 * k:3 * k, 0] + (tri[2 * k:3 * k, 1] - tri[2 * k:3 * k, 0]) * a).astype(np.float32)  # slivers
+        tri[3 * k:4 * k, :, 1] = tri[3 * k:4 * k, :1, 1] + (rng.normal(0, 1e-6, (k, 3)) * gs[3 * k:4 * k, 1:2]).astype(np.float32)  # Nx ~ 0
+        tri = np.ascontiguousarray(tri.reshape(n, 9))
+        # keep only triangles that overlap their Level-1 cell (the kernel only ever sees those)
+        keep = oracle.tribox_batch(mid, (gs / np.float32(2.0)).astype(np.float32), tri).astype(bool)
+        mid_k, gs_k, tri_k = np.ascontiguousarray(mid[keep]), np.ascontiguousarray(gs[keep]), np.ascontiguousarray(tri[keep])
+        out = np.zeros(4, np.int64)
+        probe.probe_plane_cull(len(mid_k), _fp(mid_k), _fp(gs_k), n2, _fp(tri_k), out.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert out[0] == 0, (n2, out)
+        print('n2=%d: kept %d, plane-pass %d, SAT-pass %d of %d sub-voxels' % (n2, out[1], out[2], out[3], len(mid_k) * n2 ** 3))
+        total += out
+    assert total[2] > 1000000 and total[3] > 100000        # the sweep exercised plenty of passing sub-voxels
+    assert total[1] < 4 * total[2]                         # and the interval is not vacuous: it keeps < 4x what passes
+    print("plane culling: kept %d sub-voxels, %d pass the plane predicate, %d the full SAT" % (total[1], total[2], total[3]))
+
+
+def test_certified_z_runs_agree_with_per_cell_evaluation(probe):
+    """gpv::ray_z_run decides a whole run of cells along a column from one evaluation; whenever it does, the per-cell
+    ray_cell results must all agree (no hit at all / every cell hit).  Origins are placed inside the triangle's projection
+    so that the column test passes; near-vertical, huge-coordinate and plane-grazing cases included."""
+    probe.probe_z_run.argtypes = [C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+    rng = np.random.default_rng(11)
+    tot = np.zeros(3, np.int64)
+    for nz in (2, 4, 16, 32):
+        n = 400000
+        scale = 10.0 ** rng.uniform(-2, 3, (n, 1, 1))
+        tri = (rng.normal(0, 1, (n, 3, 3)) * scale + rng.normal(0, 1, (n, 1, 3)) * scale * rng.choice([0, 1, 30], (n, 1, 1))).astype(np.float32)
+        k = n // 5
+        tri[:k, 2, :2] = (tri[:k, 0, :2] + (tri[:k, 1, :2] - tri[:k, 0, :2]) * rng.uniform(0, 1, (k, 1)) +
+                          rng.normal(0, 1e-4, (k, 2)) * scale[:k, 0]).astype(np.float32)          # near-vertical: tiny 2-D determinant
+        w = rng.dirichlet([1, 1, 1], n).astype(np.float32)
+        o = (tri * w[:, :, None]).sum(1)                                                           # a point of the triangle
+        oxy = np.ascontiguousarray(o[:, :2], np.float32)
+        dz = (10.0 ** rng.uniform(-3, 0, n) * scale[:, 0, 0]).astype(np.float32)
+        z0 = (o[:, 2] - dz * rng.uniform(-1.5 * nz, 2.5 * nz, n) * (rng.uniform(0, 1, n) < 0.8)).astype(np.float32)  # runs below / across / above / grazing
+        zrun = np.ascontiguousarray(np.stack([z0, dz], -1), np.float32)
+        out = np.zeros(3, np.int64)
+        probe.probe_z_run(n, _fp(oxy), _fp(zrun), nz, _fp(np.ascontiguousarray(tri.reshape(n, 9))), out.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert out[0] == 0, (nz, out)
+        tot += out
+    assert tot[2] > 400000 and tot[1] > 0.3 * tot[2], tot
+    print("z-runs: %d column-passing pairs, %d decided from one evaluation" % (tot[2], tot[1]))
