@@ -180,19 +180,6 @@ def workload_config(args):
             "cache": "L2 flushed between timed steps (256 MiB memset); outputs (>=221 MB at 256/16) exceed L2"}
 
 
-def slab_cuts(per_layer_cost, R):
-    """cut z into R contiguous slabs of ~equal cost (deterministic; every rank computes the same cuts)"""
-    c = np.concatenate([[0], np.cumsum(per_layer_cost.astype(np.float64))])
-    nz = len(per_layer_cost)
-    cuts = [0]
-    for r in range(1, R):
-        z = int(np.searchsorted(c, c[-1] * r / R))
-        z = min(max(z, cuts[-1] + 1), nz - (R - r))
-        cuts.append(z)
-    cuts.append(nz)
-    return cuts
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -231,69 +218,24 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     # ---- z-slab plan (N > 1): replicated Level-1 pre-pass gives per-layer Level-2 cost; cuts are deterministic
+    from gpview_b200 import sharded
     z0, z1 = 0, 0
     whole = ctx.voxelize_device(d_tris, mesh, gpv.Params(args.l1, args.l2, gpv.GPV_NO_LEVEL2), sptr)
     nz = int(whole.num_div[2]); plane = int(whole.num_div[0]) * int(whole.num_div[1])
-    total_tests = None
     if world > 1:
-        bi = whole.boundary_index()
-        off = whole.cell_off().astype(np.int64)
-        cost = np.bincount(bi // plane, weights=(off[1:] - off[:-1]) + 8.0, minlength=nz)
-        cuts = slab_cuts(cost, world)
+        cuts = sharded.plan_slabs(sharded.layer_cost(whole.boundary_index(), whole.cell_off(), plane, nz), world)
         z0, z1 = cuts[rank], cuts[rank + 1]
     params = gpv.Params(args.l1, args.l2, gpv.GPV_PROFILE, z0, z1)  # CUDA events around every kernel, on the launching stream
     phase_acc = {}
-
-    def wrap(ptr, nbytes):
-        class P:
-            pass
-        p = P()
-        p.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
-        return torch.as_tensor(p, device="cuda")
-
     gathered = {}
-
-    def gather(res):
-        """slab pieces -> rank 0 (concatenation only): sizes by all_gather, payload by batched send/recv"""
-        sizes = torch.tensor([res.cells, res.nb], device="cuda", dtype=torch.int64)
-        allsz = [torch.empty_like(sizes) for _ in range(world)]
-        dist.all_gather(allsz, sizes)
-        allsz = torch.stack(allsz).cpu().numpy()
-        n23 = res.n23
-        streams = [("l1", res.c.d_level1_inout, 1, 0), ("pre", res.c.d_prefix, 4, 0), ("l2", res.c.d_level2_inout, n23, 1)]
-        ops = []
-        for name, ptr, unit, which in streams:
-            mine = wrap(ptr, int(allsz[rank][which]) * unit) if int(allsz[rank][which]) else torch.empty(0, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                tot = int(allsz[:, which].sum()) * unit
-                if name not in gathered or gathered[name].numel() < tot:
-                    gathered[name] = torch.empty(tot, dtype=torch.uint8, device="cuda")
-                o = 0
-                for r in range(world):
-                    nby = int(allsz[r][which]) * unit
-                    if r == 0:
-                        gathered[name][o:o + nby].copy_(mine, non_blocking=True)
-                    elif nby:
-                        ops.append(dist.P2POp(dist.irecv, gathered[name][o:o + nby], r))
-                    o += nby
-            elif mine.numel():
-                ops.append(dist.P2POp(dist.isend, mine, 0))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        if rank == 0:  # slab-local prefix sums -> global: add the boundary counts of the lower slabs
-            o = 0; base = 0
-            pre = gathered["pre"].view(torch.int32)
-            for r in range(world):
-                ncell = int(allsz[r][0])
-                if base:
-                    pre[o:o + ncell] += base
-                o += ncell; base += int(allsz[r][1])
 
     def step():
         res = ctx.voxelize_device(d_tris, mesh, params, sptr)
-        if world > 1:
-            gather(res)
+        if world > 1:  # slab pieces -> rank 0 over NCCL (concatenation only), inside the timed region
+            w = lambda ptr, n: sharded.wrap_device_bytes(torch, ptr, n)
+            pieces = {"l1": (w(res.c.d_level1_inout, res.cells), 1, 0), "prefix": (w(res.c.d_prefix, res.cells * 4), 4, 0),
+                      "l2": (w(res.c.d_level2_inout, res.nb * res.n23), res.n23, 1)}
+            sharded.gather_to_rank0(dist, torch, rank, world, pieces, res.cells, res.nb, gathered)
         return res
 
     def barrier():

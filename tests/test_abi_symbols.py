@@ -1,0 +1,66 @@
+"""The C-ABI library loads without a GPU and exports exactly the symbols include/gpview_b200.h declares (no compute calls)."""
+import os
+import re
+import subprocess
+
+from util import ROOT
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "gpview_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", src)))
+
+
+def test_header_and_binding_agree(product):
+    from gpview_b200 import binding
+    declared = header_functions()
+    assert sorted(binding.NATIVE_SYMBOLS + binding.COMPAT_SYMBOLS) == declared
+
+
+def test_library_exports_every_declared_symbol(product):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", product.LIB_PATH], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [f for f in header_functions() if f not in exported]
+    assert not missing, missing
+
+
+def test_compat_symbols_are_unmangled_c(product):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", product.LIB_PATH], text=True)
+    for name in ("CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"):
+        assert re.search(r" T %s$" % name, out, flags=re.M), name
+
+
+def test_no_cpu_fallback(product):
+    """Without a device the native tier refuses to create a context instead of computing on the host."""
+    L = product.lib()
+    if L.gpv_device_count() > 0:
+        return
+    try:
+        product.Context(0)
+    except product.GpvError as e:
+        assert "no CPU fallback" in str(e) or "CUDA" in str(e)
+    else:
+        raise AssertionError("gpv_create succeeded without a GPU")
+
+
+def test_only_sm100a_code_in_the_library(product):
+    out = subprocess.run(["cuobjdump", "-lelf", product.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under gpview_b200/ or include/ may import, link or execute it."""
+    bad = []
+    for base in ("gpview_b200", "include"):
+        for d, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                    txt = open(os.path.join(d, f), errors="replace").read()
+                    for m in re.finditer(r"^.*(?:import|include|from|dlopen|CDLL|-l|-L).*\boracle\b.*$", txt, flags=re.M):
+                        line = m.group(0).strip()
+                        if line.startswith(("//", "#", "*", '"""')) or "oracle/gpv_oracle.c gpvo_axis_table" in line:
+                            continue
+                        bad.append((f, line))
+    assert not bad, bad

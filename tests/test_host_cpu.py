@@ -1,0 +1,130 @@
+"""Host side of the native tier on the CPU: loaders with Object::ReadObject / ReadOFFObject semantics, grid sizing of
+Object::PerformVoxelization, and the Object::SaveVoxelization file contract -- product (gpv_*) vs oracle, and vs the
+reference itself in the build container.  No compute entry point is called (no GPU here)."""
+import ctypes as C
+import filecmp
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLDEN_CASES, HAVE_REF, REF, golden, mesh_path
+
+
+def _same_mesh(a, b):
+    return (np.array_equal(a.tris, b.tris) and np.array_equal(np.asarray(a.bbox_min if hasattr(a, "bbox_min") else a.bmin), b.bmin)
+            and np.array_equal(np.asarray(a.bbox_max if hasattr(a, "bbox_max") else a.bmax), b.bmax))
+
+
+@pytest.mark.parametrize("name", ["cessna", "sphere", "torus", "block", "cad"])
+def test_loader_matches_oracle(product, oracle, tmp_path_factory, name):
+    path = mesh_path(name, tmp_path_factory.getbasetemp())
+    pm, om = product.load_mesh(path), oracle.OracleMesh(path)
+    assert pm.ntri == om.ntri and _same_mesh(pm, om)
+    assert pm.max_model_size == om.max_model_size
+
+
+OBJ_QUIRKS = {
+    # the reference splits on single ' ' OR single '\\t' (whichever yields more fields), reads "a/b/c" faces, keeps stale
+    # coordinates on short `v` lines, takes the bbox over ALL `v` lines and drops an unterminated last line (App. B9)
+    "tabs": "v\t0\t0\t0\nv\t1\t0\t0\nv\t0\t1\t0\nv\t0\t0\t1\nf\t1\t2\t3\nf\t1\t2\t4\n",
+    "slashes": "v 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nvn 0 0 1\nvt 0 0\nf 1/1/1 2/1/1 3/1/1\nf 1//1 2//1 4//1\nf 2/1 3/1 4/1\n",
+    "unreferenced_vertex_in_bbox": "v 0 0 0\nv 1 0 0\nv 0 1 0\nv 9 9 9\nf 1 2 3\n",
+    "no_final_newline": "v 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nf 1 2 3\nf 1 2 4",
+    "crlf": "v 0 0 0\r\nv 1 0 0\r\nv 0 1 0\r\nf 1 2 3\r\n",
+    "comments_and_groups": "# c\no obj\ng grp\nv 0 0 0\nv 1.5e0 0 0\nv 0 2.25 0\nusemtl m\ns off\nf 1 2 3\n",
+    "short_vertex_line": "v 1 2 3\nv 4 5\nv 0 0 0\nf 1 2 3\n",
+}
+
+
+@pytest.mark.parametrize("case", sorted(OBJ_QUIRKS))
+def test_obj_quirks(product, oracle, tmp_path, case):
+    p = tmp_path / (case + ".obj")
+    p.write_bytes(OBJ_QUIRKS[case].encode())
+    pm, om = product.load_mesh(str(p)), oracle.OracleMesh(str(p))
+    assert pm.ntri == om.ntri and _same_mesh(pm, om)
+    if case == "no_final_newline":
+        assert pm.ntri == 1
+    if case == "unreferenced_vertex_in_bbox":
+        assert pm.bbox_max[0] > 9
+    if case == "short_vertex_line":
+        assert list(pm.tris[0][3:6]) == [4, 5, 3]
+    if HAVE_REF:
+        from oracle import refbind
+        ro = refbind.RefObject(str(p))
+        assert np.array_equal(ro.tris, pm.tris) and np.array_equal(ro.bmin, pm.bbox_min) and np.array_equal(ro.bmax, pm.bbox_max)
+        ro.close()
+
+
+def test_obj_errors_are_reported_not_aborted(product, tmp_path):
+    for name, txt in {"double_space": "v 0  0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n", "bad_index": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n",
+                      "empty": "\n"}.items():
+        p = tmp_path / (name + ".obj")
+        p.write_text(txt)
+        with pytest.raises(product.GpvError):
+            product.load_mesh(str(p))
+    with pytest.raises(product.GpvError):
+        product.load_mesh(str(tmp_path / "missing.obj"))
+    with pytest.raises(product.GpvError):
+        product.load_mesh(str(tmp_path / "mesh.stl"))
+
+
+def test_off_reads_exactly_three_indices_and_bbox_over_referenced(product, oracle, tmp_path):
+    p = tmp_path / "q.off"
+    p.write_text("OFF\n5 2 0\n0 0 0\n1 0 0\n0 1 0\n0 0 1\n50 50 50\n3 0 1 2\n3 0 1 3\n")
+    pm, om = product.load_mesh(str(p)), oracle.OracleMesh(str(p))
+    assert pm.ntri == 2 and _same_mesh(pm, om)
+    assert pm.bbox_max[0] < 2          # vertex 4 is not referenced: OFF bbox ignores it (src/Object.cpp:257-266)
+    p2 = tmp_path / "oneline.off"
+    p2.write_text("OFF 4 2 0 0 0 0 1 0 0 0 1 0 0 0 1 3 0 1 2 3 0 1 3")
+    assert product.load_mesh(str(p2)).ntri == 2
+
+
+@pytest.mark.parametrize("name,l1,l2", GOLDEN_CASES)
+def test_grid_sizing_matches_reference_fixture(product, tmp_path_factory, name, l1, l2):
+    info, _ = golden("%s_%d_%d" % (name, l1, l2))
+    m = product.load_mesh(mesh_path(name, tmp_path_factory.getbasetemp()))
+    g = product.grid_for(m.bbox_min, m.bbox_max, m.max_model_size, l1, l2)
+    assert list(g.num_div) == info["num_div"]
+    assert [np.float32(x).tobytes().hex() for x in g.grid_size] == info["grid_size_hex"]
+    assert [float(np.float32(x)) for x in g.grid_size2] == pytest.approx(info["grid_size2"], rel=0, abs=0)
+
+
+def test_grid_sizing_fuzz_vs_oracle(product, oracle):
+    rng = np.random.default_rng(9)
+    for _ in range(300):
+        lo = rng.uniform(-100, 100, 3).astype(np.float32)
+        hi = (lo + 10.0 ** rng.uniform(-3, 3, 3)).astype(np.float32)
+        ms = np.float32(np.max(hi - lo))
+        l1, l2 = int(rng.integers(1, 1500)), int(rng.integers(1, 33))
+        a, b = product.grid_for(lo, hi, ms, l1, l2), oracle.make_grid(lo, hi, ms, l1, l2)
+        assert list(a.num_div) == list(b.numDiv) and list(a.grid_size) == list(b.gridSize) and list(a.grid_size2) == list(b.gridSize2)
+        assert list(a.ext1) == list(b.ext1) and list(a.ext2) == list(b.ext2)
+
+
+def test_save_writes_the_reference_file_contract(product, oracle, tmp_path_factory, tmp_path):
+    """gpv_save from host streams == the oracle's writer == (build container) Object::SaveVoxelization, byte for byte."""
+    from gpview_b200 import binding as B
+    path = mesh_path("torus", tmp_path_factory.getbasetemp())
+    pm = product.load_mesh(path)
+    r = oracle.OracleMesh(path).voxelize(32, 4, oracle.FILL_CERTIFIED, 4)
+    res = B.CResult()
+    res.grid = product.grid_for(pm.bbox_min, pm.bbox_max, pm.max_model_size, 32, 4)
+    res.cells, res.n_boundary, res.n23 = r.cells, r.nb, r.n23
+    res.l1_inside, res.l1_boundary, res.l2_inside, res.l2_boundary = r.counts
+    l1 = (r.l1_state * 127).astype(np.uint8); l2 = (r.l2_state * 127).astype(np.uint8)
+    keep = [l1, r.prefix, l2, r.l1_normal, r.l2_normal]
+    hs = B.CHostStreams(l1.ctypes.data, r.prefix.ctypes.data, None, l2.ctypes.data, r.l1_normal.ctypes.data, r.l2_normal.ctypes.data, l2.nbytes, 0)
+    d1, d2 = tmp_path / "gpv", tmp_path / "ora"
+    d1.mkdir(); d2.mkdir()
+
+    class R:  # minimal stand-in for binding.Result
+        c = res
+    B.save(pm, R, hs, -1, str(d1))
+    r.save(-1, str(d2))
+    names = sorted(os.listdir(d1))
+    assert names == ["Obj-1Level1BoundaryPrefixSum.raw", "Obj-1Level1InOut.raw", "Obj-1Level1Normal.raw", "Obj-1Level2InOut.raw",
+                     "Obj-1Level2Normal.raw", "Obj-1VoxelConfig.txt"]
+    for n in names:
+        assert filecmp.cmp(d1 / n, d2 / n, shallow=False), n
+    assert keep

@@ -1,0 +1,80 @@
+"""N > 1 host logic on CPU: world_size-2 and -3 gloo groups run gpview_b200.sharded (slab plan + gather to rank 0); each rank's
+"slab result" is cut out of the oracle's whole-grid result (the definition of a correct slab), the gathered
+streams on rank 0 must equal the whole."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from util import mesh_path
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, path, l1, l2, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gpview_b200 import sharded
+        from oracle import oraclebind as O
+        r = O.OracleMesh(path).voxelize(l1, l2, O.FILL_CERTIFIED | O.NO_NORMALS, 1)
+        nx, ny, nz = [int(x) for x in r.num_div]
+        plane = nx * ny
+        off = np.concatenate([[0], np.cumsum(r.cell_count[r.boundary_index])])
+        cuts = sharded.plan_slabs(sharded.layer_cost(r.boundary_index, off, plane, nz), world)
+        z0, z1 = cuts[rank], cuts[rank + 1]
+        c0, c1 = z0 * plane, z1 * plane
+        b0, b1 = int(r.prefix[c0]), int(r.prefix[c1]) if c1 < r.cells else r.nb
+        l1s = torch.from_numpy((r.l1_state[c0:c1] * 127).astype(np.uint8))
+        pre = torch.from_numpy((r.prefix[c0:c1] - b0).astype(np.int32)).view(torch.uint8)     # slab-local, like the C ABI
+        l2s = torch.from_numpy((r.l2_state[b0 * r.n23:b1 * r.n23] * 127).astype(np.uint8))
+        pieces = {"l1": (l1s, 1, 0), "prefix": (pre, 4, 0), "l2": (l2s, r.n23, 1)}
+        out, sizes = sharded.gather_to_rank0(dist, torch, rank, world, pieces, c1 - c0, b1 - b0)
+        if rank == 0:
+            ok = (np.array_equal(out["l1"].numpy(), r.l1_state * 127) and np.array_equal(out["prefix"].view(torch.int32).numpy(), r.prefix)
+                  and np.array_equal(out["l2"].numpy(), r.l2_state * 127) and int(sizes[:, 1].sum()) == r.nb and cuts[0] == 0 and cuts[-1] == nz)
+            q.put(("ok" if ok else "mismatch", cuts))
+    except Exception as e:  # pragma: no cover
+        if rank == 0:
+            q.put(("error: %r" % (e,), None))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_reassembles_the_whole_grid(tmp_path_factory, world):
+    path = mesh_path("cessna", tmp_path_factory.getbasetemp())
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, path, 32, 4, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    status, cuts = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert status == "ok", status
+    assert len(cuts) == world + 1 and all(b > a for a, b in zip(cuts, cuts[1:]))
+
+
+def test_plan_slabs_balances_cost():
+    from gpview_b200 import sharded
+    rng = np.random.default_rng(0)
+    cost = rng.uniform(0, 1, 256) ** 4
+    for world in (1, 2, 4, 8):
+        cuts = sharded.plan_slabs(cost, world)
+        assert cuts[0] == 0 and cuts[-1] == 256 and len(cuts) == world + 1
+        per = [cost[a:b].sum() for a, b in zip(cuts, cuts[1:])]
+        assert max(per) <= cost.sum() / world + cost.max() + 1e-9
+    assert sharded.plan_slabs(np.zeros(8), 8) == list(range(9))
+    with pytest.raises(ValueError):
+        sharded.plan_slabs(np.ones(4), 5)
