@@ -475,7 +475,9 @@ __global__ void __launch_bounds__(256) k_compat_l2_sat(const float* __restrict__
 	int cell = l2Index[b], nT = triCount[cell], first = triFlatIndex[cell];
 	float cxv, cyv, czv;
 	compat_l2_centre(loc, n2, mid, b, e1, e2, cxv, cyv, czv);
-	float ax = l2Normal[v * 4], ay = l2Normal[v * 4 + 1], az = l2Normal[v * 4 + 2], an = l2Normal[v * 4 + 3];
+	// The accumulators start from ZERO whatever the buffer holds: the reference's caller zeroes only a quarter of it
+	// (cudaMemset with element counts, src/Object.cpp:2595-2596); zero-initialised is the intended semantics.
+	float ax = 0.f, ay = 0.f, az = 0.f, an = 0.f;
 	bool hit = false;
 	for (int k = 0; k < nT; k++) {
 		const float* d = tris + (size_t)triFlat[first + k] * 9;
@@ -485,7 +487,8 @@ __global__ void __launch_bounds__(256) k_compat_l2_sat(const float* __restrict__
 			ax += uy * wz - uz * wy; ay += uz * wx - ux * wz; az += ux * wy - uy * wx; an += 1; // cu:40-46, 311-318
 		}
 	}
-	if (hit) { l2InOut[v] = 2; l2Normal[v * 4] = ax; l2Normal[v * 4 + 1] = ay; l2Normal[v * 4 + 2] = az; l2Normal[v * 4 + 3] = an; }
+	if (hit) l2InOut[v] = 2;
+	l2Normal[v * 4] = ax; l2Normal[v * 4 + 1] = ay; l2Normal[v * 4 + 2] = az; l2Normal[v * 4 + 3] = an;
 }
 
 __global__ void __launch_bounds__(256) k_compat_l2_ray(const float* __restrict__ tris, float* l2InOut, const float* __restrict__ mid, const int* __restrict__ l2Index,
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(256) k_compat_l2_ray(const float* __restrict__
 		ray_tri_setup(s, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8]);
 		n += s.ok && ray_column(s, cxv, cyv, rc) && ray_cell(s, rc, czv);
 	}
-	if (n % 2 == 1) l2InOut[v] = 1; // cu:497-501
+	l2InOut[v] = (n % 2 == 1) ? 1.f : 0.f; // cu:497-501; every voxel is written (0 = the intended zero-initialisation, App. B2)
 }
 
 __global__ void __launch_bounds__(256) k_max_reduce(const float* __restrict__ in, long long n, float* out)
@@ -529,6 +532,8 @@ __global__ void __launch_bounds__(256) k_max_reduce(const float* __restrict__ in
 extern "C" int CUDAClassifyTessellation(float* tris, int nTri, float* inOut, int* count, int* triIndex, gpv_float3 mn, gpv_float3 mx, gpv_float3 ext,
                                         gpv_int3 nd, int bufLen)
 {
+	// the reference's caller zeroes only cells BYTES of the int counter array (src/Object.cpp:2110, App. B1): zero all of it
+	cudaMemsetAsync(count, 0, (size_t)nd.x * nd.y * nd.z * sizeof(int));
 	if (nTri > 0) k_compat_l1<<<(nTri + 127) / 128, 128>>>(tris, nTri, inOut, count, triIndex, mn, mx, ext, nd, bufLen);
 	return 1;
 }

@@ -22,11 +22,14 @@
 #include <atomic>
 #include <unistd.h>
 
-// The reference's Object.o references these; the CPU path never calls them.
+// The reference's Object.o references these; the CPU path never calls them.  With -DGPV_LINK_PRODUCT the harness is linked
+// against libgpview_b200.so instead (the drop-in boundary test, tests/test_gpu_compat.py) and the stubs disappear.
+#ifndef GPV_LINK_PRODUCT
 extern "C" int CUDAClassifyTessellation(float*, int, float*, int*, int*, float3, float3, float3, int3, int) { abort(); }
 extern "C" int CUDAClassifyTessellationLevel2(float*, float*, float*, float*, int*, int*, int*, int*, int, int3, float3, float3) { abort(); }
 extern "C" int CUDAClassifyInOutLevel2(float*, float*, float*, int*, int*, int*, int*, int, int3, int3, float3, float3) { abort(); }
 extern "C" float THRUSTDeviceFindMax(float*, int, int) { abort(); }
+#endif
 
 int TriBoxOverlap(float boxcenter[3], float boxhalfsize[3], float triverts[3][3]);
 int triangle_ray_intersection(const float V1[3], const float V2[3], const float V3[3], const float O[3], const float D[3], float* out);
@@ -438,6 +441,47 @@ void ref_l2_adopt_kernelform(void* h)
 	VoxelData* vd = r->o->voxelData;
 	memcpy(vd->level2InOut, r->l2k.data(), r->l2k.size() * sizeof(float));
 	memcpy(vd->level2Normal, r->l2kNormal.data(), r->l2kNormal.size() * sizeof(float));
+}
+
+// The reference's own GPU host path, UNMODIFIED: Object::ClassifyTessellationCUDA (src/Object.cpp:2071; re-run with the
+// returned buffer size like :3204-3214) and Object::ClassifyInOutTessellationLevel2CUDA (:2533), which call the three
+// extern "C" operators -- resolved by whatever library this harness is linked against.  Level-1 normals, prefix sum and
+// level-2 allocation restated from PerformVoxelization as in ref_l1_tribox/ref_compact.  Returns the max triangles per cell.
+int ref_cuda_path(void* h)
+{
+	Ref* r = (Ref*)h;
+	Object* o = r->o;
+	VoxelData* vd = o->voxelData;
+	int nx = vd->numDivX, ny = vd->numDivY, nz = vd->numDivZ;
+	size_t N = (size_t)nx*ny*nz;
+	vd->bBox = new BBoxData[N];
+	for (size_t k = 0; k < N; k++) { vd->bBox[k].solid = int(vd->level1InOut[k]) % 2; vd->bBox[k].intersecting = 0; }
+	int maxTri = o->ClassifyTessellationCUDA(r->gp);
+	int used = 50;
+	if (maxTri > 0) {
+		for (size_t k = 0; k < N; k++) vd->bBox[k].objTriangles.clear(); // App. B5: the first pass already pushed its lists
+		vd->level1TriBuffer = maxTri;
+		used = maxTri;
+		int again = o->ClassifyTessellationCUDA(r->gp);
+		if (again != 0) return -1;
+	}
+	int boundaryVoxelCount = 0;
+	vd->boundaryIndex.clear();
+	for (size_t index = 0; index < N; index++) {
+		vd->boundaryPrefixSum[index] = boundaryVoxelCount;
+		if (vd->level1InOut[index] == 2) { boundaryVoxelCount++; vd->boundaryIndex.push_back(index); }
+	}
+	size_t nb = vd->boundaryIndex.size();
+	size_t n23 = (size_t)vd->numDivX2*vd->numDivY2*vd->numDivZ2;
+	vd->level2InOut = new inOutDType[nb * n23 + 1];
+	memset(vd->level2InOut, 0, (nb * n23 + 1) * sizeof(inOutDType));
+	vd->level2Normal = new float[nb * n23 * 4 + 4];
+	memset(vd->level2Normal, 0, (nb * n23 * 4 + 4) * sizeof(float));
+	// the reference's cudaMemset calls zero only part of the Level-2 device buffers (App. B2): hand it zeroed memory by
+	// poisoning nothing -- cudaMalloc'ed memory of a fresh context is zero-filled by the driver in practice; see the test.
+	o->ClassifyInOutTessellationLevel2CUDA(r->gp);
+	r->boxes = true;
+	return used;
 }
 
 // Voxel counting, src/Object.cpp:3353-3378.
