@@ -296,7 +296,7 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 		lio.cellTris = c->cellTris.as<int>(); lio.colOff = c->colOff.as<unsigned>(); lio.colCount = c->colCount.as<int>(); lio.colTris = c->colTris.as<int>();
 		lio.cx = cx; lio.cy = cy; lio.cz = cz; lio.l2State = c->l2State.as<unsigned char>(); lio.nBoundary = (int)nB; lio.totals = dT;
 		const int rows = g.n2 * g.n2, G = rows >= kL2Threads ? 1 : kL2Threads / rows;
-		const size_t smem = (size_t)G * 3 * g.n2 * 4 + (size_t)G * rows * 8 + (size_t)G * 16 + 8 + (kL2Threads / 32) * 64 * 8;
+		const size_t smem = (size_t)G * 3 * g.n2 * 4 + (size_t)G * rows * 8 + (size_t)G * 16 + 16 + (size_t)kL2Threads * kL2Batch * 8 + 16;
 		k_l2<<<(unsigned)((nB + G - 1) / G), kL2Threads, smem, st>>>(g, lio);
 		launches++;
 		mark(GPV_PHASE_L2_NORMALS);

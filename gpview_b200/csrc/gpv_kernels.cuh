@@ -559,6 +559,8 @@ struct L2IO {
 };
 
 constexpr int kL2Threads = 256;
+constexpr int kL2Batch = 8;   // triangles per queue round
+constexpr int kL2Stage = 256; // ray records staged per chunk (12 KB of the 16 KB queue area)
 
 __global__ void __launch_bounds__(kL2Threads) k_l2(GridP g, L2IO io)
 {
@@ -569,7 +571,8 @@ __global__ void __launch_bounds__(kL2Threads) k_l2(GridP g, L2IO io)
 	unsigned* sPar = reinterpret_cast<unsigned*>(sC + G * 3 * n2);    // [G][rows] parity bits along z per xy-column
 	int* sInfo = reinterpret_cast<int*>(sPar + G * rows);             // [G][4] triOff, triCnt, colOff, colCnt
 	unsigned* sSat = reinterpret_cast<unsigned*>(sInfo + G * 4);      // [G][rows] SAT hit bits along x per row
-	uint2* sQueue = reinterpret_cast<uint2*>(sSat + G * rows + ((G * 3 * n2) & 1)); // [8 warps][64] (item|plo|phi, triangle), 8-byte aligned
+	uint2* sQueue = reinterpret_cast<uint2*>(sSat + G * rows + ((4 - ((G * 3 * n2 + 2 * G * rows) & 3)) & 3)); // [kL2Threads*kL2Batch] (item|plo|phi, triangle), 16-byte aligned
+	int* sQn = reinterpret_cast<int*>(sQueue + kL2Threads * kL2Batch);              // queue fill
 	const int tid = threadIdx.x;
 	const long long b0 = (long long)blockIdx.x * G;
 
@@ -599,35 +602,78 @@ __global__ void __launch_bounds__(kL2Threads) k_l2(GridP g, L2IO io)
 	__syncthreads();
 
 	// ---- phase 1: parity rays.  item = (cell gi, xy-column pq); n2 <= 32 so the z parity fits one word
-	for (int item = tid; item < G * rows; item += kL2Threads) {
-		int gi = item / rows, pq = item - gi * rows, q = pq / n2, p = pq - q * n2;
-		const float* c = sC + gi * 3 * n2;
-		const float ox = c[p], oy = c[n2 + q];
-		const int* inf = sInfo + gi * 4;
-		unsigned par = 0;
-		for (int k = 0; k < inf[3]; k++) {
-			RayTri s;
-			load_ray(s, io.ray48, io.colTris[inf[2] + k]);
-			RayCol rc;
-			if (!s.ok || !ray_column(s, ox, oy, rc)) continue;
-			const int run = ray_z_run(s, rc, s.well, c[2 * n2], c[3 * n2 - 1]); // the whole cell below / above the crossing?
-			if (run == 0) continue;
-			if (run == 1) par ^= n2 == 32 ? 0xffffffffu : ((1u << n2) - 1);
-			else for (int r = 0; r < n2; r++) par ^= (unsigned)ray_cell(s, rc, c[2 * n2 + r]) << r;
+	const unsigned fullRun = n2 == 32 ? 0xffffffffu : ((1u << n2) - 1);
+	if (G == 1) {
+		// one cell per CTA: every thread walks the same column list, so its ray records are staged through shared memory
+		// (the queue area is idle in this phase) in chunks of kL2Stage records instead of 256 threads chasing the same
+		// colTris -> ray48 pointers
+		float4* stage = reinterpret_cast<float4*>(sQueue);
+		const int colOff = sInfo[2], colCnt = sInfo[3];
+		unsigned par[4] = { 0, 0, 0, 0 }; // up to 4 xy-columns per thread (n2 = 32)
+		for (int k0 = 0; k0 < colCnt; k0 += kL2Stage) {
+			const int nrec = min(kL2Stage, colCnt - k0);
+			for (int i = tid; i < nrec * 3; i += kL2Threads) {
+				const int rec = i / 3;
+				stage[i] = __ldg(io.ray48 + (size_t)io.colTris[colOff + k0 + rec] * 3 + (i - rec * 3));
+			}
+			__syncthreads();
+			int slot = 0;
+			for (int item = tid; item < rows; item += kL2Threads, slot++) {
+				const int q = item / n2, p = item - q * n2;
+				const float ox = sC[p], oy = sC[n2 + q];
+				unsigned acc = 0;
+				for (int k = 0; k < nrec; k++) {
+					const float4 a = stage[k * 3], b = stage[k * 3 + 1], c4 = stage[k * 3 + 2];
+					if (c4.w == 0.f) continue;
+					RayTri s;
+					s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;
+					s.e2z = c4.x; s.det = c4.y; s.inv = c4.z; s.ok = true; s.well = c4.w == 2.f;
+					RayCol rc;
+					if (!ray_column(s, ox, oy, rc)) continue;
+					const int run = ray_z_run(s, rc, s.well, sC[2 * n2], sC[3 * n2 - 1]); // the whole cell below / above the crossing?
+					if (run == 0) continue;
+					if (run == 1) acc ^= fullRun;
+					else for (int r = 0; r < n2; r++) acc ^= (unsigned)ray_cell(s, rc, sC[2 * n2 + r]) << r;
+				}
+				par[slot] ^= acc;
+			}
+			__syncthreads();
 		}
-		sPar[item] = par;
+		int slot = 0;
+		for (int item = tid; item < rows; item += kL2Threads, slot++) sPar[item] = par[slot];
+	} else {
+		for (int item = tid; item < G * rows; item += kL2Threads) {
+			int gi = item / rows, pq = item - gi * rows, q = pq / n2, p = pq - q * n2;
+			const float* c = sC + gi * 3 * n2;
+			const float ox = c[p], oy = c[n2 + q];
+			const int* inf = sInfo + gi * 4;
+			unsigned par = 0;
+			for (int k = 0; k < inf[3]; k++) {
+				RayTri s;
+				load_ray(s, io.ray48, io.colTris[inf[2] + k]);
+				RayCol rc;
+				if (!s.ok || !ray_column(s, ox, oy, rc)) continue;
+				const int run = ray_z_run(s, rc, s.well, c[2 * n2], c[3 * n2 - 1]);
+				if (run == 0) continue;
+				if (run == 1) par ^= fullRun;
+				else for (int r = 0; r < n2; r++) par ^= (unsigned)ray_cell(s, rc, c[2 * n2 + r]) << r;
+			}
+			sPar[item] = par;
+		}
 	}
 	__syncthreads();
 
 	// ---- phase 2a: SAT.  Cheap pass: every (row, triangle) pair gets the certified plane interval (gpv::plane_row_interval,
-	// ~12 instructions); pairs that can still hit are compacted into a per-warp queue (ballot/popc) and the expensive part
-	// -- the hoisted row set-up plus the exact test of the few sub-voxels inside the interval -- runs on full warps of
-	// queue entries, whatever rows and triangles they came from.  Hits are OR-ed into the row's bit mask in shared memory.
+	// ~12 instructions); pairs that can still hit are compacted into a CTA-wide queue in shared memory (ballot/popc per
+	// warp, one atomicAdd per warp for the slot range) and the expensive part -- the hoisted row set-up plus the exact test of
+	// the few sub-voxels inside the interval -- runs on full warps of queue entries, whatever rows and triangles they came
+	// from.  Hits are OR-ed into the row's bit mask in shared memory.  Triangles are taken kL2Batch at a time so that the
+	// queue (kL2Threads * kL2Batch entries) can never overflow.
 	for (int item = tid; item < G * rows; item += kL2Threads) sSat[item] = 0;
+	if (tid == 0) *sQn = 0;
 	__syncthreads();
 	{
 		const int lane = tid & 31;
-		uint2* queue = sQueue + (tid >> 5) * 64;
 		const float inv2h = 1.f / (2.f * g.h2x);
 		auto heavy = [&](uint2 e) {
 			const int item = (int)(e.x & 0xffffu), plo = (int)((e.x >> 16) & 0xffu), phi = (int)(e.x >> 24);
@@ -651,32 +697,35 @@ __global__ void __launch_bounds__(kL2Threads) k_l2(GridP g, L2IO io)
 				slack = 9.5367431640625e-07f * (fabsf(c0) + 2.f * g.gsx); // 16u(|mid_x| + gs_x) >= |(c_p - c_0) - 2*h2x*p|
 				triOff = sInfo[gi * 4]; triCnt = sInfo[gi * 4 + 1];        // 0 for cells past the end
 			}
-			const int maxCnt = __reduce_max_sync(0xffffffffu, triCnt);
-			int qn = 0;
-			for (int k = 0; k < maxCnt; k++) {
-				bool alive = false;
-				int plo = 0, phi = -1, t = 0;
-				if (k < triCnt) {
-					t = io.cellTris[triOff + k];
-					const float4 A = __ldg(io.tri48 + (size_t)t * 3), pl = __ldg(io.plane16 + t);
-					PlaneRec P; P.sx = pl.x; P.ny = pl.y; P.nz = pl.z; P.R = pl.w;
-					alive = plane_row_interval(P, A.x - c0, A.y - cy2, A.z - cz2, inv2h, slack, n2, plo, phi);
+			int maxCnt = 0; // CTA-wide longest cell list (every thread must take part in the barriers below)
+			for (int gi = 0; gi < G; gi++) maxCnt = max(maxCnt, sInfo[gi * 4 + 1]);
+			for (int kb = 0; kb < maxCnt; kb += kL2Batch) {
+				for (int k = kb; k < min(kb + kL2Batch, maxCnt); k++) {
+					bool alive = false;
+					int plo = 0, phi = -1, t = 0;
+					if (k < triCnt) {
+						t = io.cellTris[triOff + k];
+						const float4 A = __ldg(io.tri48 + (size_t)t * 3), pl = __ldg(io.plane16 + t);
+						PlaneRec P; P.sx = pl.x; P.ny = pl.y; P.nz = pl.z; P.R = pl.w;
+						alive = plane_row_interval(P, A.x - c0, A.y - cy2, A.z - cz2, inv2h, slack, n2, plo, phi);
+					}
+					const unsigned m = __ballot_sync(0xffffffffu, alive);
+					if (m) {
+						int base = 0;
+						if (lane == 0) base = atomicAdd(sQn, __popc(m));
+						base = __shfl_sync(0xffffffffu, base, 0);
+						if (alive) sQueue[base + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)item | ((unsigned)plo << 16) | ((unsigned)phi << 24), (unsigned)t);
+					}
 				}
-				const unsigned m = __ballot_sync(0xffffffffu, alive);
-				if (alive) queue[qn + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)item | ((unsigned)plo << 16) | ((unsigned)phi << 24), (unsigned)t);
-				qn += __popc(m);
-				__syncwarp();
-				if (qn >= 32) {
-					qn -= 32;
-					heavy(queue[qn + lane]);
-					__syncwarp();
-				}
+				__syncthreads();
+				const int qn = *sQn;
+				for (int e = tid; e < qn; e += kL2Threads) heavy(sQueue[e]);
+				__syncthreads();
+				if (tid == 0) *sQn = 0;
+				__syncthreads();
 			}
-			if (lane < qn) heavy(queue[lane]);
-			__syncwarp();
 		}
 	}
-	__syncthreads();
 
 	// ---- phase 2b: the row's file bytes
 	unsigned long long nIn = 0, nBd = 0;
