@@ -59,7 +59,7 @@ struct gpv_ctx {
 	int device = 0;
 	int smCount = 0;
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
-	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16;
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, longList;
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
@@ -103,7 +103,7 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16 };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->longList };
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
 	if (c->haveEvents) for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -267,12 +267,27 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	                                                   c->crossTri.as<int>(), dT);
 	launches += 2;
 	mark(GPV_PHASE_SORT);
-	if (nB > 0) {
-		k_sort_segments<false><<<(unsigned)((nB * 32 + 255) / 256), 256, 0, st>>>(c->bTriOff.as<unsigned>(), (int)nB, c->cellTris.as<int>(), nullptr);
-		launches++;
+	{ // canonical order: warp per list; lists longer than kSortSmem go through a work list to k_sort_long (CTA per list)
+		if (c->longList.ensure((size_t)(nB + ncol) * 4 + 64)) return 1;
+		unsigned* longCnt = c->longList.as<unsigned>();           // [0] cell lists, [1] column lists
+		int* longCells = c->longList.as<int>() + 16;
+		int* longCols = longCells + nB;
+		GPV_CUDA(cudaMemsetAsync(longCnt, 0, 64, st));
+		static bool attrSet = false;
+		if (!attrSet) {
+			GPV_CUDA(cudaFuncSetAttribute(k_sort_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortLongSmem * 4));
+			GPV_CUDA(cudaFuncSetAttribute(k_sort_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortLongSmem * 4));
+			attrSet = true;
+		}
+		if (nB > 0) {
+			k_sort_segments<false><<<(unsigned)((nB * 32 + 255) / 256), 256, 0, st>>>(c->bTriOff.as<unsigned>(), (int)nB, c->cellTris.as<int>(), nullptr, longCells, longCnt);
+			k_sort_long<false><<<c->smCount, kSortLongThreads, kSortLongSmem * 4, st>>>(c->bTriOff.as<unsigned>(), longCells, longCnt, c->cellTris.as<int>(), nullptr);
+			launches += 2;
+		}
+		k_sort_segments<true><<<(unsigned)((ncol * 32 + 255) / 256), 256, 0, st>>>(c->colOff.as<unsigned>(), (int)ncol, c->colTris.as<int>(), c->colCount.as<int>(), longCols, longCnt + 1);
+		k_sort_long<true><<<c->smCount, kSortLongThreads, kSortLongSmem * 4, st>>>(c->colOff.as<unsigned>(), longCols, longCnt + 1, c->colTris.as<int>(), c->colCount.as<int>());
+		launches += 2;
 	}
-	k_sort_segments<true><<<(unsigned)((ncol * 32 + 255) / 256), 256, 0, st>>>(c->colOff.as<unsigned>(), (int)ncol, c->colTris.as<int>(), c->colCount.as<int>());
-	launches++;
 	mark(GPV_PHASE_FILL_SWEEP);
 	{
 		dim3 grid((g.nx + 31) / 32, g.ny, (g.z1 - g.z0 + 127) / 128), block(32, 4);

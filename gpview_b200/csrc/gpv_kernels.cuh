@@ -145,8 +145,8 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
 
 // ------------------------------------------------------------------------------------------------ balanced triangle work
 // The (triangle, cell) items of all triangles form one flat index space (off = exclusive scan of the per-triangle item
-// counts).  Work block w owns items [w*1024, (w+1)*1024); work blocks are strided over a persistent grid.  The triangles
-// a work block touches are a CONTIGUOUS range, staged tile by tile (<= 128 records) into shared memory by TMA; each
+// counts), cut into equal contiguous ranges, one per CTA of a persistent grid (one binary search per CTA).  The triangles
+// a range touches are a CONTIGUOUS range too, staged tile by tile (<= 128 records) into shared memory by TMA; each
 // thread finds the owner of its item by binary search in the tile's offsets (shared memory) and decodes the cell from the
 // item's rank inside the footprint.  This removes the footprint skew (cessna-256: mean 64, max 6,762 cells per triangle;
 // an ill-conditioned triangle of the parity fill has nx*ny candidate columns) that a triangle-per-thread map suffers from.
@@ -167,37 +167,54 @@ __device__ __forceinline__ void for_each_work_item(WorkSmem& sm, const unsigned*
 	__syncthreads();
 	const unsigned long long total = *totalPtr;
 	uint32_t parity = 0;
-	for (unsigned long long wb = blockIdx.x; wb * kWorkBlock < total; wb += gridDim.x) {
-		const unsigned long long B0 = wb * kWorkBlock, B1 = min(total, B0 + kWorkBlock);
-		if (tid == 0) { // largest t with off[t] <= B0   (off[0] = 0 <= B0 < total = off[nTri])
-			int lo = 0, hi = nTri;
-			while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (off[mid] <= B0) lo = mid; else hi = mid; }
-			sm.t0 = lo;
+	// this CTA's contiguous item range [R0,R1): ceil(nBlocks/grid) work blocks of kWorkBlock items
+	const unsigned long long nBlocks = (total + kWorkBlock - 1) / kWorkBlock, per = (nBlocks + gridDim.x - 1) / gridDim.x;
+	const unsigned long long R0 = min(total, blockIdx.x * per * kWorkBlock), R1 = min(total, (blockIdx.x + 1ull) * per * kWorkBlock);
+	if (R0 >= R1) return;
+	if (tid == 0) { // largest t with off[t] <= R0   (off[0] = 0 <= R0 < total = off[nTri]); ONE search per CTA
+		int lo = 0, hi = nTri;
+		while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (off[mid] <= R0) lo = mid; else hi = mid; }
+		sm.t0 = lo;
+	}
+	__syncthreads();
+	int t = sm.t0;
+	for (;;) {
+		const int nt = min(kTileTris, nTri - t);
+		__syncthreads(); // the previous round's readers of sm.off / sm.t0 are done
+		for (int i = tid; i <= nt; i += kWorkThreads) sm.off[i] = off[t + i];
+		if (tid == 0) sm.t0 = 0x7fffffff;
+		__syncthreads();
+		const unsigned o0 = sm.off[0];
+		if (sm.off[nt] == o0) {
+			// no item in these 128 triangles (e.g. a run of triangles that can never be hit): fast-forward.  Every thread
+			// probes the end offset of one of the next 128 tiles; the first tile that ends beyond o0 holds the next item.
+			if (o0 >= R1 || t + nt >= nTri) break;
+			const long long probe = (long long)t + (long long)(tid + 1) * kTileTris;
+			if (off[min((long long)nTri, probe)] > o0) atomicMin(&sm.t0, tid);
+			__syncthreads();
+			const int first = sm.t0;
+			if (first == 0x7fffffff) { if ((long long)t + (long long)kWorkThreads * kTileTris >= nTri) break; t += kWorkThreads * kTileTris; }
+			else t += first * kTileTris;
+			continue;
+		}
+		if (tid == 0) {
+			mbar_expect(&sm.bar, (uint32_t)nt * (HAS_FP ? 64u : 48u));
+			tma_bulk_g2s(sm.rec, rec48 + (size_t)t * 3, (uint32_t)nt * 48u, &sm.bar);
+			if (HAS_FP) tma_bulk_g2s(sm.fp, fp + t, (uint32_t)nt * 16u, &sm.bar);
+		}
+		mbar_wait(&sm.bar, parity);
+		parity ^= 1;
+		__syncthreads();
+		const unsigned long long cb = max(R0, (unsigned long long)sm.off[0]), ce = min(R1, (unsigned long long)sm.off[nt]);
+		const bool last = sm.off[nt] >= R1 || t + nt >= nTri;
+		for (unsigned long long c = cb + tid; c < ce; c += kWorkThreads) {
+			int lo = 0, hi = nt; // largest k in [0,nt) with off[k] <= c
+			while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm.off[mid] <= c) lo = mid; else hi = mid; }
+			f(t + lo, sm.rec + lo * 3, sm.fp + lo, (unsigned)(c - sm.off[lo]));
 		}
 		__syncthreads();
-		int t = sm.t0;
-		for (;;) {
-			const int nt = min(kTileTris, nTri - t);
-			for (int i = tid; i <= nt; i += kWorkThreads) sm.off[i] = off[t + i];
-			if (tid == 0) {
-				mbar_expect(&sm.bar, (uint32_t)nt * (HAS_FP ? 64u : 48u));
-				tma_bulk_g2s(sm.rec, rec48 + (size_t)t * 3, (uint32_t)nt * 48u, &sm.bar);
-				if (HAS_FP) tma_bulk_g2s(sm.fp, fp + t, (uint32_t)nt * 16u, &sm.bar);
-			}
-			mbar_wait(&sm.bar, parity);
-			parity ^= 1;
-			__syncthreads();
-			const unsigned long long cb = max(B0, (unsigned long long)sm.off[0]), ce = min(B1, (unsigned long long)sm.off[nt]);
-			const bool last = sm.off[nt] >= B1 || t + nt >= nTri;
-			for (unsigned long long c = cb + tid; c < ce; c += kWorkThreads) {
-				int lo = 0, hi = nt; // largest k in [0,nt) with off[k] <= c
-				while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm.off[mid] <= c) lo = mid; else hi = mid; }
-				f(t + lo, sm.rec + lo * 3, sm.fp + lo, (unsigned)(c - sm.off[lo]));
-			}
-			__syncthreads();
-			if (last) break;
-			t += nt;
-		}
+		if (last) break;
+		t += nt;
 	}
 }
 
@@ -476,8 +493,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(ScanIO io)
 // yields, src/Object.cpp:2705-2748; the GPU path's atomic slots are nondeterministic).  len <= 32: rank sort in
 // registers; longer: in-place bitonic network in the all-ascending "flip" form, valid for any length.
 // UNIQUE (column lists): drops duplicates (a triangle hits several cells of one column) and stores the unique count.
+constexpr int kSortSmem = 1024; // list length sorted in shared memory (4 KB per warp)
+
 template <bool UNIQUE>
-__global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restrict__ off, int nSeg, int* data, int* uniqueCount)
+__global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restrict__ off, int nSeg, int* data, int* uniqueCount, int* longList, unsigned* longCount)
 {
 	const int lane = threadIdx.x & 31;
 	const int seg = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -508,6 +527,20 @@ __global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restric
 		if (lane == 0) uniqueCount[seg] = __popc(km);
 		return;
 	}
+	// longer lists: bitonic network in this warp's slice of shared memory; lists beyond kSortSmem entries (a column under a
+	// pole of a finely tessellated body collects thousands of triangles) are handed to k_sort_long, one CTA per list
+	if (len > kSortSmem) {
+		if (lane == 0) longList[atomicAdd(longCount, 1u)] = seg;
+		return;
+	}
+	__shared__ int sSort[8][kSortSmem];
+	int* dst = a; // where the sorted (and de-duplicated) list ends up
+	{
+		int* sb = sSort[threadIdx.x >> 5];
+		for (int i = lane; i < len; i += 32) sb[i] = a[i];
+		__syncwarp();
+		a = sb;
+	}
 	for (int k = 2; (k >> 1) < len; k <<= 1) {
 		for (int i = lane; i < len; i += 32) { // flip: mirror inside blocks of k
 			int l = i ^ (k - 1);
@@ -522,7 +555,7 @@ __global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restric
 			__syncwarp();
 		}
 	}
-	if (UNIQUE) { // in-place compaction, 32 elements at a time, reads finish before writes of the same round
+	if (UNIQUE) { // compaction, 32 elements at a time; in place when a == dst: the reads of a round finish before its writes
 		int w = 0, carry = 0;
 		for (int b0 = 0; b0 < len; b0 += 32) {
 			int i = b0 + lane;
@@ -533,11 +566,78 @@ __global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restric
 			unsigned km = __ballot_sync(0xffffffffu, keep);
 			carry = __shfl_sync(0xffffffffu, x, 31);
 			__syncwarp();
-			if (keep) a[w + __popc(km & ((1u << lane) - 1))] = x;
+			if (keep) dst[w + __popc(km & ((1u << lane) - 1))] = x;
 			w += __popc(km);
 			__syncwarp();
 		}
 		if (lane == 0) uniqueCount[seg] = w;
+	} else if (a != dst) {
+		for (int i = lane; i < len; i += 32) dst[i] = a[i];
+	}
+}
+
+// Long lists: one CTA of 1024 threads per list, same all-ascending bitonic network with CTA barriers; up to kSortLongSmem
+// entries in (opt-in, 64 KB) dynamic shared memory, in place in global memory beyond that.
+constexpr int kSortLongThreads = 1024, kSortLongSmem = 16384;
+
+template <bool UNIQUE>
+__global__ void __launch_bounds__(kSortLongThreads) k_sort_long(const unsigned* __restrict__ off, const int* __restrict__ longList,
+                                                               const unsigned* __restrict__ longCount, int* data, int* uniqueCount)
+{
+	extern __shared__ int sLong[];
+	__shared__ int sW;
+	const int tid = threadIdx.x;
+	for (unsigned w = blockIdx.x; w < *longCount; w += gridDim.x) {
+		const int seg = longList[w];
+		const unsigned beg = off[seg];
+		const int len = (int)(off[seg + 1] - beg);
+		int* dst = data + beg;
+		int* a = dst;
+		if (len <= kSortLongSmem) {
+			for (int i = tid; i < len; i += kSortLongThreads) sLong[i] = dst[i];
+			a = sLong;
+		}
+		__syncthreads();
+		for (int k = 2; (k >> 1) < len; k <<= 1) {
+			for (int i = tid; i < len; i += kSortLongThreads) {
+				int l = i ^ (k - 1);
+				if (l > i && l < len) { int x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+			}
+			__syncthreads();
+			for (int j = k >> 2; j > 0; j >>= 1) {
+				for (int i = tid; i < len; i += kSortLongThreads) {
+					int l = i ^ j;
+					if (l > i && l < len) { int x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+				}
+				__syncthreads();
+			}
+		}
+		if (UNIQUE) { // CTA-wide compaction in chunks of 1024: reads of a chunk finish (barrier) before its writes
+			if (tid == 0) sW = 0;
+			__syncthreads();
+			for (int b0 = 0; b0 < len; b0 += kSortLongThreads) {
+				const int i = b0 + tid;
+				const int x = i < len ? a[i] : 0;
+				const bool keep = i < len && (i == 0 || x != a[i - 1]);
+				const unsigned km = __ballot_sync(0xffffffffu, keep);
+				__shared__ int sWarpCnt[32];
+				if ((tid & 31) == 0) sWarpCnt[tid >> 5] = __popc(km);
+				__syncthreads();
+				int before = 0;
+				for (int q = 0; q < (tid >> 5); q++) before += sWarpCnt[q];
+				int total = 0;
+				for (int q = 0; q < 32; q++) total += sWarpCnt[q];
+				const int base = sW;
+				__syncthreads();
+				if (keep) dst[base + before + __popc(km & ((1u << (tid & 31)) - 1))] = x;
+				if (tid == 0) sW = base + total;
+				__syncthreads();
+			}
+			if (tid == 0) uniqueCount[seg] = sW;
+		} else if (a != dst) {
+			for (int i = tid; i < len; i += kSortLongThreads) dst[i] = a[i];
+		}
+		__syncthreads();
 	}
 }
 

@@ -276,15 +276,22 @@ GPV_HD int fill_candidates(const RayTri& s, float minx, float miny, float gsx, f
 	float ax = fabsf(s.e1x), ay = fabsf(s.e1y), bx = fabsf(s.e2x), by = fabsf(s.e2y);
 	float B = fmaxf(fmaxf(ax * by + ay * bx, 2.f * (bx * by)), 2.f * (ax * ay));
 	if (!(fabsf(s.det) >= 1.6e-5f * B)) return 2;
-	float rx = 1.04f * (ax + bx) + 1e-30f, ry = 1.04f * (ay + by) + 1e-30f;
-	float lo = floorf((s.v1x - rx - minx) / gsx) - 1.f, hi = floorf((s.v1x + rx - minx) / gsx) + 1.f;
+	// With the signs: u' >= 0 and v' >= 0 force U, V >= -2.05/127 = -0.0162 and u'+v' <= 1 forces U+V <= 1.04, so
+	// T = U*a + V*b lies in the projected triangle {0, a, b} grown by 6 % of (|a|+|b|) per axis.  Column centres are
+	// x_i = minx + (i+0.5)*gs up to f32 rounding: i >= (lo-minx)/gs - 0.5; the slack covers the rounding of lo/hi themselves
+	// (u*|v1|), of the centre table (u*|coord|) and of this index arithmetic.
+	const float mx = 0.06f * (ax + bx) + 1e-30f, my = 0.06f * (ay + by) + 1e-30f;
+	const float lox = s.v1x + fminf(0.f, fminf(s.e1x, s.e2x)) - mx, hix = s.v1x + fmaxf(0.f, fmaxf(s.e1x, s.e2x)) + mx;
+	const float loy = s.v1y + fminf(0.f, fminf(s.e1y, s.e2y)) - my, hiy = s.v1y + fmaxf(0.f, fmaxf(s.e1y, s.e2y)) + my;
+	const float sx = 0.02f + 4.8e-7f * (fabsf(lox) + fabsf(hix) + fabsf(minx)) / gsx, sy = 0.02f + 4.8e-7f * (fabsf(loy) + fabsf(hiy) + fabsf(miny)) / gsy;
+	float lo = ceilf((lox - minx) / gsx - 0.5f - sx), hi = floorf((hix - minx) / gsx - 0.5f + sx);
 	if (!(lo == lo) || !(hi == hi)) return 2;
 	i0 = lo < 0.f ? 0 : (lo > 2e9f ? 2000000000 : (int)lo);
-	i1 = hi > (float)(nx - 1) ? nx - 1 : (int)hi;
-	lo = floorf((s.v1y - ry - miny) / gsy) - 1.f; hi = floorf((s.v1y + ry - miny) / gsy) + 1.f;
+	i1 = hi > (float)(nx - 1) ? nx - 1 : (hi < -1.f ? -1 : (int)hi);
+	lo = ceilf((loy - miny) / gsy - 0.5f - sy); hi = floorf((hiy - miny) / gsy - 0.5f + sy);
 	if (!(lo == lo) || !(hi == hi)) return 2;
 	j0 = lo < 0.f ? 0 : (lo > 2e9f ? 2000000000 : (int)lo);
-	j1 = hi > (float)(ny - 1) ? ny - 1 : (int)hi;
+	j1 = hi > (float)(ny - 1) ? ny - 1 : (hi < -1.f ? -1 : (int)hi);
 	return (i0 <= i1 && j0 <= j1) ? 1 : 0;
 }
 

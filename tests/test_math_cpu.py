@@ -224,3 +224,42 @@ def test_certified_z_runs_agree_with_per_cell_evaluation(probe):
         tot += out
     assert tot[2] > 400000 and tot[1] > 0.3 * tot[2], tot
     print("z-runs: %d column-passing pairs, %d decided from one evaluation" % (tot[2], tot[1]))
+
+
+@pytest.mark.parametrize("origin,gs", [(0.0, 0.125), (1000.0, 0.125), (-250000.0, 1.0), (3.0, 1e-3), (0.0, 40.0)])
+def test_certified_candidates_tight_and_covering_on_shifted_grids(probe, origin, gs):
+    """Same property as above on grids far from the origin / with tiny or huge cells, with triangles from 1/20 of a cell
+    to 30 cells across; also checks that the rectangle is tight (not more than ~2 columns of slack per side on average)."""
+    rng = np.random.default_rng(int(abs(origin)) + int(gs * 1000))
+    nx = ny = 40
+    gs = np.float32(gs)
+    mn = np.float32(origin)
+    cx = (np.float64(mn) + (np.arange(nx) + 0.5) * np.float64(gs)).astype(np.float32)
+    n = 2500
+    size = (10.0 ** rng.uniform(-1.3, 1.5, (n, 1, 1))) * float(gs)
+    ctr = float(mn) + rng.uniform(0, nx, (n, 1, 3)) * float(gs)
+    t = (ctr + rng.normal(0, 1, (n, 3, 3)) * size).astype(np.float32).reshape(n, 9)
+    cand = np.zeros((n, 5), np.int32)
+    probe.probe_candidates(n, _fp(t), mn, mn, gs, gs, nx, ny, cand.ctypes.data_as(C.POINTER(C.c_int32)))
+    jj, ii = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    oxy = np.ascontiguousarray(np.stack([cx[ii.reshape(-1)], cx[jj.reshape(-1)]], -1), np.float32)
+    area_c = area_h = 0
+    for q in range(n):
+        tt = np.ascontiguousarray(np.repeat(t[q:q + 1], nx * ny, 0))
+        hit = np.zeros(nx * ny, np.uint8)
+        probe.probe_column(nx * ny, _fp(oxy), _fp(tt), _bp(hit))
+        hit = hit.reshape(ny, nx).astype(bool)
+        kind, i0, i1, j0, j1 = cand[q]
+        if kind == 2:
+            continue
+        if kind == 0:
+            assert not hit.any(), q
+            continue
+        outside = np.ones((ny, nx), bool)
+        outside[j0:j1 + 1, i0:i1 + 1] = False
+        assert not (hit & outside).any(), (q, cand[q], np.argwhere(hit & outside)[:4])
+        if hit.any():
+            ys, xs = np.nonzero(hit)
+            area_h += (xs.max() - xs.min() + 1) * (ys.max() - ys.min() + 1)
+            area_c += (i1 - i0 + 1) * (j1 - j0 + 1)
+    assert area_c <= 2.5 * area_h + 4 * n, (area_c, area_h)
