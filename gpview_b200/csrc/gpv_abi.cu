@@ -19,6 +19,7 @@
 #include "../../include/gpview_b200.h"
 #include "gpv_internal.h"
 #include "gpv_kernels.cuh"
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -63,6 +64,8 @@ struct gpv_ctx {
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
+	cudaStream_t copyStream = nullptr;  // D2H of finished streams overlaps the rest of the pipeline (gpv_voxelize_host)
+	cudaEvent_t evChunk[17] = {};
 };
 
 using namespace gpv;
@@ -93,6 +96,8 @@ extern "C" int gpv_create(int device, gpv_ctx** out)
 	c->smCount = prop.multiProcessorCount;
 	GPV_CUDA(cudaHostAlloc((void**)&c->hTotals, sizeof(Totals), cudaHostAllocDefault));
 	if (c->totals.ensure(sizeof(Totals))) { delete c; return 1; }
+	GPV_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+	for (cudaEvent_t& e : c->evChunk) GPV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	*out = c;
 	return 0;
 }
@@ -107,6 +112,8 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
 	if (c->haveEvents) for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+	for (cudaEvent_t e : c->evChunk) if (e) cudaEventDestroy(e);
+	if (c->copyStream) cudaStreamDestroy(c->copyStream);
 	delete c;
 }
 
@@ -155,8 +162,10 @@ static int run_scan_offsets(gpv_ctx* c, cudaStream_t st, const int* in, long lon
 	return 0;
 }
 
-extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tri, const float bmin[3], const float bmax[3], float max_model_size,
-                                   const gpv_params* prm, void* stream, gpv_result* out)
+constexpr int kMaxChunks = 16; // Level-2 chunks whose D2H copies overlap the next chunk's refinement (host sink only)
+
+static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const float bmin[3], const float bmax[3], float max_model_size,
+                         const gpv_params* prm, void* stream, gpv_result* out, const gpv_host_streams* sink)
 {
 	if (!c) return fail("gpv_voxelize_device: null ctx");
 	if (n_tri <= 0 || n_tri > 0x7fffffff) return fail("gpv_voxelize_device: triangle count out of range");
@@ -304,6 +313,16 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 			launches++;
 		}
 	}
+	if (sink) { // Level-1 streams are final once the fill sweep is done: send them while Level-2 computes
+		if (sink->level2_inout && wantL2 && (int64_t)(nB * n23) > sink->level2_capacity) return fail("gpv_voxelize_host: level2 host buffer too small");
+		if (sink->boundary_index && nB > sink->boundary_capacity) return fail("gpv_voxelize_host: boundary_index host buffer too small");
+		GPV_CUDA(cudaEventRecord(c->evChunk[kMaxChunks], st));
+		GPV_CUDA(cudaStreamWaitEvent(c->copyStream, c->evChunk[kMaxChunks], 0));
+		if (sink->level1_inout) GPV_CUDA(cudaMemcpyAsync(sink->level1_inout, c->l1State.p, (size_t)cells, cudaMemcpyDeviceToHost, c->copyStream));
+		if (sink->prefix) GPV_CUDA(cudaMemcpyAsync(sink->prefix, c->prefix.p, (size_t)cells * 4, cudaMemcpyDeviceToHost, c->copyStream));
+		if (sink->boundary_index && nB) GPV_CUDA(cudaMemcpyAsync(sink->boundary_index, c->boundaryIndex.p, (size_t)nB * 4, cudaMemcpyDeviceToHost, c->copyStream));
+		if (sink->level1_normal && wantN) GPV_CUDA(cudaMemcpyAsync(sink->level1_normal, c->l1Normal.p, (size_t)cells * 3, cudaMemcpyDeviceToHost, c->copyStream));
+	}
 	L2IO lio{};
 	mark(GPV_PHASE_L2);
 	if (wantL2 && nB > 0) {
@@ -312,17 +331,35 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 		lio.cx = cx; lio.cy = cy; lio.cz = cz; lio.l2State = c->l2State.as<unsigned char>(); lio.nBoundary = (int)nB; lio.totals = dT;
 		const int rows = g.n2 * g.n2, G = rows >= kL2Threads ? 1 : kL2Threads / rows;
 		const size_t smem = (size_t)G * 3 * g.n2 * 4 + (size_t)G * rows * 8 + (size_t)G * 16 + 16 + (size_t)kL2Threads * kL2Batch * 8 + 16;
-		k_l2<<<(unsigned)((nB + G - 1) / G), kL2Threads, smem, st>>>(g, lio);
-		launches++;
+		// With a host sink the boundary cells are refined in chunks and every finished chunk's bytes start their way to the
+		// host on the copy stream while the next chunk computes (e2e is PCIe-bound: 1 B per Level-2 voxel).
+		long long chunks = 1;
+		if (sink && sink->level2_inout) chunks = std::min<long long>(kMaxChunks, std::max<long long>(1, (nB * n23 + (24ll << 20) - 1) / (24ll << 20)));
+		const long long per = ((nB + chunks - 1) / chunks + G - 1) / G * G; // whole CTAs per chunk
+		for (long long k = 0; k < chunks; k++) {
+			const long long bb = k * per, be = std::min(nB, bb + per);
+			if (bb >= be) break;
+			lio.bBegin = (int)bb; lio.nBoundary = (int)be;
+			k_l2<<<(unsigned)((be - bb + G - 1) / G), kL2Threads, smem, st>>>(g, lio);
+			launches++;
+			if (sink && sink->level2_inout) {
+				GPV_CUDA(cudaEventRecord(c->evChunk[k], st));
+				GPV_CUDA(cudaStreamWaitEvent(c->copyStream, c->evChunk[k], 0));
+				GPV_CUDA(cudaMemcpyAsync(sink->level2_inout + bb * n23, c->l2State.as<uint8_t>() + bb * n23, (size_t)((be - bb) * n23), cudaMemcpyDeviceToHost, c->copyStream));
+			}
+		}
+		lio.bBegin = 0; lio.nBoundary = (int)nB;
 		mark(GPV_PHASE_L2_NORMALS);
 		if (wantN) {
 			k_l2_normals<<<(unsigned)((nB * n23 + 255) / 256), 256, 0, st>>>(g, lio, c->l2Normal.as<unsigned char>());
 			launches++;
+			if (sink && sink->level2_normal) GPV_CUDA(cudaMemcpyAsync(sink->level2_normal, c->l2Normal.p, (size_t)(nB * n23) * 3, cudaMemcpyDeviceToHost, st));
 		}
 	}
 	mark(GPV_PHASE_COUNT);
 	GPV_CUDA(cudaMemcpyAsync(c->hTotals, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
 	GPV_CUDA(cudaStreamSynchronize(st));
+	if (sink) GPV_CUDA(cudaStreamSynchronize(c->copyStream));
 	GPV_CUDA(cudaGetLastError());
 	const Totals T2 = *c->hTotals;
 
@@ -356,6 +393,12 @@ extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tr
 	return 0;
 }
 
+extern "C" int gpv_voxelize_device(gpv_ctx* c, const float* d_tris, int64_t n_tri, const float bmin[3], const float bmax[3], float max_model_size,
+                                   const gpv_params* prm, void* stream, gpv_result* out)
+{
+	return voxelize_impl(c, d_tris, n_tri, bmin, bmax, max_model_size, prm, stream, out, nullptr);
+}
+
 extern "C" int gpv_voxelize_host(gpv_ctx* c, const gpv_mesh* mesh, const gpv_params* prm, void* stream, gpv_result* out, gpv_host_streams* h)
 {
 	if (!c || !mesh || !mesh->tris) return fail("gpv_voxelize_host: null argument");
@@ -363,16 +406,8 @@ extern "C" int gpv_voxelize_host(gpv_ctx* c, const gpv_mesh* mesh, const gpv_par
 	cudaStream_t st = (cudaStream_t)stream;
 	if (c->scratch.ensure((size_t)mesh->n_tri * 36)) return 1;
 	GPV_CUDA(cudaMemcpyAsync(c->scratch.p, mesh->tris, (size_t)mesh->n_tri * 36, cudaMemcpyHostToDevice, st));
-	if (gpv_voxelize_device(c, c->scratch.as<float>(), mesh->n_tri, mesh->bbox_min, mesh->bbox_max, mesh->max_model_size, prm, stream, out)) return 1;
-	const size_t cells = (size_t)out->cells, l2n = (size_t)(out->n_boundary * out->n23);
-	if (h->level2_inout && out->d_level2_inout && (int64_t)l2n > h->level2_capacity) return fail("gpv_voxelize_host: level2 host buffer too small");
-	if (h->boundary_index && out->n_boundary > h->boundary_capacity) return fail("gpv_voxelize_host: boundary_index host buffer too small");
-	if (h->level1_inout) GPV_CUDA(cudaMemcpyAsync(h->level1_inout, out->d_level1_inout, cells, cudaMemcpyDeviceToHost, st));
-	if (h->prefix) GPV_CUDA(cudaMemcpyAsync(h->prefix, out->d_prefix, cells * 4, cudaMemcpyDeviceToHost, st));
-	if (h->boundary_index && out->n_boundary) GPV_CUDA(cudaMemcpyAsync(h->boundary_index, out->d_boundary_index, (size_t)out->n_boundary * 4, cudaMemcpyDeviceToHost, st));
-	if (h->level2_inout && out->d_level2_inout && l2n) GPV_CUDA(cudaMemcpyAsync(h->level2_inout, out->d_level2_inout, l2n, cudaMemcpyDeviceToHost, st));
-	if (h->level1_normal && out->d_level1_normal) GPV_CUDA(cudaMemcpyAsync(h->level1_normal, out->d_level1_normal, cells * 3, cudaMemcpyDeviceToHost, st));
-	if (h->level2_normal && out->d_level2_normal && l2n) GPV_CUDA(cudaMemcpyAsync(h->level2_normal, out->d_level2_normal, l2n * 3, cudaMemcpyDeviceToHost, st));
+	// every stream goes to the host from inside the pipeline (Level-1 streams during Level-2, Level-2 chunk by chunk)
+	if (voxelize_impl(c, c->scratch.as<float>(), mesh->n_tri, mesh->bbox_min, mesh->bbox_max, mesh->max_model_size, prm, stream, out, h)) return 1;
 	GPV_CUDA(cudaStreamSynchronize(st));
 	return 0;
 }

@@ -654,6 +654,7 @@ struct L2IO {
 	const unsigned* colOff; const int* colCount; const int* colTris;
 	const float* cx; const float* cy; const float* cz;
 	unsigned char* l2State; // nBoundary * n2^3 file bytes
+	int bBegin;             // this launch refines boundary ranks [bBegin, nBoundary)
 	int nBoundary;
 	Totals* totals;
 };
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(kL2Threads) k_l2(GridP g, L2IO io)
 	uint2* sQueue = reinterpret_cast<uint2*>(sSat + G * rows + ((4 - ((G * 3 * n2 + 2 * G * rows) & 3)) & 3)); // [kL2Threads*kL2Batch] (item|plo|phi, triangle), 16-byte aligned
 	int* sQn = reinterpret_cast<int*>(sQueue + kL2Threads * kL2Batch);              // queue fill
 	const int tid = threadIdx.x;
-	const long long b0 = (long long)blockIdx.x * G;
+	const long long b0 = io.bBegin + (long long)blockIdx.x * G;
 
 	for (int k = tid; k < G * 3 * n2; k += kL2Threads) {
 		int gi = k / (3 * n2), rem = k - gi * 3 * n2, ax = rem / n2, p = rem - ax * n2;

@@ -88,3 +88,49 @@ def test_zslabs_concatenate_to_whole(product, oracle, ctx, tmp_path_factory):
             base += s.nb
         for k in parts:
             assert np.array_equal(np.concatenate(parts[k]), w[k]), (R, k)
+
+
+@pytest.mark.parametrize("name,l1,l2", [("cessna", 64, 4), ("cessna", 256, 16), ("torus", 32, 4)])
+def test_host_call_delivers_the_same_streams(product, oracle, ctx, tmp_path_factory, name, l1, l2):
+    """gpv_voxelize_host (H2D + pipeline + chunked, overlapped D2H) must hand the host exactly what the device holds."""
+    from gpview_b200 import binding as B
+    path = mesh_path(name, tmp_path_factory.getbasetemp())
+    mesh = product.load_mesh(path)
+    info, _ = golden("%s_%d_%d" % (name, l1, l2))
+    cells = int(np.prod(info["num_div"])); nb = info["l1_boundary"]; n23 = l2 ** 3
+    l1s = np.full(cells, 7, np.uint8); pre = np.full(cells, -1, np.int32); bi = np.full(nb, -1, np.int32)
+    l2s = np.full(nb * n23, 7, np.uint8); n1 = np.full(cells * 3, 7, np.uint8); n2 = np.full(nb * n23 * 3, 7, np.uint8)
+    hs = B.CHostStreams(l1s.ctypes.data, pre.ctypes.data, bi.ctypes.data, l2s.ctypes.data, n1.ctypes.data, n2.ctypes.data, l2s.nbytes, nb)
+    res = ctx.voxelize_host(mesh, product.Params(l1, l2, product.GPV_NORMALS), hs)
+    assert res.counts == [info["l1_inside"], info["l1_boundary"], info["l2_inside"], info["l2_boundary"]]
+    s = info["streams"]
+    assert sha(l1s) == s["Level1InOut"]["sha256"] and sha(pre) == s["Level1BoundaryPrefixSum"]["sha256"] and sha(bi) == s["BoundaryIndex"]["sha256"]
+    assert sha(l2s) == s["Level2InOut"]["sha256"]
+    assert sha(n1) == s["Level1Normal"]["sha256"] and sha(n2) == s["Level2Normal"]["sha256"]
+    # too-small host buffers are refused, not overrun
+    hs2 = B.CHostStreams(l1s.ctypes.data, pre.ctypes.data, bi.ctypes.data, l2s.ctypes.data, None, None, l2s.nbytes - 1, nb)
+    with pytest.raises(product.GpvError):
+        ctx.voxelize_host(mesh, product.Params(l1, l2, 0), hs2)
+
+
+def test_save_from_gpu_matches_reference_files(product, oracle, ctx, tmp_path_factory, tmp_path):
+    """mesh file -> gpv_voxelize_host -> gpv_save: the six ObjN* files byte-identical to the oracle's writer (== the
+    reference's Object::SaveVoxelization, tests/test_oracle_ref.py)."""
+    import filecmp, os
+    from gpview_b200 import binding as B
+    path = mesh_path("block", tmp_path_factory.getbasetemp())
+    mesh = product.load_mesh(path)
+    ores = oracle.OracleMesh(path).voxelize(32, 4, oracle.FILL_CERTIFIED, 4)
+    cells, nb, n23 = ores.cells, ores.nb, ores.n23
+    bufs = [np.zeros(cells, np.uint8), np.zeros(cells, np.int32), np.zeros(nb, np.int32), np.zeros(nb * n23, np.uint8), np.zeros(cells * 3, np.uint8),
+            np.zeros(nb * n23 * 3, np.uint8)]
+    hs = B.CHostStreams(*[b.ctypes.data for b in bufs], bufs[3].nbytes, nb)
+    res = ctx.voxelize_host(mesh, product.Params(32, 4, product.GPV_NORMALS), hs)
+    d1, d2 = tmp_path / "gpu", tmp_path / "ora"
+    d1.mkdir(); d2.mkdir()
+    B.save(mesh, res, hs, 3, str(d1))
+    ores.save(3, str(d2))
+    names = sorted(os.listdir(d1))
+    assert len(names) == 6 and names == sorted(os.listdir(d2))
+    for n in names:
+        assert filecmp.cmp(d1 / n, d2 / n, shallow=False), n
