@@ -4,16 +4,19 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--l1 256 --l2 16 --mesh cessna|sphere|torus|cad]
 
 One "step" = one full voxelization of the model (Level-1 SAT binning, parity fill, boundary compaction, Level-2
-refinement), triangles resident in HBM when the timed region starts, outputs resident in HBM when it ends.
-Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+refinement), triangles resident in HBM when the timed region starts, outputs resident in HBM when it ends (N > 1: gathered
+on rank 0 over NCCL).  Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   roofline      dominant kernel (k_l2): algorithmic tri-box FLOPs (124 per reference-equivalent test) over
-                its CUDA-event time, against the non-FMA FP32 issue rate measured live by gpv_measure_fp32_peak
+                its CUDA-event time (events recorded around the kernel on the launching stream, inside the timed steps),
+                against the non-FMA FP32 issue rate measured live by gpv_measure_fp32_peak
   roofline_hbm  the same launch's output bytes against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the reference's own TriBoxOverlap object code (oracle/_ref) -- or the oracle port when _ref is absent --
-                inside the Level-2 loop nest on a bounded sample of boundary cells, all host threads
-  e2e           the same metric through gpv_voxelize_host: pinned HOST triangles in, HOST streams out, copies timed
-N > 1 (torchrun): the grid is cut into z-slabs balanced by boundary-cell count, one rank per GPU; the Level-1 passes are
-replicated (cheap), Level-2 is sharded, slab pieces are gathered on rank 0 over NCCL inside the timed region.
+                inside the Level-2 loop nest on a bounded sample of boundary cells, all host threads (rank 0, N = 1)
+  e2e           the same metric through gpv_voxelize_host: pinned HOST triangles in, HOST streams out, copies timed.
+                N > 1: every rank delivers the byte range of its z-slab to its own pinned host buffer over its own PCIe
+                link (ranges are disjoint and ordered, prefix sums made global with the all-gathered boundary counts)
+N > 1 (torchrun): the grid is cut into z-slabs balanced by Level-2 cost, one rank per GPU; the Level-1 passes are
+replicated (cheap), Level-2 is sharded.
 """
 import argparse
 import ctypes as C
@@ -29,7 +32,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FLOPS_PER_TRIBOX = 124  # 66 MUL + 58 ADD/SUB, SURVEY.md 8(a8)
 
@@ -52,7 +54,7 @@ def make_mesh_file(name, tmp):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons while the GPU runs the benchmark steps (B200_PROFILING.md recipe)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -61,7 +63,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -69,21 +71,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def count(self, t0):
+        return sum(1 for t, r in self.rows if t >= t0 and len(r) > 8)
+
+    def stop(self, t0, t1, extended):
         if self.p:
             self.p.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) > 8]
+        num = lambda s: float(s) if s.replace(".", "", 1).isdigit() else None
+        sm = [num(r[1]) for r in rows if num(r[1]) is not None]
+        mx = [num(r[2]) for r in rows if num(r[2]) is not None]
+        pw = [num(r[3]) for r in rows if num(r[3]) is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) > 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "window": "timed steps" + (" + %d extra untimed steps of the same work (the timed region is shorter than the sampling period)" % extended if extended else "")}
 
 
 def measured_peaks():
@@ -95,7 +103,7 @@ def measured_peaks():
 
 
 def ncu_traffic():
-    """dram bytes per k_l2 launch from the committed ncu --set full summary (profiles/), or None."""
+    """dram bytes per k_l2 launch from the committed ncu --set full summary (profiles/traffic.json), or {}."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
@@ -103,60 +111,43 @@ def ncu_traffic():
     return {}
 
 
-def cpu_baseline(mesh_path, l1, l2, threads, target_seconds=12.0):
-    """Time the reference's TriBoxOverlap (oracle/_ref, kind 'reference') in the Level-2 loop nest of
-    cuda/CUDAClassifyTessellation.cu:428-445 on a bounded sample of boundary cells; falls back to the oracle port."""
-    try:
-        from oracle import refbind
-        if not refbind.available():
-            raise RuntimeError("no _ref")
+def reference_timer(mesh_path, l1, l2, threads):
+    """(kind, n_boundary, fn(cells) -> (seconds, tests)): the reference's TriBoxOverlap object code (oracle/_ref) in the
+    Level-2 loop nest of cuda/CUDAClassifyTessellation.cu:428-445, or the oracle port when _ref was not built."""
+    from oracle import refbind
+    if refbind.available():
         o = refbind.RefObject(mesh_path)
         o.setup(l1, l2)
         o.l1_tribox()
         o.compact()
-        nb = o.nboundary()
-        s, n = o.time_l2_tribox(0, min(nb, 256), threads)  # calibrate
-        per_cell = s / max(1, min(nb, 256))
-        cells = int(max(256, min(nb, target_seconds / max(per_cell, 1e-9))))
-        s, n = o.time_l2_tribox(0, cells, threads)
-        o.close()
-        kind = "reference"
-    except Exception:
-        from oracle import oraclebind as O
-        m = O.OracleMesh(mesh_path)
-        r = m.voxelize(l1, l2, O.FILL_COLLIST | O.NO_L2 | O.NO_NORMALS, threads)
-        nb = r.nb
-        s, n = r.time_l2_tribox(0, min(nb, 256), threads)
-        per_cell = s / max(1, min(nb, 256))
-        cells = int(max(256, min(nb, target_seconds / max(per_cell, 1e-9))))
-        s, n = r.time_l2_tribox(0, cells, threads)
-        kind = "port"
+        return "reference", o.nboundary(), (lambda c: o.time_l2_tribox(0, c, threads))
+    from oracle import oraclebind as O
+    r = O.OracleMesh(mesh_path).voxelize(l1, l2, O.FILL_COLLIST | O.NO_L2 | O.NO_NORMALS, threads)
+    return "port", r.nb, (lambda c: r.time_l2_tribox(0, c, threads))
+
+
+def cpu_baseline(mesh_path, l1, l2, threads, target_seconds=12.0):
+    kind, nb, timer = reference_timer(mesh_path, l1, l2, threads)
+    s, n = timer(min(nb, 256))
+    cells = int(max(256, min(nb, target_seconds / max(s / max(1, min(nb, 256)), 1e-9))))
+    s, n = timer(cells)
     return {"value": n / s / 1e9, "unit": "G tri-box tests/s", "cores": threads, "kind": kind,
             "sample": "Level-2 SAT loop nest over the first %d of %d boundary cells (%d tests, %.2f s)" % (cells, nb, n, s)}
 
 
+def workload_config(args):
+    return {"workload": "%s Level1 %d + Level2 %d^3 (BASELINE.json configs[1] when cessna/256/16), .raw occupancy streams"
+                        % (args.mesh, args.l1, args.l2), "l1": args.l1, "l2": args.l2, "mesh": args.mesh,
+            "cache": "L2 flushed between timed steps (256 MiB memset); outputs (>=221 MB at 256/16) exceed L2"}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU TriBoxOverlap path on this box's host cores (all threads)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
-    tmp = tempfile.mkdtemp(prefix="gpvbench")
-    path = make_mesh_file(args.mesh, tmp)
-    from oracle import refbind
-    kind = "reference" if refbind.available() else "port"
-    if kind == "reference":
-        o = refbind.RefObject(path)
-        o.setup(args.l1, args.l2)
-        o.l1_tribox()
-        o.compact()
-        nb = o.nboundary()
-        timer = lambda c: o.time_l2_tribox(0, c, threads)
-    else:
-        from oracle import oraclebind as O
-        r = O.OracleMesh(path).voxelize(args.l1, args.l2, O.FILL_COLLIST | O.NO_L2 | O.NO_NORMALS, threads)
-        nb = r.nb
-        timer = lambda c: r.time_l2_tribox(0, c, threads)
+    path = make_mesh_file(args.mesh, tempfile.mkdtemp(prefix="gpvbench"))
+    kind, nb, timer = reference_timer(path, args.l1, args.l2, threads)
     s, n = timer(min(nb, 256))
     cells = int(max(256, min(nb, 1.0 / max(s / max(1, min(nb, 256)), 1e-9))))  # ~1 s per step
     for _ in range(args.warmup):
@@ -169,15 +160,9 @@ def run_reference_arm(args):
     sample = "Level-2 SAT loop nest (cuda/CUDAClassifyTessellation.cu:428-445) over %d of %d boundary cells per step" % (cells, nb)
     print(json.dumps({"impl": "reference", "metric": "G tri-box tests/s", "value": v, "unit": "G tri-box tests/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
-                      "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if args.mesh != "cessna" else "cessna.obj fixture",
+                      "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "cessna.obj fixture" if args.mesh == "cessna" else "synthetic",
                       "config": workload_config(args), "cpu_baseline": {"value": v, "unit": "G tri-box tests/s", "cores": threads, "kind": kind, "sample": sample},
                       "e2e": {"value": v, "unit": "G tri-box tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
-
-
-def workload_config(args):
-    return {"workload": "%s Level1 %d + Level2 %d^3 (BASELINE.json configs[1] when cessna/256/16), .raw streams, occupancy only"
-                        % (args.mesh, args.l1, args.l2), "l1": args.l1, "l2": args.l2, "mesh": args.mesh,
-            "cache": "L2 flushed between timed steps (256 MiB memset); outputs (>=221 MB at 256/16) exceed L2"}
 
 
 def main():
@@ -197,6 +182,7 @@ def main():
     import torch
     import gpview_b200 as gpv
     from gpview_b200 import binding as B
+    from gpview_b200 import sharded
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,25 +194,24 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    tmp = tempfile.mkdtemp(prefix="gpvbench")
-    path = make_mesh_file(args.mesh, tmp)
+    path = make_mesh_file(args.mesh, tempfile.mkdtemp(prefix="gpvbench"))
     mesh = gpv.load_mesh(path)
     ctx = gpv.Context(local)
+    L = gpv.lib()
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
     d_tris = ctx.upload(mesh)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    # ---- z-slab plan (N > 1): replicated Level-1 pre-pass gives per-layer Level-2 cost; cuts are deterministic
-    from gpview_b200 import sharded
+    # ---- z-slab plan (N > 1): the replicated Level-1 pre-pass gives the Level-2 cost per layer; cuts are deterministic
     z0, z1 = 0, 0
     whole = ctx.voxelize_device(d_tris, mesh, gpv.Params(args.l1, args.l2, gpv.GPV_NO_LEVEL2), sptr)
     nz = int(whole.num_div[2]); plane = int(whole.num_div[0]) * int(whole.num_div[1])
+    cuts = [0, nz]
     if world > 1:
         cuts = sharded.plan_slabs(sharded.layer_cost(whole.boundary_index(), whole.cell_off(), plane, nz), world)
         z0, z1 = cuts[rank], cuts[rank + 1]
     params = gpv.Params(args.l1, args.l2, gpv.GPV_PROFILE, z0, z1)  # CUDA events around every kernel, on the launching stream
-    phase_acc = {}
     gathered = {}
 
     def step():
@@ -243,14 +228,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        res = step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        res = step()
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches = 0
+    launches, phase_acc = 0, {}
+    t_timed0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xff)
         barrier()
@@ -261,76 +247,106 @@ def main():
         for ph, v in res.phase_ms.items():
             phase_acc[ph] = phase_acc.get(ph, 0.0) + v
     barrier()
+    # the timed region (tens of ms) is shorter than nvidia-smi's sampling period: keep the same work running, untimed, until
+    # the sampler has seen the GPU under this load
+    extended = 0
+    flag = torch.zeros(1, device="cuda")
+    while True:
+        need = 1.0 if (rank == 0 and sampler.p is not None and sampler.count(t_timed0) < 8 and extended < 400) else 0.0
+        flag.fill_(need)
+        if world > 1:
+            dist.broadcast(flag, 0)
+        if flag.item() == 0.0:
+            break
+        for _ in range(10):
+            step()
+        extended += 10
+    barrier()
+    t_timed1 = time.perf_counter()
+    clocks = sampler.stop(t_timed0, t_timed1, extended) if rank == 0 else None
+
     ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device="cuda", dtype=torch.float64)
     tests_local = torch.tensor([res.stats["l2_box_tests"]], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tests_local)
-    total_ms = float(ms.item())
+    ms_per_step = float(ms.item()) / args.steps
     tests = float(tests_local.item()) + res.stats["l1_box_tests"]  # Level-1 tests are replicated: counted once
-    ms_per_step = total_ms / args.steps
     value = tests / (ms_per_step * 1e-3) / 1e9
 
-    # ---- dominant kernel timed alone (its own CUDA events, L2 flushed): Level-2 refinement
-    roof = roof_hbm = None
-    e2e = None
-    clocks = sampler.stop() if rank == 0 else None
-    if rank == 0 and world == 1:
-        kt = {"k_l2_ms": phase_acc["l2"] / args.steps}
+    # ---- e2e: pinned host triangles in, host streams out, through gpv_voxelize_host (each rank: its slab, its PCIe link)
+    cells, nb, n23 = res.cells, res.nb, res.n23
+    hb = {k: L.gpv_alloc_host(n) for k, n in (("l1", cells), ("pre", cells * 4), ("bi", nb * 4 + 64), ("l2", nb * n23 + 64))}
+    pinned_tris = L.gpv_alloc_host(mesh.ntri * 36)
+    C.memmove(pinned_tris, C.cast(mesh.c.tris, C.c_void_p), mesh.ntri * 36)
+    pm = B.CMesh(mesh.c.n_tri, C.cast(pinned_tris, C.POINTER(C.c_float)), mesh.c.bbox_min, mesh.c.bbox_max, mesh.c.max_model_size, mesh.c.n_verts)
+    hs = B.CHostStreams(hb["l1"], hb["pre"], hb["bi"], hb["l2"], None, None, nb * n23 + 64, nb + 16)
+    r2 = B.CResult()
+    e2e_params = gpv.Params(args.l1, args.l2, 0, z0, z1)
+    pre_np = np.ctypeslib.as_array(C.cast(hb["pre"], C.POINTER(C.c_int32)), shape=(cells,))
+    nb_all = torch.zeros(world, dtype=torch.int64, device="cuda")
+
+    def e2e_step():
+        if L.gpv_voxelize_host(ctx.h, C.byref(pm), C.byref(e2e_params.c), sptr, C.byref(r2), C.byref(hs)):
+            raise SystemExit(L.gpv_last_error().decode())
+        if world > 1:  # slab-local prefix sums -> global: boundary counts of the lower slabs
+            mine = torch.tensor([r2.n_boundary], dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(nb_all, mine)
+            base = int(nb_all[:rank].sum().item())
+            if base:
+                np.add(pre_np, base, out=pre_np)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t_e2e = 0.0
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step()  # returns after the last D2H has landed (stream syncs inside)
+        if world > 1:
+            dist.barrier()
+        t_e2e += time.perf_counter() - t0
+    te = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+    dsum = torch.tensor([float(cells + cells * 4 + nb * 4 + nb * n23)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(dsum)
+    e2e_ms = 1e3 * float(te.item()) / args.steps
+    got = np.ctypeslib.as_array(C.cast(hb["l2"], C.POINTER(C.c_uint8)), shape=(nb * n23,))
+    assert int((got == 254).sum()) == res.counts[3], "e2e host stream does not match the device counts"
+    e2e = {"value": tests / (e2e_ms * 1e-3) / 1e9, "unit": "G tri-box tests/s", "ms_per_model": e2e_ms,
+           "h2d_bytes_per_step": mesh.ntri * 36 * world, "d2h_bytes_per_step": int(dsum.item()),
+           "timing": "host wall clock around gpv_voxelize_host, max over ranks (pinned buffers both ways; Level-2 D2H overlaps the refinement; "
+                     "the call returns after the last byte has landed)"}
+    for p in list(hb.values()) + [pinned_tris]:
+        L.gpv_free_host(p)
+
+    if rank == 0:
+        k_l2_ms = phase_acc["l2"] / args.steps
         fp32_peak = ctx.fp32_peak()
         hbm_peak, hbm_src = measured_peaks()
         traffic = ncu_traffic()
         flops = FLOPS_PER_TRIBOX * res.stats["l2_box_tests"]
-        ach = flops / (kt["k_l2_ms"] * 1e-3) / 1e12
-        roof = {"kernel": "k_l2 (Level-2 refinement: parity rays + hoisted SAT)", "bound": "fp32", "achieved": ach, "peak": fp32_peak / 1e12,
-                "unit": "TFLOP/s", "frac": ach / (fp32_peak / 1e12), "traffic": traffic.get("k_l2_dram_bytes"),
+        ach = flops / (k_l2_ms * 1e-3) / 1e12
+        roof = {"kernel": "k_l2 (Level-2 refinement: parity rays + hoisted SAT)" + (" on rank 0's slab" if world > 1 else ""), "bound": "fp32",
+                "achieved": ach, "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": ach / (fp32_peak / 1e12),
+                "traffic": traffic.get("k_l2_dram_bytes") if world == 1 else None,
                 "peak_source": "non-FMA FP32 issue rate measured live (gpv_measure_fp32_peak: independent FMUL/FADD chains); "
                                "MEASURED_PEAKS.json has no FP32 entry",
-                "algorithmic": "%d reference-equivalent tri-box tests x 124 FLOP; the kernel hoists the x-independent part of each test "
-                               "per sub-voxel row and exits early, so frac can exceed what executed-instruction counts suggest" % res.stats["l2_box_tests"],
-                "kernel_ms": kt["k_l2_ms"], "share_of_step": kt["k_l2_ms"] / ms_per_step}
+                "algorithmic": "%d reference-equivalent tri-box tests x 124 FLOP per launch; the kernel skips tests that certified plane culling proves "
+                               "negative and hoists the x-independent part of the rest, so frac can exceed 1 (executed instruction counts: profiles/)"
+                               % res.stats["l2_box_tests"],
+                "kernel_ms": k_l2_ms, "share_of_step": k_l2_ms / ms_per_step}
         out_bytes = res.nb * res.n23
-        roof_hbm = {"kernel": "k_l2", "bound": "hbm", "achieved": out_bytes / (kt["k_l2_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": out_bytes / (kt["k_l2_ms"] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("k_l2_dram_bytes"), "peak_source": hbm_src,
-                    "algorithmic": "1 B per Level-2 voxel written (%d B)" % out_bytes}
-        # ---- e2e: pinned host triangles in, host streams out, through gpv_voxelize_host
-        L = gpv.lib()
-        cells, nb, n23 = res.cells, res.nb, res.n23
-        hb = {k: L.gpv_alloc_host(n) for k, n in (("l1", cells), ("pre", cells * 4), ("bi", nb * 4 + 64), ("l2", nb * n23 + 64))}
-        pinned_tris = L.gpv_alloc_host(mesh.ntri * 36)
-        C.memmove(pinned_tris, C.cast(mesh.c.tris, C.c_void_p), mesh.ntri * 36)
-        pm = B.CMesh(mesh.c.n_tri, C.cast(pinned_tris, C.POINTER(C.c_float)), mesh.c.bbox_min, mesh.c.bbox_max, mesh.c.max_model_size, mesh.c.n_verts)
-        hs = B.CHostStreams(hb["l1"], hb["pre"], hb["bi"], hb["l2"], None, None, nb * n23 + 64, nb + 16)
-        r2 = B.CResult()
-        def e2e_step():
-            rc = L.gpv_voxelize_host(ctx.h, C.byref(pm), C.byref(params.c), sptr, C.byref(r2), C.byref(hs))
-            if rc:
-                raise SystemExit(L.gpv_last_error().decode())
-        for _ in range(args.warmup):
-            e2e_step()
-        torch.cuda.synchronize()
-        t_e2e = 0.0
-        for k in range(args.steps):
-            flush.fill_(k & 0xff)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            e2e_step()  # returns after the last D2H has landed (stream sync inside)
-            t_e2e += time.perf_counter() - t0
-        e2e_ms = 1e3 * t_e2e / args.steps
-        got = np.ctypeslib.as_array(C.cast(hb["l2"], C.POINTER(C.c_uint8)), shape=(nb * n23,))
-        assert int((got == 254).sum()) == res.counts[3], "e2e host stream does not match the device counts"
-        e2e = {"value": tests / (e2e_ms * 1e-3) / 1e9, "unit": "G tri-box tests/s", "ms_per_model": e2e_ms,
-               "h2d_bytes_per_step": mesh.ntri * 36, "d2h_bytes_per_step": int(cells + cells * 4 + nb * 4 + nb * n23),
-               "timing": "host wall clock around gpv_voxelize_host (pinned buffers both ways; the call ends with a stream sync)"}
-        for p in hb.values():
-            L.gpv_free_host(p)
-        L.gpv_free_host(pinned_tris)
-
-    if rank == 0:
+        roof_hbm = {"kernel": "k_l2", "bound": "hbm", "achieved": out_bytes / (k_l2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": out_bytes / (k_l2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("k_l2_dram_bytes") if world == 1 else None,
+                    "peak_source": hbm_src, "algorithmic": "1 B per Level-2 voxel written (%d B)" % out_bytes}
         line = {"metric": "G tri-box tests/s", "value": value, "unit": "G tri-box tests/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "ms_per_model": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "cessna.obj fixture (reference sample mesh)" if args.mesh == "cessna" else "synthetic",
-                "config": dict(workload_config(args), parallelism="z-slabs x%d, Level-1 replicated, NCCL gather to rank 0" % world if world > 1 else "1 GPU",
+                "config": dict(workload_config(args), parallelism=("z-slabs x%d (cuts %s), Level-1 replicated, NCCL gather to rank 0" % (world, cuts)) if world > 1 else "1 GPU",
                                tri_box_tests_per_model=int(tests), triangles=mesh.ntri, grid=[int(x) for x in res.num_div]),
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_hbm": roof_hbm,
                 "phase_ms": {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0},
