@@ -134,3 +134,29 @@ def test_save_from_gpu_matches_reference_files(product, oracle, ctx, tmp_path_fa
     assert len(names) == 6 and names == sorted(os.listdir(d2))
     for n in names:
         assert filecmp.cmp(d1 / n, d2 / n, shallow=False), n
+
+
+def test_cli_writes_the_reference_file_set(product, oracle, tmp_path_factory, tmp_path):
+    """tools/gpview_voxelize (the headless stand-in for GPView's `t` key, C++ Object facade over the C ABI) on two meshes: file
+    names follow GPView's objID numbering (-1, 0, ...) and every file equals the oracle's writer byte for byte."""
+    import filecmp, os, subprocess
+    from util import ROOT
+    exe = os.path.join(ROOT, "tools", "gpview_voxelize")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tools")])
+    paths = [mesh_path("torus", tmp_path_factory.getbasetemp()), mesh_path("sphere", tmp_path_factory.getbasetemp())]
+    out = tmp_path / "cli"
+    out.mkdir()
+    log = subprocess.run([exe, "--l1", "32", "--l2", "4", "--out", str(out)] + paths, capture_output=True, text=True)
+    assert log.returncode == 0, log.stderr
+    assert "Boundary Voxels Level2" in log.stdout
+    for k, p in enumerate(paths):
+        ref = tmp_path / ("ora%d" % k)
+        ref.mkdir()
+        oracle.OracleMesh(p).voxelize(32, 4, oracle.FILL_CERTIFIED, 4).save(k - 1, str(ref))
+        names = sorted(os.listdir(ref))
+        assert len(names) == 6
+        for n in names:
+            assert filecmp.cmp(ref / n, out / n, shallow=False), n
+    bad = subprocess.run([exe, str(tmp_path / "nope.obj")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "Unable to open file" in bad.stderr
