@@ -46,11 +46,16 @@ class CHostStreams(C.Structure):
                 ("level1_normal", C.c_void_p), ("level2_normal", C.c_void_p), ("level2_capacity", C.c_int64), ("boundary_capacity", C.c_int64)]
 
 
+class CBatchStats(C.Structure):
+    _fields_ = [("models_done", C.c_int64), ("models_failed", C.c_int64), ("models_skipped", C.c_int64), ("seconds", C.c_double),
+                ("parse_seconds", C.c_double), ("gpu_seconds", C.c_double), ("save_seconds", C.c_double)]
+
+
 # every symbol include/gpview_b200.h declares (tests/test_abi_symbols.py checks the header against this and the .so)
 NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh",
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
-                  "gpv_save", "gpv_measure_fp32_peak", "gpv_measure_copy_peak"]
+                  "gpv_save", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak"]
 COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
 
 _lib = None
@@ -89,6 +94,8 @@ def lib():
         L.gpv_voxelize_device.argtypes = [vp, vp, C.c_int64, fp, fp, C.c_float, C.POINTER(CParams), vp, C.POINTER(CResult)]
         L.gpv_voxelize_host.argtypes = [vp, C.POINTER(CMesh), C.POINTER(CParams), vp, C.POINTER(CResult), C.POINTER(CHostStreams)]
         L.gpv_save.argtypes = [C.POINTER(CMesh), C.POINTER(CResult), C.POINTER(CHostStreams), C.c_int, C.c_char_p]
+        L.gpv_voxelize_batch.argtypes = [C.POINTER(C.c_char_p), C.c_int64, C.POINTER(CParams), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int,
+                                         C.POINTER(CBatchStats)]
         L.gpv_measure_fp32_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         L.gpv_measure_copy_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         _lib = L
@@ -257,6 +264,18 @@ class Context:
         v = C.c_double()
         _check(lib().gpv_measure_copy_peak(self.h, None, C.byref(v)))
         return v.value
+
+
+def voxelize_batch(paths, params, devices=(0,), threads=4, out_dir=None, first_obj_id=0, skip_existing=False):
+    """gpv_voxelize_batch: returns the stats dict; raises GpvError if a model failed."""
+    arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    dev = (C.c_int * len(devices))(*devices)
+    st = CBatchStats()
+    rc = lib().gpv_voxelize_batch(arr, len(paths), C.byref(params.c), dev, len(devices), threads, os.fsencode(out_dir) if out_dir else None, first_obj_id,
+                                  int(skip_existing), C.byref(st))
+    stats = {k: getattr(st, k) for k, _ in CBatchStats._fields_}
+    _check(rc)
+    return stats
 
 
 def save(mesh, result, host, obj_id, directory):

@@ -1,0 +1,101 @@
+// gpview_b200/csrc/gpv_batch.cpp -- batched dataset generation (BASELINE.json config 5: thousands of small .off/.obj meshes
+// -> the six ObjN* files each, for 3-D CNN training sets, README.md:22-27 of the reference).
+//
+// The reference does this one GLUT session per model.  Here a pool of host threads, each with its own gpv_ctx (device
+// buffers and stream), pinned staging buffers and file I/O, pulls paths from a shared counter: parse -> gpv_voxelize_host
+// -> gpv_save.  Contexts on the same device overlap each other's kernels, copies and host work; devices are assigned
+// round-robin, so one call drives every GPU of the box (models are independent: no collective).
+// Restartable: with skip_existing, a model whose VoxelConfig file is already there is not recomputed.
+#include "../../include/gpview_b200.h"
+#include "gpv_internal.h"
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <sys/stat.h>
+
+namespace {
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct Pinned {
+	void* p = nullptr; int64_t cap = 0;
+	bool ensure(int64_t bytes) { if (bytes <= cap) return true; gpv_free_host(p); p = gpv_alloc_host(bytes + bytes / 4 + 4096); cap = p ? bytes + bytes / 4 + 4096 : 0; return p != nullptr; }
+	~Pinned() { gpv_free_host(p); }
+};
+}
+
+extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, const gpv_params* params, const int* devices, int n_devices, int threads,
+                                  const char* out_dir, int first_obj_id, int skip_existing, gpv_batch_stats* stats)
+{
+	if (!paths || n_paths <= 0 || !params || n_devices <= 0 || threads <= 0) return gpv::fail("gpv_voxelize_batch: bad arguments");
+	std::atomic<int64_t> next(0), done(0), failed(0), skipped(0);
+	std::mutex errMu;
+	std::string firstErr;
+	double tParse = 0, tGpu = 0, tSave = 0;
+	const double t0 = now();
+	auto worker = [&](int w) {
+		gpv_ctx* ctx = nullptr;
+		if (gpv_create(devices[w % n_devices], &ctx)) { std::lock_guard<std::mutex> g(errMu); if (firstErr.empty()) firstErr = gpv_last_error(); return; }
+		Pinned l1, pre, bi, l2, n1, n2;
+		double parse = 0, gpu = 0, save = 0;
+		const bool wantN = (params->flags & GPV_NORMALS) != 0, wantL2 = !(params->flags & GPV_NO_LEVEL2) && params->voxel_count2 > 0;
+		for (;;) {
+			const int64_t i = next.fetch_add(1);
+			if (i >= n_paths) break;
+			const int objID = first_obj_id + (int)i;
+			if (skip_existing && out_dir) {
+				struct stat sb;
+				std::string cfg = std::string(out_dir) + "/Obj" + std::to_string(objID) + "VoxelConfig.txt";
+				if (stat(cfg.c_str(), &sb) == 0 && sb.st_size > 0) { skipped++; continue; }
+			}
+			auto bail = [&]() { failed++; std::lock_guard<std::mutex> g(errMu); if (firstErr.empty()) firstErr = std::string(paths[i]) + ": " + gpv_last_error(); };
+			double a = now();
+			gpv_mesh mesh;
+			if (gpv_load_mesh(paths[i], &mesh)) { bail(); continue; }
+			double b = now();
+			parse += b - a;
+			gpv_grid g;
+			if (gpv_make_grid(mesh.bbox_min, mesh.bbox_max, mesh.max_model_size, params->voxel_count, wantL2 ? params->voxel_count2 : 1, &g)) { bail(); gpv_free_mesh(&mesh); continue; }
+			const int64_t cells = (int64_t)g.num_div[0] * g.num_div[1] * g.num_div[2], n23 = (int64_t)g.n2 * g.n2 * g.n2;
+			int64_t capB = std::max<int64_t>(1024, l2.cap / std::max<int64_t>(1, n23)); // boundary cells the Level-2 buffer can take
+			bool ok = false;
+			gpv_result res;
+			for (int attempt = 0; attempt < 2 && !ok; attempt++) {
+				if (!l1.ensure(cells) || !pre.ensure(cells * 4) || !bi.ensure(capB * 4) || (wantL2 && !l2.ensure(capB * n23)) || (wantN && !n1.ensure(cells * 3)) ||
+				    (wantN && wantL2 && !n2.ensure(capB * n23 * 3))) break;
+				gpv_host_streams h{ (uint8_t*)l1.p, (int32_t*)pre.p, (int32_t*)bi.p, wantL2 ? (uint8_t*)l2.p : nullptr, wantN ? (uint8_t*)n1.p : nullptr,
+					                (wantN && wantL2) ? (uint8_t*)n2.p : nullptr, capB * n23, capB };
+				if (gpv_voxelize_host(ctx, &mesh, params, nullptr, &res, &h) == 0) {
+					ok = true;
+					double c = now();
+					gpu += c - b;
+					if (out_dir && gpv_save(&mesh, &res, &h, objID, out_dir)) ok = false;
+					save += now() - c;
+				} else {
+					// too small a Level-2 buffer: the call reports it after the Level-1 pass; size it from a Level-1-only run
+					gpv_params p1 = *params; p1.flags |= GPV_NO_LEVEL2; p1.flags &= ~GPV_NORMALS;
+					gpv_host_streams none{};
+					if (gpv_voxelize_host(ctx, &mesh, &p1, nullptr, &res, &none)) break;
+					capB = res.n_boundary + 16;
+				}
+			}
+			if (!ok) bail(); else done++;
+			gpv_free_mesh(&mesh);
+		}
+		gpv_destroy(ctx);
+		std::lock_guard<std::mutex> g(errMu);
+		tParse += parse; tGpu += gpu; tSave += save;
+	};
+	std::vector<std::thread> pool;
+	for (int w = 0; w < threads; w++) pool.emplace_back(worker, w);
+	for (auto& t : pool) t.join();
+	if (stats) {
+		stats->models_done = done; stats->models_failed = failed; stats->models_skipped = skipped;
+		stats->seconds = now() - t0; stats->parse_seconds = tParse; stats->gpu_seconds = tGpu; stats->save_seconds = tSave;
+	}
+	if (failed > 0 || (done == 0 && skipped == 0)) return gpv::fail(firstErr.empty() ? "gpv_voxelize_batch: no model processed" : firstErr);
+	return 0;
+}

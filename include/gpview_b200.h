@@ -158,6 +158,17 @@ int gpv_voxelize_host(gpv_ctx* ctx, const gpv_mesh* mesh, const gpv_params* para
 /* Object::SaveVoxelization (src/Object.cpp:2934-3075): the six ObjN*.{txt,raw} files into `dir` from host streams */
 int gpv_save(const gpv_mesh* mesh, const gpv_result* res, const gpv_host_streams* host, int obj_id, const char* dir);
 
+/* Batched dataset generation (BASELINE.json config 5): `threads` host threads, each with its own ctx on devices[w % n_devices],
+ * pull paths from a shared queue: load -> gpv_voxelize_host -> gpv_save(out_dir, obj id = first_obj_id + index).  out_dir NULL:
+ * nothing is written.  skip_existing: a model whose ObjNVoxelConfig.txt exists is skipped (restartable).  The *_seconds are
+ * summed over threads.  Returns non-zero if any model failed (message of the first failure in gpv_last_error()). */
+typedef struct {
+	int64_t models_done, models_failed, models_skipped;
+	double seconds, parse_seconds, gpu_seconds, save_seconds;
+} gpv_batch_stats;
+int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, const gpv_params* params, const int* devices, int n_devices, int threads,
+                       const char* out_dir, int first_obj_id, int skip_existing, gpv_batch_stats* stats);
+
 /* micro-benchmarks used for the roofline denominators (bench.py): achieved non-FMA FP32 lane-ops/s and copy GB/s */
 int gpv_measure_fp32_peak(gpv_ctx* ctx, void* stream, double* ops_per_s);
 int gpv_measure_copy_peak(gpv_ctx* ctx, void* stream, double* gb_per_s);

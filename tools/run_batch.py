@@ -1,0 +1,76 @@
+#!/usr/bin/env python3
+"""Config 5 (BASELINE.json): batched dataset generation -- N drilled-block .off meshes (~5k triangles) at Level-1 64 + Level-2 4^3.
+
+  python tools/run_batch.py [--models 2000] [--distinct 100] [--threads 16] [--gpus 1] [--save] [--check 5]
+
+Writes `distinct` seeded meshes (gpview_b200.meshgen.drilled_block, seed = SEED_BASE + i) once, then runs gpv_voxelize_batch over
+`models` paths cycling through them (every path is parsed again: parsing is part of the pipeline).  --check K compares the
+files of the first K models with the oracle's writer (test infrastructure).  Prints one JSON line with models/s."""
+import argparse
+import filecmp
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--models", type=int, default=2000)
+    ap.add_argument("--distinct", type=int, default=100)
+    ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--l1", type=int, default=64)
+    ap.add_argument("--l2", type=int, default=4)
+    ap.add_argument("--save", action="store_true")
+    ap.add_argument("--normals", action="store_true")
+    ap.add_argument("--check", type=int, default=0)
+    a = ap.parse_args()
+    import gpview_b200 as gpv
+    from gpview_b200 import binding as B, meshgen as M
+    d = tempfile.mkdtemp(prefix="gpvbatch")
+    t0 = time.time()
+    files = []
+    for i in range(a.distinct):
+        V, F = M.drilled_block(seed=M.SEED_BASE + i, n_seg=160, n_grid=36)
+        p = os.path.join(d, "block%05d.off" % i)
+        M.write_off(p, V, F)
+        files.append(p)
+    gen_s = time.time() - t0
+    paths = [files[i % a.distinct] for i in range(a.models)]
+    out = os.path.join(d, "out") if (a.save or a.check) else None
+    if out:
+        os.makedirs(out)
+    flags = gpv.GPV_NORMALS if a.normals else 0
+    B.voxelize_batch(paths[:min(len(paths), 4 * a.threads)], gpv.Params(a.l1, a.l2, flags), list(range(a.gpus)), a.threads, None)  # warm-up: contexts, pools
+    st = B.voxelize_batch(paths, gpv.Params(a.l1, a.l2, flags), list(range(a.gpus)), a.threads, out, 0, False)
+    line = {"config": "drilled-block .off meshes (~5k triangles), Level1 %d + Level2 %d^3" % (a.l1, a.l2), "models": a.models, "distinct_meshes": a.distinct,
+            "threads": a.threads, "gpus": a.gpus, "saved": bool(out), "normals": a.normals, "models_per_s": st["models_done"] / st["seconds"],
+            "seconds": st["seconds"], "per_model_ms_summed_over_threads": {k: 1e3 * st[k + "_seconds"] / max(1, st["models_done"]) for k in ("parse", "gpu", "save")},
+            "mesh_generation_s": gen_s, "failed": st["models_failed"]}
+    if a.check:
+        from oracle import oraclebind as O
+        ok = True
+        for i in range(min(a.check, a.models)):
+            ref = os.path.join(d, "ref%d" % i)
+            os.makedirs(ref)
+            O.OracleMesh(paths[i]).voxelize(a.l1, a.l2, O.FILL_CERTIFIED | (0 if a.normals else O.NO_NORMALS), 2).save(i, ref)
+            for n in os.listdir(ref):
+                if not a.normals and "Normal" in n:
+                    continue
+                ok = ok and filecmp.cmp(os.path.join(ref, n), os.path.join(out, n), shallow=False)
+        line["files_match_oracle"] = ok
+        # restart: nothing is recomputed when the outputs exist
+        st2 = B.voxelize_batch(paths, gpv.Params(a.l1, a.l2, flags), list(range(a.gpus)), a.threads, out, 0, True)
+        line["restart_skipped"] = st2["models_skipped"]
+    print(json.dumps(line))
+    if a.check and not line["files_match_oracle"]:
+        raise SystemExit(1)
+
+
+if __name__ == "__main__":
+    main()
