@@ -65,6 +65,7 @@ struct gpv_ctx {
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
 	cudaStream_t copyStream = nullptr;  // D2H of finished streams overlaps the rest of the pipeline (gpv_voxelize_host)
+	cudaStream_t ownStream = nullptr;   // gpv_stream(): a non-blocking stream for callers that run several contexts side by side
 	cudaEvent_t evChunk[17] = {};
 };
 
@@ -97,6 +98,7 @@ extern "C" int gpv_create(int device, gpv_ctx** out)
 	GPV_CUDA(cudaHostAlloc((void**)&c->hTotals, sizeof(Totals), cudaHostAllocDefault));
 	if (c->totals.ensure(sizeof(Totals))) { delete c; return 1; }
 	GPV_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+	GPV_CUDA(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
 	for (cudaEvent_t& e : c->evChunk) GPV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	*out = c;
 	return 0;
@@ -114,8 +116,11 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	if (c->haveEvents) for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
 	for (cudaEvent_t e : c->evChunk) if (e) cudaEventDestroy(e);
 	if (c->copyStream) cudaStreamDestroy(c->copyStream);
+	if (c->ownStream) cudaStreamDestroy(c->ownStream);
 	delete c;
 }
+
+extern "C" void* gpv_stream(gpv_ctx* c) { return c ? (void*)c->ownStream : nullptr; }
 
 extern "C" void* gpv_alloc_host(int64_t bytes)
 {

@@ -8,6 +8,7 @@
 // Restartable: with skip_existing, a model whose VoxelConfig file is already there is not recomputed.
 #include "../../include/gpview_b200.h"
 #include "gpv_internal.h"
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -68,7 +69,7 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
 				    (wantN && wantL2 && !n2.ensure(capB * n23 * 3))) break;
 				gpv_host_streams h{ (uint8_t*)l1.p, (int32_t*)pre.p, (int32_t*)bi.p, wantL2 ? (uint8_t*)l2.p : nullptr, wantN ? (uint8_t*)n1.p : nullptr,
 					                (wantN && wantL2) ? (uint8_t*)n2.p : nullptr, capB * n23, capB };
-				if (gpv_voxelize_host(ctx, &mesh, params, nullptr, &res, &h) == 0) {
+				if (gpv_voxelize_host(ctx, &mesh, params, gpv_stream(ctx), &res, &h) == 0) {
 					ok = true;
 					double c = now();
 					gpu += c - b;
@@ -78,7 +79,7 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
 					// too small a Level-2 buffer: the call reports it after the Level-1 pass; size it from a Level-1-only run
 					gpv_params p1 = *params; p1.flags |= GPV_NO_LEVEL2; p1.flags &= ~GPV_NORMALS;
 					gpv_host_streams none{};
-					if (gpv_voxelize_host(ctx, &mesh, &p1, nullptr, &res, &none)) break;
+					if (gpv_voxelize_host(ctx, &mesh, &p1, gpv_stream(ctx), &res, &none)) break;
 					capB = res.n_boundary + 16;
 				}
 			}

@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(ScanIO io)
 // yields, src/Object.cpp:2705-2748; the GPU path's atomic slots are nondeterministic).  len <= 32: rank sort in
 // registers; longer: in-place bitonic network in the all-ascending "flip" form, valid for any length.
 // UNIQUE (column lists): drops duplicates (a triangle hits several cells of one column) and stores the unique count.
-constexpr int kSortSmem = 1024; // list length sorted in shared memory (4 KB per warp)
+constexpr int kSortSmem = 128; // longest list the warp-per-list kernel takes (rank sort in shared memory); longer ones go to k_sort_long
 
 template <bool UNIQUE>
 __global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restrict__ off, int nSeg, int* data, int* uniqueCount, int* longList, unsigned* longCount)
@@ -527,8 +527,8 @@ __global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restric
 		if (lane == 0) uniqueCount[seg] = __popc(km);
 		return;
 	}
-	// longer lists: bitonic network in this warp's slice of shared memory; lists beyond kSortSmem entries (a column under a
-	// pole of a finely tessellated body collects thousands of triangles) are handed to k_sort_long, one CTA per list
+	// lists beyond kSortSmem entries (a column under a pole of a finely tessellated body collects thousands of triangles)
+	// are handed to k_sort_long, one CTA of 1024 threads per list
 	if (len > kSortSmem) {
 		if (lane == 0) longList[atomicAdd(longCount, 1u)] = seg;
 		return;
@@ -542,8 +542,8 @@ __global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restric
 		a = sb;
 	}
 	// Rank (enumeration) sort: every element counts the elements that must precede it and is stored at that position.  All
-	// lanes read the same a[j] at the same time (shared-memory broadcast), there are no barriers between compare rounds, and
-	// for lists of this size it beats the bitonic network by 5-10x on the single warp that owns the list.
+	// lanes read the same a[j] at the same time (shared-memory broadcast) and there are no barriers between compare rounds:
+	// for lists of up to 128 entries (<= 512 rounds per lane) it beats a bitonic network on the single warp that owns the list.
 	if (!UNIQUE) {
 		for (int i = lane; i < len; i += 32) {
 			const int x = a[i];

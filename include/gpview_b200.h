@@ -126,6 +126,9 @@ int gpv_device_count(void);
 /* context: device buffers are pooled (grow-only) inside the ctx */
 int gpv_create(int device, gpv_ctx** out);
 void gpv_destroy(gpv_ctx* ctx);
+/* a non-blocking cudaStream_t owned by the ctx: pass it as `stream` when several contexts run side by side (the NULL stream is
+ * CUDA's legacy default stream and serialises them) */
+void* gpv_stream(gpv_ctx* ctx);
 
 /* loaders with the reference's semantics (Object::ReadObject src/Object.cpp:395-584, Object::ReadOFFObject :171-317);
  * gpv_load_mesh dispatches on the last three characters like main() (src/GPView.cpp:1642-1659) */

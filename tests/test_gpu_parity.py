@@ -160,3 +160,34 @@ def test_cli_writes_the_reference_file_set(product, oracle, tmp_path_factory, tm
             assert filecmp.cmp(ref / n, out / n, shallow=False), n
     bad = subprocess.run([exe, str(tmp_path / "nope.obj")], capture_output=True, text=True)
     assert bad.returncode == 1 and "Unable to open file" in bad.stderr
+
+
+@pytest.mark.parametrize("trial", range(6))
+def test_hostile_triangle_soups_match_brute_force_oracle(product, oracle, ctx, trial):
+    """Random triangle soups (not manifolds) with slivers, near-vertical walls, tiny and huge triangles, large coordinates:
+    exercises the ill-conditioned (test-every-column) path of the certified fill, long per-cell lists, footprints covering the
+    whole grid and every culling shortcut -- against the oracle's literal brute force (Object::ClassifyInOutCPU semantics)."""
+    rng = np.random.default_rng(100 + trial)
+    n = 400
+    scale = [1.0, 1.0, 50.0, 500.0, 1.0, 2000.0][trial]
+    t = rng.uniform(-1, 1, (n, 3, 3)) * scale
+    k = n // 5
+    t[:k, 2] = t[:k, 0] + (t[:k, 1] - t[:k, 0]) * rng.uniform(-0.5, 1.5, (k, 1)) + rng.normal(0, 1e-6 * scale, (k, 3))      # slivers
+    t[k:2 * k, 2, :2] = t[k:2 * k, 0, :2] + rng.normal(0, 1e-7 * scale, (k, 2))                                            # vertical walls
+    t[2 * k:3 * k] = t[2 * k:3 * k, :1] + rng.normal(0, 0.02 * scale, (k, 3, 3))                                            # small triangles
+    t[3 * k:3 * k + 5] *= 3.0                                                                                              # a few giants
+    tris = t.reshape(n, 9).astype(np.float32)
+    l1, l2 = [(24, 2), (20, 4), (16, 8), (12, 16), (28, 3), (24, 5)][trial]
+    mesh = product.mesh_from_triangles(tris)
+    om = oracle.OracleMesh(tris=tris)
+    assert np.array_equal(mesh.bbox_min, om.bmin) and np.array_equal(mesh.bbox_max, om.bmax)
+    res = ctx.voxelize(mesh, product.Params(l1, l2, product.GPV_NORMALS))
+    want = om.voxelize(l1, l2, oracle.FILL_BRUTE | oracle.L2_NAIVE, 8)
+    assert res.stats["fill_ill_conditioned"] == om.voxelize(l1, l2, oracle.FILL_CERTIFIED | oracle.NO_L2 | oracle.NO_NORMALS, 4).stats["fillIllConditioned"]
+    assert res.counts == want.counts
+    assert np.array_equal(res.level1_inout(), want.l1_state * 127)
+    assert np.array_equal(res.prefix(), want.prefix)
+    assert np.array_equal(res.level2_inout(), want.l2_state * 127)
+    assert np.array_equal(res.cell_tris(), want.cell_tris)
+    assert np.array_equal(res.level1_normal(), want.l1_normal)
+    assert np.array_equal(res.level2_normal(), want.l2_normal)
