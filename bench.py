@@ -194,8 +194,14 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    path = make_mesh_file(args.mesh, tempfile.mkdtemp(prefix="gpvbench"))
-    mesh = gpv.load_mesh(path)
+    if args.mesh == "cessna":  # through the reference-semantics OBJ loader, like the reference does
+        path = make_mesh_file(args.mesh, tempfile.mkdtemp(prefix="gpvbench"))
+        mesh = gpv.load_mesh(path)
+    else:  # large synthetic meshes are handed over as triangle arrays (same bbox rule as the loader; writing a 1 GB OBJ is not the point)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import run_config
+        path = None
+        mesh = gpv.mesh_from_triangles(run_config.make_tris(args.mesh))
     ctx = gpv.Context(local)
     L = gpv.lib()
     stream = torch.cuda.current_stream()
@@ -351,7 +357,7 @@ def main():
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_hbm": roof_hbm,
                 "phase_ms": {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0},
                 "counts": {"l1_inside": whole.counts[0], "l1_boundary": whole.counts[1]}}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and path is not None:
             line["cpu_baseline"] = cpu_baseline(path, args.l1, args.l2, os.cpu_count() or 1)
         print(json.dumps(line))
     ctx.free_device(d_tris)
