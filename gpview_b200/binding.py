@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgpview_b200.so")
+LIB_PATH = os.environ.get("GPVIEW_B200_LIB", os.path.join(HERE, "libgpview_b200.so"))  # override: A/B builds of the same ABI
 
 GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE = 1, 2, 4, 8
 

@@ -659,11 +659,14 @@ struct L2IO {
 	Totals* totals;
 };
 
+#ifndef GPV_L2_MINBLOCKS
+#define GPV_L2_MINBLOCKS 5 // 48 registers: 5 CTAs per SM measured 4-8 % faster than 4 (64 registers) on cessna 256/16 and sphere 512/8
+#endif
 constexpr int kL2Threads = 256;
 constexpr int kL2Batch = 8;   // triangles per queue round
 constexpr int kL2Stage = 256; // ray records staged per chunk (12 KB of the 16 KB queue area)
 
-__global__ void __launch_bounds__(kL2Threads) k_l2(GridP g, L2IO io)
+__global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2IO io)
 {
 	extern __shared__ unsigned char smemRaw[];
 	const int n2 = g.n2, rows = n2 * n2;
