@@ -46,6 +46,14 @@ class CHostStreams(C.Structure):
                 ("level1_normal", C.c_void_p), ("level2_normal", C.c_void_p), ("level2_capacity", C.c_int64), ("boundary_capacity", C.c_int64)]
 
 
+class CVoxelFile(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3), ("num_div", C.c_int * 3), ("grid_size", C.c_float * 3),
+                ("l1_inside", C.c_int64), ("l1_boundary", C.c_int64), ("has_level2", C.c_int), ("num_div2", C.c_int * 3), ("grid_size2", C.c_float * 3),
+                ("l2_inside", C.c_int64), ("l2_boundary", C.c_int64), ("cells", C.c_int64), ("n_boundary", C.c_int64), ("n23", C.c_int64),
+                ("level1_inout", C.POINTER(C.c_uint8)), ("level1_normal", C.POINTER(C.c_uint8)), ("prefix_sum", C.POINTER(C.c_int32)),
+                ("level2_inout", C.POINTER(C.c_uint8)), ("level2_normal", C.POINTER(C.c_uint8))]
+
+
 class CBatchStats(C.Structure):
     _fields_ = [("models_done", C.c_int64), ("models_failed", C.c_int64), ("models_skipped", C.c_int64), ("seconds", C.c_double),
                 ("parse_seconds", C.c_double), ("gpu_seconds", C.c_double), ("save_seconds", C.c_double)]
@@ -55,7 +63,7 @@ class CBatchStats(C.Structure):
 NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_stream", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh",
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
-                  "gpv_save", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak"]
+                  "gpv_save", "gpv_load_voxels", "gpv_free_voxels", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak"]
 COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
 
 _lib = None
@@ -264,6 +272,26 @@ class Context:
         v = C.c_double()
         _check(lib().gpv_measure_copy_peak(self.h, None, C.byref(v)))
         return v.value
+
+
+def load_voxels(directory, obj_id):
+    """gpv_load_voxels -> dict of numpy copies of the streams plus the VoxelConfig fields."""
+    v = CVoxelFile()
+    L = lib()
+    L.gpv_load_voxels.argtypes = [C.c_char_p, C.c_int, C.POINTER(CVoxelFile)]
+    L.gpv_free_voxels.argtypes = [C.POINTER(CVoxelFile)]; L.gpv_free_voxels.restype = None
+    _check(L.gpv_load_voxels(os.fsencode(directory), obj_id, C.byref(v)))
+    try:
+        cp = lambda p, n, dt: (np.ctypeslib.as_array(p, shape=(int(n),)).astype(dt, copy=True) if p and n else None)
+        l2n = int(v.n_boundary * v.n23)
+        return {"name": v.name.decode(), "num_div": list(v.num_div), "num_div2": list(v.num_div2) if v.has_level2 else None,
+                "bbox_min": list(v.bbox_min), "bbox_max": list(v.bbox_max), "grid_size": list(v.grid_size), "grid_size2": list(v.grid_size2),
+                "counts": [int(v.l1_inside), int(v.l1_boundary), int(v.l2_inside), int(v.l2_boundary)],
+                "level1_inout": cp(v.level1_inout, v.cells, np.uint8), "level1_normal": cp(v.level1_normal, v.cells * 3, np.uint8),
+                "prefix_sum": cp(v.prefix_sum, v.cells, np.int32), "level2_inout": cp(v.level2_inout, l2n, np.uint8),
+                "level2_normal": cp(v.level2_normal, l2n * 3, np.uint8)}
+    finally:
+        L.gpv_free_voxels(C.byref(v))
 
 
 def voxelize_batch(paths, params, devices=(0,), threads=4, out_dir=None, first_obj_id=0, skip_existing=False):

@@ -67,6 +67,7 @@ struct gpv_ctx {
 	cudaStream_t copyStream = nullptr;  // D2H of finished streams overlaps the rest of the pipeline (gpv_voxelize_host)
 	cudaStream_t ownStream = nullptr;   // gpv_stream(): a non-blocking stream for callers that run several contexts side by side
 	cudaEvent_t evChunk[17] = {};
+	bool sortAttrSet = false;
 };
 
 using namespace gpv;
@@ -287,11 +288,10 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		int* longCells = c->longList.as<int>() + 16;
 		int* longCols = longCells + nB;
 		GPV_CUDA(cudaMemsetAsync(longCnt, 0, 64, st));
-		static bool attrSet = false;
-		if (!attrSet) {
+		if (!c->sortAttrSet) { // function attributes are per device: once per context, not once per process
 			GPV_CUDA(cudaFuncSetAttribute(k_sort_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortLongSmem * 4));
 			GPV_CUDA(cudaFuncSetAttribute(k_sort_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortLongSmem * 4));
-			attrSet = true;
+			c->sortAttrSet = true;
 		}
 		if (nB > 0) {
 			k_sort_segments<false><<<(unsigned)((nB * 32 + 255) / 256), 256, 0, st>>>(c->bTriOff.as<unsigned>(), (int)nB, c->cellTris.as<int>(), nullptr, longCells, longCnt);

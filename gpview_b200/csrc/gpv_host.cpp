@@ -276,3 +276,64 @@ extern "C" int gpv_save(const gpv_mesh* mesh, const gpv_result* res, const gpv_h
 	             dump("Level2Normal.raw", h->level2_normal, l2n * 3, 127);
 	return ok ? 0 : gpv::fail("Unable to open output file for writing");
 }
+
+// ---- reader of the six-file set.  The reference can only read back one hard-coded 48x64x64 uchar grid
+// (Object::ReadRAWObject, src/Object.cpp:319-392); this generalises it by parsing ObjNVoxelConfig.txt (written by
+// SaveVoxelization, :3009-3022) for the sizes, so that outputs can be re-loaded, diffed and fed to a 3-D CNN loader.
+namespace {
+bool read_exact(const std::string& path, void* dst, size_t bytes)
+{
+	FILE* f = fopen(path.c_str(), "rb");
+	if (!f) return false;
+	fseek(f, 0, SEEK_END);
+	long sz = ftell(f);
+	fseek(f, 0, SEEK_SET);
+	bool ok = (size_t)sz == bytes && (bytes == 0 || fread(dst, 1, bytes, f) == bytes);
+	fclose(f);
+	return ok;
+}
+}
+
+extern "C" void gpv_free_voxels(gpv_voxel_file* v)
+{
+	if (!v) return;
+	free(v->level1_inout); free(v->level1_normal); free(v->prefix_sum); free(v->level2_inout); free(v->level2_normal);
+	v->level1_inout = v->level1_normal = v->level2_inout = v->level2_normal = nullptr;
+	v->prefix_sum = nullptr;
+}
+
+extern "C" int gpv_load_voxels(const char* dir, int obj_id, gpv_voxel_file* v)
+{
+	memset(v, 0, sizeof *v);
+	const std::string prefix = std::string(dir) + "/Obj" + std::to_string(obj_id);
+	FILE* f = fopen((prefix + "VoxelConfig.txt").c_str(), "r");
+	if (!f) return gpv::fail("Unable to open " + prefix + "VoxelConfig.txt");
+	long long a = 0, b = 0;
+	int n = fscanf(f, "%63s %f %f %f %f %f %f %d %d %d %f %f %f %lld %lld", v->name, &v->bbox_min[0], &v->bbox_min[1], &v->bbox_min[2], &v->bbox_max[0],
+	               &v->bbox_max[1], &v->bbox_max[2], &v->num_div[0], &v->num_div[1], &v->num_div[2], &v->grid_size[0], &v->grid_size[1], &v->grid_size[2], &a, &b);
+	if (n != 15) { fclose(f); return gpv::fail(prefix + "VoxelConfig.txt: malformed Level-1 header"); }
+	v->l1_inside = a; v->l1_boundary = b;
+	n = fscanf(f, "%d %d %d %f %f %f %lld %lld", &v->num_div2[0], &v->num_div2[1], &v->num_div2[2], &v->grid_size2[0], &v->grid_size2[1], &v->grid_size2[2], &a, &b);
+	fclose(f);
+	v->has_level2 = n == 8;
+	if (v->has_level2) { v->l2_inside = a; v->l2_boundary = b; }
+	else if (n > 0) return gpv::fail(prefix + "VoxelConfig.txt: malformed Level-2 block");
+	if (v->num_div[0] <= 0 || v->num_div[1] <= 0 || v->num_div[2] <= 0) return gpv::fail(prefix + "VoxelConfig.txt: bad resolution");
+	v->cells = (int64_t)v->num_div[0] * v->num_div[1] * v->num_div[2];
+	v->n_boundary = v->l1_boundary;
+	v->n23 = v->has_level2 ? (int64_t)v->num_div2[0] * v->num_div2[1] * v->num_div2[2] : 0;
+	auto grab = [&](const char* suffix, size_t bytes, void** dst, bool required) -> int {
+		*dst = malloc(bytes ? bytes : 1);
+		if (!*dst) return gpv::fail("out of host memory");
+		if (read_exact(prefix + suffix, *dst, bytes)) return 0;
+		free(*dst); *dst = nullptr;
+		return required ? gpv::fail(prefix + suffix + ": missing or not the size ObjNVoxelConfig.txt implies") : 0;
+	};
+	int rc = grab("Level1InOut.raw", (size_t)v->cells, (void**)&v->level1_inout, true) || grab("Level1Normal.raw", (size_t)v->cells * 3, (void**)&v->level1_normal, false);
+	if (!rc && v->has_level2)
+		rc = grab("Level1BoundaryPrefixSum.raw", (size_t)v->cells * 4, (void**)&v->prefix_sum, true) ||
+		     grab("Level2InOut.raw", (size_t)(v->n_boundary * v->n23), (void**)&v->level2_inout, true) ||
+		     grab("Level2Normal.raw", (size_t)(v->n_boundary * v->n23) * 3, (void**)&v->level2_normal, false);
+	if (rc) { gpv_free_voxels(v); return 1; }
+	return 0;
+}

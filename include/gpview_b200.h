@@ -161,6 +161,22 @@ int gpv_voxelize_host(gpv_ctx* ctx, const gpv_mesh* mesh, const gpv_params* para
 /* Object::SaveVoxelization (src/Object.cpp:2934-3075): the six ObjN*.{txt,raw} files into `dir` from host streams */
 int gpv_save(const gpv_mesh* mesh, const gpv_result* res, const gpv_host_streams* host, int obj_id, const char* dir);
 
+/* Reader of the six-file set written by gpv_save / Object::SaveVoxelization: sizes come from ObjNVoxelConfig.txt (the reference can
+ * only read back one hard-coded 48x64x64 grid, Object::ReadRAWObject src/Object.cpp:319-392).  Arrays are malloc'ed; the two
+ * normal streams are NULL when their files are absent.  Free with gpv_free_voxels. */
+typedef struct {
+	char name[64];             /* "Obj<N>" */
+	float bbox_min[3], bbox_max[3];
+	int num_div[3]; float grid_size[3];
+	int64_t l1_inside, l1_boundary;
+	int has_level2; int num_div2[3]; float grid_size2[3];
+	int64_t l2_inside, l2_boundary;
+	int64_t cells, n_boundary, n23;
+	uint8_t* level1_inout; uint8_t* level1_normal; int32_t* prefix_sum; uint8_t* level2_inout; uint8_t* level2_normal;
+} gpv_voxel_file;
+int gpv_load_voxels(const char* dir, int obj_id, gpv_voxel_file* out);
+void gpv_free_voxels(gpv_voxel_file* v);
+
 /* Batched dataset generation (BASELINE.json config 5): `threads` host threads, each with its own ctx on devices[w % n_devices],
  * pull paths from a shared queue: load -> gpv_voxelize_host -> gpv_save(out_dir, obj id = first_obj_id + index).  out_dir NULL:
  * nothing is written.  skip_existing: a model whose ObjNVoxelConfig.txt exists is skipped (restartable).  The *_seconds are

@@ -128,3 +128,32 @@ def test_save_writes_the_reference_file_contract(product, oracle, tmp_path_facto
     for n in names:
         assert filecmp.cmp(d1 / n, d2 / n, shallow=False), n
     assert keep
+
+
+def test_voxel_files_round_trip(product, oracle, tmp_path_factory, tmp_path):
+    """gpv_load_voxels reads back what SaveVoxelization-format writers produce (sizes from ObjNVoxelConfig.txt), with and
+    without Level 2 / normals, and refuses files whose sizes contradict the config."""
+    from gpview_b200 import binding as B
+    path = mesh_path("sphere", tmp_path_factory.getbasetemp())
+    r = oracle.OracleMesh(path).voxelize(32, 4, oracle.FILL_CERTIFIED, 4)
+    r.save(5, str(tmp_path))
+    v = B.load_voxels(str(tmp_path), 5)
+    assert v["name"] == "Obj5" and v["num_div"] == list(r.num_div) and v["num_div2"] == [4, 4, 4] and v["counts"] == r.counts
+    assert np.array_equal(v["level1_inout"], r.l1_state * 127) and np.array_equal(v["prefix_sum"], r.prefix)
+    assert np.array_equal(v["level2_inout"], r.l2_state * 127)
+    assert np.array_equal(v["level1_normal"], r.l1_normal) and np.array_equal(v["level2_normal"], r.l2_normal)
+    assert v["grid_size"] == pytest.approx([float(x) for x in r.grid_size], rel=1e-5)     # the config prints 6 significant digits
+    os.remove(tmp_path / "Obj5Level2Normal.raw")
+    assert B.load_voxels(str(tmp_path), 5)["level2_normal"] is None                        # optional stream
+    with open(tmp_path / "Obj5Level2InOut.raw", "ab") as f:
+        f.write(b"\\0")
+    with pytest.raises(product.GpvError):
+        B.load_voxels(str(tmp_path), 5)                                                    # size contradicts the config
+    r1 = oracle.OracleMesh(path).voxelize(32, 0, oracle.FILL_CERTIFIED, 4)
+    d2 = tmp_path / "l1only"
+    d2.mkdir()
+    r1.save(0, str(d2))
+    v1 = B.load_voxels(str(d2), 0)
+    assert v1["num_div2"] is None and v1["level2_inout"] is None and np.array_equal(v1["level1_inout"], r1.l1_state * 127)
+    with pytest.raises(product.GpvError):
+        B.load_voxels(str(d2), 9)
