@@ -33,6 +33,7 @@ struct Totals {
 	unsigned long long binWork, crossWork; // totals of the two balanced work spaces (exclusive scans of binCnt / crossCnt)
 	unsigned long long l1Hits, crossPairs, nIll, l1Inside, l2Inside, l2Boundary;
 	unsigned int nBoundary, triTotal, colTotalOver, crossTotal;
+	unsigned int nBoundaryCols, pad0, pad1, pad2; // Level-1 columns that hold boundary cells (size of the Level-2 crossing lists)
 };
 
 constexpr int kWorkThreads = 128;                        // threads per CTA of the balanced triangle-work kernels
@@ -359,6 +360,7 @@ struct ScanIO {
 	unsigned long long* desc; unsigned* tileCounter;
 	// MODE_CELLS
 	int* prefix; int* boundaryIndex; unsigned* bTriOff; unsigned char* bmask; long long globalBase; Totals* totals;
+	int* colFlag; long long plane; // MODE_CELLS also flags the Level-1 columns that hold boundary cells (plane = nx*ny)
 	// MODE_OFFS
 	unsigned* off; unsigned* totalOut; unsigned long long* totalOut64; // either total pointer may be null
 };
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(ScanIO io)
 			if (v[k] > 0) {
 				flags |= 1u << k;
 				io.boundaryIndex[b] = (int)(io.globalBase + first + k);
+				io.colFlag[(io.globalBase + first + k) % io.plane] = 1; // this Level-1 column holds a boundary cell (same value from every writer)
 				io.bTriOff[b] = ts;
 			}
 			run += item[k];
@@ -644,14 +647,15 @@ __global__ void __launch_bounds__(kSortLongThreads) k_sort_long(const unsigned* 
 // ------------------------------------------------------------------------------------------------ k_l2
 // K4.  Replaces CUDAClassifyInOutLevel2Kernel (cu:450-504) + CUDAClassifyTessellationLevel2Kernel (cu:403-448).
 // A CTA of 256 threads refines G = max(1, 256/n2^2) boundary cells; a thread owns (cell, q, r): first as an xy-column
-// (p=q', q=r') of the parity-ray phase, then as a row of n2 sub-voxels along x in the SAT phase, so the y/z part of every
-// SAT test is hoisted out of the x loop (gpv::SatRow) and each row leaves as ONE vector store of final file bytes
-// (n2 = 16: 128-bit; rows of a CTA are contiguous in Level2InOut.raw).
+// (p=q', q=r') of the parity-ray phase, then as a row of n2 sub-voxels along x in the SAT phase; each row leaves as ONE
+// vector store of final file bytes (n2 = 16: 128-bit; rows of a CTA are contiguous in Level2InOut.raw).
 // Sub-voxel centre (cu:423-425 / 472-474): ((2p+1)*ext2 + mid) - ext1, all f32.
 struct L2IO {
 	const float4* tri48; const float4* ray48; const float4* plane16;
 	const int* boundaryIndex; const unsigned* bTriOff; const int* cellTris;
 	const unsigned* colOff; const int* colCount; const int* colTris;
+	const int* colFlag; const unsigned* colRank; // Level-1 columns that hold boundary cells, and their rank (exclusive scan of colFlag)
+	uint4* xList;                                // [boundary column rank][n2*n2]: crossing list of every sub-voxel column (k_l2_cross)
 	const float* cx; const float* cy; const float* cz;
 	unsigned char* l2State; // nBoundary * n2^3 file bytes
 	int bBegin;             // this launch refines boundary ranks [bBegin, nBoundary)
@@ -659,26 +663,139 @@ struct L2IO {
 	Totals* totals;
 };
 
+// exact a / d for 0 <= a < 2^21 with inv = 1.f / (float)d: (a + 0.5) / d is at least 0.5/d away from an integer, the f32 error
+// of the product is below (a/d) * 2^-22
+__device__ __forceinline__ int fast_div(int a, float inv) { return __float2int_rz(((float)a + 0.5f) * inv); }
+
+// K4a.  Level-2 crossing lists.  The det/u/v part of the +Z ray test depends only on the xy position of a sub-voxel column, and
+// all boundary cells of one Level-1 column share their n2 x n2 sub-columns AND their candidate triangles (the column list,
+// cu:461-463).  So that part is evaluated once per (Level-1 column, sub-column, triangle) -- not once per boundary cell (cessna-256:
+// ~9 boundary cells per boundary column, 24 triangles per column list) -- and the few triangles that pass are kept per sub-column
+// as 16 bytes: count, then up to kXSlots 16-bit positions in the column list.  k_l2 walks only that list; a sub-column with more
+// crossings than slots (or a column list beyond 65,535 entries) is marked kXAll and k_l2 walks the column list itself.
+constexpr int kXSlots = 7;
+constexpr unsigned kXAll = 0xffffu;
+constexpr int kL2Stage = 256; // ray records staged per chunk by k_l2_cross (12 KB)
+
+__device__ __forceinline__ uint4 pack_xlist(unsigned n, const unsigned short* pos, bool all)
+{
+	if (all || n > (unsigned)kXSlots) return make_uint4(kXAll, 0u, 0u, 0u);
+	return make_uint4(n | ((unsigned)pos[0] << 16), pos[1] | ((unsigned)pos[2] << 16), pos[3] | ((unsigned)pos[4] << 16), pos[5] | ((unsigned)pos[6] << 16));
+}
+
+__global__ void __launch_bounds__(256) k_l2_cross(GridP g, L2IO io)
+{
+	__shared__ float4 sStage[kL2Stage * 3]; // G == 1: ray records of the column list, kL2Stage at a time
+	const int n2 = g.n2, rows = n2 * n2;
+	const int G = max(1, 256 / rows);
+	const int tid = threadIdx.x;
+	const long long ncol = (long long)g.nx * g.ny;
+	const float invN2 = 1.f / (float)n2;
+	if (G == 1) {
+		const int col = blockIdx.x;
+		if (!io.colFlag[col]) return;
+		const int jy = col / g.nx, ix = col - jy * g.nx;
+		const unsigned off = io.colOff[col];
+		const int cnt = io.colCount[col];
+		const float mx = io.cx[ix], my = io.cy[jy];
+		uint4* out = io.xList + (size_t)io.colRank[col] * rows;
+		for (int item0 = 0; item0 < rows; item0 += 256) { // one round unless n2 = 32
+			const int item = item0 + tid;
+			const int q = fast_div(item, invN2), p = item - q * n2;
+			const float ox = (float)(2 * p + 1) * g.h2x + mx - g.h1x, oy = (float)(2 * q + 1) * g.h2y + my - g.h1y; // cu:472-473
+			unsigned short pos[kXSlots] = { 0, 0, 0, 0, 0, 0, 0 };
+			unsigned n = 0;
+			for (int k0 = 0; k0 < cnt; k0 += kL2Stage) {
+				const int nrec = min(kL2Stage, cnt - k0);
+				__syncthreads();
+				for (int i = tid; i < nrec * 3; i += 256) {
+					const int rec = i / 3;
+					sStage[i] = __ldg(io.ray48 + (size_t)io.colTris[off + k0 + rec] * 3 + (i - rec * 3));
+				}
+				__syncthreads();
+				if (item < rows) {
+					for (int k = 0; k < nrec; k++) {
+						const float4 a = sStage[k * 3], b = sStage[k * 3 + 1], c4 = sStage[k * 3 + 2];
+						if (c4.w == 0.f) continue;
+						RayTri s;
+						s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;
+						s.e2z = c4.x; s.det = c4.y; s.inv = c4.z; s.ok = true; s.well = false;
+						RayCol rc;
+						if (!ray_column(s, ox, oy, rc)) continue;
+#pragma unroll
+						for (int j = 0; j < kXSlots; j++) if (n == (unsigned)j) pos[j] = (unsigned short)(k0 + k);
+						n++;
+					}
+				}
+			}
+			if (item < rows) out[item] = pack_xlist(n, pos, cnt > 65535);
+		}
+	} else {
+		const int gi = fast_div(tid, 1.f / (float)rows), item = tid - gi * rows;
+		const long long col = (long long)blockIdx.x * G + gi;
+		if (gi >= G || col >= ncol || !io.colFlag[col]) return;
+		const int jy = (int)(col / g.nx), ix = (int)(col - (long long)jy * g.nx);
+		const int q = fast_div(item, invN2), p = item - q * n2;
+		const float ox = (float)(2 * p + 1) * g.h2x + io.cx[ix] - g.h1x, oy = (float)(2 * q + 1) * g.h2y + io.cy[jy] - g.h1y;
+		const unsigned off = io.colOff[col];
+		const int cnt = io.colCount[col];
+		unsigned short pos[kXSlots] = { 0, 0, 0, 0, 0, 0, 0 };
+		unsigned n = 0;
+		for (int k = 0; k < cnt; k++) {
+			RayTri s;
+			load_ray(s, io.ray48, io.colTris[off + k]);
+			RayCol rc;
+			if (!s.ok || !ray_column(s, ox, oy, rc)) continue;
+#pragma unroll
+			for (int j = 0; j < kXSlots; j++) if (n == (unsigned)j) pos[j] = (unsigned short)k;
+			n++;
+		}
+		io.xList[(size_t)io.colRank[col] * rows + item] = pack_xlist(n, pos, cnt > 65535);
+	}
+}
+
 #ifndef GPV_L2_MINBLOCKS
 #define GPV_L2_MINBLOCKS 5 // 48 registers: 5 CTAs per SM measured 4-8 % faster than 4 (64 registers) on cessna 256/16 and sphere 512/8
 #endif
 constexpr int kL2Threads = 256;
-constexpr int kL2Batch = 8;   // triangles per queue round
-constexpr int kL2Stage = 256; // ray records staged per chunk (12 KB of the 16 KB queue area)
+constexpr int kL2Batch = 8;   // triangles per round of the (row, triangle) queue
+
+// shared-memory layout of k_l2 (bytes), shared by the kernel and the launch code
+struct L2Smem { int par, sat, info, q1, q2, qn, total; };
+__host__ __device__ inline L2Smem l2_smem_layout(int n2)
+{
+	const int rows = n2 * n2, G = rows >= kL2Threads ? 1 : kL2Threads / rows, items = G * rows;
+	L2Smem L;
+	int o = G * 3 * n2 * 4;          // [G][3][n2] sub-voxel centres
+	L.par = o; o += items * 4;       // [items] parity bits along z per xy-column
+	L.sat = o; o += items * 4;       // [items] SAT hit bits along x per row
+	L.info = o; o += G * 8 * 4;      // [G][8] triOff, triCnt, colOff, colCnt, xList base (2 words), valid, -
+	o = (o + 15) & ~15;
+	L.q1 = o; o += kL2Threads * kL2Batch * 8;    // (row, triangle) queue: item | plo<<16 | phi<<24, triangle
+	L.q2 = o; o += kL2Threads * n2 * 2;          // sub-voxel queue of one slice of kL2Threads (row, triangle) entries: entry<<5 | p
+	o = (o + 15) & ~15;
+	L.qn = o; o += 16;               // queue fills: [0..1] (row, triangle) queue, ping-pong; [2..3] sub-voxel queue, ping-pong
+	L.total = o;
+	return L;
+}
 
 __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2IO io)
 {
-	extern __shared__ unsigned char smemRaw[];
+	extern __shared__ __align__(16) unsigned char smemRaw[];
 	const int n2 = g.n2, rows = n2 * n2;
 	const int G = max(1, kL2Threads / rows);
-	float* sC = reinterpret_cast<float*>(smemRaw);                   // [G][3][n2] sub-voxel centres
-	unsigned* sPar = reinterpret_cast<unsigned*>(sC + G * 3 * n2);    // [G][rows] parity bits along z per xy-column
-	int* sInfo = reinterpret_cast<int*>(sPar + G * rows);             // [G][4] triOff, triCnt, colOff, colCnt
-	unsigned* sSat = reinterpret_cast<unsigned*>(sInfo + G * 4);      // [G][rows] SAT hit bits along x per row
-	uint2* sQueue = reinterpret_cast<uint2*>(sSat + G * rows + ((4 - ((G * 3 * n2 + 2 * G * rows) & 3)) & 3)); // [kL2Threads*kL2Batch] (item|plo|phi, triangle), 16-byte aligned
-	int* sQn = reinterpret_cast<int*>(sQueue + kL2Threads * kL2Batch);              // queue fill
-	const int tid = threadIdx.x;
+	const int nItems = G * rows;
+	const L2Smem L = l2_smem_layout(n2);
+	float* sC = reinterpret_cast<float*>(smemRaw);
+	unsigned* sPar = reinterpret_cast<unsigned*>(smemRaw + L.par);
+	unsigned* sSat = reinterpret_cast<unsigned*>(smemRaw + L.sat);
+	int* sInfo = reinterpret_cast<int*>(smemRaw + L.info);
+	uint2* sQ1 = reinterpret_cast<uint2*>(smemRaw + L.q1);
+	unsigned short* sQ2 = reinterpret_cast<unsigned short*>(smemRaw + L.q2);
+	int* sQn = reinterpret_cast<int*>(smemRaw + L.qn);
+	const int tid = threadIdx.x, lane = tid & 31;
 	const long long b0 = io.bBegin + (long long)blockIdx.x * G;
+	const float invRows = 1.f / (float)rows, invN2 = 1.f / (float)n2;
 
 	for (int k = tid; k < G * 3 * n2; k += kL2Threads) {
 		int gi = k / (3 * n2), rem = k - gi * 3 * n2, ax = rem / n2, p = rem - ax * n2;
@@ -695,115 +812,87 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	}
 	for (int gi = tid; gi < G; gi += kL2Threads) {
 		long long b = b0 + gi;
-		int* inf = sInfo + gi * 4;
+		int* inf = sInfo + gi * 8;
 		if (b < io.nBoundary) {
 			int l1 = io.boundaryIndex[b];
 			int col = l1 % (g.nx * g.ny);
 			inf[0] = (int)io.bTriOff[b]; inf[1] = (int)(io.bTriOff[b + 1] - io.bTriOff[b]);
 			inf[2] = (int)io.colOff[col]; inf[3] = io.colCount[col];
-		} else { inf[0] = inf[1] = inf[2] = inf[3] = 0; }
+			const unsigned long long xb = (unsigned long long)io.colRank[col] * (unsigned)rows;
+			inf[4] = (int)(unsigned)xb; inf[5] = (int)(unsigned)(xb >> 32); inf[6] = 1; inf[7] = 0;
+		} else { for (int k = 0; k < 8; k++) inf[k] = 0; }
 	}
+	for (int item = tid; item < nItems; item += kL2Threads) sSat[item] = 0;
+	if (tid < 4) sQn[tid] = 0;
 	__syncthreads();
 
-	// ---- phase 1: parity rays.  item = (cell gi, xy-column pq); n2 <= 32 so the z parity fits one word
+	// ---- phase 1: parity rays.  item = (cell gi, xy-column pq); n2 <= 32 so the z parity fits one word.  Only the triangles on
+	// the sub-column's crossing list (k_l2_cross) are visited; per triangle the certified z-run decides the whole cell at once
+	// unless the crossing lies inside it.
 	const unsigned fullRun = n2 == 32 ? 0xffffffffu : ((1u << n2) - 1);
-	if (G == 1) {
-		// one cell per CTA: every thread walks the same column list, so its ray records are staged through shared memory
-		// (the queue area is idle in this phase) in chunks of kL2Stage records instead of 256 threads chasing the same
-		// colTris -> ray48 pointers
-		float4* stage = reinterpret_cast<float4*>(sQueue);
-		const int colOff = sInfo[2], colCnt = sInfo[3];
-		unsigned par[4] = { 0, 0, 0, 0 }; // up to 4 xy-columns per thread (n2 = 32)
-		for (int k0 = 0; k0 < colCnt; k0 += kL2Stage) {
-			const int nrec = min(kL2Stage, colCnt - k0);
-			for (int i = tid; i < nrec * 3; i += kL2Threads) {
-				const int rec = i / 3;
-				stage[i] = __ldg(io.ray48 + (size_t)io.colTris[colOff + k0 + rec] * 3 + (i - rec * 3));
-			}
-			__syncthreads();
-			int slot = 0;
-			for (int item = tid; item < rows; item += kL2Threads, slot++) {
-				const int q = item / n2, p = item - q * n2;
-				const float ox = sC[p], oy = sC[n2 + q];
-				unsigned acc = 0;
-				for (int k = 0; k < nrec; k++) {
-					const float4 a = stage[k * 3], b = stage[k * 3 + 1], c4 = stage[k * 3 + 2];
-					if (c4.w == 0.f) continue;
-					RayTri s;
-					s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;
-					s.e2z = c4.x; s.det = c4.y; s.inv = c4.z; s.ok = true; s.well = c4.w == 2.f;
-					RayCol rc;
-					if (!ray_column(s, ox, oy, rc)) continue;
-					const int run = ray_z_run(s, rc, s.well, sC[2 * n2], sC[3 * n2 - 1]); // the whole cell below / above the crossing?
-					if (run == 0) continue;
-					if (run == 1) acc ^= fullRun;
-					else for (int r = 0; r < n2; r++) acc ^= (unsigned)ray_cell(s, rc, sC[2 * n2 + r]) << r;
-				}
-				par[slot] ^= acc;
-			}
-			__syncthreads();
-		}
-		int slot = 0;
-		for (int item = tid; item < rows; item += kL2Threads, slot++) sPar[item] = par[slot];
-	} else {
-		for (int item = tid; item < G * rows; item += kL2Threads) {
-			int gi = item / rows, pq = item - gi * rows, q = pq / n2, p = pq - q * n2;
+	for (int item = tid; item < nItems; item += kL2Threads) {
+		const int gi = fast_div(item, invRows), pq = item - gi * rows, q = fast_div(pq, invN2), p = pq - q * n2;
+		const int* inf = sInfo + gi * 8;
+		unsigned par = 0;
+		if (inf[6]) {
 			const float* c = sC + gi * 3 * n2;
 			const float ox = c[p], oy = c[n2 + q];
-			const int* inf = sInfo + gi * 4;
-			unsigned par = 0;
-			for (int k = 0; k < inf[3]; k++) {
+			auto one = [&](int t) {
 				RayTri s;
-				load_ray(s, io.ray48, io.colTris[inf[2] + k]);
+				load_ray(s, io.ray48, t);
 				RayCol rc;
-				if (!s.ok || !ray_column(s, ox, oy, rc)) continue;
-				const int run = ray_z_run(s, rc, s.well, c[2 * n2], c[3 * n2 - 1]);
-				if (run == 0) continue;
+				if (!s.ok || !ray_column(s, ox, oy, rc)) return;
+				const int run = ray_z_run(s, rc, s.well, c[2 * n2], c[3 * n2 - 1]); // the whole cell below / above the crossing?
+				if (run == 0) return;
 				if (run == 1) par ^= fullRun;
 				else for (int r = 0; r < n2; r++) par ^= (unsigned)ray_cell(s, rc, c[2 * n2 + r]) << r;
+			};
+			const unsigned long long xb = (unsigned long long)(unsigned)inf[4] | ((unsigned long long)(unsigned)inf[5] << 32);
+			const uint4 e = __ldg(io.xList + xb + pq);
+			const unsigned n = e.x & 0xffffu;
+			if (n != kXAll) {
+				for (unsigned j = 0; j < n; j++) {
+					const unsigned w = (j + 1) >> 1;
+					const unsigned v = w == 0 ? e.x : (w == 1 ? e.y : (w == 2 ? e.z : e.w));
+					one(io.colTris[inf[2] + ((v >> (((j + 1) & 1) * 16)) & 0xffffu)]);
+				}
+			} else {
+				for (int k = 0; k < inf[3]; k++) one(io.colTris[inf[2] + k]);
 			}
-			sPar[item] = par;
 		}
+		sPar[item] = par;
 	}
-	__syncthreads();
 
-	// ---- phase 2a: SAT.  Cheap pass: every (row, triangle) pair gets the certified plane interval (gpv::plane_row_interval,
-	// ~12 instructions); pairs that can still hit are compacted into a CTA-wide queue in shared memory (ballot/popc per
-	// warp, one atomicAdd per warp for the slot range) and the expensive part -- the hoisted row set-up plus the exact test of
-	// the few sub-voxels inside the interval -- runs on full warps of queue entries, whatever rows and triangles they came
-	// from.  Hits are OR-ed into the row's bit mask in shared memory.  Triangles are taken kL2Batch at a time so that the
-	// queue (kL2Threads * kL2Batch entries) can never overflow.
-	for (int item = tid; item < G * rows; item += kL2Threads) sSat[item] = 0;
-	if (tid == 0) *sQn = 0;
-	__syncthreads();
+	// ---- phase 2a: SAT, three stages over shared-memory queues so that every stage runs on full warps.
+	//   A  every (row, triangle) pair of the cell gets the certified plane interval (gpv::plane_row_interval, ~12 instructions);
+	//      pairs that can still hit go to the (row, triangle) queue (ballot/popc per warp, one atomicAdd per warp).
+	//   B1 one queue entry per thread: the p-independent predicates of the SAT (gpv::sat_row_setup: y/z AABB, the three X-axis
+	//      tests) and the certified x-AABB clip; survivors are expanded into one sub-voxel queue entry per p of their interval
+	//      (warp scan of the interval lengths, one atomicAdd per warp).
+	//   B2 one sub-voxel per thread: the row state is re-created (gpv::sat_row_values, no predicates) and the remaining
+	//      predicates are evaluated (gpv::sat_row_test); hits are OR-ed into the row's bit mask in shared memory.
+	// Triangles are taken kL2Batch at a time and queue entries kL2Threads at a time, so neither queue can overflow; the queue
+	// fills are ping-pong counters, reset one round ahead, which keeps it to two barriers per round.
 	{
-		const int lane = tid & 31;
 		const float inv2h = 1.f / (2.f * g.h2x);
-		auto heavy = [&](uint2 e) {
-			const int item = (int)(e.x & 0xffffu), plo = (int)((e.x >> 16) & 0xffu), phi = (int)(e.x >> 24);
-			const int gi = item / rows, row = item - gi * rows, r = row / n2, q = row - r * n2;
-			const float* c = sC + gi * 3 * n2;
-			const float4 A = __ldg(io.tri48 + (size_t)e.y * 3), B = __ldg(io.tri48 + (size_t)e.y * 3 + 1), C = __ldg(io.tri48 + (size_t)e.y * 3 + 2);
-			SatRow s;
-			if (!sat_row_setup(s, c[n2 + q], c[2 * n2 + r], g.h2y, g.h2z, A.y, A.z, B.y, B.z, C.y, C.z)) return;
-			unsigned bits = 0;
-			for (int p = plo; p <= phi; p++) bits |= (unsigned)sat_row_test(s, c[p], g.h2x, g.h2y, g.h2z, A.x, B.x, C.x) << p;
-			if (bits) atomicOr(sSat + item, bits);
-		};
-		for (int itemBase = 0; itemBase < G * rows; itemBase += kL2Threads) { // one round unless n2 = 32
+		int maxCnt = 0; // CTA-wide longest cell list (every thread must take part in the barriers below)
+		for (int gi = 0; gi < G; gi++) maxCnt = max(maxCnt, sInfo[gi * 8 + 1]);
+		int round1 = 0, round2 = 0;
+		for (int itemBase = 0; itemBase < nItems; itemBase += kL2Threads) { // one pass unless n2 = 32
 			const int item = itemBase + tid;
 			int triOff = 0, triCnt = 0;
 			float c0 = 0.f, cy2 = 0.f, cz2 = 0.f, slack = 0.f;
-			if (item < G * rows) {
-				const int gi = item / rows, row = item - gi * rows, r = row / n2, q = row - r * n2;
+			if (item < nItems) {
+				const int gi = fast_div(item, invRows), row = item - gi * rows, r = fast_div(row, invN2), q = row - r * n2;
 				const float* c = sC + gi * 3 * n2;
 				c0 = c[0]; cy2 = c[n2 + q]; cz2 = c[2 * n2 + r];
 				slack = 9.5367431640625e-07f * (fabsf(c0) + 2.f * g.gsx); // 16u(|mid_x| + gs_x) >= |(c_p - c_0) - 2*h2x*p|
-				triOff = sInfo[gi * 4]; triCnt = sInfo[gi * 4 + 1];        // 0 for cells past the end
+				triOff = sInfo[gi * 8]; triCnt = sInfo[gi * 8 + 1];        // 0 for cells past the end
 			}
-			int maxCnt = 0; // CTA-wide longest cell list (every thread must take part in the barriers below)
-			for (int gi = 0; gi < G; gi++) maxCnt = max(maxCnt, sInfo[gi * 4 + 1]);
 			for (int kb = 0; kb < maxCnt; kb += kL2Batch) {
+				int* q1n = sQn + (round1 & 1);
+				if (tid == 0) sQn[(round1 + 1) & 1] = 0; // the other counter: every read of it lies behind a barrier, its next use after the next one
+				// stage A
 				for (int k = kb; k < min(kb + kL2Batch, maxCnt); k++) {
 					bool alive = false;
 					int plo = 0, phi = -1, t = 0;
@@ -816,25 +905,73 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 					const unsigned m = __ballot_sync(0xffffffffu, alive);
 					if (m) {
 						int base = 0;
-						if (lane == 0) base = atomicAdd(sQn, __popc(m));
+						if (lane == 0) base = atomicAdd(q1n, __popc(m));
 						base = __shfl_sync(0xffffffffu, base, 0);
-						if (alive) sQueue[base + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)item | ((unsigned)plo << 16) | ((unsigned)phi << 24), (unsigned)t);
+						if (alive) sQ1[base + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)item | ((unsigned)plo << 16) | ((unsigned)phi << 24), (unsigned)t);
 					}
 				}
 				__syncthreads();
-				const int qn = *sQn;
-				for (int e = tid; e < qn; e += kL2Threads) heavy(sQueue[e]);
-				__syncthreads();
-				if (tid == 0) *sQn = 0;
-				__syncthreads();
+				const int n1 = *q1n;
+				round1++;
+				for (int s0 = 0; s0 < n1; s0 += kL2Threads) {
+					int* q2n = sQn + 2 + (round2 & 1);
+					// stage B1
+					int len = 0, plo = 0;
+					if (s0 + tid < n1) {
+						const uint2 e = sQ1[s0 + tid];
+						const int it = (int)(e.x & 0xffffu);
+						const int gi = fast_div(it, invRows), row = it - gi * rows, r = fast_div(row, invN2), q = row - r * n2;
+						const float* c = sC + gi * 3 * n2;
+						const float4 A = __ldg(io.tri48 + (size_t)e.y * 3), B = __ldg(io.tri48 + (size_t)e.y * 3 + 1), C = __ldg(io.tri48 + (size_t)e.y * 3 + 2);
+						SatRow s;
+						if (sat_row_setup(s, c[n2 + q], c[2 * n2 + r], g.h2y, g.h2z, A.y, A.z, B.y, B.z, C.y, C.z)) {
+							int phi = (int)(e.x >> 24);
+							plo = (int)((e.x >> 16) & 0xffu);
+							const float sl = 9.5367431640625e-07f * (fabsf(c[0]) + 2.f * g.gsx);
+							x_row_clip(fminf(A.x, fminf(B.x, C.x)), fmaxf(A.x, fmaxf(B.x, C.x)), c[0], g.h2x, g.gsx, inv2h, sl, n2, plo, phi);
+							len = max(0, phi - plo + 1);
+						}
+					}
+					int incl = len;
+#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) {
+						const int y = __shfl_up_sync(0xffffffffu, incl, o);
+						if (lane >= o) incl += y;
+					}
+					const int warpTot = __shfl_sync(0xffffffffu, incl, 31);
+					if (warpTot) {
+						int base = 0;
+						if (lane == 31) base = atomicAdd(q2n, warpTot);
+						base = __shfl_sync(0xffffffffu, base, 31) + incl - len;
+						for (int j = 0; j < len; j++) sQ2[base + j] = (unsigned short)((tid << 5) | (plo + j));
+					}
+					__syncthreads();
+					const int n2q = *q2n;
+					if (tid == 0) sQn[2 + ((round2 + 1) & 1)] = 0;
+					round2++;
+					// stage B2
+					for (int v = tid; v < n2q; v += kL2Threads) {
+						const unsigned x = sQ2[v];
+						const uint2 e = sQ1[s0 + (int)(x >> 5)];
+						const int p = (int)(x & 31u), it = (int)(e.x & 0xffffu);
+						const int gi = fast_div(it, invRows), row = it - gi * rows, r = fast_div(row, invN2), q = row - r * n2;
+						const float* c = sC + gi * 3 * n2;
+						const float4 A = __ldg(io.tri48 + (size_t)e.y * 3), B = __ldg(io.tri48 + (size_t)e.y * 3 + 1), C = __ldg(io.tri48 + (size_t)e.y * 3 + 2);
+						SatRow s;
+						sat_row_values(s, c[n2 + q], c[2 * n2 + r], g.h2y, g.h2z, A.y, A.z, B.y, B.z, C.y, C.z);
+						if (sat_row_test(s, c[p], g.h2x, g.h2y, g.h2z, A.x, B.x, C.x)) atomicOr(sSat + it, 1u << p);
+					}
+					__syncthreads();
+				}
 			}
 		}
 	}
+	__syncthreads();
 
 	// ---- phase 2b: the row's file bytes
 	unsigned long long nIn = 0, nBd = 0;
-	for (int item = tid; item < G * rows; item += kL2Threads) {
-		int gi = item / rows, row = item - gi * rows, r = row / n2, q = row - r * n2;
+	for (int item = tid; item < nItems; item += kL2Threads) {
+		const int gi = fast_div(item, invRows), row = item - gi * rows, r = fast_div(row, invN2), q = row - r * n2;
 		long long b = b0 + gi;
 		if (b >= io.nBoundary) continue;
 		const unsigned sat = sSat[item];
@@ -844,37 +981,14 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 		par &= ~sat;
 		nIn += __popc(par); nBd += __popc(sat);
 		unsigned char* out = io.l2State + ((size_t)b * rows + row) * n2;
-		if (n2 == 16) {
-			unsigned w[4];
-#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				unsigned x = 0;
-#pragma unroll
-				for (int e = 0; e < 4; e++) {
-					int p = k * 4 + e;
-					x |= (((sat >> p) & 1) ? 254u : (((par >> p) & 1) ? 127u : 0u)) << (8 * e);
-				}
-				w[k] = x;
-			}
-			*reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
-		} else if (n2 == 8) {
-			unsigned w[2];
-#pragma unroll
-			for (int k = 0; k < 2; k++) {
-				unsigned x = 0;
-#pragma unroll
-				for (int e = 0; e < 4; e++) {
-					int p = k * 4 + e;
-					x |= (((sat >> p) & 1) ? 254u : (((par >> p) & 1) ? 127u : 0u)) << (8 * e);
-				}
-				w[k] = x;
-			}
-			*reinterpret_cast<uint2*>(out) = make_uint2(w[0], w[1]);
-		} else if (n2 == 4) {
-			unsigned x = 0;
-#pragma unroll
-			for (int e = 0; e < 4; e++) x |= (((sat >> e) & 1) ? 254u : (((par >> e) & 1) ? 127u : 0u)) << (8 * e);
-			*reinterpret_cast<unsigned*>(out) = x;
+		// four sub-voxels per 32-bit word: (nibble * 0x204081) & 0x01010101 spreads bit k of the nibble to byte k
+		auto word = [&](int k) { return (((par >> (4 * k)) & 15u) * 0x204081u & 0x01010101u) * 127u + (((sat >> (4 * k)) & 15u) * 0x204081u & 0x01010101u) * 254u; };
+		if (n2 == 16) *reinterpret_cast<uint4*>(out) = make_uint4(word(0), word(1), word(2), word(3));
+		else if (n2 == 8) *reinterpret_cast<uint2*>(out) = make_uint2(word(0), word(1));
+		else if (n2 == 4) *reinterpret_cast<unsigned*>(out) = word(0);
+		else if (n2 == 32) {
+			reinterpret_cast<uint4*>(out)[0] = make_uint4(word(0), word(1), word(2), word(3));
+			reinterpret_cast<uint4*>(out)[1] = make_uint4(word(4), word(5), word(6), word(7));
 		} else {
 			for (int p = 0; p < n2; p++) out[p] = ((sat >> p) & 1) ? 254 : (((par >> p) & 1) ? 127 : 0);
 		}

@@ -115,6 +115,31 @@ GPV_HD bool sat_row_setup(SatRow& s, float cy, float cz, float hy, float hz,
 	return true;
 }
 
+// the row quantities of sat_row_setup WITHOUT its predicates, for a (row, triangle) pair that is already known to pass them
+// (the voxel-level queue of k_l2 re-creates the row state per sub-voxel instead of carrying 17 floats through shared memory)
+GPV_HD void sat_row_values(SatRow& s, float cy, float cz, float hy, float hz,
+                           float t0y, float t0z, float t1y, float t1z, float t2y, float t2z)
+{
+	s.v0y = t0y - cy; s.v0z = t0z - cz; s.v1y = t1y - cy; s.v1z = t1z - cz; s.v2y = t2y - cy; s.v2z = t2z - cz;
+	s.e0y = s.v1y - s.v0y; s.e0z = s.v1z - s.v0z;
+	s.e1y = s.v2y - s.v1y; s.e1z = s.v2z - s.v1z;
+	s.e2y = s.v0y - s.v2y; s.e2z = s.v0z - s.v2z;
+	s.nx = s.e0y * s.e1z - s.e0z * s.e1y;
+	s.py0 = -hy - s.v0y; s.py1 = hy - s.v0y; s.pz0 = -hz - s.v0z; s.pz1 = hz - s.v0z;
+}
+
+// Certified clip of a row's index interval [plo,phi] to the sub-voxels whose x-AABB predicate (cu:284-286) can pass:
+// fl(tmin - c_p) <= hx and fl(tmax - c_p) >= -hx need c_p within [tmin - hx, tmax + hx] up to rounding.  c0 = centre of the
+// row's first sub-voxel, |c_p - c0 - 2*hx*p| <= slack (see plane_row_interval); the 128u margin covers that, the rounding of
+// the predicate's own subtraction and of the bounds below.  Never drops a sub-voxel that passes; the exact test still runs.
+GPV_HD void x_row_clip(float tmin, float tmax, float c0, float hx, float gsx, float inv2h, float slack, int n2, int& plo, int& phi)
+{
+	const float s2 = slack + 7.62939453125e-06f * (fabsf(tmin) + fabsf(tmax) + fabsf(c0) + gsx); // 2^-17 = 128u
+	const float lo = ceilf((tmin - c0 - hx - s2) * inv2h), hi = floorf((tmax - c0 + hx + s2) * inv2h);
+	if (lo == lo && lo > (float)plo) plo = lo > (float)n2 ? n2 : (int)lo;
+	if (hi == hi && hi < (float)phi) phi = hi < -1.f ? -1 : (int)hi;
+}
+
 // the remaining predicates for one box of the row (box centre x = cx)
 GPV_HD bool sat_row_test(const SatRow& s, float cx, float hx, float hy, float hz, float t0x, float t1x, float t2x)
 {
