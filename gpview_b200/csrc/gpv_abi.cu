@@ -60,7 +60,7 @@ struct gpv_ctx {
 	int device = 0;
 	int smCount = 0;
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
-	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, longList, colFlag, colRank, xList;
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, longList, colCellCnt, colCellOff, colCellList, l2Par;
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
@@ -111,7 +111,7 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->longList, &c->colFlag, &c->colRank, &c->xList };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->longList, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par };
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
 	if (c->haveEvents) for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -215,7 +215,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	    c->boundaryIndex.ensure((size_t)cells * 4 + 32) || c->bTriOff.ensure((size_t)(cells + 1) * 4 + 32) || c->colOff.ensure((size_t)(ncol + 1) * 4 + 32) ||
 	    c->crossOff.ensure((size_t)(ncol + 1) * 4 + 32) || c->l1State.ensure((size_t)cells + 32) || c->crossFp.ensure((size_t)nTri * 16) || c->plane16.ensure((size_t)nTri * 16) ||
 	    c->binCnt.ensure((size_t)nTri * 4 + 32) || c->binOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->crossCnt.ensure((size_t)nTri * 4 + 32) ||
-	    c->crossWorkOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->colFlag.ensure((size_t)ncol * 4 + 32) || c->colRank.ensure((size_t)(ncol + 1) * 4 + 32))
+	    c->crossWorkOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->colCellCnt.ensure((size_t)ncol * 4 + 32) || c->colCellOff.ensure((size_t)(ncol + 1) * 4 + 32))
 		return 1;
 	Totals* dT = c->totals.as<Totals>();
 	mark(GPV_PHASE_SETUP);
@@ -223,7 +223,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	GPV_CUDA(cudaMemsetAsync(c->cellCount.p, 0, (size_t)cells * 4, st));
 	GPV_CUDA(cudaMemsetAsync(c->colCount.p, 0, (size_t)ncol * 4, st));
 	GPV_CUDA(cudaMemsetAsync(c->crossCount.p, 0, (size_t)ncol * 4, st));
-	GPV_CUDA(cudaMemsetAsync(c->colFlag.p, 0, (size_t)ncol * 4, st));
+	GPV_CUDA(cudaMemsetAsync(c->colCellCnt.p, 0, (size_t)ncol * 4, st));
 
 	float *cx = c->tabX.as<float>(), *cy = c->tabY.as<float>(), *cz = c->tabZ.as<float>();
 	float4 *tri48 = c->tri48.as<float4>(), *ray48 = c->ray48.as<float4>();
@@ -253,13 +253,13 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		io.desc = c->desc.as<unsigned long long>() + 1; io.tileCounter = c->desc.as<unsigned>();
 		io.prefix = c->prefix.as<int>(); io.boundaryIndex = c->boundaryIndex.as<int>(); io.bTriOff = c->bTriOff.as<unsigned>();
 		io.bmask = c->bmask.as<unsigned char>(); io.globalBase = (long long)g.z0 * ncol; io.totals = dT;
-		io.colFlag = c->colFlag.as<int>(); io.plane = ncol;
+		io.colCells = c->colCellCnt.as<int>(); io.plane = ncol;
 		k_scan<MODE_CELLS><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
 		launches++;
 	}
 	if (run_scan_offsets(c, st, c->colCount.as<int>(), ncol, c->colOff.as<unsigned>(), &dT->colTotalOver, nullptr, launches)) return 1;
 	if (run_scan_offsets(c, st, c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, nullptr, launches)) return 1;
-	if (wantL2 && run_scan_offsets(c, st, c->colFlag.as<int>(), ncol, c->colRank.as<unsigned>(), &dT->nBoundaryCols, nullptr, launches)) return 1;
+	if (wantL2 && run_scan_offsets(c, st, c->colCellCnt.as<int>(), ncol, c->colCellOff.as<unsigned>(), nullptr, nullptr, launches)) return 1;
 
 	// ---- the one size read-back
 	mark(GPV_PHASE_HOST_GAP);
@@ -273,7 +273,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	const long long n23 = (long long)g.n2 * g.n2 * g.n2;
 	if (c->cellTris.ensure((size_t)T1.triTotal * 4 + 32) || c->colTris.ensure((size_t)T1.colTotalOver * 4 + 32) || c->crossTri.ensure((size_t)T1.crossTotal * 4 + 32))
 		return 1;
-	if (wantL2 && (c->l2State.ensure((size_t)(nB * n23) + 32) || c->xList.ensure((size_t)T1.nBoundaryCols * g.n2 * g.n2 * 16 + 32))) return 1;
+	if (wantL2 && (c->l2State.ensure((size_t)(nB * n23) + 32) || c->colCellList.ensure((size_t)nB * 8 + 32) || c->l2Par.ensure((size_t)nB * g.n2 * g.n2 * 4 + 32))) return 1;
 	if (wantN && (c->l1Normal.ensure((size_t)cells * 3 + 32) || (wantL2 && c->l2Normal.ensure((size_t)(nB * n23) * 3 + 32)))) return 1;
 
 	bo.prefix = c->prefix.as<int>(); bo.bTriOff = c->bTriOff.as<unsigned>(); bo.cellTris = c->cellTris.as<int>();
@@ -337,16 +337,17 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		lio.tri48 = tri48; lio.ray48 = ray48; lio.plane16 = c->plane16.as<float4>(); lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
 		lio.cellTris = c->cellTris.as<int>(); lio.colOff = c->colOff.as<unsigned>(); lio.colCount = c->colCount.as<int>(); lio.colTris = c->colTris.as<int>();
 		lio.cx = cx; lio.cy = cy; lio.cz = cz; lio.l2State = c->l2State.as<unsigned char>(); lio.nBoundary = (int)nB; lio.totals = dT;
-		lio.colFlag = c->colFlag.as<int>(); lio.colRank = c->colRank.as<unsigned>(); lio.xList = c->xList.as<uint4>();
+		lio.colCellOff = c->colCellOff.as<unsigned>(); lio.colCellList = c->colCellList.as<int2>(); lio.l2Par = c->l2Par.as<unsigned>();
 		const int rows = g.n2 * g.n2, G = rows >= kL2Threads ? 1 : kL2Threads / rows;
 		const size_t smem = (size_t)l2_smem_layout(g.n2).total;
 		if (smem > 48 * 1024 && !c->l2AttrSet) { // n2 = 32 only (q2 queue of 16 KB on top of the 16 KB q1 queue and 12 KB of row state)
 			GPV_CUDA(cudaFuncSetAttribute(k_l2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 			c->l2AttrSet = true;
 		}
-		// K4a: crossing lists of every sub-voxel column of the Level-1 columns that hold boundary cells
-		k_l2_cross<<<(unsigned)((ncol + G - 1) / G), 256, 0, st>>>(g, lio);
-		launches++;
+		// K4a: boundary cells grouped by Level-1 column, then the parity bits of every sub-voxel column, one walk of the column list per column
+		k_col_cells<<<(unsigned)((nB + 255) / 256), 256, 0, st>>>(lio.boundaryIndex, (int)nB, (int)ncol, cz, lio.colCellOff, c->colCellCnt.as<int>(), c->colCellList.as<int2>());
+		k_l2_rays<<<(unsigned)((ncol + G - 1) / G), 256, 0, st>>>(g, lio);
+		launches += 2;
 		// With a host sink the boundary cells are refined in chunks and every finished chunk's bytes start their way to the
 		// host on the copy stream while the next chunk computes (e2e is PCIe-bound: 1 B per Level-2 voxel).
 		long long chunks = 1;

@@ -9,7 +9,8 @@
 //   k_fill_sweep    K2b +Z parity sweep per Level-1 column, coalesced along x, final Level-1 state bytes
 //   k_scan<MODE>    K3  single-pass decoupled-look-back scan: boundary prefix sum / index compaction / CSR offsets
 //   k_sort_segments canonical (ascending) order of every cell / column list; de-duplicates column lists
-//   k_l2            K4  Level-2 refinement: parity rays then hoisted SAT per sub-voxel row, 128-bit row stores
+//   k_col_cells, k_l2_rays  K4a Level-2 parity rays per sub-voxel column of each Level-1 column
+//   k_l2            K4  Level-2 refinement: hoisted SAT per sub-voxel row over shared-memory queues, 128-bit row stores
 //   k_l1_normals, k_l2_normals   K5 normals in the reference's uchar encoding
 #pragma once
 #include <cuda_runtime.h>
@@ -360,7 +361,7 @@ struct ScanIO {
 	unsigned long long* desc; unsigned* tileCounter;
 	// MODE_CELLS
 	int* prefix; int* boundaryIndex; unsigned* bTriOff; unsigned char* bmask; long long globalBase; Totals* totals;
-	int* colFlag; long long plane; // MODE_CELLS also flags the Level-1 columns that hold boundary cells (plane = nx*ny)
+	int* colCells; long long plane; // MODE_CELLS also counts the boundary cells of every Level-1 column (plane = nx*ny)
 	// MODE_OFFS
 	unsigned* off; unsigned* totalOut; unsigned long long* totalOut64; // either total pointer may be null
 };
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(ScanIO io)
 			if (v[k] > 0) {
 				flags |= 1u << k;
 				io.boundaryIndex[b] = (int)(io.globalBase + first + k);
-				io.colFlag[(io.globalBase + first + k) % io.plane] = 1; // this Level-1 column holds a boundary cell (same value from every writer)
+				atomicAdd(io.colCells + (io.globalBase + first + k) % io.plane, 1);
 				io.bTriOff[b] = ts;
 			}
 			run += item[k];
@@ -654,8 +655,8 @@ struct L2IO {
 	const float4* tri48; const float4* ray48; const float4* plane16;
 	const int* boundaryIndex; const unsigned* bTriOff; const int* cellTris;
 	const unsigned* colOff; const int* colCount; const int* colTris;
-	const int* colFlag; const unsigned* colRank; // Level-1 columns that hold boundary cells, and their rank (exclusive scan of colFlag)
-	uint4* xList;                                // [boundary column rank][n2*n2]: crossing list of every sub-voxel column (k_l2_cross)
+	const unsigned* colCellOff; const int2* colCellList; // boundary cells (slab-local rank, centre height) of every Level-1 column, CSR
+	unsigned* l2Par;                                    // [boundary rank][n2*n2] parity bits along z of every sub-voxel column (k_l2_rays)
 	const float* cx; const float* cy; const float* cz;
 	unsigned char* l2State; // nBoundary * n2^3 file bytes
 	int bBegin;             // this launch refines boundary ranks [bBegin, nBoundary)
@@ -667,23 +668,90 @@ struct L2IO {
 // of the product is below (a/d) * 2^-22
 __device__ __forceinline__ int fast_div(int a, float inv) { return __float2int_rz(((float)a + 0.5f) * inv); }
 
-// K4a.  Level-2 crossing lists.  The det/u/v part of the +Z ray test depends only on the xy position of a sub-voxel column, and
-// all boundary cells of one Level-1 column share their n2 x n2 sub-columns AND their candidate triangles (the column list,
-// cu:461-463).  So that part is evaluated once per (Level-1 column, sub-column, triangle) -- not once per boundary cell (cessna-256:
-// ~9 boundary cells per boundary column, 24 triangles per column list) -- and the few triangles that pass are kept per sub-column
-// as 16 bytes: count, then up to kXSlots 16-bit positions in the column list.  k_l2 walks only that list; a sub-column with more
-// crossings than slots (or a column list beyond 65,535 entries) is marked kXAll and k_l2 walks the column list itself.
-constexpr int kXSlots = 7;
-constexpr unsigned kXAll = 0xffffu;
-constexpr int kL2Stage = 256; // ray records staged per chunk by k_l2_cross (12 KB)
-
-__device__ __forceinline__ uint4 pack_xlist(unsigned n, const unsigned short* pos, bool all)
+// Boundary cells grouped by Level-1 column: slot by atomic decrement of the per-column count (left at 0; order inside a
+// column is irrelevant, every cell is refined independently).  Entry = (slab-local boundary rank, centre height of the cell).
+__global__ void k_col_cells(const int* __restrict__ boundaryIndex, int nBoundary, int plane, const float* __restrict__ cz,
+                            const unsigned* __restrict__ colCellOff, int* colCellCnt, int2* colCellList)
 {
-	if (all || n > (unsigned)kXSlots) return make_uint4(kXAll, 0u, 0u, 0u);
-	return make_uint4(n | ((unsigned)pos[0] << 16), pos[1] | ((unsigned)pos[2] << 16), pos[3] | ((unsigned)pos[4] << 16), pos[5] | ((unsigned)pos[6] << 16));
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nBoundary) return;
+	const int l1 = boundaryIndex[b], kz = l1 / plane, col = l1 - kz * plane;
+	colCellList[colCellOff[col] + atomicSub(colCellCnt + col, 1) - 1] = make_int2(b, __float_as_int(cz[kz]));
 }
 
-__global__ void __launch_bounds__(256) k_l2_cross(GridP g, L2IO io)
+// K4a.  Level-2 parity rays, one thread per sub-voxel COLUMN of a Level-1 column (replaces CUDAClassifyInOutLevel2Kernel,
+// cu:450-504).  The det/u/v part of the +Z ray test depends only on the xy position of the sub-column, and all boundary cells
+// of one Level-1 column share their n2 x n2 sub-columns and their candidate triangles (the column list, cu:461-463).  So the
+// column list is walked ONCE per Level-1 column (cessna-256: ~9 boundary cells per column with boundary cells, 24 triangles per
+// list), the few triangles that pass (typically 2-4) are kept in registers, and for each boundary cell of the column each of
+// them contributes its parity bits through gpv::ray_cell_mask (certified: only the sub-voxels next to the crossing are
+// evaluated).  Output: one word per (boundary cell, sub-column), bit r = parity of sub-voxel r; k_l2 only loads it.
+constexpr int kRaySlots = 16; // crossings kept in registers (16-bit list positions); further ones are applied in a second walk of the list (rare)
+constexpr int kRayCells = 4;  // boundary cells of the column refined per register chunk
+constexpr int kL2Stage = 256; // ray records staged per chunk (12 KB)
+
+struct RaySub { // one sub-voxel column: origin, list, cells, output slot, height range of the grid column
+	float ox, oy, zMin, zMax; unsigned off; int cnt; unsigned cb, ce; int item;
+};
+
+__device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const RaySub& u, const uint4 pk0, const uint4 pk1, const unsigned n)
+{
+	const int rows = g.n2 * g.n2;
+	const unsigned nk = min(n, (unsigned)kRaySlots);
+	for (unsigned cc = u.cb; cc < u.ce; cc += kRayCells) {
+		unsigned par[kRayCells];
+		float midz[kRayCells];
+		int bb[kRayCells];
+#pragma unroll
+		for (int c = 0; c < kRayCells; c++) {
+			par[c] = 0u; bb[c] = -1; midz[c] = 0.f;
+			if (cc + c < u.ce) { const int2 e = __ldg(io.colCellList + cc + c); bb[c] = e.x; midz[c] = __int_as_float(e.y); }
+		}
+		for (unsigned j = 0; j < nk; j++) {
+			const unsigned w = j >> 1;
+			const unsigned v = w == 0 ? pk0.x : w == 1 ? pk0.y : w == 2 ? pk0.z : w == 3 ? pk0.w : w == 4 ? pk1.x : w == 5 ? pk1.y : w == 6 ? pk1.z : pk1.w;
+			RayTri s;
+			load_ray(s, io.ray48, io.colTris[u.off + ((v >> ((j & 1) * 16)) & 0xffffu)]);
+			RayCol rc;
+			if (!ray_column(s, u.ox, u.oy, rc)) continue; // cannot happen (listed because it passed); keeps rc defined
+			const float k1 = ray_col_bound(s, rc, u.zMin, u.zMax);
+#pragma unroll
+			for (int c = 0; c < kRayCells; c++) if (bb[c] >= 0) par[c] ^= ray_cell_mask(s, rc, k1, midz[c], g.h1z, g.h2z, g.n2);
+		}
+#pragma unroll
+		for (int c = 0; c < kRayCells; c++) if (bb[c] >= 0) io.l2Par[(size_t)bb[c] * rows + u.item] = par[c];
+	}
+	if (n > (unsigned)kRaySlots || u.cnt > 65536) {
+		// more crossings than slots (0.02 % of cessna-256's sub-columns have more than 15), or list positions beyond 16 bits: walk
+		// the list again and fold the remaining crossings into this thread's own words
+		unsigned seen = 0;
+		const bool all = u.cnt > 65536; // positions were not recorded reliably: redo every crossing
+		if (all) for (unsigned cc = u.cb; cc < u.ce; cc++) io.l2Par[(size_t)io.colCellList[cc].x * rows + u.item] = 0u;
+		for (int k = 0; k < u.cnt; k++) {
+			RayTri s;
+			load_ray(s, io.ray48, io.colTris[u.off + k]);
+			RayCol rc;
+			if (!s.ok || !ray_column(s, u.ox, u.oy, rc)) continue;
+			if (!all && seen++ < (unsigned)kRaySlots) continue;
+			const float k1 = ray_col_bound(s, rc, u.zMin, u.zMax);
+			for (unsigned cc = u.cb; cc < u.ce; cc++) {
+				const int2 e = io.colCellList[cc];
+				io.l2Par[(size_t)e.x * rows + u.item] ^= ray_cell_mask(s, rc, k1, __int_as_float(e.y), g.h1z, g.h2z, g.n2);
+			}
+		}
+	}
+}
+
+__device__ __forceinline__ void rays_note(uint4& pk0, uint4& pk1, unsigned& n, unsigned pos)
+{
+	const unsigned v = (pos & 0xffffu) << ((n & 1u) * 16);
+	const unsigned w = n >> 1;
+	if (w == 0) pk0.x |= v; else if (w == 1) pk0.y |= v; else if (w == 2) pk0.z |= v; else if (w == 3) pk0.w |= v;
+	else if (w == 4) pk1.x |= v; else if (w == 5) pk1.y |= v; else if (w == 6) pk1.z |= v; else if (w == 7) pk1.w |= v;
+	n++;
+}
+
+__global__ void __launch_bounds__(256, 3) k_l2_rays(GridP g, L2IO io)
 {
 	__shared__ float4 sStage[kL2Stage * 3]; // G == 1: ray records of the column list, kL2Stage at a time
 	const int n2 = g.n2, rows = n2 * n2;
@@ -693,27 +761,28 @@ __global__ void __launch_bounds__(256) k_l2_cross(GridP g, L2IO io)
 	const float invN2 = 1.f / (float)n2;
 	if (G == 1) {
 		const int col = blockIdx.x;
-		if (!io.colFlag[col]) return;
+		RaySub u;
+		u.cb = io.colCellOff[col]; u.ce = io.colCellOff[col + 1];
+		if (u.cb == u.ce) return;
 		const int jy = col / g.nx, ix = col - jy * g.nx;
-		const unsigned off = io.colOff[col];
-		const int cnt = io.colCount[col];
+		u.off = io.colOff[col]; u.cnt = io.colCount[col];
+		u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz;
 		const float mx = io.cx[ix], my = io.cy[jy];
-		uint4* out = io.xList + (size_t)io.colRank[col] * rows;
 		for (int item0 = 0; item0 < rows; item0 += 256) { // one round unless n2 = 32
-			const int item = item0 + tid;
-			const int q = fast_div(item, invN2), p = item - q * n2;
-			const float ox = (float)(2 * p + 1) * g.h2x + mx - g.h1x, oy = (float)(2 * q + 1) * g.h2y + my - g.h1y; // cu:472-473
-			unsigned short pos[kXSlots] = { 0, 0, 0, 0, 0, 0, 0 };
+			u.item = item0 + tid;
+			const int q = fast_div(u.item, invN2), p = u.item - q * n2;
+			u.ox = l2_centre(p, g.h2x, mx, g.h1x); u.oy = l2_centre(q, g.h2y, my, g.h1y); // cu:472-473
+			uint4 pk0 = make_uint4(0u, 0u, 0u, 0u), pk1 = pk0;
 			unsigned n = 0;
-			for (int k0 = 0; k0 < cnt; k0 += kL2Stage) {
-				const int nrec = min(kL2Stage, cnt - k0);
+			for (int k0 = 0; k0 < u.cnt; k0 += kL2Stage) {
+				const int nrec = min(kL2Stage, u.cnt - k0);
 				__syncthreads();
 				for (int i = tid; i < nrec * 3; i += 256) {
 					const int rec = i / 3;
-					sStage[i] = __ldg(io.ray48 + (size_t)io.colTris[off + k0 + rec] * 3 + (i - rec * 3));
+					sStage[i] = __ldg(io.ray48 + (size_t)io.colTris[u.off + k0 + rec] * 3 + (i - rec * 3));
 				}
 				__syncthreads();
-				if (item < rows) {
+				if (u.item < rows) {
 					for (int k = 0; k < nrec; k++) {
 						const float4 a = sStage[k * 3], b = sStage[k * 3 + 1], c4 = sStage[k * 3 + 2];
 						if (c4.w == 0.f) continue;
@@ -721,36 +790,34 @@ __global__ void __launch_bounds__(256) k_l2_cross(GridP g, L2IO io)
 						s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;
 						s.e2z = c4.x; s.det = c4.y; s.inv = c4.z; s.ok = true; s.well = false;
 						RayCol rc;
-						if (!ray_column(s, ox, oy, rc)) continue;
-#pragma unroll
-						for (int j = 0; j < kXSlots; j++) if (n == (unsigned)j) pos[j] = (unsigned short)(k0 + k);
-						n++;
+						if (ray_column(s, u.ox, u.oy, rc)) rays_note(pk0, pk1, n, (unsigned)(k0 + k));
 					}
 				}
 			}
-			if (item < rows) out[item] = pack_xlist(n, pos, cnt > 65535);
+			if (u.item < rows) rays_apply(g, io, u, pk0, pk1, n);
 		}
 	} else {
-		const int gi = fast_div(tid, 1.f / (float)rows), item = tid - gi * rows;
+		const int gi = fast_div(tid, 1.f / (float)rows);
 		const long long col = (long long)blockIdx.x * G + gi;
-		if (gi >= G || col >= ncol || !io.colFlag[col]) return;
+		if (gi >= G || col >= ncol) return;
+		RaySub u;
+		u.cb = io.colCellOff[col]; u.ce = io.colCellOff[col + 1];
+		if (u.cb == u.ce) return;
+		u.item = tid - gi * rows;
 		const int jy = (int)(col / g.nx), ix = (int)(col - (long long)jy * g.nx);
-		const int q = fast_div(item, invN2), p = item - q * n2;
-		const float ox = (float)(2 * p + 1) * g.h2x + io.cx[ix] - g.h1x, oy = (float)(2 * q + 1) * g.h2y + io.cy[jy] - g.h1y;
-		const unsigned off = io.colOff[col];
-		const int cnt = io.colCount[col];
-		unsigned short pos[kXSlots] = { 0, 0, 0, 0, 0, 0, 0 };
+		const int q = fast_div(u.item, invN2), p = u.item - q * n2;
+		u.ox = l2_centre(p, g.h2x, io.cx[ix], g.h1x); u.oy = l2_centre(q, g.h2y, io.cy[jy], g.h1y);
+		u.off = io.colOff[col]; u.cnt = io.colCount[col];
+		u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz;
+		uint4 pk0 = make_uint4(0u, 0u, 0u, 0u), pk1 = pk0;
 		unsigned n = 0;
-		for (int k = 0; k < cnt; k++) {
+		for (int k = 0; k < u.cnt; k++) {
 			RayTri s;
-			load_ray(s, io.ray48, io.colTris[off + k]);
+			load_ray(s, io.ray48, io.colTris[u.off + k]);
 			RayCol rc;
-			if (!s.ok || !ray_column(s, ox, oy, rc)) continue;
-#pragma unroll
-			for (int j = 0; j < kXSlots; j++) if (n == (unsigned)j) pos[j] = (unsigned short)k;
-			n++;
+			if (s.ok && ray_column(s, u.ox, u.oy, rc)) rays_note(pk0, pk1, n, (unsigned)k);
 		}
-		io.xList[(size_t)io.colRank[col] * rows + item] = pack_xlist(n, pos, cnt > 65535);
+		rays_apply(g, io, u, pk0, pk1, n);
 	}
 }
 
@@ -818,49 +885,17 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 			int col = l1 % (g.nx * g.ny);
 			inf[0] = (int)io.bTriOff[b]; inf[1] = (int)(io.bTriOff[b + 1] - io.bTriOff[b]);
 			inf[2] = (int)io.colOff[col]; inf[3] = io.colCount[col];
-			const unsigned long long xb = (unsigned long long)io.colRank[col] * (unsigned)rows;
-			inf[4] = (int)(unsigned)xb; inf[5] = (int)(unsigned)(xb >> 32); inf[6] = 1; inf[7] = 0;
+			inf[4] = 0; inf[5] = 0; inf[6] = 1; inf[7] = 0;
 		} else { for (int k = 0; k < 8; k++) inf[k] = 0; }
 	}
 	for (int item = tid; item < nItems; item += kL2Threads) sSat[item] = 0;
 	if (tid < 4) sQn[tid] = 0;
 	__syncthreads();
 
-	// ---- phase 1: parity rays.  item = (cell gi, xy-column pq); n2 <= 32 so the z parity fits one word.  Only the triangles on
-	// the sub-column's crossing list (k_l2_cross) are visited; per triangle the certified z-run decides the whole cell at once
-	// unless the crossing lies inside it.
-	const unsigned fullRun = n2 == 32 ? 0xffffffffu : ((1u << n2) - 1);
+	// ---- phase 1: the parity bits along z of every sub-voxel column (k_l2_rays), one coalesced load per item
 	for (int item = tid; item < nItems; item += kL2Threads) {
-		const int gi = fast_div(item, invRows), pq = item - gi * rows, q = fast_div(pq, invN2), p = pq - q * n2;
-		const int* inf = sInfo + gi * 8;
-		unsigned par = 0;
-		if (inf[6]) {
-			const float* c = sC + gi * 3 * n2;
-			const float ox = c[p], oy = c[n2 + q];
-			auto one = [&](int t) {
-				RayTri s;
-				load_ray(s, io.ray48, t);
-				RayCol rc;
-				if (!s.ok || !ray_column(s, ox, oy, rc)) return;
-				const int run = ray_z_run(s, rc, s.well, c[2 * n2], c[3 * n2 - 1]); // the whole cell below / above the crossing?
-				if (run == 0) return;
-				if (run == 1) par ^= fullRun;
-				else for (int r = 0; r < n2; r++) par ^= (unsigned)ray_cell(s, rc, c[2 * n2 + r]) << r;
-			};
-			const unsigned long long xb = (unsigned long long)(unsigned)inf[4] | ((unsigned long long)(unsigned)inf[5] << 32);
-			const uint4 e = __ldg(io.xList + xb + pq);
-			const unsigned n = e.x & 0xffffu;
-			if (n != kXAll) {
-				for (unsigned j = 0; j < n; j++) {
-					const unsigned w = (j + 1) >> 1;
-					const unsigned v = w == 0 ? e.x : (w == 1 ? e.y : (w == 2 ? e.z : e.w));
-					one(io.colTris[inf[2] + ((v >> (((j + 1) & 1) * 16)) & 0xffffu)]);
-				}
-			} else {
-				for (int k = 0; k < inf[3]; k++) one(io.colTris[inf[2] + k]);
-			}
-		}
-		sPar[item] = par;
+		const int gi = fast_div(item, invRows);
+		sPar[item] = sInfo[gi * 8 + 6] ? io.l2Par[(size_t)(b0 + gi) * rows + (item - gi * rows)] : 0u;
 	}
 
 	// ---- phase 2a: SAT, three stages over shared-memory queues so that every stage runs on full warps.

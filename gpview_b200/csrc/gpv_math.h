@@ -259,14 +259,14 @@ GPV_HD bool ray_column(const RayTri& s, float ox, float oy, RayCol& c)
 	c.c0 = Ty * s.e1z; c.c1 = Tx * s.e1z; c.c2 = s.e2z * Q2;
 	return true;
 }
-GPV_HD bool ray_cell(const RayTri& s, const RayCol& c, float oz)
+GPV_HD float ray_cell_t(const RayTri& s, const RayCol& c, float oz)
 {
 	float Tz = oz - s.v1z;
 	float Q0 = c.c0 - Tz * s.e1y;
 	float Q1 = Tz * s.e1x - c.c1;
-	float t = (s.e2x * Q0 + s.e2y * Q1 + c.c2) * s.inv;
-	return t > kEps;
+	return (s.e2x * Q0 + s.e2y * Q1 + c.c2) * s.inv;
 }
+GPV_HD bool ray_cell(const RayTri& s, const RayCol& c, float oz) { return ray_cell_t(s, c, oz) > kEps; }
 
 // ---- certified classification of a whole run of cells along one column (DESIGN.md "Certified z-runs").
 // For a (triangle, column) pair that passed ray_column, t as a function of the origin height is  t = alpha - Tz * (D/det') in
@@ -291,6 +291,61 @@ GPV_HD int ray_z_run(const RayTri& s, const RayCol& c, bool wellConditioned, flo
 	if (t0 + 2.f * bnd <= kEps) return 0;
 	if (t0 - 2.f * bnd - span > kEps) return 1;
 	return 2;
+}
+
+// ---- Level-2 sub-voxel centre along one axis (cu:423-425 / 472-474): ((2p+1)*ext2 + mid) - ext1, all f32
+GPV_HD float l2_centre(int p, float h2, float mid, float h1) { return (float)(2 * p + 1) * h2 + mid - h1; }
+
+// ---- parity bits of one (triangle, sub-voxel column) pair over the n2 <= 32 sub-voxels of ONE Level-1 cell: bit r is set iff
+// ray_cell(s, c, z_r), z_r = l2_centre(r, h2z, midz, h1z).  Bit-identical to n2 calls of ray_cell, but for a well-conditioned
+// triangle only the sub-voxels next to the crossing are evaluated.  With bnd an upper bound of ray_z_run's error bound for the cell:
+//   prefix   t0 - 2 bnd - 1.01 (z_a - z_0) > eps   ->  sub-voxels 0..a are hit   (ray_z_run's "all hit" claim for the run z_0..z_a,
+//            whose own bound is <= bnd because its span and heights lie inside the cell's)
+//   stop     t_r + 2 (bnd + 16u |t_r|) <= eps        ->  sub-voxels r.. are not hit (ray_z_run's "no hit" claim for the run z_r..z_hi,
+//            whose bound is <= bnd + 16u |t_r|: same magnitudes, t_r in place of t_0)
+// The index estimate only chooses where to start; every claim is checked against the actual centres.
+// The part of the bound that does not depend on the cell is computed once per (triangle, sub-column) by ray_col_bound for ALL
+// heights of the grid column [zMin, zMax] (a larger |Tz| only makes the bound more conservative); a negative k1 means "not
+// well conditioned: evaluate every sub-voxel".
+GPV_HD float ray_col_bound(const RayTri& s, const RayCol& c, float zMin, float zMax)
+{
+	if (!s.well) return -1.f;
+	const float Tm = fmaxf(fabsf(zMin - s.v1z), fabsf(zMax - s.v1z));
+	const float k1 = 9.5367431640625e-07f * (fabsf(s.inv) * (fabsf(s.e2x) * (fabsf(c.c0) + Tm * fabsf(s.e1y)) + fabsf(s.e2y) * (fabsf(c.c1) + Tm * fabsf(s.e1x)) + fabsf(c.c2))) + 1e-30f;
+	return k1 <= kFltMax ? k1 : -1.f; // NaN / inf -> no certificate
+}
+
+GPV_HD unsigned ray_cell_mask(const RayTri& s, const RayCol& c, float k1, float midz, float h1z, float h2z, int n2)
+{
+	const unsigned full = n2 >= 32 ? 0xffffffffu : ((1u << n2) - 1u);
+	const float zLo = l2_centre(0, h2z, midz, h1z);
+	int first = 0;
+	unsigned mask = 0;
+	float bnd = 0.f;
+	bool certified = false;
+	if (k1 >= 0.f) {
+		const float zHi = l2_centre(n2 - 1, h2z, midz, h1z);
+		const float t0 = ray_cell_t(s, c, zLo);
+		const float span = (zHi - zLo) * 1.01f;
+		bnd = k1 + 9.5367431640625e-07f * (fabsf(t0) + span);
+		if (bnd <= kFltMax && t0 == t0) {
+			if (t0 + 2.f * bnd <= kEps) return 0u;
+			if (t0 - 2.f * bnd - span > kEps) return full;
+			certified = true;
+			const float room = t0 - 2.f * bnd - kEps;                    // may be <= 0: then a < 0 and nothing is taken for granted
+			const float a = floorf(room / (2.02f * h2z)) - 1.f;          // spacing of the centres is 2*h2z; 1.01 = the slope margin
+			int ai = !(a >= 0.f) ? -1 : (a > (float)(n2 - 1) ? n2 - 1 : (int)a);
+			while (ai >= 0 && !(t0 - 2.f * bnd - 1.01f * (l2_centre(ai, h2z, midz, h1z) - zLo) > kEps)) ai--;
+			first = ai + 1;
+			mask = first >= 32 ? 0xffffffffu : ((1u << first) - 1u);
+		}
+	}
+	for (int r = first; r < n2; r++) {
+		const float t = ray_cell_t(s, c, l2_centre(r, h2z, midz, h1z));
+		mask |= (unsigned)(t > kEps) << r;
+		if (certified && t + 2.f * (bnd + 9.5367431640625e-07f * fabsf(t)) <= kEps) break;
+	}
+	return mask;
 }
 
 // ---- certified candidate columns for the +Z parity fill of one triangle (DESIGN.md "Certified fill").

@@ -120,3 +120,28 @@ extern "C" void probe_z_run(int64_t n, const float* oxy, const float* zrun /* z0
 	}
 	out3[0] = bad; out3[1] = decided; out3[2] = passed;
 }
+
+// ---- ray_cell_mask: the bracketed evaluation of one cell's sub-voxel column must equal n2 independent ray_cell calls.
+// cellz: midz, gsz per item (h1 = gs/2, h2 = gs/n2/2 like gpv_make_grid).  out3: [0] mismatches, [1] pairs that passed the
+// column test, [2] exact evaluations skipped
+extern "C" void probe_cell_mask(int64_t n, const float* oxy, const float* cellz, int n2, const float* tri9, int64_t* out3)
+{
+	int64_t bad = 0, passed = 0, mixed = 0;
+	for (int64_t i = 0; i < n; i++) {
+		const float* T = tri9 + i * 9;
+		RayTri s; RayCol rc;
+		ray_tri_setup(s, T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8]);
+		if (!s.ok || !ray_column(s, oxy[i * 2], oxy[i * 2 + 1], rc)) continue;
+		passed++;
+		const float mid = cellz[i * 2], gs = cellz[i * 2 + 1];
+		const float h1 = gs / 2.0; const float g2 = gs / (n2 * 1.0); const float h2 = g2 / 2.0;
+		unsigned want = 0;
+		for (int r = 0; r < n2; r++) want |= (unsigned)ray_cell(s, rc, l2_centre(r, h2, mid, h1)) << r;
+		// the column bound may be taken over any height range that contains the cell: tight, and as wide as a 1000-cell column
+		const float k1a = ray_col_bound(s, rc, mid - gs, mid + gs), k1b = ray_col_bound(s, rc, mid - 700.f * gs, mid + 300.f * gs);
+		if (ray_cell_mask(s, rc, k1a, mid, h1, h2, n2) != want || ray_cell_mask(s, rc, k1b, mid, h1, h2, n2) != want || ray_cell_mask(s, rc, -1.f, mid, h1, h2, n2) != want) bad++;
+		const unsigned full = n2 >= 32 ? 0xffffffffu : ((1u << n2) - 1u);
+		if (want != 0 && want != full) mixed++;
+	}
+	out3[0] = bad; out3[1] = passed; out3[2] = mixed;
+}

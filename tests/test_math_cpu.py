@@ -226,6 +226,38 @@ def test_certified_z_runs_agree_with_per_cell_evaluation(probe):
     print("z-runs: %d column-passing pairs, %d decided from one evaluation" % (tot[2], tot[1]))
 
 
+def test_cell_mask_equals_per_sub_voxel_evaluation(probe):
+    """gpv::ray_cell_mask (Level-2 parity bits of one cell from a certified prefix + a certified stop) must equal n2
+    independent ray_cell evaluations bit for bit: crossings inside, below, above and grazing the cell; near-vertical and
+    huge-coordinate triangles; cells from 1/1000 of the triangle to 30x its size."""
+    probe.probe_cell_mask.argtypes = [C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+    rng = np.random.default_rng(23)
+    tot = np.zeros(3, np.int64)
+    for n2 in (1, 2, 4, 5, 8, 16, 32):
+        n = 300000
+        scale = 10.0 ** rng.uniform(-2, 3, (n, 1, 1))
+        tri = (rng.normal(0, 1, (n, 3, 3)) * scale + rng.normal(0, 1, (n, 1, 3)) * scale * rng.choice([0, 1, 30, 3000], (n, 1, 1))).astype(np.float32)
+        k = n // 5
+        tri[:k, 2, :2] = (tri[:k, 0, :2] + (tri[:k, 1, :2] - tri[:k, 0, :2]) * rng.uniform(0, 1, (k, 1)) +
+                          rng.normal(0, 1e-4, (k, 2)) * scale[:k, 0]).astype(np.float32)          # near-vertical: tiny 2-D determinant
+        tri[k:2 * k, :, 2] = tri[k:2 * k, :1, 2] + rng.normal(0, 1e-5, (k, 3)).astype(np.float32) * scale[k:2 * k, 0]  # nearly horizontal
+        w = rng.dirichlet([1, 1, 1], n).astype(np.float32)
+        o = (tri * w[:, :, None]).sum(1)
+        oxy = np.ascontiguousarray(o[:, :2], np.float32)
+        gs = (10.0 ** rng.uniform(-3, 1.5, n) * scale[:, 0, 0]).astype(np.float32)
+        # cell centre: crossing inside the cell (60 %), exactly on a sub-voxel centre (10 %), cell far below / above (30 %)
+        u = rng.uniform(0, 1, n)
+        off = np.where(u < 0.6, rng.uniform(-0.6, 0.6, n), np.where(u < 0.7, (rng.integers(0, n2, n) + 0.5) / n2 - 0.5, rng.uniform(-40, 40, n)))
+        mid = (o[:, 2] + gs * off).astype(np.float32)
+        cellz = np.ascontiguousarray(np.stack([mid, gs], -1), np.float32)
+        out = np.zeros(3, np.int64)
+        probe.probe_cell_mask(n, _fp(oxy), _fp(cellz), n2, _fp(np.ascontiguousarray(tri.reshape(n, 9))), out.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert out[0] == 0, (n2, out)
+        tot += out
+    assert tot[1] > 400000 and tot[2] > 100000, tot   # plenty of passing pairs, plenty of cells with the crossing inside
+    print("cell masks: %d column-passing pairs, %d with the crossing inside the cell" % (tot[1], tot[2]))
+
+
 @pytest.mark.parametrize("origin,gs", [(0.0, 0.125), (1000.0, 0.125), (-250000.0, 1.0), (3.0, 1e-3), (0.0, 40.0)])
 def test_certified_candidates_tight_and_covering_on_shifted_grids(probe, origin, gs):
     """Same property as above on grids far from the origin / with tiny or huge cells, with triangles from 1/20 of a cell
