@@ -60,7 +60,7 @@ struct gpv_ctx {
 	int device = 0;
 	int smCount = 0;
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
-	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, longList, colCellCnt, colCellOff, colCellList, l2Par;
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, longList, colCellCnt, colCellOff, colCellList, l2Par, cellMid;
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
@@ -111,7 +111,7 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->longList, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->longList, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid };
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
 	if (c->haveEvents) for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -273,7 +273,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	const long long n23 = (long long)g.n2 * g.n2 * g.n2;
 	if (c->cellTris.ensure((size_t)T1.triTotal * 4 + 32) || c->colTris.ensure((size_t)T1.colTotalOver * 4 + 32) || c->crossTri.ensure((size_t)T1.crossTotal * 4 + 32))
 		return 1;
-	if (wantL2 && (c->l2State.ensure((size_t)(nB * n23) + 32) || c->colCellList.ensure((size_t)nB * 8 + 32) || c->l2Par.ensure((size_t)nB * g.n2 * g.n2 * 4 + 32))) return 1;
+	if (wantL2 && (c->l2State.ensure((size_t)(nB * n23) + 32) || c->colCellList.ensure((size_t)nB * 8 + 32) || c->cellMid.ensure((size_t)nB * 16 + 32) || c->l2Par.ensure((size_t)nB * g.n2 * g.n2 * 4 + 32))) return 1;
 	if (wantN && (c->l1Normal.ensure((size_t)cells * 3 + 32) || (wantL2 && c->l2Normal.ensure((size_t)(nB * n23) * 3 + 32)))) return 1;
 
 	bo.prefix = c->prefix.as<int>(); bo.bTriOff = c->bTriOff.as<unsigned>(); bo.cellTris = c->cellTris.as<int>();
@@ -337,15 +337,17 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		lio.tri48 = tri48; lio.ray48 = ray48; lio.plane16 = c->plane16.as<float4>(); lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
 		lio.cellTris = c->cellTris.as<int>(); lio.colOff = c->colOff.as<unsigned>(); lio.colCount = c->colCount.as<int>(); lio.colTris = c->colTris.as<int>();
 		lio.cx = cx; lio.cy = cy; lio.cz = cz; lio.l2State = c->l2State.as<unsigned char>(); lio.nBoundary = (int)nB; lio.totals = dT;
-		lio.colCellOff = c->colCellOff.as<unsigned>(); lio.colCellList = c->colCellList.as<int2>(); lio.l2Par = c->l2Par.as<unsigned>();
-		const int rows = g.n2 * g.n2, G = rows >= kL2Threads ? 1 : kL2Threads / rows;
-		const size_t smem = (size_t)l2_smem_layout(g.n2).total;
-		if (smem > 48 * 1024 && !c->l2AttrSet) { // n2 = 32 only (q2 queue of 16 KB on top of the 16 KB q1 queue and 12 KB of row state)
+		lio.colCellOff = c->colCellOff.as<unsigned>(); lio.colCellList = c->colCellList.as<int2>(); lio.l2Par = c->l2Par.as<unsigned>(); lio.cellMid = c->cellMid.as<float4>();
+		const L2K K = l2_constants(g.n2);
+		const int G = K.G;
+		const size_t smem = (size_t)K.total;
+		if (smem > 48 * 1024 && !c->l2AttrSet) {
 			GPV_CUDA(cudaFuncSetAttribute(k_l2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 			c->l2AttrSet = true;
 		}
 		// K4a: boundary cells grouped by Level-1 column, then the parity bits of every sub-voxel column, one walk of the column list per column
-		k_col_cells<<<(unsigned)((nB + 255) / 256), 256, 0, st>>>(lio.boundaryIndex, (int)nB, (int)ncol, cz, lio.colCellOff, c->colCellCnt.as<int>(), c->colCellList.as<int2>());
+		k_col_cells<<<(unsigned)((nB + 255) / 256), 256, 0, st>>>(lio.boundaryIndex, (int)nB, (int)ncol, g.nx, cx, cy, cz, lio.colCellOff, c->colCellCnt.as<int>(), c->colCellList.as<int2>(),
+		                                                        c->cellMid.as<float4>());
 		k_l2_rays<<<(unsigned)((ncol + G - 1) / G), 256, 0, st>>>(g, lio);
 		launches += 2;
 		// With a host sink the boundary cells are refined in chunks and every finished chunk's bytes start their way to the
@@ -357,7 +359,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			const long long bb = k * per, be = std::min(nB, bb + per);
 			if (bb >= be) break;
 			lio.bBegin = (int)bb; lio.nBoundary = (int)be;
-			k_l2<<<(unsigned)((be - bb + G - 1) / G), kL2Threads, smem, st>>>(g, lio);
+			k_l2<<<(unsigned)((be - bb + G - 1) / G), kL2Threads, smem, st>>>(g, lio, K);
 			launches++;
 			if (sink && sink->level2_inout) {
 				GPV_CUDA(cudaEventRecord(c->evChunk[k], st));

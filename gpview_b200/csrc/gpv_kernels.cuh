@@ -657,6 +657,7 @@ struct L2IO {
 	const unsigned* colOff; const int* colCount; const int* colTris;
 	const unsigned* colCellOff; const int2* colCellList; // boundary cells (slab-local rank, centre height) of every Level-1 column, CSR
 	unsigned* l2Par;                                    // [boundary rank][n2*n2] parity bits along z of every sub-voxel column (k_l2_rays)
+	const float4* cellMid;                              // [boundary rank] centre of the Level-1 cell (k_col_cells)
 	const float* cx; const float* cy; const float* cz;
 	unsigned char* l2State; // nBoundary * n2^3 file bytes
 	int bBegin;             // this launch refines boundary ranks [bBegin, nBoundary)
@@ -670,13 +671,16 @@ __device__ __forceinline__ int fast_div(int a, float inv) { return __float2int_r
 
 // Boundary cells grouped by Level-1 column: slot by atomic decrement of the per-column count (left at 0; order inside a
 // column is irrelevant, every cell is refined independently).  Entry = (slab-local boundary rank, centre height of the cell).
-__global__ void k_col_cells(const int* __restrict__ boundaryIndex, int nBoundary, int plane, const float* __restrict__ cz,
-                            const unsigned* __restrict__ colCellOff, int* colCellCnt, int2* colCellList)
+// Also the centre of every boundary cell by rank, so that k_l2 does not decode linear indices.
+__global__ void k_col_cells(const int* __restrict__ boundaryIndex, int nBoundary, int plane, int nx, const float* __restrict__ cx, const float* __restrict__ cy,
+                            const float* __restrict__ cz, const unsigned* __restrict__ colCellOff, int* colCellCnt, int2* colCellList, float4* cellMid)
 {
 	const int b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= nBoundary) return;
-	const int l1 = boundaryIndex[b], kz = l1 / plane, col = l1 - kz * plane;
-	colCellList[colCellOff[col] + atomicSub(colCellCnt + col, 1) - 1] = make_int2(b, __float_as_int(cz[kz]));
+	const int l1 = boundaryIndex[b], kz = l1 / plane, col = l1 - kz * plane, jy = col / nx, ix = col - jy * nx;
+	const float mz = cz[kz];
+	cellMid[b] = make_float4(cx[ix], cy[jy], mz, 0.f);
+	colCellList[colCellOff[col] + atomicSub(colCellCnt + col, 1) - 1] = make_int2(b, __float_as_int(mz));
 }
 
 // K4a.  Level-2 parity rays, one thread per sub-voxel COLUMN of a Level-1 column (replaces CUDAClassifyInOutLevel2Kernel,
@@ -714,7 +718,7 @@ __device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const
 			load_ray(s, io.ray48, io.colTris[u.off + ((v >> ((j & 1) * 16)) & 0xffffu)]);
 			RayCol rc;
 			if (!ray_column(s, u.ox, u.oy, rc)) continue; // cannot happen (listed because it passed); keeps rc defined
-			const float k1 = ray_col_bound(s, rc, u.zMin, u.zMax);
+			const RayColZ k1 = ray_col_bound(s, rc, u.zMin, u.zMax, g.gsz);
 #pragma unroll
 			for (int c = 0; c < kRayCells; c++) if (bb[c] >= 0) par[c] ^= ray_cell_mask(s, rc, k1, midz[c], g.h1z, g.h2z, g.n2);
 		}
@@ -733,7 +737,7 @@ __device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const
 			RayCol rc;
 			if (!s.ok || !ray_column(s, u.ox, u.oy, rc)) continue;
 			if (!all && seen++ < (unsigned)kRaySlots) continue;
-			const float k1 = ray_col_bound(s, rc, u.zMin, u.zMax);
+			const RayColZ k1 = ray_col_bound(s, rc, u.zMin, u.zMax, g.gsz);
 			for (unsigned cc = u.cb; cc < u.ce; cc++) {
 				const int2 e = io.colCellList[cc];
 				io.l2Par[(size_t)e.x * rows + u.item] ^= ray_cell_mask(s, rc, k1, __int_as_float(e.y), g.h1z, g.h2z, g.n2);
@@ -827,76 +831,75 @@ __global__ void __launch_bounds__(256, 3) k_l2_rays(GridP g, L2IO io)
 constexpr int kL2Threads = 256;
 constexpr int kL2Batch = 8;   // triangles per round of the (row, triangle) queue
 
-// shared-memory layout of k_l2 (bytes), shared by the kernel and the launch code
-struct L2Smem { int par, sat, info, q1, q2, qn, total; };
-__host__ __device__ inline L2Smem l2_smem_layout(int n2)
+// Launch constants of k_l2, computed once on the host (no integer divisions / layout arithmetic per CTA): geometry of the
+// item space and the shared-memory layout (byte offsets).
+struct L2K {
+	int n2, rows, G, nItems, parStride; // G cells per CTA, nItems = G*rows (cell, row) items, parStride = n2*(n2+1) padded parity words per cell
+	float invRows, invN2, inv3N2;
+	int par, sat, info, q1, q2, qn, total;
+};
+inline L2K l2_constants(int n2)
 {
-	const int rows = n2 * n2, G = rows >= kL2Threads ? 1 : kL2Threads / rows, items = G * rows;
-	L2Smem L;
-	int o = G * 3 * n2 * 4;          // [G][3][n2] sub-voxel centres
-	L.par = o; o += items * 4;       // [items] parity bits along z per xy-column
-	L.sat = o; o += items * 4;       // [items] SAT hit bits along x per row
-	L.info = o; o += G * 8 * 4;      // [G][8] triOff, triCnt, colOff, colCnt, xList base (2 words), valid, -
+	L2K K{};
+	K.n2 = n2; K.rows = n2 * n2; K.G = K.rows >= kL2Threads ? 1 : kL2Threads / K.rows; K.nItems = K.G * K.rows; K.parStride = n2 * (n2 + 1);
+	K.invRows = 1.f / (float)K.rows; K.invN2 = 1.f / (float)n2; K.inv3N2 = 1.f / (float)(3 * n2);
+	int o = K.G * 3 * n2 * 4;                // [G][3][n2] sub-voxel centres
+	K.par = o; o += K.G * K.parStride * 4;   // [G][n2][n2+1] parity bits along z per xy-column (q-major, padded: phase 2b reads down a column of it)
+	K.sat = o; o += K.nItems * 4;            // [nItems] SAT hit bits along x per row
+	K.info = o; o += (K.G * 2 + 2) * 4;      // [G][2] triOff, triCnt (0 for cells past the end); then the CTA-wide longest list
 	o = (o + 15) & ~15;
-	L.q1 = o; o += kL2Threads * kL2Batch * 8;    // (row, triangle) queue: item | plo<<16 | phi<<24, triangle
-	L.q2 = o; o += kL2Threads * n2 * 2;          // sub-voxel queue of one slice of kL2Threads (row, triangle) entries: entry<<5 | p
+	K.q1 = o; o += kL2Threads * kL2Batch * 8;    // (row, triangle) queue: item | plo<<16 | phi<<24, triangle
+	K.q2 = o; o += kL2Threads * n2 * 2;          // sub-voxel queue of one slice of kL2Threads (row, triangle) entries: entry<<5 | p
 	o = (o + 15) & ~15;
-	L.qn = o; o += 16;               // queue fills: [0..1] (row, triangle) queue, ping-pong; [2..3] sub-voxel queue, ping-pong
-	L.total = o;
-	return L;
+	K.qn = o; o += 16;                       // queue fills: [0..1] (row, triangle) queue, ping-pong; [2..3] sub-voxel queue, ping-pong
+	K.total = o;
+	return K;
 }
 
-__global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2IO io)
+__global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2IO io, L2K K)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
-	const int n2 = g.n2, rows = n2 * n2;
-	const int G = max(1, kL2Threads / rows);
-	const int nItems = G * rows;
-	const L2Smem L = l2_smem_layout(n2);
+	const int n2 = K.n2, rows = K.rows, G = K.G, nItems = K.nItems;
 	float* sC = reinterpret_cast<float*>(smemRaw);
-	unsigned* sPar = reinterpret_cast<unsigned*>(smemRaw + L.par);
-	unsigned* sSat = reinterpret_cast<unsigned*>(smemRaw + L.sat);
-	int* sInfo = reinterpret_cast<int*>(smemRaw + L.info);
-	uint2* sQ1 = reinterpret_cast<uint2*>(smemRaw + L.q1);
-	unsigned short* sQ2 = reinterpret_cast<unsigned short*>(smemRaw + L.q2);
-	int* sQn = reinterpret_cast<int*>(smemRaw + L.qn);
+	unsigned* sPar = reinterpret_cast<unsigned*>(smemRaw + K.par);
+	unsigned* sSat = reinterpret_cast<unsigned*>(smemRaw + K.sat);
+	int* sInfo = reinterpret_cast<int*>(smemRaw + K.info);
+	uint2* sQ1 = reinterpret_cast<uint2*>(smemRaw + K.q1);
+	unsigned short* sQ2 = reinterpret_cast<unsigned short*>(smemRaw + K.q2);
+	int* sQn = reinterpret_cast<int*>(smemRaw + K.qn);
 	const int tid = threadIdx.x, lane = tid & 31;
 	const long long b0 = io.bBegin + (long long)blockIdx.x * G;
-	const float invRows = 1.f / (float)rows, invN2 = 1.f / (float)n2;
+	const float invRows = K.invRows, invN2 = K.invN2;
 
+	if (tid == 0) sInfo[2 * G] = 0;
+	if (tid < 4) sQn[tid] = 0;
+	__syncthreads();
 	for (int k = tid; k < G * 3 * n2; k += kL2Threads) {
-		int gi = k / (3 * n2), rem = k - gi * 3 * n2, ax = rem / n2, p = rem - ax * n2;
-		long long b = b0 + gi;
+		const int gi = fast_div(k, K.inv3N2), rem = k - gi * 3 * n2, ax = fast_div(rem, invN2), p = rem - ax * n2;
+		const long long b = b0 + gi;
 		float val = 0.f;
 		if (b < io.nBoundary) {
-			int l1 = io.boundaryIndex[b];
-			int kz = l1 / (g.nx * g.ny), ij = l1 - kz * g.nx * g.ny, jy = ij / g.nx, ix = ij - jy * g.nx;
-			float mid = ax == 0 ? io.cx[ix] : (ax == 1 ? io.cy[jy] : io.cz[kz]);
-			float e2 = ax == 0 ? g.h2x : (ax == 1 ? g.h2y : g.h2z), e1 = ax == 0 ? g.h1x : (ax == 1 ? g.h1y : g.h1z);
-			val = (float)(2 * p + 1) * e2 + mid - e1;
+			const float4 m = __ldg(io.cellMid + b);
+			const float mid = ax == 0 ? m.x : (ax == 1 ? m.y : m.z);
+			const float e2 = ax == 0 ? g.h2x : (ax == 1 ? g.h2y : g.h2z), e1 = ax == 0 ? g.h1x : (ax == 1 ? g.h1y : g.h1z);
+			val = l2_centre(p, e2, mid, e1);
 		}
 		sC[k] = val;
 	}
 	for (int gi = tid; gi < G; gi += kL2Threads) {
-		long long b = b0 + gi;
-		int* inf = sInfo + gi * 8;
-		if (b < io.nBoundary) {
-			int l1 = io.boundaryIndex[b];
-			int col = l1 % (g.nx * g.ny);
-			inf[0] = (int)io.bTriOff[b]; inf[1] = (int)(io.bTriOff[b + 1] - io.bTriOff[b]);
-			inf[2] = (int)io.colOff[col]; inf[3] = io.colCount[col];
-			inf[4] = 0; inf[5] = 0; inf[6] = 1; inf[7] = 0;
-		} else { for (int k = 0; k < 8; k++) inf[k] = 0; }
+		const long long b = b0 + gi;
+		int off = 0, cnt = 0;
+		if (b < io.nBoundary) { off = (int)io.bTriOff[b]; cnt = (int)(io.bTriOff[b + 1] - io.bTriOff[b]); }
+		sInfo[gi * 2] = off; sInfo[gi * 2 + 1] = cnt;
+		atomicMax(sInfo + 2 * G, cnt);
 	}
-	for (int item = tid; item < nItems; item += kL2Threads) sSat[item] = 0;
-	if (tid < 4) sQn[tid] = 0;
-	__syncthreads();
-
 	// ---- phase 1: the parity bits along z of every sub-voxel column (k_l2_rays), one coalesced load per item
 	for (int item = tid; item < nItems; item += kL2Threads) {
-		const int gi = fast_div(item, invRows);
-		sPar[item] = sInfo[gi * 8 + 6] ? io.l2Par[(size_t)(b0 + gi) * rows + (item - gi * rows)] : 0u;
+		const int gi = fast_div(item, invRows), pq = item - gi * rows, q = fast_div(pq, invN2), p = pq - q * n2;
+		sSat[item] = 0;
+		sPar[gi * K.parStride + q * (n2 + 1) + p] = (b0 + gi < io.nBoundary) ? io.l2Par[(size_t)(b0 + gi) * rows + pq] : 0u;
 	}
+	__syncthreads();
 
 	// ---- phase 2a: SAT, three stages over shared-memory queues so that every stage runs on full warps.
 	//   A  every (row, triangle) pair of the cell gets the certified plane interval (gpv::plane_row_interval, ~12 instructions);
@@ -910,8 +913,7 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	// fills are ping-pong counters, reset one round ahead, which keeps it to two barriers per round.
 	{
 		const float inv2h = 1.f / (2.f * g.h2x);
-		int maxCnt = 0; // CTA-wide longest cell list (every thread must take part in the barriers below)
-		for (int gi = 0; gi < G; gi++) maxCnt = max(maxCnt, sInfo[gi * 8 + 1]);
+		const int maxCnt = sInfo[2 * G]; // CTA-wide longest cell list (every thread must take part in the barriers below)
 		int round1 = 0, round2 = 0;
 		for (int itemBase = 0; itemBase < nItems; itemBase += kL2Threads) { // one pass unless n2 = 32
 			const int item = itemBase + tid;
@@ -922,7 +924,7 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 				const float* c = sC + gi * 3 * n2;
 				c0 = c[0]; cy2 = c[n2 + q]; cz2 = c[2 * n2 + r];
 				slack = 9.5367431640625e-07f * (fabsf(c0) + 2.f * g.gsx); // 16u(|mid_x| + gs_x) >= |(c_p - c_0) - 2*h2x*p|
-				triOff = sInfo[gi * 8]; triCnt = sInfo[gi * 8 + 1];        // 0 for cells past the end
+				triOff = sInfo[gi * 2]; triCnt = sInfo[gi * 2 + 1];        // 0 for cells past the end
 			}
 			for (int kb = 0; kb < maxCnt; kb += kL2Batch) {
 				int* q1n = sQn + (round1 & 1);
@@ -1004,14 +1006,14 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	__syncthreads();
 
 	// ---- phase 2b: the row's file bytes
-	unsigned long long nIn = 0, nBd = 0;
+	unsigned nIn = 0, nBd = 0;
 	for (int item = tid; item < nItems; item += kL2Threads) {
 		const int gi = fast_div(item, invRows), row = item - gi * rows, r = fast_div(row, invN2), q = row - r * n2;
-		long long b = b0 + gi;
+		const long long b = b0 + gi;
 		if (b >= io.nBoundary) continue;
 		const unsigned sat = sSat[item];
 		unsigned par = 0;
-		const unsigned* pr = sPar + gi * rows + q * n2;
+		const unsigned* pr = sPar + gi * K.parStride + q * (n2 + 1); // consecutive lanes = consecutive q: stride n2+1 words, no bank conflicts
 		for (int p = 0; p < n2; p++) par |= ((pr[p] >> r) & 1u) << p;
 		par &= ~sat;
 		nIn += __popc(par); nBd += __popc(sat);
@@ -1028,8 +1030,8 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 			for (int p = 0; p < n2; p++) out[p] = ((sat >> p) & 1) ? 254 : (((par >> p) & 1) ? 127 : 0);
 		}
 	}
-	nIn = warp_sum(nIn); nBd = warp_sum(nBd);
-	if ((tid & 31) == 0 && (nIn | nBd)) { atomicAdd(&io.totals->l2Inside, nIn); atomicAdd(&io.totals->l2Boundary, nBd); }
+	nIn = __reduce_add_sync(0xffffffffu, nIn); nBd = __reduce_add_sync(0xffffffffu, nBd);
+	if (lane == 0 && (nIn | nBd)) { atomicAdd(&io.totals->l2Inside, (unsigned long long)nIn); atomicAdd(&io.totals->l2Boundary, (unsigned long long)nBd); }
 }
 
 // ------------------------------------------------------------------------------------------------ normals

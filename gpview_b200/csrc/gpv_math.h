@@ -305,17 +305,23 @@ GPV_HD float l2_centre(int p, float h2, float mid, float h1) { return (float)(2 
 //            whose bound is <= bnd + 16u |t_r|: same magnitudes, t_r in place of t_0)
 // The index estimate only chooses where to start; every claim is checked against the actual centres.
 // The part of the bound that does not depend on the cell is computed once per (triangle, sub-column) by ray_col_bound for ALL
-// heights of the grid column [zMin, zMax] (a larger |Tz| only makes the bound more conservative); a negative k1 means "not
-// well conditioned: evaluate every sub-voxel".
-GPV_HD float ray_col_bound(const RayTri& s, const RayCol& c, float zMin, float zMax)
+// heights of the grid column [zMin, zMax] (a larger |Tz| or span only makes the bound more conservative); a negative k1 means
+// "not well conditioned: evaluate every sub-voxel".
+struct RayColZ { float k1, span; }; // k1 < 0: no certificate
+GPV_HD RayColZ ray_col_bound(const RayTri& s, const RayCol& c, float zMin, float zMax, float gsz)
 {
-	if (!s.well) return -1.f;
+	RayColZ z;
+	// upper bound of 1.01 (z_hi - z_lo) of every cell of the column: the centres span (2 n2 - 2) h2z < gsz, plus their own rounding
+	z.span = 1.01f * (gsz + 9.5367431640625e-07f * (fabsf(zMin) + fabsf(zMax)));
+	z.k1 = -1.f;
+	if (!s.well) return z;
 	const float Tm = fmaxf(fabsf(zMin - s.v1z), fabsf(zMax - s.v1z));
-	const float k1 = 9.5367431640625e-07f * (fabsf(s.inv) * (fabsf(s.e2x) * (fabsf(c.c0) + Tm * fabsf(s.e1y)) + fabsf(s.e2y) * (fabsf(c.c1) + Tm * fabsf(s.e1x)) + fabsf(c.c2))) + 1e-30f;
-	return k1 <= kFltMax ? k1 : -1.f; // NaN / inf -> no certificate
+	const float k1 = 9.5367431640625e-07f * (fabsf(s.inv) * (fabsf(s.e2x) * (fabsf(c.c0) + Tm * fabsf(s.e1y)) + fabsf(s.e2y) * (fabsf(c.c1) + Tm * fabsf(s.e1x)) + fabsf(c.c2)) + z.span) + 1e-30f;
+	if (k1 <= kFltMax) z.k1 = k1; // NaN / inf -> no certificate
+	return z;
 }
 
-GPV_HD unsigned ray_cell_mask(const RayTri& s, const RayCol& c, float k1, float midz, float h1z, float h2z, int n2)
+GPV_HD unsigned ray_cell_mask(const RayTri& s, const RayCol& c, const RayColZ& z, float midz, float h1z, float h2z, int n2)
 {
 	const unsigned full = n2 >= 32 ? 0xffffffffu : ((1u << n2) - 1u);
 	const float zLo = l2_centre(0, h2z, midz, h1z);
@@ -323,14 +329,12 @@ GPV_HD unsigned ray_cell_mask(const RayTri& s, const RayCol& c, float k1, float 
 	unsigned mask = 0;
 	float bnd = 0.f;
 	bool certified = false;
-	if (k1 >= 0.f) {
-		const float zHi = l2_centre(n2 - 1, h2z, midz, h1z);
+	if (z.k1 >= 0.f) {
 		const float t0 = ray_cell_t(s, c, zLo);
-		const float span = (zHi - zLo) * 1.01f;
-		bnd = k1 + 9.5367431640625e-07f * (fabsf(t0) + span);
+		bnd = z.k1 + 9.5367431640625e-07f * fabsf(t0); // >= ray_z_run's bound for this cell (column-wide |Tz| and span)
+		if (t0 + 2.f * bnd <= kEps) return 0u;          // every comparison is false for NaN / inf: falls through to plain evaluation
+		if (t0 - 2.f * bnd - z.span > kEps) return full;
 		if (bnd <= kFltMax && t0 == t0) {
-			if (t0 + 2.f * bnd <= kEps) return 0u;
-			if (t0 - 2.f * bnd - span > kEps) return full;
 			certified = true;
 			const float room = t0 - 2.f * bnd - kEps;                    // may be <= 0: then a < 0 and nothing is taken for granted
 			const float a = floorf(room / (2.02f * h2z)) - 1.f;          // spacing of the centres is 2*h2z; 1.01 = the slope margin
