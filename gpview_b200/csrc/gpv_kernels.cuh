@@ -84,7 +84,7 @@ __global__ void k_tables(GridP g, float* cx, float* cy, float* cz)
 //   tri48  v0|v1|v2 as float4; the three w lanes carry the clipped Level-1 footprint (cu:333-378) as packed 16-bit fields
 //          w0 = lox | loy<<16, w1 = loz | dx<<16, w2 = dy | dz<<16
 //   ray48  v1xyz e1xyz e2xyz det inv ok  (gpv::RayTri)
-//   plane16 normalised plane record of the certified Level-2 plane culling (gpv::PlaneRec)
+//   plane16 plane record of the certified Level-2 plane culling, normalised by Nz (gpv::PlaneRec on permuted axes)
 //   crossFp i0 | j0<<16, di | dj<<16, kind, -   certified candidate columns of the +Z parity fill (gpv::fill_candidates)
 //   binCnt / crossCnt  number of (triangle, cell) / (triangle, column) work items
 // All records are 16-byte aligned so that contiguous triangle ranges can be moved by TMA bulk copies.
@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(256) k_prepare(const float* __restrict__ flat,
 		ray48[(base + t) * 3 + 0] = make_float4(r.v1x, r.v1y, r.v1z, r.e1x);
 		ray48[(base + t) * 3 + 1] = make_float4(r.e1y, r.e1z, r.e2x, r.e2y);
 		ray48[(base + t) * 3 + 2] = make_float4(r.e2z, r.det, r.inv, r.ok ? (r.well ? 2.f : 1.f) : 0.f);
-		PlaneRec pl = plane_rec_setup(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], g.gsx, g.gsy, g.gsz, g.h2x, g.h2y, g.h2z);
+		// normalised by Nz, for intervals along a sub-voxel column: the same function on cyclically permuted coordinates (x,y,z) <- (z,x,y)
+		PlaneRec pl = plane_rec_setup(v[2], v[0], v[1], v[5], v[3], v[4], v[8], v[6], v[7], g.gsz, g.gsx, g.gsy, g.h2z, g.h2x, g.h2y);
 		plane16[base + t] = make_float4(pl.sx, pl.ny, pl.nz, pl.R);
 		int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
 		int kind = fill_candidates(r, g.minx, g.miny, g.gsx, g.gsy, g.nx, g.ny, i0, i1, j0, j1);
@@ -834,34 +835,37 @@ constexpr int kL2Batch = 8;   // triangles per round of the (row, triangle) queu
 // Launch constants of k_l2, computed once on the host (no integer divisions / layout arithmetic per CTA): geometry of the
 // item space and the shared-memory layout (byte offsets).
 struct L2K {
-	int n2, rows, G, nItems, parStride; // G cells per CTA, nItems = G*rows (cell, row) items, parStride = n2*(n2+1) padded parity words per cell
+	int n2, rows, G, nItems;       // G cells per CTA, nItems = G*rows (cell, sub-voxel column) items
 	float invRows, invN2, inv3N2;
-	int par, sat, info, q1, q2, qn, total;
+	int sat, info, q1, q2, qn, total;
 };
 inline L2K l2_constants(int n2)
 {
 	L2K K{};
-	K.n2 = n2; K.rows = n2 * n2; K.G = K.rows >= kL2Threads ? 1 : kL2Threads / K.rows; K.nItems = K.G * K.rows; K.parStride = n2 * (n2 + 1);
+	K.n2 = n2; K.rows = n2 * n2; K.G = K.rows >= kL2Threads ? 1 : kL2Threads / K.rows; K.nItems = K.G * K.rows;
 	K.invRows = 1.f / (float)K.rows; K.invN2 = 1.f / (float)n2; K.inv3N2 = 1.f / (float)(3 * n2);
 	int o = K.G * 3 * n2 * 4;                // [G][3][n2] sub-voxel centres
-	K.par = o; o += K.G * K.parStride * 4;   // [G][n2][n2+1] parity bits along z per xy-column (q-major, padded: phase 2b reads down a column of it)
-	K.sat = o; o += K.nItems * 4;            // [nItems] SAT hit bits along x per row
+	K.sat = o; o += K.nItems * 4;            // [nItems] SAT hit bits along z per sub-voxel column
 	K.info = o; o += (K.G * 2 + 2) * 4;      // [G][2] triOff, triCnt (0 for cells past the end); then the CTA-wide longest list
 	o = (o + 15) & ~15;
-	K.q1 = o; o += kL2Threads * kL2Batch * 8;    // (row, triangle) queue: item | plo<<16 | phi<<24, triangle
-	K.q2 = o; o += kL2Threads * n2 * 2;          // sub-voxel queue of one slice of kL2Threads (row, triangle) entries: entry<<5 | p
+	K.q1 = o; o += kL2Threads * kL2Batch * 8;    // (column, triangle) queue: item | rlo<<16 | rhi<<24, triangle
+	K.q2 = o; o += kL2Threads * n2 * 2;          // sub-voxel queue of one slice of kL2Threads (column, triangle) entries: entry<<5 | r
 	o = (o + 15) & ~15;
-	K.qn = o; o += 16;                       // queue fills: [0..1] (row, triangle) queue, ping-pong; [2..3] sub-voxel queue, ping-pong
+	K.qn = o; o += 16;                       // queue fills: [0..1] (column, triangle) queue, ping-pong; [2..3] sub-voxel queue, ping-pong
 	K.total = o;
 	return K;
 }
 
+// K4.  Level-2 SAT + final bytes (replaces CUDAClassifyTessellationLevel2Kernel, cu:403-448, and the 2-overwrites-1 merge with
+// the parity kernel's result).  A CTA of 256 threads refines G = max(1, 256/n2^2) boundary cells; an item is one sub-voxel
+// COLUMN (cell, p, q) -- the same unit k_l2_rays works on, so the SAT bits and the parity bits of a column share one word
+// layout (bit r = sub-voxel r) and no transposition is needed.  Everything of the SAT that does not involve z is hoisted
+// per (column, triangle) (gpv::SatCol).  A warp's byte stores cover 32 consecutive sub-voxels of Level2InOut.raw.
 __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2IO io, L2K K)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	const int n2 = K.n2, rows = K.rows, G = K.G, nItems = K.nItems;
 	float* sC = reinterpret_cast<float*>(smemRaw);
-	unsigned* sPar = reinterpret_cast<unsigned*>(smemRaw + K.par);
 	unsigned* sSat = reinterpret_cast<unsigned*>(smemRaw + K.sat);
 	int* sInfo = reinterpret_cast<int*>(smemRaw + K.info);
 	uint2* sQ1 = reinterpret_cast<uint2*>(smemRaw + K.q1);
@@ -893,38 +897,33 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 		sInfo[gi * 2] = off; sInfo[gi * 2 + 1] = cnt;
 		atomicMax(sInfo + 2 * G, cnt);
 	}
-	// ---- phase 1: the parity bits along z of every sub-voxel column (k_l2_rays), one coalesced load per item
-	for (int item = tid; item < nItems; item += kL2Threads) {
-		const int gi = fast_div(item, invRows), pq = item - gi * rows, q = fast_div(pq, invN2), p = pq - q * n2;
-		sSat[item] = 0;
-		sPar[gi * K.parStride + q * (n2 + 1) + p] = (b0 + gi < io.nBoundary) ? io.l2Par[(size_t)(b0 + gi) * rows + pq] : 0u;
-	}
+	for (int item = tid; item < nItems; item += kL2Threads) sSat[item] = 0;
 	__syncthreads();
 
-	// ---- phase 2a: SAT, three stages over shared-memory queues so that every stage runs on full warps.
-	//   A  every (row, triangle) pair of the cell gets the certified plane interval (gpv::plane_row_interval, ~12 instructions);
-	//      pairs that can still hit go to the (row, triangle) queue (ballot/popc per warp, one atomicAdd per warp).
-	//   B1 one queue entry per thread: the p-independent predicates of the SAT (gpv::sat_row_setup: y/z AABB, the three X-axis
-	//      tests) and the certified x-AABB clip; survivors are expanded into one sub-voxel queue entry per p of their interval
+	// ---- SAT, three stages over shared-memory queues so that every stage runs on full warps.
+	//   A  every (column, triangle) pair of the cell gets the certified plane interval along z (gpv::plane_row_interval, ~12
+	//      instructions); pairs that can still hit go to the (column, triangle) queue (ballot/popc per warp, one atomicAdd per warp).
+	//   B1 one queue entry per thread: the z-independent predicates of the SAT (gpv::sat_col_setup: x/y AABB, the three Z-axis
+	//      tests) and the certified z-AABB clip; survivors are expanded into one sub-voxel queue entry per r of their interval
 	//      (warp scan of the interval lengths, one atomicAdd per warp).
-	//   B2 one sub-voxel per thread: the row state is re-created (gpv::sat_row_values, no predicates) and the remaining
-	//      predicates are evaluated (gpv::sat_row_test); hits are OR-ed into the row's bit mask in shared memory.
+	//   B2 one sub-voxel per thread: the column state is re-created (gpv::sat_col_values, no predicates) and the remaining
+	//      predicates are evaluated (gpv::sat_col_test); hits are OR-ed into the column's bit mask in shared memory.
 	// Triangles are taken kL2Batch at a time and queue entries kL2Threads at a time, so neither queue can overflow; the queue
 	// fills are ping-pong counters, reset one round ahead, which keeps it to two barriers per round.
 	{
-		const float inv2h = 1.f / (2.f * g.h2x);
+		const float inv2h = 1.f / (2.f * g.h2z);
 		const int maxCnt = sInfo[2 * G]; // CTA-wide longest cell list (every thread must take part in the barriers below)
 		int round1 = 0, round2 = 0;
 		for (int itemBase = 0; itemBase < nItems; itemBase += kL2Threads) { // one pass unless n2 = 32
 			const int item = itemBase + tid;
 			int triOff = 0, triCnt = 0;
-			float c0 = 0.f, cy2 = 0.f, cz2 = 0.f, slack = 0.f;
+			float cx2 = 0.f, cy2 = 0.f, cz0 = 0.f, slack = 0.f;
 			if (item < nItems) {
-				const int gi = fast_div(item, invRows), row = item - gi * rows, r = fast_div(row, invN2), q = row - r * n2;
+				const int gi = fast_div(item, invRows), pq = item - gi * rows, q = fast_div(pq, invN2), p = pq - q * n2;
 				const float* c = sC + gi * 3 * n2;
-				c0 = c[0]; cy2 = c[n2 + q]; cz2 = c[2 * n2 + r];
-				slack = 9.5367431640625e-07f * (fabsf(c0) + 2.f * g.gsx); // 16u(|mid_x| + gs_x) >= |(c_p - c_0) - 2*h2x*p|
-				triOff = sInfo[gi * 2]; triCnt = sInfo[gi * 2 + 1];        // 0 for cells past the end
+				cx2 = c[p]; cy2 = c[n2 + q]; cz0 = c[2 * n2];
+				slack = 9.5367431640625e-07f * (fabsf(cz0) + 2.f * g.gsz); // 16u(|mid_z| + gs_z) >= |(c_r - c_0) - 2*h2z*r|
+				triOff = sInfo[gi * 2]; triCnt = sInfo[gi * 2 + 1];         // 0 for cells past the end
 			}
 			for (int kb = 0; kb < maxCnt; kb += kL2Batch) {
 				int* q1n = sQn + (round1 & 1);
@@ -932,19 +931,19 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 				// stage A
 				for (int k = kb; k < min(kb + kL2Batch, maxCnt); k++) {
 					bool alive = false;
-					int plo = 0, phi = -1, t = 0;
+					int rlo = 0, rhi = -1, t = 0;
 					if (k < triCnt) {
 						t = io.cellTris[triOff + k];
 						const float4 A = __ldg(io.tri48 + (size_t)t * 3), pl = __ldg(io.plane16 + t);
 						PlaneRec P; P.sx = pl.x; P.ny = pl.y; P.nz = pl.z; P.R = pl.w;
-						alive = plane_row_interval(P, A.x - c0, A.y - cy2, A.z - cz2, inv2h, slack, n2, plo, phi);
+						alive = plane_row_interval(P, A.z - cz0, A.x - cx2, A.y - cy2, inv2h, slack, n2, rlo, rhi);
 					}
 					const unsigned m = __ballot_sync(0xffffffffu, alive);
 					if (m) {
 						int base = 0;
 						if (lane == 0) base = atomicAdd(q1n, __popc(m));
 						base = __shfl_sync(0xffffffffu, base, 0);
-						if (alive) sQ1[base + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)item | ((unsigned)plo << 16) | ((unsigned)phi << 24), (unsigned)t);
+						if (alive) sQ1[base + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)item | ((unsigned)rlo << 16) | ((unsigned)rhi << 24), (unsigned)t);
 					}
 				}
 				__syncthreads();
@@ -953,20 +952,20 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 				for (int s0 = 0; s0 < n1; s0 += kL2Threads) {
 					int* q2n = sQn + 2 + (round2 & 1);
 					// stage B1
-					int len = 0, plo = 0;
+					int len = 0, rlo = 0;
 					if (s0 + tid < n1) {
 						const uint2 e = sQ1[s0 + tid];
 						const int it = (int)(e.x & 0xffffu);
-						const int gi = fast_div(it, invRows), row = it - gi * rows, r = fast_div(row, invN2), q = row - r * n2;
+						const int gi = fast_div(it, invRows), pq = it - gi * rows, q = fast_div(pq, invN2), p = pq - q * n2;
 						const float* c = sC + gi * 3 * n2;
 						const float4 A = __ldg(io.tri48 + (size_t)e.y * 3), B = __ldg(io.tri48 + (size_t)e.y * 3 + 1), C = __ldg(io.tri48 + (size_t)e.y * 3 + 2);
-						SatRow s;
-						if (sat_row_setup(s, c[n2 + q], c[2 * n2 + r], g.h2y, g.h2z, A.y, A.z, B.y, B.z, C.y, C.z)) {
-							int phi = (int)(e.x >> 24);
-							plo = (int)((e.x >> 16) & 0xffu);
-							const float sl = 9.5367431640625e-07f * (fabsf(c[0]) + 2.f * g.gsx);
-							x_row_clip(fminf(A.x, fminf(B.x, C.x)), fmaxf(A.x, fmaxf(B.x, C.x)), c[0], g.h2x, g.gsx, inv2h, sl, n2, plo, phi);
-							len = max(0, phi - plo + 1);
+						SatCol s;
+						if (sat_col_setup(s, c[p], c[n2 + q], g.h2x, g.h2y, A.x, A.y, B.x, B.y, C.x, C.y)) {
+							int rhi = (int)(e.x >> 24);
+							rlo = (int)((e.x >> 16) & 0xffu);
+							const float sl = 9.5367431640625e-07f * (fabsf(c[2 * n2]) + 2.f * g.gsz);
+							axis_clip(fminf(A.z, fminf(B.z, C.z)), fmaxf(A.z, fmaxf(B.z, C.z)), c[2 * n2], g.h2z, g.gsz, inv2h, sl, n2, rlo, rhi);
+							len = max(0, rhi - rlo + 1);
 						}
 					}
 					int incl = len;
@@ -980,7 +979,7 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 						int base = 0;
 						if (lane == 31) base = atomicAdd(q2n, warpTot);
 						base = __shfl_sync(0xffffffffu, base, 31) + incl - len;
-						for (int j = 0; j < len; j++) sQ2[base + j] = (unsigned short)((tid << 5) | (plo + j));
+						for (int j = 0; j < len; j++) sQ2[base + j] = (unsigned short)((tid << 5) | (rlo + j));
 					}
 					__syncthreads();
 					const int n2q = *q2n;
@@ -990,13 +989,13 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 					for (int v = tid; v < n2q; v += kL2Threads) {
 						const unsigned x = sQ2[v];
 						const uint2 e = sQ1[s0 + (int)(x >> 5)];
-						const int p = (int)(x & 31u), it = (int)(e.x & 0xffffu);
-						const int gi = fast_div(it, invRows), row = it - gi * rows, r = fast_div(row, invN2), q = row - r * n2;
+						const int r = (int)(x & 31u), it = (int)(e.x & 0xffffu);
+						const int gi = fast_div(it, invRows), pq = it - gi * rows, q = fast_div(pq, invN2), p = pq - q * n2;
 						const float* c = sC + gi * 3 * n2;
 						const float4 A = __ldg(io.tri48 + (size_t)e.y * 3), B = __ldg(io.tri48 + (size_t)e.y * 3 + 1), C = __ldg(io.tri48 + (size_t)e.y * 3 + 2);
-						SatRow s;
-						sat_row_values(s, c[n2 + q], c[2 * n2 + r], g.h2y, g.h2z, A.y, A.z, B.y, B.z, C.y, C.z);
-						if (sat_row_test(s, c[p], g.h2x, g.h2y, g.h2z, A.x, B.x, C.x)) atomicOr(sSat + it, 1u << p);
+						SatCol s;
+						sat_col_values(s, c[p], c[n2 + q], g.h2x, g.h2y, A.x, A.y, B.x, B.y, C.x, C.y);
+						if (sat_col_test(s, c[2 * n2 + r], g.h2x, g.h2y, g.h2z, A.z, B.z, C.z)) atomicOr(sSat + it, 1u << r);
 					}
 					__syncthreads();
 				}
@@ -1005,30 +1004,24 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	}
 	__syncthreads();
 
-	// ---- phase 2b: the row's file bytes
+	// ---- the column's file bytes: SAT hit 254, else inside 127, else 0 (2 overwrites 1: src/Object.cpp:2603-2606)
 	unsigned nIn = 0, nBd = 0;
 	for (int item = tid; item < nItems; item += kL2Threads) {
-		const int gi = fast_div(item, invRows), row = item - gi * rows, r = fast_div(row, invN2), q = row - r * n2;
+		const int gi = fast_div(item, invRows), pq = item - gi * rows;
 		const long long b = b0 + gi;
 		if (b >= io.nBoundary) continue;
 		const unsigned sat = sSat[item];
-		unsigned par = 0;
-		const unsigned* pr = sPar + gi * K.parStride + q * (n2 + 1); // consecutive lanes = consecutive q: stride n2+1 words, no bank conflicts
-		for (int p = 0; p < n2; p++) par |= ((pr[p] >> r) & 1u) << p;
-		par &= ~sat;
+		const unsigned par = io.l2Par[(size_t)b * rows + pq] & ~sat;
 		nIn += __popc(par); nBd += __popc(sat);
-		unsigned char* out = io.l2State + ((size_t)b * rows + row) * n2;
-		// four sub-voxels per 32-bit word: (nibble * 0x204081) & 0x01010101 spreads bit k of the nibble to byte k
-		auto word = [&](int k) { return (((par >> (4 * k)) & 15u) * 0x204081u & 0x01010101u) * 127u + (((sat >> (4 * k)) & 15u) * 0x204081u & 0x01010101u) * 254u; };
-		if (n2 == 16) *reinterpret_cast<uint4*>(out) = make_uint4(word(0), word(1), word(2), word(3));
-		else if (n2 == 8) *reinterpret_cast<uint2*>(out) = make_uint2(word(0), word(1));
-		else if (n2 == 4) *reinterpret_cast<unsigned*>(out) = word(0);
-		else if (n2 == 32) {
-			reinterpret_cast<uint4*>(out)[0] = make_uint4(word(0), word(1), word(2), word(3));
-			reinterpret_cast<uint4*>(out)[1] = make_uint4(word(4), word(5), word(6), word(7));
-		} else {
-			for (int p = 0; p < n2; p++) out[p] = ((sat >> p) & 1) ? 254 : (((par >> p) & 1) ? 127 : 0);
+		unsigned char* out = io.l2State + ((size_t)b * rows * n2 + pq);
+		int r = 0;
+		for (; r + 4 <= n2; r += 4) {
+			// four sub-voxels at once: (nibble * 0x204081) & 0x01010101 spreads bit k of the nibble to byte k
+			const unsigned w = (((par >> r) & 15u) * 0x204081u & 0x01010101u) * 127u + (((sat >> r) & 15u) * 0x204081u & 0x01010101u) * 254u;
+			out[(size_t)r * rows] = (unsigned char)w; out[(size_t)(r + 1) * rows] = (unsigned char)(w >> 8);
+			out[(size_t)(r + 2) * rows] = (unsigned char)(w >> 16); out[(size_t)(r + 3) * rows] = (unsigned char)(w >> 24);
 		}
+		for (; r < n2; r++) out[(size_t)r * rows] = ((sat >> r) & 1) ? 254 : (((par >> r) & 1) ? 127 : 0);
 	}
 	nIn = __reduce_add_sync(0xffffffffu, nIn); nBd = __reduce_add_sync(0xffffffffu, nBd);
 	if (lane == 0 && (nIn | nBd)) { atomicAdd(&io.totals->l2Inside, (unsigned long long)nIn); atomicAdd(&io.totals->l2Boundary, (unsigned long long)nBd); }

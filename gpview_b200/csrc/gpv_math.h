@@ -82,95 +82,91 @@ GPV_HD bool tri_box_overlap(float cx, float cy, float cz, float hx, float hy, fl
 	return true;
 }
 
-// ---- Level-2 SAT, hoisted along x.  A row of sub-voxels shares (cy,cz); everything that touches only y/z components is
-// computed once per (row, triangle): the translated y/z coordinates, the y/z edge components, the three X-axis tests,
-// the y/z AABB tests and the x component of the normal.  Exact: those sub-expressions do not involve cx at all.
-struct SatRow {
-	float v0y, v0z, v1y, v1z, v2y, v2z;
-	float e0y, e0z, e1y, e1z, e2y, e2z;
-	float nx;                 // e0y*e1z - e0z*e1y
-	float py0, py1, pz0, pz1; // plane-box candidates: (-hy - v0y, hy - v0y), (-hz - v0z, hz - v0z)
+// ---- Level-2 SAT, hoisted along z.  A column of sub-voxels shares (cx,cy); everything that touches only x/y components is
+// computed once per (column, triangle): the translated x/y coordinates, the x/y edge components, the three Z-axis tests
+// (Z12 of edge 0, Z0 of edge 1, Z12 of edge 2, cu:266/273/280), the x/y AABB tests and the z component of the normal.
+// Exact: those sub-expressions do not involve cz at all.  (z is the axis of the parity rays too, so the SAT bits and the
+// parity bits of a sub-voxel column end up in the same word layout.)
+struct SatCol {
+	float v0x, v0y, v1x, v1y, v2x, v2y;
+	float e0x, e0y, e1x, e1y, e2x, e2y;
+	float nz;                 // e0x*e1y - e0y*e1x
+	float px0, px1, py0, py1; // plane-box candidates: (-hx - v0x, hx - v0x), (-hy - v0y, hy - v0y)
 };
 
-// returns false when a p-independent predicate already separates the triangle from every box of the row
-GPV_HD bool sat_row_setup(SatRow& s, float cy, float cz, float hy, float hz,
-                          float t0y, float t0z, float t1y, float t1z, float t2y, float t2z)
+// the column quantities without any predicate
+GPV_HD void sat_col_values(SatCol& s, float cx, float cy, float hx, float hy,
+                           float t0x, float t0y, float t1x, float t1y, float t2x, float t2y)
 {
-	s.v0y = t0y - cy; s.v0z = t0z - cz; s.v1y = t1y - cy; s.v1z = t1z - cz; s.v2y = t2y - cy; s.v2z = t2z - cz;
+	s.v0x = t0x - cx; s.v0y = t0y - cy; s.v1x = t1x - cx; s.v1y = t1y - cy; s.v2x = t2x - cx; s.v2y = t2y - cy;
+	s.e0x = s.v1x - s.v0x; s.e0y = s.v1y - s.v0y;
+	s.e1x = s.v2x - s.v1x; s.e1y = s.v2y - s.v1y;
+	s.e2x = s.v0x - s.v2x; s.e2y = s.v0y - s.v2y;
+	s.nz = s.e0x * s.e1y - s.e0y * s.e1x;
+	s.px0 = -hx - s.v0x; s.px1 = hx - s.v0x; s.py0 = -hy - s.v0y; s.py1 = hy - s.v0y;
+}
+
+// returns false when a z-independent predicate already separates the triangle from every box of the column
+GPV_HD bool sat_col_setup(SatCol& s, float cx, float cy, float hx, float hy,
+                          float t0x, float t0y, float t1x, float t1y, float t2x, float t2y)
+{
+	sat_col_values(s, cx, cy, hx, hy, t0x, t0y, t1x, t1y, t2x, t2y);
 	{
-		float mn = fminf(s.v0y, fminf(s.v1y, s.v2y)), mx = fmaxf(s.v0y, fmaxf(s.v1y, s.v2y));
+		float mn = fminf(s.v0x, fminf(s.v1x, s.v2x)), mx = fmaxf(s.v0x, fmaxf(s.v1x, s.v2x));
+		if (mn > hx || mx < -hx) return false;
+		mn = fminf(s.v0y, fminf(s.v1y, s.v2y)); mx = fmaxf(s.v0y, fmaxf(s.v1y, s.v2y));
 		if (mn > hy || mx < -hy) return false;
-		mn = fminf(s.v0z, fminf(s.v1z, s.v2z)); mx = fmaxf(s.v0z, fmaxf(s.v1z, s.v2z));
-		if (mn > hz || mx < -hz) return false;
 	}
-	s.e0y = s.v1y - s.v0y; s.e0z = s.v1z - s.v0z;
-	s.e1y = s.v2y - s.v1y; s.e1z = s.v2z - s.v1z;
-	s.e2y = s.v0y - s.v2y; s.e2z = s.v0z - s.v2z;
-	// X01(e0), X01(e1), X2(e2): a = e.z, b = e.y, rad = |e.z|*hy + |e.y|*hz
-	if (axis_separates(s.e0z * s.v0y - s.e0y * s.v0z, s.e0z * s.v2y - s.e0y * s.v2z, fabsf(s.e0z) * hy + fabsf(s.e0y) * hz)) return false;
-	if (axis_separates(s.e1z * s.v0y - s.e1y * s.v0z, s.e1z * s.v2y - s.e1y * s.v2z, fabsf(s.e1z) * hy + fabsf(s.e1y) * hz)) return false;
-	if (axis_separates(s.e2z * s.v0y - s.e2y * s.v0z, s.e2z * s.v1y - s.e2y * s.v1z, fabsf(s.e2z) * hy + fabsf(s.e2y) * hz)) return false;
-	s.nx = s.e0y * s.e1z - s.e0z * s.e1y;
-	s.py0 = -hy - s.v0y; s.py1 = hy - s.v0y; s.pz0 = -hz - s.v0z; s.pz1 = hz - s.v0z;
+	// Z12(e0), Z0(e1), Z12(e2): a = e.y, b = e.x, rad = |e.y|*hx + |e.x|*hy
+	if (axis_separates(s.e0y * s.v1x - s.e0x * s.v1y, s.e0y * s.v2x - s.e0x * s.v2y, fabsf(s.e0y) * hx + fabsf(s.e0x) * hy)) return false;
+	if (axis_separates(s.e1y * s.v0x - s.e1x * s.v0y, s.e1y * s.v1x - s.e1x * s.v1y, fabsf(s.e1y) * hx + fabsf(s.e1x) * hy)) return false;
+	if (axis_separates(s.e2y * s.v1x - s.e2x * s.v1y, s.e2y * s.v2x - s.e2x * s.v2y, fabsf(s.e2y) * hx + fabsf(s.e2x) * hy)) return false;
 	return true;
 }
 
-// the row quantities of sat_row_setup WITHOUT its predicates, for a (row, triangle) pair that is already known to pass them
-// (the voxel-level queue of k_l2 re-creates the row state per sub-voxel instead of carrying 17 floats through shared memory)
-GPV_HD void sat_row_values(SatRow& s, float cy, float cz, float hy, float hz,
-                           float t0y, float t0z, float t1y, float t1z, float t2y, float t2z)
+// Certified clip of an index interval [lo,hi] along one axis to the sub-voxels whose AABB predicate on that axis (cu:284-298)
+// can pass: fl(tmin - c_k) <= h and fl(tmax - c_k) >= -h need c_k within [tmin - h, tmax + h] up to rounding.  c0 = centre of
+// the first sub-voxel of the line, |c_k - c0 - 2*h*k| <= slack (see plane_row_interval); the 128u margin covers that, the
+// rounding of the predicate's own subtraction and of the bounds below.  Never drops a sub-voxel that passes; the exact test still runs.
+GPV_HD void axis_clip(float tmin, float tmax, float c0, float h, float gs, float inv2h, float slack, int n2, int& lo, int& hi)
 {
-	s.v0y = t0y - cy; s.v0z = t0z - cz; s.v1y = t1y - cy; s.v1z = t1z - cz; s.v2y = t2y - cy; s.v2z = t2z - cz;
-	s.e0y = s.v1y - s.v0y; s.e0z = s.v1z - s.v0z;
-	s.e1y = s.v2y - s.v1y; s.e1z = s.v2z - s.v1z;
-	s.e2y = s.v0y - s.v2y; s.e2z = s.v0z - s.v2z;
-	s.nx = s.e0y * s.e1z - s.e0z * s.e1y;
-	s.py0 = -hy - s.v0y; s.py1 = hy - s.v0y; s.pz0 = -hz - s.v0z; s.pz1 = hz - s.v0z;
+	const float s2 = slack + 7.62939453125e-06f * (fabsf(tmin) + fabsf(tmax) + fabsf(c0) + gs); // 2^-17 = 128u
+	const float a = ceilf((tmin - c0 - h - s2) * inv2h), b = floorf((tmax - c0 + h + s2) * inv2h);
+	if (a == a && a > (float)lo) lo = a > (float)n2 ? n2 : (int)a;
+	if (b == b && b < (float)hi) hi = b < -1.f ? -1 : (int)b;
 }
 
-// Certified clip of a row's index interval [plo,phi] to the sub-voxels whose x-AABB predicate (cu:284-286) can pass:
-// fl(tmin - c_p) <= hx and fl(tmax - c_p) >= -hx need c_p within [tmin - hx, tmax + hx] up to rounding.  c0 = centre of the
-// row's first sub-voxel, |c_p - c0 - 2*hx*p| <= slack (see plane_row_interval); the 128u margin covers that, the rounding of
-// the predicate's own subtraction and of the bounds below.  Never drops a sub-voxel that passes; the exact test still runs.
-GPV_HD void x_row_clip(float tmin, float tmax, float c0, float hx, float gsx, float inv2h, float slack, int n2, int& plo, int& phi)
+// the remaining predicates for one box of the column (box centre z = cz)
+GPV_HD bool sat_col_test(const SatCol& s, float cz, float hx, float hy, float hz, float t0z, float t1z, float t2z)
 {
-	const float s2 = slack + 7.62939453125e-06f * (fabsf(tmin) + fabsf(tmax) + fabsf(c0) + gsx); // 2^-17 = 128u
-	const float lo = ceilf((tmin - c0 - hx - s2) * inv2h), hi = floorf((tmax - c0 + hx + s2) * inv2h);
-	if (lo == lo && lo > (float)plo) plo = lo > (float)n2 ? n2 : (int)lo;
-	if (hi == hi && hi < (float)phi) phi = hi < -1.f ? -1 : (int)hi;
-}
-
-// the remaining predicates for one box of the row (box centre x = cx)
-GPV_HD bool sat_row_test(const SatRow& s, float cx, float hx, float hy, float hz, float t0x, float t1x, float t2x)
-{
-	float v0x = t0x - cx, v1x = t1x - cx, v2x = t2x - cx;
+	float v0z = t0z - cz, v1z = t1z - cz, v2z = t2z - cz;
 	{
-		float mn = fminf(v0x, fminf(v1x, v2x)), mx = fmaxf(v0x, fmaxf(v1x, v2x));
-		if (mn > hx || mx < -hx) return false;
+		float mn = fminf(v0z, fminf(v1z, v2z)), mx = fmaxf(v0z, fmaxf(v1z, v2z));
+		if (mn > hz || mx < -hz) return false;
 	}
-	float e0x = v1x - v0x, e1x = v2x - v1x;
+	float e0z = v1z - v0z, e1z = v2z - v1z;
 	{
-		float ny = s.e0z * e1x - e0x * s.e1z, nz = e0x * s.e1y - s.e0y * e1x;
-		float mnx = (s.nx > 0.0f) ? (-hx - v0x) : (hx - v0x), mxx = (s.nx > 0.0f) ? (hx - v0x) : (-hx - v0x);
+		float nx = s.e0y * e1z - e0z * s.e1y, ny = e0z * s.e1x - s.e0x * e1z;
+		float mnx = (nx > 0.0f) ? s.px0 : s.px1, mxx = (nx > 0.0f) ? s.px1 : s.px0;
 		float mny = (ny > 0.0f) ? s.py0 : s.py1, mxy = (ny > 0.0f) ? s.py1 : s.py0;
-		float mnz = (nz > 0.0f) ? s.pz0 : s.pz1, mxz = (nz > 0.0f) ? s.pz1 : s.pz0;
-		if (s.nx * mnx + ny * mny + nz * mnz > 0.0f) return false;
-		if (!(s.nx * mxx + ny * mxy + nz * mxz >= 0.0f)) return false;
+		float mnz = (s.nz > 0.0f) ? (-hz - v0z) : (hz - v0z), mxz = (s.nz > 0.0f) ? (hz - v0z) : (-hz - v0z);
+		if (nx * mnx + ny * mny + s.nz * mnz > 0.0f) return false;
+		if (!(nx * mxx + ny * mxy + s.nz * mxz >= 0.0f)) return false;
 	}
-	float e2x = v0x - v2x;
-	float fex;
-	// edge 0: Y02, Z12
-	fex = fabsf(e0x);
-	if (axis_separates(-s.e0z * v0x + e0x * s.v0z, -s.e0z * v2x + e0x * s.v2z, fabsf(s.e0z) * hx + fex * hz)) return false;
-	if (axis_separates(s.e0y * v1x - e0x * s.v1y, s.e0y * v2x - e0x * s.v2y, fabsf(s.e0y) * hx + fex * hy)) return false;
-	// edge 1: Y02, Z0
-	fex = fabsf(e1x);
-	if (axis_separates(-s.e1z * v0x + e1x * s.v0z, -s.e1z * v2x + e1x * s.v2z, fabsf(s.e1z) * hx + fex * hz)) return false;
-	if (axis_separates(s.e1y * v0x - e1x * s.v0y, s.e1y * v1x - e1x * s.v1y, fabsf(s.e1y) * hx + fex * hy)) return false;
-	// edge 2: Y1, Z12
-	fex = fabsf(e2x);
-	if (axis_separates(-s.e2z * v0x + e2x * s.v0z, -s.e2z * v1x + e2x * s.v1z, fabsf(s.e2z) * hx + fex * hz)) return false;
-	if (axis_separates(s.e2y * v1x - e2x * s.v1y, s.e2y * v2x - e2x * s.v2y, fabsf(s.e2y) * hx + fex * hy)) return false;
+	float e2z = v0z - v2z;
+	float fez;
+	// edge 0: X01, Y02
+	fez = fabsf(e0z);
+	if (axis_separates(e0z * s.v0y - s.e0y * v0z, e0z * s.v2y - s.e0y * v2z, fez * hy + fabsf(s.e0y) * hz)) return false;
+	if (axis_separates(-e0z * s.v0x + s.e0x * v0z, -e0z * s.v2x + s.e0x * v2z, fez * hx + fabsf(s.e0x) * hz)) return false;
+	// edge 1: X01, Y02
+	fez = fabsf(e1z);
+	if (axis_separates(e1z * s.v0y - s.e1y * v0z, e1z * s.v2y - s.e1y * v2z, fez * hy + fabsf(s.e1y) * hz)) return false;
+	if (axis_separates(-e1z * s.v0x + s.e1x * v0z, -e1z * s.v2x + s.e1x * v2z, fez * hx + fabsf(s.e1x) * hz)) return false;
+	// edge 2: X2, Y1
+	fez = fabsf(e2z);
+	if (axis_separates(e2z * s.v0y - s.e2y * v0z, e2z * s.v1y - s.e2y * v1z, fez * hy + fabsf(s.e2y) * hz)) return false;
+	if (axis_separates(-e2z * s.v0x + s.e2x * v0z, -e2z * s.v1x + s.e2x * v1z, fez * hx + fabsf(s.e2x) * hz)) return false;
 	return true;
 }
 
@@ -180,6 +176,8 @@ GPV_HD bool sat_row_test(const SatRow& s, float cx, float hx, float hy, float hz
 // from -r -/+ N.(t0-c) by at most 488 u M^3 (u = 2^-24, M = bound on every translated coordinate of the triangle seen from
 // any sub-voxel centre of a Level-1 cell the triangle overlaps); our own f32 evaluation of the left side adds < 500 u M^3.
 // With E = 2048 u M^3 = 2^-13 M^3:   |N.(t0 - c)| > r + E   ==>   the reference's plane predicate FAILS.
+// (The product calls these two functions with the coordinates permuted cyclically, (x,y,z) <- (z,x,y): a cyclic relabelling maps
+// e0 x e1 onto itself, so "x" below is the z axis of the grid and the interval runs along a sub-voxel COLUMN.)
 // Along a row of sub-voxels (fixed cy, cz) N.(t0 - c_p) = D0 - Nx * s_p with s_p = c_p - c_0, so the sub-voxels that can
 // pass form an index interval.  The record is normalised by Nx so that the interval needs no division per row:
 //   x = 1: (1, Ny/Nx, Nz/Nx, (r+E)/|Nx|)      x = 0: Nx too small to normalise, (0, Ny, Nz, r+E): whole row or nothing

@@ -14,10 +14,16 @@ void probe_sat_full(int64_t n, const float* c, const float* h, const float* t, u
 }
 void probe_sat_row(int64_t n, const float* c, const float* h, const float* t, uint8_t* out)
 {
+	// the hoisted Level-2 form (z-independent part per column, then the per-sub-voxel part), both ways k_l2 uses it:
+	// setup + test, and values (no predicates) + test for pairs that passed the setup
 	for (int64_t i = 0; i < n; i++) {
 		const float *C = c + i * 3, *H = h + i * 3, *T = t + i * 9;
-		SatRow s;
-		out[i] = sat_row_setup(s, C[1], C[2], H[1], H[2], T[1], T[2], T[4], T[5], T[7], T[8]) && sat_row_test(s, C[0], H[0], H[1], H[2], T[0], T[3], T[6]);
+		SatCol s, v;
+		const bool pre = sat_col_setup(s, C[0], C[1], H[0], H[1], T[0], T[1], T[3], T[4], T[6], T[7]);
+		sat_col_values(v, C[0], C[1], H[0], H[1], T[0], T[1], T[3], T[4], T[6], T[7]);
+		const bool a = pre && sat_col_test(s, C[2], H[0], H[1], H[2], T[2], T[5], T[8]);
+		const bool b = pre && sat_col_test(v, C[2], H[0], H[1], H[2], T[2], T[5], T[8]);
+		out[i] = a == b ? a : 2;
 	}
 }
 void probe_ray(int64_t n, const float* o, const float* t, uint8_t* out)
@@ -71,6 +77,9 @@ static bool plane_pred_ref(float cx, float cy, float cz, float hx, float hy, flo
 }
 extern "C" void probe_plane_cull(int64_t n, const float* mid3, const float* gs3, int n2, const float* tri9, int64_t* out4)
 {
+	// k_l2's culling of one sub-voxel column (p,q): plane interval along z (plane record on cyclically permuted axes), then the
+	// certified z-AABB clip.  violations = sub-voxels outside the plane interval whose plane predicate passes, or outside the
+	// clipped interval whose full SAT passes.
 	int64_t violations = 0, kept = 0, planePass = 0, satPass = 0;
 	for (int64_t i = 0; i < n; i++) {
 		const float *mid = mid3 + i * 3, *gs = gs3 + i * 3, *T = tri9 + i * 9;
@@ -79,19 +88,24 @@ extern "C" void probe_plane_cull(int64_t n, const float* mid3, const float* gs3,
 			h1[a] = gs[a] / 2.0; float g2 = gs[a] / (n2 * 1.0); h2[a] = g2 / 2.0;
 			for (int p = 0; p < n2; p++) c[a][p] = (float)(2 * p + 1) * h2[a] + mid[a] - h1[a];
 		}
-		PlaneRec pl = plane_rec_setup(T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8], gs[0], gs[1], gs[2], h2[0], h2[1], h2[2]);
-		float inv2h = 1.f / (2.f * h2[0]);
-		float slack = 9.5367431640625e-07f * (fabsf(mid[0]) + gs[0]); // 16u(|mid|+gs)
-		for (int r = 0; r < n2; r++) for (int q = 0; q < n2; q++) {
-			int plo, phi;
-			bool any = plane_row_interval(pl, T[0] - c[0][0], T[1] - c[1][q], T[2] - c[2][r], inv2h, slack, n2, plo, phi);
-			if (!any) { plo = 0; phi = -1; }
-			for (int p = 0; p < n2; p++) {
+		PlaneRec pl = plane_rec_setup(T[2], T[0], T[1], T[5], T[3], T[4], T[8], T[6], T[7], gs[2], gs[0], gs[1], h2[2], h2[0], h2[1]);
+		float inv2h = 1.f / (2.f * h2[2]);
+		float slack = 9.5367431640625e-07f * (fabsf(c[2][0]) + 2.f * gs[2]); // as in k_l2
+		const float zmin = fminf(T[2], fminf(T[5], T[8])), zmax = fmaxf(T[2], fmaxf(T[5], T[8]));
+		for (int q = 0; q < n2; q++) for (int p = 0; p < n2; p++) {
+			int rlo, rhi;
+			bool any = plane_row_interval(pl, T[2] - c[2][0], T[0] - c[0][p], T[1] - c[1][q], inv2h, slack, n2, rlo, rhi);
+			if (!any) { rlo = 0; rhi = -1; }
+			int clo = rlo, chi = rhi;
+			axis_clip(zmin, zmax, c[2][0], h2[2], gs[2], inv2h, slack, n2, clo, chi);
+			for (int r = 0; r < n2; r++) {
 				bool pp = plane_pred_ref(c[0][p], c[1][q], c[2][r], h2[0], h2[1], h2[2], T);
-				bool in = p >= plo && p <= phi;
-				kept += in; planePass += pp;
+				bool in = r >= rlo && r <= rhi, inc = r >= clo && r <= chi;
+				kept += inc; planePass += pp;
 				if (pp && !in) violations++;
-				if (pp && tri_box_overlap(c[0][p], c[1][q], c[2][r], h2[0], h2[1], h2[2], T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8])) satPass++;
+				bool sat = tri_box_overlap(c[0][p], c[1][q], c[2][r], h2[0], h2[1], h2[2], T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8]);
+				if (sat && !inc) violations++;
+				if (sat) satPass++;
 			}
 		}
 	}
