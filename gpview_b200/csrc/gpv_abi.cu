@@ -67,7 +67,7 @@ struct gpv_ctx {
 	cudaStream_t copyStream = nullptr;  // D2H of finished streams overlaps the rest of the pipeline (gpv_voxelize_host)
 	cudaStream_t ownStream = nullptr;   // gpv_stream(): a non-blocking stream for callers that run several contexts side by side
 	cudaEvent_t evChunk[17] = {};
-	bool sortAttrSet = false, l2AttrSet = false;
+	bool sortAttrSet = false;
 };
 
 using namespace gpv;
@@ -341,10 +341,8 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		const L2K K = l2_constants(g.n2);
 		const int G = K.G;
 		const size_t smem = (size_t)K.total;
-		if (smem > 48 * 1024 && !c->l2AttrSet) {
-			GPV_CUDA(cudaFuncSetAttribute(k_l2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-			c->l2AttrSet = true;
-		}
+		void (*l2fn)(GridP, L2IO, L2K) = g.n2 == 16 ? k_l2<16> : g.n2 == 8 ? k_l2<8> : g.n2 == 4 ? k_l2<4> : g.n2 == 2 ? k_l2<2> : k_l2<0>;
+		if (smem > 48 * 1024) return fail("k_l2: shared-memory layout exceeds 48 KB"); // cannot happen for n2 <= 32 (41 KB)
 		// K4a: boundary cells grouped by Level-1 column, then the parity bits of every sub-voxel column, one walk of the column list per column
 		k_col_cells<<<(unsigned)((nB + 255) / 256), 256, 0, st>>>(lio.boundaryIndex, (int)nB, (int)ncol, g.nx, cx, cy, cz, lio.colCellOff, c->colCellCnt.as<int>(), c->colCellList.as<int2>(),
 		                                                        c->cellMid.as<float4>());
@@ -359,7 +357,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			const long long bb = k * per, be = std::min(nB, bb + per);
 			if (bb >= be) break;
 			lio.bBegin = (int)bb; lio.nBoundary = (int)be;
-			k_l2<<<(unsigned)((be - bb + G - 1) / G), kL2Threads, smem, st>>>(g, lio, K);
+			l2fn<<<(unsigned)((be - bb + G - 1) / G), kL2Threads, smem, st>>>(g, lio, K);
 			launches++;
 			if (sink && sink->level2_inout) {
 				GPV_CUDA(cudaEventRecord(c->evChunk[k], st));

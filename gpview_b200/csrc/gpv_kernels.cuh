@@ -696,7 +696,7 @@ constexpr int kRayCells = 4;  // boundary cells of the column refined per regist
 constexpr int kL2Stage = 256; // ray records staged per chunk (12 KB)
 
 struct RaySub { // one sub-voxel column: origin, list, cells, output slot, height range of the grid column
-	float ox, oy, zMin, zMax; unsigned off; int cnt; unsigned cb, ce; int item;
+	float ox, oy, zMin, zMax, inv101, inv099; unsigned off; int cnt; unsigned cb, ce; int item;
 };
 
 __device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const RaySub& u, const uint4 pk0, const uint4 pk1, const unsigned n)
@@ -719,7 +719,7 @@ __device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const
 			load_ray(s, io.ray48, io.colTris[u.off + ((v >> ((j & 1) * 16)) & 0xffffu)]);
 			RayCol rc;
 			if (!ray_column(s, u.ox, u.oy, rc)) continue; // cannot happen (listed because it passed); keeps rc defined
-			const RayColZ k1 = ray_col_bound(s, rc, u.zMin, u.zMax, g.gsz);
+			const RayColZ k1 = ray_col_bound(s, rc, u.zMin, u.zMax, g.gsz, u.inv101, u.inv099);
 #pragma unroll
 			for (int c = 0; c < kRayCells; c++) if (bb[c] >= 0) par[c] ^= ray_cell_mask(s, rc, k1, midz[c], g.h1z, g.h2z, g.n2);
 		}
@@ -738,7 +738,7 @@ __device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const
 			RayCol rc;
 			if (!s.ok || !ray_column(s, u.ox, u.oy, rc)) continue;
 			if (!all && seen++ < (unsigned)kRaySlots) continue;
-			const RayColZ k1 = ray_col_bound(s, rc, u.zMin, u.zMax, g.gsz);
+			const RayColZ k1 = ray_col_bound(s, rc, u.zMin, u.zMax, g.gsz, u.inv101, u.inv099);
 			for (unsigned cc = u.cb; cc < u.ce; cc++) {
 				const int2 e = io.colCellList[cc];
 				io.l2Par[(size_t)e.x * rows + u.item] ^= ray_cell_mask(s, rc, k1, __int_as_float(e.y), g.h1z, g.h2z, g.n2);
@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(256, 3) k_l2_rays(GridP g, L2IO io)
 		if (u.cb == u.ce) return;
 		const int jy = col / g.nx, ix = col - jy * g.nx;
 		u.off = io.colOff[col]; u.cnt = io.colCount[col];
-		u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz;
+		u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz; u.inv101 = 1.f / (2.02f * g.h2z); u.inv099 = 1.f / (1.98f * g.h2z);
 		const float mx = io.cx[ix], my = io.cy[jy];
 		for (int item0 = 0; item0 < rows; item0 += 256) { // one round unless n2 = 32
 			u.item = item0 + tid;
@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(256, 3) k_l2_rays(GridP g, L2IO io)
 		const int q = fast_div(u.item, invN2), p = u.item - q * n2;
 		u.ox = l2_centre(p, g.h2x, io.cx[ix], g.h1x); u.oy = l2_centre(q, g.h2y, io.cy[jy], g.h1y);
 		u.off = io.colOff[col]; u.cnt = io.colCount[col];
-		u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz;
+		u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz; u.inv101 = 1.f / (2.02f * g.h2z); u.inv099 = 1.f / (1.98f * g.h2z);
 		uint4 pk0 = make_uint4(0u, 0u, 0u, 0u), pk1 = pk0;
 		unsigned n = 0;
 		for (int k = 0; k < u.cnt; k++) {
@@ -861,10 +861,12 @@ inline L2K l2_constants(int n2)
 // COLUMN (cell, p, q) -- the same unit k_l2_rays works on, so the SAT bits and the parity bits of a column share one word
 // layout (bit r = sub-voxel r) and no transposition is needed.  Everything of the SAT that does not involve z is hoisted
 // per (column, triangle) (gpv::SatCol).  A warp's byte stores cover 32 consecutive sub-voxels of Level2InOut.raw.
+// N2 > 0: n2 fixed at compile time (2, 4, 8, 16: index arithmetic by shifts, unrolled byte loop); N2 = 0: any n2 <= 32.
+template <int N2>
 __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2IO io, L2K K)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
-	const int n2 = K.n2, rows = K.rows, G = K.G, nItems = K.nItems;
+	const int n2 = N2 ? N2 : K.n2, rows = N2 ? N2 * N2 : K.rows, G = N2 ? (N2 * N2 >= kL2Threads ? 1 : kL2Threads / (N2 * N2)) : K.G, nItems = G * rows;
 	float* sC = reinterpret_cast<float*>(smemRaw);
 	unsigned* sSat = reinterpret_cast<unsigned*>(smemRaw + K.sat);
 	int* sInfo = reinterpret_cast<int*>(smemRaw + K.info);
@@ -873,13 +875,15 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	int* sQn = reinterpret_cast<int*>(smemRaw + K.qn);
 	const int tid = threadIdx.x, lane = tid & 31;
 	const long long b0 = io.bBegin + (long long)blockIdx.x * G;
-	const float invRows = K.invRows, invN2 = K.invN2;
+	auto div_rows = [&](int a) { return N2 ? a / (N2 ? N2 * N2 : 1) : fast_div(a, K.invRows); };
+	auto div_n2 = [&](int a) { return N2 ? a / (N2 ? N2 : 1) : fast_div(a, K.invN2); };
+	auto div_3n2 = [&](int a) { return N2 ? a / (N2 ? 3 * N2 : 1) : fast_div(a, K.inv3N2); };
 
 	if (tid == 0) sInfo[2 * G] = 0;
 	if (tid < 4) sQn[tid] = 0;
 	__syncthreads();
 	for (int k = tid; k < G * 3 * n2; k += kL2Threads) {
-		const int gi = fast_div(k, K.inv3N2), rem = k - gi * 3 * n2, ax = fast_div(rem, invN2), p = rem - ax * n2;
+		const int gi = div_3n2(k), rem = k - gi * 3 * n2, ax = div_n2(rem), p = rem - ax * n2;
 		const long long b = b0 + gi;
 		float val = 0.f;
 		if (b < io.nBoundary) {
@@ -919,7 +923,7 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 			int triOff = 0, triCnt = 0;
 			float cx2 = 0.f, cy2 = 0.f, cz0 = 0.f, slack = 0.f;
 			if (item < nItems) {
-				const int gi = fast_div(item, invRows), pq = item - gi * rows, q = fast_div(pq, invN2), p = pq - q * n2;
+				const int gi = div_rows(item), pq = item - gi * rows, q = div_n2(pq), p = pq - q * n2;
 				const float* c = sC + gi * 3 * n2;
 				cx2 = c[p]; cy2 = c[n2 + q]; cz0 = c[2 * n2];
 				slack = 9.5367431640625e-07f * (fabsf(cz0) + 2.f * g.gsz); // 16u(|mid_z| + gs_z) >= |(c_r - c_0) - 2*h2z*r|
@@ -956,7 +960,7 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 					if (s0 + tid < n1) {
 						const uint2 e = sQ1[s0 + tid];
 						const int it = (int)(e.x & 0xffffu);
-						const int gi = fast_div(it, invRows), pq = it - gi * rows, q = fast_div(pq, invN2), p = pq - q * n2;
+						const int gi = div_rows(it), pq = it - gi * rows, q = div_n2(pq), p = pq - q * n2;
 						const float* c = sC + gi * 3 * n2;
 						const float4 A = __ldg(io.tri48 + (size_t)e.y * 3), B = __ldg(io.tri48 + (size_t)e.y * 3 + 1), C = __ldg(io.tri48 + (size_t)e.y * 3 + 2);
 						SatCol s;
@@ -990,7 +994,7 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 						const unsigned x = sQ2[v];
 						const uint2 e = sQ1[s0 + (int)(x >> 5)];
 						const int r = (int)(x & 31u), it = (int)(e.x & 0xffffu);
-						const int gi = fast_div(it, invRows), pq = it - gi * rows, q = fast_div(pq, invN2), p = pq - q * n2;
+						const int gi = div_rows(it), pq = it - gi * rows, q = div_n2(pq), p = pq - q * n2;
 						const float* c = sC + gi * 3 * n2;
 						const float4 A = __ldg(io.tri48 + (size_t)e.y * 3), B = __ldg(io.tri48 + (size_t)e.y * 3 + 1), C = __ldg(io.tri48 + (size_t)e.y * 3 + 2);
 						SatCol s;
@@ -1007,7 +1011,7 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	// ---- the column's file bytes: SAT hit 254, else inside 127, else 0 (2 overwrites 1: src/Object.cpp:2603-2606)
 	unsigned nIn = 0, nBd = 0;
 	for (int item = tid; item < nItems; item += kL2Threads) {
-		const int gi = fast_div(item, invRows), pq = item - gi * rows;
+		const int gi = div_rows(item), pq = item - gi * rows;
 		const long long b = b0 + gi;
 		if (b >= io.nBoundary) continue;
 		const unsigned sat = sSat[item];

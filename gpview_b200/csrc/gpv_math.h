@@ -216,8 +216,10 @@ GPV_HD bool plane_row_interval(const PlaneRec& pl, float v0x0, float v0y, float 
 	if (!(pl.R <= kFltMax)) return true;
 	float D = pl.sx * v0x0 + pl.ny * v0y + pl.nz * v0z;
 	if (pl.sx == 0.f) return !(fabsf(D) > pl.R);
-	// floor/ceil already round outwards; the f32 error of the two bounds (<= 3u(|D|+R)) is inside the E budget folded into R
-	float lo = floorf((D - pl.R - slack) * inv2h), hi = ceilf((D + pl.R + slack) * inv2h);
+	// index k can pass only if lo <= k <= hi as real numbers; the f32 error of the two bounds (<= 3u(|D|+R), i.e. below 1e-5 of an
+	// index for any cell the triangle overlaps) is inside the E budget folded into R and again inside the 2^-7 widening
+	const float xl = (D - pl.R - slack) * inv2h, xh = (D + pl.R + slack) * inv2h;
+	float lo = ceilf(xl - (0.0078125f + 1e-6f * fabsf(xl))), hi = floorf(xh + (0.0078125f + 1e-6f * fabsf(xh)));
 	if (!(lo == lo) || !(hi == hi)) return true;
 	if (lo > 0.f) plo = lo > (float)n2 ? n2 : (int)lo;
 	if (hi < (float)(n2 - 1)) phi = hi < -1.f ? -1 : (int)hi;
@@ -296,21 +298,16 @@ GPV_HD float l2_centre(int p, float h2, float mid, float h1) { return (float)(2 
 
 // ---- parity bits of one (triangle, sub-voxel column) pair over the n2 <= 32 sub-voxels of ONE Level-1 cell: bit r is set iff
 // ray_cell(s, c, z_r), z_r = l2_centre(r, h2z, midz, h1z).  Bit-identical to n2 calls of ray_cell, but for a well-conditioned
-// triangle only the sub-voxels next to the crossing are evaluated.  With bnd an upper bound of ray_z_run's error bound for the cell:
-//   prefix   t0 - 2 bnd - 1.01 (z_a - z_0) > eps   ->  sub-voxels 0..a are hit   (ray_z_run's "all hit" claim for the run z_0..z_a,
-//            whose own bound is <= bnd because its span and heights lie inside the cell's)
-//   stop     t_r + 2 (bnd + 16u |t_r|) <= eps        ->  sub-voxels r.. are not hit (ray_z_run's "no hit" claim for the run z_r..z_hi,
-//            whose bound is <= bnd + 16u |t_r|: same magnitudes, t_r in place of t_0)
-// The index estimate only chooses where to start; every claim is checked against the actual centres.
-// The part of the bound that does not depend on the cell is computed once per (triangle, sub-column) by ray_col_bound for ALL
-// heights of the grid column [zMin, zMax] (a larger |Tz| or span only makes the bound more conservative); a negative k1 means
-// "not well conditioned: evaluate every sub-voxel".
-struct RayColZ { float k1, span; }; // k1 < 0: no certificate
-GPV_HD RayColZ ray_col_bound(const RayTri& s, const RayCol& c, float zMin, float zMax, float gsz)
+// triangle only the sub-voxels next to the crossing are evaluated (certificates below).  The part of ray_z_run's error bound
+// that does not depend on the cell is computed once per (triangle, sub-column) by ray_col_bound for ALL heights of the grid
+// column [zMin, zMax] (a larger |Tz| or span only makes the bound more conservative).
+struct RayColZ { float k1, span, inv101, inv099; }; // k1 < 0: no certificate; inv101 = 1/(1.01*2*h2z), inv099 = 1/(0.99*2*h2z): index estimates per unit of t
+GPV_HD RayColZ ray_col_bound(const RayTri& s, const RayCol& c, float zMin, float zMax, float gsz, float inv101, float inv099)
 {
 	RayColZ z;
 	// upper bound of 1.01 (z_hi - z_lo) of every cell of the column: the centres span (2 n2 - 2) h2z < gsz, plus their own rounding
 	z.span = 1.01f * (gsz + 9.5367431640625e-07f * (fabsf(zMin) + fabsf(zMax)));
+	z.inv101 = inv101; z.inv099 = inv099;
 	z.k1 = -1.f;
 	if (!s.well) return z;
 	const float Tm = fmaxf(fabsf(zMin - s.v1z), fabsf(zMax - s.v1z));
@@ -319,34 +316,37 @@ GPV_HD RayColZ ray_col_bound(const RayTri& s, const RayCol& c, float zMin, float
 	return z;
 }
 
+// For a well-conditioned triangle t falls with height with slope in [0.998, 1.002] (ray_z_run), and every f32 t of the cell is
+// within bnd_r <= bnd + 16u |t_r| <= 3 bnd of the exact one.  So with d_r = z_r - z_0 >= 0:
+//   t0 - 2 bnd - 1.01 d_r > eps   ->  sub-voxel r (and every lower one) is hit        (ray_z_run's "all hit" claim for the run z_0..z_r)
+//   t0 + 4 bnd - 0.99 d_r <= eps  ->  sub-voxel r (and every higher one) is not hit   (t_r <= t0 + bnd_0 + bnd_r - 0.998 d_r)
+// The two index estimates only choose where to start; both claims are checked against the actual centres, and the sub-voxels
+// between them (none or one, as the gap is 2 % of the height plus 6 bnd) are evaluated.
 GPV_HD unsigned ray_cell_mask(const RayTri& s, const RayCol& c, const RayColZ& z, float midz, float h1z, float h2z, int n2)
 {
 	const unsigned full = n2 >= 32 ? 0xffffffffu : ((1u << n2) - 1u);
 	const float zLo = l2_centre(0, h2z, midz, h1z);
-	int first = 0;
-	unsigned mask = 0;
-	float bnd = 0.f;
-	bool certified = false;
+	int first = 0, last = n2; // sub-voxels [first, last) are evaluated; below first: hit, from last on: not hit
 	if (z.k1 >= 0.f) {
 		const float t0 = ray_cell_t(s, c, zLo);
-		bnd = z.k1 + 9.5367431640625e-07f * fabsf(t0); // >= ray_z_run's bound for this cell (column-wide |Tz| and span)
+		const float bnd = z.k1 + 9.5367431640625e-07f * fabsf(t0); // >= ray_z_run's bound for this cell (column-wide |Tz| and span)
 		if (t0 + 2.f * bnd <= kEps) return 0u;          // every comparison is false for NaN / inf: falls through to plain evaluation
-		if (t0 - 2.f * bnd - z.span > kEps) return full;
+		const float hi = t0 - 2.f * bnd;
+		if (hi - z.span > kEps) return full;
 		if (bnd <= kFltMax && t0 == t0) {
-			certified = true;
-			const float room = t0 - 2.f * bnd - kEps;                    // may be <= 0: then a < 0 and nothing is taken for granted
-			const float a = floorf(room / (2.02f * h2z)) - 1.f;          // spacing of the centres is 2*h2z; 1.01 = the slope margin
-			int ai = !(a >= 0.f) ? -1 : (a > (float)(n2 - 1) ? n2 - 1 : (int)a);
-			while (ai >= 0 && !(t0 - 2.f * bnd - 1.01f * (l2_centre(ai, h2z, midz, h1z) - zLo) > kEps)) ai--;
-			first = ai + 1;
-			mask = first >= 32 ? 0xffffffffu : ((1u << first) - 1u);
+			const float A = (hi - kEps) * z.inv101;
+			int a = A >= 0.f ? (A < (float)n2 ? (int)A : n2 - 1) : -1;
+			while (a >= 0 && !(hi - 1.01f * (l2_centre(a, h2z, midz, h1z) - zLo) > kEps)) a--;
+			first = a + 1;
+			const float lo = t0 + 4.f * bnd;
+			const float B = ceilf((lo - kEps) * z.inv099);
+			int m = B < (float)n2 ? (B > (float)first ? (int)B : first) : n2;
+			while (m < n2 && !(lo - 0.99f * (l2_centre(m, h2z, midz, h1z) - zLo) <= kEps)) m++;
+			last = m;
 		}
 	}
-	for (int r = first; r < n2; r++) {
-		const float t = ray_cell_t(s, c, l2_centre(r, h2z, midz, h1z));
-		mask |= (unsigned)(t > kEps) << r;
-		if (certified && t + 2.f * (bnd + 9.5367431640625e-07f * fabsf(t)) <= kEps) break;
-	}
+	unsigned mask = first >= 32 ? 0xffffffffu : ((1u << first) - 1u);
+	for (int r = first; r < last; r++) mask |= (unsigned)(ray_cell_t(s, c, l2_centre(r, h2z, midz, h1z)) > kEps) << r;
 	return mask;
 }
 

@@ -152,7 +152,7 @@ extern "C" void probe_cell_mask(int64_t n, const float* oxy, const float* cellz,
 		unsigned want = 0;
 		for (int r = 0; r < n2; r++) want |= (unsigned)ray_cell(s, rc, l2_centre(r, h2, mid, h1)) << r;
 		// the column bound may be taken over any height range that contains the cell: tight, and as wide as a 1000-cell column
-		const RayColZ za = ray_col_bound(s, rc, mid - gs, mid + gs, gs), zb = ray_col_bound(s, rc, mid - 700.f * gs, mid + 300.f * gs, gs);
+		const RayColZ za = ray_col_bound(s, rc, mid - gs, mid + gs, gs, 1.f / (2.02f * h2), 1.f / (1.98f * h2)), zb = ray_col_bound(s, rc, mid - 700.f * gs, mid + 300.f * gs, gs, 1.f / (2.02f * h2), 1.f / (1.98f * h2));
 		RayColZ zn = za; zn.k1 = -1.f;
 		if (ray_cell_mask(s, rc, za, mid, h1, h2, n2) != want || ray_cell_mask(s, rc, zb, mid, h1, h2, n2) != want || ray_cell_mask(s, rc, zn, mid, h1, h2, n2) != want) bad++;
 		const unsigned full = n2 >= 32 ? 0xffffffffu : ((1u << n2) - 1u);
