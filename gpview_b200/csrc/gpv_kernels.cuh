@@ -692,7 +692,7 @@ __global__ void k_col_cells(const int* __restrict__ boundaryIndex, int nBoundary
 // them contributes its parity bits through gpv::ray_cell_mask (certified: only the sub-voxels next to the crossing are
 // evaluated).  Output: one word per (boundary cell, sub-column), bit r = parity of sub-voxel r; k_l2 only loads it.
 constexpr int kRaySlots = 16; // crossings kept in registers (16-bit list positions); further ones are applied in a second walk of the list (rare)
-constexpr int kRayCells = 4;  // boundary cells of the column refined per register chunk
+constexpr int kRayCells = 8;  // boundary cells of the column refined per register chunk
 constexpr int kL2Stage = 256; // ray records staged per chunk (12 KB)
 
 struct RaySub { // one sub-voxel column: origin, list, cells, output slot, height range of the grid column
