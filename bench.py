@@ -103,7 +103,7 @@ def measured_peaks():
 
 
 def ncu_traffic():
-    """dram bytes per k_l2 launch from the committed ncu --set full summary (profiles/traffic.json), or {}."""
+    """per-kernel numbers of the committed ncu --set full capture (profiles/traffic.json, tools/ncu_summary.py --traffic), or {}."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
@@ -330,31 +330,46 @@ def main():
         L.gpv_free_host(p)
 
     if rank == 0:
-        k_l2_ms = phase_acc["l2"] / args.steps
+        k_l2_ms = phase_acc["l2"] / args.steps                 # the SAT kernel alone (CUDA events on the launching stream)
+        k_rays_ms = phase_acc.get("l2_rays", 0.0) / args.steps   # k_col_cells + k_l2_rays
         fp32_peak = ctx.fp32_peak()
         hbm_peak, hbm_src = measured_peaks()
-        traffic = ncu_traffic()
+        ncu = ncu_traffic().get("kernels", {})
+        sat_name = "k_l2<%d>" % (args.l2 if args.l2 in (2, 4, 8, 16) else 0)
+        n_sat, n_rays = ncu.get(sat_name, {}), ncu.get("k_l2_rays", {})
         flops = FLOPS_PER_TRIBOX * res.stats["l2_box_tests"]
         ach = flops / (k_l2_ms * 1e-3) / 1e12
-        roof = {"kernel": "k_l2 (Level-2 refinement: parity rays + hoisted SAT)" + (" on rank 0's slab" if world > 1 else ""), "bound": "fp32",
+        ncu_note = lambda d: {"issue_active_pct": d.get("issue_active_pct"), "warp_inst_executed": d.get("warp_inst_executed"),
+                              "pipe_fma_pct": d.get("pipe_fma_pct"), "pipe_alu_pct": d.get("pipe_alu_pct"), "time_us": d.get("time_us"),
+                              "source": "profiles/" + d["source"]} if d else None
+        roof = {"kernel": sat_name + " (Level-2 SAT over shared-memory queues + final bytes)" + (" on rank 0's slab" if world > 1 else ""), "bound": "fp32",
                 "achieved": ach, "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": ach / (fp32_peak / 1e12),
-                "traffic": traffic.get("k_l2_dram_bytes") if world == 1 else None,
+                "traffic": n_sat.get("dram_bytes") if world == 1 else None,
                 "peak_source": "non-FMA FP32 issue rate measured live (gpv_measure_fp32_peak: independent FMUL/FADD chains); "
                                "MEASURED_PEAKS.json has no FP32 entry",
-                "algorithmic": "%d reference-equivalent tri-box tests x 124 FLOP per launch; the kernel skips tests that certified plane culling proves "
-                               "negative and hoists the x-independent part of the rest, so frac can exceed 1 (executed instruction counts: profiles/)"
-                               % res.stats["l2_box_tests"],
+                "algorithmic": "%d reference-equivalent tri-box tests x 124 FLOP per launch (SURVEY.md 8d).  frac > 1 is expected: certified plane / AABB "
+                               "culling proves ~94 %% of the reference's tests negative without running them and the z-independent part of the rest is "
+                               "hoisted per sub-voxel column.  What the kernel actually executes is bounded by instruction issue: see `ncu` "
+                               "(issue-slot utilisation of the same command under ncu --set full)" % res.stats["l2_box_tests"],
+                "ncu": ncu_note(n_sat) if world == 1 else None,
                 "kernel_ms": k_l2_ms, "share_of_step": k_l2_ms / ms_per_step}
+        ray_flops = 51.0 * res.stats.get("l2_ray_tests", 0)
+        roof_rays = {"kernel": "k_l2_rays (Level-2 parity rays per sub-voxel column)", "bound": "fp32", "kernel_ms": k_rays_ms, "share_of_step": k_rays_ms / ms_per_step,
+                     "achieved": ray_flops / (k_rays_ms * 1e-3) / 1e12 if k_rays_ms > 0 and ray_flops else None, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+                     "algorithmic": "%d reference-equivalent ray tests x 51 FLOP (+1 division) per launch" % res.stats.get("l2_ray_tests", 0),
+                     "traffic": n_rays.get("dram_bytes") if world == 1 else None, "ncu": ncu_note(n_rays) if world == 1 else None}
+        if roof_rays["achieved"]:
+            roof_rays["frac"] = roof_rays["achieved"] / roof_rays["peak"]
         out_bytes = res.nb * res.n23
-        roof_hbm = {"kernel": "k_l2", "bound": "hbm", "achieved": out_bytes / (k_l2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": out_bytes / (k_l2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("k_l2_dram_bytes") if world == 1 else None,
+        roof_hbm = {"kernel": sat_name, "bound": "hbm", "achieved": out_bytes / (k_l2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": out_bytes / (k_l2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": n_sat.get("dram_bytes") if world == 1 else None,
                     "peak_source": hbm_src, "algorithmic": "1 B per Level-2 voxel written (%d B)" % out_bytes}
         line = {"metric": "G tri-box tests/s", "value": value, "unit": "G tri-box tests/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "ms_per_model": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "cessna.obj fixture (reference sample mesh)" if args.mesh == "cessna" else "synthetic",
                 "config": dict(workload_config(args), parallelism=("z-slabs x%d (cuts %s), Level-1 replicated, NCCL gather to rank 0" % (world, cuts)) if world > 1 else "1 GPU",
                                tri_box_tests_per_model=int(tests), triangles=mesh.ntri, grid=[int(x) for x in res.num_div]),
-                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_hbm": roof_hbm,
+                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_rays": roof_rays, "roofline_hbm": roof_hbm,
                 "phase_ms": {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0},
                 "counts": {"l1_inside": whole.counts[0], "l1_boundary": whole.counts[1]}}
         if world == 1 and not args.no_cpu_baseline and path is not None:

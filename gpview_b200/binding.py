@@ -38,7 +38,7 @@ class CResult(C.Structure):
                     "tri_total", "fill_crossings", "fill_ill_conditioned", "kernel_launches")] + [("phase_ms", C.c_float * 16)]
 
 
-PHASES = ["setup", "bin_count", "cross_count", "scan", "host_gap", "bin_fill", "cross_fill", "sort", "fill_sweep", "l1_normals", "l2", "l2_normals"]
+PHASES = ["setup", "bin_count", "cross_count", "scan", "host_gap", "bin_fill", "cross_fill", "sort", "fill_sweep", "l1_normals", "l2_rays", "l2", "l2_normals"]
 
 
 class CHostStreams(C.Structure):
@@ -184,7 +184,7 @@ class Result:
         self.n2, self.cells, self.nb, self.n23 = int(g.n2), int(cres.cells), int(cres.n_boundary), int(cres.n23)
         self.z0, self.z1 = int(cres.z0), int(cres.z1)
         self.counts = [int(cres.l1_inside), int(cres.l1_boundary), int(cres.l2_inside), int(cres.l2_boundary)]
-        self.stats = {k: int(getattr(cres, k)) for k in ("l1_box_tests", "l1_box_hits", "l2_box_tests", "tri_total", "fill_crossings",
+        self.stats = {k: int(getattr(cres, k)) for k in ("l1_box_tests", "l1_box_hits", "l2_box_tests", "l2_ray_tests", "tri_total", "fill_crossings",
                                                          "fill_ill_conditioned", "kernel_launches")}
         self.phase_ms = dict(zip(PHASES, [float(x) for x in cres.phase_ms]))
 

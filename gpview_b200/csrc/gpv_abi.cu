@@ -332,7 +332,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		if (sink->level1_normal && wantN) GPV_CUDA(cudaMemcpyAsync(sink->level1_normal, c->l1Normal.p, (size_t)cells * 3, cudaMemcpyDeviceToHost, c->copyStream));
 	}
 	L2IO lio{};
-	mark(GPV_PHASE_L2);
+	mark(GPV_PHASE_L2_RAYS);
 	if (wantL2 && nB > 0) {
 		lio.tri48 = tri48; lio.ray48 = ray48; lio.plane16 = c->plane16.as<float4>(); lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
 		lio.cellTris = c->cellTris.as<int>(); lio.colOff = c->colOff.as<unsigned>(); lio.colCount = c->colCount.as<int>(); lio.colTris = c->colTris.as<int>();
@@ -345,9 +345,10 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		if (smem > 48 * 1024) return fail("k_l2: shared-memory layout exceeds 48 KB"); // cannot happen for n2 <= 32 (41 KB)
 		// K4a: boundary cells grouped by Level-1 column, then the parity bits of every sub-voxel column, one walk of the column list per column
 		k_col_cells<<<(unsigned)((nB + 255) / 256), 256, 0, st>>>(lio.boundaryIndex, (int)nB, (int)ncol, g.nx, cx, cy, cz, lio.colCellOff, c->colCellCnt.as<int>(), c->colCellList.as<int2>(),
-		                                                        c->cellMid.as<float4>());
+		                                                        c->cellMid.as<float4>(), lio.colCount, dT);
 		k_l2_rays<<<(unsigned)((ncol + G - 1) / G), 256, 0, st>>>(g, lio);
 		launches += 2;
+		mark(GPV_PHASE_L2);
 		// With a host sink the boundary cells are refined in chunks and every finished chunk's bytes start their way to the
 		// host on the copy stream while the next chunk computes (e2e is PCIe-bound: 1 B per Level-2 voxel).
 		long long chunks = 1;
@@ -395,7 +396,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	out->l1_box_tests = (int64_t)T2.binWork; out->l1_box_hits = (int64_t)T2.l1Hits; // sum of clipped footprints = the reference's loop nest (cu:374-378)
 	out->tri_total = T2.triTotal;
 	out->l2_box_tests = wantL2 ? (int64_t)T2.triTotal * n23 : 0; // reference-equivalent: n2^3 x sum of cell list lengths (cu:428)
-	out->l2_ray_tests = 0;
+	out->l2_ray_tests = wantL2 ? (int64_t)T2.l2ColPairs * n23 : 0; // reference-equivalent: n2^3 x sum of column list lengths (cu:461-463)
 	out->fill_crossings = (int64_t)T2.crossPairs; out->fill_ill_conditioned = (int64_t)T2.nIll;
 	out->kernel_launches = launches;
 	if (prof) {

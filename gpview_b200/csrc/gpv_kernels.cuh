@@ -33,6 +33,7 @@ struct GridP {
 struct Totals {
 	unsigned long long binWork, crossWork; // totals of the two balanced work spaces (exclusive scans of binCnt / crossCnt)
 	unsigned long long l1Hits, crossPairs, nIll, l1Inside, l2Inside, l2Boundary;
+	unsigned long long l2ColPairs; // sum over boundary cells of their column-list length (reference-equivalent Level-2 ray tests / n2^3)
 	unsigned int nBoundary, triTotal, colTotalOver, crossTotal;
 	unsigned int nBoundaryCols, pad0, pad1, pad2; // Level-1 columns that hold boundary cells (size of the Level-2 crossing lists)
 };
@@ -674,9 +675,14 @@ __device__ __forceinline__ int fast_div(int a, float inv) { return __float2int_r
 // column is irrelevant, every cell is refined independently).  Entry = (slab-local boundary rank, centre height of the cell).
 // Also the centre of every boundary cell by rank, so that k_l2 does not decode linear indices.
 __global__ void k_col_cells(const int* __restrict__ boundaryIndex, int nBoundary, int plane, int nx, const float* __restrict__ cx, const float* __restrict__ cy,
-                            const float* __restrict__ cz, const unsigned* __restrict__ colCellOff, int* colCellCnt, int2* colCellList, float4* cellMid)
+                            const float* __restrict__ cz, const unsigned* __restrict__ colCellOff, int* colCellCnt, int2* colCellList, float4* cellMid,
+                            const int* __restrict__ colCount, Totals* totals)
 {
 	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long pairs = 0;
+	if (b < nBoundary) pairs = (unsigned long long)colCount[boundaryIndex[b] % plane];
+	pairs = warp_sum(pairs);
+	if ((threadIdx.x & 31) == 0 && pairs) atomicAdd(&totals->l2ColPairs, pairs);
 	if (b >= nBoundary) return;
 	const int l1 = boundaryIndex[b], kz = l1 / plane, col = l1 - kz * plane, jy = col / nx, ix = col - jy * nx;
 	const float mz = cz[kz];

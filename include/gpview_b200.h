@@ -110,7 +110,7 @@ typedef struct {
 } gpv_result;
 
 enum { GPV_PHASE_SETUP = 0, GPV_PHASE_BIN_COUNT, GPV_PHASE_CROSS_COUNT, GPV_PHASE_SCAN, GPV_PHASE_HOST_GAP, GPV_PHASE_BIN_FILL,
-       GPV_PHASE_CROSS_FILL, GPV_PHASE_SORT, GPV_PHASE_FILL_SWEEP, GPV_PHASE_L1_NORMALS, GPV_PHASE_L2, GPV_PHASE_L2_NORMALS, GPV_PHASE_COUNT };
+       GPV_PHASE_CROSS_FILL, GPV_PHASE_SORT, GPV_PHASE_FILL_SWEEP, GPV_PHASE_L1_NORMALS, GPV_PHASE_L2_RAYS, GPV_PHASE_L2, GPV_PHASE_L2_NORMALS, GPV_PHASE_COUNT };
 
 /* host copies of the streams (caller-allocated; any pointer may be NULL to skip that stream) */
 typedef struct {

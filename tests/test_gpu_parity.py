@@ -30,7 +30,8 @@ def test_streams_match_oracle_and_golden(product, oracle, ctx, tmp_path_factory,
     assert res.counts == ores.counts == [info["l1_inside"], info["l1_boundary"], info["l2_inside"], info["l2_boundary"]]
     assert res.stats["l1_box_tests"] == ores.stats["l1BoxTests"] == info["l1_box_tests"]
     assert res.stats["l1_box_hits"] == ores.stats["l1BoxHits"] == info["l1_box_hits"]
-    assert res.stats["l2_box_tests"] == ores.stats["l2BoxTests"]
+    assert res.stats["l2_box_tests"] == ores.stats["l2BoxTests"] == info["l2_box_tests"]
+    assert res.stats["l2_ray_tests"] == ores.stats["l2RayTests"] == info["l2_ray_tests"]
     assert res.stats["fill_ill_conditioned"] == ores.stats["fillIllConditioned"]
     assert res.stats["fill_crossings"] == ores.stats["fillCrossings"]
 

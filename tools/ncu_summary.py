@@ -1,10 +1,13 @@
 #!/usr/bin/env python3
-"""Write the judged summaries from an ncu report: python tools/ncu_summary.py report.ncu-rep out_prefix [kernel-key]
- -> <out_prefix>_summary.txt (key raw metrics per launch) and, with a kernel key, profiles/traffic.json (dram bytes/launch)."""
+"""Write the judged summaries from an ncu report: python tools/ncu_summary.py report.ncu-rep out_prefix [--traffic]
+ -> <out_prefix>_summary.txt (key raw metrics per launch) and, with --traffic, profiles/traffic.json: per kernel (short name,
+ last launch wins) dram bytes per launch, duration, executed warp instructions and issue-slot utilisation -- the numbers
+ bench.py quotes under "roofline" (it never runs under a profiler itself)."""
 import csv
 import io
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -21,27 +24,45 @@ def to_bytes(v, unit):
     return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
 
+def to_us(v, unit):
+    f = float(v.replace(",", ""))
+    return f * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(unit, 1)
+
+
+def short(name):
+    return re.sub(r"^(void )?(gpv::)?", "", name).split("(")[0]
+
+
 def main():
     rep, prefix = sys.argv[1], sys.argv[2]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     lines = ["source: %s  (ncu --set full --clock-control none --import-source on)" % os.path.basename(rep)]
-    traffic = None
+    per_kernel = {}
+    col = {k: hdr.index(k) for k in KEYS if k in hdr}
     for r in rows[2:]:
-        lines.append("--- %s  (launch id %s)" % (r[hdr.index("Kernel Name")], r[0]))
+        name = r[hdr.index("Kernel Name")]
+        lines.append("--- %s  (launch id %s)" % (name, r[0]))
         for k in KEYS:
-            if k in hdr:
-                lines.append("%-66s %s %s" % (k, r[hdr.index(k)], units[hdr.index(k)]))
-        if traffic is None and "dram__bytes_read.sum" in hdr:
-            i, j = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-            traffic = to_bytes(r[i], units[i]) + to_bytes(r[j], units[j])
+            if k in col:
+                lines.append("%-66s %s %s" % (k, r[col[k]], units[col[k]]))
+        if "dram__bytes_read.sum" in col:
+            i, j, t = col["dram__bytes_read.sum"], col["dram__bytes_write.sum"], col["gpu__time_duration.sum"]
+            per_kernel[short(name)] = {
+                "dram_bytes": to_bytes(r[i], units[i]) + to_bytes(r[j], units[j]),
+                "time_us": to_us(r[t], units[t]),
+                "warp_inst_executed": float(r[col["smsp__inst_executed.sum"]].replace(",", "")),
+                "issue_active_pct": float(r[col["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+                "lanes_per_inst": float(r[col["smsp__thread_inst_executed_per_inst_executed.ratio"]]),
+                "pipe_fma_pct": float(r[col["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]]),
+                "pipe_alu_pct": float(r[col["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]]),
+                "source": os.path.basename(prefix) + "_summary.txt"}
     open(prefix + "_summary.txt", "w").write("\n".join(lines) + "\n")
-    if len(sys.argv) > 3 and traffic is not None:
+    if "--traffic" in sys.argv[3:]:
         p = os.path.join(os.path.dirname(os.path.abspath(prefix)), "traffic.json")
         d = json.load(open(p)) if os.path.exists(p) else {}
-        d[sys.argv[3]] = traffic
-        d[sys.argv[3] + "_source"] = os.path.basename(prefix) + "_summary.txt"
+        d.setdefault("kernels", {}).update(per_kernel)
         json.dump(d, open(p, "w"), indent=1)
     print("\n".join(lines[:24]))
 
