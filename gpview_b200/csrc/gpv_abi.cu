@@ -3,18 +3,20 @@
 // Pipeline of gpv_voxelize_device (what Object::PerformVoxelization, src/Object.cpp:3077-3430, does between
 // CreateFlatTriangleData and SaveVoxelization, re-designed for one B200):
 //
-//   k_tables, k_prepare     48 B triangle / ray records, footprints, work-item counts
-//   k_scan<OFFS> x2         balanced work spaces of the two triangle-parallel sweeps
+//   k_clear                 every counter of the call
+//   k_prepare               48 B triangle / ray / plane records, footprints, work-item counts, centre tables
+//   k_scan_offs3            balanced work spaces of the two triangle-parallel sweeps (two scans, one launch)
 //   k_bin<count>            K1 count sweep: cellCount, colCount(over), l1Hits
 //   k_cross<count>          K2a count sweep: crossCount
-//   k_scan<CELLS>           K3: prefix, boundaryIndex, bTriOff, bmask, nBoundary, triTotal
-//   k_scan<OFFS> x2         column-list offsets, crossing-list offsets
-//   ---- one 64-byte read-back (sizes of the variable-length buffers) ----
+//   k_scan<CELLS>           K3: prefix, boundaryIndex, bTriOff, bmask, per-column boundary-cell counts, nBoundary, triTotal
+//   k_scan_offs3            column-list, crossing-list and column-cell offsets (three scans, one launch)
+//   ---- one 128-byte read-back (sizes of the variable-length buffers) ----
 //   k_bin<fill>, k_cross<fill>
-//   k_sort_segments x2      canonical ascending cell lists; sorted + de-duplicated column lists
+//   k_sort_segments / k_sort_long x2   canonical ascending cell lists; sorted + de-duplicated column lists
 //   k_fill_sweep            K2b: final Level-1 bytes + inside count
 //   k_l1_normals            (GPV_NORMALS)
-//   k_l2                    K4: Level-2 bytes + counts
+//   k_col_cells, k_l2_rays  K4a: boundary cells by column, Level-2 parity bits per sub-voxel column
+//   k_l2<n2>                K4: Level-2 SAT + final bytes + counts
 //   k_l2_normals            (GPV_NORMALS)
 #include "../../include/gpview_b200.h"
 #include "gpv_internal.h"
@@ -97,7 +99,8 @@ extern "C" int gpv_create(int device, gpv_ctx** out)
 	c->device = device;
 	c->smCount = prop.multiProcessorCount;
 	GPV_CUDA(cudaHostAlloc((void**)&c->hTotals, sizeof(Totals), cudaHostAllocDefault));
-	if (c->totals.ensure(sizeof(Totals))) { delete c; return 1; }
+	static_assert(sizeof(Totals) <= 128, "gpv_ctx::totals: Totals in the first 128 bytes, the sort's long-list counters behind");
+	if (c->totals.ensure(256)) { delete c; return 1; }
 	GPV_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
 	GPV_CUDA(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
 	for (cudaEvent_t& e : c->evChunk) GPV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -153,19 +156,23 @@ extern "C" int gpv_stream_sync(void* stream)
 	return 0;
 }
 
-static int run_scan_offsets(gpv_ctx* c, cudaStream_t st, const int* in, long long n, unsigned* off, unsigned* totalOut, unsigned long long* totalOut64,
-                            int64_t& launches)
+// offset scans (k_scan_offs3): up to three per launch; the look-back descriptors live in regions of c->desc cleared by k_clear
+struct ScanReq { const int* in; long long n; unsigned* off; unsigned* totalOut; unsigned long long* totalOut64; size_t descOff; };
+static size_t desc_bytes(long long n) { return (size_t)(((n + kScanTile - 1) / kScanTile + 1) * 8 + 16 + 15) & ~(size_t)15; }
+static void launch_scans(gpv_ctx* c, cudaStream_t st, const ScanReq* r, int count, int64_t& launches)
 {
-	long long tiles = (n + kScanTile - 1) / kScanTile;
-	if (c->desc.ensure((size_t)(tiles + 1) * 8 + 16)) return 1;
-	GPV_CUDA(cudaMemsetAsync(c->desc.p, 0, (size_t)(tiles + 1) * 8 + 16, st));
-	ScanIO io{};
-	io.in = in; io.n = n;
-	io.desc = c->desc.as<unsigned long long>() + 1; io.tileCounter = c->desc.as<unsigned>();
-	io.off = off; io.totalOut = totalOut; io.totalOut64 = totalOut64;
-	k_scan<MODE_OFFS><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
+	ScanIO3 io3{};
+	long long maxTiles = 1;
+	for (int k = 0; k < count; k++) {
+		ScanIO& io = io3.s[k];
+		io.in = r[k].in; io.n = r[k].n;
+		io.tileCounter = reinterpret_cast<unsigned*>(c->desc.as<char>() + r[k].descOff);
+		io.desc = reinterpret_cast<unsigned long long*>(c->desc.as<char>() + r[k].descOff) + 1;
+		io.off = r[k].off; io.totalOut = r[k].totalOut; io.totalOut64 = r[k].totalOut64;
+		maxTiles = std::max(maxTiles, (r[k].n + kScanTile - 1) / kScanTile);
+	}
+	k_scan_offs3<<<dim3((unsigned)maxTiles, (unsigned)count), kScanThreads, 0, st>>>(io3);
 	launches++;
-	return 0;
 }
 
 constexpr int kMaxChunks = 16; // Level-2 chunks whose D2H copies overlap the next chunk's refinement (host sink only)
@@ -219,23 +226,42 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		return 1;
 	Totals* dT = c->totals.as<Totals>();
 	mark(GPV_PHASE_SETUP);
-	GPV_CUDA(cudaMemsetAsync(dT, 0, sizeof(Totals), st));
-	GPV_CUDA(cudaMemsetAsync(c->cellCount.p, 0, (size_t)cells * 4, st));
-	GPV_CUDA(cudaMemsetAsync(c->colCount.p, 0, (size_t)ncol * 4, st));
-	GPV_CUDA(cudaMemsetAsync(c->crossCount.p, 0, (size_t)ncol * 4, st));
-	GPV_CUDA(cudaMemsetAsync(c->colCellCnt.p, 0, (size_t)ncol * 4, st));
+	// look-back descriptor regions of the six scans of this call
+	size_t dOff[7];
+	{
+		const long long ns[6] = { nTri, nTri, cells, ncol, ncol, ncol };
+		dOff[0] = 0;
+		for (int k = 0; k < 6; k++) dOff[k + 1] = dOff[k] + desc_bytes(ns[k]);
+		if (c->desc.ensure(dOff[6] + 32)) return 1;
+	}
+	{ // one launch zeroes every counter of the call (instead of a dozen memsets)
+		ClearList cl{};
+		int k = 0;
+		auto add = [&](void* p, size_t bytes) { cl.p[k] = reinterpret_cast<uint4*>(p); cl.n16[k] = (bytes + 15) / 16; k++; };
+		add(dT, 256);                                   // Totals + the two long-list counters of the sort (gpv_ctx::totals is 256 B)
+		add(c->cellCount.p, (size_t)cells * 4);
+		add(c->colCount.p, (size_t)ncol * 4);
+		add(c->crossCount.p, (size_t)ncol * 4);
+		add(c->colCellCnt.p, (size_t)ncol * 4);
+		add(c->desc.p, dOff[6]);
+		k_clear<<<dim3((unsigned)std::min<long long>(c->smCount * 8, (cells * 4 / 16 + 255) / 256 + 1), (unsigned)k), 256, 0, st>>>(cl);
+		launches++;
+	}
 
 	float *cx = c->tabX.as<float>(), *cy = c->tabY.as<float>(), *cz = c->tabZ.as<float>();
 	float4 *tri48 = c->tri48.as<float4>(), *ray48 = c->ray48.as<float4>();
 	{
 		int m = g.nx > g.ny ? g.nx : g.ny; m = m > g.nz ? m : g.nz;
-		k_tables<<<(m + 255) / 256, 256, 0, st>>>(g, cx, cy, cz);
-		k_prepare<<<(nTri + 255) / 256, 256, 0, st>>>(d_tris, nTri, g, tri48, ray48, c->plane16.as<float4>(), c->crossFp.as<int4>(), c->binCnt.as<int>(), c->crossCnt.as<int>(), dT);
-		launches += 2;
+		m = m > nTri ? m : nTri; // k_prepare also fills the per-axis centre tables
+		k_prepare<<<(m + 255) / 256, 256, 0, st>>>(d_tris, nTri, g, tri48, ray48, c->plane16.as<float4>(), c->crossFp.as<int4>(), c->binCnt.as<int>(), c->crossCnt.as<int>(), dT, cx, cy, cz);
+		launches++;
 	}
 	// balanced work spaces: exclusive scans of the per-triangle item counts; totals stay on the device (persistent grids read them)
-	if (run_scan_offsets(c, st, c->binCnt.as<int>(), nTri, c->binOff.as<unsigned>(), nullptr, &dT->binWork, launches)) return 1;
-	if (run_scan_offsets(c, st, c->crossCnt.as<int>(), nTri, c->crossWorkOff.as<unsigned>(), nullptr, &dT->crossWork, launches)) return 1;
+	{
+		const ScanReq r[2] = { { c->binCnt.as<int>(), nTri, c->binOff.as<unsigned>(), nullptr, &dT->binWork, dOff[0] },
+			                   { c->crossCnt.as<int>(), nTri, c->crossWorkOff.as<unsigned>(), nullptr, &dT->crossWork, dOff[1] } };
+		launch_scans(c, st, r, 2, launches);
+	}
 	BinOut bo{};
 	bo.cellCount = c->cellCount.as<int>(); bo.colCount = c->colCount.as<int>(); bo.totals = dT;
 	mark(GPV_PHASE_BIN_COUNT);
@@ -246,20 +272,21 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	mark(GPV_PHASE_SCAN);
 	{ // K3 boundary compaction
 		long long tiles = (cells + kScanTile - 1) / kScanTile;
-		if (c->desc.ensure((size_t)(tiles + 1) * 8 + 16)) return 1;
-		GPV_CUDA(cudaMemsetAsync(c->desc.p, 0, (size_t)(tiles + 1) * 8 + 16, st));
 		ScanIO io{};
 		io.in = c->cellCount.as<int>(); io.n = cells;
-		io.desc = c->desc.as<unsigned long long>() + 1; io.tileCounter = c->desc.as<unsigned>();
+		io.tileCounter = reinterpret_cast<unsigned*>(c->desc.as<char>() + dOff[2]); io.desc = reinterpret_cast<unsigned long long*>(c->desc.as<char>() + dOff[2]) + 1;
 		io.prefix = c->prefix.as<int>(); io.boundaryIndex = c->boundaryIndex.as<int>(); io.bTriOff = c->bTriOff.as<unsigned>();
 		io.bmask = c->bmask.as<unsigned char>(); io.globalBase = (long long)g.z0 * ncol; io.totals = dT;
 		io.colCells = c->colCellCnt.as<int>(); io.plane = ncol;
 		k_scan<MODE_CELLS><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
 		launches++;
 	}
-	if (run_scan_offsets(c, st, c->colCount.as<int>(), ncol, c->colOff.as<unsigned>(), &dT->colTotalOver, nullptr, launches)) return 1;
-	if (run_scan_offsets(c, st, c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, nullptr, launches)) return 1;
-	if (wantL2 && run_scan_offsets(c, st, c->colCellCnt.as<int>(), ncol, c->colCellOff.as<unsigned>(), nullptr, nullptr, launches)) return 1;
+	{
+		const ScanReq r[3] = { { c->colCount.as<int>(), ncol, c->colOff.as<unsigned>(), &dT->colTotalOver, nullptr, dOff[3] },
+			                   { c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, nullptr, dOff[4] },
+			                   { c->colCellCnt.as<int>(), ncol, c->colCellOff.as<unsigned>(), nullptr, nullptr, dOff[5] } };
+		launch_scans(c, st, r, wantL2 ? 3 : 2, launches);
+	}
 
 	// ---- the one size read-back
 	mark(GPV_PHASE_HOST_GAP);
@@ -287,10 +314,9 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	mark(GPV_PHASE_SORT);
 	{ // canonical order: warp per list; lists longer than kSortSmem go through a work list to k_sort_long (CTA per list)
 		if (c->longList.ensure((size_t)(nB + ncol) * 4 + 64)) return 1;
-		unsigned* longCnt = c->longList.as<unsigned>();           // [0] cell lists, [1] column lists
+		unsigned* longCnt = reinterpret_cast<unsigned*>(c->totals.as<char>() + 128); // [0] cell lists, [1] column lists (zeroed by k_clear)
 		int* longCells = c->longList.as<int>() + 16;
 		int* longCols = longCells + nB;
-		GPV_CUDA(cudaMemsetAsync(longCnt, 0, 64, st));
 		if (!c->sortAttrSet) { // function attributes are per device: once per context, not once per process
 			GPV_CUDA(cudaFuncSetAttribute(k_sort_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortLongSmem * 4));
 			GPV_CUDA(cudaFuncSetAttribute(k_sort_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortLongSmem * 4));

@@ -2,8 +2,9 @@
 //
 // Compiled ONLY with  nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false  (see DESIGN.md "Numerics").
 // Kernel inventory (SURVEY.md 2.3 "new kernels"):
-//   k_tables        per-axis Level-1 cell-centre tables (kills all FP64 / int->float work in the inner loops)
-//   k_prepare       36 B flat triangles -> 48 B float4x3 records (TMA-able, footprint in the w lanes) + 48 B +Z ray records
+//   k_clear         every counter of the call in one launch
+//   k_prepare       36 B flat triangles -> 48 B float4x3 records (TMA-able, footprint in the w lanes) + 48 B +Z ray records;
+//                   also the per-axis Level-1 cell-centre tables (kills all FP64 / int->float work in the inner loops)
 //   k_bin<FILL>     K1  triangle -> Level-1 cell SAT binning (count / fill sweeps), TMA-staged triangle tiles
 //   k_cross<FILL>   K2a certified (column, triangle) crossing detection for the parity fill
 //   k_fill_sweep    K2b +Z parity sweep per Level-1 column, coalesced along x, final Level-1 state bytes
@@ -69,17 +70,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 	}
 }
 
-// ------------------------------------------------------------------------------------------------ k_tables
-// centre[p] = fl32((p + 0.5) * ext * 2 + min) evaluated in double exactly like cu:382-384 (== ray origin
-// src/Object.cpp:743-745 == mid point :2567-2569, see oracle/gpv_oracle.c gpvo_axis_table).
-__global__ void k_tables(GridP g, float* cx, float* cy, float* cz)
-{
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < g.nx) cx[i] = (float)((i + 0.5) * (double)g.h1x * 2 + (double)g.minx);
-	if (i < g.ny) cy[i] = (float)((i + 0.5) * (double)g.h1y * 2 + (double)g.miny);
-	if (i < g.nz) cz[i] = (float)((i + 0.5) * (double)g.h1z * 2 + (double)g.minz);
-}
-
 // ------------------------------------------------------------------------------------------------ k_prepare
 // flat float[9] per triangle (src/Object.cpp:3496-3527 layout) ->
 //   tri48  v0|v1|v2 as float4; the three w lanes carry the clipped Level-1 footprint (cu:333-378) as packed 16-bit fields
@@ -89,13 +79,21 @@ __global__ void k_tables(GridP g, float* cx, float* cy, float* cz)
 //   crossFp i0 | j0<<16, di | dj<<16, kind, -   certified candidate columns of the +Z parity fill (gpv::fill_candidates)
 //   binCnt / crossCnt  number of (triangle, cell) / (triangle, column) work items
 // All records are 16-byte aligned so that contiguous triangle ranges can be moved by TMA bulk copies.
+// Centre tables: centre[p] = fl32((p + 0.5) * ext * 2 + min) evaluated in double exactly like cu:382-384 (== ray origin
+// src/Object.cpp:743-745 == mid point :2567-2569, see oracle/gpv_oracle.c gpvo_axis_table).
 __global__ void __launch_bounds__(256) k_prepare(const float* __restrict__ flat, long long nTri, GridP g, float4* __restrict__ tri48,
                                                  float4* __restrict__ ray48, float4* __restrict__ plane16, int4* __restrict__ crossFp,
-                                                 int* __restrict__ binCnt, int* __restrict__ crossCnt, Totals* totals)
+                                                 int* __restrict__ binCnt, int* __restrict__ crossCnt, Totals* totals, float* cx, float* cy, float* cz)
 {
 	__shared__ float s[256 * 9];
 	long long base = (long long)blockIdx.x * 256;
-	int n = (int)min((long long)256, nTri - base);
+	{ // the per-axis centre tables of k_tables, fused (the grid covers max(nx, ny, nz) threads as well)
+		const long long i = base + threadIdx.x;
+		if (i < g.nx) cx[i] = (float)((i + 0.5) * (double)g.h1x * 2 + (double)g.minx);
+		if (i < g.ny) cy[i] = (float)((i + 0.5) * (double)g.h1y * 2 + (double)g.miny);
+		if (i < g.nz) cz[i] = (float)((i + 0.5) * (double)g.h1z * 2 + (double)g.minz);
+	}
+	int n = (int)max((long long)0, min((long long)256, nTri - base));
 	for (int i = threadIdx.x; i < n * 9; i += 256) s[i] = flat[base * 9 + i]; // coalesced
 	__syncthreads();
 	int t = threadIdx.x;
@@ -380,7 +378,7 @@ __device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long lon
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kScanThreads) k_scan(ScanIO io)
+__device__ __forceinline__ void scan_body(const ScanIO& io)
 {
 	__shared__ unsigned sTile;
 	__shared__ unsigned long long sWarp[kScanThreads / 32];
@@ -492,6 +490,28 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(ScanIO io)
 			if (io.totalOut64) *io.totalOut64 = run;
 		}
 	}
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kScanThreads) k_scan(ScanIO io) { scan_body<MODE>(io); }
+
+// up to three independent offset scans in one launch (blockIdx.y selects the scan; blocks beyond a scan's tile count leave)
+struct ScanIO3 { ScanIO s[3]; };
+__global__ void __launch_bounds__(kScanThreads) k_scan_offs3(ScanIO3 io3)
+{
+	const ScanIO& io = io3.s[blockIdx.y];
+	if ((long long)blockIdx.x * kScanTile >= io.n) return;
+	scan_body<MODE_OFFS>(io);
+}
+
+// one launch instead of a dozen cudaMemsetAsync calls: zero up to 12 buffers (16-byte granules; every buffer carries >= 32 B of slack)
+struct ClearList { uint4* p[12]; unsigned long long n16[12]; };
+__global__ void __launch_bounds__(256) k_clear(ClearList cl)
+{
+	uint4* p = cl.p[blockIdx.y];
+	const unsigned long long n = cl.n16[blockIdx.y];
+	const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+	for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256) p[i] = z;
 }
 
 // ------------------------------------------------------------------------------------------------ k_sort_segments
