@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--l1", type=int, default=256)
     ap.add_argument("--l2", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: slabs written into rank 0's buffers over NVLink peer memory from inside the kernels (GPV_GATHER), or gathered with NCCL send/recv")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -217,12 +219,22 @@ def main():
     if world > 1:
         cuts = sharded.plan_slabs(sharded.layer_cost(whole.boundary_index(), whole.cell_off(), plane, nz), world)
         z0, z1 = cuts[rank], cuts[rank + 1]
-    params = gpv.Params(args.l1, args.l2, gpv.GPV_PROFILE, z0, z1)  # CUDA events around every kernel, on the launching stream
+    peer = world > 1 and args.gather == "peer"
+    n23 = args.l2 ** 3
+    if peer:  # rank 0 owns the whole-grid streams; the other ranks map them (CUDA IPC) and write their slabs over NVLink
+        desc = B.CGatherDesc()
+        if rank == 0:
+            desc = ctx.gather_create(plane * nz, int(whole.nb) * n23)
+        t = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        desc = B.CGatherDesc.from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
+        ctx.gather_attach(desc, rank, world)
+    params = gpv.Params(args.l1, args.l2, gpv.GPV_PROFILE | (gpv.GPV_GATHER if peer else 0), z0, z1)  # CUDA events around every kernel, on the launching stream
     gathered = {}
 
     def step():
         res = ctx.voxelize_device(d_tris, mesh, params, sptr)
-        if world > 1:  # slab pieces -> rank 0 over NCCL (concatenation only), inside the timed region
+        if world > 1 and not peer:  # slab pieces -> rank 0 over NCCL (concatenation only), inside the timed region
             w = lambda ptr, n: sharded.wrap_device_bytes(torch, ptr, n)
             pieces = {"l1": (w(res.c.d_level1_inout, res.cells), 1, 0), "prefix": (w(res.c.d_prefix, res.cells * 4), 4, 0),
                       "l2": (w(res.c.d_level2_inout, res.nb * res.n23), res.n23, 1)}
@@ -271,6 +283,24 @@ def main():
     t_timed1 = time.perf_counter()
     clocks = sampler.stop(t_timed0, t_timed1, extended) if rank == 0 else None
 
+    gather_ok = None
+    if world > 1:  # untimed: the gathered streams on rank 0 must equal a single-GPU run of the whole grid, byte for byte
+        if peer:
+            ctx.gather_detach() if rank else None
+        if rank == 0:
+            w = lambda ptr, n: sharded.wrap_device_bytes(torch, ptr, n)
+            if peer:
+                p1, p2, p3, nbt = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+                B._check(L.gpv_gather_result(ctx.h, C.byref(p1), C.byref(p2), C.byref(p3), C.byref(nbt)))
+                got = {"l1": w(p1.value, plane * nz).clone(), "prefix": w(p2.value, plane * nz * 4).clone(), "l2": w(p3.value, nbt.value * n23).clone()}
+                ctx.gather_detach()
+            else:
+                got = {k: v.clone() for k, v in gathered.items()}
+            ref = ctx.voxelize_device(d_tris, mesh, gpv.Params(args.l1, args.l2, 0), sptr)
+            want = {"l1": w(ref.c.d_level1_inout, ref.cells), "prefix": w(ref.c.d_prefix, ref.cells * 4), "l2": w(ref.c.d_level2_inout, ref.nb * ref.n23)}
+            gather_ok = all(got[k].numel() == want[k].numel() and bool(torch.equal(got[k], want[k])) for k in want)
+            assert gather_ok, "gathered slabs differ from the single-GPU result"
+        barrier()
     ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device="cuda", dtype=torch.float64)
     tests_local = torch.tensor([res.stats["l2_box_tests"]], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -367,7 +397,7 @@ def main():
         line = {"metric": "G tri-box tests/s", "value": value, "unit": "G tri-box tests/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "ms_per_model": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "cessna.obj fixture (reference sample mesh)" if args.mesh == "cessna" else "synthetic",
-                "config": dict(workload_config(args), parallelism=("z-slabs x%d (cuts %s), Level-1 replicated, NCCL gather to rank 0" % (world, cuts)) if world > 1 else "1 GPU",
+                "config": dict(workload_config(args), parallelism=("z-slabs x%d (cuts %s), Level-1 replicated, %s; gathered streams == single-GPU result: %s" % (world, cuts, "slabs written into rank 0's buffers over NVLink peer memory from inside the kernels (GPV_GATHER), 8-byte count exchange through a mailbox, no collective" if peer else "NCCL send/recv gather to rank 0", gather_ok)) if world > 1 else "1 GPU",
                                tri_box_tests_per_model=int(tests), triangles=mesh.ntri, grid=[int(x) for x in res.num_div]),
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_rays": roof_rays, "roofline_hbm": roof_hbm,
                 "phase_ms": {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0},

@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GPVIEW_B200_LIB", os.path.join(HERE, "libgpview_b200.so"))  # override: A/B builds of the same ABI
 
-GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE = 1, 2, 4, 8
+GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE, GPV_GATHER = 1, 2, 4, 8, 16
 
 
 class GpvError(RuntimeError):
@@ -54,6 +54,11 @@ class CVoxelFile(C.Structure):
                 ("level2_inout", C.POINTER(C.c_uint8)), ("level2_normal", C.POINTER(C.c_uint8))]
 
 
+class CGatherDesc(C.Structure):
+    _fields_ = [("l1", C.c_ubyte * 64), ("prefix", C.c_ubyte * 64), ("l2", C.c_ubyte * 64), ("mailbox", C.c_ubyte * 64), ("cells_total", C.c_int64),
+                ("l2_capacity", C.c_int64), ("owner_device", C.c_int32), ("reserved", C.c_int32)]
+
+
 class CBatchStats(C.Structure):
     _fields_ = [("models_done", C.c_int64), ("models_failed", C.c_int64), ("models_skipped", C.c_int64), ("seconds", C.c_double),
                 ("parse_seconds", C.c_double), ("gpu_seconds", C.c_double), ("save_seconds", C.c_double)]
@@ -63,7 +68,8 @@ class CBatchStats(C.Structure):
 NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_stream", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh",
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
-                  "gpv_save", "gpv_load_voxels", "gpv_free_voxels", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak"]
+                  "gpv_save", "gpv_load_voxels", "gpv_free_voxels", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
+                  "gpv_gather_create", "gpv_gather_attach", "gpv_gather_attach_local", "gpv_gather_detach", "gpv_gather_result"]
 COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
 
 _lib = None
@@ -87,6 +93,7 @@ def lib():
         L.gpv_device_count.restype = C.c_int
         L.gpv_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.gpv_destroy.argtypes = [vp]; L.gpv_destroy.restype = None
+        L.gpv_stream.argtypes = [vp]; L.gpv_stream.restype = vp
         for n in ("gpv_load_obj", "gpv_load_off", "gpv_load_mesh"):
             getattr(L, n).argtypes = [C.c_char_p, C.POINTER(CMesh)]
         L.gpv_mesh_from_triangles.argtypes = [fp, C.c_int64, C.POINTER(CMesh)]
@@ -106,6 +113,11 @@ def lib():
                                          C.POINTER(CBatchStats)]
         L.gpv_measure_fp32_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         L.gpv_measure_copy_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
+        L.gpv_gather_create.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(CGatherDesc)]
+        L.gpv_gather_attach.argtypes = [vp, C.POINTER(CGatherDesc), C.c_int, C.c_int]
+        L.gpv_gather_attach_local.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.gpv_gather_detach.argtypes = [vp]; L.gpv_gather_detach.restype = None
+        L.gpv_gather_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 
@@ -262,6 +274,38 @@ class Context:
         r = CResult()
         _check(lib().gpv_voxelize_host(self.h, C.byref(mesh.c), C.byref(params.c), stream, C.byref(r), C.byref(host)))
         return Result(r, self)
+
+    def stream(self):
+        """The ctx's own non-blocking cudaStream_t (as a c_void_p) for callers that run several contexts side by side."""
+        return C.c_void_p(lib().gpv_stream(self.h))
+
+    # ---- multi-GPU gather over NVLink peer memory (gpv_gather_*)
+    def gather_create(self, cells_total, l2_capacity):
+        d = CGatherDesc()
+        _check(lib().gpv_gather_create(self.h, int(cells_total), int(l2_capacity), C.byref(d)))
+        return d
+
+    def gather_attach(self, desc, rank, world):
+        _check(lib().gpv_gather_attach(self.h, C.byref(desc), rank, world))
+
+    def gather_attach_local(self, owner, rank, world):
+        _check(lib().gpv_gather_attach_local(self.h, owner.h, rank, world))
+
+    def gather_detach(self):
+        lib().gpv_gather_detach(self.h)
+
+    def gather_result(self, cells_total, n23):
+        """Gathering rank: (level1_inout, prefix, level2_inout, n_boundary_total) copied to the host."""
+        l1, pre, l2, nb = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        _check(lib().gpv_gather_result(self.h, C.byref(l1), C.byref(pre), C.byref(l2), C.byref(nb)))
+        out = []
+        for ptr, n, dt in ((l1, cells_total, np.uint8), (pre, cells_total, np.int32), (l2, nb.value * n23, np.uint8)):
+            a = np.empty(int(n), dt)
+            if n:
+                _check(lib().gpv_memcpy_d2h(a.ctypes.data, ptr, a.nbytes, None))
+                _check(lib().gpv_stream_sync(None))
+            out.append(a)
+        return out[0], out[1], out[2], int(nb.value)
 
     def fp32_peak(self):
         v = C.c_double()

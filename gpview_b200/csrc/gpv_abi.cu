@@ -70,6 +70,15 @@ struct gpv_ctx {
 	cudaStream_t ownStream = nullptr;   // gpv_stream(): a non-blocking stream for callers that run several contexts side by side
 	cudaEvent_t evChunk[17] = {};
 	bool sortAttrSet = false;
+	// GPV_GATHER (gpv_gather_*): the gathering rank's whole-grid streams and mailbox, local or mapped over NVLink
+	struct {
+		bool on = false, owner = false, ipc = false;
+		int rank = 0, world = 1;
+		unsigned epoch = 0;
+		uint8_t* l1 = nullptr; int32_t* prefix = nullptr; uint8_t* l2 = nullptr; gpv::GatherMail* mail = nullptr;
+		int64_t cellsTotal = 0, l2Cap = 0, nbTotal = 0;
+	} gather;
+	gpv::DevBuf gatherL1, gatherPrefix, gatherL2, gatherMail;
 };
 
 using namespace gpv;
@@ -114,7 +123,8 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->longList, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->longList, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
+	gpv_gather_detach(c);
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
 	if (c->haveEvents) for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -187,6 +197,9 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	cudaStream_t st = (cudaStream_t)stream;
 	const bool wantL2 = !(prm->flags & GPV_NO_LEVEL2) && prm->voxel_count2 > 0;
 	const bool wantN = (prm->flags & GPV_NORMALS) != 0;
+	const bool gather = (prm->flags & GPV_GATHER) != 0;
+	if (gather && !c->gather.on) return fail("GPV_GATHER without gpv_gather_attach");
+	if (gather && (wantN || sink)) return fail("GPV_GATHER supports neither GPV_NORMALS nor the host-stream call");
 	if (gpv_make_grid(bmin, bmax, max_model_size, prm->voxel_count, wantL2 ? prm->voxel_count2 : 1, &out->grid)) return 1;
 	const gpv_grid& gg = out->grid;
 	if (gg.n2 > 32) return fail("voxel_count2 > 32 is not supported (Level-2 z parity is kept in one 32-bit word)");
@@ -204,6 +217,8 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	const long long cells = ncol * (g.z1 - g.z0);
 	if (ncol * g.nz > 0x7fffffffLL) return fail("grid exceeds 2^31 cells: boundary_index is int32 (file contract); shard finer");
 	if (g.nx > 32767 || g.ny > 32767 || g.nz > 32767) return fail("grid axis exceeds 32767 cells (footprints are packed in 16-bit fields)");
+	if (gather && ncol * g.nz != c->gather.cellsTotal) return fail("GPV_GATHER: the gather buffers were created for a different grid");
+	const unsigned epoch = gather ? ++c->gather.epoch : 0; // every rank counts its GPV_GATHER calls: same order on all ranks
 	const int nTri = (int)n_tri;
 	int64_t launches = 0;
 	const bool prof = (prm->flags & GPV_PROFILE) != 0;
@@ -300,7 +315,11 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	const long long n23 = (long long)g.n2 * g.n2 * g.n2;
 	if (c->cellTris.ensure((size_t)T1.triTotal * 4 + 32) || c->colTris.ensure((size_t)T1.colTotalOver * 4 + 32) || c->crossTri.ensure((size_t)T1.crossTotal * 4 + 32))
 		return 1;
-	if (wantL2 && (c->l2State.ensure((size_t)(nB * n23) + 32) || c->colCellList.ensure((size_t)nB * 8 + 32) || c->cellMid.ensure((size_t)nB * 16 + 32) || c->l2Par.ensure((size_t)nB * g.n2 * g.n2 * 4 + 32))) return 1;
+	if (gather) { // the one exchange step: boundary counts of the lower slabs (8 bytes per rank through the mailbox)
+		k_gather_exchange<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, wantL2 ? c->gather.l2Cap / n23 : (long long)0x7fffffff, dT);
+		launches++;
+	}
+	if (wantL2 && (c->l2State.ensure(gather ? 32 : (size_t)(nB * n23) + 32) || c->colCellList.ensure((size_t)nB * 8 + 32) || c->cellMid.ensure((size_t)nB * 16 + 32) || c->l2Par.ensure((size_t)nB * g.n2 * g.n2 * 4 + 32))) return 1;
 	if (wantN && (c->l1Normal.ensure((size_t)cells * 3 + 32) || (wantL2 && c->l2Normal.ensure((size_t)(nB * n23) * 3 + 32)))) return 1;
 
 	bo.prefix = c->prefix.as<int>(); bo.bTriOff = c->bTriOff.as<unsigned>(); bo.cellTris = c->cellTris.as<int>();
@@ -335,8 +354,12 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	{
 		dim3 grid((g.nx + 31) / 32, g.ny, (g.z1 - g.z0 + 127) / 128), block(32, 4);
 		k_fill_sweep<<<grid, block, 0, st>>>(ray48, g, cx, cy, cz, c->crossOff.as<unsigned>(), c->crossTri.as<int>(), c->bmask.as<unsigned char>(),
-		                                     c->l1State.as<unsigned char>(), dT);
+		                                     gather ? c->gather.l1 + (size_t)g.z0 * ncol : c->l1State.as<unsigned char>(), dT);
 		launches++;
+		if (gather) { // slab-local prefix sums + boundary cells of the lower slabs -> their final place on the gathering rank
+			k_gather_prefix<<<(unsigned)std::min<long long>(c->smCount * 8, (cells / 4 + 255) / 256 + 1), 256, 0, st>>>(c->prefix.as<int>(), c->gather.prefix + (size_t)g.z0 * ncol, cells, dT);
+			launches++;
+		}
 	}
 	mark(GPV_PHASE_L1_NORMALS);
 	if (wantN) {
@@ -362,7 +385,8 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	if (wantL2 && nB > 0) {
 		lio.tri48 = tri48; lio.ray48 = ray48; lio.plane16 = c->plane16.as<float4>(); lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
 		lio.cellTris = c->cellTris.as<int>(); lio.colOff = c->colOff.as<unsigned>(); lio.colCount = c->colCount.as<int>(); lio.colTris = c->colTris.as<int>();
-		lio.cx = cx; lio.cy = cy; lio.cz = cz; lio.l2State = c->l2State.as<unsigned char>(); lio.nBoundary = (int)nB; lio.totals = dT;
+		lio.cx = cx; lio.cy = cy; lio.cz = cz; lio.nBoundary = (int)nB; lio.totals = dT;
+		lio.l2State = gather ? c->gather.l2 : c->l2State.as<unsigned char>(); lio.l2Base = gather ? &dT->gatherBase : nullptr;
 		lio.colCellOff = c->colCellOff.as<unsigned>(); lio.colCellList = c->colCellList.as<int2>(); lio.l2Par = c->l2Par.as<unsigned>(); lio.cellMid = c->cellMid.as<float4>();
 		const L2K K = l2_constants(g.n2);
 		const int G = K.G;
@@ -400,19 +424,31 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			if (sink && sink->level2_normal) GPV_CUDA(cudaMemcpyAsync(sink->level2_normal, c->l2Normal.p, (size_t)(nB * n23) * 3, cudaMemcpyDeviceToHost, st));
 		}
 	}
+	if (gather) { // completion flag behind this rank's last store; the gathering rank returns when every rank has signalled
+		k_gather_done<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch);
+		launches++;
+		if (c->gather.rank == 0) { k_gather_wait<<<1, 1, 0, st>>>(c->gather.mail, c->gather.world, epoch, dT); launches++; }
+	}
 	mark(GPV_PHASE_COUNT);
 	GPV_CUDA(cudaMemcpyAsync(c->hTotals, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
 	GPV_CUDA(cudaStreamSynchronize(st));
 	if (sink) GPV_CUDA(cudaStreamSynchronize(c->copyStream));
 	GPV_CUDA(cudaGetLastError());
 	const Totals T2 = *c->hTotals;
+	if (gather && T2.gatherError) return fail(T2.gatherError == 1 ? "GPV_GATHER: Level-2 gather buffer too small for the boundary cells of all slabs" : "GPV_GATHER: timed out waiting for a peer rank");
+	if (gather && c->gather.rank == 0) { // total boundary count: the mailbox holds every slab's count of this epoch
+		GatherMail hm;
+		GPV_CUDA(cudaMemcpy(&hm, c->gather.mail, sizeof hm, cudaMemcpyDeviceToHost));
+		c->gather.nbTotal = 0;
+		for (int q = 0; q < c->gather.world; q++) c->gather.nbTotal += (unsigned)hm.count[epoch & 1][q];
+	}
 
 	out->z0 = g.z0; out->z1 = g.z1;
 	out->cells = cells; out->n_boundary = nB; out->n23 = n23;
-	out->d_level1_inout = c->l1State.as<uint8_t>();
-	out->d_prefix = c->prefix.as<int32_t>();
+	out->d_level1_inout = gather ? c->gather.l1 + (size_t)g.z0 * ncol : c->l1State.as<uint8_t>(); // gather: this slab's bytes where they landed
+	out->d_prefix = c->prefix.as<int32_t>();                                                          // always the slab-local sums
 	out->d_boundary_index = c->boundaryIndex.as<int32_t>();
-	out->d_level2_inout = wantL2 ? c->l2State.as<uint8_t>() : nullptr;
+	out->d_level2_inout = !wantL2 ? nullptr : gather ? c->gather.l2 + (size_t)T2.gatherBase * n23 : c->l2State.as<uint8_t>();
 	out->d_level1_normal = wantN ? c->l1Normal.as<uint8_t>() : nullptr;
 	out->d_level2_normal = (wantN && wantL2) ? c->l2Normal.as<uint8_t>() : nullptr;
 	out->d_cell_off = c->bTriOff.as<uint32_t>(); out->d_cell_tris = c->cellTris.as<int32_t>();
@@ -453,6 +489,91 @@ extern "C" int gpv_voxelize_host(gpv_ctx* c, const gpv_mesh* mesh, const gpv_par
 	// every stream goes to the host from inside the pipeline (Level-1 streams during Level-2, Level-2 chunk by chunk)
 	if (voxelize_impl(c, c->scratch.as<float>(), mesh->n_tri, mesh->bbox_min, mesh->bbox_max, mesh->max_model_size, prm, stream, out, h)) return 1;
 	GPV_CUDA(cudaStreamSynchronize(st));
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ gather over peer memory
+extern "C" void gpv_gather_detach(gpv_ctx* c)
+{
+	if (!c || !c->gather.on) return;
+	cudaSetDevice(c->device);
+	if (c->gather.ipc) {
+		cudaIpcCloseMemHandle(c->gather.l1); cudaIpcCloseMemHandle(c->gather.prefix); cudaIpcCloseMemHandle(c->gather.l2); cudaIpcCloseMemHandle(c->gather.mail);
+	}
+	c->gather = {};
+}
+
+extern "C" int gpv_gather_create(gpv_ctx* c, int64_t cells_total, int64_t l2_capacity, gpv_gather_desc* out)
+{
+	if (!c || !out || cells_total <= 0 || l2_capacity < 0) return fail("gpv_gather_create: bad argument");
+	GPV_CUDA(cudaSetDevice(c->device));
+	if (c->gatherL1.ensure((size_t)cells_total + 64) || c->gatherPrefix.ensure((size_t)cells_total * 4 + 64) || c->gatherL2.ensure((size_t)l2_capacity + 64) ||
+	    c->gatherMail.ensure(sizeof(GatherMail)))
+		return 1;
+	GPV_CUDA(cudaMemset(c->gatherMail.p, 0, sizeof(GatherMail)));
+	memset(out, 0, sizeof *out);
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "gpv_gather_desc carries 64-byte IPC handles");
+	cudaIpcMemHandle_t h;
+	GPV_CUDA(cudaIpcGetMemHandle(&h, c->gatherL1.p)); memcpy(out->l1, &h, 64);
+	GPV_CUDA(cudaIpcGetMemHandle(&h, c->gatherPrefix.p)); memcpy(out->prefix, &h, 64);
+	GPV_CUDA(cudaIpcGetMemHandle(&h, c->gatherL2.p)); memcpy(out->l2, &h, 64);
+	GPV_CUDA(cudaIpcGetMemHandle(&h, c->gatherMail.p)); memcpy(out->mailbox, &h, 64);
+	out->cells_total = cells_total; out->l2_capacity = l2_capacity; out->owner_device = c->device;
+	c->gather = {};
+	c->gather.owner = true; c->gather.cellsTotal = cells_total; c->gather.l2Cap = l2_capacity;
+	return 0;
+}
+
+static int gather_bind(gpv_ctx* c, void* l1, void* prefix, void* l2, void* mail, int64_t cellsTotal, int64_t l2Cap, int rank, int world, bool ipc)
+{
+	if (rank < 0 || world < 1 || rank >= world || world > 16) return fail("gpv_gather_attach: bad rank / world (at most 16 ranks)");
+	c->gather.on = true; c->gather.ipc = ipc; c->gather.rank = rank; c->gather.world = world; c->gather.epoch = 0;
+	c->gather.l1 = (uint8_t*)l1; c->gather.prefix = (int32_t*)prefix; c->gather.l2 = (uint8_t*)l2; c->gather.mail = (GatherMail*)mail;
+	c->gather.cellsTotal = cellsTotal; c->gather.l2Cap = l2Cap;
+	return 0;
+}
+
+extern "C" int gpv_gather_attach(gpv_ctx* c, const gpv_gather_desc* d, int rank, int world)
+{
+	if (!c || !d) return fail("gpv_gather_attach: null argument");
+	GPV_CUDA(cudaSetDevice(c->device));
+	if (c->gather.owner) { // the gathering rank uses its own allocations
+		if (rank != 0) return fail("gpv_gather_attach: the ctx that created the gather buffers is rank 0");
+		return gather_bind(c, c->gatherL1.p, c->gatherPrefix.p, c->gatherL2.p, c->gatherMail.p, d->cells_total, d->l2_capacity, rank, world, false);
+	}
+	void* p[4] = {};
+	const unsigned char* hs[4] = { d->l1, d->prefix, d->l2, d->mailbox };
+	for (int k = 0; k < 4; k++) {
+		cudaIpcMemHandle_t h;
+		memcpy(&h, hs[k], 64);
+		GPV_CUDA(cudaIpcOpenMemHandle(&p[k], h, cudaIpcMemLazyEnablePeerAccess));
+	}
+	return gather_bind(c, p[0], p[1], p[2], p[3], d->cells_total, d->l2_capacity, rank, world, true);
+}
+
+extern "C" int gpv_gather_attach_local(gpv_ctx* c, gpv_ctx* owner, int rank, int world)
+{
+	if (!c || !owner || !owner->gather.owner) return fail("gpv_gather_attach_local: the owner ctx has no gather buffers");
+	GPV_CUDA(cudaSetDevice(c->device));
+	if (c->device != owner->device) {
+		cudaError_t e = cudaDeviceEnablePeerAccess(owner->device, 0);
+		if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+		cudaGetLastError();
+	}
+	const bool own = c == owner;
+	if (own && rank != 0) return fail("gpv_gather_attach_local: the owner is rank 0");
+	const int64_t cellsTotal = owner->gather.cellsTotal, l2Cap = owner->gather.l2Cap;
+	if (!own) c->gather = {};
+	return gather_bind(c, owner->gatherL1.p, owner->gatherPrefix.p, owner->gatherL2.p, owner->gatherMail.p, cellsTotal, l2Cap, rank, world, false);
+}
+
+extern "C" int gpv_gather_result(gpv_ctx* c, uint8_t** l1, int32_t** prefix, uint8_t** l2, int64_t* nb)
+{
+	if (!c || !c->gather.on || c->gather.rank != 0) return fail("gpv_gather_result: not the gathering rank");
+	if (l1) *l1 = c->gather.l1;
+	if (prefix) *prefix = c->gather.prefix;
+	if (l2) *l2 = c->gather.l2;
+	if (nb) *nb = c->gather.nbTotal;
 	return 0;
 }
 

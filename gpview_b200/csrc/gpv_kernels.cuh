@@ -35,8 +35,9 @@ struct Totals {
 	unsigned long long binWork, crossWork; // totals of the two balanced work spaces (exclusive scans of binCnt / crossCnt)
 	unsigned long long l1Hits, crossPairs, nIll, l1Inside, l2Inside, l2Boundary;
 	unsigned long long l2ColPairs; // sum over boundary cells of their column-list length (reference-equivalent Level-2 ray tests / n2^3)
+	long long gatherBase;          // GPV_GATHER: boundary cells of the lower slabs (k_gather_exchange); -1 = exchange failed
+	unsigned long long gatherError; // 1 capacity exceeded, 2 timed out waiting for a peer
 	unsigned int nBoundary, triTotal, colTotalOver, crossTotal;
-	unsigned int nBoundaryCols, pad0, pad1, pad2; // Level-1 columns that hold boundary cells (size of the Level-2 crossing lists)
 };
 
 constexpr int kWorkThreads = 128;                        // threads per CTA of the balanced triangle-work kernels
@@ -681,7 +682,8 @@ struct L2IO {
 	unsigned* l2Par;                                    // [boundary rank][n2*n2] parity bits along z of every sub-voxel column (k_l2_rays)
 	const float4* cellMid;                              // [boundary rank] centre of the Level-1 cell (k_col_cells)
 	const float* cx; const float* cy; const float* cz;
-	unsigned char* l2State; // nBoundary * n2^3 file bytes
+	unsigned char* l2State; // nBoundary * n2^3 file bytes (local, or the gathering rank's buffer over NVLink)
+	const long long* l2Base; // gather: boundary cells of the lower slabs (device-resident, k_gather_exchange); null = 0
 	int bBegin;             // this launch refines boundary ranks [bBegin, nBoundary)
 	int nBoundary;
 	Totals* totals;
@@ -886,7 +888,7 @@ inline L2K l2_constants(int n2)
 // the parity kernel's result).  A CTA of 256 threads refines G = max(1, 256/n2^2) boundary cells; an item is one sub-voxel
 // COLUMN (cell, p, q) -- the same unit k_l2_rays works on, so the SAT bits and the parity bits of a column share one word
 // layout (bit r = sub-voxel r) and no transposition is needed.  Everything of the SAT that does not involve z is hoisted
-// per (column, triangle) (gpv::SatCol).  A warp's byte stores cover 32 consecutive sub-voxels of Level2InOut.raw.
+// per (column, triangle) (gpv::SatCol).  The CTA's block of Level2InOut.raw is assembled in shared memory and stored 128 bits per thread.
 // N2 > 0: n2 fixed at compile time (2, 4, 8, 16: index arithmetic by shifts, unrolled byte loop); N2 = 0: any n2 <= 32.
 template <int N2>
 __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2IO io, L2K K)
@@ -1034,7 +1036,12 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	}
 	__syncthreads();
 
-	// ---- the column's file bytes: SAT hit 254, else inside 127, else 0 (2 overwrites 1: src/Object.cpp:2603-2606)
+	// ---- the file bytes: SAT hit 254, else inside 127, else 0 (2 overwrites 1: src/Object.cpp:2603-2606).  Every thread
+	// expands its column into the CTA's block of Level2InOut.raw staged in shared memory (the queue area, idle now; the cells of
+	// a CTA are consecutive boundary ranks, so the block is contiguous in the file); the block then leaves as 128-bit
+	// coalesced stores -- to local HBM, or over NVLink into the gathering rank's buffer (gpv_gather_*).
+	unsigned char* sOut = smemRaw + K.q1;
+	const int n23 = rows * n2;
 	unsigned nIn = 0, nBd = 0;
 	for (int item = tid; item < nItems; item += kL2Threads) {
 		const int gi = div_rows(item), pq = item - gi * rows;
@@ -1043,18 +1050,107 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 		const unsigned sat = sSat[item];
 		const unsigned par = io.l2Par[(size_t)b * rows + pq] & ~sat;
 		nIn += __popc(par); nBd += __popc(sat);
-		unsigned char* out = io.l2State + ((size_t)b * rows * n2 + pq);
+		unsigned char* o = sOut + gi * n23 + pq;
 		int r = 0;
 		for (; r + 4 <= n2; r += 4) {
 			// four sub-voxels at once: (nibble * 0x204081) & 0x01010101 spreads bit k of the nibble to byte k
 			const unsigned w = (((par >> r) & 15u) * 0x204081u & 0x01010101u) * 127u + (((sat >> r) & 15u) * 0x204081u & 0x01010101u) * 254u;
-			out[(size_t)r * rows] = (unsigned char)w; out[(size_t)(r + 1) * rows] = (unsigned char)(w >> 8);
-			out[(size_t)(r + 2) * rows] = (unsigned char)(w >> 16); out[(size_t)(r + 3) * rows] = (unsigned char)(w >> 24);
+			o[r * rows] = (unsigned char)w; o[(r + 1) * rows] = (unsigned char)(w >> 8);
+			o[(r + 2) * rows] = (unsigned char)(w >> 16); o[(r + 3) * rows] = (unsigned char)(w >> 24);
 		}
-		for (; r < n2; r++) out[(size_t)r * rows] = ((sat >> r) & 1) ? 254 : (((par >> r) & 1) ? 127 : 0);
+		for (; r < n2; r++) o[r * rows] = ((sat >> r) & 1) ? 254 : (((par >> r) & 1) ? 127 : 0);
+	}
+	__syncthreads();
+	{
+		const long long nValid = min((long long)G, (long long)io.nBoundary - b0);
+		const long long gbase = io.l2Base ? *io.l2Base : 0ll; // gather: boundary cells of the lower slabs; < 0 = exchange failed, write nothing
+		const int total = (gbase < 0 || nValid <= 0) ? 0 : (int)nValid * n23;
+		unsigned char* out = io.l2State + (size_t)(gbase + b0) * n23;
+		const int vec = ((reinterpret_cast<size_t>(out) & 15) == 0) ? (total & ~15) : 0;
+		for (int i = tid * 16; i < vec; i += kL2Threads * 16) *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(sOut + i);
+		for (int i = vec + tid; i < total; i += kL2Threads) out[i] = sOut[i];
 	}
 	nIn = __reduce_add_sync(0xffffffffu, nIn); nBd = __reduce_add_sync(0xffffffffu, nBd);
 	if (lane == 0 && (nIn | nBd)) { atomicAdd(&io.totals->l2Inside, (unsigned long long)nIn); atomicAdd(&io.totals->l2Boundary, (unsigned long long)nBd); }
+}
+
+// ------------------------------------------------------------------------------------------------ gather over peer memory
+// Multi-GPU: every rank writes its slab's streams straight into the gathering rank's buffers over NVLink peer
+// memory.  The only data the ranks exchange is 8 bytes each: the slab's boundary-cell count, posted in a mailbox in the
+// gathering rank's memory; rank r adds up the counts of the lower slabs -- that fixes the offset of its Level-2 blocks and the
+// constant that makes its prefix sums global.  A second flag per rank signals completion.  Flags are tagged with the call's
+// epoch; the count slots are double-buffered by epoch parity (a rank can run at most one call ahead of a slower one: every
+// rank's next exchange needs rank 0's count, and rank 0 starts its next call only after all ranks signalled completion).
+struct GatherMail { unsigned long long count[2][16]; unsigned long long done[16]; };
+constexpr unsigned long long kGatherTimeoutNs = 5000000000ull; // a missing peer must not hang the GPU
+
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+// <<<1, 1>>> after the size read-back: post this slab's boundary count, collect the lower slabs'
+__global__ void k_gather_exchange(GatherMail* mail, int rank, unsigned epoch, long long capCells, Totals* totals)
+{
+	const unsigned nB = totals->nBoundary;
+	st_sys(&mail->count[epoch & 1][rank], ((unsigned long long)epoch << 32) | nB);
+	long long base = 0;
+	const unsigned long long t0 = global_ns();
+	for (int q = 0; q < rank && base >= 0; q++) {
+		unsigned long long v;
+		do {
+			v = ld_sys(&mail->count[epoch & 1][q]);
+			if ((unsigned)(v >> 32) != epoch && global_ns() - t0 > kGatherTimeoutNs) { totals->gatherError = 2; base = -1; break; }
+		} while ((unsigned)(v >> 32) != epoch);
+		if (base >= 0) base += (unsigned)v;
+	}
+	if (base >= 0 && base + nB > capCells) { totals->gatherError = 1; base = -1; }
+	totals->gatherBase = base;
+}
+
+// slab-local prefix sums -> global, written at their final place in the gathering rank's Level1BoundaryPrefixSum stream
+__global__ void __launch_bounds__(256) k_gather_prefix(const int* __restrict__ local, int* out, long long n, const Totals* totals)
+{
+	const long long base = totals->gatherBase;
+	if (base < 0) return;
+	const int add = (int)base;
+	const long long n4 = ((reinterpret_cast<size_t>(out) & 15) == 0 && (reinterpret_cast<size_t>(local) & 15) == 0) ? n / 4 : 0;
+	for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+		int4 v = reinterpret_cast<const int4*>(local)[i];
+		v.x += add; v.y += add; v.z += add; v.w += add;
+		reinterpret_cast<int4*>(out)[i] = v;
+	}
+	for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = local[i] + add;
+}
+
+// <<<1, 1>>> behind the last kernel of the call: everything this rank wrote to the gathering rank is ordered before the flag
+__global__ void k_gather_done(GatherMail* mail, int rank, unsigned epoch)
+{
+	__threadfence_system();
+	st_sys(&mail->done[rank], (unsigned long long)epoch);
+}
+
+// <<<1, 1>>> on the gathering rank: returns when every rank has signalled completion of this epoch
+__global__ void k_gather_wait(GatherMail* mail, int world, unsigned epoch, Totals* totals)
+{
+	const unsigned long long t0 = global_ns();
+	for (int q = 0; q < world; q++) {
+		while (ld_sys(&mail->done[q]) < (unsigned long long)epoch) {
+			if (global_ns() - t0 > kGatherTimeoutNs) { totals->gatherError = 2; return; }
+		}
+	}
 }
 
 // ------------------------------------------------------------------------------------------------ normals

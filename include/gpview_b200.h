@@ -71,6 +71,7 @@ typedef struct {
 #define GPV_NO_LEVEL2    2     /* GLParameters::level2Voxels == false */
 #define GPV_KEEP_LISTS   4     /* keep CSR cell lists / column lists readable after the call (gpv_result list pointers) */
 #define GPV_PROFILE      8     /* record a CUDA event pair around every kernel of the pipeline -> gpv_result.phase_ms */
+#define GPV_GATHER      16     /* multi-GPU: write this slab's streams straight into the gathering rank's buffers (gpv_gather_*) */
 
 typedef struct {
 	int voxel_count;           /* GLParameters::voxelCount  (Level-1 cells along the longest axis; reference default 8) */
@@ -157,6 +158,29 @@ int gpv_voxelize_device(gpv_ctx* ctx, const float* d_tris, int64_t n_tri, const 
 /* same, from HOST triangles into HOST streams: H2D + pipeline + D2H (the reference-facing call: what
  * Object::PerformVoxelization does between CreateFlatTriangleData and SaveVoxelization) */
 int gpv_voxelize_host(gpv_ctx* ctx, const gpv_mesh* mesh, const gpv_params* params, void* stream, gpv_result* out, gpv_host_streams* host);
+
+/* ---- multi-GPU gather over NVLink peer memory (one process per GPU, one ctx per process).
+ * The gathering rank (rank 0) allocates the whole-grid streams once and exports them as CUDA IPC handles; every other rank maps
+ * them (peer access over NVLink / NVSwitch).  A call with GPV_GATHER then writes its slab's Level1InOut bytes, its globalised
+ * prefix sums and its Level-2 blocks directly at their final offsets in rank 0's memory from inside the kernels that produce
+ * them -- there is no separate collective.  The one exchange step of the path (boundary counts of the lower slabs, which fix
+ * every Level-2 offset) and the completion signal are 8-byte flags in a mailbox in rank 0's memory, written and polled by
+ * one-thread kernels on the callers' streams; all ranks must issue their GPV_GATHER calls in the same order.
+ * gpv_gather_desc is plain bytes: ship it to the other ranks with any transport (torch.distributed broadcast, a file, a pipe).
+ * GPV_NORMALS is not supported together with GPV_GATHER. */
+typedef struct {
+	unsigned char l1[64], prefix[64], l2[64], mailbox[64];   /* cudaIpcMemHandle_t of the four allocations */
+	int64_t cells_total;                                     /* nx*ny*nz of the grid the buffers were sized for */
+	int64_t l2_capacity;                                     /* bytes behind l2 */
+	int32_t owner_device, reserved;
+} gpv_gather_desc;
+int gpv_gather_create(gpv_ctx* ctx, int64_t cells_total, int64_t l2_capacity, gpv_gather_desc* out);      /* gathering rank only */
+int gpv_gather_attach(gpv_ctx* ctx, const gpv_gather_desc* desc, int rank, int world);                    /* every rank, the gathering one included */
+int gpv_gather_attach_local(gpv_ctx* ctx, gpv_ctx* owner, int rank, int world);                           /* same-process ranks (tests, several GPUs in one process) */
+void gpv_gather_detach(gpv_ctx* ctx);
+/* gathering rank, after its own GPV_GATHER call returned (it returns once every rank has signalled completion): device views of
+ * the whole-grid streams and the total boundary count */
+int gpv_gather_result(gpv_ctx* ctx, uint8_t** d_level1_inout, int32_t** d_prefix, uint8_t** d_level2_inout, int64_t* n_boundary_total);
 
 /* Object::SaveVoxelization (src/Object.cpp:2934-3075): the six ObjN*.{txt,raw} files into `dir` from host streams */
 int gpv_save(const gpv_mesh* mesh, const gpv_result* res, const gpv_host_streams* host, int obj_id, const char* dir);

@@ -192,3 +192,50 @@ def test_hostile_triangle_soups_match_brute_force_oracle(product, oracle, ctx, t
     assert np.array_equal(res.cell_tris(), want.cell_tris)
     assert np.array_equal(res.level1_normal(), want.l1_normal)
     assert np.array_equal(res.level2_normal(), want.l2_normal)
+
+
+@pytest.mark.parametrize("name,l1,l2,R", [("cessna", 64, 4, 3), ("torus", 32, 4, 2), ("cessna", 128, 8, 4)])
+def test_peer_memory_gather_equals_whole(product, ctx, tmp_path_factory, name, l1, l2, R):
+    """GPV_GATHER: R ranks -- here R contexts of one process on one device, each on its own thread and stream --
+    write their z-slabs straight into rank 0's whole-grid streams (Level-1 bytes from the fill sweep, prefix sums globalised
+    by the exchanged boundary counts, Level-2 blocks from k_l2 at their final offsets).  Rank 0's buffers must equal the
+    single-call result byte for byte; run twice to exercise the epoch / double-buffered mailbox."""
+    import threading
+    path = mesh_path(name, tmp_path_factory.getbasetemp())
+    mesh = product.load_mesh(path)
+    whole = ctx.voxelize(mesh, product.Params(l1, l2, 0))
+    w_l1, w_pre, w_l2 = whole.level1_inout(), whole.prefix(), whole.level2_inout()
+    nz, cells, n23 = int(whole.num_div[2]), whole.cells, whole.n23
+    ranks = [product.Context(0) for _ in range(R)]
+    try:
+        ranks[0].gather_create(cells, whole.nb * n23)
+        for r in range(R):
+            ranks[r].gather_attach_local(ranks[0], r, R)
+        cuts = [nz * r // R for r in range(R + 1)]
+        for rep in range(2):
+            errs = []
+
+            def work(r):
+                try:
+                    d = ranks[r].upload(mesh)
+                    ranks[r].voxelize_device(d, mesh, product.Params(l1, l2, product.GPV_GATHER, cuts[r], cuts[r + 1]), ranks[r].stream())
+                    ranks[r].free_device(d)
+                except Exception as e:  # noqa: BLE001
+                    errs.append((r, repr(e)))
+            th = [threading.Thread(target=work, args=(r,)) for r in range(R)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            assert not errs, errs
+            g_l1, g_pre, g_l2, nb = ranks[0].gather_result(cells, n23)
+            assert nb == whole.nb
+            assert np.array_equal(g_l1, w_l1), (rep, "l1")
+            assert np.array_equal(g_pre, w_pre), (rep, "prefix")
+            assert np.array_equal(g_l2, w_l2), (rep, "l2")
+        # without an attached gather the flag is refused, not ignored
+        with pytest.raises(product.GpvError):
+            ctx.voxelize(mesh, product.Params(l1, l2, product.GPV_GATHER))
+    finally:
+        for c in ranks:
+            c.close()
