@@ -252,6 +252,26 @@ def main():
     for _ in range(args.warmup):
         res = step()
     barrier()
+    if world > 1:
+        # Untimed load balancing: the a-priori cost model only knows list lengths.  Rescale every slab's layer costs to the Level-2
+        # time its rank measured, re-cut, repeat; every rank derives the same cuts from the all-gathered times (no data moves).
+        layer = sharded.layer_cost(whole.boundary_index(), whole.cell_off(), plane, nz).astype(np.float64) + 1e-9
+        for _ in range(4):
+            t_mine = torch.tensor([res.phase_ms.get("l2_rays", 0.0) + res.phase_ms.get("l2", 0.0)], device="cuda", dtype=torch.float64)
+            t_all = torch.zeros(world, device="cuda", dtype=torch.float64)
+            dist.all_gather_into_tensor(t_all, t_mine)
+            t_all = t_all.cpu().numpy()
+            if t_all.max() < 1.08 * t_all.mean():
+                break
+            for r in range(world):
+                sl = slice(cuts[r], cuts[r + 1])
+                layer[sl] *= max(t_all[r], 1e-6) / layer[sl].sum()
+            cuts = sharded.plan_slabs(layer, world)
+            params.c.z0, params.c.z1 = cuts[rank], cuts[rank + 1]
+            z0, z1 = cuts[rank], cuts[rank + 1]
+            for _ in range(2):
+                res = step()
+            barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches, phase_acc = 0, {}
     t_timed0 = time.perf_counter()
