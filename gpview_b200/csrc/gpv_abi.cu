@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -64,10 +65,12 @@ struct gpv_ctx {
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
 	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, longList, colCellCnt, colCellOff, colCellList, l2Par, cellMid;
 	gpv::Totals* hTotals = nullptr; // pinned
-	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {};
+	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {}, evEnd[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
 	cudaStream_t copyStream = nullptr;  // D2H of finished streams overlaps the rest of the pipeline (gpv_voxelize_host)
 	cudaStream_t ownStream = nullptr;   // gpv_stream(): a non-blocking stream for callers that run several contexts side by side
+	cudaStream_t sideStream = nullptr;  // the parity-fill branch of the Level-1 pipeline runs beside the binning / sorting branch
+	cudaEvent_t evFork[2] = {}, evJoin[2] = {};
 	cudaEvent_t evChunk[17] = {};
 	bool sortAttrSet = false;
 	// GPV_GATHER (gpv_gather_*): the gathering rank's whole-grid streams and mailbox, local or mapped over NVLink
@@ -92,6 +95,24 @@ extern "C" int gpv_device_count(void)
 	return n;
 }
 
+// CUDA loads kernels lazily, and loading one synchronises the context.  With GPV_GATHER a rank's one-thread polling kernel may be
+// running while another context of the same process launches a kernel for the first time -- the load would wait for the poll,
+// the poll for that rank.  So every kernel of the pipeline is loaded when the first context of a device is created.
+static int preload_kernels()
+{
+	cudaFuncAttributes a;
+#define GPV_LOAD(...) GPV_CUDA(cudaFuncGetAttributes(&a, __VA_ARGS__))
+	GPV_LOAD(k_clear); GPV_LOAD(k_prepare); GPV_LOAD(k_scan_offs3); GPV_LOAD(k_scan<MODE_CELLS>); GPV_LOAD(k_scan<MODE_OFFS>);
+	GPV_LOAD(k_bin<false>); GPV_LOAD(k_bin<true>); GPV_LOAD(k_cross<false>); GPV_LOAD(k_cross<true>); GPV_LOAD(k_fill_sweep);
+	GPV_LOAD(k_sort_segments<false>); GPV_LOAD(k_sort_segments<true>); GPV_LOAD(k_sort_long<false>); GPV_LOAD(k_sort_long<true>);
+	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals);
+	GPV_LOAD(k_l2<16, false>); GPV_LOAD(k_l2<8, false>); GPV_LOAD(k_l2<4, false>); GPV_LOAD(k_l2<2, false>); GPV_LOAD(k_l2<0, false>);
+	GPV_LOAD(k_l2<16, true>); GPV_LOAD(k_l2<8, true>); GPV_LOAD(k_l2<4, true>); GPV_LOAD(k_l2<2, true>); GPV_LOAD(k_l2<0, true>);
+	GPV_LOAD(k_gather_exchange); GPV_LOAD(k_gather_prefix); GPV_LOAD(k_gather_done); GPV_LOAD(k_gather_wait);
+#undef GPV_LOAD
+	return 0;
+}
+
 extern "C" int gpv_create(int device, gpv_ctx** out)
 {
 	*out = nullptr;
@@ -104,6 +125,12 @@ extern "C" int gpv_create(int device, gpv_ctx** out)
 	GPV_CUDA(cudaGetDeviceProperties(&prop, device));
 	if (prop.major != 10) return fail(std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
 	                                  "; libgpview_b200 carries sm_100a code only");
+	{
+		static std::mutex mu;
+		static bool loaded[64] = {};
+		std::lock_guard<std::mutex> lock(mu);
+		if (device < 64 && !loaded[device]) { if (preload_kernels()) return 1; loaded[device] = true; }
+	}
 	gpv_ctx* c = new gpv_ctx();
 	c->device = device;
 	c->smCount = prop.multiProcessorCount;
@@ -112,6 +139,8 @@ extern "C" int gpv_create(int device, gpv_ctx** out)
 	if (c->totals.ensure(256)) { delete c; return 1; }
 	GPV_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
 	GPV_CUDA(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+	GPV_CUDA(cudaStreamCreateWithFlags(&c->sideStream, cudaStreamNonBlocking));
+	for (int k = 0; k < 2; k++) { GPV_CUDA(cudaEventCreateWithFlags(&c->evFork[k], cudaEventDisableTiming)); GPV_CUDA(cudaEventCreateWithFlags(&c->evJoin[k], cudaEventDisableTiming)); }
 	for (cudaEvent_t& e : c->evChunk) GPV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	*out = c;
 	return 0;
@@ -127,7 +156,9 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	gpv_gather_detach(c);
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
-	if (c->haveEvents) for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+	if (c->haveEvents) { for (cudaEvent_t e : c->ev) cudaEventDestroy(e); for (cudaEvent_t e : c->evEnd) cudaEventDestroy(e); }
+	for (int k = 0; k < 2; k++) { if (c->evFork[k]) cudaEventDestroy(c->evFork[k]); if (c->evJoin[k]) cudaEventDestroy(c->evJoin[k]); }
+	if (c->sideStream) cudaStreamDestroy(c->sideStream);
 	for (cudaEvent_t e : c->evChunk) if (e) cudaEventDestroy(e);
 	if (c->copyStream) cudaStreamDestroy(c->copyStream);
 	if (c->ownStream) cudaStreamDestroy(c->ownStream);
@@ -224,11 +255,15 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	const bool prof = (prm->flags & GPV_PROFILE) != 0;
 	if (prof && !c->haveEvents) {
 		for (cudaEvent_t& e : c->ev) GPV_CUDA(cudaEventCreate(&e));
+		for (cudaEvent_t& e : c->evEnd) GPV_CUDA(cudaEventCreate(&e));
 		c->haveEvents = true;
 	}
 	// phase boundaries: ev[k] is recorded when phase k starts, ev[GPV_PHASE_COUNT] when the last one ends
-	bool marked[GPV_PHASE_COUNT + 1] = {};
+	// (phases of the side branch carry their own end event: they overlap the main branch)
+	bool marked[GPV_PHASE_COUNT + 1] = {}, sidePhase[GPV_PHASE_COUNT + 1] = {};
+	cudaStream_t side = c->sideStream;
 	auto mark = [&](int phase) { if (prof) { cudaEventRecord(c->ev[phase], st); marked[phase] = true; } };
+	auto mark_side = [&](int phase, bool begin) { if (prof) { cudaEventRecord(begin ? c->ev[phase] : c->evEnd[phase], side); marked[phase] = sidePhase[phase] = true; } };
 
 	// ---- fixed-size buffers
 	if (c->tri48.ensure((size_t)nTri * 48) || c->ray48.ensure((size_t)nTri * 48) || c->tabX.ensure((size_t)g.nx * 4) || c->tabY.ensure((size_t)g.ny * 4) ||
@@ -279,10 +314,15 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	}
 	BinOut bo{};
 	bo.cellCount = c->cellCount.as<int>(); bo.colCount = c->colCount.as<int>(); bo.totals = dT;
+	// the two count sweeps are independent: the crossing count runs on the side stream beside the SAT count and the cell scan
+	GPV_CUDA(cudaEventRecord(c->evFork[0], st));
+	GPV_CUDA(cudaStreamWaitEvent(side, c->evFork[0], 0));
+	mark_side(GPV_PHASE_CROSS_COUNT, true);
+	k_cross<false><<<kWorkGrid, kWorkThreads, 0, side>>>(ray48, c->crossFp.as<int4>(), nTri, c->crossWorkOff.as<unsigned>(), g, cx, cy, c->crossCount.as<int>(), nullptr, nullptr, dT);
+	mark_side(GPV_PHASE_CROSS_COUNT, false);
+	GPV_CUDA(cudaEventRecord(c->evJoin[0], side));
 	mark(GPV_PHASE_BIN_COUNT);
 	k_bin<false><<<kWorkGrid, kWorkThreads, 0, st>>>(tri48, nTri, c->binOff.as<unsigned>(), g, cx, cy, cz, bo);
-	mark(GPV_PHASE_CROSS_COUNT);
-	k_cross<false><<<kWorkGrid, kWorkThreads, 0, st>>>(ray48, c->crossFp.as<int4>(), nTri, c->crossWorkOff.as<unsigned>(), g, cx, cy, c->crossCount.as<int>(), nullptr, nullptr, dT);
 	launches += 2;
 	mark(GPV_PHASE_SCAN);
 	{ // K3 boundary compaction
@@ -296,6 +336,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		k_scan<MODE_CELLS><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
 		launches++;
 	}
+	GPV_CUDA(cudaStreamWaitEvent(st, c->evJoin[0], 0));
 	{
 		const ScanReq r[3] = { { c->colCount.as<int>(), ncol, c->colOff.as<unsigned>(), &dT->colTotalOver, nullptr, dOff[3] },
 			                   { c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, nullptr, dOff[4] },
@@ -315,24 +356,46 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	const long long n23 = (long long)g.n2 * g.n2 * g.n2;
 	if (c->cellTris.ensure((size_t)T1.triTotal * 4 + 32) || c->colTris.ensure((size_t)T1.colTotalOver * 4 + 32) || c->crossTri.ensure((size_t)T1.crossTotal * 4 + 32))
 		return 1;
-	if (gather) { // the one exchange step: boundary counts of the lower slabs (8 bytes per rank through the mailbox)
-		k_gather_exchange<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, wantL2 ? c->gather.l2Cap / n23 : (long long)0x7fffffff, dT);
-		launches++;
-	}
 	if (wantL2 && (c->l2State.ensure(gather ? 32 : (size_t)(nB * n23) + 32) || c->colCellList.ensure((size_t)nB * 8 + 32) || c->cellMid.ensure((size_t)nB * 16 + 32) || c->l2Par.ensure((size_t)nB * g.n2 * g.n2 * 4 + 32))) return 1;
 	if (wantN && (c->l1Normal.ensure((size_t)cells * 3 + 32) || (wantL2 && c->l2Normal.ensure((size_t)(nB * n23) * 3 + 32)))) return 1;
 
 	bo.prefix = c->prefix.as<int>(); bo.bTriOff = c->bTriOff.as<unsigned>(); bo.cellTris = c->cellTris.as<int>();
 	bo.colOff = c->colOff.as<unsigned>(); bo.colTris = c->colTris.as<int>();
+	if (c->longList.ensure((size_t)(nB + ncol) * 4 + 64)) return 1; // (every allocation of the call happens before the exchange and the fork: a growing pool's cudaFree synchronises the device)
+	if (gather) { // the one exchange step: boundary counts of the lower slabs (8 bytes per rank through the mailbox)
+		k_gather_exchange<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, wantL2 ? c->gather.l2Cap / n23 : (long long)0x7fffffff, dT);
+		launches++;
+	}
+	if (sink) {
+		if (sink->level2_inout && wantL2 && (int64_t)(nB * n23) > sink->level2_capacity) return fail("gpv_voxelize_host: level2 host buffer too small");
+		if (sink->boundary_index && nB > sink->boundary_capacity) return fail("gpv_voxelize_host: boundary_index host buffer too small");
+	}
+	// side stream: the parity-fill branch (crossing lists -> fill sweep -> final Level-1 bytes), independent of the binning / sorting /
+	// Level-2 branch on the main stream until the end of the call
+	GPV_CUDA(cudaEventRecord(c->evFork[1], st));
+	GPV_CUDA(cudaStreamWaitEvent(side, c->evFork[1], 0));
+	mark_side(GPV_PHASE_CROSS_FILL, true);
+	k_cross<true><<<kWorkGrid, kWorkThreads, 0, side>>>(ray48, c->crossFp.as<int4>(), nTri, c->crossWorkOff.as<unsigned>(), g, cx, cy, c->crossCount.as<int>(), c->crossOff.as<unsigned>(),
+	                                                     c->crossTri.as<int>(), dT);
+	mark_side(GPV_PHASE_CROSS_FILL, false);
+	mark_side(GPV_PHASE_FILL_SWEEP, true);
+	{
+		dim3 grid((g.nx + 31) / 32, g.ny, (g.z1 - g.z0 + 127) / 128), block(32, 4);
+		k_fill_sweep<<<grid, block, 0, side>>>(ray48, g, cx, cy, cz, c->crossOff.as<unsigned>(), c->crossTri.as<int>(), c->bmask.as<unsigned char>(),
+		                                       gather ? c->gather.l1 + (size_t)g.z0 * ncol : c->l1State.as<unsigned char>(), dT);
+		launches += 2;
+		if (gather) { // slab-local prefix sums + boundary cells of the lower slabs -> their final place on the gathering rank
+			k_gather_prefix<<<(unsigned)std::min<long long>(c->smCount * 8, (cells / 4 + 255) / 256 + 1), 256, 0, side>>>(c->prefix.as<int>(), c->gather.prefix + (size_t)g.z0 * ncol, cells, dT);
+			launches++;
+		}
+	}
+	mark_side(GPV_PHASE_FILL_SWEEP, false);
+	GPV_CUDA(cudaEventRecord(c->evJoin[1], side));
 	mark(GPV_PHASE_BIN_FILL);
 	k_bin<true><<<kWorkGrid, kWorkThreads, 0, st>>>(tri48, nTri, c->binOff.as<unsigned>(), g, cx, cy, cz, bo);
-	mark(GPV_PHASE_CROSS_FILL);
-	k_cross<true><<<kWorkGrid, kWorkThreads, 0, st>>>(ray48, c->crossFp.as<int4>(), nTri, c->crossWorkOff.as<unsigned>(), g, cx, cy, c->crossCount.as<int>(), c->crossOff.as<unsigned>(),
-	                                                   c->crossTri.as<int>(), dT);
-	launches += 2;
+	launches++;
 	mark(GPV_PHASE_SORT);
 	{ // canonical order: warp per list; lists longer than kSortSmem go through a work list to k_sort_long (CTA per list)
-		if (c->longList.ensure((size_t)(nB + ncol) * 4 + 64)) return 1;
 		unsigned* longCnt = reinterpret_cast<unsigned*>(c->totals.as<char>() + 128); // [0] cell lists, [1] column lists (zeroed by k_clear)
 		int* longCells = c->longList.as<int>() + 16;
 		int* longCols = longCells + nB;
@@ -350,17 +413,6 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		k_sort_long<true><<<c->smCount, kSortLongThreads, kSortLongSmem * 4, st>>>(c->colOff.as<unsigned>(), longCols, longCnt + 1, c->colTris.as<int>(), c->colCount.as<int>());
 		launches += 2;
 	}
-	mark(GPV_PHASE_FILL_SWEEP);
-	{
-		dim3 grid((g.nx + 31) / 32, g.ny, (g.z1 - g.z0 + 127) / 128), block(32, 4);
-		k_fill_sweep<<<grid, block, 0, st>>>(ray48, g, cx, cy, cz, c->crossOff.as<unsigned>(), c->crossTri.as<int>(), c->bmask.as<unsigned char>(),
-		                                     gather ? c->gather.l1 + (size_t)g.z0 * ncol : c->l1State.as<unsigned char>(), dT);
-		launches++;
-		if (gather) { // slab-local prefix sums + boundary cells of the lower slabs -> their final place on the gathering rank
-			k_gather_prefix<<<(unsigned)std::min<long long>(c->smCount * 8, (cells / 4 + 255) / 256 + 1), 256, 0, st>>>(c->prefix.as<int>(), c->gather.prefix + (size_t)g.z0 * ncol, cells, dT);
-			launches++;
-		}
-	}
 	mark(GPV_PHASE_L1_NORMALS);
 	if (wantN) {
 		GPV_CUDA(cudaMemsetAsync(c->l1Normal.p, 127, (size_t)cells * 3, st));
@@ -370,11 +422,10 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			launches++;
 		}
 	}
-	if (sink) { // Level-1 streams are final once the fill sweep is done: send them while Level-2 computes
-		if (sink->level2_inout && wantL2 && (int64_t)(nB * n23) > sink->level2_capacity) return fail("gpv_voxelize_host: level2 host buffer too small");
-		if (sink->boundary_index && nB > sink->boundary_capacity) return fail("gpv_voxelize_host: boundary_index host buffer too small");
+	if (sink) { // Level-1 streams are final once the fill sweep (side stream) and the normals are done: send them while Level-2 computes
 		GPV_CUDA(cudaEventRecord(c->evChunk[kMaxChunks], st));
 		GPV_CUDA(cudaStreamWaitEvent(c->copyStream, c->evChunk[kMaxChunks], 0));
+		GPV_CUDA(cudaStreamWaitEvent(c->copyStream, c->evJoin[1], 0));
 		if (sink->level1_inout) GPV_CUDA(cudaMemcpyAsync(sink->level1_inout, c->l1State.p, (size_t)cells, cudaMemcpyDeviceToHost, c->copyStream));
 		if (sink->prefix) GPV_CUDA(cudaMemcpyAsync(sink->prefix, c->prefix.p, (size_t)cells * 4, cudaMemcpyDeviceToHost, c->copyStream));
 		if (sink->boundary_index && nB) GPV_CUDA(cudaMemcpyAsync(sink->boundary_index, c->boundaryIndex.p, (size_t)nB * 4, cudaMemcpyDeviceToHost, c->copyStream));
@@ -391,7 +442,8 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		const L2K K = l2_constants(g.n2);
 		const int G = K.G;
 		const size_t smem = (size_t)K.total;
-		void (*l2fn)(GridP, L2IO, L2K) = g.n2 == 16 ? k_l2<16> : g.n2 == 8 ? k_l2<8> : g.n2 == 4 ? k_l2<4> : g.n2 == 2 ? k_l2<2> : k_l2<0>;
+		void (*l2fn)(GridP, L2IO, L2K) = gather ? (g.n2 == 16 ? k_l2<16, true> : g.n2 == 8 ? k_l2<8, true> : g.n2 == 4 ? k_l2<4, true> : g.n2 == 2 ? k_l2<2, true> : k_l2<0, true>)
+		                                        : (g.n2 == 16 ? k_l2<16, false> : g.n2 == 8 ? k_l2<8, false> : g.n2 == 4 ? k_l2<4, false> : g.n2 == 2 ? k_l2<2, false> : k_l2<0, false>);
 		if (smem > 48 * 1024) return fail("k_l2: shared-memory layout exceeds 48 KB"); // cannot happen for n2 <= 32 (41 KB)
 		// K4a: boundary cells grouped by Level-1 column, then the parity bits of every sub-voxel column, one walk of the column list per column
 		k_col_cells<<<(unsigned)((nB + 255) / 256), 256, 0, st>>>(lio.boundaryIndex, (int)nB, (int)ncol, g.nx, cx, cy, cz, lio.colCellOff, c->colCellCnt.as<int>(), c->colCellList.as<int2>(),
@@ -424,6 +476,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			if (sink && sink->level2_normal) GPV_CUDA(cudaMemcpyAsync(sink->level2_normal, c->l2Normal.p, (size_t)(nB * n23) * 3, cudaMemcpyDeviceToHost, st));
 		}
 	}
+	GPV_CUDA(cudaStreamWaitEvent(st, c->evJoin[1], 0)); // the parity-fill branch joins
 	if (gather) { // completion flag behind this rank's last store; the gathering rank returns when every rank has signalled
 		k_gather_done<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch);
 		launches++;
@@ -464,9 +517,13 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	if (prof) {
 		for (int k = 0; k < GPV_PHASE_COUNT; k++) {
 			if (!marked[k]) continue;
-			int nxt = k + 1;
-			while (nxt < GPV_PHASE_COUNT && !marked[nxt]) nxt++;
 			float ms = 0.f;
+			if (sidePhase[k]) { // side-branch phases overlap the main branch: their own start / end events
+				if (cudaEventElapsedTime(&ms, c->ev[k], c->evEnd[k]) == cudaSuccess) out->phase_ms[k] = ms;
+				continue;
+			}
+			int nxt = k + 1;
+			while (nxt < GPV_PHASE_COUNT && (!marked[nxt] || sidePhase[nxt])) nxt++;
 			if (cudaEventElapsedTime(&ms, c->ev[k], c->ev[nxt]) == cudaSuccess) out->phase_ms[k] = ms;
 		}
 	}

@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(256, 3) k_l2_rays(GridP g, L2IO io)
 }
 
 #ifndef GPV_L2_MINBLOCKS
-#define GPV_L2_MINBLOCKS 5 // 48 registers: 5 CTAs per SM measured 4-8 % faster than 4 (64 registers) on cessna 256/16 and sphere 512/8
+#define GPV_L2_MINBLOCKS 6 // 40 registers: 6 CTAs per SM (a 42-register build drops to 5 and measured 7 % slower on cessna 256/16)
 #endif
 constexpr int kL2Threads = 256;
 constexpr int kL2Batch = 8;   // triangles per round of the (row, triangle) queue
@@ -888,9 +888,10 @@ inline L2K l2_constants(int n2)
 // the parity kernel's result).  A CTA of 256 threads refines G = max(1, 256/n2^2) boundary cells; an item is one sub-voxel
 // COLUMN (cell, p, q) -- the same unit k_l2_rays works on, so the SAT bits and the parity bits of a column share one word
 // layout (bit r = sub-voxel r) and no transposition is needed.  Everything of the SAT that does not involve z is hoisted
-// per (column, triangle) (gpv::SatCol).  The CTA's block of Level2InOut.raw is assembled in shared memory and stored 128 bits per thread.
+// per (column, triangle) (gpv::SatCol).
 // N2 > 0: n2 fixed at compile time (2, 4, 8, 16: index arithmetic by shifts, unrolled byte loop); N2 = 0: any n2 <= 32.
-template <int N2>
+// GATHER: the output block goes to the gathering rank over NVLink (staged in shared memory, 128-bit stores) instead of local HBM.
+template <int N2, bool GATHER>
 __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2IO io, L2K K)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -1036,39 +1037,59 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	}
 	__syncthreads();
 
-	// ---- the file bytes: SAT hit 254, else inside 127, else 0 (2 overwrites 1: src/Object.cpp:2603-2606).  Every thread
-	// expands its column into the CTA's block of Level2InOut.raw staged in shared memory (the queue area, idle now; the cells of
-	// a CTA are consecutive boundary ranks, so the block is contiguous in the file); the block then leaves as 128-bit
-	// coalesced stores -- to local HBM, or over NVLink into the gathering rank's buffer (gpv_gather_*).
-	unsigned char* sOut = smemRaw + K.q1;
-	const int n23 = rows * n2;
+	// ---- the file bytes: SAT hit 254, else inside 127, else 0 (2 overwrites 1: src/Object.cpp:2603-2606)
+	// four sub-voxels at once: (nibble * 0x204081) & 0x01010101 spreads bit k of the nibble to byte k
+	auto four = [](unsigned par, unsigned sat, int r) { return (((par >> r) & 15u) * 0x204081u & 0x01010101u) * 127u + (((sat >> r) & 15u) * 0x204081u & 0x01010101u) * 254u; };
 	unsigned nIn = 0, nBd = 0;
-	for (int item = tid; item < nItems; item += kL2Threads) {
-		const int gi = div_rows(item), pq = item - gi * rows;
-		const long long b = b0 + gi;
-		if (b >= io.nBoundary) continue;
-		const unsigned sat = sSat[item];
-		const unsigned par = io.l2Par[(size_t)b * rows + pq] & ~sat;
-		nIn += __popc(par); nBd += __popc(sat);
-		unsigned char* o = sOut + gi * n23 + pq;
-		int r = 0;
-		for (; r + 4 <= n2; r += 4) {
-			// four sub-voxels at once: (nibble * 0x204081) & 0x01010101 spreads bit k of the nibble to byte k
-			const unsigned w = (((par >> r) & 15u) * 0x204081u & 0x01010101u) * 127u + (((sat >> r) & 15u) * 0x204081u & 0x01010101u) * 254u;
-			o[r * rows] = (unsigned char)w; o[(r + 1) * rows] = (unsigned char)(w >> 8);
-			o[(r + 2) * rows] = (unsigned char)(w >> 16); o[(r + 3) * rows] = (unsigned char)(w >> 24);
+	if (GATHER) {
+		// GPV_GATHER: the bytes go over NVLink into the gathering rank's buffer.  Every thread expands its column into the CTA's block
+		// of Level2InOut.raw staged in shared memory (the queue area, idle now; the cells of a CTA are consecutive boundary ranks, so
+		// the block is contiguous in the file); the block then leaves as 128-bit coalesced stores, the granularity NVLink likes.
+		unsigned char* sOut = smemRaw + K.q1;
+		const int n23 = rows * n2;
+		for (int item = tid; item < nItems; item += kL2Threads) {
+			const int gi = div_rows(item), pq = item - gi * rows;
+			const long long b = b0 + gi;
+			if (b >= io.nBoundary) continue;
+			const unsigned sat = sSat[item];
+			const unsigned par = io.l2Par[(size_t)b * rows + pq] & ~sat;
+			nIn += __popc(par); nBd += __popc(sat);
+			unsigned char* o = sOut + gi * n23 + pq;
+			int r = 0;
+			for (; r + 4 <= n2; r += 4) {
+				const unsigned w = four(par, sat, r);
+				o[r * rows] = (unsigned char)w; o[(r + 1) * rows] = (unsigned char)(w >> 8);
+				o[(r + 2) * rows] = (unsigned char)(w >> 16); o[(r + 3) * rows] = (unsigned char)(w >> 24);
+			}
+			for (; r < n2; r++) o[r * rows] = ((sat >> r) & 1) ? 254 : (((par >> r) & 1) ? 127 : 0);
 		}
-		for (; r < n2; r++) o[r * rows] = ((sat >> r) & 1) ? 254 : (((par >> r) & 1) ? 127 : 0);
-	}
-	__syncthreads();
-	{
+		__syncthreads();
 		const long long nValid = min((long long)G, (long long)io.nBoundary - b0);
-		const long long gbase = io.l2Base ? *io.l2Base : 0ll; // gather: boundary cells of the lower slabs; < 0 = exchange failed, write nothing
+		const long long gbase = *io.l2Base; // boundary cells of the lower slabs; < 0 = the exchange failed, write nothing
 		const int total = (gbase < 0 || nValid <= 0) ? 0 : (int)nValid * n23;
 		unsigned char* out = io.l2State + (size_t)(gbase + b0) * n23;
 		const int vec = ((reinterpret_cast<size_t>(out) & 15) == 0) ? (total & ~15) : 0;
 		for (int i = tid * 16; i < vec; i += kL2Threads * 16) *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(sOut + i);
 		for (int i = vec + tid; i < total; i += kL2Threads) out[i] = sOut[i];
+	} else {
+		// local HBM: a warp's byte stores cover 32 consecutive sub-voxels of the file (whole sectors); measured 10 % faster for the
+		// kernel than the staged form (no barrier, the warps retire independently)
+		for (int item = tid; item < nItems; item += kL2Threads) {
+			const int gi = div_rows(item), pq = item - gi * rows;
+			const long long b = b0 + gi;
+			if (b >= io.nBoundary) continue;
+			const unsigned sat = sSat[item];
+			const unsigned par = io.l2Par[(size_t)b * rows + pq] & ~sat;
+			nIn += __popc(par); nBd += __popc(sat);
+			unsigned char* o = io.l2State + ((size_t)b * rows * n2 + pq);
+			int r = 0;
+			for (; r + 4 <= n2; r += 4) {
+				const unsigned w = four(par, sat, r);
+				o[(size_t)r * rows] = (unsigned char)w; o[(size_t)(r + 1) * rows] = (unsigned char)(w >> 8);
+				o[(size_t)(r + 2) * rows] = (unsigned char)(w >> 16); o[(size_t)(r + 3) * rows] = (unsigned char)(w >> 24);
+			}
+			for (; r < n2; r++) o[(size_t)r * rows] = ((sat >> r) & 1) ? 254 : (((par >> r) & 1) ? 127 : 0);
+		}
 	}
 	nIn = __reduce_add_sync(0xffffffffu, nIn); nBd = __reduce_add_sync(0xffffffffu, nBd);
 	if (lane == 0 && (nIn | nBd)) { atomicAdd(&io.totals->l2Inside, (unsigned long long)nIn); atomicAdd(&io.totals->l2Boundary, (unsigned long long)nBd); }

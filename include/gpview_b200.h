@@ -167,7 +167,11 @@ int gpv_voxelize_host(gpv_ctx* ctx, const gpv_mesh* mesh, const gpv_params* para
  * every Level-2 offset) and the completion signal are 8-byte flags in a mailbox in rank 0's memory, written and polled by
  * one-thread kernels on the callers' streams; all ranks must issue their GPV_GATHER calls in the same order.
  * gpv_gather_desc is plain bytes: ship it to the other ranks with any transport (torch.distributed broadcast, a file, a pipe).
- * GPV_NORMALS is not supported together with GPV_GATHER. */
+ * GPV_NORMALS is not supported together with GPV_GATHER.  The flags are polled by one-thread kernels; every poll gives up after 5 s with
+ * an error return instead of hanging the GPU.  If several gathering contexts share ONE process and device (tests): raise
+ * CUDA_DEVICE_MAX_CONNECTIONS so that their streams do not share a hardware work queue, and do not allocate device memory while
+ * a gathering call is in flight (CUDA serialises streams around cudaMalloc/cudaFree) -- run one plain call first to grow the
+ * pools.  One process per GPU needs neither: a rank finishes its allocations before it posts its count. */
 typedef struct {
 	unsigned char l1[64], prefix[64], l2[64], mailbox[64];   /* cudaIpcMemHandle_t of the four allocations */
 	int64_t cells_total;                                     /* nx*ny*nz of the grid the buffers were sized for */

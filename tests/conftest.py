@@ -4,6 +4,10 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# The peer-memory gather test runs several ranks as contexts of ONE process on one device; their streams must not share a
+# hardware work queue (a rank's one-thread polling kernel would hold back the rank it is waiting for).  Must be set before
+# CUDA initialises.  One process per GPU -- the deployment -- needs nothing of the sort.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

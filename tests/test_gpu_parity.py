@@ -212,27 +212,38 @@ def test_peer_memory_gather_equals_whole(product, ctx, tmp_path_factory, name, l
         for r in range(R):
             ranks[r].gather_attach_local(ranks[0], r, R)
         cuts = [nz * r // R for r in range(R + 1)]
+        # Same-process ranks only: CUDA serialises streams around every cudaMalloc / cudaFree, so nothing may allocate while a rank's
+        # polling kernel is in flight.  Upload first and let one plain slab call grow every context's pools.  (One process per
+        # GPU -- the deployment, bench.py -- has no such constraint: a rank allocates before it posts its count.)
+        dev = [ranks[r].upload(mesh) for r in range(R)]
+        for r in range(R):
+            ranks[r].voxelize_device(dev[r], mesh, product.Params(l1, l2, 0, cuts[r], cuts[r + 1]))
         for rep in range(2):
-            errs = []
+            for attempt in range(2):
+                errs = []
 
-            def work(r):
-                try:
-                    d = ranks[r].upload(mesh)
-                    ranks[r].voxelize_device(d, mesh, product.Params(l1, l2, product.GPV_GATHER, cuts[r], cuts[r + 1]), ranks[r].stream())
-                    ranks[r].free_device(d)
-                except Exception as e:  # noqa: BLE001
-                    errs.append((r, repr(e)))
-            th = [threading.Thread(target=work, args=(r,)) for r in range(R)]
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
+                def work(r):
+                    try:
+                        ranks[r].voxelize_device(dev[r], mesh, product.Params(l1, l2, product.GPV_GATHER, cuts[r], cuts[r + 1]), ranks[r].stream())
+                    except Exception as e:  # noqa: BLE001
+                        errs.append((r, repr(e)))
+                th = [threading.Thread(target=work, args=(r,)) for r in range(R)]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                # ranks sharing one device can still be serialised by the driver (a shared box, hardware queue aliasing): the 5 s
+                # poll timeout then turns into an error on every rank -- by design -- and the epoch stays in step; try once more
+                if not errs or not all("timed out" in e for _, e in errs) or len(errs) != R:
+                    break
             assert not errs, errs
             g_l1, g_pre, g_l2, nb = ranks[0].gather_result(cells, n23)
             assert nb == whole.nb
             assert np.array_equal(g_l1, w_l1), (rep, "l1")
             assert np.array_equal(g_pre, w_pre), (rep, "prefix")
             assert np.array_equal(g_l2, w_l2), (rep, "l2")
+        for r in range(R):
+            ranks[r].free_device(dev[r])
         # without an attached gather the flag is refused, not ignored
         with pytest.raises(product.GpvError):
             ctx.voxelize(mesh, product.Params(l1, l2, product.GPV_GATHER))
