@@ -233,8 +233,8 @@ def test_peer_memory_gather_equals_whole(product, ctx, tmp_path_factory, name, l
                 for t in th:
                     t.join()
                 # ranks sharing one device can still be serialised by the driver (a shared box, hardware queue aliasing): the 5 s
-                # poll timeout then turns into an error on every rank -- by design -- and the epoch stays in step; try once more
-                if not errs or not all("timed out" in e for _, e in errs) or len(errs) != R:
+                # poll timeout then turns into an error return -- by design -- and every rank's epoch stays in step; try once more
+                if not errs or not all("timed out" in e for _, e in errs):
                     break
             assert not errs, errs
             g_l1, g_pre, g_l2, nb = ranks[0].gather_result(cells, n23)
