@@ -450,6 +450,7 @@ __device__ __forceinline__ void scan_body(const ScanIO& io)
 	if (MODE == MODE_CELLS) {
 		int pre[kScanItems];
 		unsigned flags = 0;
+		const unsigned col0 = (unsigned)(io.globalBase + first) % (unsigned)io.plane; // once per thread, not per boundary cell (linear indices are < 2^31)
 #pragma unroll
 		for (int k = 0; k < kScanItems; k++) {
 			unsigned b = (unsigned)(run >> 31), ts = (unsigned)(run & 0x7fffffffu);
@@ -457,7 +458,9 @@ __device__ __forceinline__ void scan_body(const ScanIO& io)
 			if (v[k] > 0) {
 				flags |= 1u << k;
 				io.boundaryIndex[b] = (int)(io.globalBase + first + k);
-				atomicAdd(io.colCells + (io.globalBase + first + k) % io.plane, 1);
+				unsigned col = col0 + (unsigned)k; // < 2 * plane + 8: the column of cell first + k
+				while (col >= (unsigned)io.plane) col -= (unsigned)io.plane;
+				atomicAdd(io.colCells + col, 1);
 				io.bTriOff[b] = ts;
 			}
 			run += item[k];
@@ -874,7 +877,7 @@ inline L2K l2_constants(int n2)
 	K.invRows = 1.f / (float)K.rows; K.invN2 = 1.f / (float)n2; K.inv3N2 = 1.f / (float)(3 * n2);
 	int o = K.G * 3 * n2 * 4;                // [G][3][n2] sub-voxel centres
 	K.sat = o; o += K.nItems * 4;            // [nItems] SAT hit bits along z per sub-voxel column
-	K.info = o; o += (K.G * 2 + 2) * 4;      // [G][2] triOff, triCnt (0 for cells past the end); then the CTA-wide longest list
+	K.info = o; o += (K.G * 3 + 4) * 4;      // [G][2] triOff, triCnt (0 for cells past the end); then [G+1] prefix of the cells' pair counts
 	o = (o + 15) & ~15;
 	K.q1 = o; o += kL2Threads * kL2Batch * 8;    // (column, triangle) queue: item | rlo<<16 | rhi<<24, triangle
 	K.q2 = o; o += kL2Threads * n2 * 2;          // sub-voxel queue of one slice of kL2Threads (column, triangle) entries: entry<<5 | r
@@ -908,9 +911,7 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	auto div_n2 = [&](int a) { return N2 ? a / (N2 ? N2 : 1) : fast_div(a, K.invN2); };
 	auto div_3n2 = [&](int a) { return N2 ? a / (N2 ? 3 * N2 : 1) : fast_div(a, K.inv3N2); };
 
-	if (tid == 0) sInfo[2 * G] = 0;
 	if (tid < 4) sQn[tid] = 0;
-	__syncthreads();
 	for (int k = tid; k < G * 3 * n2; k += kL2Threads) {
 		const int gi = div_3n2(k), rem = k - gi * 3 * n2, ax = div_n2(rem), p = rem - ax * n2;
 		const long long b = b0 + gi;
@@ -928,7 +929,21 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 		int off = 0, cnt = 0;
 		if (b < io.nBoundary) { off = (int)io.bTriOff[b]; cnt = (int)(io.bTriOff[b + 1] - io.bTriOff[b]); }
 		sInfo[gi * 2] = off; sInfo[gi * 2 + 1] = cnt;
-		atomicMax(sInfo + 2 * G, cnt);
+	}
+	__syncthreads();
+	if (tid < 32) { // exclusive prefix of the cells' pair counts (rows * triangles), one warp
+		int* pre = sInfo + 2 * G + 1;
+		int carry = 0;
+		for (int g0 = 0; g0 < G; g0 += 32) {
+			const int gi = g0 + tid;
+			const int v = gi < G ? rows * sInfo[gi * 2 + 1] : 0;
+			int incl = v;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
+			if (gi < G) pre[gi] = carry + incl - v;
+			carry += __shfl_sync(0xffffffffu, incl, 31);
+		}
+		if (tid == 0) pre[G] = carry;
 	}
 	for (int item = tid; item < nItems; item += kL2Threads) sSat[item] = 0;
 	__syncthreads();
@@ -945,28 +960,49 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	// fills are ping-pong counters, reset one round ahead, which keeps it to two barriers per round.
 	{
 		const float inv2h = 1.f / (2.f * g.h2z);
-		const int maxCnt = sInfo[2 * G]; // CTA-wide longest cell list (every thread must take part in the barriers below)
 		int round1 = 0, round2 = 0;
-		for (int itemBase = 0; itemBase < nItems; itemBase += kL2Threads) { // one pass unless n2 = 32
-			const int item = itemBase + tid;
-			int triOff = 0, triCnt = 0;
-			float cx2 = 0.f, cy2 = 0.f, cz0 = 0.f, slack = 0.f;
-			if (item < nItems) {
-				const int gi = div_rows(item), pq = item - gi * rows, q = div_n2(pq), p = pq - q * n2;
-				const float* c = sC + gi * 3 * n2;
-				cx2 = c[p]; cy2 = c[n2 + q]; cz0 = c[2 * n2];
-				slack = 9.5367431640625e-07f * (fabsf(cz0) + 2.f * g.gsz); // 16u(|mid_z| + gs_z) >= |(c_r - c_0) - 2*h2z*r|
-				triOff = sInfo[gi * 2]; triCnt = sInfo[gi * 2 + 1];         // 0 for cells past the end
-			}
-			for (int kb = 0; kb < maxCnt; kb += kL2Batch) {
+		// Stage A enumerates the (column, triangle) pairs of the CTA, kL2Threads * kL2Batch per round.
+		//   n2 = 16 (one cell, one column per thread): thread = column, triangles 8 at a time; the column state stays in registers.
+		//   otherwise: ONE flat pair space over all cells of the CTA, pair -> (cell, triangle, column) through the prefix sums of
+		//   the cells' pair counts.  A CTA holds up to 256 cells with very different list lengths (a cell at a pole of a finely
+		//   tessellated body carries hundreds of triangles, its neighbours ten): the flat space keeps every thread busy whatever
+		//   the skew, where a thread-per-column loop runs as long as the longest list of the CTA.
+		constexpr bool kFlat = N2 != 16;
+		const int* sPre = sInfo + 2 * G + 1; // [G+1] exclusive prefix of rows * triCnt
+		const int pairTotal = kFlat ? sPre[G] : rows * sInfo[1];
+		float cx2 = 0.f, cy2 = 0.f, cz0 = 0.f, slack = 0.f;
+		if (!kFlat) {
+			const int q = div_n2(tid), p = tid - q * n2;
+			cx2 = sC[p]; cy2 = sC[n2 + q]; cz0 = sC[2 * n2];
+			slack = 9.5367431640625e-07f * (fabsf(cz0) + 2.f * g.gsz); // 16u(|mid_z| + gs_z) >= |(c_r - c_0) - 2*h2z*r|
+		}
+		{
+			for (int pairBase = 0; pairBase < pairTotal; pairBase += kL2Threads * kL2Batch) {
 				int* q1n = sQn + (round1 & 1);
 				if (tid == 0) sQn[(round1 + 1) & 1] = 0; // the other counter: every read of it lies behind a barrier, its next use after the next one
 				// stage A
-				for (int k = kb; k < min(kb + kL2Batch, maxCnt); k++) {
+				for (int j = 0; j < kL2Batch; j++) {
+					const int pr = pairBase + j * kL2Threads + tid;
+					if (pairBase + j * kL2Threads >= pairTotal) break; // uniform
 					bool alive = false;
-					int rlo = 0, rhi = -1, t = 0;
-					if (k < triCnt) {
-						t = io.cellTris[triOff + k];
+					int rlo = 0, rhi = -1, t = 0, item = tid;
+					if (pr < pairTotal) {
+						int k;
+						if (kFlat) {
+							int lo = 0, hi = G; // largest gi with sPre[gi] <= pr
+							while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sPre[mid] <= pr) lo = mid; else hi = mid; }
+							const int local = pr - sPre[lo];
+							k = div_rows(local);
+							const int pq = local - k * rows, q = div_n2(pq), p = pq - q * n2;
+							const float* c = sC + lo * 3 * n2;
+							cx2 = c[p]; cy2 = c[n2 + q]; cz0 = c[2 * n2];
+							slack = 9.5367431640625e-07f * (fabsf(cz0) + 2.f * g.gsz);
+							item = lo * rows + pq;
+							t = io.cellTris[sInfo[lo * 2] + k];
+						} else {
+							k = pr >> 8; // rows == kL2Threads == 256: the pair's column is this thread's
+							t = io.cellTris[sInfo[0] + k];
+						}
 						const float4 A = __ldg(io.tri48 + (size_t)t * 3), pl = __ldg(io.plane16 + t);
 						PlaneRec P; P.sx = pl.x; P.ny = pl.y; P.nz = pl.z; P.R = pl.w;
 						alive = plane_row_interval(P, A.z - cz0, A.x - cx2, A.y - cy2, inv2h, slack, n2, rlo, rhi);
