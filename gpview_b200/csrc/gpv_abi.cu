@@ -102,7 +102,7 @@ static int preload_kernels()
 {
 	cudaFuncAttributes a;
 #define GPV_LOAD(...) GPV_CUDA(cudaFuncGetAttributes(&a, __VA_ARGS__))
-	GPV_LOAD(k_clear); GPV_LOAD(k_prepare); GPV_LOAD(k_scan_offs3); GPV_LOAD(k_scan<MODE_CELLS>); GPV_LOAD(k_scan<MODE_OFFS>);
+	GPV_LOAD(k_clear); GPV_LOAD(k_prepare); GPV_LOAD(k_scan_offs3); GPV_LOAD((k_scan<MODE_CELLS, 1>)); GPV_LOAD((k_scan<MODE_CELLS, 4>));
 	GPV_LOAD(k_bin<false>); GPV_LOAD(k_bin<true>); GPV_LOAD(k_cross<false>); GPV_LOAD(k_cross<true>); GPV_LOAD(k_fill_sweep);
 	GPV_LOAD(k_sort_segments<false>); GPV_LOAD(k_sort_segments<true>); GPV_LOAD(k_sort_long<false>); GPV_LOAD(k_sort_long<true>);
 	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals);
@@ -326,14 +326,16 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	launches += 2;
 	mark(GPV_PHASE_SCAN);
 	{ // K3 boundary compaction
-		long long tiles = (cells + kScanTile - 1) / kScanTile;
+		const int V = cells > (16ll << 20) ? 4 : 1; // sub-tiles per tile: large grids amortise the per-tile latency over 32 KB of input
+		long long tiles = (cells + (long long)V * kScanTile - 1) / ((long long)V * kScanTile);
 		ScanIO io{};
 		io.in = c->cellCount.as<int>(); io.n = cells;
 		io.tileCounter = reinterpret_cast<unsigned*>(c->desc.as<char>() + dOff[2]); io.desc = reinterpret_cast<unsigned long long*>(c->desc.as<char>() + dOff[2]) + 1;
 		io.prefix = c->prefix.as<int>(); io.boundaryIndex = c->boundaryIndex.as<int>(); io.bTriOff = c->bTriOff.as<unsigned>();
 		io.bmask = c->bmask.as<unsigned char>(); io.globalBase = (long long)g.z0 * ncol; io.totals = dT;
 		io.colCells = c->colCellCnt.as<int>(); io.plane = ncol;
-		k_scan<MODE_CELLS><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
+		if (V == 4) k_scan<MODE_CELLS, 4><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
+		else k_scan<MODE_CELLS, 1><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
 		launches++;
 	}
 	GPV_CUDA(cudaStreamWaitEvent(st, c->evJoin[0], 0));

@@ -378,50 +378,64 @@ __device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long lon
 	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <int MODE>
+// V = sub-tiles of kScanTile items per tile: one tile id, one look-back and one descriptor per V * 2048 items, so the fixed
+// latency of a tile (atomic, look-back, barriers) is paid once per 8 KB * V of input -- V = 4 for grids beyond 16 M cells.
+template <int MODE, int V>
 __device__ __forceinline__ void scan_body(const ScanIO& io)
 {
+	static_assert(V * (kScanThreads / 32) <= 32, "the warp totals of a tile are scanned by one warp");
 	__shared__ unsigned sTile;
-	__shared__ unsigned long long sWarp[kScanThreads / 32];
+	__shared__ unsigned long long sWarp[V * (kScanThreads / 32)];
 	__shared__ unsigned long long sExcl;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	constexpr int kWarps = kScanThreads / 32;
 	if (tid == 0) sTile = atomicAdd(io.tileCounter, 1u);
 	__syncthreads();
 	const unsigned tile = sTile;
-	const long long first = (long long)tile * kScanTile + (long long)tid * kScanItems;
+	const long long tileFirst = (long long)tile * (V * kScanTile) + (long long)tid * kScanItems;
 
-	int v[kScanItems];
-	if (first + kScanItems <= io.n) {
-		const int4* p = reinterpret_cast<const int4*>(io.in + first);
-		int4 a = p[0], b = p[1];
-		v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-	} else {
+	// the tile's items are read twice: once for the sums (before the look-back) and once, from L2, for the outputs -- holding
+	// 8 * V values per thread across the look-back would cost the registers that keep enough tiles in flight per SM
+	auto load8 = [&](long long first, int* x) {
+		if (first + kScanItems <= io.n) {
+			const int4* p = reinterpret_cast<const int4*>(io.in + first);
+			const int4 a = __ldcg(p), b = __ldcg(p + 1);
+			x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+		} else {
 #pragma unroll
-		for (int k = 0; k < kScanItems; k++) v[k] = (first + k < io.n) ? io.in[first + k] : 0;
-	}
-	unsigned long long item[kScanItems], threadSum = 0;
+			for (int k = 0; k < kScanItems; k++) x[k] = (first + k < io.n) ? io.in[first + k] : 0;
+		}
+	};
+	auto item_of = [](int x) { return (MODE == MODE_CELLS) ? (((unsigned long long)(x > 0) << 31) | (unsigned)x) : (unsigned long long)(unsigned)x; };
+	unsigned long long threadSum[V], incl[V];
 #pragma unroll
-	for (int k = 0; k < kScanItems; k++) {
-		item[k] = (MODE == MODE_CELLS) ? (((unsigned long long)(v[k] > 0) << 31) | (unsigned)v[k]) : (unsigned long long)(unsigned)v[k];
-		threadSum += item[k];
-	}
-	unsigned long long incl = threadSum;
+	for (int s = 0; s < V; s++) {
+		int v[kScanItems];
+		load8(tileFirst + (long long)s * kScanTile, v);
+		unsigned long long t = 0;
 #pragma unroll
-	for (int o = 1; o < 32; o <<= 1) {
-		unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
-		if (lane >= o) incl += y;
+		for (int k = 0; k < kScanItems; k++) t += item_of(v[k]);
+		threadSum[s] = t;
+		unsigned long long in = t;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			unsigned long long y = __shfl_up_sync(0xffffffffu, in, o);
+			if (lane >= o) in += y;
+		}
+		incl[s] = in;
+		if (lane == 31) sWarp[s * kWarps + warp] = in;
 	}
-	if (lane == 31) sWarp[warp] = incl;
 	__syncthreads();
 	if (warp == 0) {
-		unsigned long long w = lane < kScanThreads / 32 ? sWarp[lane] : 0, wi = w;
+		// exclusive prefix over the V * 8 warp totals in item order (sub-tile major), then the tile's look-back
+		unsigned long long w = lane < V * kWarps ? sWarp[lane] : 0, wi = w;
 #pragma unroll
-		for (int o = 1; o < 8; o <<= 1) {
+		for (int o = 1; o < V * kWarps; o <<= 1) {
 			unsigned long long y = __shfl_up_sync(0xffffffffu, wi, o);
 			if (lane >= o) wi += y;
 		}
-		const unsigned long long blockAgg = __shfl_sync(0xffffffffu, wi, kScanThreads / 32 - 1);
-		if (lane < kScanThreads / 32) sWarp[lane] = wi - w;
+		const unsigned long long blockAgg = __shfl_sync(0xffffffffu, wi, V * kWarps - 1);
+		if (lane < V * kWarps) sWarp[lane] = wi - w;
 		unsigned long long excl = 0;
 		if (tile == 0) {
 			if (lane == 0) st_desc(io.desc, kDescIncl | blockAgg);
@@ -445,59 +459,65 @@ __device__ __forceinline__ void scan_body(const ScanIO& io)
 		if (lane == 0) sExcl = excl;
 	}
 	__syncthreads();
-	unsigned long long run = sExcl + sWarp[warp] + (incl - threadSum);
 
-	if (MODE == MODE_CELLS) {
-		int pre[kScanItems];
-		unsigned flags = 0;
-		const unsigned col0 = (unsigned)(io.globalBase + first) % (unsigned)io.plane; // once per thread, not per boundary cell (linear indices are < 2^31)
 #pragma unroll
-		for (int k = 0; k < kScanItems; k++) {
-			unsigned b = (unsigned)(run >> 31), ts = (unsigned)(run & 0x7fffffffu);
-			pre[k] = (int)b;
-			if (v[k] > 0) {
-				flags |= 1u << k;
-				io.boundaryIndex[b] = (int)(io.globalBase + first + k);
-				unsigned col = col0 + (unsigned)k; // < 2 * plane + 8: the column of cell first + k
-				while (col >= (unsigned)io.plane) col -= (unsigned)io.plane;
-				atomicAdd(io.colCells + col, 1);
-				io.bTriOff[b] = ts;
+	for (int s = 0; s < V; s++) {
+		const long long first = tileFirst + (long long)s * kScanTile;
+		unsigned long long run = sExcl + sWarp[s * kWarps + warp] + (incl[s] - threadSum[s]);
+		int v[kScanItems];
+		load8(first, v);
+		if (MODE == MODE_CELLS) {
+			int pre[kScanItems];
+			unsigned flags = 0;
+			const unsigned col0 = (unsigned)(io.globalBase + first) % (unsigned)io.plane; // once per thread, not per boundary cell (linear indices are < 2^31)
+#pragma unroll
+			for (int k = 0; k < kScanItems; k++) {
+				unsigned b = (unsigned)(run >> 31), ts = (unsigned)(run & 0x7fffffffu);
+				pre[k] = (int)b;
+				if (v[k] > 0) {
+					flags |= 1u << k;
+					io.boundaryIndex[b] = (int)(io.globalBase + first + k);
+					unsigned col = col0 + (unsigned)k; // < 2 * plane + 8: the column of cell first + k
+					while (col >= (unsigned)io.plane) col -= (unsigned)io.plane;
+					atomicAdd(io.colCells + col, 1);
+					io.bTriOff[b] = ts;
+				}
+				run += item_of(v[k]);
 			}
-			run += item[k];
-		}
-		if (first + kScanItems <= io.n) {
-			int4* p = reinterpret_cast<int4*>(io.prefix + first);
-			p[0] = make_int4(pre[0], pre[1], pre[2], pre[3]);
-			p[1] = make_int4(pre[4], pre[5], pre[6], pre[7]);
-			io.bmask[first >> 3] = (unsigned char)flags;
+			if (first + kScanItems <= io.n) {
+				int4* p = reinterpret_cast<int4*>(io.prefix + first);
+				p[0] = make_int4(pre[0], pre[1], pre[2], pre[3]);
+				p[1] = make_int4(pre[4], pre[5], pre[6], pre[7]);
+				io.bmask[first >> 3] = (unsigned char)flags;
+			} else {
+#pragma unroll
+				for (int k = 0; k < kScanItems; k++) if (first + k < io.n) io.prefix[first + k] = pre[k];
+				if (first < io.n) io.bmask[first >> 3] = (unsigned char)flags;
+			}
+			if (first <= io.n - 1 && io.n - 1 < first + kScanItems) { // the thread that owns the last item publishes the totals
+				unsigned nb = (unsigned)(run >> 31), tt = (unsigned)(run & 0x7fffffffu);
+				io.prefix[io.n] = (int)nb;
+				io.bTriOff[nb] = tt;
+				io.totals->nBoundary = nb;
+				io.totals->triTotal = tt;
+			}
 		} else {
 #pragma unroll
-			for (int k = 0; k < kScanItems; k++) if (first + k < io.n) io.prefix[first + k] = pre[k];
-			if (first < io.n) io.bmask[first >> 3] = (unsigned char)flags;
-		}
-		if (first <= io.n - 1 && io.n - 1 < first + kScanItems) { // the thread that owns the last item publishes the totals
-			unsigned nb = (unsigned)(run >> 31), tt = (unsigned)(run & 0x7fffffffu);
-			io.prefix[io.n] = (int)nb;
-			io.bTriOff[nb] = tt;
-			io.totals->nBoundary = nb;
-			io.totals->triTotal = tt;
-		}
-	} else {
-#pragma unroll
-		for (int k = 0; k < kScanItems; k++) {
-			if (first + k < io.n) io.off[first + k] = (unsigned)run;
-			run += item[k];
-		}
-		if (first <= io.n - 1 && io.n - 1 < first + kScanItems) {
-			io.off[io.n] = (unsigned)run;
-			if (io.totalOut) *io.totalOut = (unsigned)run;
-			if (io.totalOut64) *io.totalOut64 = run;
+			for (int k = 0; k < kScanItems; k++) {
+				if (first + k < io.n) io.off[first + k] = (unsigned)run;
+				run += item_of(v[k]);
+			}
+			if (first <= io.n - 1 && io.n - 1 < first + kScanItems) {
+				io.off[io.n] = (unsigned)run;
+				if (io.totalOut) *io.totalOut = (unsigned)run;
+				if (io.totalOut64) *io.totalOut64 = run;
+			}
 		}
 	}
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kScanThreads) k_scan(ScanIO io) { scan_body<MODE>(io); }
+template <int MODE, int V>
+__global__ void __launch_bounds__(kScanThreads) k_scan(ScanIO io) { scan_body<MODE, V>(io); }
 
 // up to three independent offset scans in one launch (blockIdx.y selects the scan; blocks beyond a scan's tile count leave)
 struct ScanIO3 { ScanIO s[3]; };
@@ -505,7 +525,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_offs3(ScanIO3 io3)
 {
 	const ScanIO& io = io3.s[blockIdx.y];
 	if ((long long)blockIdx.x * kScanTile >= io.n) return;
-	scan_body<MODE_OFFS>(io);
+	scan_body<MODE_OFFS, 1>(io);
 }
 
 // one launch instead of a dozen cudaMemsetAsync calls: zero up to 12 buffers (16-byte granules; every buffer carries >= 32 B of slack)
@@ -847,11 +867,26 @@ __global__ void __launch_bounds__(256, 3) k_l2_rays(GridP g, L2IO io)
 		u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz; u.inv101 = 1.f / (2.02f * g.h2z); u.inv099 = 1.f / (1.98f * g.h2z);
 		uint4 pk0 = make_uint4(0u, 0u, 0u, 0u), pk1 = pk0;
 		unsigned n = 0;
-		for (int k = 0; k < u.cnt; k++) {
-			RayTri s;
-			load_ray(s, io.ray48, io.colTris[u.off + k]);
-			RayCol rc;
-			if (s.ok && ray_column(s, u.ox, u.oy, rc)) rays_note(pk0, pk1, n, (unsigned)k);
+		// the walk is a chain of dependent loads (list entry -> ray record): four entries at a time keep four chains in flight
+		for (int k0 = 0; k0 < u.cnt; k0 += 4) {
+			int t[4];
+			float4 ra[4], rb[4], rc4[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) t[j] = k0 + j < u.cnt ? io.colTris[u.off + k0 + j] : -1;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if (t[j] >= 0) { ra[j] = __ldg(io.ray48 + (size_t)t[j] * 3); rb[j] = __ldg(io.ray48 + (size_t)t[j] * 3 + 1); rc4[j] = __ldg(io.ray48 + (size_t)t[j] * 3 + 2); }
+				else rc4[j] = make_float4(0.f, 0.f, 0.f, 0.f); // class 0: never hits
+			}
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if (rc4[j].w == 0.f) continue;
+				RayTri s;
+				s.v1x = ra[j].x; s.v1y = ra[j].y; s.v1z = ra[j].z; s.e1x = ra[j].w; s.e1y = rb[j].x; s.e1z = rb[j].y; s.e2x = rb[j].z; s.e2y = rb[j].w;
+				s.e2z = rc4[j].x; s.det = rc4[j].y; s.inv = rc4[j].z; s.ok = true; s.well = false;
+				RayCol rc;
+				if (ray_column(s, u.ox, u.oy, rc)) rays_note(pk0, pk1, n, (unsigned)(k0 + j));
+			}
 		}
 		rays_apply(g, io, u, pk0, pk1, n);
 	}

@@ -250,3 +250,19 @@ def test_peer_memory_gather_equals_whole(product, ctx, tmp_path_factory, name, l
     finally:
         for c in ranks:
             c.close()
+
+
+def test_large_grid_paths_match_oracle(product, oracle, ctx, tmp_path_factory):
+    """A grid beyond 16 M cells takes the 4-sub-tile boundary scan (k_scan<CELLS, 4>) and, at n2 = 2, the flat multi-cell pair
+    space of k_l2 with 64 cells per CTA: every stream against the oracle (certified fill; ~25 M cells, n2 = 2)."""
+    path = mesh_path("torus", tmp_path_factory.getbasetemp())
+    mesh = product.load_mesh(path)
+    res = ctx.voxelize(mesh, product.Params(448, 2, product.GPV_KEEP_LISTS))
+    assert res.cells > (16 << 20)
+    ores = oracle.OracleMesh(path).voxelize(448, 2, oracle.FILL_CERTIFIED | oracle.NO_NORMALS, 8)
+    assert res.counts == ores.counts
+    assert np.array_equal(res.level1_inout(), ores.l1_state * 127)
+    assert np.array_equal(res.prefix(), ores.prefix)
+    assert np.array_equal(res.boundary_index(), ores.boundary_index)
+    assert np.array_equal(res.level2_inout(), ores.l2_state * 127)
+    assert np.array_equal(res.cell_tris(), ores.cell_tris)
