@@ -322,18 +322,30 @@ GPV_HD RayColZ ray_col_bound(const RayTri& s, const RayCol& c, float zMin, float
 //   t0 + 4 bnd - 0.99 d_r <= eps  ->  sub-voxel r (and every higher one) is not hit   (t_r <= t0 + bnd_0 + bnd_r - 0.998 d_r)
 // The two index estimates only choose where to start; both claims are checked against the actual centres, and the sub-voxels
 // between them (none or one, as the gap is 2 % of the height plus 6 bnd) are evaluated.
-GPV_HD unsigned ray_cell_mask(const RayTri& s, const RayCol& c, const RayColZ& z, float midz, float h1z, float h2z, int n2)
+// Fast classification of one cell: 0 = no sub-voxel is hit, 1 = every sub-voxel is hit, 2 = undecided (the crossing lies in or
+// next to the cell, or there is no certificate): call ray_cell_mask_exact.  Split from the exact part so that a warp can run the
+// cheap classification over many cells first and then the exact part with all undecided lanes together.
+GPV_HD int ray_cell_class(const RayTri& s, const RayCol& c, const RayColZ& z, float midz, float h1z, float h2z)
 {
-	const unsigned full = n2 >= 32 ? 0xffffffffu : ((1u << n2) - 1u);
+	if (!(z.k1 >= 0.f)) return 2;
+	const float t0 = ray_cell_t(s, c, l2_centre(0, h2z, midz, h1z));
+	const float bnd = z.k1 + 9.5367431640625e-07f * fabsf(t0); // >= ray_z_run's bound for this cell (column-wide |Tz| and span)
+	if (t0 + 2.f * bnd <= kEps) return 0;              // every comparison is false for NaN / inf: undecided
+	if (t0 - 2.f * bnd - z.span > kEps) return 1;
+	return 2;
+}
+
+// The undecided cells: certified hit prefix, certified miss suffix, exact evaluation in between (or of every sub-voxel when
+// there is no certificate).
+GPV_HD unsigned ray_cell_mask_exact(const RayTri& s, const RayCol& c, const RayColZ& z, float midz, float h1z, float h2z, int n2)
+{
 	const float zLo = l2_centre(0, h2z, midz, h1z);
 	int first = 0, last = n2; // sub-voxels [first, last) are evaluated; below first: hit, from last on: not hit
 	if (z.k1 >= 0.f) {
 		const float t0 = ray_cell_t(s, c, zLo);
-		const float bnd = z.k1 + 9.5367431640625e-07f * fabsf(t0); // >= ray_z_run's bound for this cell (column-wide |Tz| and span)
-		if (t0 + 2.f * bnd <= kEps) return 0u;          // every comparison is false for NaN / inf: falls through to plain evaluation
-		const float hi = t0 - 2.f * bnd;
-		if (hi - z.span > kEps) return full;
+		const float bnd = z.k1 + 9.5367431640625e-07f * fabsf(t0);
 		if (bnd <= kFltMax && t0 == t0) {
+			const float hi = t0 - 2.f * bnd;
 			const float A = (hi - kEps) * z.inv101;
 			int a = A >= 0.f ? (A < (float)n2 ? (int)A : n2 - 1) : -1;
 			while (a >= 0 && !(hi - 1.01f * (l2_centre(a, h2z, midz, h1z) - zLo) > kEps)) a--;
@@ -348,6 +360,14 @@ GPV_HD unsigned ray_cell_mask(const RayTri& s, const RayCol& c, const RayColZ& z
 	unsigned mask = first >= 32 ? 0xffffffffu : ((1u << first) - 1u);
 	for (int r = first; r < last; r++) mask |= (unsigned)(ray_cell_t(s, c, l2_centre(r, h2z, midz, h1z)) > kEps) << r;
 	return mask;
+}
+
+GPV_HD unsigned ray_cell_mask(const RayTri& s, const RayCol& c, const RayColZ& z, float midz, float h1z, float h2z, int n2)
+{
+	const int cls = ray_cell_class(s, c, z, midz, h1z, h2z);
+	if (cls == 0) return 0u;
+	if (cls == 1) return n2 >= 32 ? 0xffffffffu : ((1u << n2) - 1u);
+	return ray_cell_mask_exact(s, c, z, midz, h1z, h2z, n2);
 }
 
 // ---- certified candidate columns for the +Z parity fill of one triangle (DESIGN.md "Certified fill").
