@@ -63,7 +63,7 @@ struct gpv_ctx {
 	int device = 0;
 	int smCount = 0;
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
-	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, longList, colCellCnt, colCellOff, colCellList, l2Par, cellMid;
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, aabbxy16, longList, colCellCnt, colCellOff, colCellList, l2Par, cellMid;
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {}, evEnd[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
@@ -152,7 +152,7 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->longList, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->aabbxy16, &c->longList, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
 	gpv_gather_detach(c);
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
@@ -270,7 +270,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	    c->tabZ.ensure((size_t)g.nz * 4) || c->cellCount.ensure((size_t)cells * 4 + 32) || c->colCount.ensure((size_t)ncol * 4 + 32) ||
 	    c->crossCount.ensure((size_t)ncol * 4 + 32) || c->prefix.ensure((size_t)(cells + 1) * 4 + 32) || c->bmask.ensure((size_t)cells / 8 + 64) ||
 	    c->boundaryIndex.ensure((size_t)cells * 4 + 32) || c->bTriOff.ensure((size_t)(cells + 1) * 4 + 32) || c->colOff.ensure((size_t)(ncol + 1) * 4 + 32) ||
-	    c->crossOff.ensure((size_t)(ncol + 1) * 4 + 32) || c->l1State.ensure((size_t)cells + 32) || c->crossFp.ensure((size_t)nTri * 16) || c->plane16.ensure((size_t)nTri * 16) ||
+	    c->crossOff.ensure((size_t)(ncol + 1) * 4 + 32) || c->l1State.ensure((size_t)cells + 32) || c->crossFp.ensure((size_t)nTri * 16) || c->plane16.ensure((size_t)nTri * 16) || c->aabbxy16.ensure((size_t)nTri * 16) ||
 	    c->binCnt.ensure((size_t)nTri * 4 + 32) || c->binOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->crossCnt.ensure((size_t)nTri * 4 + 32) ||
 	    c->crossWorkOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->colCellCnt.ensure((size_t)ncol * 4 + 32) || c->colCellOff.ensure((size_t)(ncol + 1) * 4 + 32))
 		return 1;
@@ -303,7 +303,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	{
 		int m = g.nx > g.ny ? g.nx : g.ny; m = m > g.nz ? m : g.nz;
 		m = m > nTri ? m : nTri; // k_prepare also fills the per-axis centre tables
-		k_prepare<<<(m + 255) / 256, 256, 0, st>>>(d_tris, nTri, g, tri48, ray48, c->plane16.as<float4>(), c->crossFp.as<int4>(), c->binCnt.as<int>(), c->crossCnt.as<int>(), dT, cx, cy, cz);
+		k_prepare<<<(m + 255) / 256, 256, 0, st>>>(d_tris, nTri, g, tri48, ray48, c->plane16.as<float4>(), c->aabbxy16.as<float4>(), c->crossFp.as<int4>(), c->binCnt.as<int>(), c->crossCnt.as<int>(), dT, cx, cy, cz);
 		launches++;
 	}
 	// balanced work spaces: exclusive scans of the per-triangle item counts; totals stay on the device (persistent grids read them)
@@ -436,7 +436,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	L2IO lio{};
 	mark(GPV_PHASE_L2_RAYS);
 	if (wantL2 && nB > 0) {
-		lio.tri48 = tri48; lio.ray48 = ray48; lio.plane16 = c->plane16.as<float4>(); lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
+		lio.tri48 = tri48; lio.ray48 = ray48; lio.plane16 = c->plane16.as<float4>(); lio.aabbxy16 = c->aabbxy16.as<float4>(); lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
 		lio.cellTris = c->cellTris.as<int>(); lio.colOff = c->colOff.as<unsigned>(); lio.colCount = c->colCount.as<int>(); lio.colTris = c->colTris.as<int>();
 		lio.cx = cx; lio.cy = cy; lio.cz = cz; lio.nBoundary = (int)nB; lio.totals = dT;
 		lio.l2State = gather ? c->gather.l2 : c->l2State.as<unsigned char>(); lio.l2Base = gather ? &dT->gatherBase : nullptr;

@@ -77,13 +77,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 //          w0 = lox | loy<<16, w1 = loz | dx<<16, w2 = dy | dz<<16
 //   ray48  v1xyz e1xyz e2xyz det inv ok  (gpv::RayTri)
 //   plane16 plane record of the certified Level-2 plane culling, normalised by Nz (gpv::PlaneRec on permuted axes)
+//   aabbxy16 xmin xmax ymin ymax of the triangle: the x / y AABB predicates of the SAT per sub-voxel column, exactly
+//           (fl(t - c) is monotone in t, so min_i fl(t_i - c) = fl(min_i t_i - c))
 //   crossFp i0 | j0<<16, di | dj<<16, kind, -   certified candidate columns of the +Z parity fill (gpv::fill_candidates)
 //   binCnt / crossCnt  number of (triangle, cell) / (triangle, column) work items
 // All records are 16-byte aligned so that contiguous triangle ranges can be moved by TMA bulk copies.
 // Centre tables: centre[p] = fl32((p + 0.5) * ext * 2 + min) evaluated in double exactly like cu:382-384 (== ray origin
 // src/Object.cpp:743-745 == mid point :2567-2569, see oracle/gpv_oracle.c gpvo_axis_table).
 __global__ void __launch_bounds__(256) k_prepare(const float* __restrict__ flat, long long nTri, GridP g, float4* __restrict__ tri48,
-                                                 float4* __restrict__ ray48, float4* __restrict__ plane16, int4* __restrict__ crossFp,
+                                                 float4* __restrict__ ray48, float4* __restrict__ plane16, float4* __restrict__ aabbxy16, int4* __restrict__ crossFp,
                                                  int* __restrict__ binCnt, int* __restrict__ crossCnt, Totals* totals, float* cx, float* cy, float* cz)
 {
 	__shared__ float s[256 * 9];
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(256) k_prepare(const float* __restrict__ flat,
 		// normalised by Nz, for intervals along a sub-voxel column: the same function on cyclically permuted coordinates (x,y,z) <- (z,x,y)
 		PlaneRec pl = plane_rec_setup(v[2], v[0], v[1], v[5], v[3], v[4], v[8], v[6], v[7], g.gsz, g.gsx, g.gsy, g.h2z, g.h2x, g.h2y);
 		plane16[base + t] = make_float4(pl.sx, pl.ny, pl.nz, pl.R);
+		aabbxy16[base + t] = make_float4(fminf(v[0], fminf(v[3], v[6])), fmaxf(v[0], fmaxf(v[3], v[6])), fminf(v[1], fminf(v[4], v[7])), fmaxf(v[1], fmaxf(v[4], v[7])));
 		int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
 		int kind = fill_candidates(r, g.minx, g.miny, g.gsx, g.gsy, g.nx, g.ny, i0, i1, j0, j1);
 		if (kind == 2) { i0 = 0; j0 = 0; i1 = g.nx - 1; j1 = g.ny - 1; ill = 1; }
@@ -698,7 +701,7 @@ __global__ void __launch_bounds__(kSortLongThreads) k_sort_long(const unsigned* 
 // vector store of final file bytes (n2 = 16: 128-bit; rows of a CTA are contiguous in Level2InOut.raw).
 // Sub-voxel centre (cu:423-425 / 472-474): ((2p+1)*ext2 + mid) - ext1, all f32.
 struct L2IO {
-	const float4* tri48; const float4* ray48; const float4* plane16;
+	const float4* tri48; const float4* ray48; const float4* plane16; const float4* aabbxy16;
 	const int* boundaryIndex; const unsigned* bTriOff; const int* cellTris;
 	const unsigned* colOff; const int* colCount; const int* colTris;
 	const unsigned* colCellOff; const int2* colCellList; // boundary cells (slab-local rank, centre height) of every Level-1 column, CSR
@@ -1058,9 +1061,17 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 							k = pr >> 8; // rows == kL2Threads == 256: the pair's column is this thread's
 							t = io.cellTris[sInfo[0] + k];
 						}
-						const float4 A = __ldg(io.tri48 + (size_t)t * 3), pl = __ldg(io.plane16 + t);
-						PlaneRec P; P.sx = pl.x; P.ny = pl.y; P.nz = pl.z; P.R = pl.w;
-						alive = plane_row_interval(P, A.z - cz0, A.x - cx2, A.y - cy2, inv2h, slack, n2, rlo, rhi);
+						bool inBox = true;
+						if (kFlat) { // the exact x / y AABB predicates of this column (cu:284-292) from the triangle's extent: small triangles
+							         // (1-2 cells across) miss most columns of a cell; n2 = 16 models have triangles larger than their cells
+							const float4 bb = __ldg(io.aabbxy16 + t);
+							inBox = !(bb.x - cx2 > g.h2x || bb.y - cx2 < -g.h2x || bb.z - cy2 > g.h2y || bb.w - cy2 < -g.h2y);
+						}
+						if (inBox) {
+							const float4 A = __ldg(io.tri48 + (size_t)t * 3), pl = __ldg(io.plane16 + t);
+							PlaneRec P; P.sx = pl.x; P.ny = pl.y; P.nz = pl.z; P.R = pl.w;
+							alive = plane_row_interval(P, A.z - cz0, A.x - cx2, A.y - cy2, inv2h, slack, n2, rlo, rhi);
+						}
 					}
 					const unsigned m = __ballot_sync(0xffffffffu, alive);
 					if (m) {
