@@ -104,7 +104,7 @@ static int preload_kernels()
 #define GPV_LOAD(...) GPV_CUDA(cudaFuncGetAttributes(&a, __VA_ARGS__))
 	GPV_LOAD(k_clear); GPV_LOAD(k_prepare); GPV_LOAD(k_scan_offs3); GPV_LOAD((k_scan<MODE_CELLS, 1>)); GPV_LOAD((k_scan<MODE_CELLS, 4>));
 	GPV_LOAD(k_bin<false>); GPV_LOAD(k_bin<true>); GPV_LOAD(k_cross<false>); GPV_LOAD(k_cross<true>); GPV_LOAD(k_fill_sweep);
-	GPV_LOAD(k_sort_segments<false>); GPV_LOAD(k_sort_segments<true>); GPV_LOAD(k_sort_long<false>); GPV_LOAD(k_sort_long<true>);
+	GPV_LOAD(k_sort_segments); GPV_LOAD(k_sort_long);
 	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals);
 	GPV_LOAD(k_l2<16, false>); GPV_LOAD(k_l2<8, false>); GPV_LOAD(k_l2<4, false>); GPV_LOAD(k_l2<2, false>); GPV_LOAD(k_l2<0, false>);
 	GPV_LOAD(k_l2<16, true>); GPV_LOAD(k_l2<8, true>); GPV_LOAD(k_l2<4, true>); GPV_LOAD(k_l2<2, true>); GPV_LOAD(k_l2<0, true>);
@@ -402,17 +402,14 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		int* longCells = c->longList.as<int>() + 16;
 		int* longCols = longCells + nB;
 		if (!c->sortAttrSet) { // function attributes are per device: once per context, not once per process
-			GPV_CUDA(cudaFuncSetAttribute(k_sort_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortLongSmem * 4));
-			GPV_CUDA(cudaFuncSetAttribute(k_sort_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortLongSmem * 4));
+			GPV_CUDA(cudaFuncSetAttribute(k_sort_long, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortLongSmem * 4));
 			c->sortAttrSet = true;
 		}
-		if (nB > 0) {
-			k_sort_segments<false><<<(unsigned)((nB * 32 + 255) / 256), 256, 0, st>>>(c->bTriOff.as<unsigned>(), (int)nB, c->cellTris.as<int>(), nullptr, longCells, longCnt);
-			k_sort_long<false><<<c->smCount, kSortLongThreads, kSortLongSmem * 4, st>>>(c->bTriOff.as<unsigned>(), longCells, longCnt, c->cellTris.as<int>(), nullptr);
-			launches += 2;
-		}
-		k_sort_segments<true><<<(unsigned)((ncol * 32 + 255) / 256), 256, 0, st>>>(c->colOff.as<unsigned>(), (int)ncol, c->colTris.as<int>(), c->colCount.as<int>(), longCols, longCnt + 1);
-		k_sort_long<true><<<c->smCount, kSortLongThreads, kSortLongSmem * 4, st>>>(c->colOff.as<unsigned>(), longCols, longCnt + 1, c->colTris.as<int>(), c->colCount.as<int>());
+		const SortSeg sc = { c->bTriOff.as<unsigned>(), (int)nB, c->cellTris.as<int>(), nullptr, longCells, longCnt };
+		const SortSeg sk = { c->colOff.as<unsigned>(), (int)ncol, c->colTris.as<int>(), c->colCount.as<int>(), longCols, longCnt + 1 };
+		const long long segs = std::max<long long>(nB, ncol);
+		k_sort_segments<<<dim3((unsigned)((segs * 32 + 255) / 256), 2), 256, 0, st>>>(sc, sk);
+		k_sort_long<<<dim3(c->smCount, 2), kSortLongThreads, kSortLongSmem * 4, st>>>(sc, sk);
 		launches += 2;
 	}
 	mark(GPV_PHASE_L1_NORMALS);

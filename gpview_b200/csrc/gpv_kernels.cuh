@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(256) k_clear(ClearList cl)
 constexpr int kSortSmem = 128; // longest list the warp-per-list kernel takes (rank sort in shared memory); longer ones go to k_sort_long
 
 template <bool UNIQUE>
-__global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restrict__ off, int nSeg, int* data, int* uniqueCount, int* longList, unsigned* longCount)
+__device__ __forceinline__ void sort_segments_body(const unsigned* __restrict__ off, int nSeg, int* data, int* uniqueCount, int* longList, unsigned* longCount)
 {
 	const int lane = threadIdx.x & 31;
 	const int seg = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restric
 	if (len <= 32) {
 		int x = lane < len ? a[lane] : 0x7fffffff;
 		int rank = 0;
-		for (int j = 0; j < 32; j++) {
+		for (int j = 0; j < len; j++) { // lanes >= len hold INT_MAX and rank behind every entry: only the list's own entries are compared
 			int y = __shfl_sync(0xffffffffu, x, j);
 			rank += (y < x) || (y == x && j < lane);
 		}
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restric
 		if (!UNIQUE) { if (lane < len) a[rank] = x; return; }
 		// sorted value of position `lane` = the x whose rank == lane: exchange through shuffles
 		int sorted = 0x7fffffff;
-		for (int j = 0; j < 32; j++) {
+		for (int j = 0; j < len; j++) {
 			int y = __shfl_sync(0xffffffffu, x, j), ry = __shfl_sync(0xffffffffu, rank, j);
 			if (ry == lane) sorted = y;
 		}
@@ -629,15 +629,22 @@ __global__ void __launch_bounds__(256) k_sort_segments(const unsigned* __restric
 	}
 }
 
+// cell lists (blockIdx.y = 0) and column lists (blockIdx.y = 1, de-duplicated) in one launch
+struct SortSeg { const unsigned* off; int nSeg; int* data; int* uniqueCount; int* longList; unsigned* longCount; };
+__global__ void __launch_bounds__(256) k_sort_segments(SortSeg cells, SortSeg cols)
+{
+	if (blockIdx.y == 0) sort_segments_body<false>(cells.off, cells.nSeg, cells.data, nullptr, cells.longList, cells.longCount);
+	else sort_segments_body<true>(cols.off, cols.nSeg, cols.data, cols.uniqueCount, cols.longList, cols.longCount);
+}
+
 // Long lists: one CTA of 1024 threads per list, same all-ascending bitonic network with CTA barriers; up to kSortLongSmem
 // entries in (opt-in, 64 KB) dynamic shared memory, in place in global memory beyond that.
 constexpr int kSortLongThreads = 1024, kSortLongSmem = 16384;
 
 template <bool UNIQUE>
-__global__ void __launch_bounds__(kSortLongThreads) k_sort_long(const unsigned* __restrict__ off, const int* __restrict__ longList,
-                                                               const unsigned* __restrict__ longCount, int* data, int* uniqueCount)
+__device__ __forceinline__ void sort_long_body(const unsigned* __restrict__ off, const int* __restrict__ longList,
+                                               const unsigned* __restrict__ longCount, int* data, int* uniqueCount, int* sLong)
 {
-	extern __shared__ int sLong[];
 	__shared__ int sW;
 	const int tid = threadIdx.x;
 	for (unsigned w = blockIdx.x; w < *longCount; w += gridDim.x) {
@@ -692,6 +699,13 @@ __global__ void __launch_bounds__(kSortLongThreads) k_sort_long(const unsigned* 
 		}
 		__syncthreads();
 	}
+}
+
+__global__ void __launch_bounds__(kSortLongThreads) k_sort_long(SortSeg cells, SortSeg cols)
+{
+	extern __shared__ int sLongDyn[];
+	if (blockIdx.y == 0) sort_long_body<false>(cells.off, cells.longList, cells.longCount, cells.data, nullptr, sLongDyn);
+	else sort_long_body<true>(cols.off, cols.longList, cols.longCount, cols.data, cols.uniqueCount, sLongDyn);
 }
 
 // ------------------------------------------------------------------------------------------------ k_l2
