@@ -385,7 +385,7 @@ def main():
         fp32_peak = ctx.fp32_peak()
         hbm_peak, hbm_src = measured_peaks()
         ncu = ncu_traffic().get("kernels", {})
-        sat_name = "k_l2<%d, %s>" % (args.l2 if args.l2 in (2, 4, 8, 16) else 0, "true" if (world > 1 and args.gather == "peer") else "false")
+        sat_name = "k_l2<%d, %s>" % (args.l2 if args.l2 in (2, 4, 8, 16) else 0, "1" if (world > 1 and args.gather == "peer") else "0")
         n_sat, n_rays = ncu.get(sat_name, {}), ncu.get("k_l2_rays", {})
         flops = FLOPS_PER_TRIBOX * res.stats["l2_box_tests"]
         ach = flops / (k_l2_ms * 1e-3) / 1e12

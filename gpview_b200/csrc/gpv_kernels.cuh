@@ -1002,8 +1002,8 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 		if (b < io.nBoundary) { off = (int)io.bTriOff[b]; cnt = (int)(io.bTriOff[b + 1] - io.bTriOff[b]); }
 		sInfo[gi * 2] = off; sInfo[gi * 2 + 1] = cnt;
 	}
-	__syncthreads();
-	if (tid < 32) { // exclusive prefix of the cells' pair counts (rows * triangles), one warp
+	if (N2 != 16) __syncthreads();
+	if (N2 != 16 && tid < 32) { // exclusive prefix of the cells' pair counts (rows * triangles), one warp (n2 = 16: one cell, not needed)
 		int* pre = sInfo + 2 * G + 1;
 		int carry = 0;
 		for (int g0 = 0; g0 < G; g0 += 32) {
