@@ -216,8 +216,10 @@ def main():
     whole = ctx.voxelize_device(d_tris, mesh, gpv.Params(args.l1, args.l2, gpv.GPV_NO_LEVEL2), sptr)
     nz = int(whole.num_div[2]); plane = int(whole.num_div[0]) * int(whole.num_div[1])
     cuts = [0, nz]
-    if world > 1:
-        cuts = sharded.plan_slabs(sharded.layer_cost(whole.boundary_index(), whole.cell_off(), plane, nz), world)
+    layer0 = None
+    if world > 1:  # (the pre-pass result views die with the next call on the ctx: take the cost model now)
+        layer0 = sharded.layer_cost(whole.boundary_index(), whole.cell_off(), plane, nz).astype(np.float64)
+        cuts = sharded.plan_slabs(layer0, world)
         z0, z1 = cuts[rank], cuts[rank + 1]
     peer = world > 1 and args.gather == "peer"
     n23 = args.l2 ** 3
@@ -253,25 +255,41 @@ def main():
         res = step()
     barrier()
     if world > 1:
-        # Untimed load balancing: the a-priori cost model only knows list lengths.  Rescale every slab's layer costs to the Level-2
-        # time its rank measured, re-cut, repeat; every rank derives the same cuts from the all-gathered times (no data moves).
-        layer = sharded.layer_cost(whole.boundary_index(), whole.cell_off(), plane, nz).astype(np.float64) + 1e-9
+        # Untimed load balancing: the a-priori cost model only knows list lengths.  Rescale every slab's layer costs to the device
+        # time its rank measured (every phase but the final wait for the other ranks), re-cut, repeat; keep the best cuts seen.
+        # Every rank derives the same cuts from the all-gathered times (no data moves).
+        layer = layer0 + 1e-9
+
+        def measured(r):
+            t = torch.tensor([sum(v for k, v in r.phase_ms.items() if k not in ("l2_normals", "host_gap"))], device="cuda", dtype=torch.float64)
+            out = torch.zeros(world, device="cuda", dtype=torch.float64)
+            dist.all_gather_into_tensor(out, t)
+            return out.cpu().numpy()
+
+        def set_cuts(c):
+            params.c.z0, params.c.z1 = c[rank], c[rank + 1]
+
+        t_all = measured(res)
+        best = (float(t_all.max()), list(cuts))
         for _ in range(4):
-            t_mine = torch.tensor([res.phase_ms.get("l2_rays", 0.0) + res.phase_ms.get("l2", 0.0)], device="cuda", dtype=torch.float64)
-            t_all = torch.zeros(world, device="cuda", dtype=torch.float64)
-            dist.all_gather_into_tensor(t_all, t_mine)
-            t_all = t_all.cpu().numpy()
-            if t_all.max() < 1.08 * t_all.mean():
+            if t_all.max() < 1.05 * t_all.mean():
                 break
             for r in range(world):
                 sl = slice(cuts[r], cuts[r + 1])
                 layer[sl] *= max(t_all[r], 1e-6) / layer[sl].sum()
             cuts = sharded.plan_slabs(layer, world)
-            params.c.z0, params.c.z1 = cuts[rank], cuts[rank + 1]
-            z0, z1 = cuts[rank], cuts[rank + 1]
+            set_cuts(cuts)
             for _ in range(2):
                 res = step()
             barrier()
+            t_all = measured(res)
+            if float(t_all.max()) < best[0]:
+                best = (float(t_all.max()), list(cuts))
+        cuts = best[1]
+        set_cuts(cuts)
+        z0, z1 = cuts[rank], cuts[rank + 1]
+        res = step()
+        barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches, phase_acc = 0, {}
     t_timed0 = time.perf_counter()
