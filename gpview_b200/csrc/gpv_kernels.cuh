@@ -8,11 +8,13 @@
 //   k_bin<FILL>     K1  triangle -> Level-1 cell SAT binning (count / fill sweeps), TMA-staged triangle tiles
 //   k_cross<FILL>   K2a certified (column, triangle) crossing detection for the parity fill
 //   k_fill_sweep    K2b +Z parity sweep per Level-1 column, coalesced along x, final Level-1 state bytes
-//   k_scan<MODE>    K3  single-pass decoupled-look-back scan: boundary prefix sum / index compaction / CSR offsets
-//   k_sort_segments canonical (ascending) order of every cell / column list; de-duplicates column lists
-//   k_col_cells, k_l2_rays  K4a Level-2 parity rays per sub-voxel column of each Level-1 column
-//   k_l2            K4  Level-2 refinement: hoisted SAT per sub-voxel row over shared-memory queues, 128-bit row stores
+//   k_scan<MODE,V>  K3  single-pass decoupled-look-back scan: boundary prefix sum / index compaction / per-column cell counts;
+//   k_scan_offs3        up to three CSR offset scans per launch
+//   k_sort_segments, k_sort_long   canonical (ascending) order of every cell / column list; de-duplicates column lists
+//   k_col_cells, k_l2_rays  K4a Level-2 parity rays per sub-voxel column of each Level-1 column (certified cell masks)
+//   k_l2<N2,GATHER> K4  Level-2 SAT hoisted along z per sub-voxel column, three stages over shared-memory queues, final bytes
 //   k_l1_normals, k_l2_normals   K5 normals in the reference's uchar encoding
+//   k_gather_*      multi-GPU: slab streams written into the gathering rank's buffers over NVLink peer memory (8-byte mailbox)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
