@@ -791,24 +791,26 @@ __device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const
 			RayCol rc;
 			if (!ray_column(s, u.ox, u.oy, rc)) continue; // cannot happen (listed because it passed); keeps rc defined
 			const RayColZ k1 = ray_col_bound(s, rc, u.zMin, u.zMax, g.gsz, u.inv101, u.inv099);
-			// cheap classification of every cell of the chunk first (no hit / all hit / undecided) ...
+			// two heights per crossing classify every cell of the chunk with two comparisons (gpv::ray_col_thresholds: all hit below
+			// zAll, no hit from zNone on) ...
+			const RayThr thr = ray_col_thresholds(s, rc, k1, u.zMin, u.zMax);
 			unsigned undecided = 0;
 #pragma unroll
 			for (int c = 0; c < kRayCells; c++) {
 				if (bb[c] < 0) continue;
-				const int cls = ray_cell_class(s, rc, k1, midz[c], g.h1z, g.h2z);
-				if (cls == 1) par[c] ^= fullRun;
-				else if (cls == 2) undecided |= 1u << c;
+				const float zLoC = l2_centre(0, g.h2z, midz[c], g.h1z), zHiC = l2_centre(g.n2 - 1, g.h2z, midz[c], g.h1z);
+				if (zHiC < thr.zAll) par[c] ^= fullRun;
+				else if (!(zLoC >= thr.zNone)) undecided |= 1u << c;
 			}
-			// ... then the exact masks of the undecided ones (normally the one cell that holds the crossing), one per lane and round:
-			// the lanes of a warp run this part together although their crossings lie in different cells
+			// ... the cells in between (normally the one that holds the crossing) get their masks from gpv::ray_cell_mask, one per lane
+			// and round: the lanes of a warp run this part together although their crossings lie in different cells
 			while (undecided) {
 				const int c = __ffs(undecided) - 1;
 				undecided &= undecided - 1;
 				float mz = midz[0];
 #pragma unroll
 				for (int q = 1; q < kRayCells; q++) if (q == c) mz = midz[q];
-				const unsigned m = ray_cell_mask_exact(s, rc, k1, mz, g.h1z, g.h2z, g.n2);
+				const unsigned m = ray_cell_mask(s, rc, k1, mz, g.h1z, g.h2z, g.n2);
 #pragma unroll
 				for (int q = 0; q < kRayCells; q++) if (q == c) par[q] ^= m;
 			}

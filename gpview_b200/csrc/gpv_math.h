@@ -322,6 +322,40 @@ GPV_HD RayColZ ray_col_bound(const RayTri& s, const RayCol& c, float zMin, float
 //   t0 + 4 bnd - 0.99 d_r <= eps  ->  sub-voxel r (and every higher one) is not hit   (t_r <= t0 + bnd_0 + bnd_r - 0.998 d_r)
 // The two index estimates only choose where to start; both claims are checked against the actual centres, and the sub-voxels
 // between them (none or one, as the gap is 2 % of the height plus 6 bnd) are evaluated.
+// ---- per (triangle, sub-voxel column): two heights that classify most cells of the grid column without evaluating anything per
+// cell.  With t falling at slope in [0.998, 1.002] and every f32 t of the column within bndc = k1 + 16u(|t| + 2.2 H) of the
+// exact one (H = height of the grid column; ray_z_run's bound with the column-wide |Tz| and span):
+//   claim 1 (ray_z_run "all hit", run [zMin, z]):   t(zMin) - 2 bndc - 1.01 (z - zMin) > eps  ->  every centre in [zMin, z] is hit
+//   a second evaluation at zr = that height (clamped to the column) tightens both sides, the slope uncertainty now acting on
+//   the short distance from zr to the crossing instead of on the whole column:
+//   claim 2 (same, run [zr, z]):                     t(zr) - 2 bndc - 1.01 (z - zr) > eps      ->  every centre in [zr, z] is hit
+//   claim 3 (t_z <= t_zr + 2 bndc - 0.998 (z - zr)): t(zr) + 4 bndc - 0.99 (z - zr) <= eps     ->  no centre at or above z is hit (z >= zr)
+// A cell whose highest centre lies below zAll is all hit, one whose lowest centre lies at or above zNone is not hit at all;
+// only the cells in between (the one that holds the crossing, sometimes a neighbour) go through ray_cell_class / _exact.
+// The margins absorb the f32 rounding of the threshold arithmetic itself.  No certificate (k1 < 0): zAll = -inf, zNone = +inf.
+struct RayThr { float zAll, zNone; };
+GPV_HD RayThr ray_col_thresholds(const RayTri& s, const RayCol& c, const RayColZ& z, float zMin, float zMax)
+{
+	RayThr r;
+	r.zAll = -INFINITY; r.zNone = INFINITY;
+	if (!(z.k1 >= 0.f)) return r;
+	const float H = zMax - zMin;
+	const float t1 = ray_cell_t(s, c, zMin);
+	const float b1 = z.k1 + 9.5367431640625e-07f * (fabsf(t1) + 2.2f * H);
+	const float mg = 1.9073486328125e-06f * (fabsf(zMin) + fabsf(zMax) + fabsf(t1)) + 1e-30f; // 32u of the magnitudes involved
+	float zr = zMin + (t1 - 2.f * b1 - kEps) * 0.9900990128517151f - mg; // 1 / 1.01
+	if (!(zr > zMin)) zr = zMin; // (also NaN)
+	if (zr > zMax) zr = zMax;
+	const float t2 = ray_cell_t(s, c, zr);
+	const float b2 = z.k1 + 9.5367431640625e-07f * (fabsf(t2) + 2.2f * H);
+	const float za = zr + (t2 - 2.f * b2 - kEps) * 0.9900990128517151f - mg;
+	const float zn = zr + (t2 + 4.f * b2 - kEps) * 1.0101009607315063f + mg;  // 1 / 0.99
+	if (!(b1 <= kFltMax) || !(b2 <= kFltMax) || !(t1 == t1) || !(t2 == t2)) return r;
+	r.zAll = za;                 // NaN compares false everywhere: no cell is classified by it
+	r.zNone = zn > zr ? zn : zr; // claim 3 speaks about heights at or above zr only
+	return r;
+}
+
 // Fast classification of one cell: 0 = no sub-voxel is hit, 1 = every sub-voxel is hit, 2 = undecided (the crossing lies in or
 // next to the cell, or there is no certificate): call ray_cell_mask_exact.  Split from the exact part so that a warp can run the
 // cheap classification over many cells first and then the exact part with all undecided lanes together.

@@ -160,3 +160,37 @@ extern "C" void probe_cell_mask(int64_t n, const float* oxy, const float* cellz,
 	}
 	out3[0] = bad; out3[1] = passed; out3[2] = mixed;
 }
+
+// ---- ray_col_thresholds: for cells at many heights of a grid column [zMin, zMax] the threshold classification (all hit below
+// zAll, no hit from zNone on) must agree with n2 independent ray_cell evaluations.  colz: zMin, gs (cell size), ncell per item.
+// out4: [0] mismatches, [1] passing pairs, [2] cells classified by a threshold, [3] cells checked
+extern "C" void probe_col_thresholds(int64_t n, const float* oxy, const float* colz, int n2, const float* tri9, int64_t* out4)
+{
+	int64_t bad = 0, passed = 0, byThr = 0, cells = 0;
+	for (int64_t i = 0; i < n; i++) {
+		const float* T = tri9 + i * 9;
+		RayTri s; RayCol rc;
+		ray_tri_setup(s, T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8]);
+		if (!s.ok || !ray_column(s, oxy[i * 2], oxy[i * 2 + 1], rc)) continue;
+		passed++;
+		const float zmin0 = colz[i * 3], gs = colz[i * 3 + 1];
+		const int ncell = (int)colz[i * 3 + 2];
+		const float h1 = gs / 2.0; const float g2 = gs / (n2 * 1.0); const float h2 = g2 / 2.0;
+		// centre table like k_prepare: fl32((k + 0.5) * h1 * 2 + min) in double
+		const float zMin = (float)((0 + 0.5) * (double)h1 * 2 + (double)zmin0) - gs, zMax = (float)((ncell - 1 + 0.5) * (double)h1 * 2 + (double)zmin0) + gs;
+		const RayColZ z = ray_col_bound(s, rc, zMin, zMax, gs, 1.f / (2.02f * h2), 1.f / (1.98f * h2));
+		const RayThr thr = ray_col_thresholds(s, rc, z, zMin, zMax);
+		const unsigned full = n2 >= 32 ? 0xffffffffu : ((1u << n2) - 1u);
+		for (int k = 0; k < ncell; k++) {
+			const float mid = (float)((k + 0.5) * (double)h1 * 2 + (double)zmin0);
+			unsigned want = 0;
+			for (int r = 0; r < n2; r++) want |= (unsigned)ray_cell(s, rc, l2_centre(r, h2, mid, h1)) << r;
+			const float zLoC = l2_centre(0, h2, mid, h1), zHiC = l2_centre(n2 - 1, h2, mid, h1);
+			cells++;
+			if (zHiC < thr.zAll) { byThr++; if (want != full) bad++; }
+			else if (zLoC >= thr.zNone) { byThr++; if (want != 0u) bad++; }
+			else if (ray_cell_mask(s, rc, z, mid, h1, h2, n2) != want) bad++;
+		}
+	}
+	out4[0] = bad; out4[1] = passed; out4[2] = byThr; out4[3] = cells;
+}

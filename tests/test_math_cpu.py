@@ -258,6 +258,39 @@ def test_cell_mask_equals_per_sub_voxel_evaluation(probe):
     print("cell masks: %d column-passing pairs, %d with the crossing inside the cell" % (tot[1], tot[2]))
 
 
+def test_column_thresholds_classify_cells_like_per_sub_voxel_evaluation(probe):
+    """gpv::ray_col_thresholds gives, per (triangle, sub-voxel column), one height below which every cell of the grid column is
+    all hit and one from which on no cell is hit (two evaluations of t, certified slope and rounding bounds).  Every cell the
+    thresholds classify must agree with n2 independent ray_cell evaluations; columns of 4 to 1000 cells, cells from 1/300 of
+    the triangle to 30x its size, columns far from the origin, near-vertical / near-horizontal triangles."""
+    probe.probe_col_thresholds.argtypes = [C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+    rng = np.random.default_rng(29)
+    tot = np.zeros(4, np.int64)
+    for n2 in (1, 2, 4, 8, 16, 32):
+        n = 40000
+        scale = 10.0 ** rng.uniform(-2, 3, (n, 1, 1))
+        tri = (rng.normal(0, 1, (n, 3, 3)) * scale + rng.normal(0, 1, (n, 1, 3)) * scale * rng.choice([0, 1, 30, 3000], (n, 1, 1))).astype(np.float32)
+        k = n // 5
+        tri[:k, 2, :2] = (tri[:k, 0, :2] + (tri[:k, 1, :2] - tri[:k, 0, :2]) * rng.uniform(0, 1, (k, 1)) +
+                          rng.normal(0, 1e-4, (k, 2)) * scale[:k, 0]).astype(np.float32)          # near-vertical
+        tri[k:2 * k, :, 2] = tri[k:2 * k, :1, 2] + rng.normal(0, 1e-5, (k, 3)).astype(np.float32) * scale[k:2 * k, 0]  # nearly horizontal
+        w = rng.dirichlet([1, 1, 1], n).astype(np.float32)
+        o = (tri * w[:, :, None]).sum(1)
+        oxy = np.ascontiguousarray(o[:, :2], np.float32)
+        gs = (10.0 ** rng.uniform(-2.5, 1.5, n) * scale[:, 0, 0]).astype(np.float32)
+        ncell = rng.choice([4, 16, 64, 256, 1000], n)
+        # the crossing somewhere inside the column (80 %), or the whole column below / above it
+        frac = np.where(rng.uniform(0, 1, n) < 0.8, rng.uniform(0, 1, n), rng.choice([-0.5, 1.5], n))
+        zmin = (o[:, 2] - gs * ncell * frac).astype(np.float32)
+        colz = np.ascontiguousarray(np.stack([zmin, gs, ncell.astype(np.float32)], -1), np.float32)
+        out = np.zeros(4, np.int64)
+        probe.probe_col_thresholds(n, _fp(oxy), _fp(colz), n2, _fp(np.ascontiguousarray(tri.reshape(n, 9))), out.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert out[0] == 0, (n2, out)
+        tot += out
+    assert tot[1] > 50000 and tot[2] > 0.8 * tot[3], tot   # the thresholds decide the bulk of the cells (88 % in this hostile mix)
+    print("column thresholds: %d pairs, %d of %d cells classified without a per-cell evaluation" % (tot[1], tot[2], tot[3]))
+
+
 @pytest.mark.parametrize("origin,gs", [(0.0, 0.125), (1000.0, 0.125), (-250000.0, 1.0), (3.0, 1e-3), (0.0, 40.0)])
 def test_certified_candidates_tight_and_covering_on_shifted_grids(probe, origin, gs):
     """Same property as above on grids far from the origin / with tiny or huge cells, with triangles from 1/20 of a cell
