@@ -326,7 +326,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	launches += 2;
 	mark(GPV_PHASE_SCAN);
 	{ // K3 boundary compaction
-		const int V = cells > (16ll << 20) ? 4 : 1; // sub-tiles per tile: large grids amortise the per-tile latency over 32 KB of input
+		const int V = cells > (1ll << 20) ? 4 : 1; // sub-tiles per tile: beyond a million cells the per-tile latency is amortised over 32 KB of input
 		long long tiles = (cells + (long long)V * kScanTile - 1) / ((long long)V * kScanTile);
 		ScanIO io{};
 		io.in = c->cellCount.as<int>(); io.n = cells;

@@ -384,7 +384,7 @@ __device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long lon
 }
 
 // V = sub-tiles of kScanTile items per tile: one tile id, one look-back and one descriptor per V * 2048 items, so the fixed
-// latency of a tile (atomic, look-back, barriers) is paid once per 8 KB * V of input -- V = 4 for grids beyond 16 M cells.
+// latency of a tile (atomic, look-back, barriers) is paid once per 8 KB * V of input -- V = 4 for grids beyond 1 M cells.
 template <int MODE, int V>
 __device__ __forceinline__ void scan_body(const ScanIO& io)
 {
