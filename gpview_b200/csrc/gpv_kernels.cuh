@@ -43,8 +43,6 @@ struct Totals {
 };
 
 constexpr int kWorkThreads = 128;                        // threads per CTA of the balanced triangle-work kernels
-constexpr int kWorkItems = 8;                            // work items per thread and work block
-constexpr int kWorkBlock = kWorkThreads * kWorkItems;    // 1024 (triangle, cell) items per work block
 constexpr int kTileTris = 128;                           // triangle records staged per TMA tile (6 KB + 2 KB)
 constexpr int kWorkGrid = 148 * 8;                       // persistent grid: 8 CTAs per SM, work blocks strided over it
 
@@ -175,9 +173,10 @@ __device__ __forceinline__ void for_each_work_item(WorkSmem& sm, const unsigned*
 	__syncthreads();
 	const unsigned long long total = *totalPtr;
 	uint32_t parity = 0;
-	// this CTA's contiguous item range [R0,R1): ceil(nBlocks/grid) work blocks of kWorkBlock items
-	const unsigned long long nBlocks = (total + kWorkBlock - 1) / kWorkBlock, per = (nBlocks + gridDim.x - 1) / gridDim.x;
-	const unsigned long long R0 = min(total, blockIdx.x * per * kWorkBlock), R1 = min(total, (blockIdx.x + 1ull) * per * kWorkBlock);
+	// this CTA's contiguous item range [R0,R1): the items are dealt out in units of one item per thread (128), so that a small model
+	// (cessna-256: 478 k items) still spreads over the whole persistent grid instead of 1,024 items on each of a third of the CTAs
+	const unsigned long long nBlocks = (total + kWorkThreads - 1) / kWorkThreads, per = (nBlocks + gridDim.x - 1) / gridDim.x;
+	const unsigned long long R0 = min(total, blockIdx.x * per * kWorkThreads), R1 = min(total, (blockIdx.x + 1ull) * per * kWorkThreads);
 	if (R0 >= R1) return;
 	if (tid == 0) { // largest t with off[t] <= R0   (off[0] = 0 <= R0 < total = off[nTri]); ONE search per CTA
 		int lo = 0, hi = nTri;

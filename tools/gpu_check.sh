@@ -2,7 +2,7 @@
 # Development helper for one gpurun call: GPU test suite, the headline bench (summary), optional extra configs with parity.
 #   tools/gpu_check.sh [cad] [sphere] [block]
 cd "$(dirname "$0")/.."
-echo "== pytest -m gpu"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+echo "== pytest -m gpu"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee /tmp/pytest_tail.log
 echo "== bench cessna 256/16"
 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
@@ -21,3 +21,4 @@ for l in L:
     elif 'Error' in l or 'error' in l: print(l)
 P
 done
+echo "== pytest again: $(tail -1 /tmp/pytest_tail.log)"
