@@ -63,7 +63,7 @@ struct gpv_ctx {
 	int device = 0;
 	int smCount = 0;
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
-	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, aabbxy16, longList, colCellCnt, colCellOff, colCellList, l2Par, cellMid;
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, aabbxy16, longList, colCursor, binBits, colCellCnt, colCellOff, colCellList, l2Par, cellMid;
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {}, evEnd[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
@@ -102,7 +102,7 @@ static int preload_kernels()
 {
 	cudaFuncAttributes a;
 #define GPV_LOAD(...) GPV_CUDA(cudaFuncGetAttributes(&a, __VA_ARGS__))
-	GPV_LOAD(k_clear); GPV_LOAD(k_prepare); GPV_LOAD(k_scan_offs3); GPV_LOAD((k_scan<MODE_CELLS, 1>)); GPV_LOAD((k_scan<MODE_CELLS, 4>));
+	GPV_LOAD(k_clear); GPV_LOAD(k_clear_bits); GPV_LOAD(k_prepare); GPV_LOAD(k_scan_offs3); GPV_LOAD((k_scan<MODE_CELLS, 1>)); GPV_LOAD((k_scan<MODE_CELLS, 4>));
 	GPV_LOAD(k_bin<false>); GPV_LOAD(k_bin<true>); GPV_LOAD(k_cross<false>); GPV_LOAD(k_cross<true>); GPV_LOAD(k_fill_sweep);
 	GPV_LOAD(k_sort_segments); GPV_LOAD(k_sort_long);
 	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals);
@@ -152,7 +152,7 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->aabbxy16, &c->longList, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->aabbxy16, &c->longList, &c->colCursor, &c->binBits, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
 	gpv_gather_detach(c);
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
@@ -272,8 +272,12 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	    c->boundaryIndex.ensure((size_t)cells * 4 + 32) || c->bTriOff.ensure((size_t)(cells + 1) * 4 + 32) || c->colOff.ensure((size_t)(ncol + 1) * 4 + 32) ||
 	    c->crossOff.ensure((size_t)(ncol + 1) * 4 + 32) || c->l1State.ensure((size_t)cells + 32) || c->crossFp.ensure((size_t)nTri * 16) || c->plane16.ensure((size_t)nTri * 16) || c->aabbxy16.ensure((size_t)nTri * 16) ||
 	    c->binCnt.ensure((size_t)nTri * 4 + 32) || c->binOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->crossCnt.ensure((size_t)nTri * 4 + 32) ||
-	    c->crossWorkOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->colCellCnt.ensure((size_t)ncol * 4 + 32) || c->colCellOff.ensure((size_t)(ncol + 1) * 4 + 32))
+	    c->crossWorkOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->colCellCnt.ensure((size_t)ncol * 4 + 32) || c->colCursor.ensure((size_t)ncol * 4 + 32) || c->colCellOff.ensure((size_t)(ncol + 1) * 4 + 32))
 		return 1;
+	// (triangle, column) bitmaps of the two binning sweeps: one bit per work item at most.  The work-space size is known on the
+	// device only; a first guess here, the exact size after the read-back (then the call starts over, once per growth).
+	if (!c->binBits.cap && c->binBits.ensure((size_t)std::max<long long>(1 << 20, 64ll * nTri) / 8 * 2 + 64)) return 1;
+	const unsigned long long bitsCap = ((unsigned long long)(c->binBits.cap - 64) / 2 / 4) * 32; // bits per sweep (whole words)
 	Totals* dT = c->totals.as<Totals>();
 	mark(GPV_PHASE_SETUP);
 	// look-back descriptor regions of the six scans of this call
@@ -293,6 +297,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		add(c->colCount.p, (size_t)ncol * 4);
 		add(c->crossCount.p, (size_t)ncol * 4);
 		add(c->colCellCnt.p, (size_t)ncol * 4);
+		add(c->colCursor.p, (size_t)ncol * 4);
 		add(c->desc.p, dOff[6]);
 		k_clear<<<dim3((unsigned)std::min<long long>(c->smCount * 8, (cells * 4 / 16 + 255) / 256 + 1), (unsigned)k), 256, 0, st>>>(cl);
 		launches++;
@@ -314,6 +319,9 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	}
 	BinOut bo{};
 	bo.cellCount = c->cellCount.as<int>(); bo.colCount = c->colCount.as<int>(); bo.totals = dT;
+	bo.bits = c->binBits.as<unsigned>(); bo.bitsCap = bitsCap;
+	k_clear_bits<<<c->smCount * 4, 256, 0, st>>>(c->binBits.as<unsigned>(), bitsCap, dT);
+	launches++;
 	// the two count sweeps are independent: the crossing count runs on the side stream beside the SAT count and the cell scan
 	GPV_CUDA(cudaEventRecord(c->evFork[0], st));
 	GPV_CUDA(cudaStreamWaitEvent(side, c->evFork[0], 0));
@@ -354,6 +362,11 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	const Totals T1 = *c->hTotals;
 	if (T1.l1Hits > 0x7ffffff0ull) return fail("more than 2^31 (cell, triangle) pairs in one slab: shard finer");
 	if (T1.binWork > 0xfffffff0ull || T1.crossWork > 0xfffffff0ull) return fail("more than 2^32 (triangle, cell) work items: work offsets are 32-bit");
+	if (T1.binWork > bitsCap) { // the binning sweeps left without doing anything: grow the bitmaps and start the call over (first call of a larger model only)
+		if (c->binBits.ensure((size_t)((T1.binWork + 31) / 32 * 4) * 2 + 64)) return 1;
+		if (gather) c->gather.epoch--; // nothing of this call has reached the mailbox yet: the repeated call takes the same epoch
+		return voxelize_impl(c, d_tris, n_tri, bmin, bmax, max_model_size, prm, stream, out, sink);
+	}
 	const long long nB = T1.nBoundary;
 	const long long n23 = (long long)g.n2 * g.n2 * g.n2;
 	if (c->cellTris.ensure((size_t)T1.triTotal * 4 + 32) || c->colTris.ensure((size_t)T1.colTotalOver * 4 + 32) || c->crossTri.ensure((size_t)T1.crossTotal * 4 + 32))
@@ -362,7 +375,8 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	if (wantN && (c->l1Normal.ensure((size_t)cells * 3 + 32) || (wantL2 && c->l2Normal.ensure((size_t)(nB * n23) * 3 + 32)))) return 1;
 
 	bo.prefix = c->prefix.as<int>(); bo.bTriOff = c->bTriOff.as<unsigned>(); bo.cellTris = c->cellTris.as<int>();
-	bo.colOff = c->colOff.as<unsigned>(); bo.colTris = c->colTris.as<int>();
+	bo.colOff = c->colOff.as<unsigned>(); bo.colTris = c->colTris.as<int>(); bo.colCursor = c->colCursor.as<int>();
+	bo.bits = c->binBits.as<unsigned>() + bitsCap / 32; // the fill sweep's own bitmap
 	if (c->longList.ensure((size_t)(nB + ncol) * 4 + 64)) return 1; // (every allocation of the call happens before the exchange and the fork: a growing pool's cudaFree synchronises the device)
 	if (gather) { // the one exchange step: boundary counts of the lower slabs (8 bytes per rank through the mailbox)
 		k_gather_exchange<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, wantL2 ? c->gather.l2Cap / n23 : (long long)0x7fffffff, dT);
@@ -397,7 +411,11 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	k_bin<true><<<kWorkGrid, kWorkThreads, 0, st>>>(tri48, nTri, c->binOff.as<unsigned>(), g, cx, cy, cz, bo);
 	launches++;
 	mark(GPV_PHASE_SORT);
-	{ // canonical order: warp per list; lists longer than kSortSmem go through a work list to k_sort_long (CTA per list)
+	if (wantN || (prm->flags & GPV_KEEP_LISTS)) {
+		// canonical (ascending) order of the cell and column lists: needed only where the order shows -- the f32 sums of the normals and
+		// lists handed to the caller.  Occupancy does not depend on it (the SAT ORs its hits, the parity rays XOR theirs), and the
+		// column lists are duplicate-free by construction.  Warp per list; lists longer than kSortSmem go through a work list to
+		// k_sort_long (CTA per list).
 		unsigned* longCnt = reinterpret_cast<unsigned*>(c->totals.as<char>() + 128); // [0] cell lists, [1] column lists (zeroed by k_clear)
 		int* longCells = c->longList.as<int>() + 16;
 		int* longCols = longCells + nB;

@@ -217,7 +217,7 @@ __device__ __forceinline__ void for_each_work_item(WorkSmem& sm, const unsigned*
 		for (unsigned long long c = cb + tid; c < ce; c += kWorkThreads) {
 			int lo = 0, hi = nt; // largest k in [0,nt) with off[k] <= c
 			while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm.off[mid] <= c) lo = mid; else hi = mid; }
-			f(t + lo, sm.rec + lo * 3, sm.fp + lo, (unsigned)(c - sm.off[lo]));
+			f(t + lo, sm.rec + lo * 3, sm.fp + lo, (unsigned)(c - sm.off[lo]), sm.off[lo]);
 		}
 		__syncthreads();
 		if (last) break;
@@ -226,13 +226,22 @@ __device__ __forceinline__ void for_each_work_item(WorkSmem& sm, const unsigned*
 }
 
 // ------------------------------------------------------------------------------------------------ k_bin
-// K1.  Replaces CUDAClassifyTessellationKernel (cu:320-401) + the host CSR flatten (src/Object.cpp:2137-2180).
-// One thread = one (triangle, Level-1 cell) SAT test (cu:374-395).  Two sweeps over the same balanced work space:
-//   FILL=false  cellCount[cell]++ (slab cells only), colCount[col]++ (every hit: column lists are de-duplicated later)
-//   FILL=true   cellTris[bTriOff[prefix[cell]] + slot], colTris[colOff[col] + slot]   (slots by atomic decrement)
+// K1.  Replaces CUDAClassifyTessellationKernel (cu:320-401) + the host CSR flatten and per-column de-duplication
+// (src/Object.cpp:2137-2180).  One thread = one (triangle, Level-1 cell) SAT test of the clipped footprint (cu:374-395).
+// A triangle hits several cells of a column but enters the COLUMN's list once: every (triangle, column of its footprint) pair
+// owns one bit of a bitmap laid out over the same flat work space (bit = the triangle's work offset + the column's index in
+// its footprint), and the thread whose atomicOr finds the bit clear is the one that adds.  The reference de-duplicates on the
+// host with a bool[numTriangles] per column; here the lists are duplicate-free by construction and need no sort to be USED
+// (only to be compared -- GPV_KEEP_LISTS -- and for the order-dependent f32 sums of the normals).  Two sweeps over the same
+// balanced work space, each with its own bitmap:
+//   FILL=false  cellCount[cell]++ (slab cells only), colCount[col]++
+//   FILL=true   cellTris[bTriOff[prefix[cell]] + slot] (slot by atomic decrement), colTris[colOff[col] + slot] (slot by a cursor)
 struct BinOut {
 	int* cellCount;            // slab-local linear index
-	int* colCount;             // nx*ny
+	int* colCount;             // nx*ny: length of every column list (kept)
+	int* colCursor;            // FILL: nx*ny, zeroed
+	unsigned* bits;            // this sweep's (triangle, column) bitmap, zeroed over the work space (k_clear_bits)
+	unsigned long long bitsCap; // bits available; a larger work space makes the sweep leave (the host grows the pool and starts over)
 	const int* prefix;         // FILL: slab-local boundary rank of each cell
 	const unsigned* bTriOff;   // FILL
 	int* cellTris;             // FILL
@@ -241,31 +250,41 @@ struct BinOut {
 	Totals* totals;
 };
 
+// zeroes both sweeps' bitmaps over the work space of this model (its size is on the device only)
+__global__ void __launch_bounds__(256) k_clear_bits(unsigned* bits, unsigned long long capBits, const Totals* totals)
+{
+	const unsigned long long n = totals->binWork;
+	if (n > capBits) return;
+	const unsigned long long words = (n + 31) / 32, capWords = capBits / 32;
+	for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < words; i += (unsigned long long)gridDim.x * 256) { bits[i] = 0u; bits[capWords + i] = 0u; }
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(kWorkThreads) k_bin(const float4* __restrict__ tri48, int nTri, const unsigned* __restrict__ binOff, GridP g,
                                                       const float* __restrict__ cx, const float* __restrict__ cy, const float* __restrict__ cz, BinOut o)
 {
 	__shared__ __align__(128) WorkSmem sm;
+	if (o.totals->binWork > o.bitsCap) return;
 	unsigned long long hits = 0;
-	for_each_work_item<false>(sm, binOff, nTri, &o.totals->binWork, tri48, nullptr, [&](int t, const float4* rec, const int4*, unsigned local) {
+	for_each_work_item<false>(sm, binOff, nTri, &o.totals->binWork, tri48, nullptr, [&](int t, const float4* rec, const int4*, unsigned local, unsigned base) {
 		const float4 a = rec[0], b = rec[1], c = rec[2];
 		const unsigned w0 = __float_as_uint(a.w), w1 = __float_as_uint(b.w), w2 = __float_as_uint(c.w);
 		const unsigned dx = w1 >> 16, dy = w2 & 0xffffu;
-		const unsigned rest = local / dx;
-		const int p = (int)((w0 & 0xffffu) + (local - rest * dx)), q = (int)((w0 >> 16) + rest % dy), r = (int)((w1 & 0xffffu) + rest / dy);
+		const unsigned rest = local / dx, rz = rest / dy;
+		const int p = (int)((w0 & 0xffffu) + (local - rest * dx)), q = (int)((w0 >> 16) + (rest - rz * dy)), r = (int)((w1 & 0xffffu) + rz);
 		if (!tri_box_overlap(cx[p], cy[q], cz[r], g.h1x, g.h1y, g.h1z, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z)) return;
 		hits++;
 		const int col = q * g.nx + p;
-		if (!FILL) {
-			atomicAdd(o.colCount + col, 1);
-			if (r >= g.z0 && r < g.z1) atomicAdd(o.cellCount + ((size_t)(r - g.z0) * g.ny * g.nx + col), 1);
-		} else {
-			o.colTris[o.colOff[col] + atomicSub(o.colCount + col, 1) - 1] = t;
-			if (r >= g.z0 && r < g.z1) {
-				const size_t li = (size_t)(r - g.z0) * g.ny * g.nx + col;
-				o.cellTris[o.bTriOff[o.prefix[li]] + atomicSub(o.cellCount + li, 1) - 1] = t;
-			}
+		if (r >= g.z0 && r < g.z1) {
+			const size_t li = (size_t)(r - g.z0) * g.ny * g.nx + col;
+			if (!FILL) atomicAdd(o.cellCount + li, 1);
+			else o.cellTris[o.bTriOff[o.prefix[li]] + atomicSub(o.cellCount + li, 1) - 1] = t;
 		}
+		const unsigned long long bit = (unsigned long long)base + (local - rz * dx * dy); // < base + dx*dy <= the triangle's end of the work space
+		const unsigned mask = 1u << (bit & 31);
+		if (atomicOr(o.bits + (bit >> 5), mask) & mask) return; // another cell of this column has entered the triangle already
+		if (!FILL) atomicAdd(o.colCount + col, 1);
+		else o.colTris[o.colOff[col] + atomicAdd(o.colCursor + col, 1)] = t;
 	});
 	if (!FILL) {
 		hits = warp_sum(hits);
@@ -286,7 +305,7 @@ __global__ void __launch_bounds__(kWorkThreads) k_cross(const float4* __restrict
 {
 	__shared__ __align__(128) WorkSmem sm;
 	unsigned long long found = 0;
-	for_each_work_item<true>(sm, workOff, nTri, &totals->crossWork, ray48, crossFp, [&](int t, const float4* rec, const int4* fp, unsigned local) {
+	for_each_work_item<true>(sm, workOff, nTri, &totals->crossWork, ray48, crossFp, [&](int t, const float4* rec, const int4* fp, unsigned local, unsigned) {
 		const float4 a = rec[0], b = rec[1], c = rec[2];
 		RayTri s;
 		s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;

@@ -69,7 +69,8 @@ typedef struct {
 /* flags */
 #define GPV_NORMALS      1     /* also produce Level1Normal / Level2Normal streams */
 #define GPV_NO_LEVEL2    2     /* GLParameters::level2Voxels == false */
-#define GPV_KEEP_LISTS   4     /* keep CSR cell lists / column lists readable after the call (gpv_result list pointers) */
+#define GPV_KEEP_LISTS   4     /* CSR cell lists / column lists in canonical (ascending) order for the caller (gpv_result list pointers);
+                                  without it (and without GPV_NORMALS) the lists stay in the order the binning left them: occupancy does not depend on it */
 #define GPV_PROFILE      8     /* record a CUDA event pair around every kernel of the pipeline -> gpv_result.phase_ms */
 #define GPV_GATHER      16     /* multi-GPU: write this slab's streams straight into the gathering rank's buffers (gpv_gather_*) */
 
@@ -98,7 +99,7 @@ typedef struct {
 	/* CSR lists (GPV_KEEP_LISTS): ascending triangle ids */
 	uint32_t* d_cell_off;      /* n_boundary+1, indexed by slab-local boundary rank */
 	int32_t* d_cell_tris;
-	uint32_t* d_col_off;       /* nx*ny+1 (slack between columns: use d_col_count) */
+	uint32_t* d_col_off;       /* nx*ny+1 */
 	int32_t* d_col_count;      /* nx*ny */
 	int32_t* d_col_tris;
 	/* counts (src/Object.cpp:3353-3378) */

@@ -60,6 +60,12 @@ def test_streams_match_oracle_and_golden(product, oracle, ctx, tmp_path_factory,
     assert sha(res.level1_normal()) == info["streams"]["Level1Normal"]["sha256"]
     assert np.array_equal(res.level2_normal(), ores.l2_normal)
     assert sha(res.level2_normal()) == info["streams"]["Level2Normal"]["sha256"]
+    # the plain call (no normals, no lists for the caller) skips the list sorts: occupancy must not depend on the list order
+    plain = ctx.voxelize(mesh, product.Params(l1, l2, 0))
+    assert plain.counts == res.counts and plain.stats["l1_box_tests"] == info["l1_box_tests"] and plain.stats["l2_ray_tests"] == info["l2_ray_tests"]
+    assert sha(plain.level1_inout()) == info["streams"]["Level1InOut"]["sha256"]
+    assert sha(plain.prefix()) == info["streams"]["Level1BoundaryPrefixSum"]["sha256"]
+    assert sha(plain.level2_inout()) == info["streams"]["Level2InOut"]["sha256"]
 
 
 def test_no_level2_and_no_normals(product, oracle, ctx, tmp_path_factory):
