@@ -274,10 +274,7 @@ def main():
         for _ in range(4):
             if t_all.max() < 1.05 * t_all.mean():
                 break
-            for r in range(world):
-                sl = slice(cuts[r], cuts[r + 1])
-                layer[sl] *= max(t_all[r], 1e-6) / layer[sl].sum()
-            cuts = sharded.plan_slabs(layer, world)
+            layer, cuts = sharded.rebalance(layer, cuts, t_all)
             set_cuts(cuts)
             for _ in range(2):
                 res = step()

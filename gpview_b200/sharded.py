@@ -38,6 +38,18 @@ def layer_cost(boundary_index, cell_off, plane, nz, per_cell_overhead=8.0):
     return np.bincount(bi // plane, weights=(off[1:] - off[:-1]) + per_cell_overhead, minlength=nz)
 
 
+def rebalance(layer_cost_now, cuts, seconds_per_rank):
+    """One step of measured-time load balancing: rescale every slab's layer costs so that the slab's cost equals the time its
+    rank measured, then re-cut.  `layer_cost_now` (nz floats, > 0) is updated in place and returned with the new cuts.  Every rank
+    calls this with the same all-gathered times, so every rank gets the same cuts (no data moves)."""
+    layer = layer_cost_now
+    world = len(cuts) - 1
+    for r in range(world):
+        sl = slice(cuts[r], cuts[r + 1])
+        layer[sl] *= max(float(seconds_per_rank[r]), 1e-9) / max(float(layer[sl].sum()), 1e-30)
+    return layer, plan_slabs(layer, world)
+
+
 def gather_to_rank0(dist, torch, rank, world, pieces, cells, n_boundary, out_cache=None):
     """Concatenate the slab pieces on rank 0.
 

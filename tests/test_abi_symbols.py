@@ -64,3 +64,36 @@ def test_product_never_touches_the_oracle():
                             continue
                         bad.append((f, line))
     assert not bad, bad
+
+
+def test_flags_and_struct_sizes_match_the_header(product):
+    """The ctypes mirror (gpview_b200/binding.py) must carry the header's flag values and struct sizes: compile a probe against
+    include/gpview_b200.h with the host compiler and compare (no GPU needed)."""
+    import ctypes as C
+    import tempfile
+    from gpview_b200 import binding as B
+    src = r"""
+#include "gpview_b200.h"
+#include <stdio.h>
+int main(void) {
+    printf("GPV_NORMALS %d\nGPV_NO_LEVEL2 %d\nGPV_KEEP_LISTS %d\nGPV_PROFILE %d\nGPV_GATHER %d\n", GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE, GPV_GATHER);
+    printf("gpv_mesh %zu\ngpv_grid %zu\ngpv_params %zu\ngpv_result %zu\ngpv_host_streams %zu\ngpv_gather_desc %zu\ngpv_batch_stats %zu\ngpv_voxel_file %zu\n",
+           sizeof(gpv_mesh), sizeof(gpv_grid), sizeof(gpv_params), sizeof(gpv_result), sizeof(gpv_host_streams), sizeof(gpv_gather_desc), sizeof(gpv_batch_stats), sizeof(gpv_voxel_file));
+    printf("GPV_PHASE_COUNT %d\n", (int)GPV_PHASE_COUNT);
+    return 0;
+}
+"""
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "probe.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "probe")
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.check_call([cc, "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        got = dict(line.split() for line in subprocess.check_output([exe], text=True).splitlines())
+    for name in ("GPV_NORMALS", "GPV_NO_LEVEL2", "GPV_KEEP_LISTS", "GPV_PROFILE", "GPV_GATHER"):
+        assert int(got[name]) == getattr(B, name), name
+    mirrors = {"gpv_mesh": B.CMesh, "gpv_grid": B.CGrid, "gpv_params": B.CParams, "gpv_result": B.CResult, "gpv_host_streams": B.CHostStreams,
+               "gpv_gather_desc": B.CGatherDesc, "gpv_batch_stats": B.CBatchStats, "gpv_voxel_file": B.CVoxelFile}
+    for name, cls in mirrors.items():
+        assert int(got[name]) == C.sizeof(cls), (name, got[name], C.sizeof(cls))
+    assert int(got["GPV_PHASE_COUNT"]) == len(B.PHASES)

@@ -78,3 +78,22 @@ def test_plan_slabs_balances_cost():
     assert sharded.plan_slabs(np.zeros(8), 8) == list(range(9))
     with pytest.raises(ValueError):
         sharded.plan_slabs(np.ones(4), 5)
+
+
+def test_rebalance_converges_on_a_skewed_cost():
+    """sharded.rebalance: ranks whose true cost per layer differs from the a-priori model (here: a quadratic profile the model knows
+    nothing about) converge to slabs of equal measured time in a few steps; cuts stay strictly increasing and cover [0, nz]."""
+    import numpy as np
+    from gpview_b200 import sharded
+    nz, world = 256, 8
+    true = 1.0 + 40.0 * np.exp(-((np.arange(nz) - 128.0) / 18.0) ** 2) + 0.02 * np.arange(nz)   # what the GPU would take per layer
+    layer = np.ones(nz)                                                                           # what the model believes
+    cuts = sharded.plan_slabs(layer, world)
+    for _ in range(6):
+        t = np.array([true[cuts[r]:cuts[r + 1]].sum() for r in range(world)])
+        if t.max() < 1.05 * t.mean():
+            break
+        layer, cuts = sharded.rebalance(layer, cuts, t)
+        assert cuts[0] == 0 and cuts[-1] == nz and all(b > a for a, b in zip(cuts, cuts[1:]))
+    t = np.array([true[cuts[r]:cuts[r + 1]].sum() for r in range(world)])
+    assert t.max() < 1.25 * t.mean(), (cuts, t)
