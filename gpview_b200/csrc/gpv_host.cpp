@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -99,34 +101,70 @@ int export_mesh(std::vector<float>& tris, int64_t nVerts, const float mn[3], con
 
 } // namespace
 
-extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
+namespace {
+// ------------------------------------------------------------------------------------------------ chunk-parallel parsing
+// Both loaders cut the file into chunks at token boundaries (OBJ: lines), parse the chunks on host threads and stitch the
+// results in file order, so that a single 10 M-triangle file (0.7 GB of text) loads in seconds instead of half a minute
+// (SURVEY.md 8f3).  One chunk on one thread IS the sequential loader: the same code runs either way, and the result --
+// every float, the order of the triangles, the error that is reported -- does not depend on the number of chunks
+// (tests/test_host_cpu.py cuts the fixtures into 1..7 chunks).  GPV_LOAD_THREADS overrides the thread count (default: one per
+// 4 MB of text, at most the hardware concurrency).
+int load_threads(size_t bytes)
 {
-	memset(out, 0, sizeof *out);
-	std::vector<char> buf;
-	if (!read_file(path, buf)) return gpv::fail(std::string("Unable to open file \"") + path + "\""); // the reference abort()s (:409-413)
-	std::vector<float> verts, tris;
+	long t = 0;
+	if (const char* e = getenv("GPV_LOAD_THREADS")) t = strtol(e, nullptr, 10);
+	if (t <= 0) {
+		const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+		t = (long)std::min<size_t>(hw, std::max<size_t>(1, bytes >> 22));
+	}
+	return (int)std::min<long>(t, 256);
+}
+
+template <class F>
+void run_chunks(int n, F&& f)
+{
+	if (n <= 1) { f(0); return; }
+	std::vector<std::thread> pool;
+	for (int k = 1; k < n; k++) pool.emplace_back([&f, k] { f(k); });
+	f(0);
+	for (auto& t : pool) t.join();
+}
+
+struct ObjChunk {
+	size_t begin = 0, end = 0;            // [begin, end): whole lines, each ending with '\n'
+	size_t nLines = 0;
+	std::vector<float> v;                 // 3 per `v` line (missing coordinates are filled in when the chunks are stitched)
+	std::vector<unsigned char> vParsed;   // coordinates present on the line (0..3)
+	std::vector<long> f;                  // 3 raw indices per `f` line
+	std::vector<size_t> fLine, fVertsBefore; // chunk-local line number; `v` lines of this chunk before the face
+	size_t errLine = (size_t)-1;          // chunk-local line number of the first parse error
+	int errKind = 0;                      // 1 vertex coordinate, 2 face index
+};
+
+void parse_obj_chunk(const char* data, ObjChunk& c)
+{
 	std::vector<Field> bySpace, byTab;
-	float mn[3] = { 0, 0, 0 }, mx[3] = { 0, 0, 0 };
-	float pt[3] = { 0, 0, 0 }; // declared outside the loop in the reference: short `v` lines keep stale coordinates
-	size_t pos = 0, lineNo = 0;
-	while (pos < buf.size()) {
+	size_t pos = c.begin;
+	while (pos < c.end) {
 		size_t e = pos;
-		while (e < buf.size() && buf[e] != '\n') e++;
-		if (e == buf.size()) break; // getline reached EOF: `if (!in.good()) break;` drops an unterminated last line (:425)
-		const char* line = buf.data() + pos;
-		size_t len = e - pos;
+		while (data[e] != '\n') e++; // the chunk ends with '\n'
+		const char* line = data + pos;
+		const size_t len = e - pos;
 		pos = e + 1;
-		lineNo++;
+		const size_t lineNo = c.nLines++;
 		split_fields(line, len, ' ', bySpace);
 		split_fields(line, len, '\t', byTab);
 		const std::vector<Field>& w = bySpace.size() > byTab.size() ? bySpace : byTab; // :419-423
 		if (w.empty()) continue;
 		if (w[0].n == 1 && w[0].p[0] == 'v') {
-			for (size_t i = 1; i < w.size() && i <= 3; i++)
-				if (!field_to_float(w[i], pt[i - 1])) return gpv::fail("OBJ line " + std::to_string(lineNo) + ": bad vertex coordinate (std::stof would throw)");
-			if (verts.empty()) for (int a = 0; a < 3; a++) mn[a] = mx[a] = pt[a];
-			else for (int a = 0; a < 3; a++) { mn[a] = mn[a] < pt[a] ? mn[a] : pt[a]; mx[a] = mx[a] > pt[a] ? mx[a] : pt[a]; }
-			verts.insert(verts.end(), pt, pt + 3);
+			float pt[3] = { 0, 0, 0 };
+			unsigned char got = 0;
+			for (size_t i = 1; i < w.size() && i <= 3; i++) {
+				if (!field_to_float(w[i], pt[i - 1])) { c.errLine = lineNo; c.errKind = 1; return; } // std::stof would throw: the load ends here
+				got++;
+			}
+			c.v.insert(c.v.end(), pt, pt + 3);
+			c.vParsed.push_back(got);
 		} else if (w[0].n == 1 && w[0].p[0] == 'f') {
 			long idx[3] = { 0, 0, 0 };
 			for (size_t i = 1; i < w.size() && i <= 3; i++) { // "a", "a/b", "a/b/c", "a//c": the vertex index is the first '/' field (:480-505)
@@ -134,50 +172,182 @@ extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
 				size_t k = 0;
 				while (k < f.n && f.p[k] != '/') k++;
 				if (k > 0) f.n = k;
-				if (!field_to_long(f, idx[i - 1])) return gpv::fail("OBJ line " + std::to_string(lineNo) + ": bad face index (std::stoi would throw)");
+				if (!field_to_long(f, idx[i - 1])) { c.errLine = lineNo; c.errKind = 2; return; }
 			}
-			const long nv = (long)(verts.size() / 3);
-			for (int c = 0; c < 3; c++) {
-				idx[c] -= 1;
-				if (idx[c] < 0 || idx[c] >= nv) return gpv::fail("OBJ line " + std::to_string(lineNo) + ": face index out of range");
-			}
-			for (int c = 0; c < 3; c++) tris.insert(tris.end(), verts.begin() + idx[c] * 3, verts.begin() + idx[c] * 3 + 3);
+			c.f.insert(c.f.end(), idx, idx + 3);
+			c.fLine.push_back(lineNo);
+			c.fVertsBefore.push_back(c.vParsed.size());
 		}
 	}
-	if (verts.empty()) return gpv::fail(std::string("no vertices in ") + path);
-	return export_mesh(tris, (int64_t)(verts.size() / 3), mn, mx, out);
 }
+
+// [0, usable) cut into n pieces at line starts
+std::vector<size_t> line_cuts(const std::vector<char>& buf, size_t usable, int n)
+{
+	std::vector<size_t> cut(1, 0);
+	for (int k = 1; k < n; k++) {
+		size_t p = std::max(cut.back(), usable * (size_t)k / (size_t)n);
+		while (p < usable && p > 0 && buf[p - 1] != '\n') p++;
+		cut.push_back(std::min(p, usable));
+	}
+	cut.push_back(usable);
+	return cut;
+}
+
+} // namespace
+
+extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
+{
+	memset(out, 0, sizeof *out);
+	std::vector<char> buf;
+	if (!read_file(path, buf)) return gpv::fail(std::string("Unable to open file \"") + path + "\""); // the reference abort()s (:409-413)
+	size_t usable = buf.size(); // getline at EOF: `if (!in.good()) break;` drops an unterminated last line (:425)
+	while (usable > 0 && buf[usable - 1] != '\n') usable--;
+	const int nChunks = load_threads(usable);
+	const std::vector<size_t> cut = line_cuts(buf, usable, nChunks);
+	std::vector<ObjChunk> ch((size_t)nChunks);
+	for (int k = 0; k < nChunks; k++) { ch[k].begin = cut[k]; ch[k].end = cut[k + 1]; }
+	run_chunks(nChunks, [&](int k) { parse_obj_chunk(buf.data(), ch[k]); });
+
+	// ---- stitch in file order.  The sequential reader stops at its first error: everything behind the first chunk with a parse
+	// error is ignored, and the earliest error -- parse error or face index out of range -- is the one reported.
+	size_t nUsed = ch.size(), lineBase = 0;
+	std::vector<size_t> vertBase(ch.size() + 1, 0), faceBase(ch.size() + 1, 0), firstLine(ch.size() + 1, 0);
+	for (size_t k = 0; k < ch.size(); k++) {
+		firstLine[k] = lineBase;
+		lineBase += ch[k].nLines;
+		vertBase[k + 1] = vertBase[k] + ch[k].vParsed.size();
+		faceBase[k + 1] = faceBase[k] + ch[k].fLine.size();
+		if (ch[k].errKind) { nUsed = k + 1; break; }
+	}
+	const size_t nVerts = vertBase[nUsed], nFaces = faceBase[nUsed];
+	std::vector<float> verts(nVerts * 3);
+	bool shortLine = false;
+	for (size_t k = 0; k < nUsed; k++) {
+		if (!ch[k].v.empty()) memcpy(&verts[vertBase[k] * 3], ch[k].v.data(), ch[k].v.size() * sizeof(float));
+		for (unsigned char g : ch[k].vParsed) shortLine |= g < 3;
+	}
+	if (shortLine) { // `pt` lives outside the reference's loop: a short `v` line keeps the previous line's trailing coordinates (zero at first)
+		float pt[3] = { 0, 0, 0 };
+		size_t i = 0;
+		for (size_t k = 0; k < nUsed; k++) for (unsigned char g : ch[k].vParsed) {
+			for (int a = 0; a < 3; a++) { if (a < g) pt[a] = verts[i * 3 + a]; else verts[i * 3 + a] = pt[a]; }
+			i++;
+		}
+	}
+	// faces -> triangles; a face may only name vertices that were defined before its line
+	std::vector<float> tris(nFaces * 9);
+	std::vector<size_t> badFace(nUsed, (size_t)-1);
+	run_chunks((int)nUsed, [&](int k) {
+		const ObjChunk& c = ch[k];
+		for (size_t j = 0; j < c.fLine.size(); j++) {
+			const long nv = (long)(vertBase[k] + c.fVertsBefore[j]);
+			float* t = &tris[(faceBase[k] + j) * 9];
+			for (int q = 0; q < 3; q++) {
+				const long idx = c.f[j * 3 + q] - 1;
+				if (idx < 0 || idx >= nv) { badFace[k] = j; return; }
+				memcpy(t + q * 3, &verts[(size_t)idx * 3], 3 * sizeof(float));
+			}
+		}
+	});
+	for (size_t k = 0; k < nUsed; k++) { // the earliest error in file order
+		const size_t faceErr = badFace[k] == (size_t)-1 ? (size_t)-1 : ch[k].fLine[badFace[k]];
+		const size_t parseErr = ch[k].errKind ? ch[k].errLine : (size_t)-1;
+		if (faceErr == (size_t)-1 && parseErr == (size_t)-1) continue;
+		const bool isFace = faceErr < parseErr;
+		const std::string where = "OBJ line " + std::to_string(firstLine[k] + std::min(faceErr, parseErr) + 1);
+		if (isFace) return gpv::fail(where + ": face index out of range");
+		return gpv::fail(where + (ch[k].errKind == 1 ? ": bad vertex coordinate (std::stof would throw)" : ": bad face index (std::stoi would throw)"));
+	}
+	if (nVerts == 0) return gpv::fail(std::string("no vertices in ") + path);
+	float mn[3], mx[3]; // bbox over ALL `v` lines (:441-450)
+	for (int a = 0; a < 3; a++) mn[a] = mx[a] = verts[a];
+	for (size_t i = 0; i < nVerts; i++) for (int a = 0; a < 3; a++) {
+		const float x = verts[i * 3 + a];
+		mn[a] = mn[a] < x ? mn[a] : x;
+		mx[a] = mx[a] > x ? mx[a] : x;
+	}
+	return export_mesh(tris, (int64_t)nVerts, mn, mx, out);
+}
+
+namespace {
+// operator>> tokens of [begin, end): whitespace-separated runs; a run that touches `end` belongs to this chunk (chunks are cut
+// at whitespace)
+void off_tokens(const char* data, size_t begin, size_t end, std::vector<Field>& out)
+{
+	const char *p = data + begin, *e = data + end;
+	for (;;) {
+		while (p < e && isspace((unsigned char)*p)) p++;
+		if (p >= e) return;
+		Field f{ p, 0 };
+		while (p < e && !isspace((unsigned char)*p)) p++;
+		f.n = (size_t)(p - f.p);
+		out.push_back(f);
+	}
+}
+} // namespace
 
 extern "C" int gpv_load_off(const char* path, gpv_mesh* out)
 {
 	memset(out, 0, sizeof *out);
 	std::vector<char> buf;
 	if (!read_file(path, buf)) return gpv::fail(std::string("Unable to open file \"") + path + "\""); // the reference abort()s (:187-191)
-	const char *p = buf.data(), *end = buf.data() + buf.size();
-	auto next = [&](Field& f) -> bool { // operator>> tokenisation: skip whitespace, take the non-space run
-		while (p < end && isspace((unsigned char)*p)) p++;
-		if (p >= end) return false;
-		f.p = p;
-		while (p < end && !isspace((unsigned char)*p)) p++;
-		f.n = (size_t)(p - f.p);
-		return true;
+	// tokenise in parallel: chunks are cut at whitespace
+	const int nChunks = load_threads(buf.size());
+	std::vector<size_t> cut(1, 0);
+	for (int k = 1; k < nChunks; k++) {
+		size_t p = std::max(cut.back(), buf.size() * (size_t)k / (size_t)nChunks);
+		while (p < buf.size() && !isspace((unsigned char)buf[p])) p++;
+		cut.push_back(p);
+	}
+	cut.push_back(buf.size());
+	std::vector<std::vector<Field>> tok((size_t)nChunks);
+	run_chunks(nChunks, [&](int k) { off_tokens(buf.data(), cut[k], cut[k + 1], tok[k]); });
+	std::vector<size_t> base((size_t)nChunks + 1, 0);
+	for (int k = 0; k < nChunks; k++) base[k + 1] = base[k] + tok[k].size();
+	const size_t nTok = base[nChunks];
+	auto token = [&](size_t i) -> const Field& { // token i of the file
+		size_t k = (size_t)(std::upper_bound(base.begin(), base.end(), i) - base.begin()) - 1;
+		return tok[k][i - base[k]];
 	};
-	Field f;
 	long nV = 0, nF = 0, nE = 0;
-	if (!next(f)) return gpv::fail("OFF: empty file");                                         // in >> header
-	if (!next(f) || !field_to_long(f, nV) || !next(f) || !field_to_long(f, nF) || !next(f) || !field_to_long(f, nE))
+	if (nTok < 1) return gpv::fail("OFF: empty file");                                          // in >> header
+	if (nTok < 4 || !field_to_long(token(1), nV) || !field_to_long(token(2), nF) || !field_to_long(token(3), nE))
 		return gpv::fail("OFF: bad counts line");                                                // in >> v_len >> f_len >> n_len
 	if (nV <= 0 || nF <= 0) return gpv::fail("OFF: no vertices or faces");
+	// token 4 + i (i < 3 nV) is a coordinate; then every face takes FOUR tokens: f_count and exactly three indices whatever
+	// f_count says (:219-222).  The sequential reader fails at the first bad or missing token: so does this one.
+	const size_t vTok = 4, fTok = 4 + (size_t)nV * 3, needTok = fTok + (size_t)nF * 4;
 	std::vector<float> verts((size_t)nV * 3), tris((size_t)nF * 9);
-	for (long i = 0; i < nV * 3; i++) if (!next(f) || !field_to_float(f, verts[i])) return gpv::fail("OFF: bad vertex record");
-	for (long i = 0; i < nF; i++) {
-		long q[4]; // f_count then EXACTLY three indices whatever f_count says (:219-222)
-		for (int c = 0; c < 4; c++) if (!next(f) || !field_to_long(f, q[c])) return gpv::fail("OFF: bad face record");
-		for (int c = 0; c < 3; c++) {
-			if (q[c + 1] < 0 || q[c + 1] >= nV) return gpv::fail("OFF: face index out of range");
-			memcpy(&tris[(size_t)i * 9 + c * 3], &verts[(size_t)q[c + 1] * 3], 3 * sizeof(float));
+	std::vector<size_t> bad((size_t)nChunks, (size_t)-1); // first bad token index seen by each worker
+	const size_t haveTok = std::min(nTok, needTok);
+	run_chunks(nChunks, [&](int k) { // (any split of the token range will do: workers take equal shares)
+		const size_t i0 = vTok + (haveTok - vTok) * (size_t)k / (size_t)nChunks, i1 = vTok + (haveTok - vTok) * (size_t)(k + 1) / (size_t)nChunks;
+		for (size_t i = i0; i < i1; i++) {
+			const Field& f = token(i);
+			if (i < fTok) { if (!field_to_float(f, verts[i - vTok])) { bad[k] = i; return; } }
+			else { long q; if (!field_to_long(f, q)) { bad[k] = i; return; } }
 		}
-	}
+	});
+	size_t firstBad = nTok < needTok ? nTok : (size_t)-1; // a missing token fails like a bad one
+	for (int k = 0; k < nChunks; k++) firstBad = std::min(firstBad, bad[k]);
+	if (firstBad != (size_t)-1 && firstBad < fTok) return gpv::fail("OFF: bad vertex record");
+	// faces (vertices are complete here); the earliest failure -- bad token or index out of range -- is reported
+	std::vector<size_t> badIdx((size_t)nChunks, (size_t)-1);
+	const size_t okFaces = firstBad == (size_t)-1 ? (size_t)nF : (firstBad - fTok) / 4;
+	run_chunks(nChunks, [&](int k) {
+		const size_t j0 = okFaces * (size_t)k / (size_t)nChunks, j1 = okFaces * (size_t)(k + 1) / (size_t)nChunks;
+		for (size_t j = j0; j < j1; j++) for (int c = 0; c < 3; c++) {
+			long q = 0;
+			field_to_long(token(fTok + j * 4 + 1 + c), q);
+			if (q < 0 || q >= nV) { badIdx[k] = j; return; }
+			memcpy(&tris[j * 9 + c * 3], &verts[(size_t)q * 3], 3 * sizeof(float));
+		}
+	});
+	size_t firstBadFace = (size_t)-1;
+	for (int k = 0; k < nChunks; k++) firstBadFace = std::min(firstBadFace, badIdx[k]);
+	if (firstBadFace != (size_t)-1) return gpv::fail("OFF: face index out of range");
+	if (firstBad != (size_t)-1) return gpv::fail("OFF: bad face record");
 	float mn[3], mx[3]; // bbox over the vertices the triangles reference (:257-266)
 	for (int a = 0; a < 3; a++) mn[a] = mx[a] = tris[a];
 	for (size_t i = 0; i < tris.size(); i += 3) for (int a = 0; a < 3; a++) {

@@ -80,6 +80,59 @@ def test_off_reads_exactly_three_indices_and_bbox_over_referenced(product, oracl
     assert product.load_mesh(str(p2)).ntri == 2
 
 
+def _load_with_threads(product, path, t):
+    os.environ["GPV_LOAD_THREADS"] = str(t)
+    try:
+        return product.load_mesh(path)
+    finally:
+        os.environ.pop("GPV_LOAD_THREADS", None)
+
+
+def test_chunk_parallel_loading_is_independent_of_the_chunk_count(product, oracle, tmp_path_factory, tmp_path):
+    """the loaders cut a file into chunks parsed on host threads.  Every float, the triangle order, the bbox and
+    the error that is reported must not depend on the number of chunks: fixtures, every OBJ quirk, a 60 k-triangle mesh in both
+    formats (against the oracle's sequential reader), and files whose first error sits in the middle."""
+    from gpview_b200 import meshgen
+    files = [mesh_path(n, tmp_path_factory.getbasetemp()) for n in ("cessna", "sphere", "torus", "block", "cad")]
+    for case, txt in OBJ_QUIRKS.items():
+        p = tmp_path / (case + ".obj")
+        p.write_bytes(txt.encode())
+        files.append(str(p))
+    V, F = meshgen.uv_sphere(200, 152)
+    meshgen.write_obj(str(tmp_path / "big.obj"), V, F)
+    meshgen.write_off(str(tmp_path / "big.off"), V, F)
+    files += [str(tmp_path / "big.obj"), str(tmp_path / "big.off")]
+    for path in files:
+        om = oracle.OracleMesh(path)
+        for t in (1, 2, 3, 7):
+            pm = _load_with_threads(product, path, t)
+            assert pm.ntri == om.ntri and _same_mesh(pm, om) and pm.max_model_size == om.max_model_size, (path, t)
+    # errors: the earliest one in file order, whatever the cut
+    lines = ["v %d 0 0" % i for i in range(3000)] + ["f %d %d %d" % (i + 1, i + 2, i + 3) for i in range(2900)]
+    broken = {
+        "bad_index_mid": lines[:4000] + ["f 1 2 99999"] + lines[4000:] + ["f 1 2 0"],
+        "bad_float_mid": lines[:1500] + ["v 1 x 3"] + lines[1500:4000] + ["f 1 2 99999"] + lines[4000:],
+        "forward_reference": ["v 0 0 0", "v 1 0 0", "f 1 2 3", "v 0 1 0"] + lines,
+    }
+    for name, ls in broken.items():
+        p = tmp_path / (name + ".obj")
+        p.write_text("\n".join(ls) + "\n")
+        msgs = []
+        for t in (1, 2, 5, 7):
+            with pytest.raises(product.GpvError) as ei:
+                _load_with_threads(product, str(p), t)
+            msgs.append(str(ei.value))
+        assert len(set(msgs)) == 1, (name, msgs)
+    off_bad = tmp_path / "bad.off"
+    off_bad.write_text("OFF\n4 3 0\n0 0 0\n1 0 0\n0 1 0\n0 0 1\n3 0 1 2\n3 0 1 9\n3 0 x 2\n")
+    msgs = []
+    for t in (1, 2, 3):
+        with pytest.raises(product.GpvError) as ei:
+            _load_with_threads(product, str(off_bad), t)
+        msgs.append(str(ei.value))
+    assert len(set(msgs)) == 1 and "out of range" in msgs[0], msgs
+
+
 @pytest.mark.parametrize("name,l1,l2", GOLDEN_CASES)
 def test_grid_sizing_matches_reference_fixture(product, tmp_path_factory, name, l1, l2):
     info, _ = golden("%s_%d_%d" % (name, l1, l2))
