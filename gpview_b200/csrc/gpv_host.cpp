@@ -271,18 +271,21 @@ extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
 }
 
 namespace {
-// operator>> tokens of [begin, end): whitespace-separated runs; a run that touches `end` belongs to this chunk (chunks are cut
-// at whitespace)
-void off_tokens(const char* data, size_t begin, size_t end, std::vector<Field>& out)
+// operator>> tokens of [begin, end): whitespace-separated runs (chunks are cut at whitespace, so a run never straddles a cut).
+// f(k, field) is called with the chunk-local token number; returns the number of tokens.
+template <class F>
+size_t off_tokens(const char* data, size_t begin, size_t end, F&& f)
 {
 	const char *p = data + begin, *e = data + end;
+	size_t k = 0;
 	for (;;) {
 		while (p < e && isspace((unsigned char)*p)) p++;
-		if (p >= e) return;
-		Field f{ p, 0 };
+		if (p >= e) return k;
+		Field fld{ p, 0 };
 		while (p < e && !isspace((unsigned char)*p)) p++;
-		f.n = (size_t)(p - f.p);
-		out.push_back(f);
+		fld.n = (size_t)(p - fld.p);
+		if (!f(k, fld)) return k;
+		k++;
 	}
 }
 } // namespace
@@ -292,7 +295,7 @@ extern "C" int gpv_load_off(const char* path, gpv_mesh* out)
 	memset(out, 0, sizeof *out);
 	std::vector<char> buf;
 	if (!read_file(path, buf)) return gpv::fail(std::string("Unable to open file \"") + path + "\""); // the reference abort()s (:187-191)
-	// tokenise in parallel: chunks are cut at whitespace
+	// pass 1: count the tokens of every chunk (chunks are cut at whitespace) -> the global number of each chunk's first token
 	const int nChunks = load_threads(buf.size());
 	std::vector<size_t> cut(1, 0);
 	for (int k = 1; k < nChunks; k++) {
@@ -301,33 +304,32 @@ extern "C" int gpv_load_off(const char* path, gpv_mesh* out)
 		cut.push_back(p);
 	}
 	cut.push_back(buf.size());
-	std::vector<std::vector<Field>> tok((size_t)nChunks);
-	run_chunks(nChunks, [&](int k) { off_tokens(buf.data(), cut[k], cut[k + 1], tok[k]); });
 	std::vector<size_t> base((size_t)nChunks + 1, 0);
-	for (int k = 0; k < nChunks; k++) base[k + 1] = base[k] + tok[k].size();
+	run_chunks(nChunks, [&](int k) { base[k + 1] = off_tokens(buf.data(), cut[k], cut[k + 1], [](size_t, const Field&) { return true; }); });
+	for (int k = 0; k < nChunks; k++) base[k + 1] += base[k];
 	const size_t nTok = base[nChunks];
-	auto token = [&](size_t i) -> const Field& { // token i of the file
-		size_t k = (size_t)(std::upper_bound(base.begin(), base.end(), i) - base.begin()) - 1;
-		return tok[k][i - base[k]];
-	};
+	// header and counts: tokens 0..3 (in >> header; in >> v_len >> f_len >> n_len)
+	Field head[4] = {};
+	off_tokens(buf.data(), 0, buf.size(), [&](size_t k, const Field& f) { head[k] = f; return k < 3; });
 	long nV = 0, nF = 0, nE = 0;
-	if (nTok < 1) return gpv::fail("OFF: empty file");                                          // in >> header
-	if (nTok < 4 || !field_to_long(token(1), nV) || !field_to_long(token(2), nF) || !field_to_long(token(3), nE))
-		return gpv::fail("OFF: bad counts line");                                                // in >> v_len >> f_len >> n_len
+	if (nTok < 1) return gpv::fail("OFF: empty file");
+	if (nTok < 4 || !field_to_long(head[1], nV) || !field_to_long(head[2], nF) || !field_to_long(head[3], nE)) return gpv::fail("OFF: bad counts line");
 	if (nV <= 0 || nF <= 0) return gpv::fail("OFF: no vertices or faces");
-	// token 4 + i (i < 3 nV) is a coordinate; then every face takes FOUR tokens: f_count and exactly three indices whatever
+	// pass 2: token 4 + i (i < 3 nV) is a coordinate; then every face takes FOUR tokens: f_count and exactly three indices whatever
 	// f_count says (:219-222).  The sequential reader fails at the first bad or missing token: so does this one.
 	const size_t vTok = 4, fTok = 4 + (size_t)nV * 3, needTok = fTok + (size_t)nF * 4;
 	std::vector<float> verts((size_t)nV * 3), tris((size_t)nF * 9);
-	std::vector<size_t> bad((size_t)nChunks, (size_t)-1); // first bad token index seen by each worker
-	const size_t haveTok = std::min(nTok, needTok);
-	run_chunks(nChunks, [&](int k) { // (any split of the token range will do: workers take equal shares)
-		const size_t i0 = vTok + (haveTok - vTok) * (size_t)k / (size_t)nChunks, i1 = vTok + (haveTok - vTok) * (size_t)(k + 1) / (size_t)nChunks;
-		for (size_t i = i0; i < i1; i++) {
-			const Field& f = token(i);
-			if (i < fTok) { if (!field_to_float(f, verts[i - vTok])) { bad[k] = i; return; } }
-			else { long q; if (!field_to_long(f, q)) { bad[k] = i; return; } }
-		}
+	std::vector<long> faceTok((size_t)nF * 4);
+	std::vector<size_t> bad((size_t)nChunks, (size_t)-1); // first bad token (global number) of each chunk
+	run_chunks(nChunks, [&](int k) {
+		off_tokens(buf.data(), cut[k], cut[k + 1], [&](size_t local, const Field& f) {
+			const size_t i = base[k] + local;
+			if (i < vTok) return true;
+			if (i >= needTok) return false;
+			const bool ok = i < fTok ? field_to_float(f, verts[i - vTok]) : field_to_long(f, faceTok[i - fTok]);
+			if (!ok) bad[k] = i;
+			return ok;
+		});
 	});
 	size_t firstBad = nTok < needTok ? nTok : (size_t)-1; // a missing token fails like a bad one
 	for (int k = 0; k < nChunks; k++) firstBad = std::min(firstBad, bad[k]);
@@ -338,8 +340,7 @@ extern "C" int gpv_load_off(const char* path, gpv_mesh* out)
 	run_chunks(nChunks, [&](int k) {
 		const size_t j0 = okFaces * (size_t)k / (size_t)nChunks, j1 = okFaces * (size_t)(k + 1) / (size_t)nChunks;
 		for (size_t j = j0; j < j1; j++) for (int c = 0; c < 3; c++) {
-			long q = 0;
-			field_to_long(token(fTok + j * 4 + 1 + c), q);
+			const long q = faceTok[j * 4 + 1 + c];
 			if (q < 0 || q >= nV) { badIdx[k] = j; return; }
 			memcpy(&tris[j * 9 + c * 3], &verts[(size_t)q * 3], 3 * sizeof(float));
 		}
