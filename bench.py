@@ -429,12 +429,36 @@ def main():
         roof_hbm = {"kernel": sat_name, "bound": "hbm", "achieved": out_bytes / (k_l2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": out_bytes / (k_l2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": n_sat.get("dram_bytes") if world == 1 else None,
                     "peak_source": hbm_src, "algorithmic": "1 B per Level-2 voxel written (%d B)" % out_bytes}
+        # every phase of the pipeline against the roofline that bounds it (algorithmic bytes / flops per unit x units
+        # of this model, over the phase's CUDA-event time).  The Level-1 phases of a cessna-sized model are tens of microseconds of
+        # launch-latency-bound work: their fractions say how far a 4 M-cell grid is from filling the machine, not kernel quality.
+        try:
+            ph = {k: v / args.steps for k, v in phase_acc.items()}
+            cells_b, nb_b, ntri_b = float(res.cells), float(res.nb), float(mesh.ntri)
+            l1_flops = float(FLOPS_PER_TRIBOX * res.stats["l1_box_tests"])  # each binning sweep runs every clipped-footprint test once
+            table = [("setup", "hbm", 4 * cells_b + 16 * plane + 212 * ntri_b, "k_clear + k_prepare + work-space scans: counters zeroed, 36 B read + 176 B written per triangle"),
+                     ("bin_count", "fp32", l1_flops, "124 FLOP per (triangle, cell) test of the clipped footprints"),
+                     ("bin_fill", "fp32", l1_flops, "124 FLOP per (triangle, cell) test of the clipped footprints"),
+                     ("scan", "hbm", 8 * cells_b + 8 * nb_b + 24 * plane, "4 B read + 4 B written per cell, 8 B per boundary cell, three column scans"),
+                     ("fill_sweep", "hbm", 1.125 * cells_b, "1 B written + 1 bit read per cell"),
+                     ("l2_rays", "fp32", 51.0 * res.stats.get("l2_ray_tests", 0), "51 FLOP per reference-equivalent ray test"),
+                     ("l2", "fp32", float(flops), "124 FLOP per reference-equivalent tri-box test")]
+            per_phase = []
+            for name, bound, work, what in table:
+                t = ph.get(name, 0.0) * 1e-3
+                if t <= 0:
+                    continue
+                peak = hbm_peak * 1e9 if bound == "hbm" else fp32_peak
+                per_phase.append({"phase": name, "ms": round(t * 1e3, 4), "bound": bound, "achieved": work / t / (1e9 if bound == "hbm" else 1e12),
+                                  "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": work / t / peak, "algorithmic": what})
+        except Exception as e:  # the table is commentary: never lose the bench line over it
+            per_phase = [{"error": repr(e)}]
         line = {"metric": "G tri-box tests/s", "value": value, "unit": "G tri-box tests/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "ms_per_model": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "cessna.obj fixture (reference sample mesh)" if args.mesh == "cessna" else "synthetic",
                 "config": dict(workload_config(args), parallelism=("z-slabs x%d (cuts %s), Level-1 replicated, %s; gathered streams == single-GPU result: %s" % (world, cuts, "slabs written into rank 0's buffers over NVLink peer memory from inside the kernels (GPV_GATHER), 8-byte count exchange through a mailbox, no collective" if peer else "NCCL send/recv gather to rank 0", gather_ok)) if world > 1 else "1 GPU",
                                tri_box_tests_per_model=int(tests), triangles=mesh.ntri, grid=[int(x) for x in res.num_div]),
-                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_rays": roof_rays, "roofline_hbm": roof_hbm,
+                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_rays": roof_rays, "roofline_hbm": roof_hbm, "roofline_phases": per_phase,
                 "phase_ms": {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0},
                 "counts": {"l1_inside": whole.counts[0], "l1_boundary": whole.counts[1]}}
         if world == 1 and not args.no_cpu_baseline and path is not None:
