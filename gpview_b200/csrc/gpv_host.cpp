@@ -9,6 +9,7 @@
 // Only what feeds the voxelizer is kept (positions, faces, bbox); normals/texcoords/adjacency of the viewer are not.
 #include "../../include/gpview_b200.h"
 #include "gpv_internal.h"
+#include "gpv_parse.h"
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -21,15 +22,41 @@
 
 namespace {
 
-bool read_file(const char* path, std::vector<char>& buf)
+// Grow-only, uninitialised scratch memory kept per host thread.  A dataset run loads thousands of ~170 KB files per thread; a
+// fresh std::vector per file is zero-filled and, above malloc's 128 KB mmap threshold, mapped and unmapped every time: ~140
+// page faults per load, as expensive as the parse itself.  Blocks above 64 MB are given back when the load returns.
+template <class T>
+struct Scratch {
+	T* p = nullptr;
+	size_t cap = 0;
+	T* get(size_t n)
+	{
+		if (n > cap) {
+			free(p);
+			cap = n + n / 2 + 64;
+			p = (T*)malloc(cap * sizeof(T));
+			if (!p) cap = 0;
+		}
+		return p;
+	}
+	void trim() { if (cap * sizeof(T) > ((size_t)64 << 20)) { free(p); p = nullptr; cap = 0; } }
+	~Scratch() { free(p); }
+};
+
+// the whole file into `buf`; false = cannot open / read / allocate
+bool read_file(const char* path, Scratch<char>& buf, size_t& size)
 {
+	size = 0;
 	FILE* f = fopen(path, "rb");
 	if (!f) return false;
 	fseek(f, 0, SEEK_END);
 	long sz = ftell(f);
 	fseek(f, 0, SEEK_SET);
-	buf.resize(sz > 0 ? (size_t)sz : 0);
-	bool ok = sz <= 0 || fread(buf.data(), 1, (size_t)sz, f) == (size_t)sz;
+	bool ok = sz <= 0;
+	if (sz > 0 && buf.get((size_t)sz)) {
+		size = (size_t)sz;
+		ok = fread(buf.p, 1, size, f) == size;
+	}
 	fclose(f);
 	return ok;
 }
@@ -51,26 +78,9 @@ void split_fields(const char* s, size_t len, char delim, std::vector<Field>& out
 	}
 }
 
-bool field_to_float(const Field& f, float& v) // std::stof == strtof on the field
-{
-	char tmp[128];
-	if (f.n == 0 || f.n >= sizeof tmp) return false;
-	memcpy(tmp, f.p, f.n);
-	tmp[f.n] = 0;
-	char* end;
-	v = strtof(tmp, &end);
-	return end != tmp;
-}
-bool field_to_long(const Field& f, long& v) // std::stoi
-{
-	char tmp[64];
-	if (f.n == 0 || f.n >= sizeof tmp) return false;
-	memcpy(tmp, f.p, f.n);
-	tmp[f.n] = 0;
-	char* end;
-	v = strtol(tmp, &end, 10);
-	return end != tmp;
-}
+// std::stof / std::stoi on a field: same values as strtof / strtol, by the short exact path of gpv_parse.h when there is one
+inline bool field_to_float(const Field& f, float& v) { return gpv::parse_float(f.p, f.n, v); }
+inline bool field_to_long(const Field& f, long& v) { return gpv::parse_long(f.p, f.n, v); }
 
 // bbox padding by 0.001*|diagonal| and maxModelSize (src/Object.cpp:572-583; VectorMagnitude includes/FloatVector.h:323)
 void finish_bbox(const float mn[3], const float mx[3], gpv_mesh* m)
@@ -88,13 +98,62 @@ void finish_bbox(const float mn[3], const float mx[3], gpv_mesh* m)
 	m->max_model_size = ex > eyz ? ex : eyz;
 }
 
-int export_mesh(std::vector<float>& tris, int64_t nVerts, const float mn[3], const float mx[3], gpv_mesh* out)
+// The triangle block a gpv_mesh owns: 16 bytes of header (the block's capacity) in front of the floats.  free_tris() parks the
+// thread's last block (up to 16 MB) for the thread's next load instead of handing it back to malloc: same page-fault
+// argument as Scratch.  Only gpv_free_mesh() releases a mesh's triangles.
+struct TriBlockCache {
+	char* base = nullptr;
+	~TriBlockCache() { free(base); }
+};
+thread_local TriBlockCache g_triCache;
+const size_t kTriHeader = 16;
+
+float* alloc_tris(size_t nTri)
 {
-	out->n_tri = (int64_t)(tris.size() / 9);
+	const size_t need = kTriHeader + nTri * 9 * sizeof(float) + 16;
+	TriBlockCache& c = g_triCache;
+	if (c.base) {
+		size_t cap;
+		memcpy(&cap, c.base, sizeof cap);
+		if (cap >= need && cap <= 4 * need) {
+			char* b = c.base;
+			c.base = nullptr;
+			return (float*)(b + kTriHeader);
+		}
+	}
+	const size_t cap = need + need / 8;
+	char* b = (char*)malloc(cap);
+	if (!b) return nullptr;
+	memcpy(b, &cap, sizeof cap);
+	return (float*)(b + kTriHeader);
+}
+void free_tris(float* tris)
+{
+	char* b = (char*)tris - kTriHeader;
+	size_t cap;
+	memcpy(&cap, b, sizeof cap);
+	TriBlockCache& c = g_triCache;
+	if (cap <= ((size_t)16 << 20)) std::swap(b, c.base); // keep the newer block, release the one that was parked
+	free(b);
+}
+
+// bbox of n floats taken as xyz triples (n > 0)
+void bbox_of(const float* xyz, size_t n, float mn[3], float mx[3])
+{
+	for (int a = 0; a < 3; a++) mn[a] = mx[a] = xyz[a];
+	for (size_t i = 0; i < n; i += 3) for (int a = 0; a < 3; a++) {
+		const float x = xyz[i + a];
+		mn[a] = mn[a] < x ? mn[a] : x;
+		mx[a] = mx[a] > x ? mx[a] : x;
+	}
+}
+
+// `tris` comes from alloc_tris(nTri) and is owned by the mesh from here on
+int export_mesh(float* tris, int64_t nTri, int64_t nVerts, const float mn[3], const float mx[3], gpv_mesh* out)
+{
+	out->n_tri = nTri;
 	out->n_verts = nVerts;
-	out->tris = (float*)malloc(tris.size() * sizeof(float) + 16);
-	if (!out->tris) return gpv::fail("out of host memory");
-	memcpy(out->tris, tris.data(), tris.size() * sizeof(float));
+	out->tris = tris;
 	finish_bbox(mn, mx, out);
 	return 0;
 }
@@ -139,23 +198,54 @@ struct ObjChunk {
 	std::vector<size_t> fLine, fVertsBefore; // chunk-local line number; `v` lines of this chunk before the face
 	size_t errLine = (size_t)-1;          // chunk-local line number of the first parse error
 	int errKind = 0;                      // 1 vertex coordinate, 2 face index
+	void reset()
+	{
+		begin = end = nLines = 0;
+		v.clear(); vParsed.clear(); f.clear(); fLine.clear(); fVertsBefore.clear();
+		errLine = (size_t)-1;
+		errKind = 0;
+	}
+};
+
+// per host thread: what a load needs besides the triangle block it returns
+struct LoadScratch {
+	Scratch<char> file;
+	Scratch<float> verts;
+	Scratch<long> faceTok;
+	ObjChunk obj;
+};
+thread_local LoadScratch g_loadScratch;
+struct ScratchTrim { // a single huge file must not pin its text for the life of the thread
+	LoadScratch& s;
+	~ScratchTrim()
+	{
+		s.file.trim(); s.verts.trim(); s.faceTok.trim();
+		if (s.obj.v.capacity() * sizeof(float) > ((size_t)64 << 20)) s.obj = ObjChunk();
+	}
+};
+struct TriGuard { // error returns between alloc_tris() and export_mesh()
+	float* p;
+	~TriGuard() { if (p) free_tris(p); }
 };
 
 void parse_obj_chunk(const char* data, ObjChunk& c)
 {
-	std::vector<Field> bySpace, byTab;
+	std::vector<Field> w;
 	size_t pos = c.begin;
 	while (pos < c.end) {
-		size_t e = pos;
-		while (data[e] != '\n') e++; // the chunk ends with '\n'
+		size_t e = pos, nSpace = 0, nTab = 0;
+		for (; data[e] != '\n'; e++) { // the chunk ends with '\n'
+			nSpace += data[e] == ' ';
+			nTab += data[e] == '\t';
+		}
 		const char* line = data + pos;
 		const size_t len = e - pos;
 		pos = e + 1;
 		const size_t lineNo = c.nLines++;
-		split_fields(line, len, ' ', bySpace);
-		split_fields(line, len, '\t', byTab);
-		const std::vector<Field>& w = bySpace.size() > byTab.size() ? bySpace : byTab; // :419-423
-		if (w.empty()) continue;
+		if (len == 0) continue;
+		// split on " " and on "\t", keep the split with more fields, the tab split on a tie (:419-423): a non-empty line has
+		// one field more than it has delimiters, so the counts decide and the line is split once
+		split_fields(line, len, nSpace > nTab ? ' ' : '\t', w);
 		if (w[0].n == 1 && w[0].p[0] == 'v') {
 			float pt[3] = { 0, 0, 0 };
 			unsigned char got = 0;
@@ -182,7 +272,7 @@ void parse_obj_chunk(const char* data, ObjChunk& c)
 }
 
 // [0, usable) cut into n pieces at line starts
-std::vector<size_t> line_cuts(const std::vector<char>& buf, size_t usable, int n)
+std::vector<size_t> line_cuts(const char* buf, size_t usable, int n)
 {
 	std::vector<size_t> cut(1, 0);
 	for (int k = 1; k < n; k++) {
@@ -199,21 +289,25 @@ std::vector<size_t> line_cuts(const std::vector<char>& buf, size_t usable, int n
 extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
 {
 	memset(out, 0, sizeof *out);
-	std::vector<char> buf;
-	if (!read_file(path, buf)) return gpv::fail(std::string("Unable to open file \"") + path + "\""); // the reference abort()s (:409-413)
-	size_t usable = buf.size(); // getline at EOF: `if (!in.good()) break;` drops an unterminated last line (:425)
+	LoadScratch& S = g_loadScratch;
+	ScratchTrim trimOnReturn{ S };
+	size_t fileSize = 0;
+	if (!read_file(path, S.file, fileSize)) return gpv::fail(std::string("Unable to open file \"") + path + "\""); // the reference abort()s (:409-413)
+	const char* buf = S.file.p;
+	size_t usable = fileSize; // getline at EOF: `if (!in.good()) break;` drops an unterminated last line (:425)
 	while (usable > 0 && buf[usable - 1] != '\n') usable--;
 	const int nChunks = load_threads(usable);
 	const std::vector<size_t> cut = line_cuts(buf, usable, nChunks);
-	std::vector<ObjChunk> ch((size_t)nChunks);
-	for (int k = 0; k < nChunks; k++) { ch[k].begin = cut[k]; ch[k].end = cut[k + 1]; }
-	run_chunks(nChunks, [&](int k) { parse_obj_chunk(buf.data(), ch[k]); });
+	std::vector<ObjChunk> many(nChunks > 1 ? (size_t)nChunks : 0);
+	ObjChunk* ch = nChunks > 1 ? many.data() : &S.obj; // one chunk: the thread's own, its vectors keep their capacity
+	for (int k = 0; k < nChunks; k++) { ch[k].reset(); ch[k].begin = cut[k]; ch[k].end = cut[k + 1]; }
+	run_chunks(nChunks, [&](int k) { parse_obj_chunk(buf, ch[k]); });
 
 	// ---- stitch in file order.  The sequential reader stops at its first error: everything behind the first chunk with a parse
 	// error is ignored, and the earliest error -- parse error or face index out of range -- is the one reported.
-	size_t nUsed = ch.size(), lineBase = 0;
-	std::vector<size_t> vertBase(ch.size() + 1, 0), faceBase(ch.size() + 1, 0), firstLine(ch.size() + 1, 0);
-	for (size_t k = 0; k < ch.size(); k++) {
+	size_t nUsed = (size_t)nChunks, lineBase = 0;
+	std::vector<size_t> vertBase((size_t)nChunks + 1, 0), faceBase((size_t)nChunks + 1, 0), firstLine((size_t)nChunks + 1, 0);
+	for (size_t k = 0; k < (size_t)nChunks; k++) {
 		firstLine[k] = lineBase;
 		lineBase += ch[k].nLines;
 		vertBase[k + 1] = vertBase[k] + ch[k].vParsed.size();
@@ -221,10 +315,11 @@ extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
 		if (ch[k].errKind) { nUsed = k + 1; break; }
 	}
 	const size_t nVerts = vertBase[nUsed], nFaces = faceBase[nUsed];
-	std::vector<float> verts(nVerts * 3);
+	float* verts = nChunks > 1 ? S.verts.get(nVerts * 3 + 3) : ch[0].v.data(); // one chunk: its vertex array is the vertex array
+	if (nChunks > 1 && !verts) return gpv::fail("out of host memory");
 	bool shortLine = false;
 	for (size_t k = 0; k < nUsed; k++) {
-		if (!ch[k].v.empty()) memcpy(&verts[vertBase[k] * 3], ch[k].v.data(), ch[k].v.size() * sizeof(float));
+		if (nChunks > 1 && !ch[k].v.empty()) memcpy(&verts[vertBase[k] * 3], ch[k].v.data(), ch[k].v.size() * sizeof(float));
 		for (unsigned char g : ch[k].vParsed) shortLine |= g < 3;
 	}
 	if (shortLine) { // `pt` lives outside the reference's loop: a short `v` line keeps the previous line's trailing coordinates (zero at first)
@@ -236,7 +331,9 @@ extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
 		}
 	}
 	// faces -> triangles; a face may only name vertices that were defined before its line
-	std::vector<float> tris(nFaces * 9);
+	float* tris = alloc_tris(nFaces);
+	if (!tris) return gpv::fail("out of host memory");
+	TriGuard guard{ tris };
 	std::vector<size_t> badFace(nUsed, (size_t)-1);
 	run_chunks((int)nUsed, [&](int k) {
 		const ObjChunk& c = ch[k];
@@ -261,13 +358,9 @@ extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
 	}
 	if (nVerts == 0) return gpv::fail(std::string("no vertices in ") + path);
 	float mn[3], mx[3]; // bbox over ALL `v` lines (:441-450)
-	for (int a = 0; a < 3; a++) mn[a] = mx[a] = verts[a];
-	for (size_t i = 0; i < nVerts; i++) for (int a = 0; a < 3; a++) {
-		const float x = verts[i * 3 + a];
-		mn[a] = mn[a] < x ? mn[a] : x;
-		mx[a] = mx[a] > x ? mx[a] : x;
-	}
-	return export_mesh(tris, (int64_t)nVerts, mn, mx, out);
+	bbox_of(verts, nVerts * 3, mn, mx);
+	guard.p = nullptr;
+	return export_mesh(tris, (int64_t)nFaces, (int64_t)nVerts, mn, mx, out);
 }
 
 namespace {
@@ -279,10 +372,10 @@ size_t off_tokens(const char* data, size_t begin, size_t end, F&& f)
 	const char *p = data + begin, *e = data + end;
 	size_t k = 0;
 	for (;;) {
-		while (p < e && isspace((unsigned char)*p)) p++;
+		while (p < e && gpv::is_space((unsigned char)*p)) p++;
 		if (p >= e) return k;
 		Field fld{ p, 0 };
-		while (p < e && !isspace((unsigned char)*p)) p++;
+		while (p < e && !gpv::is_space((unsigned char)*p)) p++;
 		fld.n = (size_t)(p - fld.p);
 		if (!f(k, fld)) return k;
 		k++;
@@ -290,27 +383,63 @@ size_t off_tokens(const char* data, size_t begin, size_t end, F&& f)
 }
 } // namespace
 
+namespace {
+// Pass 2 over one chunk: token number i = base + local is a header token (i < vTok), a coordinate (i < fTok) or a face token
+// (i < needTok).  Numbers are converted where they stand (gpv::scan_*): when the conversion ends at whitespace the token is done;
+// anything else -- trailing characters, a form without a short exact path -- takes the whole token through the library,
+// exactly like the field-based route.  Returns the chunk-local number of the token it stopped at (`bad` = its global number
+// when it stopped because of a failed conversion).
+size_t off_parse_chunk(const char* data, size_t begin, size_t end, size_t base, size_t vTok, size_t fTok, size_t needTok, float* verts, long* faceTok, size_t& bad)
+{
+	const char *p = data + begin, *e = data + end;
+	size_t local = 0;
+	for (;;) {
+		while (p < e && gpv::is_space((unsigned char)*p)) p++;
+		if (p >= e) return local;
+		const size_t i = base + local;
+		if (i >= needTok) return local;
+		if (i >= vTok) {
+			const char* q = i < fTok ? gpv::scan_float(p, e, verts[i - vTok]) : gpv::scan_long(p, e, faceTok[i - fTok]);
+			if (q && (q == e || gpv::is_space((unsigned char)*q))) { p = q; local++; continue; }
+		}
+		const char* s = p;
+		while (p < e && !gpv::is_space((unsigned char)*p)) p++;
+		if (i >= vTok) {
+			const bool ok = i < fTok ? gpv::parse_float(s, (size_t)(p - s), verts[i - vTok]) : gpv::parse_long(s, (size_t)(p - s), faceTok[i - fTok]);
+			if (!ok) { bad = i; return local; }
+		}
+		local++;
+	}
+}
+} // namespace
+
 extern "C" int gpv_load_off(const char* path, gpv_mesh* out)
 {
 	memset(out, 0, sizeof *out);
-	std::vector<char> buf;
-	if (!read_file(path, buf)) return gpv::fail(std::string("Unable to open file \"") + path + "\""); // the reference abort()s (:187-191)
+	LoadScratch& S = g_loadScratch;
+	ScratchTrim trimOnReturn{ S };
+	size_t fileSize = 0;
+	if (!read_file(path, S.file, fileSize)) return gpv::fail(std::string("Unable to open file \"") + path + "\""); // the reference abort()s (:187-191)
+	const char* buf = S.file.p;
 	// pass 1: count the tokens of every chunk (chunks are cut at whitespace) -> the global number of each chunk's first token
-	const int nChunks = load_threads(buf.size());
+	const int nChunks = load_threads(fileSize);
 	std::vector<size_t> cut(1, 0);
 	for (int k = 1; k < nChunks; k++) {
-		size_t p = std::max(cut.back(), buf.size() * (size_t)k / (size_t)nChunks);
-		while (p < buf.size() && !isspace((unsigned char)buf[p])) p++;
+		size_t p = std::max(cut.back(), fileSize * (size_t)k / (size_t)nChunks);
+		while (p < fileSize && !gpv::is_space((unsigned char)buf[p])) p++;
 		cut.push_back(p);
 	}
-	cut.push_back(buf.size());
+	cut.push_back(fileSize);
 	std::vector<size_t> base((size_t)nChunks + 1, 0);
-	run_chunks(nChunks, [&](int k) { base[k + 1] = off_tokens(buf.data(), cut[k], cut[k + 1], [](size_t, const Field&) { return true; }); });
-	for (int k = 0; k < nChunks; k++) base[k + 1] += base[k];
-	const size_t nTok = base[nChunks];
+	if (nChunks > 1) { // one chunk (every file below 8 MB): its tokens are counted by pass 2 itself
+		run_chunks(nChunks, [&](int k) { base[k + 1] = off_tokens(buf, cut[k], cut[k + 1], [](size_t, const Field&) { return true; }); });
+		for (int k = 0; k < nChunks; k++) base[k + 1] += base[k];
+	}
 	// header and counts: tokens 0..3 (in >> header; in >> v_len >> f_len >> n_len)
 	Field head[4] = {};
-	off_tokens(buf.data(), 0, buf.size(), [&](size_t k, const Field& f) { head[k] = f; return k < 3; });
+	size_t nHead = 0;
+	off_tokens(buf, 0, fileSize, [&](size_t k, const Field& f) { head[k] = f; nHead = k + 1; return k < 3; });
+	size_t nTok = nChunks > 1 ? base[nChunks] : nHead;
 	long nV = 0, nF = 0, nE = 0;
 	if (nTok < 1) return gpv::fail("OFF: empty file");
 	if (nTok < 4 || !field_to_long(head[1], nV) || !field_to_long(head[2], nF) || !field_to_long(head[3], nE)) return gpv::fail("OFF: bad counts line");
@@ -318,19 +447,19 @@ extern "C" int gpv_load_off(const char* path, gpv_mesh* out)
 	// pass 2: token 4 + i (i < 3 nV) is a coordinate; then every face takes FOUR tokens: f_count and exactly three indices whatever
 	// f_count says (:219-222).  The sequential reader fails at the first bad or missing token: so does this one.
 	const size_t vTok = 4, fTok = 4 + (size_t)nV * 3, needTok = fTok + (size_t)nF * 4;
-	std::vector<float> verts((size_t)nV * 3), tris((size_t)nF * 9);
-	std::vector<long> faceTok((size_t)nF * 4);
+	// a vertex record takes >= 6 bytes of text and a face record >= 8: counts the file cannot hold end in a missing token below,
+	// and must not size the arrays
+	if ((size_t)nV > fileSize / 6 + 1) return gpv::fail("OFF: bad vertex record");
+	const size_t nFcap = std::min<size_t>((size_t)nF, fileSize / 8 + 2);
+	float* verts = S.verts.get((size_t)nV * 3);
+	long* faceTok = S.faceTok.get(nFcap * 4);
+	float* tris = alloc_tris(nFcap);
+	TriGuard guard{ tris };
+	if (!verts || !faceTok || !tris) return gpv::fail("out of host memory");
 	std::vector<size_t> bad((size_t)nChunks, (size_t)-1); // first bad token (global number) of each chunk
-	run_chunks(nChunks, [&](int k) {
-		off_tokens(buf.data(), cut[k], cut[k + 1], [&](size_t local, const Field& f) {
-			const size_t i = base[k] + local;
-			if (i < vTok) return true;
-			if (i >= needTok) return false;
-			const bool ok = i < fTok ? field_to_float(f, verts[i - vTok]) : field_to_long(f, faceTok[i - fTok]);
-			if (!ok) bad[k] = i;
-			return ok;
-		});
-	});
+	std::vector<size_t> seen((size_t)nChunks, 0); // tokens of the chunk walked before pass 2 stopped
+	run_chunks(nChunks, [&](int k) { seen[k] = off_parse_chunk(buf, cut[k], cut[k + 1], base[k], vTok, fTok, needTok, verts, faceTok, bad[k]); });
+	if (nChunks == 1) nTok = bad[0] == (size_t)-1 ? seen[0] : needTok; // ran out of tokens (< needTok) or saw enough; behind a bad token the count no longer matters
 	size_t firstBad = nTok < needTok ? nTok : (size_t)-1; // a missing token fails like a bad one
 	for (int k = 0; k < nChunks; k++) firstBad = std::min(firstBad, bad[k]);
 	if (firstBad != (size_t)-1 && firstBad < fTok) return gpv::fail("OFF: bad vertex record");
@@ -350,13 +479,9 @@ extern "C" int gpv_load_off(const char* path, gpv_mesh* out)
 	if (firstBadFace != (size_t)-1) return gpv::fail("OFF: face index out of range");
 	if (firstBad != (size_t)-1) return gpv::fail("OFF: bad face record");
 	float mn[3], mx[3]; // bbox over the vertices the triangles reference (:257-266)
-	for (int a = 0; a < 3; a++) mn[a] = mx[a] = tris[a];
-	for (size_t i = 0; i < tris.size(); i += 3) for (int a = 0; a < 3; a++) {
-		float x = tris[i + a];
-		mn[a] = mn[a] < x ? mn[a] : x;
-		mx[a] = mx[a] > x ? mx[a] : x;
-	}
-	return export_mesh(tris, nV, mn, mx, out);
+	bbox_of(tris, (size_t)nF * 9, mn, mx);
+	guard.p = nullptr;
+	return export_mesh(tris, (int64_t)nF, nV, mn, mx, out);
 }
 
 // main()'s dispatch on the last three characters (src/GPView.cpp:1642-1659)
@@ -375,20 +500,17 @@ extern "C" int gpv_mesh_from_triangles(const float* tris, int64_t n_tri, gpv_mes
 {
 	memset(out, 0, sizeof *out);
 	if (n_tri <= 0) return gpv::fail("gpv_mesh_from_triangles: no triangles");
-	std::vector<float> t(tris, tris + n_tri * 9);
+	float* t = alloc_tris((size_t)n_tri);
+	if (!t) return gpv::fail("out of host memory");
+	memcpy(t, tris, (size_t)n_tri * 9 * sizeof(float));
 	float mn[3], mx[3];
-	for (int a = 0; a < 3; a++) mn[a] = mx[a] = t[a];
-	for (size_t i = 0; i < t.size(); i += 3) for (int a = 0; a < 3; a++) {
-		float x = t[i + a];
-		mn[a] = mn[a] < x ? mn[a] : x;
-		mx[a] = mx[a] > x ? mx[a] : x;
-	}
-	return export_mesh(t, n_tri * 3, mn, mx, out);
+	bbox_of(t, (size_t)n_tri * 9, mn, mx);
+	return export_mesh(t, n_tri, n_tri * 3, mn, mx, out);
 }
 
 extern "C" void gpv_free_mesh(gpv_mesh* m)
 {
-	if (m && m->tris) { free(m->tris); m->tris = nullptr; m->n_tri = 0; }
+	if (m && m->tris) { free_tris(m->tris); m->tris = nullptr; m->n_tri = 0; }
 }
 
 static int next_div4(int a) { return (a % 4 == 0) ? a : a + (4 - a % 4); } // includes/Utilities.h:313
@@ -432,20 +554,27 @@ extern "C" int gpv_save(const gpv_mesh* mesh, const gpv_result* res, const gpv_h
 		fprintf(f, "%g\t%g\t%g\n", g.grid_size2[0], g.grid_size2[1], g.grid_size2[2]);
 		fprintf(f, "%lld\n%lld\n", (long long)res->l2_inside, (long long)res->l2_boundary);
 	}
-	fclose(f);
+	const bool cfgBad = ferror(f) != 0;
+	if (fclose(f) != 0 || cfgBad) return gpv::fail("write error on " + prefix + "VoxelConfig.txt");
+	std::string failed; // first stream that could not be opened or written in full (a full disk must not pass for a saved model)
 	auto dump = [&](const char* name, const void* p, size_t bytes, uint8_t fill) -> bool {
 		FILE* o = fopen((prefix + name).c_str(), "wb");
-		if (!o) return false;
-		if (p) fwrite(p, 1, bytes, o);
-		else { std::vector<uint8_t> z(bytes, fill); fwrite(z.data(), 1, bytes, o); } // stream not requested: neutral value
-		fclose(o);
-		return true;
+		if (!o) { failed = "Unable to open output file for writing: " + prefix + name; return false; }
+		bool ok = true;
+		if (p) ok = fwrite(p, 1, bytes, o) == bytes;
+		else { // stream not requested: neutral value, written in pieces
+			const std::vector<uint8_t> z(std::min<size_t>(bytes, (size_t)1 << 20), fill);
+			for (size_t done = 0; ok && done < bytes; done += z.size()) { const size_t n = std::min(z.size(), bytes - done); ok = fwrite(z.data(), 1, n, o) == n; }
+		}
+		ok = (fclose(o) == 0) && ok;
+		if (!ok) failed = "write error on " + prefix + name;
+		return ok;
 	};
 	const size_t cells = (size_t)res->cells, l2n = (size_t)res->n_boundary * (size_t)res->n23;
 	bool ok = dump("Level1InOut.raw", h->level1_inout, cells, 0) && dump("Level1Normal.raw", h->level1_normal, cells * 3, 127);
 	if (l2) ok = ok && dump("Level1BoundaryPrefixSum.raw", h->prefix, cells * 4, 0) && dump("Level2InOut.raw", h->level2_inout, l2n, 0) &&
 	             dump("Level2Normal.raw", h->level2_normal, l2n * 3, 127);
-	return ok ? 0 : gpv::fail("Unable to open output file for writing");
+	return ok ? 0 : gpv::fail(failed);
 }
 
 // ---- reader of the six-file set.  The reference can only read back one hard-coded 48x64x64 uchar grid

@@ -210,3 +210,98 @@ def test_voxel_files_round_trip(product, oracle, tmp_path_factory, tmp_path):
     assert v1["num_div2"] is None and v1["level2_inout"] is None and np.array_equal(v1["level1_inout"], r1.l1_state * 127)
     with pytest.raises(product.GpvError):
         B.load_voxels(str(d2), 9)
+
+
+# ------------------------------------------------------------------------------------------------ number fields of the loaders
+@pytest.fixture(scope="module")
+def parse_probe():
+    """gpview_b200/csrc/gpv_parse.h compiled for the test (tests/cpu_probe/parse_probe.cpp)."""
+    import subprocess
+    from util import ROOT
+    here = os.path.join(ROOT, "tests", "cpu_probe")
+    so, src, hdr = os.path.join(here, "parse_probe.so"), os.path.join(here, "parse_probe.cpp"), os.path.join(ROOT, "gpview_b200", "csrc", "gpv_parse.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", so, src])
+    L = C.CDLL(so)
+    for n in ("probe_parse_float_fuzz", "probe_parse_long_fuzz"):
+        getattr(L, n).restype = C.c_int64
+        getattr(L, n).argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_char_p, C.POINTER(C.c_int64)]
+    L.probe_parse_float.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_float)]
+    L.probe_parse_long.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_long)]
+    L.probe_eight_digits.argtypes = [C.c_char_p]
+    L.probe_eight_digits.restype = C.c_uint32
+    return L
+
+
+FIELD_KINDS = ["%.9g of random floats", "fixed-point coordinates", "float midpoints (exact, cut, nudged)", "digit soup", "garbage and tails", "integers"]
+
+
+@pytest.mark.parametrize("kind", range(6))
+def test_number_fields_equal_strtof_and_strtol(parse_probe, kind):
+    """The loaders' scanners must return what std::stof / std::stoi (strtof / strtol) return on the same field -- value bits,
+    whether a conversion happened, and where it ended -- on 1.5 M seeded fields of each kind, both as coordinates and as
+    indices.  Without the float-midpoint guard of gpv_parse.h the midpoint kind alone disagrees ~4000 times per million."""
+    first, fast = C.create_string_buffer(64), C.c_int64()
+    for seed in (1, 20240607, 77):
+        bad = parse_probe.probe_parse_float_fuzz(seed, 500_000, kind, first, C.byref(fast))
+        assert bad == 0, (FIELD_KINDS[kind], "float", first.value)
+        if kind < 4:
+            assert fast.value > 100_000, (FIELD_KINDS[kind], "the short path is never taken", fast.value)
+        bad = parse_probe.probe_parse_long_fuzz(seed, 500_000, kind, first, C.byref(fast))
+        assert bad == 0, (FIELD_KINDS[kind], "long", first.value)
+
+
+def test_number_fields_known_cases(parse_probe):
+    """Hand-picked fields: (text, converts?, value) as strtof / strtol define them."""
+    import struct
+    f32 = lambda x: struct.unpack("f", struct.pack("f", x))[0]
+    cases = [(b"1", 1.0), (b"-0", -0.0), (b"+.5", 0.5), (b"1.", 1.0), (b"1.e2", 100.0), (b"1e", 1.0), (b"1e+", 1.0), (b"1.5abc", 1.5), (b"1.25\r", 1.25),
+             (b"0x10", 16.0), (b"0x1p3", 8.0), (b"1e39", float("inf")), (b"1e-46", 0.0), (b"1.17549435e-38", f32(1.17549435e-38)), (b"1e-40", f32(1e-40)),
+             (b"16777217", 16777216.0), (b"16777219", 16777220.0), (b"0.1", f32(0.1)), (b"-19.624605178833008", f32(-19.624605178833008)),
+             (b"3.4028234663852886e38", f32(3.4028234663852886e38)), (b"inf", float("inf")), (b"-Infinity", float("-inf")), (b" 2", 2.0),
+             (b"00000000000000000000000001.5", 1.5), (b"0.000000000000000000000000000015e29", f32(1.5)), (b"123456789012345678901234567890", f32(1.2345678901234568e29))]
+    v = C.c_float()
+    for txt, want in cases:
+        assert parse_probe.probe_parse_float(txt, len(txt), C.byref(v)) == 1, txt
+        assert struct.pack("f", v.value) == struct.pack("f", want), (txt, v.value, want)
+    for txt in (b"", b".", b"-", b"e5", b"x", b"+-1", b"- 1", b"/3"):
+        assert parse_probe.probe_parse_float(txt, len(txt), C.byref(v)) == 0, txt
+    n = C.c_long()
+    for txt, want in [(b"7", 7), (b"-12", -12), (b"+3", 3), (b"007", 7), (b"12/5", 12), (b" 4", 4), (b"99999999999999999999", 2**63 - 1), (b"-99999999999999999999", -2**63), (b"1e5", 1)]:
+        assert parse_probe.probe_parse_long(txt, len(txt), C.byref(n)) == 1 and n.value == want, (txt, n.value)
+    for txt in (b"", b"-", b"x1", b"/1", b"+ 1"):
+        assert parse_probe.probe_parse_long(txt, len(txt), C.byref(n)) == 0, txt
+    rng = np.random.default_rng(5)
+    for x in list(rng.integers(0, 10**8, 2000)) + [0, 99999999, 10**7, 12345678]:
+        assert parse_probe.probe_eight_digits(b"%08d" % x) == x
+    for txt in (b"1234567 ", b"/2345678", b"1234:678", b"12345678"[:7] + b"\xb9"):
+        assert parse_probe.probe_eight_digits(txt) == 0xFFFFFFFF, txt
+
+
+def test_loader_keeps_its_results_across_reuse_of_the_thread_scratch(product, oracle, tmp_path_factory, tmp_path):
+    """The loaders keep their scratch memory and the last freed triangle block per host thread: loading large, small, failing
+    and large files again in one thread must give every time what a fresh load gives (== the oracle's sequential reader)."""
+    from gpview_b200 import meshgen
+    V, F = meshgen.uv_sphere(60, 40)
+    meshgen.write_obj(str(tmp_path / "s.obj"), V, F)
+    meshgen.write_off(str(tmp_path / "s.off"), V, F)
+    (tmp_path / "tiny.off").write_text("OFF\n3 1 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n")
+    (tmp_path / "bad.off").write_text("OFF\n3 2 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n3 0 1\n")
+    (tmp_path / "lying.off").write_text("OFF\n3 2000000000 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n")
+    (tmp_path / "lying2.off").write_text("OFF\n2000000000 1 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n")
+    seq = ["s.obj", "tiny.off", "s.off", "bad.off", "s.obj", "lying.off", "lying2.off", "tiny.off", "s.off", "cessna", "tiny.off", "s.obj"]
+    held = []
+    for i, name in enumerate(seq):
+        path = mesh_path("cessna", tmp_path_factory.getbasetemp()) if name == "cessna" else str(tmp_path / name)
+        if name in ("bad.off", "lying.off", "lying2.off"):
+            with pytest.raises(product.GpvError):
+                product.load_mesh(path)
+            continue
+        pm, om = product.load_mesh(path), oracle.OracleMesh(path)
+        assert pm.ntri == om.ntri and _same_mesh(pm, om), (i, name)
+        held.append((pm, om))  # meshes stay alive (and are freed in a different order): blocks must not be shared
+        if i % 3 == 2:
+            held.pop(0)
+    for pm, om in held:
+        assert np.array_equal(pm.tris, om.tris)
