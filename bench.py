@@ -418,6 +418,10 @@ def main():
                                "(issue-slot utilisation of the same command under ncu --set full)" % res.stats["l2_box_tests"],
                 "ncu": ncu_note(n_sat) if world == 1 else None,
                 "kernel_ms": k_l2_ms, "share_of_step": k_l2_ms / ms_per_step}
+        if world == 1 and n_sat.get("issue_active_pct") is not None:
+            # the executed-work view of the same kernel: share of issue slots in use (ncu capture of this command), the ceiling
+            # that actually binds a kernel whose FP32 work is comparisons, selects and non-FMA arithmetic
+            roof["frac_issue_slots"] = n_sat["issue_active_pct"] / 100.0
         ray_flops = 51.0 * res.stats.get("l2_ray_tests", 0)
         roof_rays = {"kernel": "k_l2_rays (Level-2 parity rays per sub-voxel column)", "bound": "fp32", "kernel_ms": k_rays_ms, "share_of_step": k_rays_ms / ms_per_step,
                      "achieved": ray_flops / (k_rays_ms * 1e-3) / 1e12 if k_rays_ms > 0 and ray_flops else None, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
@@ -425,6 +429,8 @@ def main():
                      "traffic": n_rays.get("dram_bytes") if world == 1 else None, "ncu": ncu_note(n_rays) if world == 1 else None}
         if roof_rays["achieved"]:
             roof_rays["frac"] = roof_rays["achieved"] / roof_rays["peak"]
+        if world == 1 and n_rays.get("issue_active_pct") is not None:
+            roof_rays["frac_issue_slots"] = n_rays["issue_active_pct"] / 100.0
         out_bytes = res.nb * res.n23
         roof_hbm = {"kernel": sat_name, "bound": "hbm", "achieved": out_bytes / (k_l2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": out_bytes / (k_l2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": n_sat.get("dram_bytes") if world == 1 else None,

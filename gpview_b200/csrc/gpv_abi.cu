@@ -134,14 +134,22 @@ extern "C" int gpv_create(int device, gpv_ctx** out)
 	gpv_ctx* c = new gpv_ctx();
 	c->device = device;
 	c->smCount = prop.multiProcessorCount;
-	GPV_CUDA(cudaHostAlloc((void**)&c->hTotals, sizeof(Totals), cudaHostAllocDefault));
 	static_assert(sizeof(Totals) <= 128, "gpv_ctx::totals: Totals in the first 128 bytes, the sort's long-list counters behind");
-	if (c->totals.ensure(256)) { delete c; return 1; }
-	GPV_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
-	GPV_CUDA(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
-	GPV_CUDA(cudaStreamCreateWithFlags(&c->sideStream, cudaStreamNonBlocking));
-	for (int k = 0; k < 2; k++) { GPV_CUDA(cudaEventCreateWithFlags(&c->evFork[k], cudaEventDisableTiming)); GPV_CUDA(cudaEventCreateWithFlags(&c->evJoin[k], cudaEventDisableTiming)); }
-	for (cudaEvent_t& e : c->evChunk) GPV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	auto init = [c]() -> int {
+		GPV_CUDA(cudaHostAlloc((void**)&c->hTotals, sizeof(Totals), cudaHostAllocDefault));
+		if (c->totals.ensure(256)) return 1;
+		GPV_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+		GPV_CUDA(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+		GPV_CUDA(cudaStreamCreateWithFlags(&c->sideStream, cudaStreamNonBlocking));
+		for (int k = 0; k < 2; k++) { GPV_CUDA(cudaEventCreateWithFlags(&c->evFork[k], cudaEventDisableTiming)); GPV_CUDA(cudaEventCreateWithFlags(&c->evJoin[k], cudaEventDisableTiming)); }
+		for (cudaEvent_t& e : c->evChunk) GPV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		return 0;
+	};
+	if (init()) { // a half-built context owns nothing the caller could release: gpv_destroy() frees whatever was created
+		const std::string why = g_err;
+		gpv_destroy(c);
+		return fail(why);
+	}
 	*out = c;
 	return 0;
 }
@@ -222,6 +230,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
                          const gpv_params* prm, void* stream, gpv_result* out, const gpv_host_streams* sink)
 {
 	if (!c) return fail("gpv_voxelize_device: null ctx");
+	if (!d_tris || !bmin || !bmax || !prm || !out) return fail("gpv_voxelize_device: null argument");
 	if (n_tri <= 0 || n_tri > 0x7fffffff) return fail("gpv_voxelize_device: triangle count out of range");
 	memset(out, 0, sizeof *out);
 	GPV_CUDA(cudaSetDevice(c->device));

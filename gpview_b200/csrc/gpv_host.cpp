@@ -61,22 +61,7 @@ bool read_file(const char* path, Scratch<char>& buf, size_t& size)
 	return ok;
 }
 
-// split() of src/Utilities.cpp:989-1004 for a one-character delimiter: empty fields are kept, a trailing delimiter adds an
-// empty field, an empty string has no fields.
 struct Field { const char* p; size_t n; };
-void split_fields(const char* s, size_t len, char delim, std::vector<Field>& out)
-{
-	out.clear();
-	size_t i = 0;
-	while (i < len) {
-		size_t j = i;
-		while (j < len && s[j] != delim) j++;
-		out.push_back({ s + i, j - i });
-		if (j == len) break;
-		i = j + 1;
-		if (i == len) out.push_back({ s + i, 0 });
-	}
-}
 
 // std::stof / std::stoi on a field: same values as strtof / strtol, by the short exact path of gpv_parse.h when there is one
 inline bool field_to_float(const Field& f, float& v) { return gpv::parse_float(f.p, f.n, v); }
@@ -230,40 +215,47 @@ struct TriGuard { // error returns between alloc_tris() and export_mesh()
 
 void parse_obj_chunk(const char* data, ObjChunk& c)
 {
-	std::vector<Field> w;
 	size_t pos = c.begin;
 	while (pos < c.end) {
-		size_t e = pos, nSpace = 0, nTab = 0;
-		for (; data[e] != '\n'; e++) { // the chunk ends with '\n'
-			nSpace += data[e] == ' ';
-			nTab += data[e] == '\t';
-		}
 		const char* line = data + pos;
-		const size_t len = e - pos;
-		pos = e + 1;
+		const char* le = (const char*)memchr(line, '\n', c.end - pos); // the chunk ends with '\n'
+		const size_t len = (size_t)(le - line);
+		pos += len + 1;
 		const size_t lineNo = c.nLines++;
-		if (len == 0) continue;
-		// split on " " and on "\t", keep the split with more fields, the tab split on a tie (:419-423): a non-empty line has
-		// one field more than it has delimiters, so the counts decide and the line is split once
-		split_fields(line, len, nSpace > nTab ? ' ' : '\t', w);
-		if (w[0].n == 1 && w[0].p[0] == 'v') {
-			float pt[3] = { 0, 0, 0 };
-			unsigned char got = 0;
-			for (size_t i = 1; i < w.size() && i <= 3; i++) {
-				if (!field_to_float(w[i], pt[i - 1])) { c.errLine = lineNo; c.errKind = 1; return; } // std::stof would throw: the load ends here
-				got++;
+		if (len == 0 || (line[0] != 'v' && line[0] != 'f')) continue; // only lines whose first field is exactly "v" or "f" matter
+		// The reference splits the line on " " and on "\t" and keeps the split with more fields, the tab split on a tie (:419-423).
+		// split() (src/Utilities.cpp:989-1004) keeps empty fields and adds one behind a trailing delimiter, so a non-empty line has
+		// one field more than it has delimiters: the delimiter counts decide, and the fields are walked where they stand.
+		char delim = ' ';
+		if (memchr(line, '\t', len)) {
+			size_t nSpace = 0, nTab = 0;
+			for (const char* q = line; q < le; q++) { nSpace += *q == ' '; nTab += *q == '\t'; }
+			delim = nSpace > nTab ? ' ' : '\t';
+		}
+		if (len > 1 && line[1] != delim) continue; // "vn", "vt", "vp", ... or a first field longer than one character
+		const bool isV = line[0] == 'v';
+		float pt[3] = { 0, 0, 0 };
+		long idx[3] = { 0, 0, 0 };
+		unsigned char got = 0;
+		const char* cur = line + 1; // at the delimiter that ends the previous field, or at the end of the line
+		for (int i = 0; i < 3 && cur < le; i++) {
+			const char* fs = cur + 1;
+			const char* fe = fs;
+			while (fe < le && *fe != delim) fe++;
+			if (isV) {
+				if (!gpv::parse_float(fs, (size_t)(fe - fs), pt[i])) { c.errLine = lineNo; c.errKind = 1; return; } // std::stof would throw: the load ends here
+			} else { // "a", "a/b", "a/b/c", "a//c": the vertex index is the first '/' field (:480-505)
+				const char* sl = fs;
+				while (sl < fe && *sl != '/') sl++;
+				if (!gpv::parse_long(fs, (size_t)((sl > fs ? sl : fe) - fs), idx[i])) { c.errLine = lineNo; c.errKind = 2; return; }
 			}
+			got++;
+			cur = fe;
+		}
+		if (isV) {
 			c.v.insert(c.v.end(), pt, pt + 3);
 			c.vParsed.push_back(got);
-		} else if (w[0].n == 1 && w[0].p[0] == 'f') {
-			long idx[3] = { 0, 0, 0 };
-			for (size_t i = 1; i < w.size() && i <= 3; i++) { // "a", "a/b", "a/b/c", "a//c": the vertex index is the first '/' field (:480-505)
-				Field f = w[i];
-				size_t k = 0;
-				while (k < f.n && f.p[k] != '/') k++;
-				if (k > 0) f.n = k;
-				if (!field_to_long(f, idx[i - 1])) { c.errLine = lineNo; c.errKind = 2; return; }
-			}
+		} else {
 			c.f.insert(c.f.end(), idx, idx + 3);
 			c.fLine.push_back(lineNo);
 			c.fVertsBefore.push_back(c.vParsed.size());

@@ -305,3 +305,51 @@ def test_loader_keeps_its_results_across_reuse_of_the_thread_scratch(product, or
             held.pop(0)
     for pm, om in held:
         assert np.array_equal(pm.tris, om.tris)
+
+
+def test_obj_line_fuzz_vs_oracle(product, oracle, tmp_path):
+    """Random OBJ text -- spaces, tabs, both, doubled and trailing delimiters, CR, slashed and signed indices, short and long `v`
+    lines, other keywords starting with v / f -- through the product's in-place field walk and the oracle's literal
+    split-twice reader: same mesh, or both refuse.  (The reference itself cannot referee here: it assert()s on `f` / `vn` / `vt`
+    lines with an unexpected field count and writes out of bounds on long `v` lines; test_obj_quirks covers it on the forms it survives.)"""
+    rng = np.random.default_rng(20240607)
+    nums = ["0", "1", "-1.5", "2.25e0", "+3", ".5", "7.", "1e-3", "0x10", "4\r", "1.5abc", "", "x", "-", "1e", "3/4"]
+    idxs = ["1", "2", "3", "4", "1/2", "2//3", "3/1/1", "04", "+2", "4\r", "", "/1", "0", "9", "-1", "2.7", "1e0", "x"]
+    heads = ["v", "v", "v", "f", "f", "vn", "vt", "#", "g", "fo", "", "vv", "V", "F"]
+    agree_ok = agree_fail = 0
+    for it in range(400):
+        lines = ["v 0 0 0", "v 1 0 0", "v 0 1 0", "v 0 0 1"]
+        for _ in range(int(rng.integers(1, 12))):
+            h = heads[rng.integers(len(heads))]
+            pool = idxs if h == "f" else nums
+            risky = rng.random() < 0.35                       # most lines well-formed, so that many files load
+            k = int(rng.integers(0, 6)) if risky else 3
+            toks = [pool[rng.integers(len(pool) if risky else 4)] for _ in range(k)]
+            style = rng.integers(5)
+            d = [" ", "\t", " ", "\t", " "][style]
+            line = d.join([h] + toks)
+            if style == 2 and risky:                          # mixed: some delimiters swapped for the other kind
+                line = "".join(("\t" if (c == " " and rng.random() < 0.4) else c) for c in line)
+            if style == 3 and risky:
+                line = "".join((" " if (c == "\t" and rng.random() < 0.5) else c) for c in line)
+            if risky and rng.random() < 0.2:
+                line += d
+            lines.append(line)
+        p = tmp_path / ("fuzz%d.obj" % it)
+        p.write_bytes(("\n".join(lines) + ("\n" if rng.random() < 0.9 else "")).encode())
+        try:
+            om = oracle.OracleMesh(str(p))
+        except RuntimeError:
+            om = None
+        try:
+            pm = product.load_mesh(str(p))
+        except product.GpvError:
+            pm = None
+        assert (om is None) == (pm is None), (it, lines)
+        if om is not None:
+            assert pm.ntri == om.ntri and _same_mesh(pm, om), (it, lines)
+            agree_ok += 1
+        else:
+            agree_fail += 1
+    assert agree_ok > 40 and agree_fail > 40, (agree_ok, agree_fail)
+    print("obj fuzz: %d files load identically, %d refused by both" % (agree_ok, agree_fail))
