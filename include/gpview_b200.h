@@ -138,7 +138,8 @@ int gpv_load_obj(const char* path, gpv_mesh* out);
 int gpv_load_off(const char* path, gpv_mesh* out);
 int gpv_load_mesh(const char* path, gpv_mesh* out);
 int gpv_mesh_from_triangles(const float* tris, int64_t n_tri, gpv_mesh* out); /* bbox over the given vertices + padding */
-void gpv_free_mesh(gpv_mesh* m);
+void gpv_free_mesh(gpv_mesh* m); /* the only way to release gpv_mesh.tris (the block has a header in front of the floats and may be
+                                  * parked for the calling thread's next load) */
 
 /* grid sizing of Object::PerformVoxelization (src/Object.cpp:3094-3134) */
 int gpv_make_grid(const float bbox_min[3], const float bbox_max[3], float max_model_size, int voxel_count, int voxel_count2, gpv_grid* out);
