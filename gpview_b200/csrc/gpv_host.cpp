@@ -86,23 +86,28 @@ void finish_bbox(const float mn[3], const float mx[3], gpv_mesh* m)
 // The triangle block a gpv_mesh owns: 16 bytes of header (the block's capacity) in front of the floats.  free_tris() parks the
 // thread's last block (up to 16 MB) for the thread's next load instead of handing it back to malloc: same page-fault
 // argument as Scratch.  Only gpv_free_mesh() releases a mesh's triangles.
-struct TriBlockCache {
-	char* base = nullptr;
-	~TriBlockCache() { free(base); }
+thread_local char* g_triParked = nullptr;   // plain thread-locals (no destructor): still valid when a static object releases a
+thread_local bool g_triParkingClosed = false; // mesh after the thread's destructors have run -- then nothing is parked any more
+struct TriParkingGuard {
+	~TriParkingGuard()
+	{
+		free(g_triParked);
+		g_triParked = nullptr;
+		g_triParkingClosed = true;
+	}
 };
-thread_local TriBlockCache g_triCache;
+thread_local TriParkingGuard g_triGuard;
 const size_t kTriHeader = 16;
 
 float* alloc_tris(size_t nTri)
 {
 	const size_t need = kTriHeader + nTri * 9 * sizeof(float) + 16;
-	TriBlockCache& c = g_triCache;
-	if (c.base) {
+	if (g_triParked) {
 		size_t cap;
-		memcpy(&cap, c.base, sizeof cap);
+		memcpy(&cap, g_triParked, sizeof cap);
 		if (cap >= need && cap <= 4 * need) {
-			char* b = c.base;
-			c.base = nullptr;
+			char* b = g_triParked;
+			g_triParked = nullptr;
 			return (float*)(b + kTriHeader);
 		}
 	}
@@ -117,8 +122,10 @@ void free_tris(float* tris)
 	char* b = (char*)tris - kTriHeader;
 	size_t cap;
 	memcpy(&cap, b, sizeof cap);
-	TriBlockCache& c = g_triCache;
-	if (cap <= ((size_t)16 << 20)) std::swap(b, c.base); // keep the newer block, release the one that was parked
+	if (cap <= ((size_t)16 << 20) && !g_triParkingClosed) {
+		(void)&g_triGuard;          // instantiates the guard: its destructor gives the parked block back when the thread ends
+		std::swap(b, g_triParked);  // keep the newer block, release the one that was parked
+	}
 	free(b);
 }
 
