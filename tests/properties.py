@@ -68,6 +68,23 @@ def rotated(tris, angles=(0.37, 1.13, 2.41), chunk=1 << 20):
     return out.reshape(-1, 9)
 
 
+def epsilon_blind_fraction(tris, chunk=1 << 20):
+    """Share of the mesh's projected (x, y) area that the reference's parity rays cannot see: Moller-Trumbore rejects a triangle
+    when |det| < 1e-6, an ABSOLUTE threshold on twice its projected area (cu:117, src/TriRayIntersection.cpp:93; App. A.5).
+    On a unit-sized body that is harmless at 1 M triangles (pole slivers only) but not at 10 M: a third to a half of the CAD
+    body's triangles fall below it and the reference's own solid fill loses 0.5 % (generic position) to 11 % (axis-aligned)
+    of the volume.  The product reproduces that bit for bit; volume arguments only apply where this fraction is small."""
+    t = np.asarray(tris, np.float32).reshape(-1, 3, 3)
+    blind = total = 0.0
+    for a in range(0, len(t), chunk):
+        c = t[a:a + chunk]
+        e1, e2 = c[:, 1] - c[:, 0], c[:, 2] - c[:, 0]
+        det = np.abs(e1[:, 0] * (-e2[:, 1]) + e1[:, 1] * e2[:, 0]).astype(np.float64)
+        total += float(det.sum())
+        blind += float(det[det < 1e-6].sum())
+    return blind / total if total > 0 else 0.0
+
+
 def check_volume_bracket(tris, grid_size, grid_size2, n23, counts, rel_tol=2e-3):
     """For a closed 2-manifold the solid's volume V is bracketed by the occupancy at both levels:
         inside cells lie wholly inside (centre inside by parity, no triangle touches the box)  ->  inside * v <= V

@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from properties import check_stream_structure, check_volume_bracket, rotated
+from properties import check_stream_structure, check_volume_bracket, epsilon_blind_fraction, rotated
 from util import GOLD
 
 pytestmark = pytest.mark.gpu
@@ -61,13 +61,17 @@ def test_fullsize_config_matches_oracle_hashes_and_properties(product, ctx, case
     del s
     # the result is a function of the triangle SET: any order of the list gives the same bytes
     perm = np.random.default_rng(20240607).permutation(len(tris))
-    res2 = ctx.voxelize(product.mesh_from_triangles(tris[perm]), prm)
+    res2 = ctx.voxelize(product.mesh_from_triangles(tris[perm]), product.Params(gold["l1"], gold["l2"], product.GPV_KEEP_LISTS))  # and with the list sorts
     assert res2.counts == gold["counts"]
     assert _streams(res2)[1] == gold["sha256"], case + " (permuted triangle list)"
-    # volume bracket at both levels, on the body in generic position (counts only: no stream leaves the device)
+    # volume bracket at both levels, on the body in generic position (counts only: no stream leaves the device) -- where the
+    # reference's absolute |det| < 1e-6 ray rejection leaves the fill meaningful: not on the 10 M-triangle body (properties.py)
     rt = rotated(tris)
-    res3 = ctx.voxelize(product.mesh_from_triangles(rt), prm)
-    check_volume_bracket(rt, res3.grid_size, res3.grid_size2, res3.n23, res3.counts)
+    if epsilon_blind_fraction(rt) < 2e-2:  # sphere 3e-3, torus 1e-3, CAD body 1e-1
+        res3 = ctx.voxelize(product.mesh_from_triangles(rt), prm)
+        check_volume_bracket(rt, res3.grid_size, res3.grid_size2, res3.n23, res3.counts)
+    else:
+        assert case == "cad_1024_2", "only the 10 M-triangle body is expected to sit below the reference's ray epsilon"
 
 
 @pytest.mark.parametrize("i", range(4))

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from properties import check_stream_structure, check_volume_bracket, mesh_volume, rotated
+from properties import check_stream_structure, check_volume_bracket, epsilon_blind_fraction, mesh_volume, rotated
 from util import GOLD, mesh_path
 
 
@@ -59,3 +59,12 @@ def test_fullsize_hash_file_is_what_the_oracle_says(oracle, tmp_path):
         if now["triangles_sha256"] != full[case]["triangles_sha256"]:
             pytest.skip("numpy builds a different mesh on this host (last-bit sin/cos): the GPU test falls back to the live oracle")
         assert now == full[case]
+
+
+def test_epsilon_blind_fraction():
+    """Two triangles of projected area 1 and 4e-7 (|det| = 2 and 8e-7): the rays cannot see the second."""
+    big = [0, 0, 0, 1, 0, 0, 0, 2, 1]
+    small = [0, 0, 0, 1e-3, 0, 5, 0, 8e-4, 0]
+    assert epsilon_blind_fraction(np.array([big], np.float32)) == 0.0
+    assert epsilon_blind_fraction(np.array([small], np.float32)) == 1.0
+    assert epsilon_blind_fraction(np.array([big, small], np.float32)) == pytest.approx(8e-7 / (2 + 8e-7), rel=1e-3)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Config 5 (BASELINE.json): batched dataset generation -- N drilled-block .off meshes (~5k triangles) at Level-1 64 + Level-2 4^3.
 
-  python tools/run_batch.py [--models 2000] [--distinct 100] [--threads 16] [--gpus 1] [--save] [--check 5]
+  python tools/run_batch.py [--models 2000] [--distinct 100] [--threads 16] [--gpus 1] [--save] [--check 5] [--parse-only]
 
 Writes `distinct` seeded meshes (gpview_b200.meshgen.drilled_block, seed = SEED_BASE + i) once, then runs gpv_voxelize_batch over
 `models` paths cycling through them (every path is parsed again: parsing is part of the pipeline).  --check K compares the
@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--save", action="store_true")
     ap.add_argument("--normals", action="store_true")
     ap.add_argument("--check", type=int, default=0)
+    ap.add_argument("--parse-only", action="store_true", help="host side alone (no GPU needed): models/s the loaders can feed on --threads host threads")
     a = ap.parse_args()
     import gpview_b200 as gpv
     from gpview_b200 import binding as B, meshgen as M
@@ -42,6 +43,29 @@ def main():
         files.append(p)
     gen_s = time.time() - t0
     paths = [files[i % a.distinct] for i in range(a.models)]
+    if a.parse_only:
+        import threading
+        nxt, lock, tris = [0], threading.Lock(), [0]
+
+        def worker():
+            n = 0
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= len(paths):
+                    break
+                n += gpv.load_mesh(paths[i]).ntri   # ctypes releases the GIL inside gpv_load_mesh
+            with lock:
+                tris[0] += n
+        t0 = time.time()
+        ts = [threading.Thread(target=worker) for _ in range(a.threads)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        dt = time.time() - t0
+        print(json.dumps({"config": "parse only: drilled-block .off meshes (~5k triangles)", "models": a.models, "threads": a.threads, "models_per_s": a.models / dt,
+                          "ms_per_model_per_thread": 1e3 * dt * a.threads / a.models, "triangles": tris[0], "mesh_generation_s": gen_s}))
+        return
     out = os.path.join(d, "out") if (a.save or a.check) else None
     if out:
         os.makedirs(out)
