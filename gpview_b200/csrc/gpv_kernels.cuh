@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kWorkThreads) k_bin(const float4* __restrict__
                                                       const float* __restrict__ cx, const float* __restrict__ cy, const float* __restrict__ cz, BinOut o)
 {
 	__shared__ __align__(128) WorkSmem sm;
-	if (o.totals->binWork > o.bitsCap) return;
+	if (o.totals->binWork > o.bitsCap || o.totals->binWork > 0xfffffff0ull) return; // bitmap too small (the host grows it and starts over) / 32-bit work offsets would wrap (the host reports it)
 	unsigned long long hits = 0;
 	for_each_work_item<false>(sm, binOff, nTri, &o.totals->binWork, tri48, nullptr, [&](int t, const float4* rec, const int4*, unsigned local, unsigned base) {
 		const float4 a = rec[0], b = rec[1], c = rec[2];
@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kWorkThreads) k_cross(const float4* __restrict
                                                         int* crossTri, Totals* totals)
 {
 	__shared__ __align__(128) WorkSmem sm;
+	if (totals->crossWork > 0xfffffff0ull) return; // work offsets are 32-bit: the host reports the error after the read-back (gpv_abi.cu), nothing may run on wrapped offsets
 	unsigned long long found = 0;
 	for_each_work_item<true>(sm, workOff, nTri, &totals->crossWork, ray48, crossFp, [&](int t, const float4* rec, const int4* fp, unsigned local, unsigned) {
 		const float4 a = rec[0], b = rec[1], c = rec[2];
