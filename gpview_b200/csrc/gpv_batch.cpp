@@ -73,7 +73,7 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
 					ok = true;
 					double c = now();
 					gpu += c - b;
-					if (out_dir && gpv_save(&mesh, &res, &h, objID, out_dir)) ok = false;
+					if (out_dir && gpv_save_streams(&mesh, &res, &h, objID, out_dir, (params->flags & GPV_SAVE_COMPUTED_ONLY) != 0)) ok = false;
 					save += now() - c;
 				} else {
 					// too small a Level-2 buffer: the call reports it after the Level-1 pass; size it from a Level-1-only run

@@ -537,6 +537,12 @@ extern "C" int gpv_make_grid(const float bmin[3], const float bmax[3], float max
 // ostream << float prints like "%g" (precision 6); file names "Obj" + to_string(objID) + suffix (:2958-2974)
 extern "C" int gpv_save(const gpv_mesh* mesh, const gpv_result* res, const gpv_host_streams* h, int obj_id, const char* dir)
 {
+	return gpv_save_streams(mesh, res, h, obj_id, dir, 0);
+}
+
+extern "C" int gpv_save_streams(const gpv_mesh* mesh, const gpv_result* res, const gpv_host_streams* h, int obj_id, const char* dir, int omit_absent)
+{
+	if (!mesh || !res || !h || !dir) return gpv::fail("gpv_save: null argument");
 	const gpv_grid& g = res->grid;
 	const bool l2 = h->level2_inout != nullptr;
 	std::string prefix = std::string(dir) + "/Obj" + std::to_string(obj_id);
@@ -557,6 +563,7 @@ extern "C" int gpv_save(const gpv_mesh* mesh, const gpv_result* res, const gpv_h
 	if (fclose(f) != 0 || cfgBad) return gpv::fail("write error on " + prefix + "VoxelConfig.txt");
 	std::string failed; // first stream that could not be opened or written in full (a full disk must not pass for a saved model)
 	auto dump = [&](const char* name, const void* p, size_t bytes, uint8_t fill) -> bool {
+		if (!p && omit_absent) return true; // not computed, not written
 		FILE* o = fopen((prefix + name).c_str(), "wb");
 		if (!o) { failed = "Unable to open output file for writing: " + prefix + name; return false; }
 		bool ok = true;

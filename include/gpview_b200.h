@@ -73,6 +73,8 @@ typedef struct {
                                   without it (and without GPV_NORMALS) the lists stay in the order the binning left them: occupancy does not depend on it */
 #define GPV_PROFILE      8     /* record a CUDA event pair around every kernel of the pipeline -> gpv_result.phase_ms */
 #define GPV_GATHER      16     /* multi-GPU: write this slab's streams straight into the gathering rank's buffers (gpv_gather_*) */
+#define GPV_SAVE_COMPUTED_ONLY 32 /* gpv_voxelize_batch: write only the streams that were computed -- no 127-filled normal files when
+                                  GPV_NORMALS is off (74 % of a 64 + 4^3 model's bytes, and file writing is what bounds a dataset run) */
 
 typedef struct {
 	int voxel_count;           /* GLParameters::voxelCount  (Level-1 cells along the longest axis; reference default 8) */
@@ -190,6 +192,9 @@ int gpv_gather_result(gpv_ctx* ctx, uint8_t** d_level1_inout, int32_t** d_prefix
 
 /* Object::SaveVoxelization (src/Object.cpp:2934-3075): the six ObjN*.{txt,raw} files into `dir` from host streams */
 int gpv_save(const gpv_mesh* mesh, const gpv_result* res, const gpv_host_streams* host, int obj_id, const char* dir);
+/* the same; omit_absent != 0: a stream whose host pointer is NULL gets no file (gpv_save writes its neutral value instead: 127
+ * for normals, 0 otherwise, so that all six files of the reference's contract always exist).  gpv_load_voxels accepts both. */
+int gpv_save_streams(const gpv_mesh* mesh, const gpv_result* res, const gpv_host_streams* host, int obj_id, const char* dir, int omit_absent);
 
 /* Reader of the six-file set written by gpv_save / Object::SaveVoxelization: sizes come from ObjNVoxelConfig.txt (the reference can
  * only read back one hard-coded 48x64x64 grid, Object::ReadRAWObject src/Object.cpp:319-392).  Arrays are malloc'ed; the two

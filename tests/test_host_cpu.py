@@ -180,6 +180,21 @@ def test_save_writes_the_reference_file_contract(product, oracle, tmp_path_facto
                      "Obj-1Level2Normal.raw", "Obj-1VoxelConfig.txt"]
     for n in names:
         assert filecmp.cmp(d1 / n, d2 / n, shallow=False), n
+    # streams that were not computed: gpv_save writes their neutral value (the reference's contract is six files), gpv_save_streams
+    # with omit_absent leaves them out (dataset runs: the filler is 3/4 of the bytes); gpv_load_voxels reads either set
+    hs2 = B.CHostStreams(l1.ctypes.data, r.prefix.ctypes.data, None, l2.ctypes.data, None, None, l2.nbytes, 0)
+    d3, d4 = tmp_path / "filled", tmp_path / "lean"
+    d3.mkdir(); d4.mkdir()
+    B.save(pm, R, hs2, 3, str(d3))
+    B.save(pm, R, hs2, 3, str(d4), omit_absent=True)
+    assert sorted(os.listdir(d3)) == [n.replace("Obj-1", "Obj3") for n in names]
+    assert sorted(os.listdir(d4)) == [n.replace("Obj-1", "Obj3") for n in names if "Normal" not in n]
+    assert set(open(d3 / "Obj3Level2Normal.raw", "rb").read()) == {127} and os.path.getsize(d3 / "Obj3Level2Normal.raw") == l2.nbytes * 3
+    for n in os.listdir(d4):
+        assert filecmp.cmp(d3 / n, d4 / n, shallow=False), n
+    va, vb = B.load_voxels(str(d3), 3), B.load_voxels(str(d4), 3)
+    assert vb["level1_normal"] is None and vb["level2_normal"] is None and va["level2_normal"] is not None
+    assert np.array_equal(va["level2_inout"], vb["level2_inout"]) and np.array_equal(vb["level2_inout"], l2) and np.array_equal(vb["prefix_sum"], r.prefix)
     assert keep
 
 

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--l2", type=int, default=4)
     ap.add_argument("--save", action="store_true")
     ap.add_argument("--normals", action="store_true")
+    ap.add_argument("--six-files", action="store_true", help="without --normals: still write the two normal files (127-filled), as gpv_save does")
     ap.add_argument("--check", type=int, default=0)
     ap.add_argument("--parse-only", action="store_true", help="host side alone (no GPU needed): models/s the loaders can feed on --threads host threads")
     a = ap.parse_args()
@@ -69,7 +70,7 @@ def main():
     out = os.path.join(d, "out") if (a.save or a.check) else None
     if out:
         os.makedirs(out)
-    flags = gpv.GPV_NORMALS if a.normals else 0
+    flags = gpv.GPV_NORMALS if a.normals else (0 if a.six_files else gpv.GPV_SAVE_COMPUTED_ONLY)
     B.voxelize_batch(paths[:min(len(paths), 4 * a.threads)], gpv.Params(a.l1, a.l2, flags), list(range(a.gpus)), a.threads, None)  # warm-up: contexts, pools
     st = B.voxelize_batch(paths, gpv.Params(a.l1, a.l2, flags), list(range(a.gpus)), a.threads, out, 0, False)
     line = {"config": "drilled-block .off meshes (~5k triangles), Level1 %d + Level2 %d^3" % (a.l1, a.l2), "models": a.models, "distinct_meshes": a.distinct,
