@@ -65,7 +65,7 @@ class CBatchStats(C.Structure):
 
 
 # every symbol include/gpview_b200.h declares (tests/test_abi_symbols.py checks the header against this and the .so)
-NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_stream", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh",
+NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_stream", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh", "gpv_load_mesh_ex",
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
                   "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_free_voxels", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
@@ -160,9 +160,15 @@ class Mesh:
             pass
 
 
-def load_mesh(path):
+def load_mesh(path, tolerant=False):
+    """gpv_load_mesh (the reference's reader semantics), or gpv_load_mesh_ex(GPV_LOAD_TOLERANT): polygons, free-form blanks, ..."""
     m = CMesh()
-    _check(lib().gpv_load_mesh(os.fsencode(path), C.byref(m)))
+    if tolerant:
+        L = lib()
+        L.gpv_load_mesh_ex.argtypes = [C.c_char_p, C.c_uint, C.POINTER(CMesh)]
+        _check(L.gpv_load_mesh_ex(os.fsencode(path), 1, C.byref(m)))
+    else:
+        _check(lib().gpv_load_mesh(os.fsencode(path), C.byref(m)))
     return Mesh(m)
 
 

@@ -53,7 +53,7 @@ bool read_file(const char* path, Scratch<char>& buf, size_t& size)
 	long sz = ftell(f);
 	fseek(f, 0, SEEK_SET);
 	bool ok = sz <= 0;
-	if (sz > 0 && buf.get((size_t)sz)) {
+	if (sz > 0 && buf.get((size_t)sz + 1)) { // one byte of slack: the tolerant OBJ reader terminates an unterminated last line
 		size = (size_t)sz;
 		ok = fread(buf.p, 1, size, f) == size;
 	}
@@ -270,6 +270,60 @@ void parse_obj_chunk(const char* data, ObjChunk& c)
 	}
 }
 
+// Tolerant twin (GPV_LOAD_TOLERANT, an extension -- SURVEY.md 8f3): what OBJ files in the wild need and the reference's reader
+// refuses or misreads.  Fields are runs of non-blank characters (any mix of spaces, tabs, CR); `v` takes its first three numbers
+// (a fourth, w or a colour, is ignored; fewer is an error, not a stale coordinate); `f` takes any number >= 3 of vertices
+// "a", "a/b", "a/b/c", "a//c" and is fan-triangulated (a0, a_k, a_k+1); negative indices count back from the vertices defined
+// so far.  Every triangle becomes one entry of the chunk's face list, so the stitching below is shared with the strict reader.
+void parse_obj_chunk_tolerant(const char* data, ObjChunk& c)
+{
+	auto blank = [](char ch) { return ch == ' ' || ch == '\t' || ch == '\r'; };
+	std::vector<long> poly;
+	size_t pos = c.begin;
+	while (pos < c.end) {
+		const char* p = data + pos;
+		const char* le = (const char*)memchr(p, '\n', c.end - pos); // the chunk ends with '\n'
+		pos += (size_t)(le - p) + 1;
+		const size_t lineNo = c.nLines++;
+		while (p < le && blank(*p)) p++;
+		if (le - p < 2 || (*p != 'v' && *p != 'f') || !blank(p[1])) continue;
+		const bool isV = *p == 'v';
+		p++;
+		float pt[3] = { 0, 0, 0 };
+		int got = 0;
+		poly.clear();
+		bool bad = false;
+		for (;;) {
+			while (p < le && blank(*p)) p++;
+			if (p >= le || *p == '#') break;
+			const char* fs = p;
+			while (p < le && !blank(*p)) p++;
+			if (isV) {
+				if (got < 3 && !gpv::parse_float(fs, (size_t)(p - fs), pt[got])) { bad = true; break; }
+				got++;
+			} else {
+				const char* sl = fs;
+				while (sl < p && *sl != '/') sl++;
+				long idx = 0;
+				if (!gpv::parse_long(fs, (size_t)(sl - fs), idx) || idx == 0) { bad = true; break; }
+				poly.push_back(idx);
+			}
+		}
+		if (bad || (isV && got < 3) || (!isV && poly.size() < 3)) { c.errLine = lineNo; c.errKind = isV ? 1 : 2; return; }
+		if (isV) {
+			c.v.insert(c.v.end(), pt, pt + 3);
+			c.vParsed.push_back(3);
+		} else {
+			for (size_t k = 1; k + 1 < poly.size(); k++) {
+				const long tri[3] = { poly[0], poly[k], poly[k + 1] };
+				c.f.insert(c.f.end(), tri, tri + 3);
+				c.fLine.push_back(lineNo);
+				c.fVertsBefore.push_back(c.vParsed.size());
+			}
+		}
+	}
+}
+
 // [0, usable) cut into n pieces at line starts
 std::vector<size_t> line_cuts(const char* buf, size_t usable, int n)
 {
@@ -285,7 +339,7 @@ std::vector<size_t> line_cuts(const char* buf, size_t usable, int n)
 
 } // namespace
 
-extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
+static int load_obj_impl(const char* path, gpv_mesh* out, bool tolerant)
 {
 	memset(out, 0, sizeof *out);
 	LoadScratch& S = g_loadScratch;
@@ -294,13 +348,14 @@ extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
 	if (!read_file(path, S.file, fileSize)) return gpv::fail(std::string("Unable to open file \"") + path + "\""); // the reference abort()s (:409-413)
 	const char* buf = S.file.p;
 	size_t usable = fileSize; // getline at EOF: `if (!in.good()) break;` drops an unterminated last line (:425)
+	if (tolerant && fileSize > 0 && buf[fileSize - 1] != '\n') { S.file.p[fileSize] = '\n'; usable = fileSize + 1; } // ... which the tolerant reader keeps
 	while (usable > 0 && buf[usable - 1] != '\n') usable--;
 	const int nChunks = load_threads(usable);
 	const std::vector<size_t> cut = line_cuts(buf, usable, nChunks);
 	std::vector<ObjChunk> many(nChunks > 1 ? (size_t)nChunks : 0);
 	ObjChunk* ch = nChunks > 1 ? many.data() : &S.obj; // one chunk: the thread's own, its vectors keep their capacity
 	for (int k = 0; k < nChunks; k++) { ch[k].reset(); ch[k].begin = cut[k]; ch[k].end = cut[k + 1]; }
-	run_chunks(nChunks, [&](int k) { parse_obj_chunk(buf, ch[k]); });
+	run_chunks(nChunks, [&](int k) { if (tolerant) parse_obj_chunk_tolerant(buf, ch[k]); else parse_obj_chunk(buf, ch[k]); });
 
 	// ---- stitch in file order.  The sequential reader stops at its first error: everything behind the first chunk with a parse
 	// error is ignored, and the earliest error -- parse error or face index out of range -- is the one reported.
@@ -340,7 +395,8 @@ extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
 			const long nv = (long)(vertBase[k] + c.fVertsBefore[j]);
 			float* t = &tris[(faceBase[k] + j) * 9];
 			for (int q = 0; q < 3; q++) {
-				const long idx = c.f[j * 3 + q] - 1;
+				const long raw = c.f[j * 3 + q];
+				const long idx = (tolerant && raw < 0) ? nv + raw : raw - 1; // tolerant: -1 is the vertex defined last
 				if (idx < 0 || idx >= nv) { badFace[k] = j; return; }
 				memcpy(t + q * 3, &verts[(size_t)idx * 3], 3 * sizeof(float));
 			}
@@ -353,6 +409,7 @@ extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
 		const bool isFace = faceErr < parseErr;
 		const std::string where = "OBJ line " + std::to_string(firstLine[k] + std::min(faceErr, parseErr) + 1);
 		if (isFace) return gpv::fail(where + ": face index out of range");
+		if (tolerant) return gpv::fail(where + (ch[k].errKind == 1 ? ": a vertex needs three numbers" : ": a face needs at least three non-zero integer vertex indices"));
 		return gpv::fail(where + (ch[k].errKind == 1 ? ": bad vertex coordinate (std::stof would throw)" : ": bad face index (std::stoi would throw)"));
 	}
 	if (nVerts == 0) return gpv::fail(std::string("no vertices in ") + path);
@@ -361,6 +418,8 @@ extern "C" int gpv_load_obj(const char* path, gpv_mesh* out)
 	guard.p = nullptr;
 	return export_mesh(tris, (int64_t)nFaces, (int64_t)nVerts, mn, mx, out);
 }
+
+extern "C" int gpv_load_obj(const char* path, gpv_mesh* out) { return load_obj_impl(path, out, false); }
 
 namespace {
 // operator>> tokens of [begin, end): whitespace-separated runs (chunks are cut at whitespace, so a run never straddles a cut).
@@ -483,6 +542,82 @@ extern "C" int gpv_load_off(const char* path, gpv_mesh* out)
 	return export_mesh(tris, (int64_t)nF, nV, mn, mx, out);
 }
 
+namespace {
+// Tolerant OFF reader (GPV_LOAD_TOLERANT, an extension): line-aware where the reference's `>>` chain is not.  '#' starts a
+// comment; the counts may follow "OFF" on the same line or come on the next one; a vertex line gives its first three numbers
+// (trailing colour fields are ignored); a face line gives `n i_1 ... i_n` with any n >= 3, fan-triangulated, and whatever follows
+// the n indices (colours) is ignored -- the reference reads exactly three indices whatever n says (src/Object.cpp:219-222), so
+// one quad shifts every later record.  Sequential: these are small files by nature.
+int load_off_tolerant(const char* path, gpv_mesh* out)
+{
+	memset(out, 0, sizeof *out);
+	LoadScratch& S = g_loadScratch;
+	ScratchTrim trimOnReturn{ S };
+	size_t fileSize = 0;
+	if (!read_file(path, S.file, fileSize)) return gpv::fail(std::string("Unable to open file \"") + path + "\"");
+	const char *p = S.file.p, *end = p + fileSize;
+	std::vector<Field> tok;
+	size_t lineNo = 0;
+	auto next_line = [&]() -> bool { // tokens of the next line that has any (comments stripped)
+		while (p < end) {
+			const char* le = (const char*)memchr(p, '\n', (size_t)(end - p));
+			if (!le) le = end;
+			const char* stop = (const char*)memchr(p, '#', (size_t)(le - p));
+			if (!stop) stop = le;
+			tok.clear();
+			for (const char* q = p; q < stop;) {
+				while (q < stop && gpv::is_space((unsigned char)*q)) q++;
+				if (q >= stop) break;
+				const char* b = q;
+				while (q < stop && !gpv::is_space((unsigned char)*q)) q++;
+				tok.push_back({ b, (size_t)(q - b) });
+			}
+			p = le < end ? le + 1 : end;
+			lineNo++;
+			if (!tok.empty()) return true;
+		}
+		return false;
+	};
+	auto where = [&]() { return "OFF line " + std::to_string(lineNo); };
+	if (!next_line()) return gpv::fail("OFF: empty file");
+	if (tok[0].n != 3 || memcmp(tok[0].p, "OFF", 3) != 0) return gpv::fail(where() + ": header is not \"OFF\" (COFF / NOFF / 4OFF variants are not supported)");
+	size_t c0 = 1;
+	if (tok.size() < 4) { if (!next_line()) return gpv::fail("OFF: bad counts line"); c0 = 0; }
+	long nV = 0, nF = 0;
+	if (tok.size() < c0 + 2 || !field_to_long(tok[c0], nV) || !field_to_long(tok[c0 + 1], nF)) return gpv::fail(where() + ": bad counts line");
+	if (nV <= 0 || nF <= 0) return gpv::fail("OFF: no vertices or faces");
+	if ((size_t)nV > fileSize / 6 + 1 || (size_t)nF > fileSize / 8 + 1) return gpv::fail("OFF: the counts line promises more records than the file can hold");
+	float* verts = S.verts.get((size_t)nV * 3);
+	if (!verts) return gpv::fail("out of host memory");
+	for (long i = 0; i < nV; i++) {
+		if (!next_line()) return gpv::fail("OFF: file ends inside the vertex list");
+		if (tok.size() < 3 || !field_to_float(tok[0], verts[i * 3]) || !field_to_float(tok[1], verts[i * 3 + 1]) || !field_to_float(tok[2], verts[i * 3 + 2]))
+			return gpv::fail(where() + ": a vertex needs three numbers");
+	}
+	std::vector<long> idx; // 3 vertex indices per triangle
+	idx.reserve((size_t)nF * 3);
+	for (long f = 0; f < nF; f++) {
+		if (!next_line()) return gpv::fail("OFF: file ends inside the face list");
+		long n = 0;
+		if (!field_to_long(tok[0], n) || n < 3 || tok.size() < (size_t)n + 1) return gpv::fail(where() + ": a face needs its vertex count (>= 3) and that many indices");
+		long a = 0, b = 0, c = 0;
+		for (long k = 0; k < n; k++) {
+			long q = 0;
+			if (!field_to_long(tok[(size_t)k + 1], q) || q < 0 || q >= nV) return gpv::fail(where() + ": face index out of range");
+			if (k == 0) a = q;
+			else { b = c; c = q; if (k >= 2) { idx.push_back(a); idx.push_back(b); idx.push_back(c); } }
+		}
+	}
+	const size_t nTri = idx.size() / 3;
+	float* tris = alloc_tris(nTri);
+	if (!tris) return gpv::fail("out of host memory");
+	for (size_t i = 0; i < idx.size(); i++) memcpy(&tris[i * 3], &verts[(size_t)idx[i] * 3], 3 * sizeof(float));
+	float mn[3], mx[3]; // bbox over the vertices the triangles reference, like the strict reader (:257-266)
+	bbox_of(tris, nTri * 9, mn, mx);
+	return export_mesh(tris, (int64_t)nTri, nV, mn, mx, out);
+}
+} // namespace
+
 // main()'s dispatch on the last three characters (src/GPView.cpp:1642-1659)
 extern "C" int gpv_load_mesh(const char* path, gpv_mesh* out)
 {
@@ -491,6 +626,18 @@ extern "C" int gpv_load_mesh(const char* path, gpv_mesh* out)
 		const char* ext = path + n - 3;
 		if (!strcmp(ext, "obj") || !strcmp(ext, "OBJ")) return gpv_load_obj(path, out);
 		if (!strcmp(ext, "off") || !strcmp(ext, "OFF")) return gpv_load_off(path, out);
+	}
+	return gpv::fail(std::string("unknown mesh extension: ") + path);
+}
+
+extern "C" int gpv_load_mesh_ex(const char* path, unsigned flags, gpv_mesh* out)
+{
+	if (!(flags & GPV_LOAD_TOLERANT)) return gpv_load_mesh(path, out);
+	size_t n = strlen(path);
+	if (n >= 3) {
+		const char* ext = path + n - 3;
+		if (!strcmp(ext, "obj") || !strcmp(ext, "OBJ")) return load_obj_impl(path, out, true);
+		if (!strcmp(ext, "off") || !strcmp(ext, "OFF")) return load_off_tolerant(path, out);
 	}
 	return gpv::fail(std::string("unknown mesh extension: ") + path);
 }

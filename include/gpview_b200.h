@@ -139,6 +139,13 @@ void* gpv_stream(gpv_ctx* ctx);
 int gpv_load_obj(const char* path, gpv_mesh* out);
 int gpv_load_off(const char* path, gpv_mesh* out);
 int gpv_load_mesh(const char* path, gpv_mesh* out);
+/* EXTENSION (not reference behaviour): flags = GPV_LOAD_TOLERANT reads what files in the wild contain and the
+ * reference's readers refuse or misread -- any run of blanks between fields, CRLF, an unterminated last line, comments, a fourth
+ * vertex coordinate or colour fields, negative (relative) OBJ indices, and polygons with more than three vertices (fan
+ * triangulation a0, a_k, a_k+1) in both formats.  A file with three-vertex faces, single delimiters, full `v` lines and a final
+ * newline gives the same mesh either way.  flags = 0 is gpv_load_mesh. */
+#define GPV_LOAD_TOLERANT 1u
+int gpv_load_mesh_ex(const char* path, unsigned flags, gpv_mesh* out);
 int gpv_mesh_from_triangles(const float* tris, int64_t n_tri, gpv_mesh* out); /* bbox over the given vertices + padding */
 void gpv_free_mesh(gpv_mesh* m); /* the only way to release gpv_mesh.tris (the block has a header in front of the floats and may be
                                   * parked for the calling thread's next load) */

@@ -49,7 +49,7 @@ public:
 
 	void ReadObject(const char* fname) { gpv_free_mesh(&mesh_); check(gpv_load_obj(fname, &mesh_)); adopt(); }
 	void ReadOFFObject(const char* fname) { gpv_free_mesh(&mesh_); check(gpv_load_off(fname, &mesh_)); adopt(); }
-	void ReadMesh(const char* fname) { gpv_free_mesh(&mesh_); check(gpv_load_mesh(fname, &mesh_)); adopt(); }
+	void ReadMesh(const char* fname, bool tolerant = false) { gpv_free_mesh(&mesh_); check(gpv_load_mesh_ex(fname, tolerant ? GPV_LOAD_TOLERANT : 0u, &mesh_)); adopt(); } // tolerant: extension, see gpv_load_mesh_ex
 	void CreateFlatTriangleData() { flatCPUTriangleData = mesh_.tris; totalNumTriangles = (int)mesh_.n_tri; } // already flat
 
 	// bufferSize is accepted for source compatibility and ignored: lists are CSR and cannot overflow (src/Object.cpp:3088)

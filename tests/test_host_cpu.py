@@ -368,3 +368,70 @@ def test_obj_line_fuzz_vs_oracle(product, oracle, tmp_path):
             agree_fail += 1
     assert agree_ok > 40 and agree_fail > 40, (agree_ok, agree_fail)
     print("obj fuzz: %d files load identically, %d refused by both" % (agree_ok, agree_fail))
+
+
+# ------------------------------------------------------------------------------------------------ tolerant readers (extension)
+def test_tolerant_readers_equal_the_strict_ones_on_clean_files(product, oracle, tmp_path_factory):
+    """GPV_LOAD_TOLERANT is a superset: on files the reference's readers take as meant (all fixtures) it yields the same mesh."""
+    for name in ("cessna", "sphere", "torus", "block", "cad"):
+        path = mesh_path(name, tmp_path_factory.getbasetemp())
+        a, b = product.load_mesh(path), product.load_mesh(path, tolerant=True)
+        assert a.ntri == b.ntri and np.array_equal(a.tris, b.tris) and np.array_equal(a.bbox_min, b.bbox_min) and np.array_equal(a.bbox_max, b.bbox_max)
+        for t in (2, 5):
+            os.environ["GPV_LOAD_THREADS"] = str(t)
+            try:
+                c = product.load_mesh(path, tolerant=True)
+            finally:
+                os.environ.pop("GPV_LOAD_THREADS", None)
+            assert np.array_equal(c.tris, a.tris)
+
+
+def test_tolerant_obj_reads_what_the_strict_reader_refuses(product, tmp_path):
+    txt = ("# a quad, a pentagon, relative indices, free-form blanks, CRLF, a w coordinate, no final newline\r\n"
+           "v  0 0 0\r\nv\t1  0 0 1.0\r\nv 1 1 0\r\n  v 0 1 0\r\nvn 0 0 1\r\nv 0.5 1.5 0 # apex\r\n"
+           "f 1 2 3 4\r\nf  1/1/1 2/1/1  3/1/1 5//1 4\r\nf -5 -4 -1\r\nf 1 2 3")
+    p = tmp_path / "wild.obj"
+    p.write_bytes(txt.encode())
+    with pytest.raises(product.GpvError):
+        product.load_mesh(str(p))
+    m = product.load_mesh(str(p), tolerant=True)
+    V = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 1.5, 0]], np.float32)
+    want = [(0, 1, 2), (0, 2, 3),            # quad
+            (0, 1, 2), (0, 2, 4), (0, 4, 3),  # pentagon 1 2 3 5 4
+            (0, 1, 4),                        # -5 -4 -1 with five vertices defined
+            (0, 1, 2)]                        # the unterminated last line
+    assert m.ntri == len(want)
+    assert np.array_equal(m.tris, np.array([V[list(t)].reshape(9) for t in want], np.float32))
+    assert m.bbox_max[1] > 1.5 and m.bbox_min[0] < 0
+    for bad in ("v 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2\n", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 0\n",
+                "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 7\n", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf -4 1 2\n", "v 0 0 0\nv 1 0 0\nf 1 2 3\nv 0 1 0\n"):
+        q = tmp_path / "bad.obj"
+        q.write_text(bad)
+        with pytest.raises(product.GpvError):
+            product.load_mesh(str(q), tolerant=True)
+
+
+def test_tolerant_off_reads_polygons_comments_and_colours(product, oracle, tmp_path):
+    txt = ("OFF # header with a comment\n# counts on their own line\n5 3 0\n\n0 0 0\n1 0 0 255 0 0\n1 1 0\n0 1 0\n0.5 1.5 0\n"
+           "4 0 1 2 3  0.5 0.5 0.5\n3 3 2 4\n5 0 1 2 4 3\n trailing junk is ignored\n")
+    p = tmp_path / "wild.off"
+    p.write_text(txt)
+    m = product.load_mesh(str(p), tolerant=True)
+    V = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 1.5, 0]], np.float32)
+    want = [(0, 1, 2), (0, 2, 3), (3, 2, 4), (0, 1, 2), (0, 2, 4), (0, 4, 3)]
+    assert m.ntri == len(want) and np.array_equal(m.tris, np.array([V[list(t)].reshape(9) for t in want], np.float32))
+    # the strict reader (reference semantics: three indices whatever the count says) misreads the same file
+    try:
+        s = product.load_mesh(str(p))
+        assert not (s.ntri == m.ntri and np.array_equal(s.tris, m.tris))
+    except product.GpvError:
+        pass
+    one = tmp_path / "oneline.off"
+    one.write_text("OFF 3 1 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n")
+    assert product.load_mesh(str(one), tolerant=True).ntri == 1
+    for bad in ("COFF\n3 1 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n", "OFF\n3 1 0\n0 0 0\n1 0 0\n0 1\n3 0 1 2\n", "OFF\n3 1 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 3\n",
+                "OFF\n3 1 0\n0 0 0\n1 0 0\n0 1 0\n4 0 1 2\n", "OFF\n3 2 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n", "OFF\n99999999 1 0\n0 0 0\n", ""):
+        q = tmp_path / "bad.off"
+        q.write_text(bad)
+        with pytest.raises(product.GpvError):
+            product.load_mesh(str(q), tolerant=True)

@@ -2,7 +2,8 @@
 // voxelizer path: load every mesh named on the command line (type by the last three characters, like main()), voxelize, write
 // the six ObjN*.{txt,raw} files.  Build: make -C tools.  No GLEW / freeglut.
 //
-//   gpview_voxelize [--l1 N] [--l2 M] [--no-level2] [--no-normals] [--obj-id K] [--out DIR] [--device D] mesh.obj|mesh.off ...
+//   gpview_voxelize [--l1 N] [--l2 M] [--no-level2] [--no-normals] [--tolerant] [--obj-id K] [--out DIR] [--device D] mesh.obj|mesh.off ...
+//   --tolerant: polygons, free-form blanks, comments, relative indices (GPV_LOAD_TOLERANT, an extension to the reference's readers)
 #include "../include/gpview_b200.hpp"
 #include <chrono>
 #include <cstdio>
@@ -14,6 +15,7 @@ int main(int argc, char** argv)
 	gpview::GLParameters gp;
 	gp.saveVoxels = false;
 	const char* out = ".";
+	bool tolerant = false;
 	int objID = -1; // GPView numbers the first OBJ -1, the second 0, ... (dlID - 3, src/GPView.cpp:181)
 	std::vector<const char*> files;
 	for (int i = 1; i < argc; i++) {
@@ -21,18 +23,19 @@ int main(int argc, char** argv)
 		else if (!strcmp(argv[i], "--l2") && i + 1 < argc) gp.voxelCount2 = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--no-level2")) gp.level2Voxels = false;
 		else if (!strcmp(argv[i], "--no-normals")) gp.normals = false;
+		else if (!strcmp(argv[i], "--tolerant")) tolerant = true;
 		else if (!strcmp(argv[i], "--obj-id") && i + 1 < argc) objID = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
 		else if (!strcmp(argv[i], "--device") && i + 1 < argc) gp.device = atoi(argv[++i]);
 		else files.push_back(argv[i]);
 	}
-	if (files.empty()) { fprintf(stderr, "usage: %s [--l1 N] [--l2 M] [--no-level2] [--no-normals] [--obj-id K] [--out DIR] mesh.obj|mesh.off ...\n", argv[0]); return 2; }
+	if (files.empty()) { fprintf(stderr, "usage: %s [--l1 N] [--l2 M] [--no-level2] [--no-normals] [--tolerant] [--obj-id K] [--out DIR] mesh.obj|mesh.off ...\n", argv[0]); return 2; }
 	try {
 		for (const char* f : files) {
 			gpview::Object o;
 			o.objID = objID++;
 			auto t0 = std::chrono::steady_clock::now();
-			o.ReadMesh(f);
+			o.ReadMesh(f, tolerant);
 			o.CreateFlatTriangleData();
 			auto t1 = std::chrono::steady_clock::now();
 			o.PerformVoxelization(&gp);
