@@ -16,9 +16,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
 #include <string>
 #include <thread>
 #include <vector>
+#include <fcntl.h>
+#include <unistd.h>
 
 namespace {
 
@@ -708,26 +712,60 @@ extern "C" int gpv_save_streams(const gpv_mesh* mesh, const gpv_result* res, con
 	}
 	const bool cfgBad = ferror(f) != 0;
 	if (fclose(f) != 0 || cfgBad) return gpv::fail("write error on " + prefix + "VoxelConfig.txt");
-	std::string failed; // first stream that could not be opened or written in full (a full disk must not pass for a saved model)
-	auto dump = [&](const char* name, const void* p, size_t bytes, uint8_t fill) -> bool {
-		if (!p && omit_absent) return true; // not computed, not written
-		FILE* o = fopen((prefix + name).c_str(), "wb");
-		if (!o) { failed = "Unable to open output file for writing: " + prefix + name; return false; }
-		bool ok = true;
-		if (p) ok = fwrite(p, 1, bytes, o) == bytes;
-		else { // stream not requested: neutral value, written in pieces
-			const std::vector<uint8_t> z(std::min<size_t>(bytes, (size_t)1 << 20), fill);
-			for (size_t done = 0; ok && done < bytes; done += z.size()) { const size_t n = std::min(z.size(), bytes - done); ok = fwrite(z.data(), 1, n, o) == n; }
-		}
-		ok = (fclose(o) == 0) && ok;
-		if (!ok) failed = "write error on " + prefix + name;
-		return ok;
-	};
+	// The streams: small sets (a dataset model: a few MB) are written by the calling thread; large ones (cessna 256 / 16 with
+	// normals: 0.9 GB) are cut into 8 MB pieces written with pwrite() by a few threads, so that the five files fill side by side.
+	// (Buffered writes to ONE file are serialised by the kernel's inode lock: the largest stream -- Level2Normal, 3/4 of the bytes
+	// -- still goes at one thread's ~2.4 GB/s; measured 0.39 -> 0.36 s for the 915 MB set in the build container.)  A stream that
+	// was not computed is written as its neutral value (or left out: omit_absent).  Any short write or failed close fails the
+	// call: a full disk must not pass for a saved model.
+	struct Stream { const char* name; const void* p; size_t bytes; uint8_t fill; int fd; };
 	const size_t cells = (size_t)res->cells, l2n = (size_t)res->n_boundary * (size_t)res->n23;
-	bool ok = dump("Level1InOut.raw", h->level1_inout, cells, 0) && dump("Level1Normal.raw", h->level1_normal, cells * 3, 127);
-	if (l2) ok = ok && dump("Level1BoundaryPrefixSum.raw", h->prefix, cells * 4, 0) && dump("Level2InOut.raw", h->level2_inout, l2n, 0) &&
-	             dump("Level2Normal.raw", h->level2_normal, l2n * 3, 127);
-	return ok ? 0 : gpv::fail(failed);
+	Stream st[5] = { { "Level1InOut.raw", h->level1_inout, cells, 0, -1 }, { "Level1Normal.raw", h->level1_normal, cells * 3, 127, -1 },
+		             { "Level1BoundaryPrefixSum.raw", h->prefix, cells * 4, 0, -1 }, { "Level2InOut.raw", h->level2_inout, l2n, 0, -1 },
+		             { "Level2Normal.raw", h->level2_normal, l2n * 3, 127, -1 } };
+	const int nStreams = l2 ? 5 : 2;
+	const size_t kPiece = (size_t)8 << 20;
+	struct Piece { int s; size_t off, len; };
+	std::vector<Piece> pieces;
+	std::string failed;
+	size_t total = 0;
+	for (int k = 0; k < nStreams && failed.empty(); k++) {
+		if (!st[k].p && omit_absent) continue; // not computed, not written
+		st[k].fd = open((prefix + st[k].name).c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0666);
+		if (st[k].fd < 0) { failed = "Unable to open output file for writing: " + prefix + st[k].name; break; } // the reference abort()s (:2988-2992)
+		for (size_t off = 0; off < st[k].bytes; off += kPiece) pieces.push_back({ k, off, std::min(kPiece, st[k].bytes - off) });
+		total += st[k].bytes;
+	}
+	std::atomic<size_t> next(0);
+	std::atomic<int> badStream(-1);
+	auto work = [&]() {
+		std::vector<uint8_t> filler;
+		for (;;) {
+			const size_t i = next.fetch_add(1);
+			if (i >= pieces.size() || badStream.load() >= 0) return;
+			const Piece& pc = pieces[i];
+			const Stream& sm = st[pc.s];
+			const uint8_t* src = (const uint8_t*)sm.p + pc.off;
+			if (!sm.p) {
+				if (filler.size() < pc.len || filler[0] != sm.fill) filler.assign(std::max(filler.size(), pc.len), sm.fill);
+				src = filler.data();
+			}
+			for (size_t done = 0; done < pc.len;) {
+				const ssize_t w = pwrite(sm.fd, src + done, pc.len - done, (off_t)(pc.off + done));
+				if (w < 0 && errno == EINTR) continue;
+				if (w <= 0) { int none = -1; badStream.compare_exchange_strong(none, pc.s); return; }
+				done += (size_t)w;
+			}
+		}
+	};
+	if (failed.empty()) {
+		const int nThreads = total < ((size_t)32 << 20) ? 1 : (int)std::min<size_t>({ (size_t)8, (size_t)std::max(1u, std::thread::hardware_concurrency()), pieces.size() });
+		run_chunks(nThreads, [&](int) { work(); });
+		if (badStream.load() >= 0) failed = "write error on " + prefix + st[badStream.load()].name;
+	}
+	for (int k = 0; k < nStreams; k++)
+		if (st[k].fd >= 0 && close(st[k].fd) != 0 && failed.empty()) failed = "write error on " + prefix + st[k].name;
+	return failed.empty() ? 0 : gpv::fail(failed);
 }
 
 // ---- reader of the six-file set.  The reference can only read back one hard-coded 48x64x64 uchar grid
