@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GPVIEW_B200_LIB", os.path.join(HERE, "libgpview_b200.so"))  # override: A/B builds of the same ABI
 
-GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE, GPV_GATHER, GPV_SAVE_COMPUTED_ONLY = 1, 2, 4, 8, 16, 32
+GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE, GPV_GATHER, GPV_SAVE_COMPUTED_ONLY, GPV_BATCH_TOLERANT_LOAD = 1, 2, 4, 8, 16, 32, 64
 
 
 class GpvError(RuntimeError):

@@ -55,7 +55,7 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
 			auto bail = [&]() { failed++; std::lock_guard<std::mutex> g(errMu); if (firstErr.empty()) firstErr = std::string(paths[i]) + ": " + gpv_last_error(); };
 			double a = now();
 			gpv_mesh mesh;
-			if (gpv_load_mesh(paths[i], &mesh)) { bail(); continue; }
+			if (gpv_load_mesh_ex(paths[i], (params->flags & GPV_BATCH_TOLERANT_LOAD) ? GPV_LOAD_TOLERANT : 0u, &mesh)) { bail(); continue; }
 			double b = now();
 			parse += b - a;
 			gpv_grid g;

@@ -73,6 +73,7 @@ typedef struct {
                                   without it (and without GPV_NORMALS) the lists stay in the order the binning left them: occupancy does not depend on it */
 #define GPV_PROFILE      8     /* record a CUDA event pair around every kernel of the pipeline -> gpv_result.phase_ms */
 #define GPV_GATHER      16     /* multi-GPU: write this slab's streams straight into the gathering rank's buffers (gpv_gather_*) */
+#define GPV_BATCH_TOLERANT_LOAD 64 /* gpv_voxelize_batch: read the meshes with GPV_LOAD_TOLERANT (gpv_load_mesh_ex) */
 #define GPV_SAVE_COMPUTED_ONLY 32 /* gpv_voxelize_batch: write only the streams that were computed -- no 127-filled normal files when
                                   GPV_NORMALS is off (74 % of a 64 + 4^3 model's bytes, and file writing is what bounds a dataset run) */
 

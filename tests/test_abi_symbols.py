@@ -77,6 +77,7 @@ def test_flags_and_struct_sizes_match_the_header(product):
 #include <stdio.h>
 int main(void) {
     printf("GPV_NORMALS %d\nGPV_NO_LEVEL2 %d\nGPV_KEEP_LISTS %d\nGPV_PROFILE %d\nGPV_GATHER %d\n", GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE, GPV_GATHER);
+    printf("GPV_SAVE_COMPUTED_ONLY %d\nGPV_BATCH_TOLERANT_LOAD %d\nGPV_LOAD_TOLERANT %u\n", GPV_SAVE_COMPUTED_ONLY, GPV_BATCH_TOLERANT_LOAD, GPV_LOAD_TOLERANT);
     printf("gpv_mesh %zu\ngpv_grid %zu\ngpv_params %zu\ngpv_result %zu\ngpv_host_streams %zu\ngpv_gather_desc %zu\ngpv_batch_stats %zu\ngpv_voxel_file %zu\n",
            sizeof(gpv_mesh), sizeof(gpv_grid), sizeof(gpv_params), sizeof(gpv_result), sizeof(gpv_host_streams), sizeof(gpv_gather_desc), sizeof(gpv_batch_stats), sizeof(gpv_voxel_file));
     printf("GPV_PHASE_COUNT %d\n", (int)GPV_PHASE_COUNT);
@@ -90,8 +91,11 @@ int main(void) {
         cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
         subprocess.check_call([cc, "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         got = dict(line.split() for line in subprocess.check_output([exe], text=True).splitlines())
-    for name in ("GPV_NORMALS", "GPV_NO_LEVEL2", "GPV_KEEP_LISTS", "GPV_PROFILE", "GPV_GATHER"):
+    for name in ("GPV_NORMALS", "GPV_NO_LEVEL2", "GPV_KEEP_LISTS", "GPV_PROFILE", "GPV_GATHER", "GPV_SAVE_COMPUTED_ONLY", "GPV_BATCH_TOLERANT_LOAD"):
         assert int(got[name]) == getattr(B, name), name
+    assert int(got["GPV_LOAD_TOLERANT"]) == 1  # binding.load_mesh(tolerant=True) passes 1
+    flags = [int(got[n]) for n in ("GPV_NORMALS", "GPV_NO_LEVEL2", "GPV_KEEP_LISTS", "GPV_PROFILE", "GPV_GATHER", "GPV_SAVE_COMPUTED_ONLY", "GPV_BATCH_TOLERANT_LOAD")]
+    assert len(set(flags)) == len(flags) and all(f & (f - 1) == 0 for f in flags), "gpv_params.flags bits must be distinct powers of two"
     mirrors = {"gpv_mesh": B.CMesh, "gpv_grid": B.CGrid, "gpv_params": B.CParams, "gpv_result": B.CResult, "gpv_host_streams": B.CHostStreams,
                "gpv_gather_desc": B.CGatherDesc, "gpv_batch_stats": B.CBatchStats, "gpv_voxel_file": B.CVoxelFile}
     for name, cls in mirrors.items():
