@@ -68,7 +68,7 @@ class CBatchStats(C.Structure):
 NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_stream", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh", "gpv_load_mesh_ex",
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
-                  "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_free_voxels", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
+                  "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
                   "gpv_gather_create", "gpv_gather_attach", "gpv_gather_attach_local", "gpv_gather_detach", "gpv_gather_result"]
 COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
 
@@ -363,3 +363,17 @@ def save(mesh, result, host, obj_id, directory, omit_absent=False):
         _check(lib().gpv_save_streams(C.byref(mesh.c), C.byref(result.c), C.byref(host), obj_id, os.fsencode(directory), 1))
     else:
         _check(lib().gpv_save(C.byref(mesh.c), C.byref(result.c), C.byref(host), obj_id, os.fsencode(directory)))
+
+
+def expand_dense(level1_inout, prefix, level2_inout, num_div, n2):
+    """gpv_expand_dense: (nz*n2, ny*n2, nx*n2) uint8 array in the file encoding (0 outside / 127 inside / 254 boundary)."""
+    l1 = np.ascontiguousarray(level1_inout, np.uint8)
+    pre = np.ascontiguousarray(prefix, np.int32)
+    l2 = np.ascontiguousarray(level2_inout, np.uint8)
+    nd = (C.c_int * 3)(*[int(x) for x in num_div])
+    n2 = int(n2)
+    out = np.empty((int(num_div[2]) * n2, int(num_div[1]) * n2, int(num_div[0]) * n2), np.uint8)
+    L = lib()
+    L.gpv_expand_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int64, C.c_void_p, C.c_int64]
+    _check(L.gpv_expand_dense(l1.ctypes.data, pre.ctypes.data, l2.ctypes.data, nd, n2, l2.size // max(1, n2 ** 3), out.ctypes.data, out.nbytes))
+    return out

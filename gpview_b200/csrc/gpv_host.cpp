@@ -785,6 +785,54 @@ bool read_exact(const std::string& path, void* dst, size_t bytes)
 }
 }
 
+// The two-level result as ONE dense grid at the effective resolution (nx*n2, ny*n2, nz*n2), z-major like every other stream:
+// what a 3-D CNN consumes (README.md:22-27 of the reference).  An outside / inside Level-1 cell becomes n2^3 voxels of its
+// state, a boundary cell its Level-2 block (Level2InOut index = prefix[cell]*n2^3 + r*n2^2 + q*n2 + p, cu:466-469 / :499).
+// States stay in the file encoding (0 / 127 / 254).  Rows of n2 voxels are copied at a time; z-layers are dealt to host threads.
+extern "C" int gpv_expand_dense(const uint8_t* level1_inout, const int32_t* prefix, const uint8_t* level2_inout, const int num_div[3], int n2,
+                                int64_t n_boundary, uint8_t* out, int64_t out_bytes)
+{
+	if (!level1_inout || !prefix || !level2_inout || !num_div || !out || n2 < 1) return gpv::fail("gpv_expand_dense: bad argument");
+	const int64_t nx = num_div[0], ny = num_div[1], nz = num_div[2], n23 = (int64_t)n2 * n2 * n2;
+	const int64_t X = nx * n2, Y = ny * n2, Z = nz * n2;
+	if (nx < 1 || ny < 1 || nz < 1 || out_bytes < X * Y * Z) return gpv::fail("gpv_expand_dense: output buffer smaller than (nx*n2)*(ny*n2)*(nz*n2) bytes");
+	std::atomic<int64_t> next(0);
+	std::atomic<bool> bad(false);
+	const int threads = (int)std::min<int64_t>({ (int64_t)16, (int64_t)std::max(1u, std::thread::hardware_concurrency()), nz, std::max<int64_t>(1, X * Y * Z >> 22) });
+	run_chunks(threads, [&](int) {
+		for (;;) {
+			const int64_t z = next.fetch_add(1);
+			if (z >= nz) return;
+			for (int64_t y = 0; y < ny; y++) {
+				const uint8_t* row = level1_inout + (z * ny + y) * nx;
+				for (int64_t x = 0; x < nx;) {
+					if (row[x] != 254) { // a run of cells of one plain state: one memset per dense row
+						int64_t x1 = x + 1;
+						while (x1 < nx && row[x1] == row[x]) x1++;
+						for (int r = 0; r < n2; r++) for (int q = 0; q < n2; q++)
+							memset(out + ((z * n2 + r) * Y + (y * n2 + q)) * X + x * n2, row[x], (size_t)((x1 - x) * n2));
+						x = x1;
+						continue;
+					}
+					const int64_t b = prefix[(z * ny + y) * nx + x];
+					if (b < 0 || b >= n_boundary) { bad = true; return; } // streams that do not belong together
+					const uint8_t* block = level2_inout + b * n23;
+					uint8_t* dst0 = out + ((z * n2) * Y + y * n2) * X + x * n2;
+					switch (n2) { // fixed-size copies for the usual resolutions: the compiler turns them into single moves
+					case 2: for (int r = 0; r < 2; r++) for (int q = 0; q < 2; q++) memcpy(dst0 + (r * Y + q) * X, block + (r * 2 + q) * 2, 2); break;
+					case 4: for (int r = 0; r < 4; r++) for (int q = 0; q < 4; q++) memcpy(dst0 + (r * Y + q) * X, block + (r * 4 + q) * 4, 4); break;
+					case 8: for (int r = 0; r < 8; r++) for (int q = 0; q < 8; q++) memcpy(dst0 + (r * Y + q) * X, block + (r * 8 + q) * 8, 8); break;
+					case 16: for (int r = 0; r < 16; r++) for (int q = 0; q < 16; q++) memcpy(dst0 + (r * Y + q) * X, block + (r * 16 + q) * 16, 16); break;
+					default: for (int r = 0; r < n2; r++) for (int q = 0; q < n2; q++) memcpy(dst0 + (r * Y + q) * X, block + ((int64_t)r * n2 + q) * n2, (size_t)n2);
+					}
+					x++;
+				}
+			}
+		}
+	});
+	return bad ? gpv::fail("gpv_expand_dense: a boundary cell's prefix sum points outside the Level-2 stream") : 0;
+}
+
 extern "C" void gpv_free_voxels(gpv_voxel_file* v)
 {
 	if (!v) return;

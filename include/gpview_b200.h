@@ -220,6 +220,12 @@ typedef struct {
 int gpv_load_voxels(const char* dir, int obj_id, gpv_voxel_file* out);
 void gpv_free_voxels(gpv_voxel_file* v);
 
+/* The two-level result as one dense grid at the effective resolution (num_div[a] * n2 per axis, z-major, file encoding 0/127/254):
+ * the input of a 3-D CNN (the reference's stated consumer, README.md:22-27).  Inside / outside Level-1 cells are filled with
+ * their state, boundary cells with their Level-2 block.  Host memory in, host memory out (out_bytes >= the dense size). */
+int gpv_expand_dense(const uint8_t* level1_inout, const int32_t* prefix, const uint8_t* level2_inout, const int num_div[3], int n2,
+                     int64_t n_boundary, uint8_t* out, int64_t out_bytes);
+
 /* Batched dataset generation (BASELINE.json config 5): `threads` host threads, each with its own ctx on devices[w % n_devices],
  * pull paths from a shared queue: load -> gpv_voxelize_host -> gpv_save(out_dir, obj id = first_obj_id + index).  out_dir NULL:
  * nothing is written.  skip_existing: a model whose ObjNVoxelConfig.txt exists is skipped (restartable).  The *_seconds are

@@ -435,3 +435,36 @@ def test_tolerant_off_reads_polygons_comments_and_colours(product, oracle, tmp_p
         q.write_text(bad)
         with pytest.raises(product.GpvError):
             product.load_mesh(str(q), tolerant=True)
+
+
+# ------------------------------------------------------------------------------------------------ consumer side: dense grids, Dataset
+def test_dense_expansion_and_dataset(product, oracle, tmp_path_factory, tmp_path):
+    """gpv_expand_dense / gpview_b200.dataset: the two-level file set as one grid at the effective resolution, against a direct
+    numpy construction; the torch Dataset over a directory of sets."""
+    from gpview_b200 import binding as B, dataset as D
+    path = mesh_path("torus", tmp_path_factory.getbasetemp())
+    for obj_id, (l1, l2) in enumerate([(16, 4), (12, 3), (8, 1)]):
+        r = oracle.OracleMesh(path).voxelize(l1, l2, oracle.FILL_CERTIFIED, 4)
+        r.save(obj_id, str(tmp_path))
+        nx, ny, nz = [int(x) for x in r.num_div]
+        n2 = l2
+        want = np.repeat(np.repeat(np.repeat((r.l1_state * 127).reshape(nz, ny, nx), n2, 0), n2, 1), n2, 2)
+        blocks = (r.l2_state * 127).reshape(r.nb, n2, n2, n2)
+        for b, cell in enumerate(r.boundary_index):
+            z, y, x = cell // (nx * ny), (cell // nx) % ny, cell % nx
+            want[z * n2:(z + 1) * n2, y * n2:(y + 1) * n2, x * n2:(x + 1) * n2] = blocks[b]
+        got = B.expand_dense(r.l1_state * 127, r.prefix, r.l2_state * 127, r.num_div, n2)
+        assert got.shape == want.shape and np.array_equal(got, want)
+        assert int((got == 254).sum()) == r.counts[3] and int((got == 127).sum()) == r.counts[0] * n2 ** 3 + r.counts[2]
+        g2, meta = D.load_grid(str(tmp_path), obj_id, "dense")
+        assert np.array_equal(g2, want // 127) and meta["num_div"] == [nx, ny, nz]
+        g1, _ = D.load_grid(str(tmp_path), obj_id, "level1", occupancy=True)
+        assert np.array_equal(g1, (r.l1_state > 0).reshape(nz, ny, nx))
+    assert D.list_object_ids(str(tmp_path)) == [0, 1, 2]
+    ds = D.VoxelFolder(str(tmp_path))
+    x, meta = ds[1]
+    assert len(ds) == 3 and tuple(x.shape) == (1, meta["num_div"][2] * 3, meta["num_div"][1] * 3, meta["num_div"][0] * 3) and int(x.max()) == 2
+    # streams that do not belong together are refused, not read out of bounds
+    r = oracle.OracleMesh(path).voxelize(16, 4, oracle.FILL_CERTIFIED, 4)
+    with pytest.raises(product.GpvError):
+        B.expand_dense(r.l1_state * 127, r.prefix, (r.l2_state * 127)[: 10 * 64], r.num_div, 4)
