@@ -18,6 +18,35 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def write_meshes(d, distinct):
+    from gpview_b200 import meshgen as M
+    files = []
+    for i in range(distinct):
+        V, F = M.drilled_block(seed=M.SEED_BASE + i, n_seg=160, n_grid=36)
+        p = os.path.join(d, "block%05d.off" % i)
+        M.write_off(p, V, F)
+        files.append(p)
+    return files
+
+
+def run_procs(a):
+    """--procs P: P copies of this tool, each on its share of the models; wall clock from the moment all are started (their
+    warm-up batches included, so take --models large) to the last one's exit."""
+    import subprocess
+    d = tempfile.mkdtemp(prefix="gpvbatch")
+    write_meshes(d, a.distinct)
+    base = [sys.executable, os.path.abspath(__file__), "--models", str(a.models), "--distinct", str(a.distinct), "--threads", str(a.threads), "--gpus", str(a.gpus),
+            "--l1", str(a.l1), "--l2", str(a.l2), "--mesh-dir", d] + (["--normals"] if a.normals else []) + (["--save"] if a.save else [])
+    t0 = time.time()
+    ps = [subprocess.Popen(base + ["--share", "%d/%d" % (k, a.procs)], stdout=subprocess.PIPE, text=True) for k in range(a.procs)]
+    outs = [p.communicate()[0] for p in ps]
+    dt = time.time() - t0
+    rows = [json.loads(o.strip().splitlines()[-1]) for o in outs if o.strip()]
+    print(json.dumps({"config": "drilled-block .off meshes, %d processes x %d threads on %d GPU(s)" % (a.procs, a.threads, a.gpus), "models": a.models,
+                      "wall_seconds_incl_startup": dt, "models_per_s_sum_of_processes": sum(r["models_per_s"] for r in rows),
+                      "per_process": [{k: r[k] for k in ("models", "models_per_s", "seconds", "failed")} for r in rows]}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--models", type=int, default=2000)
@@ -31,19 +60,23 @@ def main():
     ap.add_argument("--six-files", action="store_true", help="without --normals: still write the two normal files (127-filled), as gpv_save does")
     ap.add_argument("--check", type=int, default=0)
     ap.add_argument("--parse-only", action="store_true", help="host side alone (no GPU needed): models/s the loaders can feed on --threads host threads")
+    ap.add_argument("--procs", type=int, default=1, help="experiment: P worker processes (own CUDA contexts) of --threads threads each, every process runs "
+                    "gpv_voxelize_batch on its share of the models; one process saturates its own launch path at ~7 k models/s per GPU")
+    ap.add_argument("--mesh-dir", default=None, help=argparse.SUPPRESS)   # worker processes of --procs: meshes already written here
+    ap.add_argument("--share", default=None, help=argparse.SUPPRESS)      # "k/P": this worker's share of the model list
     a = ap.parse_args()
+    if a.procs > 1 and not a.share:
+        return run_procs(a)
     import gpview_b200 as gpv
     from gpview_b200 import binding as B, meshgen as M
-    d = tempfile.mkdtemp(prefix="gpvbatch")
+    d = a.mesh_dir or tempfile.mkdtemp(prefix="gpvbatch")
     t0 = time.time()
-    files = []
-    for i in range(a.distinct):
-        V, F = M.drilled_block(seed=M.SEED_BASE + i, n_seg=160, n_grid=36)
-        p = os.path.join(d, "block%05d.off" % i)
-        M.write_off(p, V, F)
-        files.append(p)
+    files = write_meshes(d, a.distinct) if not a.mesh_dir else [os.path.join(d, "block%05d.off" % i) for i in range(a.distinct)]
     gen_s = time.time() - t0
     paths = [files[i % a.distinct] for i in range(a.models)]
+    if a.share:
+        k, P = [int(x) for x in a.share.split("/")]
+        paths = paths[k::P]
     if a.parse_only:
         import threading
         nxt, lock, tris = [0], threading.Lock(), [0]
@@ -73,7 +106,7 @@ def main():
     flags = gpv.GPV_NORMALS if a.normals else (0 if a.six_files else gpv.GPV_SAVE_COMPUTED_ONLY)
     B.voxelize_batch(paths[:min(len(paths), 4 * a.threads)], gpv.Params(a.l1, a.l2, flags), list(range(a.gpus)), a.threads, None)  # warm-up: contexts, pools
     st = B.voxelize_batch(paths, gpv.Params(a.l1, a.l2, flags), list(range(a.gpus)), a.threads, out, 0, False)
-    line = {"config": "drilled-block .off meshes (~5k triangles), Level1 %d + Level2 %d^3" % (a.l1, a.l2), "models": a.models, "distinct_meshes": a.distinct,
+    line = {"config": "drilled-block .off meshes (~5k triangles), Level1 %d + Level2 %d^3" % (a.l1, a.l2), "models": len(paths), "distinct_meshes": a.distinct,
             "threads": a.threads, "gpus": a.gpus, "saved": bool(out), "normals": a.normals, "models_per_s": st["models_done"] / st["seconds"],
             "seconds": st["seconds"], "per_model_ms_summed_over_threads": {k: 1e3 * st[k + "_seconds"] / max(1, st["models_done"]) for k in ("parse", "gpu", "save")},
             "mesh_generation_s": gen_s, "failed": st["models_failed"]}
