@@ -63,3 +63,44 @@ def test_threaded_brute_force_equals_member_function():
     b = refbind.RefObject(path); b.setup(24, 2); b.l1_inout_brute(4)
     assert np.array_equal(a.level1_inout(), b.level1_inout())
     a.close(); b.close()
+
+
+def test_oracle_equals_reference_on_random_meshes(oracle, tmp_path):
+    """The pin beyond the fixture meshes: random triangle soups, scattered small triangles, quantised (degenerate-rich) soups,
+    slivers / near-vertical walls and a perturbed closed body, at random small resolutions -- reference live (brute-force fill,
+    its own tri-box classification, kernel-form Level 2) == oracle brute force == the oracle's certified fast paths, which
+    is what the GPU tests compare with.  (A 15-minute soak of this generator, 28,017 meshes, found no difference.)"""
+    from oracle import refbind
+    from gpview_b200 import meshgen
+    rng = np.random.default_rng(424242)
+    p = str(tmp_path / "s.obj")
+    for it in range(150):
+        nt, kind = int(rng.integers(4, 200)), it % 5
+        if kind == 0:
+            V = rng.uniform(-1, 1, (nt * 3, 3))
+        elif kind == 1:
+            V = (rng.uniform(-1, 1, (nt, 1, 3)) + rng.normal(0, 0.05, (nt, 3, 3))).reshape(-1, 3)
+        elif kind == 2:
+            V = np.round(rng.uniform(-1, 1, (nt * 3, 3)) * 4) / 4
+        elif kind == 3:
+            a, b, t = rng.uniform(-1, 1, (nt, 3)), rng.uniform(-1, 1, (nt, 3)), rng.uniform(0, 1, (nt, 1))
+            V = np.stack([a, b, a + (b - a) * t + rng.normal(0, 1e-5, (nt, 3))], 1).reshape(-1, 3)
+        else:
+            Vs, Fs = meshgen.uv_sphere(12, 8)
+            V = Vs[Fs].reshape(-1, 3) + rng.normal(0, 0.02, (len(Fs) * 3, 3))
+        V = V.astype(np.float32)
+        meshgen.write_obj(p, V, np.arange(len(V)).reshape(-1, 3))
+        l1, l2 = int(rng.choice([4, 8, 12, 20])), int(rng.choice([1, 2, 3, 4]))
+        ro, om = refbind.RefObject(p, obj_id=7), oracle.OracleMesh(p)
+        assert np.array_equal(ro.tris, om.tris) and np.array_equal(ro.bmin, om.bmin) and np.array_equal(ro.bmax, om.bmax), it
+        ro.setup(l1, l2); ro.l1_inout_brute(0); ro.l1_tribox(); ro.compact(); ro.l2_kernelform(2); ro.adopt_kernelform()
+        cnt = ro.count()
+        r = om.voxelize(l1, l2, oracle.FILL_BRUTE | oracle.L2_NAIVE, 2)
+        rc = om.voxelize(l1, l2, oracle.FILL_CERTIFIED, 2)
+        where = (it, kind, l1, l2)
+        assert list(r.num_div) == list(ro.num_div), where
+        assert np.array_equal(r.l1_state, ro.level1_inout().astype(np.uint8)), where
+        assert np.array_equal(r.prefix, ro.prefix()) and np.array_equal(r.boundary_index, ro.boundary_index()), where
+        assert np.array_equal(r.l2_state, ro.level2_inout_kernel().astype(np.uint8)) and r.counts == cnt, where
+        assert np.array_equal(rc.l1_state, r.l1_state) and np.array_equal(rc.l2_state, r.l2_state) and rc.counts == r.counts, where
+        ro.close()
