@@ -62,3 +62,13 @@ def test_workload_description_and_peaks():
     peak, src = b.measured_peaks()
     assert peak > 1000 and ("measured" in src or "fallback" in src)
     assert b.FLOPS_PER_TRIBOX == 124
+
+
+def test_cpu_baseline_reports_all_cores_and_one_thread(tmp_path):
+    """the reference's TriBoxOverlap loop nest on every host core and on one thread (its actual execution model)."""
+    b = _bench()
+    path = b.make_mesh_file("cessna", str(tmp_path))
+    out = b.cpu_baseline(path, 64, 4, os.cpu_count() or 1, target_seconds=0.5)
+    assert out["kind"] in ("reference", "port") and out["value"] > 0 and out["cores"] == (os.cpu_count() or 1) and "boundary cells" in out["sample"]
+    one = out["single_thread"]
+    assert one["cores"] == 1 and one["value"] > 0 and one["unit"] == out["unit"]
