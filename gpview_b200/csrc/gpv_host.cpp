@@ -274,6 +274,26 @@ void parse_obj_chunk(const char* data, ObjChunk& c)
 	}
 }
 
+// Number fields of the tolerant readers: the WHOLE field must be the number ("1.5abc", "0.5" as an index, "3/" are errors).  The
+// strict readers keep the reference's strtof / strtol prefix semantics; the tolerant ones are lenient about layout, not about digits.
+bool whole_long(const char* p, size_t n, long& v)
+{
+	const char* q = gpv::scan_long(p, p + n, v);
+	return q == p + n && n > 0;
+}
+bool whole_float(const char* p, size_t n, float& v)
+{
+	if (const char* q = gpv::scan_float(p, p + n, v)) return q == p + n;
+	char tmp[128]; // no short exact path (long mantissa, subnormal, inf / nan, ...): the library, which must also consume the whole field
+	if (n == 0 || n >= sizeof tmp) return false;
+	memcpy(tmp, p, n);
+	tmp[n] = 0;
+	if (gpv::is_space((unsigned char)tmp[0])) return false;
+	char* end;
+	v = strtof(tmp, &end);
+	return end == tmp + n;
+}
+
 // Tolerant twin (GPV_LOAD_TOLERANT, an extension -- SURVEY.md 8f3): what OBJ files in the wild need and the reference's reader
 // refuses or misreads.  Fields are runs of non-blank characters (any mix of spaces, tabs, CR); `v` takes its first three numbers
 // (a fourth, w or a colour, is ignored; fewer is an error, not a stale coordinate); `f` takes any number >= 3 of vertices
@@ -303,13 +323,13 @@ void parse_obj_chunk_tolerant(const char* data, ObjChunk& c)
 			const char* fs = p;
 			while (p < le && !blank(*p)) p++;
 			if (isV) {
-				if (got < 3 && !gpv::parse_float(fs, (size_t)(p - fs), pt[got])) { bad = true; break; }
+				if (got < 3 && !whole_float(fs, (size_t)(p - fs), pt[got])) { bad = true; break; }
 				got++;
 			} else {
 				const char* sl = fs;
 				while (sl < p && *sl != '/') sl++;
 				long idx = 0;
-				if (!gpv::parse_long(fs, (size_t)(sl - fs), idx) || idx == 0) { bad = true; break; }
+				if (!whole_long(fs, (size_t)(sl - fs), idx) || idx == 0) { bad = true; break; }
 				poly.push_back(idx);
 			}
 		}
@@ -588,14 +608,14 @@ int load_off_tolerant(const char* path, gpv_mesh* out)
 	size_t c0 = 1;
 	if (tok.size() < 4) { if (!next_line()) return gpv::fail("OFF: bad counts line"); c0 = 0; }
 	long nV = 0, nF = 0;
-	if (tok.size() < c0 + 2 || !field_to_long(tok[c0], nV) || !field_to_long(tok[c0 + 1], nF)) return gpv::fail(where() + ": bad counts line");
+	if (tok.size() < c0 + 2 || !whole_long(tok[c0].p, tok[c0].n, nV) || !whole_long(tok[c0 + 1].p, tok[c0 + 1].n, nF)) return gpv::fail(where() + ": bad counts line");
 	if (nV <= 0 || nF <= 0) return gpv::fail("OFF: no vertices or faces");
 	if ((size_t)nV > fileSize / 6 + 1 || (size_t)nF > fileSize / 8 + 1) return gpv::fail("OFF: the counts line promises more records than the file can hold");
 	float* verts = S.verts.get((size_t)nV * 3);
 	if (!verts) return gpv::fail("out of host memory");
 	for (long i = 0; i < nV; i++) {
 		if (!next_line()) return gpv::fail("OFF: file ends inside the vertex list");
-		if (tok.size() < 3 || !field_to_float(tok[0], verts[i * 3]) || !field_to_float(tok[1], verts[i * 3 + 1]) || !field_to_float(tok[2], verts[i * 3 + 2]))
+		if (tok.size() < 3 || !whole_float(tok[0].p, tok[0].n, verts[i * 3]) || !whole_float(tok[1].p, tok[1].n, verts[i * 3 + 1]) || !whole_float(tok[2].p, tok[2].n, verts[i * 3 + 2]))
 			return gpv::fail(where() + ": a vertex needs three numbers");
 	}
 	std::vector<long> idx; // 3 vertex indices per triangle
@@ -603,11 +623,11 @@ int load_off_tolerant(const char* path, gpv_mesh* out)
 	for (long f = 0; f < nF; f++) {
 		if (!next_line()) return gpv::fail("OFF: file ends inside the face list");
 		long n = 0;
-		if (!field_to_long(tok[0], n) || n < 3 || tok.size() < (size_t)n + 1) return gpv::fail(where() + ": a face needs its vertex count (>= 3) and that many indices");
+		if (!whole_long(tok[0].p, tok[0].n, n) || n < 3 || tok.size() < (size_t)n + 1) return gpv::fail(where() + ": a face needs its vertex count (>= 3) and that many indices");
 		long a = 0, b = 0, c = 0;
 		for (long k = 0; k < n; k++) {
 			long q = 0;
-			if (!field_to_long(tok[(size_t)k + 1], q) || q < 0 || q >= nV) return gpv::fail(where() + ": face index out of range");
+			if (!whole_long(tok[(size_t)k + 1].p, tok[(size_t)k + 1].n, q) || q < 0 || q >= nV) return gpv::fail(where() + ": face index missing, not an integer or out of range");
 			if (k == 0) a = q;
 			else { b = c; c = q; if (k >= 2) { idx.push_back(a); idx.push_back(b); idx.push_back(c); } }
 		}

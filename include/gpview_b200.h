@@ -143,7 +143,8 @@ int gpv_load_mesh(const char* path, gpv_mesh* out);
 /* EXTENSION (not reference behaviour): flags = GPV_LOAD_TOLERANT reads what files in the wild contain and the
  * reference's readers refuse or misread -- any run of blanks between fields, CRLF, an unterminated last line, comments, a fourth
  * vertex coordinate or colour fields, negative (relative) OBJ indices, and polygons with more than three vertices (fan
- * triangulation a0, a_k, a_k+1) in both formats.  A file with three-vertex faces, single delimiters, full `v` lines and a final
+ * triangulation a0, a_k, a_k+1) in both formats.  Lenient about layout, not about digits: a number field must be a number as a
+ * whole ("1.5abc", or "0.5" where an index belongs, is an error; the strict readers keep the reference's strtof / strtol prefix rule).  A file with three-vertex faces, single delimiters, full `v` lines and a final
  * newline gives the same mesh either way.  flags = 0 is gpv_load_mesh. */
 #define GPV_LOAD_TOLERANT 1u
 int gpv_load_mesh_ex(const char* path, unsigned flags, gpv_mesh* out);
