@@ -138,6 +138,9 @@ void* gpv_stream(gpv_ctx* ctx);
 /* loaders with the reference's semantics (Object::ReadObject src/Object.cpp:395-584, Object::ReadOFFObject :171-317);
  * gpv_load_mesh dispatches on the last three characters like main() (src/GPView.cpp:1642-1659) */
 int gpv_load_obj(const char* path, gpv_mesh* out);
+/* Where the reference's readers die, these report: a field std::stof / std::stoi would throw invalid_argument on, a face index out
+ * of range, a missing file -> non-zero + gpv_last_error() (the reference abort()s, crashes or reads garbage).  One leniency: a
+ * coordinate std::stof rejects as out of range ("1e-40", "1e39": strtof sets ERANGE) is taken with strtof's value. */
 int gpv_load_off(const char* path, gpv_mesh* out);
 int gpv_load_mesh(const char* path, gpv_mesh* out);
 /* EXTENSION (not reference behaviour): flags = GPV_LOAD_TOLERANT reads what files in the wild contain and the

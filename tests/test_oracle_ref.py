@@ -104,3 +104,41 @@ def test_oracle_equals_reference_on_random_meshes(oracle, tmp_path):
         assert np.array_equal(r.l2_state, ro.level2_inout_kernel().astype(np.uint8)) and r.counts == cnt, where
         assert np.array_equal(rc.l1_state, r.l1_state) and np.array_equal(rc.l2_state, r.l2_state) and rc.counts == r.counts, where
         ro.close()
+
+
+def test_product_obj_reader_equals_the_live_reference_on_quirky_files(tmp_path):
+    """The product's strict OBJ reader against Object::ReadObject itself on 1,500 random files from the subset the reference
+    survives (it assert()s on `f` / `vn` / `vt` lines with other field counts, throws on stof range errors and writes out of
+    bounds on long `v` lines): tab- or space-separated lines, short `v` lines (stale coordinates), numeric prefixes ("1.5abc",
+    "4\\r"), "a/b", "a//c", "a/b/c", leading zeros and plus signs, comments and other keywords, a missing final newline --
+    triangles and padded bounding box bit for bit.  (261,151 files in a soak.)"""
+    import gpview_b200 as gpv
+    from oracle import refbind
+    rng = np.random.default_rng(31337)
+    p = str(tmp_path / "r.obj")
+    nums = ["0", "1", "-1.5", "2.25e0", "+3", ".5", "7.", "1e-3", "0.333333343", "1.5abc", "4\r", "-0", "00012.5", "3.4e38"]
+    bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+    for it in range(1500):
+        lines, nv = ["v 0 0 0", "v 1 0 0", "v 0 1 0"], 3
+        for _ in range(int(rng.integers(1, 14))):
+            r, d1 = rng.random(), (" " if rng.random() < 0.8 else "\t")
+            if r < 0.45:
+                k = 3 if rng.random() < 0.8 else int(rng.integers(0, 3))
+                lines.append(d1.join(["v"] + [nums[rng.integers(len(nums))] for _ in range(k)]))
+                nv += 1
+            elif r < 0.85:
+                def ix():
+                    s, v = str(int(rng.integers(1, nv + 1))), rng.random()
+                    return s if v < 0.5 else s + "/1" if v < 0.65 else s + "//2" if v < 0.8 else s + "/1/2" if v < 0.9 else ("0" + s if v < 0.95 else "+" + s)
+                lines.append(d1.join(["f", ix(), ix(), ix()]) + ("\r" if rng.random() < 0.15 else ""))
+            else:
+                lines.append(["vn 0 0 1", "vt 0.5 0.5", "# comment", "g grp", "", "usemtl m", "s off", "o obj", "vn\t0\t1\t0"][rng.integers(9)])
+        txt = "\n".join(lines) + ("\n" if rng.random() < 0.85 else "")
+        with open(p, "w", newline="") as f:
+            f.write(txt)
+        ro = refbind.RefObject(p)
+        pm = gpv.load_mesh(p)
+        want = ro.tris.reshape(-1, 9)
+        assert pm.ntri == len(want) and np.array_equal(bits(pm.tris), bits(want)), (it, txt)
+        assert np.array_equal(bits(pm.bbox_min), bits(ro.bmin)) and np.array_equal(bits(pm.bbox_max), bits(ro.bmax)), (it, txt)
+        ro.close()
