@@ -176,3 +176,29 @@ def test_product_off_reader_equals_the_live_reference(tmp_path):
         assert pm.ntri == len(want) and np.array_equal(bits(pm.tris), bits(want)), (it, txt)
         assert np.array_equal(bits(pm.bbox_min), bits(ro.bmin)) and np.array_equal(bits(pm.bbox_max), bits(ro.bmax)), (it, txt)
         ro.close()
+
+
+def test_grid_sizing_equals_the_live_reference_on_random_models(tmp_path):
+    """gpv_make_grid (+ the loader's padded bounding box and maxModelSize) against the reference's own arithmetic
+    (src/Object.cpp:572-583, 3094-3134) on 600 random models: coordinates from 1e-3 to 1e4, offsets up to 1e4, cubes (ties
+    between the axes) and flat boxes, Level-1 counts around the GetNextDiv4 steps, Level-2 1..32 -- numDiv, gridSize, gridSize2
+    bit for bit.  (165,280 models in a soak.)"""
+    import gpview_b200 as gpv
+    from gpview_b200 import meshgen
+    from oracle import refbind
+    rng = np.random.default_rng(99)
+    p = str(tmp_path / "g.obj")
+    bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+    for it in range(600):
+        scale, off = 10.0 ** rng.uniform(-3, 4), rng.uniform(-1, 1, 3) * 10.0 ** rng.uniform(-2, 4)
+        ext = np.ones(3) if rng.random() < 0.2 else 10.0 ** rng.uniform(-1.5, 0, 3)
+        V = (rng.uniform(-1, 1, (12, 3)) * ext * scale + off).astype(np.float32)
+        meshgen.write_obj(p, V, np.arange(12).reshape(-1, 3))
+        l1, l2 = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 16, 31, 33, 63, 64, 65, 100, 127, 129])), int(rng.integers(1, 33))
+        ro, pm = refbind.RefObject(p), gpv.load_mesh(p)
+        ro.setup(l1, l2)
+        g = gpv.grid_for(pm.bbox_min, pm.bbox_max, pm.max_model_size, l1, l2)
+        where = (it, l1, l2, list(V[0]))
+        assert pm.max_model_size == ro.max_model_size and list(g.num_div) == [int(x) for x in ro.num_div], where
+        assert np.array_equal(bits(list(g.grid_size)), bits(ro.grid_size)) and np.array_equal(bits(list(g.grid_size2)), bits(ro.grid_size2)), where
+        ro.close()
