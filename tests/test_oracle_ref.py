@@ -189,6 +189,7 @@ def test_grid_sizing_equals_the_live_reference_on_random_models(tmp_path):
     rng = np.random.default_rng(99)
     p = str(tmp_path / "g.obj")
     bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+    refused = 0
     for it in range(600):
         scale, off = 10.0 ** rng.uniform(-3, 4), rng.uniform(-1, 1, 3) * 10.0 ** rng.uniform(-2, 4)
         ext = np.ones(3) if rng.random() < 0.2 else 10.0 ** rng.uniform(-1.5, 0, 3)
@@ -197,8 +198,14 @@ def test_grid_sizing_equals_the_live_reference_on_random_models(tmp_path):
         l1, l2 = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 16, 31, 33, 63, 64, 65, 100, 127, 129])), int(rng.integers(1, 33))
         ro, pm = refbind.RefObject(p), gpv.load_mesh(p)
         ro.setup(l1, l2)
-        g = gpv.grid_for(pm.bbox_min, pm.bbox_max, pm.max_model_size, l1, l2)
+        try:
+            g = gpv.grid_for(pm.bbox_min, pm.bbox_max, pm.max_model_size, l1, l2)
+        except gpv.GpvError:      # a box that collapses in f32 (tiny model far from the origin): refused, the reference divides by zero
+            refused += 1
+            ro.close()
+            continue
         where = (it, l1, l2, list(V[0]))
         assert pm.max_model_size == ro.max_model_size and list(g.num_div) == [int(x) for x in ro.num_div], where
         assert np.array_equal(bits(list(g.grid_size)), bits(ro.grid_size)) and np.array_equal(bits(list(g.grid_size2)), bits(ro.grid_size2)), where
         ro.close()
+    assert refused < 100, refused
