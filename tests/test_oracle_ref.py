@@ -209,3 +209,55 @@ def test_grid_sizing_equals_the_live_reference_on_random_models(tmp_path):
         assert np.array_equal(bits(list(g.grid_size)), bits(ro.grid_size)) and np.array_equal(bits(list(g.grid_size2)), bits(ro.grid_size2)), where
         ro.close()
     assert refused < 100, refused
+
+
+def test_writer_equals_save_voxelization_on_random_models(tmp_path):
+    """gpv_save fed with the reference's own arrays against Object::SaveVoxelization on 200 random models whose sizes span eleven
+    orders of magnitude (the %g text of ObjNVoxelConfig.txt: fixed, scientific, negative), object ids -1..499: the config file,
+    Level1InOut, Level1BoundaryPrefixSum and Level2InOut byte for byte.  (14,779 models in a soak.)"""
+    import shutil
+    import gpview_b200 as gpv
+    from gpview_b200 import binding as B, meshgen
+    from oracle import refbind
+    rng = np.random.default_rng(2024)
+    p = str(tmp_path / "m.obj")
+    Vs, Fs = meshgen.uv_sphere(8, 6)
+    done = 0
+    for it in range(200):
+        scale = 10.0 ** rng.uniform(-5, 6)
+        V = (Vs * rng.uniform(0.3, 1, 3) * scale + rng.uniform(-1, 1, 3) * scale * 10.0 ** rng.uniform(-1, 2)).astype(np.float32)
+        meshgen.write_obj(p, V, Fs)
+        l1, l2, oid = int(rng.choice([4, 8, 12])), int(rng.choice([1, 2, 3])), int(rng.integers(-1, 500))
+        ro, pm = refbind.RefObject(p, obj_id=oid), gpv.load_mesh(p)
+        ro.setup(l1, l2); ro.l1_inout_brute(0); ro.l1_tribox(); ro.compact(); ro.l2_kernelform(1); ro.adopt_kernelform()
+        cnt = ro.count()
+        d1, d2 = tmp_path / "ref", tmp_path / "gpv"
+        for d in (d1, d2):
+            shutil.rmtree(d, ignore_errors=True)
+            d.mkdir()
+        ro.save(str(d1))
+        try:
+            g = gpv.grid_for(pm.bbox_min, pm.bbox_max, pm.max_model_size, l1, l2)
+        except gpv.GpvError:
+            ro.close()
+            continue
+        res = B.CResult()
+        res.grid = g
+        l1s = (ro.level1_inout() * np.float32(127)).astype(np.uint8)
+        pre = ro.prefix().copy()
+        l2s = (ro.level2_inout() * np.float32(127)).astype(np.uint8)
+        res.cells, res.n_boundary, res.n23 = len(l1s), ro.nboundary(), l2 ** 3
+        res.l1_inside, res.l1_boundary, res.l2_inside, res.l2_boundary = cnt
+        hs = B.CHostStreams(l1s.ctypes.data, pre.ctypes.data, None, l2s.ctypes.data, None, None, l2s.nbytes, 0)
+
+        class R:
+            c = res
+        B.save(pm, R, hs, oid, str(d2))
+        names = sorted(os.listdir(d1))
+        assert names == sorted(os.listdir(d2)) and len(names) == 6, (it, names)
+        for n in names:
+            if "Normal" not in n:
+                assert filecmp.cmp(d1 / n, d2 / n, shallow=False), (it, n, scale, open(d1 / n, "rb").read()[:300], open(d2 / n, "rb").read()[:300])
+        ro.close()
+        done += 1
+    assert done > 150
