@@ -267,3 +267,86 @@ def test_writer_equals_save_voxelization_on_random_models(tmp_path):
         ro.close()
         done += 1
     assert done > 150
+
+
+EMU = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libgpvref_emu.so")
+
+
+def _emu_lib():
+    import ctypes as C
+    from oracle import refbind
+    refbind.LIB_PATH, refbind._lib = EMU, None
+    L = refbind.lib()
+    L.ref_cuda_path.argtypes = [C.c_void_p]
+    L.ref_cuda_path.restype = C.c_int
+    return L
+
+
+def _restore_ref_lib():
+    from oracle import refbind
+    refbind.LIB_PATH, refbind._lib = os.path.join(os.path.dirname(EMU), "libgpvref.so"), None
+
+
+def _reference_gpu_path_vs_oracle(oracle, L, path, l1, l2):
+    """Object::ClassifyTessellationCUDA (with its two-pass buffer re-run) + Object::ClassifyInOutTessellationLevel2CUDA on the
+    host-executed kernels; the GL solid fill, which cannot run headless, is seeded from the oracle.  Returns the buffer size used."""
+    import ctypes as C
+    from oracle import refbind
+    want = oracle.OracleMesh(path).voxelize(l1, l2, oracle.FILL_CERTIFIED, 4)
+    ro = refbind.RefObject(path)
+    ro.setup(l1, l2)
+    fill = want.l1_fill_only.astype(np.float32)
+    C.memmove(L.ref_level1InOut(ro.h), fill.ctypes.data, fill.nbytes)
+    used = L.ref_cuda_path(ro.h)
+    where = (path, l1, l2, used)
+    assert np.array_equal(ro.level1_inout().astype(np.uint8), want.l1_state), where
+    assert np.array_equal(ro.boundary_index(), want.boundary_index), where
+    assert np.array_equal(ro.level2_inout().astype(np.uint8), want.l2_state), where
+    assert ro.count() == want.counts, where
+    # Level-2 normals after the reference's host averaging (src/Object.cpp:2613-2632) in its file encoding: the emulated threads run
+    # in ascending order, which is the oracle's canonical accumulation order, so even these agree bit for bit
+    n = ro.level2_normal().reshape(-1, 4)[:, :3].reshape(-1)
+    assert np.array_equal((n * np.float32(256.0 / 3.0) + np.float32(127.0)).astype(np.uint8), want.l2_normal), where
+    ro.close()
+    return used
+
+
+@pytest.mark.skipif(not os.path.exists(EMU), reason="oracle/_ref/libgpvref_emu.so not built")
+@pytest.mark.parametrize("name,l1,l2", [("cessna", 32, 4), ("torus", 24, 8), ("cessna", 64, 4), ("block", 20, 3), ("cad", 16, 5)])
+def test_reference_gpu_path_on_host_executed_kernels_equals_the_oracle(oracle, tmp_path_factory, name, l1, l2):
+    """The last link of the pin: the reference's GPU path SOURCE FOR SOURCE -- its unmodified host code driving its unmodified
+    kernel source (cuda/CUDAClassifyTessellation.cu compiled as C++ and run thread by thread, oracle/ref_kernels_host.cpp) --
+    gives the oracle's Level-1 states, boundary list, Level-2 states, counts and Level-2 normals.  So the "kernel form" the
+    oracle restates IS what the reference's kernels compute (under strict IEEE; g++ -ffp-contract=off == nvcc -fmad=false)."""
+    path = os.path.join(REF, "files", "cessna.obj") if name == "cessna" else mesh_path(name, tmp_path_factory.getbasetemp())
+    try:
+        used = _reference_gpu_path_vs_oracle(oracle, _emu_lib(), path, l1, l2)
+    finally:
+        _restore_ref_lib()
+    if name == "cessna":
+        assert used == (946 if l1 == 32 else 329)   # more triangles per cell than the default buffer of 50: the re-run (src/Object.cpp:3204-3214)
+
+
+@pytest.mark.skipif(not os.path.exists(EMU), reason="oracle/_ref/libgpvref_emu.so not built")
+def test_reference_gpu_path_on_host_executed_kernels_random_meshes(oracle, tmp_path):
+    from gpview_b200 import meshgen
+    rng = np.random.default_rng(8080)
+    p = str(tmp_path / "s.obj")
+    try:
+        L = _emu_lib()
+        for it in range(60):
+            nt, kind = int(rng.integers(4, 150)), it % 4
+            if kind == 0:
+                V = rng.uniform(-1, 1, (nt * 3, 3))
+            elif kind == 1:
+                V = (rng.uniform(-1, 1, (nt, 1, 3)) + rng.normal(0, 0.08, (nt, 3, 3))).reshape(-1, 3)
+            elif kind == 2:
+                V = np.round(rng.uniform(-1, 1, (nt * 3, 3)) * 4) / 4
+            else:
+                Vs, Fs = meshgen.uv_sphere(10, 7)
+                V = Vs[Fs].reshape(-1, 3) + rng.normal(0, 0.02, (len(Fs) * 3, 3))
+            V = V.astype(np.float32)
+            meshgen.write_obj(p, V, np.arange(len(V)).reshape(-1, 3))
+            _reference_gpu_path_vs_oracle(oracle, L, p, int(rng.choice([4, 8, 12, 16])), int(rng.choice([1, 2, 3, 4])))
+    finally:
+        _restore_ref_lib()
