@@ -350,3 +350,20 @@ def test_reference_gpu_path_on_host_executed_kernels_random_meshes(oracle, tmp_p
             _reference_gpu_path_vs_oracle(oracle, L, p, int(rng.choice([4, 8, 12, 16])), int(rng.choice([1, 2, 3, 4])))
     finally:
         _restore_ref_lib()
+
+
+@pytest.mark.skipif(not os.path.exists(EMU), reason="oracle/_ref/libgpvref_emu.so not built")
+def test_reference_gpu_path_tool_plumbing(oracle, tmp_path_factory):
+    """tools/bench_reference_gpu_path.py (reference's kernels vs compat vs native, for the GPU box) with its reference worker on the
+    host-executed kernels: the worker runs through to its JSON line and reports the oracle's counts."""
+    import json
+    import subprocess
+    import sys
+    from util import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_reference_gpu_path.py"), "--emulated-only", "--mesh", "torus", "--l1", "16", "--l2", "2", "--reps", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    run = out["runs"]["emulated"]
+    want = oracle.OracleMesh(mesh_path("torus", tmp_path_factory.getbasetemp())).voxelize(16, 2, oracle.FILL_CERTIFIED | oracle.NO_NORMALS, 2)
+    assert run["counts"] == want.counts and run["tri_buffer"] == 50 and len(run["seconds"]) == 1

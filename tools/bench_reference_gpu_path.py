@@ -66,7 +66,8 @@ def worker(kind, path, l1, l2, reps):
                    note="normals included (the reference always computes them)")
     else:
         from oracle import refbind
-        refbind.LIB_PATH = os.path.join(ROOT, "oracle", "_ref", "libgpvref_refcuda.so" if kind == "reference" else "libgpvref_b200.so")
+        # "emulated": the reference's kernel source executed on the host (oracle/ref_kernels_host.cpp) -- no GPU, checks this tool's plumbing
+        refbind.LIB_PATH = os.path.join(ROOT, "oracle", "_ref", {"reference": "libgpvref_refcuda.so", "compat": "libgpvref_b200.so", "emulated": "libgpvref_emu.so"}[kind])
         refbind._lib = None
         L = refbind.lib()
         L.ref_cuda_path.argtypes = [C.c_void_p]
@@ -92,6 +93,7 @@ def main():
     ap.add_argument("--l1", type=int, default=64)
     ap.add_argument("--l2", type=int, default=4)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--emulated-only", action="store_true", help="no GPU: run the reference's host code on its host-executed kernel source only (plumbing check)")
     ap.add_argument("--worker", default=None)
     ap.add_argument("--path", default=None)
     a = ap.parse_args()
@@ -99,7 +101,7 @@ def main():
         return worker(a.worker, a.path, a.l1, a.l2, a.reps)
     path = mesh_file(a.mesh, tempfile.mkdtemp(prefix="gpvref"))
     rows = {}
-    for kind in ("reference", "compat", "native"):
+    for kind in (("emulated",) if a.emulated_only else ("reference", "compat", "native")):
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", kind, "--path", path, "--l1", str(a.l1), "--l2", str(a.l2), "--reps", str(a.reps)],
                            capture_output=True, text=True)
         line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
@@ -108,7 +110,7 @@ def main():
     summary = {"config": "%s Level1 %d + Level2 %d^3, normals on" % (a.mesh, a.l1, a.l2), "best_seconds": best, "runs": rows}
     if "native" in best:
         summary["speedup_over"] = {k: best[k] / best["native"] for k in best if k != "native"}
-    if all("l1" in v for v in rows.values()):
+    if "native" in rows and all("l1" in v for v in rows.values()):
         summary["states_agree"] = {k: (rows[k]["l1"] == rows["native"]["l1"] and rows[k]["l2"] == rows["native"]["l2"] and rows[k]["counts"] == rows["native"]["counts"])
                                    for k in rows if k != "native"}
     print(json.dumps(summary))
