@@ -2,11 +2,12 @@
 //
 // cuda/CUDAClassifyTessellation.cu holds the three kernels of the reference's operator boundary.  They are plain per-thread
 // code (no shared memory, no barriers; one atomicAdd), so the unmodified kernel source compiles as C++ once the CUDA built-ins
-// exist: oracle/Makefile writes the file's text up to its <<< >>> launch wrappers into oracle/_ref/ref_kernels_host.inc (a
-// build artefact next to the GL shim, never committed), this file supplies threadIdx / blockIdx / blockDim / atomicAdd,
-// includes that text, and re-creates the three extern "C" operators as loops over the thread indices the wrappers would
-// launch (cu:507-540).  A dozen CUDA runtime calls are answered with host memory, so that the reference's UNMODIFIED host code
-// (Object::ClassifyTessellationCUDA, Object::ClassifyInOutTessellationLevel2CUDA) runs against them without a GPU:
+// exist: oracle/Makefile pipes this file to the compiler with the reference file's text up to its <<< >>> launch wrappers
+// spliced in at the marker below (read from $(GPVIEW_REF) where it lies; no copy is written anywhere).  This file supplies
+// threadIdx / blockIdx / blockDim / atomicAdd in front of that text and, behind it, re-creates the three extern "C" operators
+// as loops over the thread indices the wrappers would launch (cu:507-540).  A dozen CUDA runtime calls are answered with host
+// memory, so that the reference's UNMODIFIED host code (Object::ClassifyTessellationCUDA,
+// Object::ClassifyInOutTessellationLevel2CUDA) runs against them without a GPU:
 // oracle/_ref/libgpvref_emu.so = the reference's GPU path, source for source, under g++ -O2 -ffp-contract=off (the strict-IEEE
 // twin of nvcc -fmad=false: + - * / and sqrt round identically).  tests/test_oracle_ref.py compares it with the oracle.
 //
@@ -20,7 +21,7 @@ static dim3 blockDim, gridDim;
 static inline int atomicAdd(int* p, int v) { const int old = *p; *p += v; return old; }
 static inline float atomicAdd(float* p, float v) { const float old = *p; *p += v; return old; }
 
-#include "_ref/ref_kernels_host.inc" // the reference's kernel source, cut in front of its launch wrappers by oracle/Makefile
+// @@REFERENCE_KERNEL_SOURCE@@  oracle/Makefile splices the reference's kernel source in here, on the fly (see the top of this file)
 
 static inline void at(unsigned x, unsigned y)
 {
