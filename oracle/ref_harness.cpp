@@ -179,30 +179,12 @@ double ref_l1_inout_brute_mt(void* h, int nThreads)
 }
 
 // bBox[] initialisation (src/Object.cpp:3165-3193) + Object::ClassifyTessellation (:2256) + L1 normals (:3219-3253).
-double ref_l1_tribox(void* h)
+// L1 normals, restated from PerformVoxelization (src/Object.cpp:3219-3253): the same loop follows the CPU classification and the
+// CUDA one (both leave the triangles of a cell in bBox[].objTriangles).
+static void l1_normals(Object* o)
 {
-	Ref* r = (Ref*)h;
-	Object* o = r->o;
 	VoxelData* vd = o->voxelData;
-	int nx = vd->numDivX, ny = vd->numDivY, nz = vd->numDivZ;
-	float gridSizeX = vd->gridSizeX, gridSizeY = vd->gridSizeY, gridSizeZ = vd->gridSizeZ;
-	size_t N = (size_t)nx*ny*nz;
-	vd->bBox = new BBoxData[N];
-	Float3 boxExtentsLevel1 = Float3(gridSizeX / 2.0, gridSizeY / 2.0, gridSizeZ / 2.0);
-	for (int k = 0; k < nz; k++) for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++) {
-		size_t idx = (size_t)k*ny*nx + (size_t)j*nx + i;
-		float midX = (i + 0.5)*gridSizeX + o->bBoxMin[0];
-		float midY = (j + 0.5)*gridSizeY + o->bBoxMin[1];
-		float midZ = (k + 0.5)*gridSizeZ + o->bBoxMin[2];
-		vd->bBox[idx].midPoint = Float3(midX, midY, midZ);
-		vd->bBox[idx].halfSize = boxExtentsLevel1;
-		vd->bBox[idx].solid = int(vd->level1InOut[idx]) % 2;
-		vd->bBox[idx].intersecting = 0;
-	}
-	double t0 = now();
-	o->ClassifyTessellation(r->gp);
-	double dt = now() - t0;
-	// L1 normals, src/Object.cpp:3219-3253
+	size_t N = (size_t)vd->numDivX * vd->numDivY * vd->numDivZ;
 	for (size_t k = 0; k < N; k++) {
 		int numTri = vd->bBox[k].objTriangles.size();
 		Float3 sumNorm = Float3(0, 0, 0);
@@ -227,6 +209,32 @@ double ref_l1_tribox(void* h)
 			vd->level1Normal[k * 3 + 2] = avgNorm[2];
 		}
 	}
+}
+
+double ref_l1_tribox(void* h)
+{
+	Ref* r = (Ref*)h;
+	Object* o = r->o;
+	VoxelData* vd = o->voxelData;
+	int nx = vd->numDivX, ny = vd->numDivY, nz = vd->numDivZ;
+	float gridSizeX = vd->gridSizeX, gridSizeY = vd->gridSizeY, gridSizeZ = vd->gridSizeZ;
+	size_t N = (size_t)nx*ny*nz;
+	vd->bBox = new BBoxData[N];
+	Float3 boxExtentsLevel1 = Float3(gridSizeX / 2.0, gridSizeY / 2.0, gridSizeZ / 2.0);
+	for (int k = 0; k < nz; k++) for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++) {
+		size_t idx = (size_t)k*ny*nx + (size_t)j*nx + i;
+		float midX = (i + 0.5)*gridSizeX + o->bBoxMin[0];
+		float midY = (j + 0.5)*gridSizeY + o->bBoxMin[1];
+		float midZ = (k + 0.5)*gridSizeZ + o->bBoxMin[2];
+		vd->bBox[idx].midPoint = Float3(midX, midY, midZ);
+		vd->bBox[idx].halfSize = boxExtentsLevel1;
+		vd->bBox[idx].solid = int(vd->level1InOut[idx]) % 2;
+		vd->bBox[idx].intersecting = 0;
+	}
+	double t0 = now();
+	o->ClassifyTessellation(r->gp);
+	double dt = now() - t0;
+	l1_normals(o);
 	r->boxes = true;
 	// reference-equivalent test count = sum of clipped footprints (cuda/CUDAClassifyTessellation.cu:374-378)
 	long tests = 0, hits = 0; int mx = 0;
@@ -465,6 +473,7 @@ int ref_cuda_path(void* h)
 		int again = o->ClassifyTessellationCUDA(r->gp);
 		if (again != 0) return -1;
 	}
+	l1_normals(o);
 	int boundaryVoxelCount = 0;
 	vd->boundaryIndex.clear();
 	for (size_t index = 0; index < N; index++) {

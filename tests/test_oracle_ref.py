@@ -287,13 +287,13 @@ def _restore_ref_lib():
     refbind.LIB_PATH, refbind._lib = os.path.join(os.path.dirname(EMU), "libgpvref.so"), None
 
 
-def _reference_gpu_path_vs_oracle(oracle, L, path, l1, l2):
+def _reference_gpu_path_vs_oracle(oracle, L, path, l1, l2, files_dir=None):
     """Object::ClassifyTessellationCUDA (with its two-pass buffer re-run) + Object::ClassifyInOutTessellationLevel2CUDA on the
     host-executed kernels; the GL solid fill, which cannot run headless, is seeded from the oracle.  Returns the buffer size used."""
     import ctypes as C
     from oracle import refbind
     want = oracle.OracleMesh(path).voxelize(l1, l2, oracle.FILL_CERTIFIED, 4)
-    ro = refbind.RefObject(path)
+    ro = refbind.RefObject(path, obj_id=7)
     ro.setup(l1, l2)
     fill = want.l1_fill_only.astype(np.float32)
     C.memmove(L.ref_level1InOut(ro.h), fill.ctypes.data, fill.nbytes)
@@ -307,20 +307,31 @@ def _reference_gpu_path_vs_oracle(oracle, L, path, l1, l2):
     # in ascending order, which is the oracle's canonical accumulation order, so even these agree bit for bit
     n = ro.level2_normal().reshape(-1, 4)[:, :3].reshape(-1)
     assert np.array_equal((n * np.float32(256.0 / 3.0) + np.float32(127.0)).astype(np.uint8), want.l2_normal), where
+    if files_dir is not None:  # ... and Object::SaveVoxelization behind that path writes the oracle's six files, byte for byte
+        d1, d2 = os.path.join(files_dir, "ref"), os.path.join(files_dir, "ora")
+        for d in (d1, d2):
+            os.makedirs(d)
+        ro.save(d1)
+        want.save(7, d2)
+        names = sorted(os.listdir(d1))
+        assert names == sorted(os.listdir(d2)) and len(names) == 6, where
+        for f in names:
+            assert filecmp.cmp(os.path.join(d1, f), os.path.join(d2, f), shallow=False), (where, f)
     ro.close()
     return used
 
 
 @pytest.mark.skipif(not os.path.exists(EMU), reason="oracle/_ref/libgpvref_emu.so not built")
 @pytest.mark.parametrize("name,l1,l2", [("cessna", 32, 4), ("torus", 24, 8), ("cessna", 64, 4), ("block", 20, 3), ("cad", 16, 5)])
-def test_reference_gpu_path_on_host_executed_kernels_equals_the_oracle(oracle, tmp_path_factory, name, l1, l2):
+def test_reference_gpu_path_on_host_executed_kernels_equals_the_oracle(oracle, tmp_path_factory, tmp_path, name, l1, l2):
     """The last link of the pin: the reference's GPU path SOURCE FOR SOURCE -- its unmodified host code driving its unmodified
     kernel source (cuda/CUDAClassifyTessellation.cu compiled as C++ and run thread by thread, oracle/ref_kernels_host.cpp) --
-    gives the oracle's Level-1 states, boundary list, Level-2 states, counts and Level-2 normals.  So the "kernel form" the
+    gives the oracle's Level-1 states, boundary list, Level-2 states, counts and normals, and Object::SaveVoxelization behind it the
+    oracle's six files byte for byte.  So the "kernel form" the
     oracle restates IS what the reference's kernels compute (under strict IEEE; g++ -ffp-contract=off == nvcc -fmad=false)."""
     path = os.path.join(REF, "files", "cessna.obj") if name == "cessna" else mesh_path(name, tmp_path_factory.getbasetemp())
     try:
-        used = _reference_gpu_path_vs_oracle(oracle, _emu_lib(), path, l1, l2)
+        used = _reference_gpu_path_vs_oracle(oracle, _emu_lib(), path, l1, l2, str(tmp_path))
     finally:
         _restore_ref_lib()
     if name == "cessna":
