@@ -101,3 +101,15 @@ int main(void) {
     for name, cls in mirrors.items():
         assert int(got[name]) == C.sizeof(cls), (name, got[name], C.sizeof(cls))
     assert int(got["GPV_PHASE_COUNT"]) == len(B.PHASES)
+
+
+def test_plain_c_example_builds_and_fails_loudly_without_a_gpu(product):
+    """tools/example_native.c -- the native tier used from C99 exactly as INTEGRATION.md shows -- compiles with -Wall -Wextra against
+    the header, links against the library, reads a mesh with the reference's loader semantics, and (here, without a device)
+    stops at gpv_create with the no-CPU-fallback message instead of computing anything on the host."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tools"), "example_native"])
+    r = subprocess.run([os.path.join(ROOT, "tools", "example_native"), os.path.join(ROOT, "tests", "golden", "meshes", "torus.off"), "32", "4", "/tmp"],
+                       capture_output=True, text=True)
+    assert "576 triangles, Level-1 grid 32 x 32 x 12" in r.stdout
+    if product.lib().gpv_device_count() == 0:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr

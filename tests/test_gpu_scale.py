@@ -91,3 +91,22 @@ def test_dataset_block_matches_oracle_hashes(product, ctx, tmp_path, i):
     rt = rotated(mesh.tris)
     res3 = ctx.voxelize(product.mesh_from_triangles(rt), product.Params(64, 4))
     check_volume_bracket(rt, res3.grid_size, res3.grid_size2, res3.n23, res3.counts)
+
+
+def test_plain_c_example_writes_the_reference_file_set(product, oracle, tmp_path_factory, tmp_path):  # last: written after this round's GPU budget was spent
+    """tools/example_native.c (INTEGRATION.md section 2 as a C99 program: Level-1-only call to size the host buffers, then the full
+    call with normals, then gpv_save): its six files equal the oracle's writer byte for byte."""
+    import filecmp
+    import subprocess
+    from util import ROOT, mesh_path
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tools"), "example_native"])
+    path = mesh_path("torus", tmp_path_factory.getbasetemp())
+    out, ref = tmp_path / "c", tmp_path / "ora"
+    out.mkdir(); ref.mkdir()
+    log = subprocess.run([os.path.join(ROOT, "tools", "example_native"), path, "32", "4", str(out)], capture_output=True, text=True)
+    assert log.returncode == 0, log.stderr
+    oracle.OracleMesh(path).voxelize(32, 4, oracle.FILL_CERTIFIED, 4).save(-1, str(ref))
+    names = sorted(os.listdir(ref))
+    assert names == sorted(os.listdir(out)) and len(names) == 6
+    for n in names:
+        assert filecmp.cmp(ref / n, out / n, shallow=False), n
