@@ -61,14 +61,14 @@ class CGatherDesc(C.Structure):
 
 class CBatchStats(C.Structure):
     _fields_ = [("models_done", C.c_int64), ("models_failed", C.c_int64), ("models_skipped", C.c_int64), ("seconds", C.c_double),
-                ("parse_seconds", C.c_double), ("gpu_seconds", C.c_double), ("save_seconds", C.c_double)]
+                ("parse_seconds", C.c_double), ("gpu_seconds", C.c_double), ("save_seconds", C.c_double), ("level2_resizes", C.c_int64)]
 
 
 # every symbol include/gpview_b200.h declares (tests/test_abi_symbols.py checks the header against this and the .so)
 NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_stream", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh", "gpv_load_mesh_ex",
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
-                  "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
+                  "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_check_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
                   "gpv_gather_create", "gpv_gather_attach", "gpv_gather_attach_local", "gpv_gather_detach", "gpv_gather_result"]
 COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
 
@@ -323,6 +323,13 @@ class Context:
         v = C.c_double()
         _check(lib().gpv_measure_copy_peak(self.h, None, C.byref(v)))
         return v.value
+
+
+def check_voxels(directory, obj_id):
+    """gpv_check_voxels: True when the six-file set is complete (config parses, every stream has the size it implies)."""
+    L = lib()
+    L.gpv_check_voxels.argtypes = [C.c_char_p, C.c_int]
+    return L.gpv_check_voxels(os.fsencode(directory), int(obj_id)) == 0
 
 
 def load_voxels(directory, obj_id):

@@ -852,17 +852,19 @@ extern "C" int CUDAClassifyInOutLevel2(float* tris, float* l2InOut, float* mid, 
 	return 1;
 }
 
+namespace gpv { __device__ float g_maxPart[256 + 1]; } // per-device scratch of THRUSTDeviceFindMax: no allocation per call
+
 extern "C" float THRUSTDeviceFindMax(float* data, int w, int h)
 {
+	// cuda/THRUSTUtilities.cu:44-61: thrust::max_element over w*h floats on the default stream, then a one-element D2H.
 	long long n = (long long)w * h;
-	if (n <= 0) return 0.f;
+	if (n <= 0 || !data) return 0.f;
 	float* part = nullptr;
+	if (cudaGetSymbolAddress((void**)&part, gpv::g_maxPart) != cudaSuccess) return 0.f;
 	const int blocks = 256;
-	if (cudaMalloc(&part, (blocks + 1) * sizeof(float)) != cudaSuccess) return 0.f;
 	k_max_reduce<<<blocks, 256>>>(data, n, part);
 	k_max_reduce<<<1, 256>>>(part, blocks, part + blocks);
 	float r = 0.f;
-	cudaMemcpy(&r, part + blocks, sizeof(float), cudaMemcpyDeviceToHost);
-	cudaFree(part);
+	if (cudaMemcpy(&r, part + blocks, sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return 0.f;
 	return r;
 }

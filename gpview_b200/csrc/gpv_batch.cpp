@@ -5,7 +5,7 @@
 // buffers and stream), pinned staging buffers and file I/O, pulls paths from a shared counter: parse -> gpv_voxelize_host
 // -> gpv_save.  Contexts on the same device overlap each other's kernels, copies and host work; devices are assigned
 // round-robin, so one call drives every GPU of the box (models are independent: no collective).
-// Restartable: with skip_existing, a model whose VoxelConfig file is already there is not recomputed.
+// Restartable: with skip_existing, a model whose six-file set is complete (gpv_check_voxels) is not recomputed.
 #include "../../include/gpview_b200.h"
 #include "gpv_internal.h"
 #include <algorithm>
@@ -16,7 +16,6 @@
 #include <string>
 #include <thread>
 #include <vector>
-#include <sys/stat.h>
 
 namespace {
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -32,7 +31,7 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
                                   const char* out_dir, int first_obj_id, int skip_existing, gpv_batch_stats* stats)
 {
 	if (!paths || n_paths <= 0 || !params || n_devices <= 0 || threads <= 0) return gpv::fail("gpv_voxelize_batch: bad arguments");
-	std::atomic<int64_t> next(0), done(0), failed(0), skipped(0);
+	std::atomic<int64_t> next(0), done(0), failed(0), skipped(0), resizes(0);
 	std::mutex errMu;
 	std::string firstErr;
 	double tParse = 0, tGpu = 0, tSave = 0;
@@ -47,11 +46,9 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
 			const int64_t i = next.fetch_add(1);
 			if (i >= n_paths) break;
 			const int objID = first_obj_id + (int)i;
-			if (skip_existing && out_dir) {
-				struct stat sb;
-				std::string cfg = std::string(out_dir) + "/Obj" + std::to_string(objID) + "VoxelConfig.txt";
-				if (stat(cfg.c_str(), &sb) == 0 && sb.st_size > 0) { skipped++; continue; }
-			}
+			// restart: a model is skipped only when its set is COMPLETE -- the config parses and every stream has the size it implies
+			// (gpv_check_voxels; gpv_save_streams writes the config last, so a killed run leaves none)
+			if (skip_existing && out_dir && gpv_check_voxels(out_dir, objID) == 0) { skipped++; continue; }
 			auto bail = [&]() { failed++; std::lock_guard<std::mutex> g(errMu); if (firstErr.empty()) firstErr = std::string(paths[i]) + ": " + gpv_last_error(); };
 			double a = now();
 			gpv_mesh mesh;
@@ -81,6 +78,7 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
 					gpv_host_streams none{};
 					if (gpv_voxelize_host(ctx, &mesh, &p1, gpv_stream(ctx), &res, &none)) break;
 					capB = res.n_boundary + 16;
+					resizes++;
 				}
 			}
 			if (!ok) bail(); else done++;
@@ -94,7 +92,7 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
 	for (int w = 0; w < threads; w++) pool.emplace_back(worker, w);
 	for (auto& t : pool) t.join();
 	if (stats) {
-		stats->models_done = done; stats->models_failed = failed; stats->models_skipped = skipped;
+		stats->models_done = done; stats->models_failed = failed; stats->models_skipped = skipped; stats->level2_resizes = resizes;
 		stats->seconds = now() - t0; stats->parse_seconds = tParse; stats->gpu_seconds = tGpu; stats->save_seconds = tSave;
 	}
 	if (failed > 0 || (done == 0 && skipped == 0)) return gpv::fail(firstErr.empty() ? "gpv_voxelize_batch: no model processed" : firstErr);

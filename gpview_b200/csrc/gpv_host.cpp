@@ -22,6 +22,7 @@
 #include <thread>
 #include <vector>
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 namespace {
@@ -717,21 +718,11 @@ extern "C" int gpv_save_streams(const gpv_mesh* mesh, const gpv_result* res, con
 	const gpv_grid& g = res->grid;
 	const bool l2 = h->level2_inout != nullptr;
 	std::string prefix = std::string(dir) + "/Obj" + std::to_string(obj_id);
-	FILE* f = fopen((prefix + "VoxelConfig.txt").c_str(), "w");
-	if (!f) return gpv::fail("Unable to open output file for writing"); // the reference abort()s (:2988-2992)
-	fprintf(f, "Obj%d\n", obj_id);
-	fprintf(f, "%g\t%g\t%g\n", mesh->bbox_min[0], mesh->bbox_min[1], mesh->bbox_min[2]);
-	fprintf(f, "%g\t%g\t%g\n", mesh->bbox_max[0], mesh->bbox_max[1], mesh->bbox_max[2]);
-	fprintf(f, "%d\t%d\t%d\n", g.num_div[0], g.num_div[1], g.num_div[2]);
-	fprintf(f, "%g\t%g\t%g\n", g.grid_size[0], g.grid_size[1], g.grid_size[2]);
-	fprintf(f, "%lld\n%lld\n", (long long)res->l1_inside, (long long)res->l1_boundary);
-	if (l2) {
-		fprintf(f, "%d\t%d\t%d\n", g.n2, g.n2, g.n2);
-		fprintf(f, "%g\t%g\t%g\n", g.grid_size2[0], g.grid_size2[1], g.grid_size2[2]);
-		fprintf(f, "%lld\n%lld\n", (long long)res->l2_inside, (long long)res->l2_boundary);
-	}
-	const bool cfgBad = ferror(f) != 0;
-	if (fclose(f) != 0 || cfgBad) return gpv::fail("write error on " + prefix + "VoxelConfig.txt");
+	// ObjNVoxelConfig.txt is what marks a set as complete (gpv_voxelize_batch's skip_existing, gpv_load_voxels, the Dataset): it is
+	// written LAST, to a temporary name, and renamed into place only after every stream has been written and closed.  A run that is
+	// killed or hits a full disk leaves no config behind, so a restart recomputes the model instead of skipping a truncated set.
+	const std::string cfgPath = prefix + "VoxelConfig.txt", cfgTmp = cfgPath + ".tmp";
+	unlink(cfgPath.c_str()); // a stale config of an earlier run must not vouch for the streams that are about to be rewritten
 	// The streams: small sets (a dataset model: a few MB) are written by the calling thread; large ones (cessna 256 / 16 with
 	// normals: 0.9 GB) are cut into 8 MB pieces written with pwrite() by a few threads, so that the five files fill side by side.
 	// (Buffered writes to ONE file are serialised by the kernel's inode lock: the largest stream -- Level2Normal, 3/4 of the bytes
@@ -785,7 +776,24 @@ extern "C" int gpv_save_streams(const gpv_mesh* mesh, const gpv_result* res, con
 	}
 	for (int k = 0; k < nStreams; k++)
 		if (st[k].fd >= 0 && close(st[k].fd) != 0 && failed.empty()) failed = "write error on " + prefix + st[k].name;
-	return failed.empty() ? 0 : gpv::fail(failed);
+	if (!failed.empty()) return gpv::fail(failed);
+	FILE* f = fopen(cfgTmp.c_str(), "w");
+	if (!f) return gpv::fail("Unable to open output file for writing: " + cfgPath); // the reference abort()s (:2988-2992)
+	fprintf(f, "Obj%d\n", obj_id);
+	fprintf(f, "%g\t%g\t%g\n", mesh->bbox_min[0], mesh->bbox_min[1], mesh->bbox_min[2]);
+	fprintf(f, "%g\t%g\t%g\n", mesh->bbox_max[0], mesh->bbox_max[1], mesh->bbox_max[2]);
+	fprintf(f, "%d\t%d\t%d\n", g.num_div[0], g.num_div[1], g.num_div[2]);
+	fprintf(f, "%g\t%g\t%g\n", g.grid_size[0], g.grid_size[1], g.grid_size[2]);
+	fprintf(f, "%lld\n%lld\n", (long long)res->l1_inside, (long long)res->l1_boundary);
+	if (l2) {
+		fprintf(f, "%d\t%d\t%d\n", g.n2, g.n2, g.n2);
+		fprintf(f, "%g\t%g\t%g\n", g.grid_size2[0], g.grid_size2[1], g.grid_size2[2]);
+		fprintf(f, "%lld\n%lld\n", (long long)res->l2_inside, (long long)res->l2_boundary);
+	}
+	const bool cfgBad = ferror(f) != 0;
+	if (fclose(f) != 0 || cfgBad) { unlink(cfgTmp.c_str()); return gpv::fail("write error on " + cfgPath); }
+	if (rename(cfgTmp.c_str(), cfgPath.c_str()) != 0) { unlink(cfgTmp.c_str()); return gpv::fail("cannot rename " + cfgTmp + " into place"); }
+	return 0;
 }
 
 // ---- reader of the six-file set.  The reference can only read back one hard-coded 48x64x64 uchar grid
@@ -861,10 +869,10 @@ extern "C" void gpv_free_voxels(gpv_voxel_file* v)
 	v->prefix_sum = nullptr;
 }
 
-extern "C" int gpv_load_voxels(const char* dir, int obj_id, gpv_voxel_file* v)
+// ObjNVoxelConfig.txt -> the scalar fields of gpv_voxel_file (no stream is touched)
+static int read_voxel_config(const std::string& prefix, gpv_voxel_file* v)
 {
 	memset(v, 0, sizeof *v);
-	const std::string prefix = std::string(dir) + "/Obj" + std::to_string(obj_id);
 	FILE* f = fopen((prefix + "VoxelConfig.txt").c_str(), "r");
 	if (!f) return gpv::fail("Unable to open " + prefix + "VoxelConfig.txt");
 	long long a = 0, b = 0;
@@ -881,6 +889,34 @@ extern "C" int gpv_load_voxels(const char* dir, int obj_id, gpv_voxel_file* v)
 	v->cells = (int64_t)v->num_div[0] * v->num_div[1] * v->num_div[2];
 	v->n_boundary = v->l1_boundary;
 	v->n23 = v->has_level2 ? (int64_t)v->num_div2[0] * v->num_div2[1] * v->num_div2[2] : 0;
+	return 0;
+}
+
+// Is the set ObjN* in `dir` complete?  The config parses and every stream it implies is there with exactly the size it implies
+// (the normal streams may be absent -- GPV_SAVE_COMPUTED_ONLY -- but not truncated).  Nothing is read but the config: this is the
+// restart test of gpv_voxelize_batch (skip_existing) and of the Dataset's directory listing.
+extern "C" int gpv_check_voxels(const char* dir, int obj_id)
+{
+	if (!dir) return gpv::fail("gpv_check_voxels: null directory");
+	gpv_voxel_file v;
+	const std::string prefix = std::string(dir) + "/Obj" + std::to_string(obj_id);
+	if (read_voxel_config(prefix, &v)) return 1;
+	auto sized = [&](const char* suffix, int64_t bytes, bool required) -> int {
+		struct stat sb;
+		if (stat((prefix + suffix).c_str(), &sb) != 0) return required ? gpv::fail(prefix + suffix + ": missing") : 0;
+		return (int64_t)sb.st_size == bytes ? 0 : gpv::fail(prefix + suffix + ": not the size ObjNVoxelConfig.txt implies");
+	};
+	if (sized("Level1InOut.raw", v.cells, true) || sized("Level1Normal.raw", v.cells * 3, false)) return 1;
+	if (v.has_level2 && (sized("Level1BoundaryPrefixSum.raw", v.cells * 4, true) || sized("Level2InOut.raw", v.n_boundary * v.n23, true) ||
+	                     sized("Level2Normal.raw", v.n_boundary * v.n23 * 3, false)))
+		return 1;
+	return 0;
+}
+
+extern "C" int gpv_load_voxels(const char* dir, int obj_id, gpv_voxel_file* v)
+{
+	const std::string prefix = std::string(dir) + "/Obj" + std::to_string(obj_id);
+	if (read_voxel_config(prefix, v)) return 1;
 	auto grab = [&](const char* suffix, size_t bytes, void** dst, bool required) -> int {
 		*dst = malloc(bytes ? bytes : 1);
 		if (!*dst) return gpv::fail("out of host memory");

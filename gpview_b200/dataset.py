@@ -16,11 +16,12 @@ from . import binding as B
 
 
 def list_object_ids(directory):
-    """Object ids of the complete sets in `directory` (those that have an ObjNVoxelConfig.txt), ascending."""
+    """Object ids of the COMPLETE sets in `directory`, ascending: an ObjNVoxelConfig.txt that parses and every stream it implies
+    present with the size it implies (gpv_check_voxels) -- a truncated set of an interrupted run is not listed."""
     ids = []
     for name in os.listdir(directory):
         m = re.fullmatch(r"Obj(-?\d+)VoxelConfig\.txt", name)
-        if m:
+        if m and B.check_voxels(directory, int(m.group(1))):
             ids.append(int(m.group(1)))
     return sorted(ids)
 

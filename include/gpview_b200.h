@@ -222,6 +222,10 @@ typedef struct {
 	uint8_t* level1_inout; uint8_t* level1_normal; int32_t* prefix_sum; uint8_t* level2_inout; uint8_t* level2_normal;
 } gpv_voxel_file;
 int gpv_load_voxels(const char* dir, int obj_id, gpv_voxel_file* out);
+/* 0 if the set ObjN* in `dir` is complete: ObjNVoxelConfig.txt parses and every stream it implies exists with exactly the size
+ * it implies (normal streams may be absent, not truncated).  Reads nothing but the config.  gpv_save_streams writes the streams
+ * first and renames the config into place last, so an interrupted run never leaves a set that passes this test. */
+int gpv_check_voxels(const char* dir, int obj_id);
 void gpv_free_voxels(gpv_voxel_file* v);
 
 /* The two-level result as one dense grid at the effective resolution (num_div[a] * n2 per axis, z-major, file encoding 0/127/254):
@@ -232,11 +236,12 @@ int gpv_expand_dense(const uint8_t* level1_inout, const int32_t* prefix, const u
 
 /* Batched dataset generation (BASELINE.json config 5): `threads` host threads, each with its own ctx on devices[w % n_devices],
  * pull paths from a shared queue: load -> gpv_voxelize_host -> gpv_save(out_dir, obj id = first_obj_id + index).  out_dir NULL:
- * nothing is written.  skip_existing: a model whose ObjNVoxelConfig.txt exists is skipped (restartable).  The *_seconds are
+ * nothing is written.  skip_existing: a model whose set is complete (gpv_check_voxels) is skipped (restartable).  The *_seconds are
  * summed over threads.  Returns non-zero if any model failed (message of the first failure in gpv_last_error()). */
 typedef struct {
 	int64_t models_done, models_failed, models_skipped;
 	double seconds, parse_seconds, gpu_seconds, save_seconds;
+	int64_t level2_resizes;    /* models whose Level-2 host buffer had to grow: sized from a Level-1-only run, then voxelized again */
 } gpv_batch_stats;
 int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, const gpv_params* params, const int* devices, int n_devices, int threads,
                        const char* out_dir, int first_obj_id, int skip_existing, gpv_batch_stats* stats);

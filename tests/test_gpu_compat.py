@@ -47,3 +47,33 @@ def test_reference_host_code_runs_on_the_product_operators(product, oracle, tmp_
     ro.close()
     refbind.LIB_PATH = os.path.join(ROOT, "oracle", "_ref", "libgpvref.so")
     refbind._lib = None
+
+
+@pytest.mark.parametrize("n,w", [(1, 1), (7, 7), (255, 5), (256, 16), (65537, 257), (1 << 22, 2048), (3 * 1000 * 1000 + 1, 1)])
+def test_thrust_device_find_max_equals_numpy(product, n, w):
+    """THRUSTDeviceFindMax (cuda/THRUSTUtilities.cu:44-61: thrust::max_element over w*h device floats + one-element read-back), the
+    fourth device symbol the reference's host code links against -- hand-written reduction, no Thrust: against np.max on random
+    data, all-negative data (the identity must not be 0), a maximum in the last element, and +inf."""
+    L = product.lib()
+    L.THRUSTDeviceFindMax.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.THRUSTDeviceFindMax.restype = C.c_float
+    h = n // w
+    n = w * h
+    rng = np.random.default_rng(n)
+    cases = [rng.standard_normal(n).astype(np.float32) * 1e3, -np.abs(rng.standard_normal(n)).astype(np.float32) - 1.0,
+             np.zeros(n, np.float32), np.full(n, -3.0e38, np.float32)]
+    cases[2][-1] = 5.5
+    if n > 3:
+        big = rng.standard_normal(n).astype(np.float32)
+        big[n // 3] = np.inf
+        cases.append(big)
+    d = L.gpv_alloc_device(n * 4)
+    assert d
+    try:
+        for a in cases:
+            assert L.gpv_memcpy_h2d(d, a.ctypes.data, a.nbytes, None) == 0 and L.gpv_stream_sync(None) == 0
+            got = L.THRUSTDeviceFindMax(d, w, h)
+            assert np.float32(got) == a.max(), (n, got, a.max())
+        assert L.THRUSTDeviceFindMax(d, 0, 5) == 0.0   # empty range: the reference dereferences end(); we return 0
+    finally:
+        L.gpv_free_device(d)

@@ -227,6 +227,51 @@ def test_voxel_files_round_trip(product, oracle, tmp_path_factory, tmp_path):
         B.load_voxels(str(d2), 9)
 
 
+def test_interrupted_save_leaves_no_config_and_check_voxels_sees_truncation(product, oracle, tmp_path_factory, tmp_path):
+    """ObjNVoxelConfig.txt is the completeness marker (batch restart, Dataset listing): gpv_save_streams writes it LAST, by
+    rename, and removes a stale one first -- a save that fails on a stream leaves no config; gpv_check_voxels accepts only sets
+    whose streams have exactly the sizes the config implies (a truncated stream of a killed run is not 'complete')."""
+    from gpview_b200 import binding as B
+    from gpview_b200 import dataset
+    path = mesh_path("block", tmp_path_factory.getbasetemp())
+    pm = product.load_mesh(path)
+    r = oracle.OracleMesh(path).voxelize(16, 2, oracle.FILL_CERTIFIED, 2)
+    res = B.CResult()
+    res.grid = product.grid_for(pm.bbox_min, pm.bbox_max, pm.max_model_size, 16, 2)
+    res.cells, res.n_boundary, res.n23 = r.cells, r.nb, r.n23
+    res.l1_inside, res.l1_boundary, res.l2_inside, res.l2_boundary = r.counts
+    l1 = (r.l1_state * 127).astype(np.uint8); l2 = (r.l2_state * 127).astype(np.uint8)
+    hs = B.CHostStreams(l1.ctypes.data, r.prefix.ctypes.data, None, l2.ctypes.data, None, None, l2.nbytes, 0)
+
+    class R:
+        c = res
+    d = tmp_path / "set"
+    d.mkdir()
+    assert not B.check_voxels(str(d), 7)
+    B.save(pm, R, hs, 7, str(d), omit_absent=True)
+    assert B.check_voxels(str(d), 7) and dataset.list_object_ids(str(d)) == [7]
+    assert not [n for n in os.listdir(d) if n.endswith(".tmp")]
+    # a later save of the same id that cannot open a stream (a directory sits where Level2InOut.raw belongs): error, and the
+    # config of the earlier, complete run is gone too -- it must not vouch for streams that were being rewritten
+    os.remove(d / "Obj7Level2InOut.raw")
+    os.mkdir(d / "Obj7Level2InOut.raw")
+    with pytest.raises(product.GpvError):
+        B.save(pm, R, hs, 7, str(d), omit_absent=True)
+    assert not os.path.exists(d / "Obj7VoxelConfig.txt") and not B.check_voxels(str(d), 7) and dataset.list_object_ids(str(d)) == []
+    os.rmdir(d / "Obj7Level2InOut.raw")
+    B.save(pm, R, hs, 7, str(d), omit_absent=True)
+    assert B.check_voxels(str(d), 7)
+    # truncated stream (what a killed run or a full disk leaves when an OLD writer put the config first)
+    with open(d / "Obj7Level2InOut.raw", "r+b") as f:
+        f.truncate(l2.nbytes - 1)
+    assert not B.check_voxels(str(d), 7) and "size" in product.lib().gpv_last_error().decode()
+    assert dataset.list_object_ids(str(d)) == []
+    with open(d / "Obj7Level2InOut.raw", "ab") as f:
+        f.write(b"\0")
+    os.remove(d / "Obj7Level1BoundaryPrefixSum.raw")
+    assert not B.check_voxels(str(d), 7) and "missing" in product.lib().gpv_last_error().decode()
+
+
 # ------------------------------------------------------------------------------------------------ number fields of the loaders
 @pytest.fixture(scope="module")
 def parse_probe():
