@@ -239,7 +239,9 @@ def main():
         dist.broadcast(t, 0)
         desc = B.CGatherDesc.from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
         ctx.gather_attach(desc, rank, world)
-    params = gpv.Params(args.l1, args.l2, gpv.GPV_PROFILE | (gpv.GPV_GATHER if peer else 0), z0, z1)  # CUDA events around every kernel, on the launching stream
+    # peer gather: the library shares the work out itself (Level-1 bytes by equal z-slabs, Level-2 by interleaved column groups); the
+    # cost-balanced z cuts above are what the NCCL gather and the e2e leg use
+    params = gpv.Params(args.l1, args.l2, gpv.GPV_PROFILE | (gpv.GPV_GATHER if peer else 0), 0 if peer else z0, 0 if peer else z1)  # CUDA events around every kernel, on the launching stream
     gathered = {}
 
     def step():
@@ -262,8 +264,8 @@ def main():
     for _ in range(args.warmup):
         res = step()
     barrier()
-    if world > 1:
-        # Untimed load balancing: the a-priori cost model only knows list lengths.  Rescale every slab's layer costs to the device
+    if world > 1 and not peer:
+        # Untimed load balancing (NCCL gather of z-slabs only): the a-priori cost model only knows list lengths.  Rescale every slab's layer costs to the device
         # time its rank measured (every phase but the final wait for the other ranks), re-cut, repeat; keep the best cuts seen.
         # Every rank derives the same cuts from the all-gathered times (no data moves).
         layer = layer0 + 1e-9
@@ -350,6 +352,13 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tests_local)
     ms_per_step = float(ms.item()) / args.steps
+    phase_per_rank = None
+    if world > 1:  # every rank's own phase times (CUDA events on its stream), so that the scaling line shows where each rank's step goes
+        mine = {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0}
+        mine["step_ms"] = round(sum(a.elapsed_time(b) for a, b in ev) / args.steps, 4)
+        mine["l2_cells"] = int(res.n_refined)
+        phase_per_rank = [None] * world
+        dist.all_gather_object(phase_per_rank, mine)
     tests = float(tests_local.item()) + res.stats["l1_box_tests"]  # Level-1 tests are replicated: counted once
     value = tests / (ms_per_step * 1e-3) / 1e9
 
@@ -485,11 +494,13 @@ def main():
         line = {"metric": "G tri-box tests/s", "value": value, "unit": "G tri-box tests/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "ms_per_model": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "cessna.obj fixture (reference sample mesh)" if args.mesh == "cessna" else "synthetic",
-                "config": dict(workload_config(args), parallelism=("z-slabs x%d (cuts %s), Level-1 replicated, %s; gathered streams == single-GPU result: %s" % (world, cuts, "slabs written into rank 0's buffers over NVLink peer memory from inside the kernels (GPV_GATHER), 8-byte count exchange through a mailbox, no collective" if peer else "NCCL send/recv gather to rank 0", gather_ok)) if world > 1 else "1 GPU",
+                "config": dict(workload_config(args), parallelism=("%d ranks, Level-1 replicated, %s; gathered streams == single-GPU result: %s" % (world, "Level-1 bytes / prefix sums by equal z-slabs, Level-2 refinement by interleaved Level-1 column groups, every rank writing its share into rank 0's buffers over NVLink peer memory from inside the kernels (GPV_GATHER): no collective, no exchange step, completion flags through a mailbox" if peer else "z-slabs (cuts %s), NCCL send/recv gather to rank 0" % cuts, gather_ok)) if world > 1 else "1 GPU",
                                tri_box_tests_per_model=int(tests), triangles=mesh.ntri, grid=[int(x) for x in res.num_div]),
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_rays": roof_rays, "roofline_hbm": roof_hbm, "roofline_phases": per_phase,
                 "phase_ms": {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0},
                 "counts": {"l1_inside": whole.counts[0], "l1_boundary": whole.counts[1]}}
+        if phase_per_rank is not None:
+            line["phase_ms_per_rank"] = phase_per_rank
         if world == 1 and not args.no_cpu_baseline and path is not None:
             line["cpu_baseline"] = cpu_baseline(path, args.l1, args.l2, os.cpu_count() or 1)
         print(json.dumps(line))

@@ -35,7 +35,7 @@ class CResult(C.Structure):
                 ("d_level1_normal", C.c_void_p), ("d_level2_normal", C.c_void_p), ("d_cell_off", C.c_void_p), ("d_cell_tris", C.c_void_p),
                 ("d_col_off", C.c_void_p), ("d_col_count", C.c_void_p), ("d_col_tris", C.c_void_p)] + [(k, C.c_int64) for k in (
                     "l1_inside", "l1_boundary", "l2_inside", "l2_boundary", "l1_box_tests", "l1_box_hits", "l2_box_tests", "l2_ray_tests",
-                    "tri_total", "fill_crossings", "fill_ill_conditioned", "kernel_launches")] + [("phase_ms", C.c_float * 16)]
+                    "tri_total", "fill_crossings", "fill_ill_conditioned", "kernel_launches")] + [("phase_ms", C.c_float * 16), ("n_refined", C.c_int64)]
 
 
 PHASES = ["setup", "bin_count", "cross_count", "scan", "host_gap", "bin_fill", "cross_fill", "sort", "fill_sweep", "l1_normals", "l2_rays", "l2", "l2_normals"]
@@ -69,7 +69,7 @@ NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destr
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
                   "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_check_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
-                  "gpv_gather_create", "gpv_gather_attach", "gpv_gather_attach_local", "gpv_gather_detach", "gpv_gather_result"]
+                  "gpv_gather_create", "gpv_gather_attach", "gpv_gather_attach_local", "gpv_gather_detach", "gpv_gather_set_timeout", "gpv_gather_result"]
 COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
 
 _lib = None
@@ -118,6 +118,7 @@ def lib():
         L.gpv_gather_attach.argtypes = [vp, C.POINTER(CGatherDesc), C.c_int, C.c_int]
         L.gpv_gather_attach_local.argtypes = [vp, vp, C.c_int, C.c_int]
         L.gpv_gather_detach.argtypes = [vp]; L.gpv_gather_detach.restype = None
+        L.gpv_gather_set_timeout.argtypes = [vp, C.c_double]
         L.gpv_gather_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
         _lib = L
     return _lib
@@ -202,6 +203,7 @@ class Result:
         self.grid_size2 = np.array(list(g.grid_size2), np.float32)
         self.n2, self.cells, self.nb, self.n23 = int(g.n2), int(cres.cells), int(cres.n_boundary), int(cres.n23)
         self.z0, self.z1 = int(cres.z0), int(cres.z1)
+        self.n_refined = int(cres.n_refined)
         self.counts = [int(cres.l1_inside), int(cres.l1_boundary), int(cres.l2_inside), int(cres.l2_boundary)]
         self.stats = {k: int(getattr(cres, k)) for k in ("l1_box_tests", "l1_box_hits", "l2_box_tests", "l2_ray_tests", "tri_total", "fill_crossings",
                                                          "fill_ill_conditioned", "kernel_launches")}

@@ -80,6 +80,7 @@ struct gpv_ctx {
 		unsigned epoch = 0;
 		uint8_t* l1 = nullptr; int32_t* prefix = nullptr; uint8_t* l2 = nullptr; gpv::GatherMail* mail = nullptr;
 		int64_t cellsTotal = 0, l2Cap = 0, nbTotal = 0;
+		unsigned long long timeoutNs = gpv::kGatherTimeoutNsDefault;
 	} gather;
 	gpv::DevBuf gatherL1, gatherPrefix, gatherL2, gatherMail;
 };
@@ -108,7 +109,7 @@ static int preload_kernels()
 	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals);
 	GPV_LOAD(k_l2<16, false>); GPV_LOAD(k_l2<8, false>); GPV_LOAD(k_l2<4, false>); GPV_LOAD(k_l2<2, false>); GPV_LOAD(k_l2<0, false>);
 	GPV_LOAD(k_l2<16, true>); GPV_LOAD(k_l2<8, true>); GPV_LOAD(k_l2<4, true>); GPV_LOAD(k_l2<2, true>); GPV_LOAD(k_l2<0, true>);
-	GPV_LOAD(k_gather_exchange); GPV_LOAD(k_gather_prefix); GPV_LOAD(k_gather_done); GPV_LOAD(k_gather_wait);
+	GPV_LOAD(k_gather_begin); GPV_LOAD(k_gather_prefix); GPV_LOAD(k_gather_done); GPV_LOAD(k_gather_wait);
 #undef GPV_LOAD
 	return 0;
 }
@@ -248,6 +249,15 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	g.z0 = 0; g.z1 = g.nz;
 	if (prm->z1 > 0) { g.z0 = prm->z0; g.z1 = prm->z1; }
 	if (g.z0 < 0 || g.z1 > g.nz || g.z0 >= g.z1) return fail("gpv_voxelize_device: bad z-slab");
+	// GPV_GATHER: every rank runs Level 1 over the WHOLE grid (global boundary ranks, whole column lists); [oz0,oz1) is only the slab of
+	// Level-1 bytes / prefix sums this rank delivers (default: an equal share of the layers), the Level-2 work is shared out by column (Own)
+	int oz0 = g.z0, oz1 = g.z1;
+	Own own{ 1, 0, 1 };
+	if (gather) {
+		if (prm->z1 <= 0) { oz0 = (int)((long long)g.nz * c->gather.rank / c->gather.world); oz1 = (int)((long long)g.nz * (c->gather.rank + 1) / c->gather.world); }
+		g.z0 = 0; g.z1 = g.nz;
+		own.world = c->gather.world; own.rank = c->gather.rank; own.group = std::max(1, 256 / (gg.n2 * gg.n2)); // = the columns one CTA of k_l2_rays walks
+	}
 	g.minx = bmin[0]; g.miny = bmin[1]; g.minz = bmin[2]; g.maxx = bmax[0]; g.maxy = bmax[1]; g.maxz = bmax[2];
 	g.gsx = gg.grid_size[0]; g.gsy = gg.grid_size[1]; g.gsz = gg.grid_size[2];
 	g.h1x = gg.ext1[0]; g.h1y = gg.ext1[1]; g.h1z = gg.ext1[2];
@@ -258,6 +268,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	if (ncol * g.nz > 0x7fffffffLL) return fail("grid exceeds 2^31 cells: boundary_index is int32 (file contract); shard finer");
 	if (g.nx > 32767 || g.ny > 32767 || g.nz > 32767) return fail("grid axis exceeds 32767 cells (footprints are packed in 16-bit fields)");
 	if (gather && ncol * g.nz != c->gather.cellsTotal) return fail("GPV_GATHER: the gather buffers were created for a different grid");
+	if (gather && oz1 > oz0 && ((long long)oz0 * ncol) % 8 != 0) return fail("GPV_GATHER: slab offset is not a multiple of 8 cells"); // cannot happen: nx, ny are multiples of 4
 	const unsigned epoch = gather ? ++c->gather.epoch : 0; // every rank counts its GPV_GATHER calls: same order on all ranks
 	const int nTri = (int)n_tri;
 	int64_t launches = 0;
@@ -350,7 +361,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		io.tileCounter = reinterpret_cast<unsigned*>(c->desc.as<char>() + dOff[2]); io.desc = reinterpret_cast<unsigned long long*>(c->desc.as<char>() + dOff[2]) + 1;
 		io.prefix = c->prefix.as<int>(); io.boundaryIndex = c->boundaryIndex.as<int>(); io.bTriOff = c->bTriOff.as<unsigned>();
 		io.bmask = c->bmask.as<unsigned char>(); io.globalBase = (long long)g.z0 * ncol; io.totals = dT;
-		io.colCells = c->colCellCnt.as<int>(); io.plane = ncol;
+		io.colCells = c->colCellCnt.as<int>(); io.plane = ncol; io.own = own;
 		if (V == 4) k_scan<MODE_CELLS, 4><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
 		else k_scan<MODE_CELLS, 1><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
 		launches++;
@@ -359,7 +370,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	{
 		const ScanReq r[3] = { { c->colCount.as<int>(), ncol, c->colOff.as<unsigned>(), &dT->colTotalOver, nullptr, dOff[3] },
 			                   { c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, nullptr, dOff[4] },
-			                   { c->colCellCnt.as<int>(), ncol, c->colCellOff.as<unsigned>(), nullptr, nullptr, dOff[5] } };
+			                   { c->colCellCnt.as<int>(), ncol, c->colCellOff.as<unsigned>(), &dT->nLocalCells, nullptr, dOff[5] } };
 		launch_scans(c, st, r, wantL2 ? 3 : 2, launches);
 	}
 
@@ -387,8 +398,10 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	bo.colOff = c->colOff.as<unsigned>(); bo.colTris = c->colTris.as<int>(); bo.colCursor = c->colCursor.as<int>();
 	bo.bits = c->binBits.as<unsigned>() + bitsCap / 32; // the fill sweep's own bitmap
 	if (c->longList.ensure((size_t)(nB + ncol) * 4 + 64)) return 1; // (every allocation of the call happens before the exchange and the fork: a growing pool's cudaFree synchronises the device)
-	if (gather) { // the one exchange step: boundary counts of the lower slabs (8 bytes per rank through the mailbox)
-		k_gather_exchange<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, wantL2 ? c->gather.l2Cap / n23 : (long long)0x7fffffff, dT);
+	if (gather) {
+		// every rank sees the same global boundary count: a gather buffer that is too small is refused by all of them, before anything is written
+		if (wantL2 && nB * n23 > c->gather.l2Cap) return fail("GPV_GATHER: Level-2 gather buffer too small for the boundary cells of the grid");
+		k_gather_begin<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, c->gather.timeoutNs, dT); // peers wait here until rank 0 has entered this call
 		launches++;
 	}
 	if (sink) {
@@ -405,12 +418,16 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	mark_side(GPV_PHASE_CROSS_FILL, false);
 	mark_side(GPV_PHASE_FILL_SWEEP, true);
 	{
-		dim3 grid((g.nx + 31) / 32, g.ny, (g.z1 - g.z0 + 127) / 128), block(32, 4);
-		k_fill_sweep<<<grid, block, 0, side>>>(ray48, g, cx, cy, cz, c->crossOff.as<unsigned>(), c->crossTri.as<int>(), c->bmask.as<unsigned char>(),
-		                                       gather ? c->gather.l1 + (size_t)g.z0 * ncol : c->l1State.as<unsigned char>(), dT);
+		GridP gs = g; // the slab of Level-1 bytes this call delivers ([oz0,oz1) with GPV_GATHER, the call's slab otherwise)
+		gs.z0 = oz0; gs.z1 = oz1;
+		const size_t slabOff = gather ? (size_t)oz0 * ncol : 0; // offset of the slab inside the whole-grid arrays of a gathering call
+		dim3 grid((g.nx + 31) / 32, g.ny, (oz1 - oz0 + 127) / 128), block(32, 4);
+		k_fill_sweep<<<grid, block, 0, side>>>(ray48, gs, cx, cy, cz, c->crossOff.as<unsigned>(), c->crossTri.as<int>(), c->bmask.as<unsigned char>() + slabOff / 8,
+		                                       gather ? c->gather.l1 + slabOff : c->l1State.as<unsigned char>(), dT);
 		launches += 2;
-		if (gather) { // slab-local prefix sums + boundary cells of the lower slabs -> their final place on the gathering rank
-			k_gather_prefix<<<(unsigned)std::min<long long>(c->smCount * 8, (cells / 4 + 255) / 256 + 1), 256, 0, side>>>(c->prefix.as<int>(), c->gather.prefix + (size_t)g.z0 * ncol, cells, dT);
+		if (gather) { // this slab of the (global) prefix sums -> its final place on the gathering rank
+			const long long n = (long long)(oz1 - oz0) * ncol;
+			k_gather_prefix<<<(unsigned)std::min<long long>(c->smCount * 8, (n / 4 + 255) / 256 + 1), 256, 0, side>>>(c->prefix.as<int>() + slabOff, c->gather.prefix + slabOff, n);
 			launches++;
 		}
 	}
@@ -463,7 +480,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		lio.tri48 = tri48; lio.ray48 = ray48; lio.plane16 = c->plane16.as<float4>(); lio.aabbxy16 = c->aabbxy16.as<float4>(); lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
 		lio.cellTris = c->cellTris.as<int>(); lio.colOff = c->colOff.as<unsigned>(); lio.colCount = c->colCount.as<int>(); lio.colTris = c->colTris.as<int>();
 		lio.cx = cx; lio.cy = cy; lio.cz = cz; lio.nBoundary = (int)nB; lio.totals = dT;
-		lio.l2State = gather ? c->gather.l2 : c->l2State.as<unsigned char>(); lio.l2Base = gather ? &dT->gatherBase : nullptr;
+		lio.l2State = gather ? c->gather.l2 : c->l2State.as<unsigned char>(); lio.own = own;
 		lio.colCellOff = c->colCellOff.as<unsigned>(); lio.colCellList = c->colCellList.as<int2>(); lio.l2Par = c->l2Par.as<unsigned>(); lio.cellMid = c->cellMid.as<float4>();
 		const L2K K = l2_constants(g.n2);
 		const int G = K.G;
@@ -473,17 +490,21 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		if (smem > 48 * 1024) return fail("k_l2: shared-memory layout exceeds 48 KB"); // cannot happen for n2 <= 32 (41 KB)
 		// K4a: boundary cells grouped by Level-1 column, then the parity bits of every sub-voxel column, one walk of the column list per column
 		k_col_cells<<<(unsigned)((nB + 255) / 256), 256, 0, st>>>(lio.boundaryIndex, (int)nB, (int)ncol, g.nx, cx, cy, cz, lio.colCellOff, c->colCellCnt.as<int>(), c->colCellList.as<int2>(),
-		                                                        c->cellMid.as<float4>(), lio.colCount, dT);
-		k_l2_rays<<<(unsigned)((ncol + G - 1) / G), 256, 0, st>>>(g, lio);
+		                                                        c->cellMid.as<float4>(), lio.colCount, lio.bTriOff, own, dT);
+		const long long nGroups = (ncol + G - 1) / G; // GPV_GATHER: group k belongs to rank k % world
+		k_l2_rays<<<(unsigned)((nGroups - own.rank + own.world - 1) / own.world), 256, 0, st>>>(g, lio);
 		launches += 2;
 		mark(GPV_PHASE_L2);
 		// With a host sink the boundary cells are refined in chunks and every finished chunk's bytes start their way to the
 		// host on the copy stream while the next chunk computes (e2e is PCIe-bound: 1 B per Level-2 voxel).
 		long long chunks = 1;
 		if (sink && sink->level2_inout) chunks = std::min<long long>(kMaxChunks, std::max<long long>(1, (nB * n23 + (24ll << 20) - 1) / (24ll << 20)));
-		const long long per = ((nB + chunks - 1) / chunks + G - 1) / G * G; // whole CTAs per chunk
+		// the cells this call refines: all boundary ranks, or (GPV_GATHER) this rank's share as listed, column by column, in colCellList
+		const long long nRefine = gather ? (long long)T1.nLocalCells : nB;
+		lio.cellList = gather ? c->colCellList.as<int2>() : nullptr;
+		const long long per = ((nRefine + chunks - 1) / chunks + G - 1) / G * G; // whole CTAs per chunk
 		for (long long k = 0; k < chunks; k++) {
-			const long long bb = k * per, be = std::min(nB, bb + per);
+			const long long bb = k * per, be = std::min(nRefine, bb + per);
 			if (bb >= be) break;
 			lio.bBegin = (int)bb; lio.nBoundary = (int)be;
 			l2fn<<<(unsigned)((be - bb + G - 1) / G), kL2Threads, smem, st>>>(g, lio, K);
@@ -494,6 +515,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 				GPV_CUDA(cudaMemcpyAsync(sink->level2_inout + bb * n23, c->l2State.as<uint8_t>() + bb * n23, (size_t)((be - bb) * n23), cudaMemcpyDeviceToHost, c->copyStream));
 			}
 		}
+		lio.cellList = nullptr;
 		lio.bBegin = 0; lio.nBoundary = (int)nB;
 		mark(GPV_PHASE_L2_NORMALS);
 		if (wantN) {
@@ -504,9 +526,9 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	}
 	GPV_CUDA(cudaStreamWaitEvent(st, c->evJoin[1], 0)); // the parity-fill branch joins
 	if (gather) { // completion flag behind this rank's last store; the gathering rank returns when every rank has signalled
-		k_gather_done<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch);
+		k_gather_done<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, dT);
 		launches++;
-		if (c->gather.rank == 0) { k_gather_wait<<<1, 1, 0, st>>>(c->gather.mail, c->gather.world, epoch, dT); launches++; }
+		if (c->gather.rank == 0) { k_gather_wait<<<1, 1, 0, st>>>(c->gather.mail, c->gather.world, epoch, c->gather.timeoutNs, dT); launches++; }
 	}
 	mark(GPV_PHASE_COUNT);
 	GPV_CUDA(cudaMemcpyAsync(c->hTotals, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
@@ -514,20 +536,15 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	if (sink) GPV_CUDA(cudaStreamSynchronize(c->copyStream));
 	GPV_CUDA(cudaGetLastError());
 	const Totals T2 = *c->hTotals;
-	if (gather && T2.gatherError) return fail(T2.gatherError == 1 ? "GPV_GATHER: Level-2 gather buffer too small for the boundary cells of all slabs" : "GPV_GATHER: timed out waiting for a peer rank");
-	if (gather && c->gather.rank == 0) { // total boundary count: the mailbox holds every slab's count of this epoch
-		GatherMail hm;
-		GPV_CUDA(cudaMemcpy(&hm, c->gather.mail, sizeof hm, cudaMemcpyDeviceToHost));
-		c->gather.nbTotal = 0;
-		for (int q = 0; q < c->gather.world; q++) c->gather.nbTotal += (unsigned)hm.count[epoch & 1][q];
-	}
+	if (gather && T2.gatherError) return fail("GPV_GATHER: timed out waiting for a peer rank");
+	if (gather) c->gather.nbTotal = nB; // the boundary ranks are global on every rank
 
-	out->z0 = g.z0; out->z1 = g.z1;
-	out->cells = cells; out->n_boundary = nB; out->n23 = n23;
-	out->d_level1_inout = gather ? c->gather.l1 + (size_t)g.z0 * ncol : c->l1State.as<uint8_t>(); // gather: this slab's bytes where they landed
-	out->d_prefix = c->prefix.as<int32_t>();                                                          // always the slab-local sums
+	out->z0 = oz0; out->z1 = oz1;
+	out->cells = cells; out->n_boundary = nB; out->n23 = n23; out->n_refined = wantL2 ? (gather ? (int64_t)T2.nLocalCells : nB) : 0;
+	out->d_level1_inout = gather ? c->gather.l1 + (size_t)oz0 * ncol : c->l1State.as<uint8_t>(); // gather: this slab's bytes where they landed
+	out->d_prefix = c->prefix.as<int32_t>();                                                          // the call's own sums (gather: the whole grid's)
 	out->d_boundary_index = c->boundaryIndex.as<int32_t>();
-	out->d_level2_inout = !wantL2 ? nullptr : gather ? c->gather.l2 + (size_t)T2.gatherBase * n23 : c->l2State.as<uint8_t>();
+	out->d_level2_inout = !wantL2 ? nullptr : gather ? c->gather.l2 : c->l2State.as<uint8_t>();
 	out->d_level1_normal = wantN ? c->l1Normal.as<uint8_t>() : nullptr;
 	out->d_level2_normal = (wantN && wantL2) ? c->l2Normal.as<uint8_t>() : nullptr;
 	out->d_cell_off = c->bTriOff.as<uint32_t>(); out->d_cell_tris = c->cellTris.as<int32_t>();
@@ -536,7 +553,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	out->l2_inside = (int64_t)T2.l2Inside; out->l2_boundary = (int64_t)T2.l2Boundary;
 	out->l1_box_tests = (int64_t)T2.binWork; out->l1_box_hits = (int64_t)T2.l1Hits; // sum of clipped footprints = the reference's loop nest (cu:374-378)
 	out->tri_total = T2.triTotal;
-	out->l2_box_tests = wantL2 ? (int64_t)T2.triTotal * n23 : 0; // reference-equivalent: n2^3 x sum of cell list lengths (cu:428)
+	out->l2_box_tests = wantL2 ? (int64_t)T2.l2LocalTris * n23 : 0; // reference-equivalent: n2^3 x sum of cell list lengths (cu:428) over the cells this call refined
 	out->l2_ray_tests = wantL2 ? (int64_t)T2.l2ColPairs * n23 : 0; // reference-equivalent: n2^3 x sum of column list lengths (cu:461-463)
 	out->fill_crossings = (int64_t)T2.crossPairs; out->fill_ill_conditioned = (int64_t)T2.nIll;
 	out->kernel_launches = launches;
@@ -583,7 +600,20 @@ extern "C" void gpv_gather_detach(gpv_ctx* c)
 	if (c->gather.ipc) {
 		cudaIpcCloseMemHandle(c->gather.l1); cudaIpcCloseMemHandle(c->gather.prefix); cudaIpcCloseMemHandle(c->gather.l2); cudaIpcCloseMemHandle(c->gather.mail);
 	}
+	// the ctx that created the buffers keeps owning them (and their sizes): it can be attached again, as rank 0 of a new session
+	const bool owner = c->gather.owner;
+	const int64_t cellsTotal = c->gather.cellsTotal, l2Cap = c->gather.l2Cap;
+	const unsigned long long timeoutNs = c->gather.timeoutNs;
 	c->gather = {};
+	c->gather.timeoutNs = timeoutNs;
+	if (owner) { c->gather.owner = true; c->gather.cellsTotal = cellsTotal; c->gather.l2Cap = l2Cap; }
+}
+
+extern "C" int gpv_gather_set_timeout(gpv_ctx* c, double seconds)
+{
+	if (!c || !(seconds > 0)) return fail("gpv_gather_set_timeout: bad argument");
+	c->gather.timeoutNs = (unsigned long long)(seconds * 1e9);
+	return 0;
 }
 
 extern "C" int gpv_gather_create(gpv_ctx* c, int64_t cells_total, int64_t l2_capacity, gpv_gather_desc* out)
@@ -602,7 +632,9 @@ extern "C" int gpv_gather_create(gpv_ctx* c, int64_t cells_total, int64_t l2_cap
 	GPV_CUDA(cudaIpcGetMemHandle(&h, c->gatherL2.p)); memcpy(out->l2, &h, 64);
 	GPV_CUDA(cudaIpcGetMemHandle(&h, c->gatherMail.p)); memcpy(out->mailbox, &h, 64);
 	out->cells_total = cells_total; out->l2_capacity = l2_capacity; out->owner_device = c->device;
+	const unsigned long long timeoutNs = c->gather.timeoutNs;
 	c->gather = {};
+	c->gather.timeoutNs = timeoutNs;
 	c->gather.owner = true; c->gather.cellsTotal = cells_total; c->gather.l2Cap = l2_capacity;
 	return 0;
 }
@@ -622,6 +654,9 @@ extern "C" int gpv_gather_attach(gpv_ctx* c, const gpv_gather_desc* d, int rank,
 	GPV_CUDA(cudaSetDevice(c->device));
 	if (c->gather.owner) { // the gathering rank uses its own allocations
 		if (rank != 0) return fail("gpv_gather_attach: the ctx that created the gather buffers is rank 0");
+		// a new session starts from epoch 0 on every rank: flags left by an earlier session on the same buffers must not satisfy its polls.
+		// (Attaching is collective: no peer is inside a call.)
+		GPV_CUDA(cudaMemset(c->gatherMail.p, 0, sizeof(GatherMail)));
 		return gather_bind(c, c->gatherL1.p, c->gatherPrefix.p, c->gatherL2.p, c->gatherMail.p, d->cells_total, d->l2_capacity, rank, world, false);
 	}
 	void* p[4] = {};
@@ -646,7 +681,8 @@ extern "C" int gpv_gather_attach_local(gpv_ctx* c, gpv_ctx* owner, int rank, int
 	const bool own = c == owner;
 	if (own && rank != 0) return fail("gpv_gather_attach_local: the owner is rank 0");
 	const int64_t cellsTotal = owner->gather.cellsTotal, l2Cap = owner->gather.l2Cap;
-	if (!own) c->gather = {};
+	if (own) { cudaSetDevice(owner->device); GPV_CUDA(cudaMemset(owner->gatherMail.p, 0, sizeof(GatherMail))); GPV_CUDA(cudaSetDevice(c->device)); } // new session (see gpv_gather_attach)
+	if (!own) { const unsigned long long t = c->gather.timeoutNs; c->gather = {}; c->gather.timeoutNs = t; }
 	return gather_bind(c, owner->gatherL1.p, owner->gatherPrefix.p, owner->gatherL2.p, owner->gatherMail.p, cellsTotal, l2Cap, rank, world, false);
 }
 

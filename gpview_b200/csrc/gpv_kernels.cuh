@@ -37,9 +37,18 @@ struct Totals {
 	unsigned long long binWork, crossWork; // totals of the two balanced work spaces (exclusive scans of binCnt / crossCnt)
 	unsigned long long l1Hits, crossPairs, nIll, l1Inside, l2Inside, l2Boundary;
 	unsigned long long l2ColPairs; // sum over boundary cells of their column-list length (reference-equivalent Level-2 ray tests / n2^3)
-	long long gatherBase;          // GPV_GATHER: boundary cells of the lower slabs (k_gather_exchange); -1 = exchange failed
-	unsigned long long gatherError; // 1 capacity exceeded, 2 timed out waiting for a peer
+	unsigned long long l2LocalTris; // sum of the cell-list lengths of the boundary cells THIS rank refines (all of them without GPV_GATHER)
+	unsigned long long gatherError; // 2 timed out waiting for a peer
 	unsigned int nBoundary, triTotal, colTotalOver, crossTotal;
+	unsigned int nLocalCells;       // boundary cells this rank refines (GPV_GATHER: those in the Level-1 columns it owns)
+};
+
+// GPV_GATHER: which rank refines a Level-1 column.  Columns are dealt out in groups of `group` consecutive columns (the columns one
+// CTA of k_l2_rays walks), group k to rank k % world: neighbouring columns cost about the same, so the interleaving balances the
+// Level-2 work without a cost model, and every column list is walked by exactly one rank.  world <= 1: everything is owned.
+struct Own {
+	int world, rank, group;
+	__host__ __device__ __forceinline__ bool operator()(unsigned col) const { return world <= 1 || (int)((col / (unsigned)group) % (unsigned)world) == rank; }
 };
 
 constexpr int kWorkThreads = 128;                        // threads per CTA of the balanced triangle-work kernels
@@ -386,7 +395,8 @@ struct ScanIO {
 	unsigned long long* desc; unsigned* tileCounter;
 	// MODE_CELLS
 	int* prefix; int* boundaryIndex; unsigned* bTriOff; unsigned char* bmask; long long globalBase; Totals* totals;
-	int* colCells; long long plane; // MODE_CELLS also counts the boundary cells of every Level-1 column (plane = nx*ny)
+	int* colCells; long long plane; // MODE_CELLS also counts the boundary cells of every Level-1 column (plane = nx*ny) this rank owns
+	Own own;
 	// MODE_OFFS
 	unsigned* off; unsigned* totalOut; unsigned long long* totalOut64; // either total pointer may be null
 };
@@ -503,7 +513,7 @@ __device__ __forceinline__ void scan_body(const ScanIO& io)
 					io.boundaryIndex[b] = (int)(io.globalBase + first + k);
 					unsigned col = col0 + (unsigned)k; // < 2 * plane + 8: the column of cell first + k
 					while (col >= (unsigned)io.plane) col -= (unsigned)io.plane;
-					atomicAdd(io.colCells + col, 1);
+					if (io.own(col)) atomicAdd(io.colCells + col, 1);
 					io.bTriOff[b] = ts;
 				}
 				run += item_of(v[k]);
@@ -744,9 +754,11 @@ struct L2IO {
 	const float4* cellMid;                              // [boundary rank] centre of the Level-1 cell (k_col_cells)
 	const float* cx; const float* cy; const float* cz;
 	unsigned char* l2State; // nBoundary * n2^3 file bytes (local, or the gathering rank's buffer over NVLink)
-	const long long* l2Base; // gather: boundary cells of the lower slabs (device-resident, k_gather_exchange); null = 0
-	int bBegin;             // this launch refines boundary ranks [bBegin, nBoundary)
+	const int2* cellList;   // GPV_GATHER: k_l2 refines the cells cellList[bBegin .. nBoundary) (.x = boundary rank; this rank's share, grouped
+	                        // by column = colCellList); null: the boundary ranks [bBegin, nBoundary) themselves
+	int bBegin;             // this launch refines slots [bBegin, nBoundary)
 	int nBoundary;
+	Own own;                // k_col_cells / k_l2_rays: the Level-1 columns this rank refines
 	Totals* totals;
 };
 
@@ -759,15 +771,21 @@ __device__ __forceinline__ int fast_div(int a, float inv) { return __float2int_r
 // Also the centre of every boundary cell by rank, so that k_l2 does not decode linear indices.
 __global__ void k_col_cells(const int* __restrict__ boundaryIndex, int nBoundary, int plane, int nx, const float* __restrict__ cx, const float* __restrict__ cy,
                             const float* __restrict__ cz, const unsigned* __restrict__ colCellOff, int* colCellCnt, int2* colCellList, float4* cellMid,
-                            const int* __restrict__ colCount, Totals* totals)
+                            const int* __restrict__ colCount, const unsigned* __restrict__ bTriOff, Own own, Totals* totals)
 {
 	const int b = blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned long long pairs = 0;
-	if (b < nBoundary) pairs = (unsigned long long)colCount[boundaryIndex[b] % plane];
-	pairs = warp_sum(pairs);
-	if ((threadIdx.x & 31) == 0 && pairs) atomicAdd(&totals->l2ColPairs, pairs);
-	if (b >= nBoundary) return;
-	const int l1 = boundaryIndex[b], kz = l1 / plane, col = l1 - kz * plane, jy = col / nx, ix = col - jy * nx;
+	unsigned long long pairs = 0, tris = 0;
+	int l1 = 0, kz = 0, col = 0;
+	bool mine = false;
+	if (b < nBoundary) {
+		l1 = boundaryIndex[b]; kz = l1 / plane; col = l1 - kz * plane;
+		mine = own((unsigned)col);
+		if (mine) { pairs = (unsigned long long)colCount[col]; tris = bTriOff[b + 1] - bTriOff[b]; }
+	}
+	pairs = warp_sum(pairs); tris = warp_sum(tris);
+	if ((threadIdx.x & 31) == 0 && (pairs | tris)) { atomicAdd(&totals->l2ColPairs, pairs); atomicAdd(&totals->l2LocalTris, tris); }
+	if (!mine) return;
+	const int jy = col / nx, ix = col - jy * nx;
 	const float mz = cz[kz];
 	cellMid[b] = make_float4(cx[ix], cy[jy], mz, 0.f);
 	colCellList[colCellOff[col] + atomicSub(colCellCnt + col, 1) - 1] = make_int2(b, __float_as_int(mz));
@@ -875,8 +893,10 @@ __global__ void __launch_bounds__(256, 3) k_l2_rays(GridP g, L2IO io)
 	const int tid = threadIdx.x;
 	const long long ncol = (long long)g.nx * g.ny;
 	const float invN2 = 1.f / (float)n2;
+	const long long group = io.own.world > 1 ? (long long)blockIdx.x * io.own.world + io.own.rank : (long long)blockIdx.x; // GPV_GATHER: this rank's groups only
 	if (G == 1) {
-		const int col = blockIdx.x;
+		const int col = (int)group;
+		if (col >= ncol) return;
 		RaySub u;
 		u.cb = io.colCellOff[col]; u.ce = io.colCellOff[col + 1];
 		if (u.cb == u.ce) return;
@@ -914,7 +934,7 @@ __global__ void __launch_bounds__(256, 3) k_l2_rays(GridP g, L2IO io)
 		}
 	} else {
 		const int gi = fast_div(tid, 1.f / (float)rows);
-		const long long col = (long long)blockIdx.x * G + gi;
+		const long long col = group * G + gi;
 		if (gi >= G || col >= ncol) return;
 		RaySub u;
 		u.cb = io.colCellOff[col]; u.ce = io.colCellOff[col + 1];
@@ -972,7 +992,7 @@ inline L2K l2_constants(int n2)
 	K.invRows = 1.f / (float)K.rows; K.invN2 = 1.f / (float)n2; K.inv3N2 = 1.f / (float)(3 * n2);
 	int o = K.G * 3 * n2 * 4;                // [G][3][n2] sub-voxel centres
 	K.sat = o; o += K.nItems * 4;            // [nItems] SAT hit bits along z per sub-voxel column
-	K.info = o; o += (K.G * 3 + 4) * 4;      // [G][2] triOff, triCnt (0 for cells past the end); then [G+1] prefix of the cells' pair counts
+	K.info = o; o += (K.G * 4 + 4) * 4;      // [G][2] triOff, triCnt (0 for cells past the end); [G+1] prefix of the cells' pair counts; [G] boundary rank of each cell (-1 past the end)
 	o = (o + 15) & ~15;
 	K.q1 = o; o += kL2Threads * kL2Batch * 8;    // (column, triangle) queue: item | rlo<<16 | rhi<<24, triangle
 	K.q2 = o; o += kL2Threads * n2 * 2;          // sub-voxel queue of one slice of kL2Threads (column, triangle) entries: entry<<5 | r
@@ -1001,17 +1021,19 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	unsigned short* sQ2 = reinterpret_cast<unsigned short*>(smemRaw + K.q2);
 	int* sQn = reinterpret_cast<int*>(smemRaw + K.qn);
 	const int tid = threadIdx.x, lane = tid & 31;
-	const long long b0 = io.bBegin + (long long)blockIdx.x * G;
-	auto div_rows = [&](int a) { return N2 ? a / (N2 ? N2 * N2 : 1) : fast_div(a, K.invRows); };
+	const long long b0 = io.bBegin + (long long)blockIdx.x * G; // first slot of this CTA; slot -> boundary rank through io.cellList (GPV_GATHER) or directly
+	int* sB = sInfo + 3 * G + 2;
+	auto div_rows = [&](int a) { return N2 ? a / (N2 ? N2 * N2 : 1) : a / K.rows; }; // generic n2: exact (stage A divides pair indices up to rows * list length, beyond fast_div's 2^21)
 	auto div_n2 = [&](int a) { return N2 ? a / (N2 ? N2 : 1) : fast_div(a, K.invN2); };
 	auto div_3n2 = [&](int a) { return N2 ? a / (N2 ? 3 * N2 : 1) : fast_div(a, K.inv3N2); };
+	auto rank_of = [&](long long slot) -> long long { return slot >= io.nBoundary ? -1ll : (io.cellList ? (long long)__ldg(&io.cellList[slot].x) : slot); };
 
 	if (tid < 4) sQn[tid] = 0;
 	for (int k = tid; k < G * 3 * n2; k += kL2Threads) {
 		const int gi = div_3n2(k), rem = k - gi * 3 * n2, ax = div_n2(rem), p = rem - ax * n2;
-		const long long b = b0 + gi;
+		const long long b = rank_of(b0 + gi);
 		float val = 0.f;
-		if (b < io.nBoundary) {
+		if (b >= 0) {
 			const float4 m = __ldg(io.cellMid + b);
 			const float mid = ax == 0 ? m.x : (ax == 1 ? m.y : m.z);
 			const float e2 = ax == 0 ? g.h2x : (ax == 1 ? g.h2y : g.h2z), e1 = ax == 0 ? g.h1x : (ax == 1 ? g.h1y : g.h1z);
@@ -1020,10 +1042,10 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 		sC[k] = val;
 	}
 	for (int gi = tid; gi < G; gi += kL2Threads) {
-		const long long b = b0 + gi;
+		const long long b = rank_of(b0 + gi);
 		int off = 0, cnt = 0;
-		if (b < io.nBoundary) { off = (int)io.bTriOff[b]; cnt = (int)(io.bTriOff[b + 1] - io.bTriOff[b]); }
-		sInfo[gi * 2] = off; sInfo[gi * 2 + 1] = cnt;
+		if (b >= 0) { off = (int)io.bTriOff[b]; cnt = (int)(io.bTriOff[b + 1] - io.bTriOff[b]); }
+		sInfo[gi * 2] = off; sInfo[gi * 2 + 1] = cnt; sB[gi] = (int)b;
 	}
 	if (N2 != 16) __syncthreads();
 	if (N2 != 16 && tid < 32) { // exclusive prefix of the cells' pair counts (rows * triangles), one warp (n2 = 16: one cell, not needed)
@@ -1188,8 +1210,8 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 		const int n23 = rows * n2;
 		for (int item = tid; item < nItems; item += kL2Threads) {
 			const int gi = div_rows(item), pq = item - gi * rows;
-			const long long b = b0 + gi;
-			if (b >= io.nBoundary) continue;
+			const long long b = sB[gi];
+			if (b < 0) continue;
 			const unsigned sat = sSat[item];
 			const unsigned par = io.l2Par[(size_t)b * rows + pq] & ~sat;
 			nIn += __popc(par); nBd += __popc(sat);
@@ -1203,20 +1225,34 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 			for (; r < n2; r++) o[r * rows] = ((sat >> r) & 1) ? 254 : (((par >> r) & 1) ? 127 : 0);
 		}
 		__syncthreads();
-		const long long nValid = min((long long)G, (long long)io.nBoundary - b0);
-		const long long gbase = *io.l2Base; // boundary cells of the lower slabs; < 0 = the exchange failed, write nothing
-		const int total = (gbase < 0 || nValid <= 0) ? 0 : (int)nValid * n23;
-		unsigned char* out = io.l2State + (size_t)(gbase + b0) * n23;
-		const int vec = ((reinterpret_cast<size_t>(out) & 15) == 0) ? (total & ~15) : 0;
-		for (int i = tid * 16; i < vec; i += kL2Threads * 16) *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(sOut + i);
-		for (int i = vec + tid; i < total; i += kL2Threads) out[i] = sOut[i];
+		// every cell's block is n2^3 contiguous bytes of Level2InOut.raw at (boundary rank) * n2^3 -- the ranks are global (every rank
+		// scans the whole grid), so no offset has to be exchanged; the cells of a CTA are not neighbours in the file (they are
+		// grouped by column), each leaves as its own run of 128-bit stores
+		const int nValid = (int)max(0ll, min((long long)G, (long long)io.nBoundary - b0));
+		const int total = nValid * n23;
+		if ((n23 & 15) == 0) {
+			for (int i = tid * 16; i < total; i += kL2Threads * 16) {
+				const int gi = i / n23, off = i - gi * n23;
+				*reinterpret_cast<uint4*>(io.l2State + (size_t)sB[gi] * n23 + off) = *reinterpret_cast<const uint4*>(sOut + i);
+			}
+		} else if ((n23 & 7) == 0) {
+			for (int i = tid * 8; i < total; i += kL2Threads * 8) {
+				const int gi = i / n23, off = i - gi * n23;
+				*reinterpret_cast<uint2*>(io.l2State + (size_t)sB[gi] * n23 + off) = *reinterpret_cast<const uint2*>(sOut + i);
+			}
+		} else {
+			for (int i = tid; i < total; i += kL2Threads) {
+				const int gi = i / n23, off = i - gi * n23;
+				io.l2State[(size_t)sB[gi] * n23 + off] = sOut[i];
+			}
+		}
 	} else {
 		// local HBM: a warp's byte stores cover 32 consecutive sub-voxels of the file (whole sectors); measured 10 % faster for the
 		// kernel than the staged form (no barrier, the warps retire independently)
 		for (int item = tid; item < nItems; item += kL2Threads) {
 			const int gi = div_rows(item), pq = item - gi * rows;
-			const long long b = b0 + gi;
-			if (b >= io.nBoundary) continue;
+			const long long b = sB[gi];
+			if (b < 0) continue;
 			const unsigned sat = sSat[item];
 			const unsigned par = io.l2Par[(size_t)b * rows + pq] & ~sat;
 			nIn += __popc(par); nBd += __popc(sat);
@@ -1235,14 +1271,17 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 }
 
 // ------------------------------------------------------------------------------------------------ gather over peer memory
-// Multi-GPU: every rank writes its slab's streams straight into the gathering rank's buffers over NVLink peer
-// memory.  The only data the ranks exchange is 8 bytes each: the slab's boundary-cell count, posted in a mailbox in the
-// gathering rank's memory; rank r adds up the counts of the lower slabs -- that fixes the offset of its Level-2 blocks and the
-// constant that makes its prefix sums global.  A second flag per rank signals completion.  Flags are tagged with the call's
-// epoch; the count slots are double-buffered by epoch parity (a rank can run at most one call ahead of a slower one: every
-// rank's next exchange needs rank 0's count, and rank 0 starts its next call only after all ranks signalled completion).
-struct GatherMail { unsigned long long count[2][16]; unsigned long long done[16]; };
-constexpr unsigned long long kGatherTimeoutNs = 5000000000ull; // a missing peer must not hang the GPU
+// Multi-GPU: every rank writes its share of the streams straight into the gathering rank's buffers over NVLink peer
+// memory, from inside the kernels that produce them.  Level 1 is computed by every rank over the whole grid (the parity rays need
+// whole column lists, cu:461-463), so every rank knows the GLOBAL boundary ranks and prefix sums: no offset has to be exchanged.
+// What is shared out is the output: the Level-1 bytes and prefix sums by z-slab (contiguous byte ranges), the Level-2 refinement by
+// Level-1 column (struct Own) -- each block lands at (global boundary rank) * n2^3.  The mailbox in the gathering rank's memory
+// carries three kinds of flags, all tagged with the call's epoch (every rank counts its GPV_GATHER calls):
+//   begin   rank 0 has entered call `epoch`: its previous result has been consumed, peers may overwrite the buffers
+//   done[r] rank r's last store of call `epoch` is visible (system-scope fence before the flag)
+//   stat    rank r's share of the counts (Level-1 inside cells of its slab, Level-2 inside / boundary voxels of its columns), summed by rank 0
+struct GatherMail { unsigned long long begin; unsigned long long done[16]; unsigned long long stat[2][16][4]; };
+constexpr unsigned long long kGatherTimeoutNsDefault = 5000000000ull; // a missing peer must not hang the GPU (gpv_gather_set_timeout)
 
 __device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p)
 {
@@ -1261,56 +1300,48 @@ __device__ __forceinline__ unsigned long long global_ns()
 	return t;
 }
 
-// <<<1, 1>>> after the size read-back: post this slab's boundary count, collect the lower slabs'
-__global__ void k_gather_exchange(GatherMail* mail, int rank, unsigned epoch, long long capCells, Totals* totals)
+// <<<1, 1>>> before this rank's first store into the gathering rank's buffers.  Rank 0 announces the call; the others wait for the
+// announcement, so that a fast rank cannot overwrite a result rank 0's caller is still reading (rank 0 enters its next call only
+// after the previous one returned).
+__global__ void k_gather_begin(GatherMail* mail, int rank, unsigned epoch, unsigned long long timeoutNs, Totals* totals)
 {
-	const unsigned nB = totals->nBoundary;
-	st_sys(&mail->count[epoch & 1][rank], ((unsigned long long)epoch << 32) | nB);
-	long long base = 0;
+	if (rank == 0) { st_sys(&mail->begin, (unsigned long long)epoch); return; }
 	const unsigned long long t0 = global_ns();
-	for (int q = 0; q < rank && base >= 0; q++) {
-		unsigned long long v;
-		do {
-			v = ld_sys(&mail->count[epoch & 1][q]);
-			if ((unsigned)(v >> 32) != epoch && global_ns() - t0 > kGatherTimeoutNs) { totals->gatherError = 2; base = -1; break; }
-		} while ((unsigned)(v >> 32) != epoch);
-		if (base >= 0) base += (unsigned)v;
-	}
-	if (base >= 0 && base + nB > capCells) { totals->gatherError = 1; base = -1; }
-	totals->gatherBase = base;
+	while (ld_sys(&mail->begin) < (unsigned long long)epoch)
+		if (global_ns() - t0 > timeoutNs) { totals->gatherError = 2; return; }
 }
 
-// slab-local prefix sums -> global, written at their final place in the gathering rank's Level1BoundaryPrefixSum stream
-__global__ void __launch_bounds__(256) k_gather_prefix(const int* __restrict__ local, int* out, long long n, const Totals* totals)
+// a z-slab of the (global) prefix sums -> its final place in the gathering rank's Level1BoundaryPrefixSum stream
+__global__ void __launch_bounds__(256) k_gather_prefix(const int* __restrict__ local, int* out, long long n)
 {
-	const long long base = totals->gatherBase;
-	if (base < 0) return;
-	const int add = (int)base;
 	const long long n4 = ((reinterpret_cast<size_t>(out) & 15) == 0 && (reinterpret_cast<size_t>(local) & 15) == 0) ? n / 4 : 0;
-	for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
-		int4 v = reinterpret_cast<const int4*>(local)[i];
-		v.x += add; v.y += add; v.z += add; v.w += add;
-		reinterpret_cast<int4*>(out)[i] = v;
-	}
-	for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = local[i] + add;
+	for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) reinterpret_cast<int4*>(out)[i] = reinterpret_cast<const int4*>(local)[i];
+	for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = local[i];
 }
 
 // <<<1, 1>>> behind the last kernel of the call: everything this rank wrote to the gathering rank is ordered before the flag
-__global__ void k_gather_done(GatherMail* mail, int rank, unsigned epoch)
+__global__ void k_gather_done(GatherMail* mail, int rank, unsigned epoch, const Totals* totals)
 {
+	unsigned long long* st = mail->stat[epoch & 1][rank];
+	st[0] = totals->l1Inside; st[1] = totals->l2Inside; st[2] = totals->l2Boundary; st[3] = totals->gatherError;
 	__threadfence_system();
 	st_sys(&mail->done[rank], (unsigned long long)epoch);
 }
 
-// <<<1, 1>>> on the gathering rank: returns when every rank has signalled completion of this epoch
-__global__ void k_gather_wait(GatherMail* mail, int world, unsigned epoch, Totals* totals)
+// <<<1, 1>>> on the gathering rank: returns when every rank has signalled completion of this epoch; the counts become the whole grid's
+__global__ void k_gather_wait(GatherMail* mail, int world, unsigned epoch, unsigned long long timeoutNs, Totals* totals)
 {
 	const unsigned long long t0 = global_ns();
+	unsigned long long in1 = 0, in2 = 0, bd2 = 0;
 	for (int q = 0; q < world; q++) {
 		while (ld_sys(&mail->done[q]) < (unsigned long long)epoch) {
-			if (global_ns() - t0 > kGatherTimeoutNs) { totals->gatherError = 2; return; }
+			if (global_ns() - t0 > timeoutNs) { totals->gatherError = 2; return; }
 		}
+		const unsigned long long* st = mail->stat[epoch & 1][q];
+		in1 += st[0]; in2 += st[1]; bd2 += st[2];
+		if (st[3]) totals->gatherError = st[3];
 	}
+	totals->l1Inside = in1; totals->l2Inside = in2; totals->l2Boundary = bd2;
 }
 
 // ------------------------------------------------------------------------------------------------ normals

@@ -72,7 +72,7 @@ typedef struct {
 #define GPV_KEEP_LISTS   4     /* CSR cell lists / column lists in canonical (ascending) order for the caller (gpv_result list pointers);
                                   without it (and without GPV_NORMALS) the lists stay in the order the binning left them: occupancy does not depend on it */
 #define GPV_PROFILE      8     /* record a CUDA event pair around every kernel of the pipeline -> gpv_result.phase_ms */
-#define GPV_GATHER      16     /* multi-GPU: write this slab's streams straight into the gathering rank's buffers (gpv_gather_*) */
+#define GPV_GATHER      16     /* multi-GPU: write this rank's share of the streams straight into the gathering rank's buffers (gpv_gather_*) */
 #define GPV_BATCH_TOLERANT_LOAD 64 /* gpv_voxelize_batch: read the meshes with GPV_LOAD_TOLERANT (gpv_load_mesh_ex) */
 #define GPV_SAVE_COMPUTED_ONLY 32 /* gpv_voxelize_batch: write only the streams that were computed -- no 127-filled normal files when
                                   GPV_NORMALS is off (74 % of a 64 + 4^3 model's bytes, and file writing is what bounds a dataset run) */
@@ -112,6 +112,7 @@ typedef struct {
 	int64_t kernel_launches;   /* kernels launched by this call */
 	/* GPV_PROFILE: device time of each phase in ms (CUDA events on the caller's stream), indexed by GPV_PHASE_* */
 	float phase_ms[16];
+	int64_t n_refined;         /* boundary cells whose Level-2 blocks THIS call produced: n_boundary, or with GPV_GATHER this rank's share */
 } gpv_result;
 
 enum { GPV_PHASE_SETUP = 0, GPV_PHASE_BIN_COUNT, GPV_PHASE_CROSS_COUNT, GPV_PHASE_SCAN, GPV_PHASE_HOST_GAP, GPV_PHASE_BIN_FILL,
@@ -177,17 +178,22 @@ int gpv_voxelize_host(gpv_ctx* ctx, const gpv_mesh* mesh, const gpv_params* para
 
 /* ---- multi-GPU gather over NVLink peer memory (one process per GPU, one ctx per process).
  * The gathering rank (rank 0) allocates the whole-grid streams once and exports them as CUDA IPC handles; every other rank maps
- * them (peer access over NVLink / NVSwitch).  A call with GPV_GATHER then writes its slab's Level1InOut bytes, its globalised
- * prefix sums and its Level-2 blocks directly at their final offsets in rank 0's memory from inside the kernels that produce
- * them -- there is no separate collective.  The one exchange step of the path (boundary counts of the lower slabs, which fix
- * every Level-2 offset) and the completion signal are 8-byte flags in a mailbox in rank 0's memory, written and polled by
- * one-thread kernels on the callers' streams; all ranks must issue their GPV_GATHER calls in the same order.
- * gpv_gather_desc is plain bytes: ship it to the other ranks with any transport (torch.distributed broadcast, a file, a pipe).
- * GPV_NORMALS is not supported together with GPV_GATHER.  The flags are polled by one-thread kernels; every poll gives up after 5 s with
- * an error return instead of hanging the GPU.  If several gathering contexts share ONE process and device (tests): raise
- * CUDA_DEVICE_MAX_CONNECTIONS so that their streams do not share a hardware work queue, and do not allocate device memory while
- * a gathering call is in flight (CUDA serialises streams around cudaMalloc/cudaFree) -- run one plain call first to grow the
- * pools.  One process per GPU needs neither: a rank finishes its allocations before it posts its count. */
+ * them (peer access over NVLink / NVSwitch).  A call with GPV_GATHER then writes its share of the streams directly at their
+ * final offsets in rank 0's memory from inside the kernels that produce them -- there is no separate collective and NO exchange
+ * step on the data path: every rank runs Level 1 over the whole grid (the parity rays need whole column lists, cu:461-463), so
+ * boundary ranks and prefix sums are global on every rank.  Shared out are
+ *   - the Level1InOut bytes and prefix sums by z-slab: [z0,z1) of gpv_params, or an equal share of the layers when z1 <= 0;
+ *   - the Level-2 refinement by Level-1 column: groups of max(1, 256/n2^2) consecutive columns are dealt to the ranks round-robin,
+ *     so that every column list is walked by exactly one rank and neighbouring columns (similar cost) land on different ranks.
+ * Completion flags and the ranks' shares of the counts travel through a mailbox in rank 0's memory (one-thread kernels on the
+ * callers' streams); rank 0's call returns once every rank has signalled, with the whole grid's counts in its gpv_result (the
+ * other ranks report their own share).  All ranks must issue their GPV_GATHER calls in the same order; a rank's call does not
+ * touch rank 0's buffers before rank 0 has entered the same call.  gpv_gather_desc is plain bytes: ship it to the other ranks
+ * with any transport (torch.distributed broadcast, a file, a pipe).  GPV_NORMALS and the host-stream call are not supported
+ * together with GPV_GATHER.  Every poll gives up after a timeout (5 s; gpv_gather_set_timeout) with an error return instead of
+ * hanging the GPU.  If several gathering contexts share ONE process and device (tests): raise CUDA_DEVICE_MAX_CONNECTIONS so
+ * that their streams do not share a hardware work queue, and do not allocate device memory while a gathering call is in flight
+ * (CUDA serialises streams around cudaMalloc/cudaFree) -- run one plain call first to grow the pools. */
 typedef struct {
 	unsigned char l1[64], prefix[64], l2[64], mailbox[64];   /* cudaIpcMemHandle_t of the four allocations */
 	int64_t cells_total;                                     /* nx*ny*nz of the grid the buffers were sized for */
@@ -197,7 +203,8 @@ typedef struct {
 int gpv_gather_create(gpv_ctx* ctx, int64_t cells_total, int64_t l2_capacity, gpv_gather_desc* out);      /* gathering rank only */
 int gpv_gather_attach(gpv_ctx* ctx, const gpv_gather_desc* desc, int rank, int world);                    /* every rank, the gathering one included */
 int gpv_gather_attach_local(gpv_ctx* ctx, gpv_ctx* owner, int rank, int world);                           /* same-process ranks (tests, several GPUs in one process) */
-void gpv_gather_detach(gpv_ctx* ctx);
+void gpv_gather_detach(gpv_ctx* ctx);                                /* the creating ctx keeps its buffers and may be attached again (a new session) */
+int gpv_gather_set_timeout(gpv_ctx* ctx, double seconds);            /* how long a poll waits for a peer before the call fails (default 5 s) */
 /* gathering rank, after its own GPV_GATHER call returned (it returns once every rank has signalled completion): device views of
  * the whole-grid streams and the total boundary count */
 int gpv_gather_result(gpv_ctx* ctx, uint8_t** d_level1_inout, int32_t** d_prefix, uint8_t** d_level2_inout, int64_t* n_boundary_total);

@@ -200,12 +200,13 @@ def test_hostile_triangle_soups_match_brute_force_oracle(product, oracle, ctx, t
     assert np.array_equal(res.level2_normal(), want.l2_normal)
 
 
-@pytest.mark.parametrize("name,l1,l2,R", [("cessna", 64, 4, 3), ("torus", 32, 4, 2), ("cessna", 128, 8, 4)])
+@pytest.mark.parametrize("name,l1,l2,R", [("cessna", 64, 4, 3), ("torus", 32, 4, 2), ("cessna", 128, 8, 4), ("sphere", 24, 16, 5), ("cad", 40, 3, 2), ("block", 40, 2, 7)])
 def test_peer_memory_gather_equals_whole(product, ctx, tmp_path_factory, name, l1, l2, R):
     """GPV_GATHER: R ranks -- here R contexts of one process on one device, each on its own thread and stream --
-    write their z-slabs straight into rank 0's whole-grid streams (Level-1 bytes from the fill sweep, prefix sums globalised
-    by the exchanged boundary counts, Level-2 blocks from k_l2 at their final offsets).  Rank 0's buffers must equal the
-    single-call result byte for byte; run twice to exercise the epoch / double-buffered mailbox."""
+    write their shares straight into rank 0's whole-grid streams: Level-1 bytes and prefix sums by z-slab, Level-2 blocks by
+    Level-1 column (every rank runs Level 1 over the whole grid, so boundary ranks are global and nothing is exchanged).  Rank 0's
+    buffers must equal the single-call result byte for byte, its counts the whole grid's; run twice to exercise the epochs, once
+    with explicit slabs and once with the default split.  (tests/test_gpu_multiproc.py is the one-process-per-rank version.)"""
     import threading
     path = mesh_path(name, tmp_path_factory.getbasetemp())
     mesh = product.load_mesh(path)
@@ -218,41 +219,50 @@ def test_peer_memory_gather_equals_whole(product, ctx, tmp_path_factory, name, l
         for r in range(R):
             ranks[r].gather_attach_local(ranks[0], r, R)
         cuts = [nz * r // R for r in range(R + 1)]
+        cuts[1] = min(cuts[1] + 1, cuts[2]) if R > 2 else cuts[1]   # uneven explicit slabs
         # Same-process ranks only: CUDA serialises streams around every cudaMalloc / cudaFree, so nothing may allocate while a rank's
-        # polling kernel is in flight.  Upload first and let one plain slab call grow every context's pools.  (One process per
-        # GPU -- the deployment, bench.py -- has no such constraint: a rank allocates before it posts its count.)
+        # polling kernel is in flight.  Upload first and let one plain whole-grid call grow every context's pools.  (One process per
+        # GPU -- the deployment, bench.py -- has no such constraint.)
         dev = [ranks[r].upload(mesh) for r in range(R)]
         for r in range(R):
-            ranks[r].voxelize_device(dev[r], mesh, product.Params(l1, l2, 0, cuts[r], cuts[r + 1]))
+            ranks[r].voxelize_device(dev[r], mesh, product.Params(l1, l2, 0))
         for rep in range(2):
-            for attempt in range(2):
-                errs = []
+            errs, shares = [], [0] * R
+            res0 = [None]
 
-                def work(r):
-                    try:
-                        ranks[r].voxelize_device(dev[r], mesh, product.Params(l1, l2, product.GPV_GATHER, cuts[r], cuts[r + 1]), ranks[r].stream())
-                    except Exception as e:  # noqa: BLE001
-                        errs.append((r, repr(e)))
-                th = [threading.Thread(target=work, args=(r,)) for r in range(R)]
-                for t in th:
-                    t.start()
-                for t in th:
-                    t.join()
-                # ranks sharing one device can still be serialised by the driver (a shared box, hardware queue aliasing): the 5 s
-                # poll timeout then turns into an error return -- by design -- and every rank's epoch stays in step; try once more
-                if not errs or not all("timed out" in e for _, e in errs):
-                    break
+            def work(r):
+                try:
+                    z0, z1 = (cuts[r], cuts[r + 1]) if rep == 0 else (0, 0)
+                    res = ranks[r].voxelize_device(dev[r], mesh, product.Params(l1, l2, product.GPV_GATHER, z0, z1), ranks[r].stream())
+                    shares[r] = res.n_refined
+                    if r == 0:
+                        res0[0] = res
+                except Exception as e:  # noqa: BLE001
+                    errs.append((r, repr(e)))
+            th = [threading.Thread(target=work, args=(r,)) for r in range(R)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
             assert not errs, errs
             g_l1, g_pre, g_l2, nb = ranks[0].gather_result(cells, n23)
             assert nb == whole.nb
             assert np.array_equal(g_l1, w_l1), (rep, "l1")
             assert np.array_equal(g_pre, w_pre), (rep, "prefix")
             assert np.array_equal(g_l2, w_l2), (rep, "l2")
+            assert res0[0].counts == whole.counts, (rep, res0[0].counts, whole.counts)   # rank 0 reports the whole grid's counts
+            assert sum(shares) == whole.nb, shares                                      # every boundary cell refined by exactly one rank
         for r in range(R):
             ranks[r].free_device(dev[r])
         # without an attached gather the flag is refused, not ignored
         with pytest.raises(product.GpvError):
             ctx.voxelize(mesh, product.Params(l1, l2, product.GPV_GATHER))
+        # a gather buffer that is too small for the grid's boundary cells is refused by the call, nothing is overrun
+        ranks[0].gather_detach()
+        ranks[0].gather_create(cells, max(0, whole.nb * n23 - 1))
+        ranks[0].gather_attach_local(ranks[0], 0, 1)
+        with pytest.raises(product.GpvError):
+            ranks[0].voxelize(mesh, product.Params(l1, l2, product.GPV_GATHER))
     finally:
         for c in ranks:
             c.close()
