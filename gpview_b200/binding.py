@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GPVIEW_B200_LIB", os.path.join(HERE, "libgpview_b200.so"))  # override: A/B builds of the same ABI
 
-GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE, GPV_GATHER, GPV_SAVE_COMPUTED_ONLY, GPV_BATCH_TOLERANT_LOAD = 1, 2, 4, 8, 16, 32, 64
+GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE, GPV_GATHER, GPV_SAVE_COMPUTED_ONLY, GPV_BATCH_TOLERANT_LOAD, GPV_PROFILE_L2, GPV_PACKED_L2 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 
 class GpvError(RuntimeError):
@@ -68,7 +68,7 @@ class CBatchStats(C.Structure):
 NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_stream", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh", "gpv_load_mesh_ex",
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
-                  "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_check_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
+                  "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_check_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_expand_packed_l2", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
                   "gpv_gather_create", "gpv_gather_attach", "gpv_gather_attach_local", "gpv_gather_detach", "gpv_gather_set_timeout", "gpv_gather_result"]
 COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
 
@@ -112,6 +112,7 @@ def lib():
         L.gpv_save_streams.argtypes = [C.POINTER(CMesh), C.POINTER(CResult), C.POINTER(CHostStreams), C.c_int, C.c_char_p, C.c_int]
         L.gpv_voxelize_batch.argtypes = [C.POINTER(C.c_char_p), C.c_int64, C.POINTER(CParams), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int,
                                          C.POINTER(CBatchStats)]
+        L.gpv_expand_packed_l2.argtypes = [vp, C.c_int64, vp]
         L.gpv_measure_fp32_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         L.gpv_measure_copy_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         L.gpv_gather_create.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(CGatherDesc)]

@@ -23,6 +23,7 @@
 #include "gpv_kernels.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -63,7 +64,7 @@ struct gpv_ctx {
 	int device = 0;
 	int smCount = 0;
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
-	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, aabbxy16, longList, colCursor, binBits, colCellCnt, colCellOff, colCellList, l2Par, cellMid;
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, aabbxy16, longList, colCursor, binBits, colCellCnt, colCellOff, colCellList, l2Par, cellMid, rayOver, rayOverflow, l2Packed;
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {}, evEnd[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
@@ -72,13 +73,23 @@ struct gpv_ctx {
 	cudaStream_t sideStream = nullptr;  // the parity-fill branch of the Level-1 pipeline runs beside the binning / sorting branch
 	cudaEvent_t evFork[2] = {}, evJoin[2] = {};
 	cudaEvent_t evChunk[17] = {};
+	cudaEvent_t evCopied[16] = {};      // GPV_PACKED_L2: a chunk of packed Level-2 words has landed in hPacked
+	void* hPacked = nullptr; size_t hPackedCap = 0; // pinned staging of the packed Level-2 stream (gpv_voxelize_host)
 	bool sortAttrSet = false;
+	// Counters that clean up after themselves: a call that completes leaves cellCount all zero again (the fill sweep of the binning
+	// takes its slots by atomic decrement) and wipes the part of the (triangle, column) bitmaps it used on the side stream, beside
+	// Level 2 -- so the next call clears neither on its critical path.  What is known to be zero:
+	void* cleanCellCount = nullptr; size_t cleanCellBytes = 0; // [cleanCellCount, +cleanCellBytes)
+	void* cleanBits = nullptr;                                  // the whole binBits pool at this address
+	cudaEvent_t evBinDone = nullptr;
+	int debugOwnWorld = 0, debugOwnRank = 0; // GPV_DEBUG_OWN (profiling one rank's share of a gathering call on a single GPU)
 	// GPV_GATHER (gpv_gather_*): the gathering rank's whole-grid streams and mailbox, local or mapped over NVLink
 	struct {
 		bool on = false, owner = false, ipc = false;
 		int rank = 0, world = 1;
 		unsigned epoch = 0;
 		uint8_t* l1 = nullptr; int32_t* prefix = nullptr; uint8_t* l2 = nullptr; gpv::GatherMail* mail = nullptr;
+		uint8_t* l2p = nullptr; // 2-bit packed Level-2 blocks of the peers (behind the byte stream in the same allocation)
 		int64_t cellsTotal = 0, l2Cap = 0, nbTotal = 0;
 		unsigned long long timeoutNs = gpv::kGatherTimeoutNsDefault;
 	} gather;
@@ -106,10 +117,11 @@ static int preload_kernels()
 	GPV_LOAD(k_clear); GPV_LOAD(k_clear_bits); GPV_LOAD(k_prepare); GPV_LOAD(k_scan_offs3); GPV_LOAD((k_scan<MODE_CELLS, 1>)); GPV_LOAD((k_scan<MODE_CELLS, 4>));
 	GPV_LOAD(k_bin<false>); GPV_LOAD(k_bin<true>); GPV_LOAD(k_cross<false>); GPV_LOAD(k_cross<true>); GPV_LOAD(k_fill_sweep);
 	GPV_LOAD(k_sort_segments); GPV_LOAD(k_sort_long);
-	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals);
-	GPV_LOAD(k_l2<16, false>); GPV_LOAD(k_l2<8, false>); GPV_LOAD(k_l2<4, false>); GPV_LOAD(k_l2<2, false>); GPV_LOAD(k_l2<0, false>);
-	GPV_LOAD(k_l2<16, true>); GPV_LOAD(k_l2<8, true>); GPV_LOAD(k_l2<4, true>); GPV_LOAD(k_l2<2, true>); GPV_LOAD(k_l2<0, true>);
-	GPV_LOAD(k_gather_begin); GPV_LOAD(k_gather_prefix); GPV_LOAD(k_gather_done); GPV_LOAD(k_gather_wait);
+	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l2_rays_overflow); GPV_LOAD(k_ray_units); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals);
+	GPV_LOAD(k_l2<16, 0>); GPV_LOAD(k_l2<8, 0>); GPV_LOAD(k_l2<4, 0>); GPV_LOAD(k_l2<2, 0>); GPV_LOAD(k_l2<0, 0>);
+	GPV_LOAD(k_l2<16, 1>); GPV_LOAD(k_l2<8, 1>); GPV_LOAD(k_l2<4, 1>); GPV_LOAD(k_l2<2, 1>); GPV_LOAD(k_l2<0, 1>);
+	GPV_LOAD(k_l2<16, 2>); GPV_LOAD(k_l2<8, 2>); GPV_LOAD(k_l2<4, 2>); GPV_LOAD(k_l2<0, 2>); GPV_LOAD(k_l2_expand);
+	GPV_LOAD(k_gather_begin); GPV_LOAD(k_gather_done); GPV_LOAD(k_gather_wait);
 #undef GPV_LOAD
 	return 0;
 }
@@ -135,15 +147,18 @@ extern "C" int gpv_create(int device, gpv_ctx** out)
 	gpv_ctx* c = new gpv_ctx();
 	c->device = device;
 	c->smCount = prop.multiProcessorCount;
+	if (const char* e = getenv("GPV_DEBUG_OWN")) { if (sscanf(e, "%d,%d", &c->debugOwnWorld, &c->debugOwnRank) != 2 || c->debugOwnRank < 0 || c->debugOwnRank >= c->debugOwnWorld) c->debugOwnWorld = 0; }
 	static_assert(sizeof(Totals) <= 128, "gpv_ctx::totals: Totals in the first 128 bytes, the sort's long-list counters behind");
 	auto init = [c]() -> int {
-		GPV_CUDA(cudaHostAlloc((void**)&c->hTotals, sizeof(Totals), cudaHostAllocDefault));
+		GPV_CUDA(cudaHostAlloc((void**)&c->hTotals, 256, cudaHostAllocDefault)); // Totals + the counters behind it
 		if (c->totals.ensure(256)) return 1;
 		GPV_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
 		GPV_CUDA(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
 		GPV_CUDA(cudaStreamCreateWithFlags(&c->sideStream, cudaStreamNonBlocking));
 		for (int k = 0; k < 2; k++) { GPV_CUDA(cudaEventCreateWithFlags(&c->evFork[k], cudaEventDisableTiming)); GPV_CUDA(cudaEventCreateWithFlags(&c->evJoin[k], cudaEventDisableTiming)); }
 		for (cudaEvent_t& e : c->evChunk) GPV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		for (cudaEvent_t& e : c->evCopied) GPV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		GPV_CUDA(cudaEventCreateWithFlags(&c->evBinDone, cudaEventDisableTiming));
 		return 0;
 	};
 	if (init()) { // a half-built context owns nothing the caller could release: gpv_destroy() frees whatever was created
@@ -161,14 +176,17 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->aabbxy16, &c->longList, &c->colCursor, &c->binBits, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->aabbxy16, &c->longList, &c->colCursor, &c->binBits, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->rayOver, &c->rayOverflow, &c->l2Packed, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
 	gpv_gather_detach(c);
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
 	if (c->haveEvents) { for (cudaEvent_t e : c->ev) cudaEventDestroy(e); for (cudaEvent_t e : c->evEnd) cudaEventDestroy(e); }
 	for (int k = 0; k < 2; k++) { if (c->evFork[k]) cudaEventDestroy(c->evFork[k]); if (c->evJoin[k]) cudaEventDestroy(c->evJoin[k]); }
+	if (c->evBinDone) cudaEventDestroy(c->evBinDone);
 	if (c->sideStream) cudaStreamDestroy(c->sideStream);
 	for (cudaEvent_t e : c->evChunk) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : c->evCopied) if (e) cudaEventDestroy(e);
+	if (c->hPacked) cudaFreeHost(c->hPacked);
 	if (c->copyStream) cudaStreamDestroy(c->copyStream);
 	if (c->ownStream) cudaStreamDestroy(c->ownStream);
 	delete c;
@@ -225,9 +243,29 @@ static void launch_scans(gpv_ctx* c, cudaStream_t st, const ScanReq* r, int coun
 	launches++;
 }
 
+constexpr unsigned kRayOverflowCap = 1u << 20; // sub-columns handed to k_l2_rays_overflow per call (16 MB of entries; cessna-256 needs ~300)
 constexpr int kMaxChunks = 16; // Level-2 chunks whose D2H copies overlap the next chunk's refinement (host sink only)
 
+static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const float bmin[3], const float bmax[3], float max_model_size,
+                         const gpv_params* prm, void* stream, gpv_result* out, const gpv_host_streams* sink);
+
 static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const float bmin[3], const float bmax[3], float max_model_size,
+                         const gpv_params* prm, void* stream, gpv_result* out, const gpv_host_streams* sink)
+{
+	const int rc = voxelize_body(c, d_tris, n_tri, bmin, bmax, max_model_size, prm, stream, out, sink);
+	if (rc && c) {
+		// An error return must not leave work in flight on the context's own streams: it would still be reading pooled buffers, or
+		// writing the caller's host memory, when the next call (or the caller) reuses them.
+		const std::string why = g_err;
+		cudaSetDevice(c->device);
+		cudaStreamSynchronize((cudaStream_t)stream); cudaStreamSynchronize(c->sideStream); cudaStreamSynchronize(c->copyStream);
+		cudaGetLastError();
+		g_err = why;
+	}
+	return rc;
+}
+
+static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const float bmin[3], const float bmax[3], float max_model_size,
                          const gpv_params* prm, void* stream, gpv_result* out, const gpv_host_streams* sink)
 {
 	if (!c) return fail("gpv_voxelize_device: null ctx");
@@ -253,6 +291,9 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	// Level-1 bytes / prefix sums this rank delivers (default: an equal share of the layers), the Level-2 work is shared out by column (Own)
 	int oz0 = g.z0, oz1 = g.z1;
 	Own own{ 1, 0, 1 };
+	if (!gather && c->debugOwnWorld > 1) { // profiling aid (GPV_DEBUG_OWN=world,rank): a plain call refines only the Level-2 share rank `rank` of `world` would
+		own.world = c->debugOwnWorld; own.rank = c->debugOwnRank; own.group = std::max(1, 256 / (gg.n2 * gg.n2));
+	}
 	if (gather) {
 		if (prm->z1 <= 0) { oz0 = (int)((long long)g.nz * c->gather.rank / c->gather.world); oz1 = (int)((long long)g.nz * (c->gather.rank + 1) / c->gather.world); }
 		g.z0 = 0; g.z1 = g.nz;
@@ -272,7 +313,8 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	const unsigned epoch = gather ? ++c->gather.epoch : 0; // every rank counts its GPV_GATHER calls: same order on all ranks
 	const int nTri = (int)n_tri;
 	int64_t launches = 0;
-	const bool prof = (prm->flags & GPV_PROFILE) != 0;
+	const bool profLight = (prm->flags & GPV_PROFILE_L2) != 0 && !(prm->flags & GPV_PROFILE); // events around the two Level-2 kernels only
+	const bool prof = (prm->flags & (GPV_PROFILE | GPV_PROFILE_L2)) != 0;
 	if (prof && !c->haveEvents) {
 		for (cudaEvent_t& e : c->ev) GPV_CUDA(cudaEventCreate(&e));
 		for (cudaEvent_t& e : c->evEnd) GPV_CUDA(cudaEventCreate(&e));
@@ -282,8 +324,8 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	// (phases of the side branch carry their own end event: they overlap the main branch)
 	bool marked[GPV_PHASE_COUNT + 1] = {}, sidePhase[GPV_PHASE_COUNT + 1] = {};
 	cudaStream_t side = c->sideStream;
-	auto mark = [&](int phase) { if (prof) { cudaEventRecord(c->ev[phase], st); marked[phase] = true; } };
-	auto mark_side = [&](int phase, bool begin) { if (prof) { cudaEventRecord(begin ? c->ev[phase] : c->evEnd[phase], side); marked[phase] = sidePhase[phase] = true; } };
+	auto mark = [&](int phase) { if (prof && (!profLight || phase >= GPV_PHASE_L2_RAYS)) { cudaEventRecord(c->ev[phase], st); marked[phase] = true; } };
+	auto mark_side = [&](int phase, bool begin) { if (prof && !profLight) { cudaEventRecord(begin ? c->ev[phase] : c->evEnd[phase], side); marked[phase] = sidePhase[phase] = true; } };
 
 	// ---- fixed-size buffers
 	if (c->tri48.ensure((size_t)nTri * 48) || c->ray48.ensure((size_t)nTri * 48) || c->tabX.ensure((size_t)g.nx * 4) || c->tabY.ensure((size_t)g.ny * 4) ||
@@ -294,10 +336,16 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	    c->binCnt.ensure((size_t)nTri * 4 + 32) || c->binOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->crossCnt.ensure((size_t)nTri * 4 + 32) ||
 	    c->crossWorkOff.ensure((size_t)(nTri + 1) * 4 + 32) || c->colCellCnt.ensure((size_t)ncol * 4 + 32) || c->colCursor.ensure((size_t)ncol * 4 + 32) || c->colCellOff.ensure((size_t)(ncol + 1) * 4 + 32))
 		return 1;
+	const long long rayCap = ncol + cells / kRayChunk + 64; // units of k_l2_rays: at most one per column that has boundary cells + one per kRayChunk cells
+	if (wantL2 && (c->rayOver.ensure((size_t)rayCap * 8) || c->rayOverflow.ensure((size_t)kRayOverflowCap * 16))) return 1;
 	// (triangle, column) bitmaps of the two binning sweeps: one bit per work item at most.  The work-space size is known on the
 	// device only; a first guess here, the exact size after the read-back (then the call starts over, once per growth).
 	if (!c->binBits.cap && c->binBits.ensure((size_t)std::max<long long>(1 << 20, 64ll * nTri) / 8 * 2 + 64)) return 1;
 	const unsigned long long bitsCap = ((unsigned long long)(c->binBits.cap - 64) / 2 / 4) * 32; // bits per sweep (whole words)
+	if (c->cleanBits != c->binBits.p) { // a new pool, or a call that did not get to wipe what it used: zero all of it once
+		GPV_CUDA(cudaMemsetAsync(c->binBits.p, 0, c->binBits.cap, st));
+	}
+	c->cleanBits = nullptr; // dirty from here on; restored when the call completes
 	Totals* dT = c->totals.as<Totals>();
 	mark(GPV_PHASE_SETUP);
 	// look-back descriptor regions of the six scans of this call
@@ -313,7 +361,8 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		int k = 0;
 		auto add = [&](void* p, size_t bytes) { cl.p[k] = reinterpret_cast<uint4*>(p); cl.n16[k] = (bytes + 15) / 16; k++; };
 		add(dT, 256);                                   // Totals + the two long-list counters of the sort (gpv_ctx::totals is 256 B)
-		add(c->cellCount.p, (size_t)cells * 4);
+		if (!(c->cleanCellCount == c->cellCount.p && c->cleanCellBytes >= (size_t)cells * 4)) add(c->cellCount.p, (size_t)cells * 4);
+		c->cleanCellCount = nullptr; c->cleanCellBytes = 0; // dirty from here on; restored when the call completes
 		add(c->colCount.p, (size_t)ncol * 4);
 		add(c->crossCount.p, (size_t)ncol * 4);
 		add(c->colCellCnt.p, (size_t)ncol * 4);
@@ -337,21 +386,14 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			                   { c->crossCnt.as<int>(), nTri, c->crossWorkOff.as<unsigned>(), nullptr, &dT->crossWork, dOff[1] } };
 		launch_scans(c, st, r, 2, launches);
 	}
+	GPV_CUDA(cudaEventRecord(c->evFork[0], st)); // the work spaces are scanned: the crossing count may start (side stream, launched below)
 	BinOut bo{};
 	bo.cellCount = c->cellCount.as<int>(); bo.colCount = c->colCount.as<int>(); bo.totals = dT;
 	bo.bits = c->binBits.as<unsigned>(); bo.bitsCap = bitsCap;
-	k_clear_bits<<<c->smCount * 4, 256, 0, st>>>(c->binBits.as<unsigned>(), bitsCap, dT);
-	launches++;
-	// the two count sweeps are independent: the crossing count runs on the side stream beside the SAT count and the cell scan
-	GPV_CUDA(cudaEventRecord(c->evFork[0], st));
-	GPV_CUDA(cudaStreamWaitEvent(side, c->evFork[0], 0));
-	mark_side(GPV_PHASE_CROSS_COUNT, true);
-	k_cross<false><<<kWorkGrid, kWorkThreads, 0, side>>>(ray48, c->crossFp.as<int4>(), nTri, c->crossWorkOff.as<unsigned>(), g, cx, cy, c->crossCount.as<int>(), nullptr, nullptr, dT);
-	mark_side(GPV_PHASE_CROSS_COUNT, false);
-	GPV_CUDA(cudaEventRecord(c->evJoin[0], side));
+	// (the main stream's kernels are enqueued first: it carries the critical path, the side stream's work hides beside it)
 	mark(GPV_PHASE_BIN_COUNT);
 	k_bin<false><<<kWorkGrid, kWorkThreads, 0, st>>>(tri48, nTri, c->binOff.as<unsigned>(), g, cx, cy, cz, bo);
-	launches += 2;
+	launches++;
 	mark(GPV_PHASE_SCAN);
 	{ // K3 boundary compaction
 		const int V = cells > (1ll << 20) ? 4 : 1; // sub-tiles per tile: beyond a million cells the per-tile latency is amortised over 32 KB of input
@@ -366,12 +408,23 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		else k_scan<MODE_CELLS, 1><<<(unsigned)tiles, kScanThreads, 0, st>>>(io);
 		launches++;
 	}
+	// the two count sweeps are independent: the crossing count runs on the side stream beside the SAT count and the cell scan
+	GPV_CUDA(cudaStreamWaitEvent(side, c->evFork[0], 0));
+	mark_side(GPV_PHASE_CROSS_COUNT, true);
+	k_cross<false><<<kWorkGrid, kWorkThreads, 0, side>>>(ray48, c->crossFp.as<int4>(), nTri, c->crossWorkOff.as<unsigned>(), g, cx, cy, c->crossCount.as<int>(), nullptr, nullptr, dT);
+	launches++;
+	mark_side(GPV_PHASE_CROSS_COUNT, false);
+	GPV_CUDA(cudaEventRecord(c->evJoin[0], side));
 	GPV_CUDA(cudaStreamWaitEvent(st, c->evJoin[0], 0));
 	{
 		const ScanReq r[3] = { { c->colCount.as<int>(), ncol, c->colOff.as<unsigned>(), &dT->colTotalOver, nullptr, dOff[3] },
 			                   { c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, nullptr, dOff[4] },
 			                   { c->colCellCnt.as<int>(), ncol, c->colCellOff.as<unsigned>(), &dT->nLocalCells, nullptr, dOff[5] } };
 		launch_scans(c, st, r, wantL2 ? 3 : 2, launches);
+		if (wantL2) { // the work list of the Level-2 parity rays: (column, chunk of its boundary cells), expensive units first
+			k_ray_units<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(c->colCellOff.as<unsigned>(), c->colCount.as<int>(), ncol, c->rayOver.as<int2>(), rayCap, dT);
+			launches++;
+		}
 	}
 
 	// ---- the one size read-back
@@ -383,7 +436,7 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	if (T1.l1Hits > 0x7ffffff0ull) return fail("more than 2^31 (cell, triangle) pairs in one slab: shard finer");
 	if (T1.binWork > 0xfffffff0ull || T1.crossWork > 0xfffffff0ull) return fail("more than 2^32 (triangle, cell) work items: work offsets are 32-bit");
 	if (T1.binWork > bitsCap) { // the binning sweeps left without doing anything: grow the bitmaps and start the call over (first call of a larger model only)
-		if (c->binBits.ensure((size_t)((T1.binWork + 31) / 32 * 4) * 2 + 64)) return 1;
+		if (c->binBits.ensure((size_t)((T1.binWork + 31) / 32 * 4) * 2 + 64)) return 1; // (a new pool: zeroed by the repeated call)
 		if (gather) c->gather.epoch--; // nothing of this call has reached the mailbox yet: the repeated call takes the same epoch
 		return voxelize_impl(c, d_tris, n_tri, bmin, bmax, max_model_size, prm, stream, out, sink);
 	}
@@ -401,17 +454,23 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	if (gather) {
 		// every rank sees the same global boundary count: a gather buffer that is too small is refused by all of them, before anything is written
 		if (wantL2 && nB * n23 > c->gather.l2Cap) return fail("GPV_GATHER: Level-2 gather buffer too small for the boundary cells of the grid");
-		k_gather_begin<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, c->gather.timeoutNs, dT); // peers wait here until rank 0 has entered this call
-		launches++;
 	}
 	if (sink) {
-		if (sink->level2_inout && wantL2 && (int64_t)(nB * n23) > sink->level2_capacity) return fail("gpv_voxelize_host: level2 host buffer too small");
+		if ((sink->level2_inout || (sink->level2_normal && wantN)) && wantL2 && (int64_t)(nB * n23) > sink->level2_capacity) return fail("gpv_voxelize_host: level2 host buffer too small");
 		if (sink->boundary_index && nB > sink->boundary_capacity) return fail("gpv_voxelize_host: boundary_index host buffer too small");
 	}
+	// main stream first (it carries the critical path): the fill sweep of the binning
+	mark(GPV_PHASE_BIN_FILL);
+	k_bin<true><<<kWorkGrid, kWorkThreads, 0, st>>>(tri48, nTri, c->binOff.as<unsigned>(), g, cx, cy, cz, bo);
+	GPV_CUDA(cudaEventRecord(c->evBinDone, st)); // both bitmaps are dead now: the side stream wipes what this call used (below)
+	launches++;
 	// side stream: the parity-fill branch (crossing lists -> fill sweep -> final Level-1 bytes), independent of the binning / sorting /
-	// Level-2 branch on the main stream until the end of the call
-	GPV_CUDA(cudaEventRecord(c->evFork[1], st));
-	GPV_CUDA(cudaStreamWaitEvent(side, c->evFork[1], 0));
+	// Level-2 branch on the main stream until the end of the call.  (No fork event: the host has just synchronised the main stream.)
+	if (gather) { // peers wait here until rank 0 has entered this call: nothing is stored into its buffers before
+		k_gather_begin<<<1, 1, 0, side>>>(c->gather.mail, c->gather.rank, epoch, c->gather.timeoutNs, dT);
+		GPV_CUDA(cudaEventRecord(c->evFork[1], side)); // the main stream's Level-2 stores wait for it too (below)
+		launches++;
+	}
 	mark_side(GPV_PHASE_CROSS_FILL, true);
 	k_cross<true><<<kWorkGrid, kWorkThreads, 0, side>>>(ray48, c->crossFp.as<int4>(), nTri, c->crossWorkOff.as<unsigned>(), g, cx, cy, c->crossCount.as<int>(), c->crossOff.as<unsigned>(),
 	                                                     c->crossTri.as<int>(), dT);
@@ -423,19 +482,27 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		const size_t slabOff = gather ? (size_t)oz0 * ncol : 0; // offset of the slab inside the whole-grid arrays of a gathering call
 		dim3 grid((g.nx + 31) / 32, g.ny, (oz1 - oz0 + 127) / 128), block(32, 4);
 		k_fill_sweep<<<grid, block, 0, side>>>(ray48, gs, cx, cy, cz, c->crossOff.as<unsigned>(), c->crossTri.as<int>(), c->bmask.as<unsigned char>() + slabOff / 8,
-		                                       gather ? c->gather.l1 + slabOff : c->l1State.as<unsigned char>(), dT);
+		                                       c->l1State.as<unsigned char>() + slabOff, dT);
 		launches += 2;
-		if (gather) { // this slab of the (global) prefix sums -> its final place on the gathering rank
-			const long long n = (long long)(oz1 - oz0) * ncol;
-			k_gather_prefix<<<(unsigned)std::min<long long>(c->smCount * 8, (n / 4 + 255) / 256 + 1), 256, 0, side>>>(c->prefix.as<int>() + slabOff, c->gather.prefix + slabOff, n);
-			launches++;
+		if (gather) {
+			// This slab of the Level-1 bytes and of the (global) prefix sums -> their final place on the gathering rank: two contiguous
+			// ranges, moved by the copy engines over NVLink beside the Level-2 kernels.  (Stored from inside the fill sweep -- 32-byte
+			// writes over NVLink -- the slab took 3x as long and the SMs' store queues held up the parity-ray kernel running beside it.)
+			const size_t n = (size_t)(oz1 - oz0) * ncol;
+			GPV_CUDA(cudaMemcpyAsync(c->gather.l1 + slabOff, c->l1State.as<unsigned char>() + slabOff, n, cudaMemcpyDefault, side));
+			GPV_CUDA(cudaMemcpyAsync(c->gather.prefix + slabOff, c->prefix.as<int>() + slabOff, n * 4, cudaMemcpyDefault, side));
 		}
 	}
 	mark_side(GPV_PHASE_FILL_SWEEP, false);
-	GPV_CUDA(cudaEventRecord(c->evJoin[1], side));
-	mark(GPV_PHASE_BIN_FILL);
-	k_bin<true><<<kWorkGrid, kWorkThreads, 0, st>>>(tri48, nTri, c->binOff.as<unsigned>(), g, cx, cy, cz, bo);
+	if (sink) { // host call: the Level-1 streams are final here and leave on this stream, beside the Level-2 chunks on the copy stream
+		if (sink->level1_inout) GPV_CUDA(cudaMemcpyAsync(sink->level1_inout, c->l1State.p, (size_t)cells, cudaMemcpyDeviceToHost, side));
+		if (sink->prefix) GPV_CUDA(cudaMemcpyAsync(sink->prefix, c->prefix.p, (size_t)cells * 4, cudaMemcpyDeviceToHost, side));
+		if (sink->boundary_index && nB) GPV_CUDA(cudaMemcpyAsync(sink->boundary_index, c->boundaryIndex.p, (size_t)nB * 4, cudaMemcpyDeviceToHost, side));
+	}
+	GPV_CUDA(cudaStreamWaitEvent(side, c->evBinDone, 0));
+	k_clear_bits<<<c->smCount * 4, 256, 0, side>>>(c->binBits.as<unsigned>(), bitsCap, dT); // the next call finds the bitmaps zeroed
 	launches++;
+	GPV_CUDA(cudaEventRecord(c->evJoin[1], side));
 	mark(GPV_PHASE_SORT);
 	if (wantN || (prm->flags & GPV_KEEP_LISTS)) {
 		// canonical (ascending) order of the cell and column lists: needed only where the order shows -- the f32 sums of the normals and
@@ -465,16 +532,13 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			launches++;
 		}
 	}
-	if (sink) { // Level-1 streams are final once the fill sweep (side stream) and the normals are done: send them while Level-2 computes
+	if (sink && sink->level1_normal && wantN) { // (the other Level-1 streams left from the side stream, right behind the fill sweep)
 		GPV_CUDA(cudaEventRecord(c->evChunk[kMaxChunks], st));
 		GPV_CUDA(cudaStreamWaitEvent(c->copyStream, c->evChunk[kMaxChunks], 0));
-		GPV_CUDA(cudaStreamWaitEvent(c->copyStream, c->evJoin[1], 0));
-		if (sink->level1_inout) GPV_CUDA(cudaMemcpyAsync(sink->level1_inout, c->l1State.p, (size_t)cells, cudaMemcpyDeviceToHost, c->copyStream));
-		if (sink->prefix) GPV_CUDA(cudaMemcpyAsync(sink->prefix, c->prefix.p, (size_t)cells * 4, cudaMemcpyDeviceToHost, c->copyStream));
-		if (sink->boundary_index && nB) GPV_CUDA(cudaMemcpyAsync(sink->boundary_index, c->boundaryIndex.p, (size_t)nB * 4, cudaMemcpyDeviceToHost, c->copyStream));
-		if (sink->level1_normal && wantN) GPV_CUDA(cudaMemcpyAsync(sink->level1_normal, c->l1Normal.p, (size_t)cells * 3, cudaMemcpyDeviceToHost, c->copyStream));
+		GPV_CUDA(cudaMemcpyAsync(sink->level1_normal, c->l1Normal.p, (size_t)cells * 3, cudaMemcpyDeviceToHost, c->copyStream));
 	}
 	L2IO lio{};
+	long long packedChunks = 0, packedPer = 0, packedCells = 0; // GPV_PACKED_L2: chunks of 2-bit words on their way to hPacked
 	mark(GPV_PHASE_L2_RAYS);
 	if (wantL2 && nB > 0) {
 		lio.tri48 = tri48; lio.ray48 = ray48; lio.plane16 = c->plane16.as<float4>(); lio.aabbxy16 = c->aabbxy16.as<float4>(); lio.boundaryIndex = c->boundaryIndex.as<int>(); lio.bTriOff = c->bTriOff.as<unsigned>();
@@ -485,36 +549,72 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		const L2K K = l2_constants(g.n2);
 		const int G = K.G;
 		const size_t smem = (size_t)K.total;
-		void (*l2fn)(GridP, L2IO, L2K) = gather ? (g.n2 == 16 ? k_l2<16, true> : g.n2 == 8 ? k_l2<8, true> : g.n2 == 4 ? k_l2<4, true> : g.n2 == 2 ? k_l2<2, true> : k_l2<0, true>)
-		                                        : (g.n2 == 16 ? k_l2<16, false> : g.n2 == 8 ? k_l2<8, false> : g.n2 == 4 ? k_l2<4, false> : g.n2 == 2 ? k_l2<2, false> : k_l2<0, false>);
+		// how the blocks leave k_l2 (L2_OUT_*): file bytes into local HBM; or 2 bits per sub-voxel -- to the gathering rank over NVLink
+		// (peers of a GPV_GATHER call; rank 0 expands them after the wait) or into the staging buffer of the host call (GPV_PACKED_L2;
+		// host threads expand); or, when n2^3 is not a multiple of 32, staged bytes for the peers of a gathering call
+		const bool canPack = (n23 % 32) == 0;
+		const bool packHost = sink && sink->level2_inout && (prm->flags & GPV_PACKED_L2) && canPack;
+		const bool packPeer = gather && c->gather.rank != 0 && canPack;
+		const int outMode = (packHost || packPeer) ? L2_OUT_PACKED : (gather && c->gather.rank != 0) ? L2_OUT_STAGED : L2_OUT_BYTES;
+		typedef void (*L2Fn)(GridP, L2IO, L2K);
+		static const L2Fn table[3][5] = { { k_l2<16, 0>, k_l2<8, 0>, k_l2<4, 0>, k_l2<2, 0>, k_l2<0, 0> },
+			                              { k_l2<16, 1>, k_l2<8, 1>, k_l2<4, 1>, k_l2<2, 1>, k_l2<0, 1> },
+			                              { k_l2<16, 2>, k_l2<8, 2>, k_l2<4, 2>, k_l2<0, 2>, k_l2<0, 2> } }; // (n2 = 2 cannot be packed: canPack is false)
+		const L2Fn l2fn = table[outMode][g.n2 == 16 ? 0 : g.n2 == 8 ? 1 : g.n2 == 4 ? 2 : g.n2 == 2 ? 3 : 4];
+		if (packHost) {
+			if (c->l2Packed.ensure((size_t)(nB * n23) / 4 + 64)) return 1;
+			if (c->hPackedCap < (size_t)(nB * n23) / 4) {
+				if (c->hPacked) cudaFreeHost(c->hPacked);
+				c->hPacked = nullptr; c->hPackedCap = 0;
+				const size_t want = (size_t)(nB * n23) / 4 + (size_t)(nB * n23) / 32 + 4096;
+				GPV_CUDA(cudaHostAlloc(&c->hPacked, want, cudaHostAllocDefault));
+				c->hPackedCap = want;
+			}
+		}
+		lio.l2Packed = packHost ? c->l2Packed.as<unsigned char>() : packPeer ? c->gather.l2p : nullptr;
 		if (smem > 48 * 1024) return fail("k_l2: shared-memory layout exceeds 48 KB"); // cannot happen for n2 <= 32 (41 KB)
 		// K4a: boundary cells grouped by Level-1 column, then the parity bits of every sub-voxel column, one walk of the column list per column
 		k_col_cells<<<(unsigned)((nB + 255) / 256), 256, 0, st>>>(lio.boundaryIndex, (int)nB, (int)ncol, g.nx, cx, cy, cz, lio.colCellOff, c->colCellCnt.as<int>(), c->colCellList.as<int2>(),
 		                                                        c->cellMid.as<float4>(), lio.colCount, lio.bTriOff, own, dT);
-		const long long nGroups = (ncol + G - 1) / G; // GPV_GATHER: group k belongs to rank k % world
-		k_l2_rays<<<(unsigned)((nGroups - own.rank + own.world - 1) / own.world), 256, 0, st>>>(g, lio);
-		launches += 2;
+		const long long nUnits = (long long)T1.nRayHeavy + T1.nRayLight;
+		RayWork rw{ c->rayOver.as<int2>(), rayCap, dT, { c->rayOverflow.as<int4>(), reinterpret_cast<unsigned*>(c->totals.as<char>() + 128) + 2, kRayOverflowCap } }; // (counter zeroed by k_clear)
+		if (nUnits > 0) {
+			k_l2_rays<<<(unsigned)((nUnits + G - 1) / G), 256, 0, st>>>(g, lio, rw);
+			k_l2_rays_overflow<<<c->smCount, 256, 0, st>>>(g, lio, rw.ov); // the few sub-columns with more crossings than register slots
+			launches += 2;
+		}
+		launches++;
 		mark(GPV_PHASE_L2);
 		// With a host sink the boundary cells are refined in chunks and every finished chunk's bytes start their way to the
 		// host on the copy stream while the next chunk computes (e2e is PCIe-bound: 1 B per Level-2 voxel).
 		long long chunks = 1;
 		if (sink && sink->level2_inout) chunks = std::min<long long>(kMaxChunks, std::max<long long>(1, (nB * n23 + (24ll << 20) - 1) / (24ll << 20)));
+		if (packHost) chunks = std::min<long long>(kMaxChunks, std::max<long long>(1, (nB * n23 + (12ll << 20) - 1) / (12ll << 20))); // 3 MB on the bus, 12 MB for the host threads per chunk
 		// the cells this call refines: all boundary ranks, or (GPV_GATHER) this rank's share as listed, column by column, in colCellList
-		const long long nRefine = gather ? (long long)T1.nLocalCells : nB;
-		lio.cellList = gather ? c->colCellList.as<int2>() : nullptr;
+		if (gather) GPV_CUDA(cudaStreamWaitEvent(st, c->evFork[1], 0)); // rank 0 has entered the call: its Level-2 buffer may be written
+		const bool byList = gather || own.world > 1;
+		const long long nRefine = byList ? (long long)T1.nLocalCells : nB;
+		lio.cellList = byList ? c->colCellList.as<int2>() : nullptr;
 		const long long per = ((nRefine + chunks - 1) / chunks + G - 1) / G * G; // whole CTAs per chunk
+		long long nChunks = 0;
 		for (long long k = 0; k < chunks; k++) {
 			const long long bb = k * per, be = std::min(nRefine, bb + per);
 			if (bb >= be) break;
+			nChunks = k + 1;
 			lio.bBegin = (int)bb; lio.nBoundary = (int)be;
 			l2fn<<<(unsigned)((be - bb + G - 1) / G), kL2Threads, smem, st>>>(g, lio, K);
 			launches++;
 			if (sink && sink->level2_inout) {
 				GPV_CUDA(cudaEventRecord(c->evChunk[k], st));
 				GPV_CUDA(cudaStreamWaitEvent(c->copyStream, c->evChunk[k], 0));
-				GPV_CUDA(cudaMemcpyAsync(sink->level2_inout + bb * n23, c->l2State.as<uint8_t>() + bb * n23, (size_t)((be - bb) * n23), cudaMemcpyDeviceToHost, c->copyStream));
+				if (packHost) {
+					GPV_CUDA(cudaMemcpyAsync((char*)c->hPacked + bb * n23 / 4, c->l2Packed.as<uint8_t>() + bb * n23 / 4, (size_t)((be - bb) * n23 / 4), cudaMemcpyDeviceToHost, c->copyStream));
+					GPV_CUDA(cudaEventRecord(c->evCopied[k], c->copyStream));
+				} else
+					GPV_CUDA(cudaMemcpyAsync(sink->level2_inout + bb * n23, c->l2State.as<uint8_t>() + bb * n23, (size_t)((be - bb) * n23), cudaMemcpyDeviceToHost, c->copyStream));
 			}
 		}
+		if (packHost) { packedChunks = nChunks; packedPer = per; packedCells = nRefine; }
 		lio.cellList = nullptr;
 		lio.bBegin = 0; lio.nBoundary = (int)nB;
 		mark(GPV_PHASE_L2_NORMALS);
@@ -528,20 +628,45 @@ static int voxelize_impl(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	if (gather) { // completion flag behind this rank's last store; the gathering rank returns when every rank has signalled
 		k_gather_done<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, dT);
 		launches++;
-		if (c->gather.rank == 0) { k_gather_wait<<<1, 1, 0, st>>>(c->gather.mail, c->gather.world, epoch, c->gather.timeoutNs, dT); launches++; }
+		if (c->gather.rank == 0) {
+			k_gather_wait<<<1, 1, 0, st>>>(c->gather.mail, c->gather.world, epoch, c->gather.timeoutNs, dT);
+			launches++;
+			if (wantL2 && nB > 0 && c->gather.world > 1 && (n23 % 32) == 0) { // the peers sent 2 bits per sub-voxel: the file bytes of their blocks
+				const long long nWords = nB * n23 / 32;
+				k_l2_expand<<<(unsigned)std::min<long long>(c->smCount * 8, (nWords + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint2*>(c->gather.l2p), c->gather.l2, nWords, (int)(n23 / 32),
+				                                                                                                   c->boundaryIndex.as<int>(), (int)ncol, own);
+				launches++;
+			}
+		}
 	}
 	mark(GPV_PHASE_COUNT);
-	GPV_CUDA(cudaMemcpyAsync(c->hTotals, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
+	GPV_CUDA(cudaMemcpyAsync(c->hTotals, dT, 144, cudaMemcpyDeviceToHost, st)); // Totals + the sort's and the ray overflow's counters
+	if (packedChunks) {
+		// Every launch and copy of the call is queued: the calling thread now follows the packed Level-2 chunks as they land and hands
+		// each to the host threads, which write the caller's byte stream while the next chunk is on the bus.
+		ExpandPool* pool = expand_pool_get();
+		expand_pool_begin(pool);
+		for (long long k = 0; k < packedChunks; k++) {
+			const long long bb = k * packedPer, be = std::min(packedCells, bb + packedPer);
+			const cudaError_t e = cudaEventSynchronize(c->evCopied[k]);
+			if (e != cudaSuccess) { expand_pool_end(pool); return fail(std::string("cudaEventSynchronize: ") + cudaGetErrorString(e)); }
+			expand_pool_submit(pool, (const char*)c->hPacked + bb * n23 / 4, sink->level2_inout + bb * n23, (size_t)((be - bb) * n23 / 32));
+		}
+		expand_pool_end(pool);
+	}
 	GPV_CUDA(cudaStreamSynchronize(st));
 	if (sink) GPV_CUDA(cudaStreamSynchronize(c->copyStream));
 	GPV_CUDA(cudaGetLastError());
 	const Totals T2 = *c->hTotals;
+	if (reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(c->hTotals) + 128)[2] > kRayOverflowCap)
+		return fail("more than 2^20 Level-2 sub-columns with over 16 ray crossings: not supported");
+	c->cleanCellCount = c->cellCount.p; c->cleanCellBytes = (size_t)cells * 4; c->cleanBits = c->binBits.p; // the call ran to its end: counters are back to zero
 	if (gather && T2.gatherError) return fail("GPV_GATHER: timed out waiting for a peer rank");
 	if (gather) c->gather.nbTotal = nB; // the boundary ranks are global on every rank
 
 	out->z0 = oz0; out->z1 = oz1;
 	out->cells = cells; out->n_boundary = nB; out->n23 = n23; out->n_refined = wantL2 ? (gather ? (int64_t)T2.nLocalCells : nB) : 0;
-	out->d_level1_inout = gather ? c->gather.l1 + (size_t)oz0 * ncol : c->l1State.as<uint8_t>(); // gather: this slab's bytes where they landed
+	out->d_level1_inout = c->l1State.as<uint8_t>() + (gather ? (size_t)oz0 * ncol : 0); // this call's slab of the bytes (gather: a copy went to rank 0)
 	out->d_prefix = c->prefix.as<int32_t>();                                                          // the call's own sums (gather: the whole grid's)
 	out->d_boundary_index = c->boundaryIndex.as<int32_t>();
 	out->d_level2_inout = !wantL2 ? nullptr : gather ? c->gather.l2 : c->l2State.as<uint8_t>();
@@ -616,11 +741,13 @@ extern "C" int gpv_gather_set_timeout(gpv_ctx* c, double seconds)
 	return 0;
 }
 
+static size_t gather_packed_offset(int64_t l2Cap) { return ((size_t)l2Cap + 255) & ~(size_t)255; } // the peers' 2-bit blocks live behind the byte stream
+
 extern "C" int gpv_gather_create(gpv_ctx* c, int64_t cells_total, int64_t l2_capacity, gpv_gather_desc* out)
 {
 	if (!c || !out || cells_total <= 0 || l2_capacity < 0) return fail("gpv_gather_create: bad argument");
 	GPV_CUDA(cudaSetDevice(c->device));
-	if (c->gatherL1.ensure((size_t)cells_total + 64) || c->gatherPrefix.ensure((size_t)cells_total * 4 + 64) || c->gatherL2.ensure((size_t)l2_capacity + 64) ||
+	if (c->gatherL1.ensure((size_t)cells_total + 64) || c->gatherPrefix.ensure((size_t)cells_total * 4 + 64) || c->gatherL2.ensure(gather_packed_offset(l2_capacity) + (size_t)l2_capacity / 4 + 64) ||
 	    c->gatherMail.ensure(sizeof(GatherMail)))
 		return 1;
 	GPV_CUDA(cudaMemset(c->gatherMail.p, 0, sizeof(GatherMail)));
@@ -644,6 +771,7 @@ static int gather_bind(gpv_ctx* c, void* l1, void* prefix, void* l2, void* mail,
 	if (rank < 0 || world < 1 || rank >= world || world > 16) return fail("gpv_gather_attach: bad rank / world (at most 16 ranks)");
 	c->gather.on = true; c->gather.ipc = ipc; c->gather.rank = rank; c->gather.world = world; c->gather.epoch = 0;
 	c->gather.l1 = (uint8_t*)l1; c->gather.prefix = (int32_t*)prefix; c->gather.l2 = (uint8_t*)l2; c->gather.mail = (GatherMail*)mail;
+	c->gather.l2p = (uint8_t*)l2 + gather_packed_offset(l2Cap);
 	c->gather.cellsTotal = cellsTotal; c->gather.l2Cap = l2Cap;
 	return 0;
 }
@@ -707,6 +835,13 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters)
 		a0 = a0 + d; a1 = a1 * m; a2 = a2 + d; a3 = a3 * m; a4 = a4 + d; a5 = a5 * m; a6 = a6 + d; a7 = a7 * m;
 	}
 	if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
+}
+
+extern "C" int gpv_expand_packed_l2(const void* packed, int64_t n_words, uint8_t* out)
+{
+	if (!packed || !out || n_words < 0) return fail("gpv_expand_packed_l2: bad argument");
+	expand_packed(packed, out, (size_t)n_words);
+	return 0;
 }
 
 extern "C" int gpv_measure_fp32_peak(gpv_ctx* c, void* stream, double* ops)

@@ -41,6 +41,7 @@ struct Totals {
 	unsigned long long gatherError; // 2 timed out waiting for a peer
 	unsigned int nBoundary, triTotal, colTotalOver, crossTotal;
 	unsigned int nLocalCells;       // boundary cells this rank refines (GPV_GATHER: those in the Level-1 columns it owns)
+	unsigned int nRayHeavy, nRayLight; // units of k_l2_rays (k_ray_units): heavy ones are listed from the front, light ones from the back
 };
 
 // GPV_GATHER: which rank refines a Level-1 column.  Columns are dealt out in groups of `group` consecutive columns (the columns one
@@ -754,6 +755,7 @@ struct L2IO {
 	const float4* cellMid;                              // [boundary rank] centre of the Level-1 cell (k_col_cells)
 	const float* cx; const float* cy; const float* cz;
 	unsigned char* l2State; // nBoundary * n2^3 file bytes (local, or the gathering rank's buffer over NVLink)
+	unsigned char* l2Packed; // L2_OUT_PACKED: nBoundary * n2^3 / 4 bytes, 2 bits per sub-voxel (local, or the gathering rank's buffer)
 	const int2* cellList;   // GPV_GATHER: k_l2 refines the cells cellList[bBegin .. nBoundary) (.x = boundary rank; this rank's share, grouped
 	                        // by column = colCellList); null: the boundary ranks [bBegin, nBoundary) themselves
 	int bBegin;             // this launch refines slots [bBegin, nBoundary)
@@ -800,13 +802,15 @@ __global__ void k_col_cells(const int* __restrict__ boundaryIndex, int nBoundary
 // evaluated).  Output: one word per (boundary cell, sub-column), bit r = parity of sub-voxel r; k_l2 only loads it.
 constexpr int kRaySlots = 16; // crossings kept in registers (16-bit list positions); further ones are applied in a second walk of the list (rare)
 constexpr int kRayCells = 8;  // boundary cells of the column refined per register chunk
-constexpr int kL2Stage = 256; // ray records staged per chunk (12 KB)
+constexpr int kL2Stage = 512; // ray records staged per chunk (24 KB); a list that fits stays staged for rays_apply
 
 struct RaySub { // one sub-voxel column: origin, list, cells, output slot, height range of the grid column
-	float ox, oy, zMin, zMax, inv101, inv099; unsigned off; int cnt; unsigned cb, ce; int item;
+	float ox, oy, zMin, zMax, inv101, inv099; unsigned off; int cnt; unsigned cb, ce; int item; int col;
 };
+// sub-columns with more crossings than kRaySlots (or list positions beyond 16 bits) are finished by k_l2_rays_overflow, a warp each
+struct RayOverflow { int4* list; unsigned* count; unsigned cap; }; // (column, first cell, end cell, item)
 
-__device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const RaySub& u, const uint4 pk0, const uint4 pk1, const unsigned n)
+__device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const RayOverflow& ov, const RaySub& u, const uint4 pk0, const uint4 pk1, const unsigned n, const float4* sRec)
 {
 	const int rows = g.n2 * g.n2;
 	const unsigned nk = min(n, (unsigned)kRaySlots);
@@ -824,7 +828,12 @@ __device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const
 			const unsigned w = j >> 1;
 			const unsigned v = w == 0 ? pk0.x : w == 1 ? pk0.y : w == 2 ? pk0.z : w == 3 ? pk0.w : w == 4 ? pk1.x : w == 5 ? pk1.y : w == 6 ? pk1.z : pk1.w;
 			RayTri s;
-			load_ray(s, io.ray48, io.colTris[u.off + ((v >> ((j & 1) * 16)) & 0xffffu)]);
+			const unsigned pos = (v >> ((j & 1) * 16)) & 0xffffu;
+			if (sRec) { // the whole column list is still staged in shared memory (G == 1, list <= kL2Stage): no dependent global loads per crossing
+				const float4 a = sRec[pos * 3], b = sRec[pos * 3 + 1], c4 = sRec[pos * 3 + 2];
+				s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;
+				s.e2z = c4.x; s.det = c4.y; s.inv = c4.z; s.ok = c4.w != 0.f; s.well = c4.w == 2.f;
+			} else load_ray(s, io.ray48, io.colTris[u.off + pos]);
 			RayCol rc;
 			if (!ray_column(s, u.ox, u.oy, rc)) continue; // cannot happen (listed because it passed); keeps rc defined
 			const RayColZ k1 = ray_col_bound(s, rc, u.zMin, u.zMax, g.gsz, u.inv101, u.inv099);
@@ -855,24 +864,12 @@ __device__ __forceinline__ void rays_apply(const GridP& g, const L2IO& io, const
 #pragma unroll
 		for (int c = 0; c < kRayCells; c++) if (bb[c] >= 0) io.l2Par[(size_t)bb[c] * rows + u.item] = par[c];
 	}
+	// more crossings than slots (0.02 % of cessna-256's sub-columns have more than 15), or list positions beyond 16 bits: the remaining
+	// crossings are folded in by k_l2_rays_overflow, a warp per sub-column (walking the list again here, one dependent load after the
+	// other, made this thread the longest-running one of the whole kernel)
 	if (n > (unsigned)kRaySlots || u.cnt > 65536) {
-		// more crossings than slots (0.02 % of cessna-256's sub-columns have more than 15), or list positions beyond 16 bits: walk
-		// the list again and fold the remaining crossings into this thread's own words
-		unsigned seen = 0;
-		const bool all = u.cnt > 65536; // positions were not recorded reliably: redo every crossing
-		if (all) for (unsigned cc = u.cb; cc < u.ce; cc++) io.l2Par[(size_t)io.colCellList[cc].x * rows + u.item] = 0u;
-		for (int k = 0; k < u.cnt; k++) {
-			RayTri s;
-			load_ray(s, io.ray48, io.colTris[u.off + k]);
-			RayCol rc;
-			if (!s.ok || !ray_column(s, u.ox, u.oy, rc)) continue;
-			if (!all && seen++ < (unsigned)kRaySlots) continue;
-			const RayColZ k1 = ray_col_bound(s, rc, u.zMin, u.zMax, g.gsz, u.inv101, u.inv099);
-			for (unsigned cc = u.cb; cc < u.ce; cc++) {
-				const int2 e = io.colCellList[cc];
-				io.l2Par[(size_t)e.x * rows + u.item] ^= ray_cell_mask(s, rc, k1, __int_as_float(e.y), g.h1z, g.h2z, g.n2);
-			}
-		}
+		const unsigned at = atomicAdd(ov.count, 1u);
+		if (at < ov.cap) ov.list[at] = make_int4(u.col, (int)u.cb, (int)u.ce, u.item); // (beyond the capacity the host sees the count and fails the call)
 	}
 }
 
@@ -885,90 +882,185 @@ __device__ __forceinline__ void rays_note(uint4& pk0, uint4& pk1, unsigned& n, u
 	n++;
 }
 
-__global__ void __launch_bounds__(256, 3) k_l2_rays(GridP g, L2IO io)
+// A Level-1 column with many boundary cells (a column that runs along a wall of the model: cessna-256 has columns with more than a
+// hundred) would keep ONE CTA busy long after the rest of the grid has drained -- the kernel's time was that column's time, on one
+// GPU as on eight.  So the unit of work is a column AND at most kRayChunk of its boundary cells.  k_ray_units lists the units of
+// all columns that have boundary cells (so empty columns cost nothing), the expensive ones -- long column list or a full chunk --
+// from the front of the array and the cheap ones from its back: CTAs are dealt out in index order, so the long units start first
+// and the short ones fill the tail.  A further chunk of a column repeats the walk of its list.
+constexpr int kRayChunk = 16;
+struct RayWork { const int2* units; long long cap; const Totals* totals; RayOverflow ov; }; // unit = (column, first entry of colCellList); cap = array length
+
+__global__ void __launch_bounds__(256) k_ray_units(const unsigned* __restrict__ colCellOff, const int* __restrict__ colCount, long long ncol, int2* units, long long cap, Totals* totals)
 {
-	__shared__ float4 sStage[kL2Stage * 3]; // G == 1: ray records of the column list, kL2Stage at a time
-	const int n2 = g.n2, rows = n2 * n2;
-	const int G = max(1, 256 / rows);
-	const int tid = threadIdx.x;
-	const long long ncol = (long long)g.nx * g.ny;
+	const long long col = (long long)blockIdx.x * 256 + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	unsigned cb = 0, cnt = 0;
+	int len = 0;
+	if (col < ncol) { cb = colCellOff[col]; cnt = colCellOff[col + 1] - cb; len = colCount[col]; }
+	const unsigned n = (cnt + kRayChunk - 1) / kRayChunk;
+	const bool heavy = len > 64 || cnt >= kRayChunk;
+	unsigned nh = heavy ? n : 0u, nl = heavy ? 0u : n, ih = nh, il = nl;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const unsigned a = __shfl_up_sync(0xffffffffu, ih, o), b = __shfl_up_sync(0xffffffffu, il, o);
+		if (lane >= o) { ih += a; il += b; }
+	}
+	unsigned bh = 0, bl = 0;
+	if (lane == 31) { if (ih) bh = atomicAdd(&totals->nRayHeavy, ih); if (il) bl = atomicAdd(&totals->nRayLight, il); }
+	bh = __shfl_sync(0xffffffffu, bh, 31) + ih - nh; bl = __shfl_sync(0xffffffffu, bl, 31) + il - nl;
+	for (unsigned k = 0; k < n; k++) {
+		const int2 u = make_int2((int)col, (int)(cb + k * kRayChunk));
+		if (heavy) units[bh + k] = u; else units[cap - 1 - (long long)(bl + k)] = u;
+	}
+}
+
+// G == 1 (n2 >= 16): the CTA's 256 threads are 256 sub-voxel columns of ONE Level-1 column; cells [cb, ce) of colCellList
+__device__ __forceinline__ void rays_unit_cta(const GridP& g, const L2IO& io, const RayOverflow& ov, float4* sStage, int col, unsigned cb, unsigned ce)
+{
+	const int n2 = g.n2, rows = n2 * n2, tid = threadIdx.x;
 	const float invN2 = 1.f / (float)n2;
-	const long long group = io.own.world > 1 ? (long long)blockIdx.x * io.own.world + io.own.rank : (long long)blockIdx.x; // GPV_GATHER: this rank's groups only
-	if (G == 1) {
-		const int col = (int)group;
-		if (col >= ncol) return;
-		RaySub u;
-		u.cb = io.colCellOff[col]; u.ce = io.colCellOff[col + 1];
-		if (u.cb == u.ce) return;
-		const int jy = col / g.nx, ix = col - jy * g.nx;
-		u.off = io.colOff[col]; u.cnt = io.colCount[col];
-		u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz; u.inv101 = 1.f / (2.02f * g.h2z); u.inv099 = 1.f / (1.98f * g.h2z);
-		const float mx = io.cx[ix], my = io.cy[jy];
-		for (int item0 = 0; item0 < rows; item0 += 256) { // one round unless n2 = 32
-			u.item = item0 + tid;
-			const int q = fast_div(u.item, invN2), p = u.item - q * n2;
-			u.ox = l2_centre(p, g.h2x, mx, g.h1x); u.oy = l2_centre(q, g.h2y, my, g.h1y); // cu:472-473
-			uint4 pk0 = make_uint4(0u, 0u, 0u, 0u), pk1 = pk0;
-			unsigned n = 0;
-			for (int k0 = 0; k0 < u.cnt; k0 += kL2Stage) {
-				const int nrec = min(kL2Stage, u.cnt - k0);
-				__syncthreads();
-				for (int i = tid; i < nrec * 3; i += 256) {
-					const int rec = i / 3;
-					sStage[i] = __ldg(io.ray48 + (size_t)io.colTris[u.off + k0 + rec] * 3 + (i - rec * 3));
-				}
-				__syncthreads();
-				if (u.item < rows) {
-					for (int k = 0; k < nrec; k++) {
-						const float4 a = sStage[k * 3], b = sStage[k * 3 + 1], c4 = sStage[k * 3 + 2];
-						if (c4.w == 0.f) continue;
-						RayTri s;
-						s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;
-						s.e2z = c4.x; s.det = c4.y; s.inv = c4.z; s.ok = true; s.well = false;
-						RayCol rc;
-						if (ray_column(s, u.ox, u.oy, rc)) rays_note(pk0, pk1, n, (unsigned)(k0 + k));
-					}
-				}
-			}
-			if (u.item < rows) rays_apply(g, io, u, pk0, pk1, n);
-		}
-	} else {
-		const int gi = fast_div(tid, 1.f / (float)rows);
-		const long long col = group * G + gi;
-		if (gi >= G || col >= ncol) return;
-		RaySub u;
-		u.cb = io.colCellOff[col]; u.ce = io.colCellOff[col + 1];
-		if (u.cb == u.ce) return;
-		u.item = tid - gi * rows;
-		const int jy = (int)(col / g.nx), ix = (int)(col - (long long)jy * g.nx);
+	RaySub u;
+	u.cb = cb; u.ce = ce; u.col = col;
+	const int jy = col / g.nx, ix = col - jy * g.nx;
+	u.off = io.colOff[col]; u.cnt = io.colCount[col];
+	u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz; u.inv101 = 1.f / (2.02f * g.h2z); u.inv099 = 1.f / (1.98f * g.h2z);
+	const float mx = io.cx[ix], my = io.cy[jy];
+	for (int item0 = 0; item0 < rows; item0 += 256) { // one round unless n2 = 32
+		u.item = item0 + tid;
 		const int q = fast_div(u.item, invN2), p = u.item - q * n2;
-		u.ox = l2_centre(p, g.h2x, io.cx[ix], g.h1x); u.oy = l2_centre(q, g.h2y, io.cy[jy], g.h1y);
-		u.off = io.colOff[col]; u.cnt = io.colCount[col];
-		u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz; u.inv101 = 1.f / (2.02f * g.h2z); u.inv099 = 1.f / (1.98f * g.h2z);
+		u.ox = l2_centre(p, g.h2x, mx, g.h1x); u.oy = l2_centre(q, g.h2y, my, g.h1y); // cu:472-473
 		uint4 pk0 = make_uint4(0u, 0u, 0u, 0u), pk1 = pk0;
 		unsigned n = 0;
-		// the walk is a chain of dependent loads (list entry -> ray record): four entries at a time keep four chains in flight
-		for (int k0 = 0; k0 < u.cnt; k0 += 4) {
-			int t[4];
-			float4 ra[4], rb[4], rc4[4];
-#pragma unroll
-			for (int j = 0; j < 4; j++) t[j] = k0 + j < u.cnt ? io.colTris[u.off + k0 + j] : -1;
-#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				if (t[j] >= 0) { ra[j] = __ldg(io.ray48 + (size_t)t[j] * 3); rb[j] = __ldg(io.ray48 + (size_t)t[j] * 3 + 1); rc4[j] = __ldg(io.ray48 + (size_t)t[j] * 3 + 2); }
-				else rc4[j] = make_float4(0.f, 0.f, 0.f, 0.f); // class 0: never hits
+		for (int k0 = 0; k0 < u.cnt; k0 += kL2Stage) {
+			const int nrec = min(kL2Stage, u.cnt - k0);
+			__syncthreads();
+			for (int i = tid; i < nrec * 3; i += 256) {
+				const int rec = i / 3;
+				sStage[i] = __ldg(io.ray48 + (size_t)io.colTris[u.off + k0 + rec] * 3 + (i - rec * 3));
 			}
-#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				if (rc4[j].w == 0.f) continue;
-				RayTri s;
-				s.v1x = ra[j].x; s.v1y = ra[j].y; s.v1z = ra[j].z; s.e1x = ra[j].w; s.e1y = rb[j].x; s.e1z = rb[j].y; s.e2x = rb[j].z; s.e2y = rb[j].w;
-				s.e2z = rc4[j].x; s.det = rc4[j].y; s.inv = rc4[j].z; s.ok = true; s.well = false;
-				RayCol rc;
-				if (ray_column(s, u.ox, u.oy, rc)) rays_note(pk0, pk1, n, (unsigned)(k0 + j));
+			__syncthreads();
+			if (u.item < rows) {
+				for (int k = 0; k < nrec; k++) {
+					const float4 a = sStage[k * 3], b = sStage[k * 3 + 1], c4 = sStage[k * 3 + 2];
+					if (c4.w == 0.f) continue;
+					RayTri s;
+					s.v1x = a.x; s.v1y = a.y; s.v1z = a.z; s.e1x = a.w; s.e1y = b.x; s.e1z = b.y; s.e2x = b.z; s.e2y = b.w;
+					s.e2z = c4.x; s.det = c4.y; s.inv = c4.z; s.ok = true; s.well = false;
+					RayCol rc;
+					if (ray_column(s, u.ox, u.oy, rc)) rays_note(pk0, pk1, n, (unsigned)(k0 + k));
+				}
 			}
 		}
-		rays_apply(g, io, u, pk0, pk1, n);
+		if (u.item < rows) rays_apply(g, io, ov, u, pk0, pk1, n, u.cnt <= kL2Stage ? sStage : nullptr);
+	}
+}
+
+// G > 1 (n2 < 16): a thread is one sub-voxel column of its own Level-1 column; no CTA-wide step
+__device__ __forceinline__ void rays_unit_thread(const GridP& g, const L2IO& io, const RayOverflow& ov, long long col, unsigned cb, unsigned ce, int item)
+{
+	const int n2 = g.n2;
+	const float invN2 = 1.f / (float)n2;
+	RaySub u;
+	u.cb = cb; u.ce = ce; u.item = item; u.col = (int)col;
+	const int jy = (int)(col / g.nx), ix = (int)(col - (long long)jy * g.nx);
+	const int q = fast_div(u.item, invN2), p = u.item - q * n2;
+	u.ox = l2_centre(p, g.h2x, io.cx[ix], g.h1x); u.oy = l2_centre(q, g.h2y, io.cy[jy], g.h1y);
+	u.off = io.colOff[col]; u.cnt = io.colCount[col];
+	u.zMin = io.cz[0] - g.gsz; u.zMax = io.cz[g.nz - 1] + g.gsz; u.inv101 = 1.f / (2.02f * g.h2z); u.inv099 = 1.f / (1.98f * g.h2z);
+	uint4 pk0 = make_uint4(0u, 0u, 0u, 0u), pk1 = pk0;
+	unsigned n = 0;
+	// the walk is a chain of dependent loads (list entry -> ray record): four entries at a time keep four chains in flight
+	for (int k0 = 0; k0 < u.cnt; k0 += 4) {
+		int t[4];
+		float4 ra[4], rb[4], rc4[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) t[j] = k0 + j < u.cnt ? io.colTris[u.off + k0 + j] : -1;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			if (t[j] >= 0) { ra[j] = __ldg(io.ray48 + (size_t)t[j] * 3); rb[j] = __ldg(io.ray48 + (size_t)t[j] * 3 + 1); rc4[j] = __ldg(io.ray48 + (size_t)t[j] * 3 + 2); }
+			else rc4[j] = make_float4(0.f, 0.f, 0.f, 0.f); // class 0: never hits
+		}
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			if (rc4[j].w == 0.f) continue;
+			RayTri s;
+			s.v1x = ra[j].x; s.v1y = ra[j].y; s.v1z = ra[j].z; s.e1x = ra[j].w; s.e1y = rb[j].x; s.e1z = rb[j].y; s.e2x = rb[j].z; s.e2y = rb[j].w;
+			s.e2z = rc4[j].x; s.det = rc4[j].y; s.inv = rc4[j].z; s.ok = true; s.well = false;
+			RayCol rc;
+			if (ray_column(s, u.ox, u.oy, rc)) rays_note(pk0, pk1, n, (unsigned)(k0 + j));
+		}
+	}
+	rays_apply(g, io, ov, u, pk0, pk1, n, nullptr);
+}
+
+// one CTA per G units (G = columns per CTA: 1 for n2 >= 16, else 256 / n2^2)
+__global__ void __launch_bounds__(256, 3) k_l2_rays(GridP g, L2IO io, RayWork w)
+{
+	__shared__ float4 sStage[kL2Stage * 3]; // G == 1: ray records of the column list, kL2Stage at a time
+	const int rows = g.n2 * g.n2;
+	const int G = max(1, 256 / rows);
+	const int tid = threadIdx.x;
+	const long long nHeavy = w.totals->nRayHeavy, nUnits = nHeavy + w.totals->nRayLight;
+	auto unit = [&](long long k) { return k < nHeavy ? w.units[k] : w.units[w.cap - 1 - (k - nHeavy)]; };
+	if (G == 1) {
+		if (blockIdx.x >= nUnits) return;
+		const int2 e = unit(blockIdx.x);
+		rays_unit_cta(g, io, w.ov, sStage, e.x, (unsigned)e.y, min(io.colCellOff[e.x + 1], (unsigned)e.y + kRayChunk));
+	} else {
+		const int gi = fast_div(tid, 1.f / (float)rows);
+		const long long k = (long long)blockIdx.x * G + gi;
+		if (gi >= G || k >= nUnits) return;
+		const int2 e = unit(k);
+		rays_unit_thread(g, io, w.ov, e.x, (unsigned)e.y, min(io.colCellOff[e.x + 1], (unsigned)e.y + kRayChunk), tid - gi * rows);
+	}
+}
+
+// The sub-columns k_l2_rays could not finish (RayOverflow): a warp per sub-column walks the column list 32 entries at a time; the
+// crossings are numbered in list order by ballot, those beyond the kRaySlots k_l2_rays has applied already (or all of them when
+// the list is too long for 16-bit positions: the words are zeroed first) are XOR-ed into the sub-column's words of every cell of
+// the unit.
+__global__ void __launch_bounds__(256) k_l2_rays_overflow(GridP g, L2IO io, RayOverflow ov)
+{
+	const int lane = threadIdx.x & 31, rows = g.n2 * g.n2;
+	const unsigned nEntries = min(*ov.count, ov.cap);
+	const float zMin = io.cz[0] - g.gsz, zMax = io.cz[g.nz - 1] + g.gsz, inv101 = 1.f / (2.02f * g.h2z), inv099 = 1.f / (1.98f * g.h2z);
+	for (unsigned w = (blockIdx.x * 256 + threadIdx.x) >> 5; w < nEntries; w += (gridDim.x * 256) >> 5) {
+		const int4 e = ov.list[w];
+		const int col = e.x, item = e.w;
+		const unsigned cb = (unsigned)e.y, ce = (unsigned)e.z;
+		const int jy = col / g.nx, ix = col - jy * g.nx;
+		const int q = fast_div(item, 1.f / (float)g.n2), p = item - q * g.n2;
+		const float ox = l2_centre(p, g.h2x, io.cx[ix], g.h1x), oy = l2_centre(q, g.h2y, io.cy[jy], g.h1y);
+		const unsigned off = io.colOff[col];
+		const int cnt = io.colCount[col];
+		const bool all = cnt > 65536;
+		if (all) {
+			for (unsigned cc = cb + lane; cc < ce; cc += 32) io.l2Par[(size_t)io.colCellList[cc].x * rows + item] = 0u;
+			__syncwarp();
+		}
+		unsigned seen = 0;
+		for (int k0 = 0; k0 < cnt; k0 += 32) {
+			const int k = k0 + lane;
+			bool hit = false;
+			RayTri s;
+			RayCol rc;
+			if (k < cnt) {
+				load_ray(s, io.ray48, io.colTris[off + k]);
+				hit = s.ok && ray_column(s, ox, oy, rc);
+			}
+			const unsigned m = __ballot_sync(0xffffffffu, hit);
+			const unsigned ordinal = seen + __popc(m & ((1u << lane) - 1u));
+			seen += __popc(m);
+			if (hit && (all || ordinal >= (unsigned)kRaySlots)) {
+				const RayColZ k1 = ray_col_bound(s, rc, zMin, zMax, g.gsz, inv101, inv099);
+				for (unsigned cc = cb; cc < ce; cc++) {
+					const int2 c2 = io.colCellList[cc];
+					const unsigned msk = ray_cell_mask(s, rc, k1, __int_as_float(c2.y), g.h1z, g.h2z, g.n2);
+					if (msk) atomicXor(io.l2Par + (size_t)c2.x * rows + item, msk);
+				}
+			}
+		}
 	}
 }
 
@@ -1008,8 +1100,15 @@ inline L2K l2_constants(int n2)
 // layout (bit r = sub-voxel r) and no transposition is needed.  Everything of the SAT that does not involve z is hoisted
 // per (column, triangle) (gpv::SatCol).
 // N2 > 0: n2 fixed at compile time (2, 4, 8, 16: index arithmetic by shifts, unrolled byte loop); N2 = 0: any n2 <= 32.
-// GATHER: the output block goes to the gathering rank over NVLink (staged in shared memory, 128-bit stores) instead of local HBM.
-template <int N2, bool GATHER>
+// OUT: how the cells' blocks leave the CTA
+//   L2_OUT_BYTES   file bytes straight to local HBM (a warp's byte stores cover 32 consecutive sub-voxels)
+//   L2_OUT_STAGED  file bytes staged in shared memory, every cell's n2^3 bytes leave as one run of 128-bit stores (peer memory over NVLink)
+//   L2_OUT_PACKED  2 bits per sub-voxel: one uint2 (inside mask, boundary mask) per 32 consecutive sub-voxels of Level2InOut.raw, staged
+//                  in shared memory, n2^3 / 4 bytes per cell at (boundary rank) * n2^3 / 4 of io.l2Packed -- a quarter of the bytes over
+//                  NVLink (gather) or PCIe (host call); k_l2_expand / the host threads of gpv_voxelize_host turn it into the file bytes.
+//                  Needs n2^3 % 32 == 0 (n2 a multiple of 4).
+enum { L2_OUT_BYTES = 0, L2_OUT_STAGED = 1, L2_OUT_PACKED = 2 };
+template <int N2, int OUT>
 __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2IO io, L2K K)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -1202,7 +1301,53 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	// four sub-voxels at once: (nibble * 0x204081) & 0x01010101 spreads bit k of the nibble to byte k
 	auto four = [](unsigned par, unsigned sat, int r) { return (((par >> r) & 15u) * 0x204081u & 0x01010101u) * 127u + (((sat >> r) & 15u) * 0x204081u & 0x01010101u) * 254u; };
 	unsigned nIn = 0, nBd = 0;
-	if (GATHER) {
+	if (OUT == L2_OUT_PACKED) {
+		uint2* sPk = reinterpret_cast<uint2*>(smemRaw + K.q1); // [G][n2^3 / 32] (inside, boundary) masks in file order
+		const int n23 = rows * n2, wpc = n23 >> 5;           // words per cell
+		constexpr bool kBallot = N2 == 16 || N2 == 8;          // rows % 32 == 0: a warp holds 32 consecutive columns of one cell
+		if (!kBallot) {
+			for (int k = tid; k < G * wpc; k += kL2Threads) sPk[k] = make_uint2(0u, 0u);
+			__syncthreads();
+		}
+		for (int item0 = 0; item0 < nItems; item0 += kL2Threads) { // (uniform trip count: ballots inside)
+			const int item = item0 + tid;
+			const int gi = item < nItems ? div_rows(item) : 0, pq = item - gi * rows;
+			const long long b = item < nItems ? sB[gi] : -1;
+			unsigned sat = 0u, par = 0u;
+			if (b >= 0) { sat = sSat[item]; par = io.l2Par[(size_t)b * rows + pq] & ~sat; }
+			nIn += __popc(par); nBd += __popc(sat);
+			if (kBallot) {
+#pragma unroll
+				for (int r = 0; r < (N2 ? N2 : 1); r++) {
+					const unsigned mi = __ballot_sync(0xffffffffu, (par >> r) & 1u), mb = __ballot_sync(0xffffffffu, (sat >> r) & 1u);
+					if (lane == (r & 31)) sPk[gi * wpc + ((r * rows + pq) >> 5)] = make_uint2(mi, mb); // lane r's own (gi, pq) lies in the same word as lane 0's
+				}
+			} else if (N2 == 4) { // rows = 16: lanes 0-15 are one cell, 16-31 the next; a word is two z-layers of 16 columns
+#pragma unroll
+				for (int k = 0; k < 2; k++) {
+					const unsigned i0 = __ballot_sync(0xffffffffu, (par >> (2 * k)) & 1u), i1 = __ballot_sync(0xffffffffu, (par >> (2 * k + 1)) & 1u);
+					const unsigned b0m = __ballot_sync(0xffffffffu, (sat >> (2 * k)) & 1u), b1m = __ballot_sync(0xffffffffu, (sat >> (2 * k + 1)) & 1u);
+					if (lane == 0) sPk[gi * wpc + k] = make_uint2((i0 & 0xffffu) | (i1 << 16), (b0m & 0xffffu) | (b1m << 16));
+					if (lane == 16) sPk[gi * wpc + k] = make_uint2((i0 >> 16) | (i1 & 0xffff0000u), (b0m >> 16) | (b1m & 0xffff0000u));
+				}
+			} else if (b >= 0) { // any other n2 with n2^3 % 32 == 0: bit by bit
+				unsigned* w = reinterpret_cast<unsigned*>(sPk);
+				for (int r = 0; r < n2; r++) {
+					const int v = gi * n23 + r * rows + pq;
+					if ((par >> r) & 1u) atomicOr(w + (v >> 5) * 2, 1u << (v & 31));
+					if ((sat >> r) & 1u) atomicOr(w + (v >> 5) * 2 + 1, 1u << (v & 31));
+				}
+			}
+		}
+		__syncthreads();
+		const int nValid = (int)max(0ll, min((long long)G, (long long)io.nBoundary - b0));
+		const int perCell = n23 >> 2, total = nValid * perCell; // bytes; perCell is a multiple of 16
+		const unsigned char* src = reinterpret_cast<const unsigned char*>(sPk);
+		for (int i = tid * 16; i < total; i += kL2Threads * 16) {
+			const int gi = i / perCell, off = i - gi * perCell;
+			*reinterpret_cast<uint4*>(io.l2Packed + (size_t)sB[gi] * perCell + off) = *reinterpret_cast<const uint4*>(src + i);
+		}
+	} else if (OUT == L2_OUT_STAGED) {
 		// GPV_GATHER: the bytes go over NVLink into the gathering rank's buffer.  Every thread expands its column into the CTA's block
 		// of Level2InOut.raw staged in shared memory (the queue area, idle now; the cells of a CTA are consecutive boundary ranks, so
 		// the block is contiguous in the file); the block then leaves as 128-bit coalesced stores, the granularity NVLink likes.
@@ -1270,6 +1415,24 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	if (lane == 0 && (nIn | nBd)) { atomicAdd(&io.totals->l2Inside, (unsigned long long)nIn); atomicAdd(&io.totals->l2Boundary, (unsigned long long)nBd); }
 }
 
+// 2-bit packed Level-2 blocks (L2_OUT_PACKED) -> file bytes.  One thread per 32 sub-voxels: a uint2 in, two 128-bit stores out.
+// `skip`: the gathering rank expands only the blocks its peers sent (its own cells were written as bytes by its own k_l2).
+__global__ void __launch_bounds__(256) k_l2_expand(const uint2* __restrict__ packed, unsigned char* __restrict__ bytes, long long nWords, int wordsPerCell,
+                                                    const int* __restrict__ boundaryIndex, int plane, Own skip)
+{
+	for (long long w = (long long)blockIdx.x * 256 + threadIdx.x; w < nWords; w += (long long)gridDim.x * 256) {
+		if (skip.world > 1 && skip((unsigned)(boundaryIndex[w / wordsPerCell] % plane))) continue;
+		const uint2 m = __ldg(packed + w);
+		unsigned o[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			o[k] = (((m.x >> (4 * k)) & 15u) * 0x204081u & 0x01010101u) * 127u + (((m.y >> (4 * k)) & 15u) * 0x204081u & 0x01010101u) * 254u;
+		uint4* dst = reinterpret_cast<uint4*>(bytes + w * 32);
+		dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+		dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ gather over peer memory
 // Multi-GPU: every rank writes its share of the streams straight into the gathering rank's buffers over NVLink peer
 // memory, from inside the kernels that produce them.  Level 1 is computed by every rank over the whole grid (the parity rays need
@@ -1309,14 +1472,6 @@ __global__ void k_gather_begin(GatherMail* mail, int rank, unsigned epoch, unsig
 	const unsigned long long t0 = global_ns();
 	while (ld_sys(&mail->begin) < (unsigned long long)epoch)
 		if (global_ns() - t0 > timeoutNs) { totals->gatherError = 2; return; }
-}
-
-// a z-slab of the (global) prefix sums -> its final place in the gathering rank's Level1BoundaryPrefixSum stream
-__global__ void __launch_bounds__(256) k_gather_prefix(const int* __restrict__ local, int* out, long long n)
-{
-	const long long n4 = ((reinterpret_cast<size_t>(out) & 15) == 0 && (reinterpret_cast<size_t>(local) & 15) == 0) ? n / 4 : 0;
-	for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) reinterpret_cast<int4*>(out)[i] = reinterpret_cast<const int4*>(local)[i];
-	for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = local[i];
 }
 
 // <<<1, 1>>> behind the last kernel of the call: everything this rank wrote to the gathering rank is ordered before the flag

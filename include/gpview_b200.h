@@ -72,6 +72,10 @@ typedef struct {
 #define GPV_KEEP_LISTS   4     /* CSR cell lists / column lists in canonical (ascending) order for the caller (gpv_result list pointers);
                                   without it (and without GPV_NORMALS) the lists stay in the order the binning left them: occupancy does not depend on it */
 #define GPV_PROFILE      8     /* record a CUDA event pair around every kernel of the pipeline -> gpv_result.phase_ms */
+#define GPV_PROFILE_L2 128     /* the same for the two Level-2 kernels only (three events: negligible host time, for timed runs) */
+#define GPV_PACKED_L2  256     /* gpv_voxelize_host: Level2InOut crosses PCIe as 2 bits per sub-voxel and is expanded into the caller's bytes
+                                  by a pool of host threads while the next chunk is on the bus (same bytes, a quarter of the transfer).
+                                  Ignored when n2^3 is not a multiple of 32.  GPV_HOST_THREADS sets the pool size (default: all cores but one). */
 #define GPV_GATHER      16     /* multi-GPU: write this rank's share of the streams straight into the gathering rank's buffers (gpv_gather_*) */
 #define GPV_BATCH_TOLERANT_LOAD 64 /* gpv_voxelize_batch: read the meshes with GPV_LOAD_TOLERANT (gpv_load_mesh_ex) */
 #define GPV_SAVE_COMPUTED_ONLY 32 /* gpv_voxelize_batch: write only the streams that were computed -- no 127-filled normal files when
@@ -240,6 +244,11 @@ void gpv_free_voxels(gpv_voxel_file* v);
  * their state, boundary cells with their Level-2 block.  Host memory in, host memory out (out_bytes >= the dense size). */
 int gpv_expand_dense(const uint8_t* level1_inout, const int32_t* prefix, const uint8_t* level2_inout, const int num_div[3], int n2,
                      int64_t n_boundary, uint8_t* out, int64_t out_bytes);
+
+/* 2-bit packed Level-2 words -> file bytes (host memory in, host memory out).  One word pair (uint32 inside mask, uint32 boundary
+ * mask) per 32 consecutive sub-voxels of Level2InOut.raw, bit k = sub-voxel 32*w + k; out gets 32*n_words bytes 0 / 127 / 254.
+ * This is the format Level 2 crosses NVLink (GPV_GATHER) and PCIe (GPV_PACKED_L2) in; exported for consumers that keep it packed. */
+int gpv_expand_packed_l2(const void* packed, int64_t n_words, uint8_t* out);
 
 /* Batched dataset generation (BASELINE.json config 5): `threads` host threads, each with its own ctx on devices[w % n_devices],
  * pull paths from a shared queue: load -> gpv_voxelize_host -> gpv_save(out_dir, obj id = first_obj_id + index).  out_dir NULL:

@@ -97,9 +97,11 @@ def test_zslabs_concatenate_to_whole(product, oracle, ctx, tmp_path_factory):
             assert np.array_equal(np.concatenate(parts[k]), w[k]), (R, k)
 
 
-@pytest.mark.parametrize("name,l1,l2", [("cessna", 64, 4), ("cessna", 256, 16), ("torus", 32, 4)])
-def test_host_call_delivers_the_same_streams(product, oracle, ctx, tmp_path_factory, name, l1, l2):
-    """gpv_voxelize_host (H2D + pipeline + chunked, overlapped D2H) must hand the host exactly what the device holds."""
+@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("name,l1,l2", [("cessna", 64, 4), ("cessna", 256, 16), ("torus", 32, 4), ("cessna", 128, 8)])
+def test_host_call_delivers_the_same_streams(product, oracle, ctx, tmp_path_factory, name, l1, l2, packed):
+    """gpv_voxelize_host (H2D + pipeline + chunked, overlapped D2H) must hand the host exactly what the device holds -- with
+    Level 2 crossing PCIe as file bytes, or (GPV_PACKED_L2) as 2 bits per sub-voxel expanded by the host-thread pool."""
     from gpview_b200 import binding as B
     path = mesh_path(name, tmp_path_factory.getbasetemp())
     mesh = product.load_mesh(path)
@@ -108,7 +110,8 @@ def test_host_call_delivers_the_same_streams(product, oracle, ctx, tmp_path_fact
     l1s = np.full(cells, 7, np.uint8); pre = np.full(cells, -1, np.int32); bi = np.full(nb, -1, np.int32)
     l2s = np.full(nb * n23, 7, np.uint8); n1 = np.full(cells * 3, 7, np.uint8); n2 = np.full(nb * n23 * 3, 7, np.uint8)
     hs = B.CHostStreams(l1s.ctypes.data, pre.ctypes.data, bi.ctypes.data, l2s.ctypes.data, n1.ctypes.data, n2.ctypes.data, l2s.nbytes, nb)
-    res = ctx.voxelize_host(mesh, product.Params(l1, l2, product.GPV_NORMALS), hs)
+    flags = product.GPV_NORMALS | (product.GPV_PACKED_L2 if packed else 0)
+    res = ctx.voxelize_host(mesh, product.Params(l1, l2, flags), hs)
     assert res.counts == [info["l1_inside"], info["l1_boundary"], info["l2_inside"], info["l2_boundary"]]
     s = info["streams"]
     assert sha(l1s) == s["Level1InOut"]["sha256"] and sha(pre) == s["Level1BoundaryPrefixSum"]["sha256"] and sha(bi) == s["BoundaryIndex"]["sha256"]
@@ -117,7 +120,15 @@ def test_host_call_delivers_the_same_streams(product, oracle, ctx, tmp_path_fact
     # too-small host buffers are refused, not overrun
     hs2 = B.CHostStreams(l1s.ctypes.data, pre.ctypes.data, bi.ctypes.data, l2s.ctypes.data, None, None, l2s.nbytes - 1, nb)
     with pytest.raises(product.GpvError):
-        ctx.voxelize_host(mesh, product.Params(l1, l2, 0), hs2)
+        ctx.voxelize_host(mesh, product.Params(l1, l2, product.GPV_PACKED_L2 if packed else 0), hs2)
+    if packed:  # the call after a refused one, a second packed call (pool reuse), and a destination that is not 64-byte aligned
+        raw = np.full(nb * n23 + 128, 7, np.uint8)
+        off = (-raw.ctypes.data) % 64 + 8
+        hs3 = B.CHostStreams(None, None, None, raw.ctypes.data + off, None, None, nb * n23, nb)
+        for _ in range(2):
+            ctx.voxelize_host(mesh, product.Params(l1, l2, product.GPV_PACKED_L2), hs3)
+            assert sha(raw[off:off + nb * n23]) == s["Level2InOut"]["sha256"]
+        assert set(raw[:off]) == {7} and set(raw[off + nb * n23:]) == {7}
 
 
 def test_save_from_gpu_matches_reference_files(product, oracle, ctx, tmp_path_factory, tmp_path):
@@ -198,6 +209,13 @@ def test_hostile_triangle_soups_match_brute_force_oracle(product, oracle, ctx, t
     assert np.array_equal(res.cell_tris(), want.cell_tris)
     assert np.array_equal(res.level1_normal(), want.l1_normal)
     assert np.array_equal(res.level2_normal(), want.l2_normal)
+    if l2 % 4 == 0:  # the 2-bit packed host transfer on every n2 it supports (ballot paths 8 / 16, the two-layer path 4, bit by bit 12 / 32)
+        from gpview_b200 import binding as B
+        got = np.full(want.nb * want.n23 + 64, 9, np.uint8)
+        hs = B.CHostStreams(None, None, None, got.ctypes.data, None, None, want.nb * want.n23, want.nb)
+        r2 = ctx.voxelize_host(mesh, product.Params(l1, l2, product.GPV_PACKED_L2), hs)
+        assert r2.counts == want.counts
+        assert np.array_equal(got[:want.nb * want.n23], want.l2_state * 127) and set(got[want.nb * want.n23:]) == {9}
 
 
 @pytest.mark.parametrize("name,l1,l2,R", [("cessna", 64, 4, 3), ("torus", 32, 4, 2), ("cessna", 128, 8, 4), ("sphere", 24, 16, 5), ("cad", 40, 3, 2), ("block", 40, 2, 7)])

@@ -741,3 +741,38 @@ def test_tolerant_off_reader_against_an_independent_model(product, tmp_path):
         loaded += 1
         assert want.shape == got.shape and np.array_equal(want.view(np.uint32), got.view(np.uint32)), (it, txt)
     assert loaded > 800 and refused > 300, (loaded, refused)
+
+
+@pytest.mark.parametrize("isa", ["", "avx2", "scalar"])
+def test_expand_packed_l2_matches_numpy_on_every_isa_path(product, isa):
+    """gpv_expand_packed_l2 (the host half of GPV_PACKED_L2 / the consumer of the 2-bit Level-2 stream): (inside, boundary) mask
+    pairs -> bytes 0 / 127 / 254, on the AVX-512, AVX2 and scalar paths (GPV_EXPAND_ISA picks a narrower one), aligned and
+    unaligned destinations, odd word counts."""
+    import subprocess, sys, textwrap
+    from util import ROOT
+    code = textwrap.dedent('''
+        import ctypes as C, numpy as np, sys
+        sys.path.insert(0, %r)
+        import gpview_b200 as gpv
+        L = gpv.lib()
+        rng = np.random.default_rng(7)
+        for n, shift in [(1, 0), (2, 0), (3, 32), (64, 0), (1001, 0), (1001, 32), (4096, 1), (5000, 17), (70001, 0)]:
+            inside = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+            bd = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+            inside &= ~bd                                  # a sub-voxel is never both
+            packed = np.stack([inside, bd], 1).copy()
+            raw = np.zeros(n * 32 + 128, np.uint8)
+            base = (-raw.ctypes.data) %% 64 + shift            # 64-byte aligned + shift
+            out = raw[base:base + n * 32]
+            assert L.gpv_expand_packed_l2(packed.ctypes.data, n, out.ctypes.data) == 0
+            bits = lambda w: ((w[:, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8).reshape(-1)
+            want = bits(inside) * 127 + bits(bd) * 254
+            assert np.array_equal(out, want), (n, shift)
+            assert raw[:base].sum() == 0 and raw[base + n * 32:].sum() == 0
+        print("ok")
+    ''') % ROOT
+    env = dict(os.environ)
+    if isa:
+        env["GPV_EXPAND_ISA"] = isa
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
