@@ -120,7 +120,7 @@ static int preload_kernels()
 	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l2_rays_overflow); GPV_LOAD(k_ray_units); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals);
 	GPV_LOAD(k_l2<16, 0>); GPV_LOAD(k_l2<8, 0>); GPV_LOAD(k_l2<4, 0>); GPV_LOAD(k_l2<2, 0>); GPV_LOAD(k_l2<0, 0>);
 	GPV_LOAD(k_l2<16, 1>); GPV_LOAD(k_l2<8, 1>); GPV_LOAD(k_l2<4, 1>); GPV_LOAD(k_l2<2, 1>); GPV_LOAD(k_l2<0, 1>);
-	GPV_LOAD(k_l2<16, 2>); GPV_LOAD(k_l2<8, 2>); GPV_LOAD(k_l2<4, 2>); GPV_LOAD(k_l2<0, 2>); GPV_LOAD(k_l2_expand);
+	GPV_LOAD(k_l2<16, 2>); GPV_LOAD(k_l2<8, 2>); GPV_LOAD(k_l2<4, 2>); GPV_LOAD(k_l2<0, 2>); GPV_LOAD(k_gather_expand); GPV_LOAD(k_gather_wait_rank);
 	GPV_LOAD(k_gather_begin); GPV_LOAD(k_gather_done); GPV_LOAD(k_gather_wait);
 #undef GPV_LOAD
 	return 0;
@@ -290,14 +290,14 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	// GPV_GATHER: every rank runs Level 1 over the WHOLE grid (global boundary ranks, whole column lists); [oz0,oz1) is only the slab of
 	// Level-1 bytes / prefix sums this rank delivers (default: an equal share of the layers), the Level-2 work is shared out by column (Own)
 	int oz0 = g.z0, oz1 = g.z1;
-	Own own{ 1, 0, 1 };
+	Own own{ 1, 0, 1, 1 };
 	if (!gather && c->debugOwnWorld > 1) { // profiling aid (GPV_DEBUG_OWN=world,rank): a plain call refines only the Level-2 share rank `rank` of `world` would
-		own.world = c->debugOwnWorld; own.rank = c->debugOwnRank; own.group = std::max(1, 256 / (gg.n2 * gg.n2));
+		own.world = c->debugOwnWorld; own.rank = c->debugOwnRank; own.group = std::max(1, 256 / (gg.n2 * gg.n2)); own.nx = g.nx;
 	}
 	if (gather) {
 		if (prm->z1 <= 0) { oz0 = (int)((long long)g.nz * c->gather.rank / c->gather.world); oz1 = (int)((long long)g.nz * (c->gather.rank + 1) / c->gather.world); }
 		g.z0 = 0; g.z1 = g.nz;
-		own.world = c->gather.world; own.rank = c->gather.rank; own.group = std::max(1, 256 / (gg.n2 * gg.n2)); // = the columns one CTA of k_l2_rays walks
+		own.world = c->gather.world; own.rank = c->gather.rank; own.group = std::max(1, 256 / (gg.n2 * gg.n2)); own.nx = g.nx; // = the columns one CTA of k_l2_rays walks
 	}
 	g.minx = bmin[0]; g.miny = bmin[1]; g.minz = bmin[2]; g.maxx = bmax[0]; g.maxy = bmax[1]; g.maxz = bmax[2];
 	g.gsx = gg.grid_size[0]; g.gsy = gg.grid_size[1]; g.gsz = gg.grid_size[2];
@@ -629,14 +629,17 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		k_gather_done<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, dT);
 		launches++;
 		if (c->gather.rank == 0) {
+			if (wantL2 && nB > 0 && c->gather.world > 1 && (n23 % 32) == 0) { // the peers sent 2 bits per sub-voxel: the file bytes of their blocks, peer by peer as they finish
+				const long long nWords = nB * n23 / 32;
+				for (int q = 1; q < c->gather.world; q++) {
+					k_gather_wait_rank<<<1, 1, 0, st>>>(c->gather.mail, q, epoch, c->gather.timeoutNs, dT);
+					k_gather_expand<<<(unsigned)std::min<long long>(c->smCount * 8, (nWords + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint2*>(c->gather.l2p), c->gather.l2, nWords, (int)(n23 / 32),
+					                                                                                                       c->boundaryIndex.as<int>(), (int)ncol, own, q);
+					launches += 2;
+				}
+			}
 			k_gather_wait<<<1, 1, 0, st>>>(c->gather.mail, c->gather.world, epoch, c->gather.timeoutNs, dT);
 			launches++;
-			if (wantL2 && nB > 0 && c->gather.world > 1 && (n23 % 32) == 0) { // the peers sent 2 bits per sub-voxel: the file bytes of their blocks
-				const long long nWords = nB * n23 / 32;
-				k_l2_expand<<<(unsigned)std::min<long long>(c->smCount * 8, (nWords + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint2*>(c->gather.l2p), c->gather.l2, nWords, (int)(n23 / 32),
-				                                                                                                   c->boundaryIndex.as<int>(), (int)ncol, own);
-				launches++;
-			}
 		}
 	}
 	mark(GPV_PHASE_COUNT);

@@ -45,11 +45,14 @@ struct Totals {
 };
 
 // GPV_GATHER: which rank refines a Level-1 column.  Columns are dealt out in groups of `group` consecutive columns (the columns one
-// CTA of k_l2_rays walks), group k to rank k % world: neighbouring columns cost about the same, so the interleaving balances the
-// Level-2 work without a cost model, and every column list is walked by exactly one rank.  world <= 1: everything is owned.
+// CTA of k_l2_rays used to walk), group k of grid row j to rank (k + j) % world: neighbouring columns cost about the same, so the
+// interleaving balances the Level-2 work without a cost model, every column list is walked by exactly one rank, and the skew by the
+// row keeps a wall of the model that runs along x OR along y from landing on one rank (nx is a multiple of 4: without the skew rank r
+// would own the same x positions in every row).  world <= 1: everything is owned.
 struct Own {
-	int world, rank, group;
-	__host__ __device__ __forceinline__ bool operator()(unsigned col) const { return world <= 1 || (int)((col / (unsigned)group) % (unsigned)world) == rank; }
+	int world, rank, group, nx;
+	__host__ __device__ __forceinline__ int owner(unsigned col) const { return (int)((col / (unsigned)group + col / (unsigned)nx) % (unsigned)world); }
+	__host__ __device__ __forceinline__ bool operator()(unsigned col) const { return world <= 1 || owner(col) == rank; }
 };
 
 constexpr int kWorkThreads = 128;                        // threads per CTA of the balanced triangle-work kernels
@@ -1415,24 +1418,6 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	if (lane == 0 && (nIn | nBd)) { atomicAdd(&io.totals->l2Inside, (unsigned long long)nIn); atomicAdd(&io.totals->l2Boundary, (unsigned long long)nBd); }
 }
 
-// 2-bit packed Level-2 blocks (L2_OUT_PACKED) -> file bytes.  One thread per 32 sub-voxels: a uint2 in, two 128-bit stores out.
-// `skip`: the gathering rank expands only the blocks its peers sent (its own cells were written as bytes by its own k_l2).
-__global__ void __launch_bounds__(256) k_l2_expand(const uint2* __restrict__ packed, unsigned char* __restrict__ bytes, long long nWords, int wordsPerCell,
-                                                    const int* __restrict__ boundaryIndex, int plane, Own skip)
-{
-	for (long long w = (long long)blockIdx.x * 256 + threadIdx.x; w < nWords; w += (long long)gridDim.x * 256) {
-		if (skip.world > 1 && skip((unsigned)(boundaryIndex[w / wordsPerCell] % plane))) continue;
-		const uint2 m = __ldg(packed + w);
-		unsigned o[8];
-#pragma unroll
-		for (int k = 0; k < 8; k++)
-			o[k] = (((m.x >> (4 * k)) & 15u) * 0x204081u & 0x01010101u) * 127u + (((m.y >> (4 * k)) & 15u) * 0x204081u & 0x01010101u) * 254u;
-		uint4* dst = reinterpret_cast<uint4*>(bytes + w * 32);
-		dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-		dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-	}
-}
-
 // ------------------------------------------------------------------------------------------------ gather over peer memory
 // Multi-GPU: every rank writes its share of the streams straight into the gathering rank's buffers over NVLink peer
 // memory, from inside the kernels that produce them.  Level 1 is computed by every rank over the whole grid (the parity rays need
@@ -1481,6 +1466,34 @@ __global__ void k_gather_done(GatherMail* mail, int rank, unsigned epoch, const 
 	st[0] = totals->l1Inside; st[1] = totals->l2Inside; st[2] = totals->l2Boundary; st[3] = totals->gatherError;
 	__threadfence_system();
 	st_sys(&mail->done[rank], (unsigned long long)epoch);
+}
+
+// Gathering rank: the peers sent their Level-2 blocks as 2 bits per sub-voxel (L2_OUT_PACKED); these two turn them into the file
+// bytes, peer by peer: a one-thread kernel waits for rank q's completion flag, then k_gather_expand expands the blocks of the
+// columns rank q owns (one thread per 32 sub-voxels: a uint2 in, two 128-bit stores out) -- the blocks of the ranks that finish
+// early are expanded while the later ones are still computing.  (A single resident grid whose threads spin on the flags was tried
+// and dropped: with several ranks on ONE device, as in the tests, the spinning grid starves the ranks it waits for.)
+__global__ void k_gather_wait_rank(GatherMail* mail, int q, unsigned epoch, unsigned long long timeoutNs, Totals* totals)
+{
+	const unsigned long long t0 = global_ns();
+	while (ld_sys(&mail->done[q]) < (unsigned long long)epoch)
+		if (global_ns() - t0 > timeoutNs) { totals->gatherError = 2; return; }
+}
+
+__global__ void __launch_bounds__(256) k_gather_expand(const uint2* __restrict__ packed, unsigned char* __restrict__ bytes, long long nWords, int wordsPerCell,
+                                                        const int* __restrict__ boundaryIndex, int plane, Own own, int q)
+{
+	for (long long w = (long long)blockIdx.x * 256 + threadIdx.x; w < nWords; w += (long long)gridDim.x * 256) {
+		if (own.owner((unsigned)(boundaryIndex[w / wordsPerCell] % plane)) != q) continue;
+		const uint2 m = __ldcg(packed + w); // (written by a peer over NVLink: not through the read-only path)
+		unsigned o[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			o[k] = (((m.x >> (4 * k)) & 15u) * 0x204081u & 0x01010101u) * 127u + (((m.y >> (4 * k)) & 15u) * 0x204081u & 0x01010101u) * 254u;
+		uint4* dst = reinterpret_cast<uint4*>(bytes + w * 32);
+		dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+		dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+	}
 }
 
 // <<<1, 1>>> on the gathering rank: returns when every rank has signalled completion of this epoch; the counts become the whole grid's
