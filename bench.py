@@ -103,74 +103,155 @@ def measured_peaks():
 
 
 def ncu_traffic():
-    """per-kernel numbers of the committed ncu --set full capture (profiles/traffic.json, tools/ncu_summary.py --traffic), or {}."""
+    """(per-kernel numbers of the committed ncu --set full capture, note): profiles/traffic.json, written by tools/ncu_summary.py
+    --traffic and stamped with a hash of the kernel sources.  A capture of OTHER sources is not quoted: ({}, why)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            return json.load(f)
-    return {}
+    if not os.path.exists(p):
+        return {}, "no capture committed"
+    with open(p) as f:
+        d = json.load(f)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ncu_summary
+    sha = ncu_summary.csrc_sha()
+    if d.get("csrc_sha") != sha:
+        return {}, "stale: profiles/traffic.json was captured from kernel sources %s, this build is %s" % (d.get("csrc_sha"), sha)
+    return d, "ncu --set full capture of this build's kernel sources (csrc_sha %s), same command, one GPU" % sha
 
 
-def reference_timer(mesh_path, l1, l2, threads):
-    """(kind, n_boundary, fn(cells) -> (seconds, tests)): the reference's TriBoxOverlap object code (oracle/_ref) in the
-    Level-2 loop nest of cuda/CUDAClassifyTessellation.cu:428-445, or the oracle port when _ref was not built."""
+class ReferencePath:
+    """The reference's CPU implementation of the WHOLE path on this box's host cores (oracle/_ref: the reference's own object code --
+    Object::ClassifyTessellation, TriBoxOverlap, triangle_ray_intersection -- driven by oracle/ref_harness.cpp):
+      Level 1   tri-box binning (Object::ClassifyTessellation, src/Object.cpp:2256-2342: its own single-threaded loop), the host CSR /
+                column-list pass (:2137-2180, :3258-3284) and the solid fill through the column lists (all host threads)
+      Level 2   per sub-voxel the parity rays over the column list (cu:450-504) and the SAT over the cell list (cu:403-448), in the
+                kernels' arithmetic, all host threads -- timed on a bounded sample of boundary cells
+    A step of the sample charges Level 1 pro rata: seconds = t_L1 * K / nB + t_L2(K cells), tests = L1 tests * K / nB + L2 tests(K).
+    When oracle/_ref was not built the oracle port's Level-2 SAT nest stands in (kind "port")."""
+
+    def __init__(self, mesh_path, l1, l2, threads):
+        from oracle import refbind
+        self.threads, self.l1, self.l2 = threads, l1, l2
+        if refbind.available():
+            self.kind = "reference"
+            o = self.o = refbind.RefObject(mesh_path)
+            o.setup(l1, l2)
+            self.t_tri = o.l1_tribox()                       # the reference's own loop (single-threaded by construction)
+            t0 = time.perf_counter()
+            o.compact()
+            self.t_lists = time.perf_counter() - t0
+            self.t_fill, self.fill_ray_tests = o.time_l1_fill_collist(threads)
+            st = o.stats()
+            self.l1_box_tests, self.nb = st["l1_box_tests"], o.nboundary()
+            self.grid = [int(x) for x in o.num_div]
+            self.triangles = o.ntri
+            self.l2_box_tests_model = int(o.tri_count()[o.boundary_index()].astype(np.int64).sum()) * max(l2, 1) ** 3
+        else:
+            from oracle import oraclebind as O
+            self.kind = "port"
+            self.r = O.OracleMesh(mesh_path).voxelize(l1, l2, O.FILL_COLLIST | O.NO_L2 | O.NO_NORMALS, threads)
+            self.t_tri = self.t_lists = self.t_fill = 0.0
+            self.fill_ray_tests = 0
+            self.l1_box_tests, self.nb = 0, self.r.nb
+            self.grid, self.triangles, self.l2_box_tests_model = [int(x) for x in self.r.num_div], None, None
+        self.t_l1 = self.t_tri + self.t_lists + self.t_fill
+
+    def sample(self, cells, threads=None):
+        """(seconds, tri-box tests, ray tests) of one step over the first `cells` boundary cells, Level 1 charged pro rata."""
+        threads = threads or self.threads
+        if self.kind == "reference":
+            s, box, rays = self.o.time_l2_path(0, cells, threads)
+        else:
+            s, box = self.r.time_l2_tribox(0, cells, threads)
+            rays = 0
+        f = cells / max(1, self.nb)
+        return s + self.t_l1 * f, box + self.l1_box_tests * f, rays + self.fill_ray_tests * f
+
+    def cells_for(self, seconds):
+        probe = min(self.nb, 64)
+        s, _, _ = self.sample(probe)
+        return int(max(probe, min(self.nb, seconds / max(s / probe, 1e-9))))
+
+    def describe(self, cells):
+        if self.kind == "port":
+            return "oracle port (oracle/_ref not built): Level-2 SAT loop nest over the first %d of %d boundary cells" % (cells, self.nb)
+        return ("whole CPU path: Level 1 measured on the whole model (ClassifyTessellation %.3f s on 1 thread -- the reference's own loop --, CSR / column lists %.3f s, "
+                "column-list fill %.3f s on %d threads) and charged pro rata; Level 2 (parity rays + SAT per sub-voxel) over the first %d of %d boundary cells per step"
+                % (self.t_tri, self.t_lists, self.t_fill, self.threads, cells, self.nb))
+
+
+def c1_reference(mesh_path, threads):
+    """BASELINE.json configs[0]: cessna Level-1 64 through the reference's CPU path -- brute-force Object::ClassifyInOutCPU loop nest
+    (src/Object.cpp:716-779, z-layers over host threads) + Object::ClassifyTessellation."""
     from oracle import refbind
-    if refbind.available():
-        o = refbind.RefObject(mesh_path)
-        o.setup(l1, l2)
-        o.l1_tribox()
-        o.compact()
-        return "reference", o.nboundary(), (lambda c, t=threads: o.time_l2_tribox(0, c, t))
-    from oracle import oraclebind as O
-    r = O.OracleMesh(mesh_path).voxelize(l1, l2, O.FILL_COLLIST | O.NO_L2 | O.NO_NORMALS, threads)
-    return "port", r.nb, (lambda c, t=threads: r.time_l2_tribox(0, c, t))
+    if not refbind.available():
+        return None
+    o = refbind.RefObject(mesh_path)
+    o.setup(64, 0)
+    t_fill = o.l1_inout_brute(threads)
+    t_tri = o.l1_tribox()
+    st = o.stats()
+    out = {"workload": "cessna Level1 64, CPU path (BASELINE.json configs[0])", "ms_per_model": 1e3 * (t_fill + t_tri), "fill_brute_force_s": t_fill,
+           "fill_ray_tests": int(o.cells) * int(o.ntri), "tri_box_s": t_tri, "tri_box_tests": st["l1_box_tests"], "cores": threads}
+    o.close()
+    return out
 
 
 def cpu_baseline(mesh_path, l1, l2, threads, target_seconds=12.0):
-    kind, nb, timer = reference_timer(mesh_path, l1, l2, threads)
-    s, n = timer(min(nb, 256))
-    cells = int(max(256, min(nb, target_seconds / max(s / max(1, min(nb, 256)), 1e-9))))
-    s, n = timer(cells)
-    out = {"value": n / s / 1e9, "unit": "G tri-box tests/s", "cores": threads, "kind": kind,
-           "sample": "Level-2 SAT loop nest over the first %d of %d boundary cells (%d tests, %.2f s)" % (cells, nb, n, s)}
+    ref = ReferencePath(mesh_path, l1, l2, threads)
+    cells = ref.cells_for(target_seconds)
+    s, box, rays = ref.sample(cells)
+    out = {"value": box / s / 1e9, "unit": "G tri-box tests/s", "cores": threads, "kind": ref.kind, "sample": ref.describe(cells),
+           "seconds": s, "ray_tests_in_sample": int(rays)}
+    if ref.kind == "reference" and ref.nb:
+        out["ms_per_model_extrapolated"] = 1e3 * s * ref.nb / cells
     try:  # BASELINE.md 5.3: the reference's actual execution model is one thread -- reported beside the all-core figure
-        c1 = int(max(256, min(nb, cells // max(1, threads) // 2)))
-        s1, n1 = timer(c1, 1)
-        out["single_thread"] = {"value": n1 / s1 / 1e9, "unit": "G tri-box tests/s", "cores": 1,
-                                "sample": "the same loop nest over the first %d boundary cells (%d tests, %.2f s)" % (c1, n1, s1)}
+        c1 = max(16, cells // max(1, threads) // 2)
+        s1, b1, _ = ref.sample(c1, 1)
+        out["single_thread"] = {"value": b1 / s1 / 1e9, "unit": "G tri-box tests/s", "cores": 1, "sample": "the same path over the first %d boundary cells (%.2f s)" % (c1, s1)}
     except Exception as e:
         out["single_thread"] = {"error": repr(e)}
     return out
 
 
-def workload_config(args):
+def workload_config(args, tests=None, triangles=None, grid=None):
+    """The workload, identically for both arms (the reference arm derives the same numbers from the reference's own data structures)."""
     return {"workload": "%s Level1 %d + Level2 %d^3 (BASELINE.json configs[1] when cessna/256/16), .raw occupancy streams"
                         % (args.mesh, args.l1, args.l2), "l1": args.l1, "l2": args.l2, "mesh": args.mesh,
-            "cache": "L2 flushed between timed steps (256 MiB memset); outputs (>=221 MB at 256/16) exceed L2"}
+            "cache": "L2 flushed between timed steps (256 MiB memset); outputs (>=221 MB at 256/16) exceed L2",
+            "tri_box_tests_per_model": tests, "triangles": triangles, "grid": grid}
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU TriBoxOverlap path on this box's host cores (all threads)."""
+    """--impl reference: the reference's own CPU implementation of the whole path on this box's host cores (all threads)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
     path = make_mesh_file(args.mesh, tempfile.mkdtemp(prefix="gpvbench"))
-    kind, nb, timer = reference_timer(path, args.l1, args.l2, threads)
-    s, n = timer(min(nb, 256))
-    cells = int(max(256, min(nb, 1.0 / max(s / max(1, min(nb, 256)), 1e-9))))  # ~1 s per step
+    ref = ReferencePath(path, args.l1, args.l2, threads)
+    cells = ref.cells_for(4.0)  # ~4 s of CPU work per step
     for _ in range(args.warmup):
-        timer(cells)
-    tot_s, tot_n = 0.0, 0
+        ref.sample(max(64, cells // 8))
+    tot_s, tot_n, tot_r = 0.0, 0.0, 0.0
     for _ in range(args.steps):
-        s, n = timer(cells)
-        tot_s += s; tot_n += n
+        s, n, r = ref.sample(cells)
+        tot_s += s; tot_n += n; tot_r += r
     v = tot_n / tot_s / 1e9
-    sample = "Level-2 SAT loop nest (cuda/CUDAClassifyTessellation.cu:428-445) over %d of %d boundary cells per step" % (cells, nb)
-    print(json.dumps({"impl": "reference", "metric": "G tri-box tests/s", "value": v, "unit": "G tri-box tests/s", "n_gpus": args.gpus,
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
-                      "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "cessna.obj fixture" if args.mesh == "cessna" else "synthetic",
-                      "config": workload_config(args), "cpu_baseline": {"value": v, "unit": "G tri-box tests/s", "cores": threads, "kind": kind, "sample": sample},
-                      "e2e": {"value": v, "unit": "G tri-box tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+    tests_model = (ref.l1_box_tests + ref.l2_box_tests_model) if ref.l2_box_tests_model is not None else None
+    line = {"impl": "reference", "metric": "G tri-box tests/s", "value": v, "unit": "G tri-box tests/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "cessna.obj fixture (reference sample mesh)" if args.mesh == "cessna" else "synthetic",
+            "config": workload_config(args, tests_model, ref.triangles, ref.grid),
+            "cpu_baseline": {"value": v, "unit": "G tri-box tests/s", "cores": threads, "kind": ref.kind, "sample": ref.describe(cells)},
+            "e2e": {"value": v, "unit": "G tri-box tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "ray_tests_per_step": tot_r / args.steps}
+    if ref.kind == "reference" and ref.nb:
+        line["ms_per_model_extrapolated"] = 1e3 * (tot_s / args.steps) * ref.nb / cells
+    if args.mesh == "cessna":
+        try:
+            line["c1"] = c1_reference(path, threads)
+        except Exception as e:  # commentary: never lose the line over it
+            line["c1"] = {"error": repr(e)}
+    print(json.dumps(line))
 
 
 def main():
@@ -383,6 +464,14 @@ def main():
     tests = float(tests_local.item()) + res.stats["l1_box_tests"]  # Level-1 tests are replicated: counted once
     value = tests / (ms_per_step * 1e-3) / 1e9
 
+    if os.environ.get("GPV_DEBUG_OWN"):
+        # profiling aid (tools/profile_round.sh): this process refined only the Level-2 share of one rank of an N-rank gathering call, on
+        # one GPU -- what ncu captures for the N > 1 roofline entries.  Not a benchmark line: print the phase times and stop.
+        print(json.dumps({"profiling_share": os.environ["GPV_DEBUG_OWN"], "ms_per_step": ms_per_step, "l2_cells": int(res.n_refined),
+                          "phase_ms": {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0}}))
+        ctx.free_device(d_tris)
+        ctx.close()
+        return
     # ---- e2e: pinned host triangles in, host streams out, through gpv_voxelize_host (each rank: its slab, its PCIe link)
     e2e_params = gpv.Params(args.l1, args.l2, 0, z0, z1)
     slab = ctx.voxelize_device(d_tris, mesh, e2e_params, sptr)  # sizes of this rank's slab (the gathering call above reports the whole grid)
@@ -467,41 +556,65 @@ def main():
         k_rays_ms = phase_acc.get("l2_rays", 0.0) / args.steps   # k_col_cells + k_l2_rays
         fp32_peak = ctx.fp32_peak()
         hbm_peak, hbm_src = measured_peaks()
-        ncu = ncu_traffic().get("kernels", {})
-        sat_name = "k_l2<%d, %s>" % (args.l2 if args.l2 in (2, 4, 8, 16) else 0, "1" if (world > 1 and args.gather == "peer") else "0")
+        # executed-work numbers of the same kernels under ncu (never taken in this run: a number measured under a profiler is not a
+        # bench value): at N = 1 the whole call, at N > 1 rank 0's share captured on one GPU (GPV_DEBUG_OWN=N,0); only quoted while the
+        # kernel sources still hash to what the capture was made from
+        ncu_all, ncu_src = ncu_traffic()
+        ncu = ncu_all.get("kernels", {}) if world == 1 else ncu_all.get("share", {}).get(str(world), {})
+        sat_name = "k_l2<%d, 0>" % (args.l2 if args.l2 in (2, 4, 8, 16) else 0)  # (rank 0 of a gathering call writes its own blocks as bytes, too)
         n_sat, n_rays = ncu.get(sat_name, {}), ncu.get("k_l2_rays", {})
         flops = FLOPS_PER_TRIBOX * res.stats["l2_box_tests"]
         ach = flops / (k_l2_ms * 1e-3) / 1e12
-        ncu_note = lambda d: {"issue_active_pct": d.get("issue_active_pct"), "warp_inst_executed": d.get("warp_inst_executed"),
-                              "pipe_fma_pct": d.get("pipe_fma_pct"), "pipe_alu_pct": d.get("pipe_alu_pct"), "time_us": d.get("time_us"),
-                              "source": "profiles/" + d["source"]} if d else None
-        roof = {"kernel": sat_name + " (Level-2 SAT over shared-memory queues + final bytes)" + (" on rank 0's slab" if world > 1 else ""), "bound": "fp32",
+
+        def ncu_note(d):
+            if not d:
+                return None
+            out = {k: d.get(k) for k in ("issue_active_pct", "warp_inst_executed", "thread_inst_executed", "lanes_per_inst", "pipe_fma_pct", "pipe_alu_pct", "time_us",
+                                         "fp32_fadd", "fp32_fmul", "fp32_ffma")}
+            out["source"] = "profiles/" + d["source"]
+            out["provenance"] = ncu_src
+            return out
+
+        def executed(d, kernel_ms):
+            """executed FP32 work of the launch (hardware counters of the capture: thread-level FADD + FMUL + FFMA, predicated-on lanes)
+            over the kernel's LIVE time, against the live FP32 issue peak: the utilisation figure (the algorithmic `frac` is a speed-up figure)"""
+            if not d or d.get("fp32_fadd") is None or kernel_ms <= 0:
+                return {}
+            lane_ops = d["fp32_fadd"] + d["fp32_fmul"] + d["fp32_ffma"]
+            return {"executed_fp32_lane_ops": lane_ops, "executed_flops": d["fp32_fadd"] + d["fp32_fmul"] + 2.0 * d["fp32_ffma"],
+                    "frac_executed": lane_ops / (kernel_ms * 1e-3) / fp32_peak,
+                    "executed_note": "FADD + FMUL + FFMA thread instructions of this launch under ncu (deterministic for the same sources and model) / live kernel time / "
+                                     "live non-FMA FP32 issue peak; the rest of the issue slots go to integer, compare, select, shared-memory and queue instructions"}
+
+        roof = {"kernel": sat_name + " (Level-2 SAT over shared-memory queues + final bytes)" + (" on rank 0's share of the boundary cells" if world > 1 else ""), "bound": "fp32",
                 "achieved": ach, "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": ach / (fp32_peak / 1e12),
-                "traffic": n_sat.get("dram_bytes") if world == 1 else None,
+                "traffic": n_sat.get("dram_bytes"),
                 "peak_source": "non-FMA FP32 issue rate measured live (gpv_measure_fp32_peak: independent FMUL/FADD chains); "
                                "MEASURED_PEAKS.json has no FP32 entry",
                 "algorithmic": "%d reference-equivalent tri-box tests x 124 FLOP per launch (SURVEY.md 8d).  frac > 1 is expected: certified plane / AABB "
                                "culling proves ~94 %% of the reference's tests negative without running them and the z-independent part of the rest is "
-                               "hoisted per sub-voxel column.  What the kernel actually executes is bounded by instruction issue: see `ncu` "
-                               "(issue-slot utilisation of the same command under ncu --set full)" % res.stats["l2_box_tests"],
-                "ncu": ncu_note(n_sat) if world == 1 else None,
+                               "hoisted per sub-voxel column -- `frac` is an algorithmic speed-up figure; `frac_executed` and `frac_issue_slots` are the "
+                               "utilisation figures" % res.stats["l2_box_tests"],
+                "ncu": ncu_note(n_sat), "ncu_provenance": ncu_src,
                 "kernel_ms": k_l2_ms, "share_of_step": k_l2_ms / ms_per_step}
-        if world == 1 and n_sat.get("issue_active_pct") is not None:
+        roof.update(executed(n_sat, k_l2_ms))
+        if n_sat.get("issue_active_pct") is not None:
             # the executed-work view of the same kernel: share of issue slots in use (ncu capture of this command), the ceiling
             # that actually binds a kernel whose FP32 work is comparisons, selects and non-FMA arithmetic
             roof["frac_issue_slots"] = n_sat["issue_active_pct"] / 100.0
         ray_flops = 51.0 * res.stats.get("l2_ray_tests", 0)
-        roof_rays = {"kernel": "k_l2_rays (Level-2 parity rays per sub-voxel column)", "bound": "fp32", "kernel_ms": k_rays_ms, "share_of_step": k_rays_ms / ms_per_step,
+        roof_rays = {"kernel": "k_l2_rays (Level-2 parity rays per sub-voxel column; + k_col_cells, k_l2_rays_overflow)", "bound": "fp32", "kernel_ms": k_rays_ms, "share_of_step": k_rays_ms / ms_per_step,
                      "achieved": ray_flops / (k_rays_ms * 1e-3) / 1e12 if k_rays_ms > 0 and ray_flops else None, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
                      "algorithmic": "%d reference-equivalent ray tests x 51 FLOP (+1 division) per launch" % res.stats.get("l2_ray_tests", 0),
-                     "traffic": n_rays.get("dram_bytes") if world == 1 else None, "ncu": ncu_note(n_rays) if world == 1 else None}
+                     "traffic": n_rays.get("dram_bytes"), "ncu": ncu_note(n_rays)}
         if roof_rays["achieved"]:
             roof_rays["frac"] = roof_rays["achieved"] / roof_rays["peak"]
-        if world == 1 and n_rays.get("issue_active_pct") is not None:
+        roof_rays.update(executed(n_rays, k_rays_ms))
+        if n_rays.get("issue_active_pct") is not None:
             roof_rays["frac_issue_slots"] = n_rays["issue_active_pct"] / 100.0
         out_bytes = res.n_refined * res.n23  # the blocks this rank's launch wrote
         roof_hbm = {"kernel": sat_name, "bound": "hbm", "achieved": out_bytes / (k_l2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": out_bytes / (k_l2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": n_sat.get("dram_bytes") if world == 1 else None,
+                    "frac": out_bytes / (k_l2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": n_sat.get("dram_bytes"),
                     "peak_source": hbm_src, "algorithmic": "1 B per Level-2 voxel written (%d B)" % out_bytes}
         # every phase of the pipeline against the roofline that bounds it (SURVEY.md 8d: algorithmic bytes / flops per unit x units
         # of this model, over the phase's CUDA-event time).  The Level-1 phases of a cessna-sized model are tens of microseconds of
@@ -530,8 +643,7 @@ def main():
         line = {"metric": "G tri-box tests/s", "value": value, "unit": "G tri-box tests/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "ms_per_model": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "cessna.obj fixture (reference sample mesh)" if args.mesh == "cessna" else "synthetic",
-                "config": dict(workload_config(args), parallelism=("%d ranks, Level-1 replicated, %s; gathered streams == single-GPU result: %s" % (world, "Level-1 bytes / prefix sums by equal z-slabs, Level-2 refinement by interleaved Level-1 column groups, every rank writing its share into rank 0's buffers over NVLink peer memory from inside the kernels (GPV_GATHER): no collective, no exchange step, completion flags through a mailbox" if peer else "z-slabs (cuts %s), NCCL send/recv gather to rank 0" % cuts, gather_ok)) if world > 1 else "1 GPU",
-                               tri_box_tests_per_model=int(tests), triangles=mesh.ntri, grid=[int(x) for x in res.num_div]),
+                "config": dict(workload_config(args, int(tests), mesh.ntri, [int(x) for x in res.num_div]), parallelism=("%d ranks, Level-1 replicated, %s; gathered streams == single-GPU result: %s" % (world, "Level-1 bytes / prefix sums by equal z-slabs, Level-2 refinement by interleaved Level-1 column groups, every rank writing its share into rank 0's buffers over NVLink peer memory from inside the kernels (GPV_GATHER): no collective, no exchange step, completion flags through a mailbox" if peer else "z-slabs (cuts %s), NCCL send/recv gather to rank 0" % cuts, gather_ok)) if world > 1 else "1 GPU"),
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_rays": roof_rays, "roofline_hbm": roof_hbm, "roofline_phases": per_phase,
                 "phase_ms": {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0},
                 "counts": {"l1_inside": whole.counts[0], "l1_boundary": whole.counts[1]}}

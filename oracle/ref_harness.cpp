@@ -622,6 +622,117 @@ double ref_time_l2_tribox(void* h, long b0, long b1, int nThreads, long* testsOu
 	return now() - t0;
 }
 
+// ---- whole-path CPU baseline (bench.py --impl reference, cpu_baseline): the pieces of the path beyond the Level-2 SAT nest, each
+// around the reference's own object code (triangle_ray_intersection, TriBoxOverlap), split across host threads.
+
+// Level-1 solid fill through the per-column lists (the form the reference's own Level-2 kernel uses, cu:461-463; byte-identical to
+// the brute force Object::ClassifyInOutCPU on cessna 64, tests/test_oracle_ref.py): every cell's +Z ray against its column list.
+// Times the loop nest only; the parities go to a scratch array (level1InOut already holds the final states).
+double ref_time_l1_fill_collist(void* h, int nThreads, long* rayTestsOut)
+{
+	Ref* r = (Ref*)h;
+	Object* o = r->o;
+	VoxelData* vd = o->voxelData;
+	int nx = vd->numDivX, ny = vd->numDivY, nz = vd->numDivZ;
+	std::vector<unsigned char> scratch((size_t)nx * ny * nz);
+	std::atomic<long> tests(0);
+	std::atomic<int> next(0);
+	double t0 = now();
+	auto work = [&]() {
+		float dir[3] = { 0, 0, 1 };
+		long rt = 0;
+		for (;;) {
+			int k = next.fetch_add(1);
+			if (k >= nz) break;
+			for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++) {
+				float c[3];
+				c[0] = o->bBoxMin[0] + (i + 0.5)*vd->gridSizeX;
+				c[1] = o->bBoxMin[1] + (j + 0.5)*vd->gridSizeY;
+				c[2] = o->bBoxMin[2] + (k + 0.5)*vd->gridSizeZ;
+				int p = j*nx + i, n = 0; float rp;
+				for (int q = 0; q < r->xyCount[p]; q++) {
+					float* d = o->flatCPUTriangleData + (size_t)r->xyFlat[r->xyFlatIndex[p] + q] * 9;
+					rt++;
+					if (triangle_ray_intersection(d, d + 3, d + 6, c, dir, &rp)) n++;
+				}
+				scratch[(size_t)k*ny*nx + p] = (unsigned char)(n % 2);
+			}
+		}
+		tests += rt;
+	};
+	std::vector<std::thread> th;
+	for (int i = 0; i < nThreads; i++) th.emplace_back(work);
+	for (auto& t : th) t.join();
+	double dt = now() - t0;
+	*rayTestsOut = tests;
+	return dt;
+}
+
+// Level 2 of the path over boundary cells [b0,b1): per sub-voxel the parity rays over the column list (cu:450-504) and then the
+// SAT over the cell list (cu:403-448), in the kernels' arithmetic, states written to a scratch array.  out[0] = tri-box tests,
+// out[1] = ray tests.
+double ref_time_l2_path(void* h, long b0, long b1, int nThreads, long* out)
+{
+	Ref* r = (Ref*)h;
+	Object* o = r->o;
+	VoxelData* vd = o->voxelData;
+	int nx = vd->numDivX, ny = vd->numDivY;
+	int n2x = vd->numDivX2, n2y = vd->numDivY2, n2z = vd->numDivZ2;
+	size_t n23 = (size_t)n2x*n2y*n2z;
+	float3 e1 = make_float3(vd->gridSizeX / 2.0, vd->gridSizeY / 2.0, vd->gridSizeZ / 2.0);
+	float3 e2 = make_float3(vd->gridSizeX2 / 2.0, vd->gridSizeY2 / 2.0, vd->gridSizeZ2 / 2.0);
+	std::vector<float> scratch((size_t)(b1 - b0) * n23, 0.f);
+	std::atomic<long> boxTests(0), rayTests(0);
+	std::atomic<long> next(b0);
+	double t0 = now();
+	auto work = [&]() {
+		float dir[3] = { 0, 0, 1 };
+		long bt = 0, rt = 0;
+		for (;;) {
+			long b = next.fetch_add(1);
+			if (b >= b1) break;
+			int l1 = vd->boundaryIndex[b];
+			int k = l1 / (nx*ny); int ij = l1 - k*nx*ny; int j = ij / nx, i = ij % nx;
+			float mid[3];
+			mid[0] = (i + 0.5)*vd->gridSizeX + o->bBoxMin[0];
+			mid[1] = (j + 0.5)*vd->gridSizeY + o->bBoxMin[1];
+			mid[2] = (k + 0.5)*vd->gridSizeZ + o->bBoxMin[2];
+			int xy = l1 % (nx*ny);
+			const int* cl = r->xyFlat.data() + r->xyFlatIndex[xy]; int ncl = r->xyCount[xy];
+			const int* tl = r->triFlat.data() + r->triFlatIndex[l1]; int ntl = r->triCount[l1];
+			for (size_t loc = 0; loc < n23; loc++) {
+				int rr = loc / (n2x*n2y); int pq = loc - rr*n2x*n2y; int q = pq / n2x, p = pq % n2x;
+				float c[3];
+				c[0] = (2 * p + 1)*e2.x + mid[0] - e1.x;
+				c[1] = (2 * q + 1)*e2.y + mid[1] - e1.y;
+				c[2] = (2 * rr + 1)*e2.z + mid[2] - e1.z;
+				int n = 0; float rp;
+				for (int t = 0; t < ncl; t++) {
+					float* d = o->flatCPUTriangleData + (size_t)cl[t] * 9;
+					rt++;
+					if (triangle_ray_intersection(d, d + 3, d + 6, c, dir, &rp)) n++;
+				}
+				float state = (n % 2 == 1) ? 1.f : 0.f;
+				float he[3] = { e2.x, e2.y, e2.z };
+				for (int t = 0; t < ntl; t++) {
+					float* d = o->flatCPUTriangleData + (size_t)tl[t] * 9;
+					float tv[3][3] = { { d[0], d[1], d[2] }, { d[3], d[4], d[5] }, { d[6], d[7], d[8] } };
+					bt++;
+					if (TriBoxOverlap(c, he, tv)) state = 2.f;
+				}
+				scratch[(size_t)(b - b0) * n23 + loc] = state;
+			}
+		}
+		boxTests += bt; rayTests += rt;
+	};
+	std::vector<std::thread> th;
+	for (int i = 0; i < nThreads; i++) th.emplace_back(work);
+	for (auto& t : th) t.join();
+	double dt = now() - t0;
+	out[0] = boxTests; out[1] = rayTests;
+	return dt;
+}
+
 void ref_close(void* h)
 {
 	Ref* r = (Ref*)h;

@@ -38,6 +38,7 @@ def lib():
             "ref_stats": (None, [vp, lp]), "ref_tribox_batch": (None, [cl, fp, fp, fp, bp]),
             "ref_triray_batch": (None, [cl, fp, fp, bp]),
             "ref_time_l2_tribox": (cd, [vp, cl, cl, ci, lp]), "ref_close": (None, [vp]),
+            "ref_time_l1_fill_collist": (cd, [vp, ci, lp]), "ref_time_l2_path": (cd, [vp, cl, cl, ci, lp]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -119,6 +120,19 @@ class RefObject:
         n = C.c_long()
         s = lib().ref_time_l2_tribox(self.h, b0, b1, threads, C.byref(n))
         return s, n.value
+
+    def time_l1_fill_collist(self, threads):
+        """(seconds, ray tests) of the Level-1 fill through the column lists on `threads` host threads (needs compact())."""
+        n = C.c_long()
+        s = lib().ref_time_l1_fill_collist(self.h, threads, C.byref(n))
+        return s, n.value
+
+    def time_l2_path(self, b0, b1, threads):
+        """(seconds, tri-box tests, ray tests) of Level 2 -- parity rays over the column list, then SAT over the cell list, per
+        sub-voxel -- over boundary cells [b0,b1) on `threads` host threads."""
+        out = (C.c_long * 2)()
+        s = lib().ref_time_l2_path(self.h, b0, b1, threads, out)
+        return s, int(out[0]), int(out[1])
 
     # arrays
     def level1_inout(self): return _arr(lib().ref_level1InOut(self.h), self.cells, np.float32)
