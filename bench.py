@@ -254,6 +254,84 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def run_batch_arm(args):
+    """--batch MODELS: config 5.  Every rank (one per GPU) runs gpv_voxelize_batch over its share of the model files on its own GPU
+    with its share of the host threads; models are independent, so there is no collective (replicas only).  value = models of all
+    ranks / the slowest rank's wall time.  --impl reference: the reference's CPU path (oracle/_ref) over a bounded sample of the models."""
+    import shutil
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    l1, l2 = (64, 4) if (args.l1, args.l2) == (256, 16) else (args.l1, args.l2)   # the config's own resolution unless given
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import run_batch
+    distinct = min(100, args.batch)
+    d = tempfile.mkdtemp(prefix="gpvbatch%d_" % rank)
+    files = run_batch.write_meshes(d, distinct)
+    cfg = {"workload": "batched dataset generation: %d drilled-block .off meshes (~5 k triangles, %d distinct, seeded) at Level1 %d + Level2 %d^3 "
+                       "(BASELINE.json configs[4]); per model: parse + H2D + voxelize + D2H%s" % (args.batch, distinct, l1, l2, " + file write" if args.batch_save else ""),
+           "l1": l1, "l2": l2, "mesh": "drilled blocks", "models": args.batch, "cache": "every model is a different file and a fresh set of device streams (no reuse between models)"}
+    threads_all = os.cpu_count() or 1
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n = min(args.batch, 12)
+        t0 = time.perf_counter()
+        for k in range(n):
+            ref = ReferencePath(files[k % distinct], l1, l2, threads_all)
+            ref.sample(ref.nb)
+            if ref.kind == "reference":
+                ref.o.close()
+        dt = time.perf_counter() - t0
+        print(json.dumps({"impl": "reference", "metric": "models/s", "value": n / dt, "unit": "models/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 * dt,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": n / dt, "unit": "models/s", "cores": threads_all, "kind": "reference", "sample": "%d models through the whole CPU path (oracle/_ref)" % n},
+                          "e2e": {"value": n / dt, "unit": "models/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        shutil.rmtree(d, ignore_errors=True)
+        return
+    import torch
+    import gpview_b200 as gpv
+    from gpview_b200 import binding as B
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    paths = [files[i % distinct] for i in range(args.batch)][rank::world]
+    threads = max(1, threads_all // world)
+    out = os.path.join(d, "out") if args.batch_save else None
+    if out:
+        os.makedirs(out)
+    prm = gpv.Params(l1, l2, gpv.GPV_SAVE_COMPUTED_ONLY)
+    B.voxelize_batch(paths[:min(len(paths), 4 * threads)], prm, [local], threads, None)   # warm-up: contexts, pools
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    st = B.voxelize_batch(paths, prm, [local], threads, out, 0, False)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    nn = torch.tensor([float(st["models_done"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nn)
+    if rank == 0:
+        clocks = sampler.stop(t0, t1, 0)
+        total, secs = float(nn.item()), float(tt.item())
+        per = {k: 1e3 * st[k + "_seconds"] / max(1, st["models_done"]) for k in ("parse", "gpu", "save")}
+        print(json.dumps({"metric": "models/s", "value": total / secs, "unit": "models/s", "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": 1e3 * secs,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": dict(cfg, parallelism="%d GPU(s) x %d host threads each, one gpv_ctx per thread, models round-robin; no collective" % (world, threads)),
+                          "clocks": clocks, "gpu_launches": int(total) * 16,
+                          "e2e": {"value": total / secs, "unit": "models/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                                  "note": "the batch call IS end to end: model files in, host streams%s out" % (" and files" if out else "")},
+                          "per_model_ms_summed_over_threads_rank0": per, "level2_resizes_rank0": st["level2_resizes"], "failed": int(st["models_failed"])}))
+    shutil.rmtree(d, ignore_errors=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -264,9 +342,16 @@ def main():
     ap.add_argument("--l1", type=int, default=256)
     ap.add_argument("--l2", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, metavar="MODELS",
+                    help="BASELINE.json configs[4]: batched dataset generation -- MODELS drilled-block .off meshes (~5 k triangles) at --l1 64 --l2 4 through "
+                         "gpv_voxelize_batch (parse + H2D + voxelize + D2H per model), models/s over all GPUs; one step = the whole batch")
+    ap.add_argument("--batch-save", action="store_true", help="--batch: also write every model's files (GPV_SAVE_COMPUTED_ONLY) into a temporary directory")
+    ap.add_argument("--normals", action="store_true", help="also produce Level1Normal / Level2Normal (the reference's full six-file contract, SURVEY.md 8f1): 3 B per cell / sub-voxel more")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: slabs written into rank 0's buffers over NVLink peer memory from inside the kernels (GPV_GATHER), or gathered with NCCL send/recv")
     args = ap.parse_args()
+    if args.batch:
+        return run_batch_arm(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -315,14 +400,14 @@ def main():
     if peer:  # rank 0 owns the whole-grid streams; the other ranks map them (CUDA IPC) and write their slabs over NVLink
         desc = B.CGatherDesc()
         if rank == 0:
-            desc = ctx.gather_create(plane * nz, int(whole.nb) * n23)
+            desc = ctx.gather_create(plane * nz, int(whole.nb) * n23, gpv.GPV_NORMALS if args.normals else 0)
         t = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8).cuda()
         dist.broadcast(t, 0)
         desc = B.CGatherDesc.from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
         ctx.gather_attach(desc, rank, world)
     # peer gather: the library shares the work out itself (Level-1 bytes by equal z-slabs, Level-2 by interleaved column groups); the
     # cost-balanced z cuts above are what the NCCL gather and the e2e leg use
-    params = gpv.Params(args.l1, args.l2, gpv.GPV_PROFILE_L2 | (gpv.GPV_GATHER if peer else 0), 0 if peer else z0, 0 if peer else z1)  # timed steps: CUDA events around the two Level-2 kernels only, on the launching stream
+    params = gpv.Params(args.l1, args.l2, gpv.GPV_PROFILE_L2 | (gpv.GPV_GATHER if peer else 0) | (gpv.GPV_NORMALS if args.normals else 0), 0 if peer else z0, 0 if peer else z1)  # timed steps: CUDA events around the two Level-2 kernels only, on the launching stream
     gathered = {}
 
     # the timed call goes straight to the C ABI with arguments built once (a Python wrapper object per call costs tens of microseconds
@@ -477,10 +562,13 @@ def main():
     slab = ctx.voxelize_device(d_tris, mesh, e2e_params, sptr)  # sizes of this rank's slab (the gathering call above reports the whole grid)
     cells, nb, n23 = slab.cells, slab.nb, slab.n23
     hb = {k: L.gpv_alloc_host(n) for k, n in (("l1", cells), ("pre", cells * 4), ("bi", nb * 4 + 64), ("l2", nb * n23 + 64))}
+    if args.normals:
+        hb.update({k: L.gpv_alloc_host(n) for k, n in (("n1", cells * 3), ("n2", nb * n23 * 3 + 64))})
     pinned_tris = L.gpv_alloc_host(mesh.ntri * 36)
     C.memmove(pinned_tris, C.cast(mesh.c.tris, C.c_void_p), mesh.ntri * 36)
     pm = B.CMesh(mesh.c.n_tri, C.cast(pinned_tris, C.POINTER(C.c_float)), mesh.c.bbox_min, mesh.c.bbox_max, mesh.c.max_model_size, mesh.c.n_verts)
-    hs = B.CHostStreams(hb["l1"], hb["pre"], hb["bi"], hb["l2"], None, None, nb * n23 + 64, nb + 16)
+    hs = B.CHostStreams(hb["l1"], hb["pre"], hb["bi"], hb["l2"], hb.get("n1"), hb.get("n2"), nb * n23 + 64, nb + 16)
+    e2e_base_flags = gpv.GPV_NORMALS if args.normals else 0
     r2 = B.CResult()
     pre_np = np.ctypeslib.as_array(C.cast(hb["pre"], C.POINTER(C.c_int32)), shape=(cells,))
     nb_all = torch.zeros(world, dtype=torch.int64, device="cuda")
@@ -496,7 +584,7 @@ def main():
                 np.add(pre_np, base, out=pre_np)
 
     def time_e2e(flags):
-        e2e_params.c.flags = flags
+        e2e_params.c.flags = flags | e2e_base_flags
         for _ in range(args.warmup):
             e2e_step()
         barrier()
@@ -524,7 +612,7 @@ def main():
     packed_wins = e2e_packed_ms is not None and e2e_packed_ms < e2e_bytes_ms
     e2e_ms = e2e_packed_ms if packed_wins else e2e_bytes_ms
     l2_d2h = nb * n23 // 4 if packed_wins else nb * n23
-    dsum = torch.tensor([float(cells + cells * 4 + nb * 4 + l2_d2h)], device="cuda", dtype=torch.float64)
+    dsum = torch.tensor([float(cells + cells * 4 + nb * 4 + l2_d2h + (3 * cells + 3 * nb * n23 if args.normals else 0))], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dsum)
     e2e = {"value": tests / (e2e_ms * 1e-3) / 1e9, "unit": "G tri-box tests/s", "ms_per_model": e2e_ms,
@@ -616,6 +704,16 @@ def main():
         roof_hbm = {"kernel": sat_name, "bound": "hbm", "achieved": out_bytes / (k_l2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": out_bytes / (k_l2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": n_sat.get("dram_bytes"),
                     "peak_source": hbm_src, "algorithmic": "1 B per Level-2 voxel written (%d B)" % out_bytes}
+        roof_normals = None
+        if args.normals and world == 1:
+            t1n, t2n = phase_acc.get("l1_normals", 0.0) / args.steps, phase_acc.get("l2_normals", 0.0) / args.steps
+            roof_normals = {"kernels": "k_l1_normals (+ 127-fill), k_l2_normals", "bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "peak_source": hbm_src,
+                            "algorithmic": "3 B written per Level-1 cell (%d B) and per Level-2 sub-voxel (%d B)" % (3 * res.cells, 3 * res.nb * res.n23),
+                            "level1": {"ms": t1n, "achieved": 3 * res.cells / (t1n * 1e-3) / 1e9 if t1n > 0 else None},
+                            "level2": {"ms": t2n, "achieved": 3 * res.nb * res.n23 / (t2n * 1e-3) / 1e9 if t2n > 0 else None}}
+            for lv in ("level1", "level2"):
+                if roof_normals[lv]["achieved"]:
+                    roof_normals[lv]["frac"] = roof_normals[lv]["achieved"] / hbm_peak
         # every phase of the pipeline against the roofline that bounds it (algorithmic bytes / flops per unit x units
         # of this model, over the phase's CUDA-event time).  The Level-1 phases of a cessna-sized model are tens of microseconds of
         # launch-latency-bound work: their fractions say how far a 4 M-cell grid is from filling the machine, not kernel quality.
@@ -649,6 +747,10 @@ def main():
                 "counts": {"l1_inside": whole.counts[0], "l1_boundary": whole.counts[1]}}
         if phase_per_rank is not None:
             line["phase_ms_per_rank"] = phase_per_rank
+        if roof_normals is not None:
+            line["roofline_normals"] = roof_normals
+        if args.normals:
+            line["config"]["workload"] += " + Level1Normal / Level2Normal streams"
         if world == 1 and not args.no_cpu_baseline and path is not None:
             line["cpu_baseline"] = cpu_baseline(path, args.l1, args.l2, os.cpu_count() or 1)
         print(json.dumps(line))

@@ -69,7 +69,7 @@ NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destr
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
                   "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_check_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_expand_packed_l2", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
-                  "gpv_gather_create", "gpv_gather_attach", "gpv_gather_attach_local", "gpv_gather_detach", "gpv_gather_set_timeout", "gpv_gather_result"]
+                  "gpv_gather_create", "gpv_gather_create_ex", "gpv_gather_normals", "gpv_gather_attach", "gpv_gather_attach_local", "gpv_gather_detach", "gpv_gather_set_timeout", "gpv_gather_result"]
 COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
 
 _lib = None
@@ -116,6 +116,8 @@ def lib():
         L.gpv_measure_fp32_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         L.gpv_measure_copy_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         L.gpv_gather_create.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(CGatherDesc)]
+        L.gpv_gather_create_ex.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, C.POINTER(CGatherDesc)]
+        L.gpv_gather_normals.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         L.gpv_gather_attach.argtypes = [vp, C.POINTER(CGatherDesc), C.c_int, C.c_int]
         L.gpv_gather_attach_local.argtypes = [vp, vp, C.c_int, C.c_int]
         L.gpv_gather_detach.argtypes = [vp]; L.gpv_gather_detach.restype = None
@@ -290,10 +292,23 @@ class Context:
         return C.c_void_p(lib().gpv_stream(self.h))
 
     # ---- multi-GPU gather over NVLink peer memory (gpv_gather_*)
-    def gather_create(self, cells_total, l2_capacity):
+    def gather_create(self, cells_total, l2_capacity, flags=0):
         d = CGatherDesc()
-        _check(lib().gpv_gather_create(self.h, int(cells_total), int(l2_capacity), C.byref(d)))
+        _check(lib().gpv_gather_create_ex(self.h, int(cells_total), int(l2_capacity), int(flags), C.byref(d)))
         return d
+
+    def gather_normals(self, cells_total, nb, n23):
+        """Gathering rank: (level1_normal, level2_normal) copied to the host."""
+        p1, p2 = C.c_void_p(), C.c_void_p()
+        _check(lib().gpv_gather_normals(self.h, C.byref(p1), C.byref(p2)))
+        out = []
+        for ptr, n in ((p1, cells_total * 3), (p2, nb * n23 * 3)):
+            a = np.empty(int(n), np.uint8)
+            if n:
+                _check(lib().gpv_memcpy_d2h(a.ctypes.data, ptr, a.nbytes, None))
+                _check(lib().gpv_stream_sync(None))
+            out.append(a)
+        return out[0], out[1]
 
     def gather_attach(self, desc, rank, world):
         _check(lib().gpv_gather_attach(self.h, C.byref(desc), rank, world))

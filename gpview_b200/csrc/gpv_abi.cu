@@ -90,6 +90,8 @@ struct gpv_ctx {
 		unsigned epoch = 0;
 		uint8_t* l1 = nullptr; int32_t* prefix = nullptr; uint8_t* l2 = nullptr; gpv::GatherMail* mail = nullptr;
 		uint8_t* l2p = nullptr; // 2-bit packed Level-2 blocks of the peers (behind the byte stream in the same allocation)
+		uint8_t* l1n = nullptr; uint8_t* l2n = nullptr; // normal streams (behind the Level-1 bytes / the packed blocks), null without GPV_NORMALS
+		int flags = 0;
 		int64_t cellsTotal = 0, l2Cap = 0, nbTotal = 0;
 		unsigned long long timeoutNs = gpv::kGatherTimeoutNsDefault;
 	} gather;
@@ -117,7 +119,7 @@ static int preload_kernels()
 	GPV_LOAD(k_clear); GPV_LOAD(k_clear_bits); GPV_LOAD(k_prepare); GPV_LOAD(k_scan_offs3); GPV_LOAD((k_scan<MODE_CELLS, 1>)); GPV_LOAD((k_scan<MODE_CELLS, 4>));
 	GPV_LOAD(k_bin<false>); GPV_LOAD(k_bin<true>); GPV_LOAD(k_cross<false>); GPV_LOAD(k_cross<true>); GPV_LOAD(k_fill_sweep);
 	GPV_LOAD(k_sort_segments); GPV_LOAD(k_sort_long);
-	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l2_rays_overflow); GPV_LOAD(k_ray_units); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals);
+	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l2_rays_overflow); GPV_LOAD(k_ray_units); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals); GPV_LOAD(k_scatter_blocks);
 	GPV_LOAD(k_l2<16, 0>); GPV_LOAD(k_l2<8, 0>); GPV_LOAD(k_l2<4, 0>); GPV_LOAD(k_l2<2, 0>); GPV_LOAD(k_l2<0, 0>);
 	GPV_LOAD(k_l2<16, 1>); GPV_LOAD(k_l2<8, 1>); GPV_LOAD(k_l2<4, 1>); GPV_LOAD(k_l2<2, 1>); GPV_LOAD(k_l2<0, 1>);
 	GPV_LOAD(k_l2<16, 2>); GPV_LOAD(k_l2<8, 2>); GPV_LOAD(k_l2<4, 2>); GPV_LOAD(k_l2<0, 2>); GPV_LOAD(k_gather_expand); GPV_LOAD(k_gather_wait_rank);
@@ -278,7 +280,8 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	const bool wantN = (prm->flags & GPV_NORMALS) != 0;
 	const bool gather = (prm->flags & GPV_GATHER) != 0;
 	if (gather && !c->gather.on) return fail("GPV_GATHER without gpv_gather_attach");
-	if (gather && (wantN || sink)) return fail("GPV_GATHER supports neither GPV_NORMALS nor the host-stream call");
+	if (gather && sink) return fail("GPV_GATHER does not support the host-stream call");
+	if (gather && wantN && !c->gather.l1n) return fail("GPV_GATHER with GPV_NORMALS: the gather buffers were created without normal streams (gpv_gather_create_ex)");
 	if (gpv_make_grid(bmin, bmax, max_model_size, prm->voxel_count, wantL2 ? prm->voxel_count2 : 1, &out->grid)) return 1;
 	const gpv_grid& gg = out->grid;
 	if (gg.n2 > 32) return fail("voxel_count2 > 32 is not supported (Level-2 z parity is kept in one 32-bit word)");
@@ -531,6 +534,10 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			                                                         (long long)g.z0 * ncol, c->l1Normal.as<unsigned char>());
 			launches++;
 		}
+		if (gather) { // this rank's z-slab of the Level-1 normals -> rank 0 (copy engine; peers store into rank 0 only once it has entered the call)
+			GPV_CUDA(cudaStreamWaitEvent(st, c->evFork[1], 0));
+			GPV_CUDA(cudaMemcpyAsync(c->gather.l1n + (size_t)oz0 * ncol * 3, c->l1Normal.as<unsigned char>() + (size_t)oz0 * ncol * 3, (size_t)(oz1 - oz0) * ncol * 3, cudaMemcpyDefault, st));
+		}
 	}
 	if (sink && sink->level1_normal && wantN) { // (the other Level-1 streams left from the side stream, right behind the fill sweep)
 		GPV_CUDA(cudaEventRecord(c->evChunk[kMaxChunks], st));
@@ -555,12 +562,16 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		const bool canPack = (n23 % 32) == 0;
 		const bool packHost = sink && sink->level2_inout && (prm->flags & GPV_PACKED_L2) && canPack;
 		const bool packPeer = gather && c->gather.rank != 0 && canPack;
-		const int outMode = (packHost || packPeer) ? L2_OUT_PACKED : (gather && c->gather.rank != 0) ? L2_OUT_STAGED : L2_OUT_BYTES;
+		// (a peer that also computes normals keeps its blocks: they are written locally and copied to rank 0 by k_scatter_blocks)
+		const bool peer = gather && c->gather.rank != 0, peerLocal = peer && wantN;
+		const int outMode = (packHost || packPeer) ? L2_OUT_PACKED : (peer && !peerLocal) ? L2_OUT_STAGED : L2_OUT_BYTES;
 		typedef void (*L2Fn)(GridP, L2IO, L2K);
 		static const L2Fn table[3][5] = { { k_l2<16, 0>, k_l2<8, 0>, k_l2<4, 0>, k_l2<2, 0>, k_l2<0, 0> },
 			                              { k_l2<16, 1>, k_l2<8, 1>, k_l2<4, 1>, k_l2<2, 1>, k_l2<0, 1> },
 			                              { k_l2<16, 2>, k_l2<8, 2>, k_l2<4, 2>, k_l2<0, 2>, k_l2<0, 2> } }; // (n2 = 2 cannot be packed: canPack is false)
 		const L2Fn l2fn = table[outMode][g.n2 == 16 ? 0 : g.n2 == 8 ? 1 : g.n2 == 4 ? 2 : g.n2 == 2 ? 3 : 4];
+		if (peerLocal && (packPeer ? c->l2Packed.ensure((size_t)(nB * n23) / 4 + 64) : c->l2State.ensure((size_t)(nB * n23) + 64))) return 1;
+		if (peerLocal && !packPeer) lio.l2State = c->l2State.as<unsigned char>();
 		if (packHost) {
 			if (c->l2Packed.ensure((size_t)(nB * n23) / 4 + 64)) return 1;
 			if (c->hPackedCap < (size_t)(nB * n23) / 4) {
@@ -571,7 +582,7 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 				c->hPackedCap = want;
 			}
 		}
-		lio.l2Packed = packHost ? c->l2Packed.as<unsigned char>() : packPeer ? c->gather.l2p : nullptr;
+		lio.l2Packed = (packHost || (packPeer && peerLocal)) ? c->l2Packed.as<unsigned char>() : packPeer ? c->gather.l2p : nullptr;
 		if (smem > 48 * 1024) return fail("k_l2: shared-memory layout exceeds 48 KB"); // cannot happen for n2 <= 32 (41 KB)
 		// K4a: boundary cells grouped by Level-1 column, then the parity bits of every sub-voxel column, one walk of the column list per column
 		k_col_cells<<<(unsigned)((nB + 255) / 256), 256, 0, st>>>(lio.boundaryIndex, (int)nB, (int)ncol, g.nx, cx, cy, cz, lio.colCellOff, c->colCellCnt.as<int>(), c->colCellList.as<int2>(),
@@ -615,14 +626,23 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			}
 		}
 		if (packHost) { packedChunks = nChunks; packedPer = per; packedCells = nRefine; }
-		lio.cellList = nullptr;
-		lio.bBegin = 0; lio.nBoundary = (int)nB;
+		if (peerLocal && nRefine > 0) { // the blocks went to local memory (the normals read them back): their copies to rank 0
+			const int per = (int)(packPeer ? n23 / 4 : n23);
+			k_scatter_blocks<<<(unsigned)std::min<long long>(c->smCount * 8, (nRefine * (per % 8 ? per : per / 8) + 255) / 256), 256, 0, st>>>(packPeer ? c->l2Packed.as<unsigned char>() : c->l2State.as<unsigned char>(),
+			                                                                                                    packPeer ? c->gather.l2p : c->gather.l2, c->colCellList.as<int2>(), nRefine, per);
+			launches++;
+		}
 		mark(GPV_PHASE_L2_NORMALS);
-		if (wantN) {
-			k_l2_normals<<<(unsigned)((nB * n23 + 255) / 256), 256, 0, st>>>(g, lio, c->l2Normal.as<unsigned char>());
+		if (wantN && nRefine > 0) {
+			lio.bBegin = 0; lio.nBoundary = (int)nRefine; // (slots again: the cells this call refined)
+			const bool fromPacked = packHost || (peerLocal && packPeer);
+			k_l2_normals<<<(unsigned)((nRefine * n23 + kNormalVoxels - 1) / kNormalVoxels), 256, 0, st>>>(g, lio, fromPacked ? nullptr : lio.l2State, fromPacked ? c->l2Packed.as<uint2>() : nullptr,
+			                                                                     gather ? c->gather.l2n : c->l2Normal.as<unsigned char>());
 			launches++;
 			if (sink && sink->level2_normal) GPV_CUDA(cudaMemcpyAsync(sink->level2_normal, c->l2Normal.p, (size_t)(nB * n23) * 3, cudaMemcpyDeviceToHost, st));
 		}
+		lio.cellList = nullptr;
+		lio.bBegin = 0; lio.nBoundary = (int)nB;
 	}
 	GPV_CUDA(cudaStreamWaitEvent(st, c->evJoin[1], 0)); // the parity-fill branch joins
 	if (gather) { // completion flag behind this rank's last store; the gathering rank returns when every rank has signalled
@@ -674,7 +694,7 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	out->d_boundary_index = c->boundaryIndex.as<int32_t>();
 	out->d_level2_inout = !wantL2 ? nullptr : gather ? c->gather.l2 : c->l2State.as<uint8_t>();
 	out->d_level1_normal = wantN ? c->l1Normal.as<uint8_t>() : nullptr;
-	out->d_level2_normal = (wantN && wantL2) ? c->l2Normal.as<uint8_t>() : nullptr;
+	out->d_level2_normal = (wantN && wantL2) ? (gather ? c->gather.l2n : c->l2Normal.as<uint8_t>()) : nullptr;
 	out->d_cell_off = c->bTriOff.as<uint32_t>(); out->d_cell_tris = c->cellTris.as<int32_t>();
 	out->d_col_off = c->colOff.as<uint32_t>(); out->d_col_count = c->colCount.as<int32_t>(); out->d_col_tris = c->colTris.as<int32_t>();
 	out->l1_inside = (int64_t)T2.l1Inside; out->l1_boundary = nB;
@@ -730,11 +750,12 @@ extern "C" void gpv_gather_detach(gpv_ctx* c)
 	}
 	// the ctx that created the buffers keeps owning them (and their sizes): it can be attached again, as rank 0 of a new session
 	const bool owner = c->gather.owner;
+	const int gflags = c->gather.flags;
 	const int64_t cellsTotal = c->gather.cellsTotal, l2Cap = c->gather.l2Cap;
 	const unsigned long long timeoutNs = c->gather.timeoutNs;
 	c->gather = {};
 	c->gather.timeoutNs = timeoutNs;
-	if (owner) { c->gather.owner = true; c->gather.cellsTotal = cellsTotal; c->gather.l2Cap = l2Cap; }
+	if (owner) { c->gather.owner = true; c->gather.cellsTotal = cellsTotal; c->gather.l2Cap = l2Cap; c->gather.flags = gflags; }
 }
 
 extern "C" int gpv_gather_set_timeout(gpv_ctx* c, double seconds)
@@ -745,12 +766,21 @@ extern "C" int gpv_gather_set_timeout(gpv_ctx* c, double seconds)
 }
 
 static size_t gather_packed_offset(int64_t l2Cap) { return ((size_t)l2Cap + 255) & ~(size_t)255; } // the peers' 2-bit blocks live behind the byte stream
+static size_t gather_l2n_offset(int64_t l2Cap) { return gather_packed_offset(l2Cap) + (((size_t)l2Cap / 4 + 255) & ~(size_t)255); } // ... and the Level-2 normals behind those
+static size_t gather_l1n_offset(int64_t cells) { return ((size_t)cells + 255) & ~(size_t)255; }                                   // Level-1 normals behind the Level-1 bytes
 
 extern "C" int gpv_gather_create(gpv_ctx* c, int64_t cells_total, int64_t l2_capacity, gpv_gather_desc* out)
 {
+	return gpv_gather_create_ex(c, cells_total, l2_capacity, 0, out);
+}
+
+extern "C" int gpv_gather_create_ex(gpv_ctx* c, int64_t cells_total, int64_t l2_capacity, int flags, gpv_gather_desc* out)
+{
 	if (!c || !out || cells_total <= 0 || l2_capacity < 0) return fail("gpv_gather_create: bad argument");
 	GPV_CUDA(cudaSetDevice(c->device));
-	if (c->gatherL1.ensure((size_t)cells_total + 64) || c->gatherPrefix.ensure((size_t)cells_total * 4 + 64) || c->gatherL2.ensure(gather_packed_offset(l2_capacity) + (size_t)l2_capacity / 4 + 64) ||
+	const bool n = (flags & GPV_NORMALS) != 0;
+	if (c->gatherL1.ensure(gather_l1n_offset(cells_total) + (n ? (size_t)cells_total * 3 : 0) + 64) || c->gatherPrefix.ensure((size_t)cells_total * 4 + 64) ||
+	    c->gatherL2.ensure(gather_l2n_offset(l2_capacity) + (n ? (size_t)l2_capacity * 3 : 0) + 64) ||
 	    c->gatherMail.ensure(sizeof(GatherMail)))
 		return 1;
 	GPV_CUDA(cudaMemset(c->gatherMail.p, 0, sizeof(GatherMail)));
@@ -761,20 +791,23 @@ extern "C" int gpv_gather_create(gpv_ctx* c, int64_t cells_total, int64_t l2_cap
 	GPV_CUDA(cudaIpcGetMemHandle(&h, c->gatherPrefix.p)); memcpy(out->prefix, &h, 64);
 	GPV_CUDA(cudaIpcGetMemHandle(&h, c->gatherL2.p)); memcpy(out->l2, &h, 64);
 	GPV_CUDA(cudaIpcGetMemHandle(&h, c->gatherMail.p)); memcpy(out->mailbox, &h, 64);
-	out->cells_total = cells_total; out->l2_capacity = l2_capacity; out->owner_device = c->device;
+	out->cells_total = cells_total; out->l2_capacity = l2_capacity; out->owner_device = c->device; out->reserved = flags & GPV_NORMALS;
 	const unsigned long long timeoutNs = c->gather.timeoutNs;
 	c->gather = {};
 	c->gather.timeoutNs = timeoutNs;
-	c->gather.owner = true; c->gather.cellsTotal = cells_total; c->gather.l2Cap = l2_capacity;
+	c->gather.owner = true; c->gather.cellsTotal = cells_total; c->gather.l2Cap = l2_capacity; c->gather.flags = flags & GPV_NORMALS;
 	return 0;
 }
 
-static int gather_bind(gpv_ctx* c, void* l1, void* prefix, void* l2, void* mail, int64_t cellsTotal, int64_t l2Cap, int rank, int world, bool ipc)
+static int gather_bind(gpv_ctx* c, void* l1, void* prefix, void* l2, void* mail, int64_t cellsTotal, int64_t l2Cap, int rank, int world, bool ipc, int flags)
 {
 	if (rank < 0 || world < 1 || rank >= world || world > 16) return fail("gpv_gather_attach: bad rank / world (at most 16 ranks)");
 	c->gather.on = true; c->gather.ipc = ipc; c->gather.rank = rank; c->gather.world = world; c->gather.epoch = 0;
 	c->gather.l1 = (uint8_t*)l1; c->gather.prefix = (int32_t*)prefix; c->gather.l2 = (uint8_t*)l2; c->gather.mail = (GatherMail*)mail;
 	c->gather.l2p = (uint8_t*)l2 + gather_packed_offset(l2Cap);
+	c->gather.flags = flags;
+	c->gather.l1n = (flags & GPV_NORMALS) ? (uint8_t*)l1 + gather_l1n_offset(cellsTotal) : nullptr;
+	c->gather.l2n = (flags & GPV_NORMALS) ? (uint8_t*)l2 + gather_l2n_offset(l2Cap) : nullptr;
 	c->gather.cellsTotal = cellsTotal; c->gather.l2Cap = l2Cap;
 	return 0;
 }
@@ -788,7 +821,7 @@ extern "C" int gpv_gather_attach(gpv_ctx* c, const gpv_gather_desc* d, int rank,
 		// a new session starts from epoch 0 on every rank: flags left by an earlier session on the same buffers must not satisfy its polls.
 		// (Attaching is collective: no peer is inside a call.)
 		GPV_CUDA(cudaMemset(c->gatherMail.p, 0, sizeof(GatherMail)));
-		return gather_bind(c, c->gatherL1.p, c->gatherPrefix.p, c->gatherL2.p, c->gatherMail.p, d->cells_total, d->l2_capacity, rank, world, false);
+		return gather_bind(c, c->gatherL1.p, c->gatherPrefix.p, c->gatherL2.p, c->gatherMail.p, d->cells_total, d->l2_capacity, rank, world, false, d->reserved);
 	}
 	void* p[4] = {};
 	const unsigned char* hs[4] = { d->l1, d->prefix, d->l2, d->mailbox };
@@ -797,7 +830,7 @@ extern "C" int gpv_gather_attach(gpv_ctx* c, const gpv_gather_desc* d, int rank,
 		memcpy(&h, hs[k], 64);
 		GPV_CUDA(cudaIpcOpenMemHandle(&p[k], h, cudaIpcMemLazyEnablePeerAccess));
 	}
-	return gather_bind(c, p[0], p[1], p[2], p[3], d->cells_total, d->l2_capacity, rank, world, true);
+	return gather_bind(c, p[0], p[1], p[2], p[3], d->cells_total, d->l2_capacity, rank, world, true, d->reserved);
 }
 
 extern "C" int gpv_gather_attach_local(gpv_ctx* c, gpv_ctx* owner, int rank, int world)
@@ -812,9 +845,19 @@ extern "C" int gpv_gather_attach_local(gpv_ctx* c, gpv_ctx* owner, int rank, int
 	const bool own = c == owner;
 	if (own && rank != 0) return fail("gpv_gather_attach_local: the owner is rank 0");
 	const int64_t cellsTotal = owner->gather.cellsTotal, l2Cap = owner->gather.l2Cap;
+	const int gflags = owner->gather.flags;
 	if (own) { cudaSetDevice(owner->device); GPV_CUDA(cudaMemset(owner->gatherMail.p, 0, sizeof(GatherMail))); GPV_CUDA(cudaSetDevice(c->device)); } // new session (see gpv_gather_attach)
 	if (!own) { const unsigned long long t = c->gather.timeoutNs; c->gather = {}; c->gather.timeoutNs = t; }
-	return gather_bind(c, owner->gatherL1.p, owner->gatherPrefix.p, owner->gatherL2.p, owner->gatherMail.p, cellsTotal, l2Cap, rank, world, false);
+	return gather_bind(c, owner->gatherL1.p, owner->gatherPrefix.p, owner->gatherL2.p, owner->gatherMail.p, cellsTotal, l2Cap, rank, world, false, gflags);
+}
+
+extern "C" int gpv_gather_normals(gpv_ctx* c, uint8_t** l1n, uint8_t** l2n)
+{
+	if (!c || !c->gather.on || c->gather.rank != 0) return fail("gpv_gather_normals: not the gathering rank");
+	if (!c->gather.l1n) return fail("gpv_gather_normals: the gather buffers were created without normal streams");
+	if (l1n) *l1n = c->gather.l1n;
+	if (l2n) *l2n = c->gather.l2n;
+	return 0;
 }
 
 extern "C" int gpv_gather_result(gpv_ctx* c, uint8_t** l1, int32_t** prefix, uint8_t** l2, int64_t* nb)

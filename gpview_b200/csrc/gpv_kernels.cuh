@@ -1418,6 +1418,20 @@ __global__ void __launch_bounds__(kL2Threads, GPV_L2_MINBLOCKS) k_l2(GridP g, L2
 	if (lane == 0 && (nIn | nBd)) { atomicAdd(&io.totals->l2Inside, (unsigned long long)nIn); atomicAdd(&io.totals->l2Boundary, (unsigned long long)nBd); }
 }
 
+// Level-2 blocks this rank refined (cellList[0 .. nCells)), bytesPerCell each, from a local whole-grid array to the
+// same offsets of the gathering rank's array: used when the blocks are needed locally as well (GPV_NORMALS reads the states back).
+__global__ void __launch_bounds__(256) k_scatter_blocks(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, const int2* __restrict__ cellList,
+                                                         long long nCells, int bytesPerCell)
+{
+	const int unit = (bytesPerCell & 7) ? 1 : 8, per = bytesPerCell / unit; // 8 bytes at a time when the blocks allow it (any even n2)
+	for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nCells * per; i += (long long)gridDim.x * 256) {
+		const long long cell = i / per;
+		const size_t off = (size_t)cellList[cell].x * bytesPerCell + (size_t)(i - cell * per) * unit;
+		if (unit == 8) *reinterpret_cast<uint2*>(dst + off) = *reinterpret_cast<const uint2*>(src + off);
+		else dst[off] = src[off];
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ gather over peer memory
 // Multi-GPU: every rank writes its share of the streams straight into the gathering rank's buffers over NVLink peer
 // memory, from inside the kernels that produce them.  Level 1 is computed by every rank over the whole grid (the parity rays need
@@ -1537,28 +1551,61 @@ __global__ void k_l1_normals(const float4* __restrict__ tri48, const int* __rest
 	l1Normal[li * 3] = encode_normal(ax); l1Normal[li * 3 + 1] = encode_normal(ay); l1Normal[li * 3 + 2] = encode_normal(az);
 }
 
-// K5b. Level-2 normals: only boundary sub-voxels (byte 254) re-run the SAT over the cell list, accumulating the
-// UN-normalised cross(e01,e02) of every hit in ascending order (cu:311-318: normalize() result discarded; cu:40-46),
-// then the host averaging of src/Object.cpp:2613-2632.  One thread per sub-voxel; others write 127,127,127.
-__global__ void __launch_bounds__(256) k_l2_normals(GridP g, L2IO io, unsigned char* __restrict__ l2Normal)
+// K5b. Level-2 normals: only boundary sub-voxels (SAT bit set) visit the cell list, accumulating the UN-normalised cross(e01,e02) of
+// every hit in ascending order (cu:311-318: normalize() result discarded; cu:40-46), then the host averaging of
+// src/Object.cpp:2613-2632; the others get 127,127,127.  A CTA takes 16,384 consecutive sub-voxels of the cells this call refined
+// (slots, like k_l2): every thread writes the neutral value for its sub-voxels and appends the boundary ones to a dense list in
+// shared memory; the list is then worked off by full warps (6 % of cessna's sub-voxels are boundary: one thread per sub-voxel
+// walking the list ran at a few lanes per warp and took 2.8 ms, five times the SAT kernel that found the hits).
+// A triangle is put through the full 13-predicate SAT only where the certified plane interval of its sub-voxel column (the one
+// k_l2 culls with, gpv::plane_row_interval) contains the sub-voxel: the predicate fails outside it, so the set of hits -- and with
+// the ascending list order the f32 sums -- are those of the reference's loop over the whole list.
+// `state`: file bytes (254 = boundary), or null with `packed` = the 2-bit words of L2_OUT_PACKED (boundary mask in .y).
+constexpr int kNormalVoxels = 16384; // (four cessna cells: ~1,000 boundary sub-voxels in the dense list, four full rounds of the CTA)
+__global__ void __launch_bounds__(256) k_l2_normals(GridP g, L2IO io, const unsigned char* __restrict__ state, const uint2* __restrict__ packed,
+                                                     unsigned char* __restrict__ l2Normal)
 {
-	const int n2 = g.n2;
-	const long long n23 = (long long)n2 * n2 * n2;
-	long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= (long long)io.nBoundary * n23) return;
-	unsigned char n0 = 127, n1 = 127, n2b = 127;
-	if (io.l2State[v] == 254) {
-		long long b = v / n23;
-		int loc = (int)(v - b * n23), r = loc / (n2 * n2), pq = loc - r * n2 * n2, q = pq / n2, p = pq - q * n2;
-		int l1 = io.boundaryIndex[b];
-		int kz = l1 / (g.nx * g.ny), ij = l1 - kz * g.nx * g.ny, jy = ij / g.nx, ix = ij - jy * g.nx;
-		float cxv = (float)(2 * p + 1) * g.h2x + io.cx[ix] - g.h1x;
-		float cyv = (float)(2 * q + 1) * g.h2y + io.cy[jy] - g.h1y;
-		float czv = (float)(2 * r + 1) * g.h2z + io.cz[kz] - g.h1z;
+	__shared__ unsigned short sList[kNormalVoxels];
+	__shared__ int sCount;
+	const int n2 = g.n2, n23 = n2 * n2 * n2, tid = threadIdx.x;
+	const long long total = (long long)(io.nBoundary - io.bBegin) * n23, V0 = (long long)blockIdx.x * kNormalVoxels;
+	const long long slot0 = V0 / n23;
+	const int rem0 = (int)(V0 - slot0 * n23);
+	if (tid == 0) sCount = 0;
+	__syncthreads();
+	auto locate = [&](int i, long long& b, int& loc) { // sub-voxel i of this CTA -> (boundary rank, index inside the block)
+		const int s = (rem0 + i) / n23;
+		loc = rem0 + i - s * n23;
+		const long long slot = io.bBegin + slot0 + s;
+		b = io.cellList ? (long long)__ldg(&io.cellList[slot].x) : slot;
+	};
+	for (int i = tid; i < kNormalVoxels && V0 + i < total; i += 256) {
+		long long b; int loc;
+		locate(i, b, loc);
+		const long long gv = b * n23 + loc; // index in Level2InOut.raw
+		const bool boundary = state ? state[gv] == 254 : ((__ldcg(&packed[gv >> 5].y) >> (gv & 31)) & 1u) != 0;
+		l2Normal[gv * 3] = 127; l2Normal[gv * 3 + 1] = 127; l2Normal[gv * 3 + 2] = 127;
+		if (boundary) sList[atomicAdd(&sCount, 1)] = (unsigned short)i;
+	}
+	__syncthreads(); // (also orders this CTA's neutral bytes before the boundary sub-voxels' stores below)
+	const float inv2h = 1.f / (2.f * g.h2z);
+	for (int k = tid; k < sCount; k += 256) {
+		long long b; int loc;
+		locate((int)sList[k], b, loc);
+		const int r = loc / (n2 * n2), pq = loc - r * n2 * n2, q = pq / n2, p = pq - q * n2;
+		const float4 mid = __ldg(io.cellMid + b);
+		const float cxv = l2_centre(p, g.h2x, mid.x, g.h1x), cyv = l2_centre(q, g.h2y, mid.y, g.h1y), czv = l2_centre(r, g.h2z, mid.z, g.h1z);
+		const float cz0 = l2_centre(0, g.h2z, mid.z, g.h1z);
+		const float slack = 9.5367431640625e-07f * (fabsf(cz0) + 2.f * g.gsz);
 		float sx = 0, sy = 0, sz = 0, cnt = 0;
-		for (unsigned k = io.bTriOff[b]; k < io.bTriOff[b + 1]; k++) {
-			int t = io.cellTris[k];
-			float4 A = __ldg(io.tri48 + (size_t)t * 3), B = __ldg(io.tri48 + (size_t)t * 3 + 1), C = __ldg(io.tri48 + (size_t)t * 3 + 2);
+		const unsigned kEnd = io.bTriOff[b + 1];
+		for (unsigned kk = io.bTriOff[b]; kk < kEnd; kk++) {
+			const int t = io.cellTris[kk];
+			const float4 A = __ldg(io.tri48 + (size_t)t * 3), pl = __ldg(io.plane16 + t);
+			PlaneRec P; P.sx = pl.x; P.ny = pl.y; P.nz = pl.z; P.R = pl.w;
+			int rlo, rhi;
+			if (!plane_row_interval(P, A.z - cz0, A.x - cxv, A.y - cyv, inv2h, slack, n2, rlo, rhi) || r < rlo || r > rhi) continue; // certified: the plane predicate fails here
+			const float4 B = __ldg(io.tri48 + (size_t)t * 3 + 1), C = __ldg(io.tri48 + (size_t)t * 3 + 2);
 			if (tri_box_overlap(cxv, cyv, czv, g.h2x, g.h2y, g.h2z, A.x, A.y, A.z, B.x, B.y, B.z, C.x, C.y, C.z)) {
 				float ax = B.x - A.x, ay = B.y - A.y, az = B.z - A.z, bx = C.x - A.x, by = C.y - A.y, bz = C.z - A.z;
 				sx += ay * bz - az * by; sy += az * bx - ax * bz; sz += ax * by - ay * bx; // cutil_math.h:409 cross()
@@ -1568,10 +1615,10 @@ __global__ void __launch_bounds__(256) k_l2_normals(GridP g, L2IO io, unsigned c
 		if (cnt > 0) {
 			float ax = sx / cnt, ay = sy / cnt, az = sz / cnt;
 			normalize3(ax, ay, az);
-			n0 = encode_normal(ax); n1 = encode_normal(ay); n2b = encode_normal(az);
+			const long long gv = b * n23 + loc;
+			l2Normal[gv * 3] = encode_normal(ax); l2Normal[gv * 3 + 1] = encode_normal(ay); l2Normal[gv * 3 + 2] = encode_normal(az);
 		}
 	}
-	l2Normal[v * 3] = n0; l2Normal[v * 3 + 1] = n1; l2Normal[v * 3 + 2] = n2b;
 }
 
 } // namespace gpv

@@ -193,8 +193,9 @@ int gpv_voxelize_host(gpv_ctx* ctx, const gpv_mesh* mesh, const gpv_params* para
  * callers' streams); rank 0's call returns once every rank has signalled, with the whole grid's counts in its gpv_result (the
  * other ranks report their own share).  All ranks must issue their GPV_GATHER calls in the same order; a rank's call does not
  * touch rank 0's buffers before rank 0 has entered the same call.  gpv_gather_desc is plain bytes: ship it to the other ranks
- * with any transport (torch.distributed broadcast, a file, a pipe).  GPV_NORMALS and the host-stream call are not supported
- * together with GPV_GATHER.  Every poll gives up after a timeout (5 s; gpv_gather_set_timeout) with an error return instead of
+ * with any transport (torch.distributed broadcast, a file, a pipe).  The host-stream call is not supported together with
+ * GPV_GATHER; GPV_NORMALS is, on buffers created by gpv_gather_create_ex(GPV_NORMALS): every rank sends the Level-1 normals of its z-slab and
+ * the Level-2 normals of the blocks it refined.  Every poll gives up after a timeout (5 s; gpv_gather_set_timeout) with an error return instead of
  * hanging the GPU.  If several gathering contexts share ONE process and device (tests): raise CUDA_DEVICE_MAX_CONNECTIONS so
  * that their streams do not share a hardware work queue, and do not allocate device memory while a gathering call is in flight
  * (CUDA serialises streams around cudaMalloc/cudaFree) -- run one plain call first to grow the pools. */
@@ -202,9 +203,11 @@ typedef struct {
 	unsigned char l1[64], prefix[64], l2[64], mailbox[64];   /* cudaIpcMemHandle_t of the four allocations */
 	int64_t cells_total;                                     /* nx*ny*nz of the grid the buffers were sized for */
 	int64_t l2_capacity;                                     /* bytes behind l2 */
-	int32_t owner_device, reserved;
+	int32_t owner_device, reserved;                          /* reserved: flags the buffers were created with (GPV_NORMALS) */
 } gpv_gather_desc;
 int gpv_gather_create(gpv_ctx* ctx, int64_t cells_total, int64_t l2_capacity, gpv_gather_desc* out);      /* gathering rank only */
+/* flags = GPV_NORMALS: room for the two normal streams as well (3 B per cell / sub-voxel), so that GPV_GATHER | GPV_NORMALS calls can be made */
+int gpv_gather_create_ex(gpv_ctx* ctx, int64_t cells_total, int64_t l2_capacity, int flags, gpv_gather_desc* out);
 int gpv_gather_attach(gpv_ctx* ctx, const gpv_gather_desc* desc, int rank, int world);                    /* every rank, the gathering one included */
 int gpv_gather_attach_local(gpv_ctx* ctx, gpv_ctx* owner, int rank, int world);                           /* same-process ranks (tests, several GPUs in one process) */
 void gpv_gather_detach(gpv_ctx* ctx);                                /* the creating ctx keeps its buffers and may be attached again (a new session) */
@@ -212,6 +215,7 @@ int gpv_gather_set_timeout(gpv_ctx* ctx, double seconds);            /* how long
 /* gathering rank, after its own GPV_GATHER call returned (it returns once every rank has signalled completion): device views of
  * the whole-grid streams and the total boundary count */
 int gpv_gather_result(gpv_ctx* ctx, uint8_t** d_level1_inout, int32_t** d_prefix, uint8_t** d_level2_inout, int64_t* n_boundary_total);
+int gpv_gather_normals(gpv_ctx* ctx, uint8_t** d_level1_normal, uint8_t** d_level2_normal);   /* gathering rank, buffers of gpv_gather_create_ex(GPV_NORMALS) */
 
 /* Object::SaveVoxelization (src/Object.cpp:2934-3075): the six ObjN*.{txt,raw} files into `dir` from host streams */
 int gpv_save(const gpv_mesh* mesh, const gpv_result* res, const gpv_host_streams* host, int obj_id, const char* dir);

@@ -286,6 +286,57 @@ def test_peer_memory_gather_equals_whole(product, ctx, tmp_path_factory, name, l
             c.close()
 
 
+@pytest.mark.parametrize("name,l1,l2,R", [("cessna", 64, 4, 3), ("torus", 32, 8, 2), ("cad", 36, 3, 4), ("sphere", 20, 16, 2)])
+def test_peer_memory_gather_with_normals(product, ctx, tmp_path_factory, name, l1, l2, R):
+    """GPV_GATHER | GPV_NORMALS (the six-file contract across several GPUs): every rank also delivers the Level-1
+    normals of its z-slab and the Level-2 normals of the blocks it refined; rank 0's six streams == the single call's, bit for bit
+    (n2 = 4, 8, 16: 2-bit blocks kept locally for the normals and copied over; n2 = 3: byte blocks)."""
+    import threading
+    path = mesh_path(name, tmp_path_factory.getbasetemp())
+    mesh = product.load_mesh(path)
+    whole = ctx.voxelize(mesh, product.Params(l1, l2, product.GPV_NORMALS))
+    want = dict(l1=whole.level1_inout(), pre=whole.prefix(), l2=whole.level2_inout(), n1=whole.level1_normal(), n2=whole.level2_normal())
+    cells, n23 = whole.cells, whole.n23
+    ranks = [product.Context(0) for _ in range(R)]
+    try:
+        ranks[0].gather_create(cells, whole.nb * n23, product.GPV_NORMALS)
+        for r in range(R):
+            ranks[r].gather_attach_local(ranks[0], r, R)
+        dev = [ranks[r].upload(mesh) for r in range(R)]
+        for r in range(R):
+            ranks[r].voxelize_device(dev[r], mesh, product.Params(l1, l2, product.GPV_NORMALS))   # grows the pools (see the test above)
+        for rep in range(2):
+            errs = []
+
+            def work(r):
+                try:
+                    ranks[r].voxelize_device(dev[r], mesh, product.Params(l1, l2, product.GPV_GATHER | product.GPV_NORMALS), ranks[r].stream())
+                except Exception as e:  # noqa: BLE001
+                    errs.append((r, repr(e)))
+            th = [threading.Thread(target=work, args=(r,)) for r in range(R)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            assert not errs, errs
+            g_l1, g_pre, g_l2, nb = ranks[0].gather_result(cells, n23)
+            g_n1, g_n2 = ranks[0].gather_normals(cells, nb, n23)
+            assert nb == whole.nb
+            for k, got in (("l1", g_l1), ("pre", g_pre), ("l2", g_l2), ("n1", g_n1), ("n2", g_n2)):
+                assert np.array_equal(got, want[k]), (rep, k)
+        for r in range(R):
+            ranks[r].free_device(dev[r])
+        # buffers created without normal streams refuse the combination
+        ranks[0].gather_detach()
+        ranks[0].gather_create(cells, whole.nb * n23)
+        ranks[0].gather_attach_local(ranks[0], 0, 1)
+        with pytest.raises(product.GpvError):
+            ranks[0].voxelize(mesh, product.Params(l1, l2, product.GPV_GATHER | product.GPV_NORMALS))
+    finally:
+        for c in ranks:
+            c.close()
+
+
 def test_large_grid_paths_match_oracle(product, oracle, ctx, tmp_path_factory):
     """A grid beyond 16 M cells takes the 4-sub-tile boundary scan (k_scan<CELLS, 4>) and, at n2 = 2, the flat multi-cell pair
     space of k_l2 with 64 cells per CTA: every stream against the oracle (certified fill; ~25 M cells, n2 = 2)."""
