@@ -243,6 +243,7 @@ def run_reference_arm(args):
             "config": workload_config(args, tests_model, ref.triangles, ref.grid),
             "cpu_baseline": {"value": v, "unit": "G tri-box tests/s", "cores": threads, "kind": ref.kind, "sample": ref.describe(cells)},
             "e2e": {"value": v, "unit": "G tri-box tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "parallelism": "%d host threads (Object::ClassifyTessellation itself on one: the reference's own loop)" % threads,
             "ray_tests_per_step": tot_r / args.steps}
     if ref.kind == "reference" and ref.nb:
         line["ms_per_model_extrapolated"] = 1e3 * (tot_s / args.steps) * ref.nb / cells
@@ -741,7 +742,8 @@ def main():
         line = {"metric": "G tri-box tests/s", "value": value, "unit": "G tri-box tests/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "ms_per_model": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "cessna.obj fixture (reference sample mesh)" if args.mesh == "cessna" else "synthetic",
-                "config": dict(workload_config(args, int(tests), mesh.ntri, [int(x) for x in res.num_div]), parallelism=("%d ranks, Level-1 replicated, %s; gathered streams == single-GPU result: %s" % (world, "Level-1 bytes / prefix sums by equal z-slabs, Level-2 refinement by interleaved Level-1 column groups, every rank writing its share into rank 0's buffers over NVLink peer memory from inside the kernels (GPV_GATHER): no collective, no exchange step, completion flags through a mailbox" if peer else "z-slabs (cuts %s), NCCL send/recv gather to rank 0" % cuts, gather_ok)) if world > 1 else "1 GPU"),
+                "config": workload_config(args, int(tests), mesh.ntri, [int(x) for x in res.num_div]),   # the workload only: identical in the reference arm's line
+                "parallelism": ("%d ranks, Level-1 replicated, %s; gathered streams == single-GPU result: %s" % (world, "Level-1 bytes / prefix sums by equal z-slabs, Level-2 refinement by interleaved Level-1 column groups, every rank writing its share into rank 0's buffers over NVLink peer memory from inside the kernels (GPV_GATHER): no collective, no exchange step, completion flags through a mailbox" if peer else "z-slabs (cuts %s), NCCL send/recv gather to rank 0" % cuts, gather_ok)) if world > 1 else "1 GPU",
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_rays": roof_rays, "roofline_hbm": roof_hbm, "roofline_phases": per_phase,
                 "phase_ms": {k: round(v / args.steps, 4) for k, v in phase_acc.items() if v > 0},
                 "counts": {"l1_inside": whole.counts[0], "l1_boundary": whole.counts[1]}}

@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GPVIEW_B200_LIB", os.path.join(HERE, "libgpview_b200.so"))  # override: A/B builds of the same ABI
 
-GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE, GPV_GATHER, GPV_SAVE_COMPUTED_ONLY, GPV_BATCH_TOLERANT_LOAD, GPV_PROFILE_L2, GPV_PACKED_L2 = 1, 2, 4, 8, 16, 32, 64, 128, 256
+GPV_NORMALS, GPV_NO_LEVEL2, GPV_KEEP_LISTS, GPV_PROFILE, GPV_GATHER, GPV_SAVE_COMPUTED_ONLY, GPV_BATCH_TOLERANT_LOAD, GPV_PROFILE_L2, GPV_PACKED_L2, GPV_COLLISION = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 
 
 class GpvError(RuntimeError):
@@ -59,6 +59,14 @@ class CGatherDesc(C.Structure):
                 ("l2_capacity", C.c_int64), ("owner_device", C.c_int32), ("reserved", C.c_int32)]
 
 
+class CCollision(C.Structure):
+    _fields_ = [("count", C.c_int64), ("index_base", C.c_int64), ("d_inv_index", C.c_void_p), ("d_center", C.c_void_p), ("d_extent", C.c_void_p)]
+
+
+class CHierarchy(C.Structure):
+    _fields_ = [("num_levels", C.c_int), ("n_boxes", C.c_int64), ("d_mid", C.c_void_p), ("d_half", C.c_void_p), ("d_solid", C.c_void_p), ("d_child", C.c_void_p)]
+
+
 class CBatchStats(C.Structure):
     _fields_ = [("models_done", C.c_int64), ("models_failed", C.c_int64), ("models_skipped", C.c_int64), ("seconds", C.c_double),
                 ("parse_seconds", C.c_double), ("gpu_seconds", C.c_double), ("save_seconds", C.c_double), ("level2_resizes", C.c_int64)]
@@ -68,7 +76,7 @@ class CBatchStats(C.Structure):
 NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_stream", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh", "gpv_load_mesh_ex",
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
-                  "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_check_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_expand_packed_l2", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
+                  "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_check_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_expand_packed_l2", "gpv_collision_boxes", "gpv_build_hierarchy", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
                   "gpv_gather_create", "gpv_gather_create_ex", "gpv_gather_normals", "gpv_gather_attach", "gpv_gather_attach_local", "gpv_gather_detach", "gpv_gather_set_timeout", "gpv_gather_result"]
 COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
 
@@ -113,6 +121,8 @@ def lib():
         L.gpv_voxelize_batch.argtypes = [C.POINTER(C.c_char_p), C.c_int64, C.POINTER(CParams), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int,
                                          C.POINTER(CBatchStats)]
         L.gpv_expand_packed_l2.argtypes = [vp, C.c_int64, vp]
+        L.gpv_collision_boxes.argtypes = [vp, vp, C.POINTER(CCollision)]
+        L.gpv_build_hierarchy.argtypes = [vp, vp, C.POINTER(CHierarchy)]
         L.gpv_measure_fp32_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         L.gpv_measure_copy_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         L.gpv_gather_create.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(CGatherDesc)]
@@ -331,6 +341,29 @@ class Context:
                 _check(lib().gpv_stream_sync(None))
             out.append(a)
         return out[0], out[1], out[2], int(nb.value)
+
+    def _d2h(self, ptr, n, dtype):
+        out = np.empty(int(n), dtype)
+        if n and ptr:
+            _check(lib().gpv_memcpy_d2h(out.ctypes.data, ptr, out.nbytes, None))
+            _check(lib().gpv_stream_sync(None))
+        return out
+
+    def collision_boxes(self):
+        """gpv_collision_boxes on the last call's streams: (inv_index, centre[n,3], extent[n,3]) copied to the host."""
+        c = CCollision()
+        _check(lib().gpv_collision_boxes(self.h, None, C.byref(c)))
+        n = int(c.count)
+        return (self._d2h(c.d_inv_index, n, np.int32) + int(c.index_base), self._d2h(c.d_center, n * 3, np.float32).reshape(-1, 3),
+                self._d2h(c.d_extent, n * 3, np.float32).reshape(-1, 3))
+
+    def build_hierarchy(self):
+        """gpv_build_hierarchy on the last call's streams (made with GPV_COLLISION): (levels, mid[n,3], half[n,3], solid[n], child[n,2])."""
+        h = CHierarchy()
+        _check(lib().gpv_build_hierarchy(self.h, None, C.byref(h)))
+        n = int(h.n_boxes)
+        return (int(h.num_levels), self._d2h(h.d_mid, n * 3, np.float32).reshape(-1, 3), self._d2h(h.d_half, n * 3, np.float32).reshape(-1, 3),
+                self._d2h(h.d_solid, n, np.uint8), self._d2h(h.d_child, n * 2, np.int32).reshape(-1, 2))
 
     def fp32_peak(self):
         v = C.c_double()

@@ -21,6 +21,7 @@
 #include "../../include/gpview_b200.h"
 #include "gpv_internal.h"
 #include "gpv_kernels.cuh"
+#include "gpv_collision.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -64,7 +65,7 @@ struct gpv_ctx {
 	int device = 0;
 	int smCount = 0;
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
-	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, aabbxy16, longList, colCursor, binBits, colCellCnt, colCellOff, colCellList, l2Par, cellMid, rayOver, rayOverflow, l2Packed;
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, aabbxy16, longList, colCursor, binBits, colCellCnt, colCellOff, colCellList, l2Par, cellMid, rayOver, rayOverflow, l2Packed, solidWords, occCount, occOff, occInv, occCenter, occExtent, hierMid, hierHalf, hierSolid, hierChild;
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {}, evEnd[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
@@ -82,6 +83,8 @@ struct gpv_ctx {
 	void* cleanCellCount = nullptr; size_t cleanCellBytes = 0; // [cleanCellCount, +cleanCellBytes)
 	void* cleanBits = nullptr;                                  // the whole binBits pool at this address
 	cudaEvent_t evBinDone = nullptr;
+	// what the last completed call left on the device, for gpv_collision_boxes / gpv_build_hierarchy
+	struct { bool valid = false, whole = false, solid = false; gpv::GridP g{}; long long cells = 0; } last;
 	int debugOwnWorld = 0, debugOwnRank = 0; // GPV_DEBUG_OWN (profiling one rank's share of a gathering call on a single GPU)
 	// GPV_GATHER (gpv_gather_*): the gathering rank's whole-grid streams and mailbox, local or mapped over NVLink
 	struct {
@@ -119,7 +122,7 @@ static int preload_kernels()
 	GPV_LOAD(k_clear); GPV_LOAD(k_clear_bits); GPV_LOAD(k_prepare); GPV_LOAD(k_scan_offs3); GPV_LOAD((k_scan<MODE_CELLS, 1>)); GPV_LOAD((k_scan<MODE_CELLS, 4>));
 	GPV_LOAD(k_bin<false>); GPV_LOAD(k_bin<true>); GPV_LOAD(k_cross<false>); GPV_LOAD(k_cross<true>); GPV_LOAD(k_fill_sweep);
 	GPV_LOAD(k_sort_segments); GPV_LOAD(k_sort_long);
-	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l2_rays_overflow); GPV_LOAD(k_ray_units); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals); GPV_LOAD(k_scatter_blocks);
+	GPV_LOAD(k_col_cells); GPV_LOAD(k_l2_rays); GPV_LOAD(k_l2_rays_overflow); GPV_LOAD(k_ray_units); GPV_LOAD(k_l1_normals); GPV_LOAD(k_l2_normals); GPV_LOAD(k_scatter_blocks); GPV_LOAD(k_occupied_count); GPV_LOAD(k_occupied_write); GPV_LOAD(k_hier_leaves); GPV_LOAD(k_hier_level);
 	GPV_LOAD(k_l2<16, 0>); GPV_LOAD(k_l2<8, 0>); GPV_LOAD(k_l2<4, 0>); GPV_LOAD(k_l2<2, 0>); GPV_LOAD(k_l2<0, 0>);
 	GPV_LOAD(k_l2<16, 1>); GPV_LOAD(k_l2<8, 1>); GPV_LOAD(k_l2<4, 1>); GPV_LOAD(k_l2<2, 1>); GPV_LOAD(k_l2<0, 1>);
 	GPV_LOAD(k_l2<16, 2>); GPV_LOAD(k_l2<8, 2>); GPV_LOAD(k_l2<4, 2>); GPV_LOAD(k_l2<0, 2>); GPV_LOAD(k_gather_expand); GPV_LOAD(k_gather_wait_rank);
@@ -178,7 +181,7 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->aabbxy16, &c->longList, &c->colCursor, &c->binBits, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->rayOver, &c->rayOverflow, &c->l2Packed, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->aabbxy16, &c->longList, &c->colCursor, &c->binBits, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->rayOver, &c->rayOverflow, &c->l2Packed, &c->solidWords, &c->occCount, &c->occOff, &c->occInv, &c->occCenter, &c->occExtent, &c->hierMid, &c->hierHalf, &c->hierSolid, &c->hierChild, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
 	gpv_gather_detach(c);
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
@@ -279,6 +282,8 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	const bool wantL2 = !(prm->flags & GPV_NO_LEVEL2) && prm->voxel_count2 > 0;
 	const bool wantN = (prm->flags & GPV_NORMALS) != 0;
 	const bool gather = (prm->flags & GPV_GATHER) != 0;
+	const bool wantSolid = (prm->flags & GPV_COLLISION) != 0;
+	c->last.valid = false;
 	if (gather && !c->gather.on) return fail("GPV_GATHER without gpv_gather_attach");
 	if (gather && sink) return fail("GPV_GATHER does not support the host-stream call");
 	if (gather && wantN && !c->gather.l1n) return fail("GPV_GATHER with GPV_NORMALS: the gather buffers were created without normal streams (gpv_gather_create_ex)");
@@ -453,7 +458,8 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	bo.prefix = c->prefix.as<int>(); bo.bTriOff = c->bTriOff.as<unsigned>(); bo.cellTris = c->cellTris.as<int>();
 	bo.colOff = c->colOff.as<unsigned>(); bo.colTris = c->colTris.as<int>(); bo.colCursor = c->colCursor.as<int>();
 	bo.bits = c->binBits.as<unsigned>() + bitsCap / 32; // the fill sweep's own bitmap
-	if (c->longList.ensure((size_t)(nB + ncol) * 4 + 64)) return 1; // (every allocation of the call happens before the exchange and the fork: a growing pool's cudaFree synchronises the device)
+	if (c->longList.ensure((size_t)(nB + ncol) * 4 + 64)) return 1;
+	if (wantSolid && !gather && c->solidWords.ensure((size_t)((g.z1 - g.z0 + 31) / 32) * ncol * 4 + 64)) return 1; // (every allocation of the call happens before the exchange and the fork: a growing pool's cudaFree synchronises the device)
 	if (gather) {
 		// every rank sees the same global boundary count: a gather buffer that is too small is refused by all of them, before anything is written
 		if (wantL2 && nB * n23 > c->gather.l2Cap) return fail("GPV_GATHER: Level-2 gather buffer too small for the boundary cells of the grid");
@@ -485,7 +491,7 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		const size_t slabOff = gather ? (size_t)oz0 * ncol : 0; // offset of the slab inside the whole-grid arrays of a gathering call
 		dim3 grid((g.nx + 31) / 32, g.ny, (oz1 - oz0 + 127) / 128), block(32, 4);
 		k_fill_sweep<<<grid, block, 0, side>>>(ray48, gs, cx, cy, cz, c->crossOff.as<unsigned>(), c->crossTri.as<int>(), c->bmask.as<unsigned char>() + slabOff / 8,
-		                                       c->l1State.as<unsigned char>() + slabOff, dT);
+		                                       c->l1State.as<unsigned char>() + slabOff, dT, (wantSolid && !gather) ? c->solidWords.as<unsigned>() : nullptr);
 		launches += 2;
 		if (gather) {
 			// This slab of the Level-1 bytes and of the (global) prefix sums -> their final place on the gathering rank: two contiguous
@@ -687,6 +693,7 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	if (gather && T2.gatherError) return fail("GPV_GATHER: timed out waiting for a peer rank");
 	if (gather) c->gather.nbTotal = nB; // the boundary ranks are global on every rank
 
+	c->last.valid = !gather; c->last.whole = g.z0 == 0 && g.z1 == g.nz; c->last.solid = wantSolid && !gather; c->last.g = g; c->last.cells = cells;
 	out->z0 = oz0; out->z1 = oz1;
 	out->cells = cells; out->n_boundary = nB; out->n23 = n23; out->n_refined = wantL2 ? (gather ? (int64_t)T2.nLocalCells : nB) : 0;
 	out->d_level1_inout = c->l1State.as<uint8_t>() + (gather ? (size_t)oz0 * ncol : 0); // this call's slab of the bytes (gather: a copy went to rank 0)
@@ -867,6 +874,76 @@ extern "C" int gpv_gather_result(gpv_ctx* c, uint8_t** l1, int32_t** prefix, uin
 	if (prefix) *prefix = c->gather.prefix;
 	if (l2) *l2 = c->gather.l2;
 	if (nb) *nb = c->gather.nbTotal;
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ voxel hierarchy / collision structures
+extern "C" int gpv_collision_boxes(gpv_ctx* c, void* stream, gpv_collision* out)
+{
+	if (!c || !out) return fail("gpv_collision_boxes: null argument");
+	memset(out, 0, sizeof *out);
+	if (!c->last.valid) return fail("gpv_collision_boxes: no completed (non-gathering) voxelization on this ctx");
+	GPV_CUDA(cudaSetDevice(c->device));
+	cudaStream_t st = (cudaStream_t)stream;
+	const GridP& g = c->last.g;
+	const long long cells = c->last.cells;
+	const long long nBlocks = (cells + kOccBlock - 1) / kOccBlock;
+	const size_t dsz = desc_bytes(nBlocks);
+	if (c->occCount.ensure((size_t)nBlocks * 4 + 32) || c->occOff.ensure((size_t)(nBlocks + 1) * 4 + 32) || c->desc.ensure(dsz + 32)) return 1;
+	GPV_CUDA(cudaMemsetAsync(c->desc.p, 0, dsz, st));
+	GPV_CUDA(cudaMemsetAsync(c->totals.as<char>() + 192, 0, 8, st));
+	k_occupied_count<<<(unsigned)nBlocks, 256, 0, st>>>(c->l1State.as<unsigned char>(), cells, c->occCount.as<int>());
+	int64_t launches = 0;
+	const ScanReq r[1] = { { c->occCount.as<int>(), nBlocks, c->occOff.as<unsigned>(), reinterpret_cast<unsigned*>(c->totals.as<char>() + 192), nullptr, 0 } };
+	launch_scans(c, st, r, 1, launches);
+	unsigned n = 0;
+	GPV_CUDA(cudaMemcpyAsync(&n, c->totals.as<char>() + 192, 4, cudaMemcpyDeviceToHost, st));
+	GPV_CUDA(cudaStreamSynchronize(st));
+	if (c->occInv.ensure((size_t)n * 4 + 32) || c->occCenter.ensure((size_t)n * 12 + 32) || c->occExtent.ensure((size_t)n * 12 + 32)) return 1;
+	if (n) k_occupied_write<<<(unsigned)nBlocks, 256, 0, st>>>(c->l1State.as<unsigned char>(), cells, c->occOff.as<unsigned>(), g.nx, g.ny, c->tabX.as<float>(), c->tabY.as<float>(),
+	                                                          c->tabZ.as<float>() + g.z0, g.h1x, g.h1y, g.h1z, c->occInv.as<int>(), c->occCenter.as<float>(), c->occExtent.as<float>());
+	GPV_CUDA(cudaStreamSynchronize(st));
+	GPV_CUDA(cudaGetLastError());
+	out->count = n; out->d_inv_index = c->occInv.as<int32_t>(); out->d_center = c->occCenter.as<float>(); out->d_extent = c->occExtent.as<float>();
+	out->index_base = (int64_t)g.z0 * g.nx * g.ny;
+	return 0;
+}
+
+extern "C" int gpv_build_hierarchy(gpv_ctx* c, void* stream, gpv_hierarchy* out)
+{
+	if (!c || !out) return fail("gpv_build_hierarchy: null argument");
+	memset(out, 0, sizeof *out);
+	if (!c->last.valid || !c->last.whole || !c->last.solid) return fail("gpv_build_hierarchy: needs a completed whole-grid voxelization made with GPV_COLLISION on this ctx");
+	const GridP& g = c->last.g;
+	auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
+	if (!pow2(g.nx) || !pow2(g.ny) || !pow2(g.nz) || (long long)g.nx * g.ny * g.nz < 2)
+		return fail("gpv_build_hierarchy: every grid dimension must be a power of two (Object::BuildHierarchy, src/Object.cpp:2790-2867, indexes out of bounds on other grids)");
+	GPV_CUDA(cudaSetDevice(c->device));
+	cudaStream_t st = (cudaStream_t)stream;
+	const int total = g.nx * g.ny * g.nz;
+	int numLevels = 0;
+	{ float y = (float)total; while (y > 1) { y /= 2; numLevels++; } } // GetExponent2, src/Utilities.cpp:349
+	if (c->hierMid.ensure((size_t)(total - 1) * 12 + 32) || c->hierHalf.ensure((size_t)(total - 1) * 12 + 32) || c->hierSolid.ensure((size_t)total + 32) || c->hierChild.ensure((size_t)(total - 1) * 8 + 32)) return 1;
+	HierOut h{ c->hierMid.as<float>(), c->hierHalf.as<float>(), c->hierSolid.as<unsigned char>(), c->hierChild.as<int>() };
+	int numLevelBoxes = total / 2;
+	k_hier_leaves<<<(numLevelBoxes + 255) / 256, 256, 0, st>>>(total, g.nx, g.ny, c->tabX.as<float>(), c->tabY.as<float>(), c->tabZ.as<float>(), g.h1x, g.h1y, g.h1z, c->solidWords.as<unsigned>(), h);
+	int dX = g.nx / 2, dY = g.ny, dZ = g.nz, prevLevelIndex = 0, levelIndex = numLevelBoxes;
+	numLevelBoxes /= 2;
+	for (int level = 2; level < numLevels + 1; level++) { // the reference's level schedule, :2822-2866
+		int iSkip = (level % 3 == 1 && dX > 1) ? 2 : 1, jSkip = (level % 3 == 2 && dY > 1) ? 2 : 1, kSkip = (level % 3 == 0 && dZ > 1) ? 2 : 1;
+		if (iSkip == 1 && jSkip == 1 && kSkip == 1) { if (dX > 1) iSkip = 2; else if (dY > 1) jSkip = 2; else if (dZ > 1) kSkip = 2; }
+		k_hier_level<<<(numLevelBoxes + 255) / 256, 256, 0, st>>>(dX, dY, dZ, iSkip, jSkip, kSkip, prevLevelIndex, levelIndex, h);
+		if (iSkip == 2) dX /= 2;
+		if (jSkip == 2) dY /= 2;
+		if (kSkip == 2) dZ /= 2;
+		prevLevelIndex += numLevelBoxes * 2;
+		levelIndex += numLevelBoxes;
+		numLevelBoxes /= 2;
+	}
+	GPV_CUDA(cudaStreamSynchronize(st));
+	GPV_CUDA(cudaGetLastError());
+	out->num_levels = numLevels; out->n_boxes = total - 1;
+	out->d_mid = h.mid; out->d_half = h.half; out->d_solid = h.solid; out->d_child = h.child;
 	return 0;
 }
 

@@ -347,7 +347,8 @@ __global__ void __launch_bounds__(kWorkThreads) k_cross(const float4* __restrict
 // (fill first, SAT overwrites: src/Object.cpp:3158 then :3202; uchar(state*127) :3031).
 __global__ void __launch_bounds__(128) k_fill_sweep(const float4* __restrict__ ray48, GridP g, const float* __restrict__ cx, const float* __restrict__ cy,
                                                     const float* __restrict__ cz, const unsigned* __restrict__ crossOff, const int* __restrict__ crossTri,
-                                                    const unsigned char* __restrict__ bmask, unsigned char* __restrict__ l1State, Totals* totals)
+                                                    const unsigned char* __restrict__ bmask, unsigned char* __restrict__ l1State, Totals* totals,
+                                                    unsigned* __restrict__ solidWords)
 {
 	const int i = blockIdx.x * 32 + threadIdx.x;
 	const int j = blockIdx.y;
@@ -371,6 +372,9 @@ __global__ void __launch_bounds__(128) k_fill_sweep(const float4* __restrict__ r
 			par ^= m;
 		}
 		const size_t plane = (size_t)g.ny * g.nx;
+		// GPV_COLLISION: the parity of every cell INCLUDING the boundary ones (BBoxData::solid is the fill before the SAT pass overwrites it,
+		// src/Object.cpp:3165-3193): one word per (column, 32 z-layers), bit kk = layer kbase + kk
+		if (solidWords) solidWords[(size_t)((kbase - g.z0) >> 5) * plane + col] = par;
 		for (int kk = 0; kk < kn; kk++) {
 			size_t li = (size_t)(kbase - g.z0 + kk) * plane + col;
 			bool bd = (bmask[li >> 3] >> (li & 7)) & 1;

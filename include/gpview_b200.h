@@ -76,6 +76,7 @@ typedef struct {
 #define GPV_PACKED_L2  256     /* gpv_voxelize_host: Level2InOut crosses PCIe as 2 bits per sub-voxel and is expanded into the caller's bytes
                                   by a pool of host threads while the next chunk is on the bus (same bytes, a quarter of the transfer).
                                   Ignored when n2^3 is not a multiple of 32.  GPV_HOST_THREADS sets the pool size (default: all cores but one). */
+#define GPV_COLLISION  512     /* also keep the parity fill of every cell (incl. boundary cells) on the device: needed by gpv_build_hierarchy */
 #define GPV_GATHER      16     /* multi-GPU: write this rank's share of the streams straight into the gathering rank's buffers (gpv_gather_*) */
 #define GPV_BATCH_TOLERANT_LOAD 64 /* gpv_voxelize_batch: read the meshes with GPV_LOAD_TOLERANT (gpv_load_mesh_ex) */
 #define GPV_SAVE_COMPUTED_ONLY 32 /* gpv_voxelize_batch: write only the streams that were computed -- no 127-filled normal files when
@@ -248,6 +249,21 @@ void gpv_free_voxels(gpv_voxel_file* v);
  * their state, boundary cells with their Level-2 block.  Host memory in, host memory out (out_bytes >= the dense size). */
 int gpv_expand_dense(const uint8_t* level1_inout, const int32_t* prefix, const uint8_t* level2_inout, const int num_div[3], int n2,
                      int64_t n_boundary, uint8_t* out, int64_t out_bytes);
+
+/* ---- voxel hierarchy / collision structures over the Level-1 grid, from the streams the LAST call on the ctx left on
+ * the device (valid until the next call).  The reference builds both on the host, from its per-cell BBoxData array.
+ * gpv_collision_boxes = Object::CollisionInitCUDA (src/Object.cpp:3530-3572): the occupied cells (inside or boundary), ascending:
+ *   d_inv_index[k] = linear cell index - index_base (VoxelData::invIndex), d_center / d_extent = 3 floats per box (boxCenterCUDAData /
+ *   boxExtentCUDAData: midPoint, halfSize of the cell).
+ * gpv_build_hierarchy = Object::BuildHierarchy (:2790-2867) + CombineBBox (:2750-2788): the binary AABB hierarchy (cells - 1 boxes: x-neighbour
+ *   pairs first, then x / y / z halved in rotation), per box midPoint, halfSize, solid, the two child indices (children of the first level
+ *   are cell indices -- the reference leaves those uninitialised --, of every further level indices into this array).  `solid` of a cell is
+ *   its parity fill BEFORE the SAT pass (also for boundary cells, :3165-3193): the call must have been made with GPV_COLLISION, on the whole
+ *   grid.  Every grid dimension must be a power of two: the reference's loop indexes out of bounds otherwise (an error here). */
+typedef struct { int64_t count, index_base; int32_t* d_inv_index; float* d_center; float* d_extent; } gpv_collision;
+typedef struct { int num_levels; int64_t n_boxes; float* d_mid; float* d_half; uint8_t* d_solid; int32_t* d_child; } gpv_hierarchy;
+int gpv_collision_boxes(gpv_ctx* ctx, void* stream, gpv_collision* out);
+int gpv_build_hierarchy(gpv_ctx* ctx, void* stream, gpv_hierarchy* out);
 
 /* 2-bit packed Level-2 words -> file bytes (host memory in, host memory out).  One word pair (uint32 inside mask, uint32 boundary
  * mask) per 32 consecutive sub-voxels of Level2InOut.raw, bit k = sub-voxel 32*w + k; out gets 32*n_words bytes 0 / 127 / 254.

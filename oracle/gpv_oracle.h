@@ -80,6 +80,10 @@ int gpvo_voxelize(const gpvo_mesh* m, int voxelCount, int voxelCount2, int flags
 void gpvo_free_result(gpvo_result* r);
 int gpvo_save(const gpvo_mesh* m, const gpvo_result* r, int objID, const char* dir); /* six files, src/Object.cpp:2934-3075 */
 
+/* voxel hierarchy / collision structures over the Level-1 grid (gpv_oracle_collision.c) */
+int64_t gpvo_collision_boxes(const gpvo_mesh* m, const gpvo_result* r, int32_t* invIndex, float* mid, float* ext);         /* Object::CollisionInitCUDA, src/Object.cpp:3530-3572 */
+int gpvo_build_hierarchy(const gpvo_mesh* m, const gpvo_result* r, float* mid, float* half, uint8_t* solid, int32_t* child); /* Object::BuildHierarchy, :2790-2867 */
+
 /* timed loop nests for bench.py's cpu_baseline ("port"): returns seconds, writes the number of tests done */
 double gpvo_time_l2_tribox(const gpvo_mesh* m, const gpvo_result* r, int64_t b0, int64_t b1, int nThreads, int64_t* tests);
 

@@ -153,6 +153,27 @@ class OracleResult:
         s = lib().gpvo_time_l2_tribox(C.byref(self.mesh.m), C.byref(self.r), b0, b1, threads, C.byref(n))
         return s, int(n.value)
 
+    def collision_boxes(self):
+        """Object::CollisionInitCUDA's arrays (src/Object.cpp:3530-3572): (inv_index, centre[n,3], extent[n,3]) of the occupied cells."""
+        L = lib()
+        L.gpvo_collision_boxes.argtypes = [C.POINTER(Mesh), C.POINTER(Result), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gpvo_collision_boxes.restype = C.c_int64
+        inv, mid, ext = np.zeros(self.cells, np.int32), np.zeros(self.cells * 3, np.float32), np.zeros(self.cells * 3, np.float32)
+        n = L.gpvo_collision_boxes(C.byref(self.mesh.m), C.byref(self.r), inv.ctypes.data, mid.ctypes.data, ext.ctypes.data)
+        return inv[:n].copy(), mid[:n * 3].reshape(-1, 3).copy(), ext[:n * 3].reshape(-1, 3).copy()
+
+    def build_hierarchy(self):
+        """Object::BuildHierarchy (src/Object.cpp:2790-2867): (levels, mid[n,3], half[n,3], solid[n], child[n,2]) with n = cells - 1;
+        None for a grid whose dimensions are not all powers of two (the reference's loop is not defined there)."""
+        L = lib()
+        L.gpvo_build_hierarchy.argtypes = [C.POINTER(Mesh), C.POINTER(Result), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        n = self.cells - 1
+        mid, half, solid, child = np.zeros(max(n, 1) * 3, np.float32), np.zeros(max(n, 1) * 3, np.float32), np.zeros(max(n, 1), np.uint8), np.zeros(max(n, 1) * 2, np.int32)
+        lv = L.gpvo_build_hierarchy(C.byref(self.mesh.m), C.byref(self.r), mid.ctypes.data, half.ctypes.data, solid.ctypes.data, child.ctypes.data)
+        if lv < 0:
+            return None
+        return lv, mid.reshape(-1, 3), half.reshape(-1, 3), solid, child.reshape(-1, 2)
+
     def __del__(self):
         try:
             lib().gpvo_free_result(C.byref(self.r))

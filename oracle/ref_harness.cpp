@@ -733,6 +733,47 @@ double ref_time_l2_path(void* h, long b0, long b1, int nThreads, long* out)
 	return dt;
 }
 
+// ---- voxel hierarchy / collision structures: the reference's OWN Object::BuildHierarchy (src/Object.cpp:2790-2867,
+// with CombineBBox :2750-2788) on the bBox[] array of ref_l1_tribox, and the host loop of Object::CollisionInitCUDA (:3530-3552; the
+// rest of that function only uploads the two arrays).  bBox[].solid must hold the parity fill: call ref_set_solid first.
+void ref_set_solid(void* h, const unsigned char* fill)
+{
+	Ref* r = (Ref*)h;
+	VoxelData* vd = r->o->voxelData;
+	size_t N = (size_t)vd->numDivX * vd->numDivY * vd->numDivZ;
+	for (size_t k = 0; k < N; k++) { vd->bBox[k].solid = int(fill[k]) % 2; vd->bBox[k].index = (int)k; }  // (index: never initialised by the reference)
+}
+
+int ref_build_hierarchy(void* h, float* mid, float* half, unsigned char* solid, int* child)
+{
+	Ref* r = (Ref*)h;
+	VoxelData* vd = r->o->voxelData;
+	int total = vd->numDivX * vd->numDivY * vd->numDivZ;
+	r->o->BuildHierarchy(r->gp);
+	for (int i = 0; i < total - 1; i++) {
+		BBoxData& b = vd->bBoxHierarchy[i];
+		for (int a = 0; a < 3; a++) { mid[i * 3 + a] = b.midPoint[a]; half[i * 3 + a] = b.halfSize[a]; }
+		solid[i] = (unsigned char)b.solid; child[2 * i] = b.childIndex1; child[2 * i + 1] = b.childIndex2;
+	}
+	return vd->numLevels;
+}
+
+long ref_collision_boxes(void* h, int* invIndex, float* mid, float* ext)
+{
+	Ref* r = (Ref*)h;
+	VoxelData* vd = r->o->voxelData;
+	int totalNumBoxes = vd->numDivX * vd->numDivY * vd->numDivZ;
+	std::vector<int> inv;
+	for (int i = 0; i < totalNumBoxes; i++)                      // :3534-3539
+		if (vd->level1InOut[i] >= 1) inv.push_back(i);
+	for (size_t i = 0; i < inv.size(); i++) {                    // :3545-3555
+		int boxIndex = inv[i];
+		invIndex[i] = boxIndex;
+		for (int a = 0; a < 3; a++) { mid[i * 3 + a] = vd->bBox[boxIndex].midPoint[a]; ext[i * 3 + a] = vd->bBox[boxIndex].halfSize[a]; }
+	}
+	return (long)inv.size();
+}
+
 void ref_close(void* h)
 {
 	Ref* r = (Ref*)h;

@@ -38,6 +38,8 @@ def lib():
             "ref_stats": (None, [vp, lp]), "ref_tribox_batch": (None, [cl, fp, fp, fp, bp]),
             "ref_triray_batch": (None, [cl, fp, fp, bp]),
             "ref_time_l2_tribox": (cd, [vp, cl, cl, ci, lp]), "ref_close": (None, [vp]),
+            "ref_set_solid": (None, [vp, C.c_void_p]), "ref_build_hierarchy": (ci, [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+            "ref_collision_boxes": (cl, [vp, C.c_void_p, C.c_void_p, C.c_void_p]),
             "ref_time_l1_fill_collist": (cd, [vp, ci, lp]), "ref_time_l2_path": (cd, [vp, cl, cl, ci, lp]),
         }
         for name, (res, args) in sig.items():
@@ -133,6 +135,20 @@ class RefObject:
         out = (C.c_long * 2)()
         s = lib().ref_time_l2_path(self.h, b0, b1, threads, out)
         return s, int(out[0]), int(out[1])
+
+    def build_hierarchy(self, fill_only):
+        """The reference's own Object::BuildHierarchy over its bBox[] (needs l1_tribox()); `fill_only` = the parity fill (bBox[].solid)."""
+        f = np.ascontiguousarray(fill_only, np.uint8)
+        lib().ref_set_solid(self.h, f.ctypes.data)
+        n = self.cells - 1
+        mid, half, solid, child = np.zeros(n * 3, np.float32), np.zeros(n * 3, np.float32), np.zeros(n, np.uint8), np.zeros(n * 2, np.int32)
+        lv = lib().ref_build_hierarchy(self.h, mid.ctypes.data, half.ctypes.data, solid.ctypes.data, child.ctypes.data)
+        return lv, mid.reshape(-1, 3), half.reshape(-1, 3), solid, child.reshape(-1, 2)
+
+    def collision_boxes(self):
+        inv, mid, ext = np.zeros(self.cells, np.int32), np.zeros(self.cells * 3, np.float32), np.zeros(self.cells * 3, np.float32)
+        n = lib().ref_collision_boxes(self.h, inv.ctypes.data, mid.ctypes.data, ext.ctypes.data)
+        return inv[:n].copy(), mid[:n * 3].reshape(-1, 3).copy(), ext[:n * 3].reshape(-1, 3).copy()
 
     # arrays
     def level1_inout(self): return _arr(lib().ref_level1InOut(self.h), self.cells, np.float32)

@@ -378,3 +378,33 @@ def test_reference_gpu_path_tool_plumbing(oracle, tmp_path_factory):
     run = out["runs"]["emulated"]
     want = oracle.OracleMesh(mesh_path("torus", tmp_path_factory.getbasetemp())).voxelize(16, 2, oracle.FILL_CERTIFIED | oracle.NO_NORMALS, 2)
     assert run["counts"] == want.counts and run["tri_buffer"] == 50 and len(run["seconds"]) == 1
+
+
+@pytest.mark.parametrize("name,l1", [("sphere", 16), ("sphere", 32), ("block", 24), ("torus", 32), ("cessna", 64)])
+def test_collision_boxes_and_hierarchy_equal_the_reference(oracle, tmp_path_factory, name, l1):
+    """the oracle's restatement of Object::CollisionInitCUDA's host loop (src/Object.cpp:3530-3552) and of
+    Object::BuildHierarchy / CombineBBox (:2750-2867) against the reference's own code on its own BBoxData array -- every box's
+    midPoint, halfSize, solid flag and child indices bit for bit, on the grids the reference's loop is defined on (all dimensions powers
+    of two); on the others (GetNextDiv4 grids in general) it indexes out of bounds and the oracle refuses."""
+    import ctypes as C
+    from oracle import refbind
+    path = mesh_path(name, tmp_path_factory.getbasetemp())
+    r = oracle.OracleMesh(path).voxelize(l1, 0, oracle.FILL_CERTIFIED | oracle.NO_NORMALS, 4)
+    ro = refbind.RefObject(path)
+    ro.setup(l1, 0)
+    fill = r.l1_fill_only.astype(np.float32)
+    C.memmove(refbind.lib().ref_level1InOut(ro.h), fill.ctypes.data, fill.nbytes)      # the GL fill's stand-in, as everywhere in this file
+    ro.l1_tribox()                                                                      # Object::ClassifyTessellation: marks the boundary cells, builds bBox[]
+    assert np.array_equal(ro.level1_inout().astype(np.uint8), r.l1_state)
+    inv, mid, ext = r.collision_boxes()
+    rinv, rmid, rext = ro.collision_boxes()
+    assert len(inv) == r.counts[0] + r.counts[1] and np.array_equal(inv, rinv) and np.array_equal(mid, rmid) and np.array_equal(ext, rext)
+    h = r.build_hierarchy()
+    pow2 = all(int(n) & (int(n) - 1) == 0 for n in r.num_div)
+    assert (h is not None) == pow2
+    if h is not None:
+        lv, hm, hh, hs, hc = h
+        rlv, rm, rh, rs, rc = ro.build_hierarchy(r.l1_fill_only)
+        assert lv == rlv and np.array_equal(hm, rm) and np.array_equal(hh, rh) and np.array_equal(hs, rs) and np.array_equal(hc, rc)
+        assert hs[-1] == (1 if r.l1_fill_only.any() else 0)                             # the root is solid iff any cell's fill is
+    ro.close()

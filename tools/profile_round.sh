@@ -18,6 +18,8 @@ for n in 2 4 8; do
   python tools/ncu_summary.py ${OUT}_l2_share$n.ncu-rep ${OUT}_l2_share$n --traffic --share $n > /dev/null
 done
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file ${OUT}_launches_cad1024_2.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --mesh cad --l1 1024 --l2 2 > ${OUT}_launches_cad.log 2>&1
+# 5. like-for-like at the reference's own operator boundary: its three kernels (recompiled for sm_100a, strict IEEE) next to the compat tier's, per launch
+ncu --target-processes all --metrics gpu__time_duration.sum --clock-control none -k regex:"CUDAClassify|k_compat" --csv --log-file ${OUT}_launches_compat_vs_reference_kernels.csv python tools/bench_reference_gpu_path.py --l1 256 --l2 16 --reps 1 > ${OUT}_compat.log 2>&1
 rm -f gpurun_out/*_share*.ncu-rep   # (the whole-call report comes back for the source-level views; the share reports are summarised only)
 ls -la gpurun_out/ | tail -20
 # back in the build container: cp gpurun_out/traffic.json gpurun_out/${P}_*_summary.txt gpurun_out/${P}_launches_*.csv profiles/
