@@ -331,7 +331,13 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	// phase boundaries: ev[k] is recorded when phase k starts, ev[GPV_PHASE_COUNT] when the last one ends
 	// (phases of the side branch carry their own end event: they overlap the main branch)
 	bool marked[GPV_PHASE_COUNT + 1] = {}, sidePhase[GPV_PHASE_COUNT + 1] = {};
-	cudaStream_t side = c->sideStream;
+	// A small model (a dataset block: 10^5 cells, a few thousand triangles) gains nothing from the side / copy streams -- its kernels are
+	// launch-latency-sized -- but pays for every fork and join: a dozen driver calls of ~45 per model, and with sixteen host threads feeding
+	// one GPU (gpv_voxelize_batch) the driver calls are what bounds the throughput.  Such a call runs on the caller's stream alone.
+	const bool serial = !gather && !prof && cells <= (1ll << 20) && nTri <= 200000;
+	cudaStream_t side = serial ? st : c->sideStream, copy = serial ? st : c->copyStream;
+	auto ev_record = [&](cudaEvent_t e, cudaStream_t s) { return serial ? cudaSuccess : cudaEventRecord(e, s); };
+	auto ev_wait = [&](cudaStream_t s, cudaEvent_t e) { return serial ? cudaSuccess : cudaStreamWaitEvent(s, e, 0); };
 	auto mark = [&](int phase) { if (prof && (!profLight || phase >= GPV_PHASE_L2_RAYS)) { cudaEventRecord(c->ev[phase], st); marked[phase] = true; } };
 	auto mark_side = [&](int phase, bool begin) { if (prof && !profLight) { cudaEventRecord(begin ? c->ev[phase] : c->evEnd[phase], side); marked[phase] = sidePhase[phase] = true; } };
 
@@ -394,7 +400,7 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			                   { c->crossCnt.as<int>(), nTri, c->crossWorkOff.as<unsigned>(), nullptr, &dT->crossWork, dOff[1] } };
 		launch_scans(c, st, r, 2, launches);
 	}
-	GPV_CUDA(cudaEventRecord(c->evFork[0], st)); // the work spaces are scanned: the crossing count may start (side stream, launched below)
+	GPV_CUDA(ev_record(c->evFork[0], st)); // the work spaces are scanned: the crossing count may start (side stream, launched below)
 	BinOut bo{};
 	bo.cellCount = c->cellCount.as<int>(); bo.colCount = c->colCount.as<int>(); bo.totals = dT;
 	bo.bits = c->binBits.as<unsigned>(); bo.bitsCap = bitsCap;
@@ -417,13 +423,13 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		launches++;
 	}
 	// the two count sweeps are independent: the crossing count runs on the side stream beside the SAT count and the cell scan
-	GPV_CUDA(cudaStreamWaitEvent(side, c->evFork[0], 0));
+	GPV_CUDA(ev_wait(side, c->evFork[0]));
 	mark_side(GPV_PHASE_CROSS_COUNT, true);
 	k_cross<false><<<kWorkGrid, kWorkThreads, 0, side>>>(ray48, c->crossFp.as<int4>(), nTri, c->crossWorkOff.as<unsigned>(), g, cx, cy, c->crossCount.as<int>(), nullptr, nullptr, dT);
 	launches++;
 	mark_side(GPV_PHASE_CROSS_COUNT, false);
-	GPV_CUDA(cudaEventRecord(c->evJoin[0], side));
-	GPV_CUDA(cudaStreamWaitEvent(st, c->evJoin[0], 0));
+	GPV_CUDA(ev_record(c->evJoin[0], side));
+	GPV_CUDA(ev_wait(st, c->evJoin[0]));
 	{
 		const ScanReq r[3] = { { c->colCount.as<int>(), ncol, c->colOff.as<unsigned>(), &dT->colTotalOver, nullptr, dOff[3] },
 			                   { c->crossCount.as<int>(), ncol, c->crossOff.as<unsigned>(), &dT->crossTotal, nullptr, dOff[4] },
@@ -471,13 +477,13 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 	// main stream first (it carries the critical path): the fill sweep of the binning
 	mark(GPV_PHASE_BIN_FILL);
 	k_bin<true><<<kWorkGrid, kWorkThreads, 0, st>>>(tri48, nTri, c->binOff.as<unsigned>(), g, cx, cy, cz, bo);
-	GPV_CUDA(cudaEventRecord(c->evBinDone, st)); // both bitmaps are dead now: the side stream wipes what this call used (below)
+	GPV_CUDA(ev_record(c->evBinDone, st)); // both bitmaps are dead now: the side stream wipes what this call used (below)
 	launches++;
 	// side stream: the parity-fill branch (crossing lists -> fill sweep -> final Level-1 bytes), independent of the binning / sorting /
 	// Level-2 branch on the main stream until the end of the call.  (No fork event: the host has just synchronised the main stream.)
 	if (gather) { // peers wait here until rank 0 has entered this call: nothing is stored into its buffers before
 		k_gather_begin<<<1, 1, 0, side>>>(c->gather.mail, c->gather.rank, epoch, c->gather.timeoutNs, dT);
-		GPV_CUDA(cudaEventRecord(c->evFork[1], side)); // the main stream's Level-2 stores wait for it too (below)
+		GPV_CUDA(ev_record(c->evFork[1], side)); // the main stream's Level-2 stores wait for it too (below)
 		launches++;
 	}
 	mark_side(GPV_PHASE_CROSS_FILL, true);
@@ -508,10 +514,10 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		if (sink->prefix) GPV_CUDA(cudaMemcpyAsync(sink->prefix, c->prefix.p, (size_t)cells * 4, cudaMemcpyDeviceToHost, side));
 		if (sink->boundary_index && nB) GPV_CUDA(cudaMemcpyAsync(sink->boundary_index, c->boundaryIndex.p, (size_t)nB * 4, cudaMemcpyDeviceToHost, side));
 	}
-	GPV_CUDA(cudaStreamWaitEvent(side, c->evBinDone, 0));
+	GPV_CUDA(ev_wait(side, c->evBinDone));
 	k_clear_bits<<<c->smCount * 4, 256, 0, side>>>(c->binBits.as<unsigned>(), bitsCap, dT); // the next call finds the bitmaps zeroed
 	launches++;
-	GPV_CUDA(cudaEventRecord(c->evJoin[1], side));
+	GPV_CUDA(ev_record(c->evJoin[1], side));
 	mark(GPV_PHASE_SORT);
 	if (wantN || (prm->flags & GPV_KEEP_LISTS)) {
 		// canonical (ascending) order of the cell and column lists: needed only where the order shows -- the f32 sums of the normals and
@@ -541,14 +547,14 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			launches++;
 		}
 		if (gather) { // this rank's z-slab of the Level-1 normals -> rank 0 (copy engine; peers store into rank 0 only once it has entered the call)
-			GPV_CUDA(cudaStreamWaitEvent(st, c->evFork[1], 0));
+			GPV_CUDA(ev_wait(st, c->evFork[1]));
 			GPV_CUDA(cudaMemcpyAsync(c->gather.l1n + (size_t)oz0 * ncol * 3, c->l1Normal.as<unsigned char>() + (size_t)oz0 * ncol * 3, (size_t)(oz1 - oz0) * ncol * 3, cudaMemcpyDefault, st));
 		}
 	}
 	if (sink && sink->level1_normal && wantN) { // (the other Level-1 streams left from the side stream, right behind the fill sweep)
-		GPV_CUDA(cudaEventRecord(c->evChunk[kMaxChunks], st));
-		GPV_CUDA(cudaStreamWaitEvent(c->copyStream, c->evChunk[kMaxChunks], 0));
-		GPV_CUDA(cudaMemcpyAsync(sink->level1_normal, c->l1Normal.p, (size_t)cells * 3, cudaMemcpyDeviceToHost, c->copyStream));
+		GPV_CUDA(ev_record(c->evChunk[kMaxChunks], st));
+		GPV_CUDA(ev_wait(copy, c->evChunk[kMaxChunks]));
+		GPV_CUDA(cudaMemcpyAsync(sink->level1_normal, c->l1Normal.p, (size_t)cells * 3, cudaMemcpyDeviceToHost, copy));
 	}
 	L2IO lio{};
 	long long packedChunks = 0, packedPer = 0, packedCells = 0; // GPV_PACKED_L2: chunks of 2-bit words on their way to hPacked
@@ -608,7 +614,7 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		if (sink && sink->level2_inout) chunks = std::min<long long>(kMaxChunks, std::max<long long>(1, (nB * n23 + (24ll << 20) - 1) / (24ll << 20)));
 		if (packHost) chunks = std::min<long long>(kMaxChunks, std::max<long long>(1, (nB * n23 + (12ll << 20) - 1) / (12ll << 20))); // 3 MB on the bus, 12 MB for the host threads per chunk
 		// the cells this call refines: all boundary ranks, or (GPV_GATHER) this rank's share as listed, column by column, in colCellList
-		if (gather) GPV_CUDA(cudaStreamWaitEvent(st, c->evFork[1], 0)); // rank 0 has entered the call: its Level-2 buffer may be written
+		if (gather) GPV_CUDA(ev_wait(st, c->evFork[1])); // rank 0 has entered the call: its Level-2 buffer may be written
 		const bool byList = gather || own.world > 1;
 		const long long nRefine = byList ? (long long)T1.nLocalCells : nB;
 		lio.cellList = byList ? c->colCellList.as<int2>() : nullptr;
@@ -622,13 +628,13 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 			l2fn<<<(unsigned)((be - bb + G - 1) / G), kL2Threads, smem, st>>>(g, lio, K);
 			launches++;
 			if (sink && sink->level2_inout) {
-				GPV_CUDA(cudaEventRecord(c->evChunk[k], st));
-				GPV_CUDA(cudaStreamWaitEvent(c->copyStream, c->evChunk[k], 0));
+				GPV_CUDA(ev_record(c->evChunk[k], st));
+				GPV_CUDA(ev_wait(copy, c->evChunk[k]));
 				if (packHost) {
-					GPV_CUDA(cudaMemcpyAsync((char*)c->hPacked + bb * n23 / 4, c->l2Packed.as<uint8_t>() + bb * n23 / 4, (size_t)((be - bb) * n23 / 4), cudaMemcpyDeviceToHost, c->copyStream));
-					GPV_CUDA(cudaEventRecord(c->evCopied[k], c->copyStream));
+					GPV_CUDA(cudaMemcpyAsync((char*)c->hPacked + bb * n23 / 4, c->l2Packed.as<uint8_t>() + bb * n23 / 4, (size_t)((be - bb) * n23 / 4), cudaMemcpyDeviceToHost, copy));
+					GPV_CUDA(cudaEventRecord(c->evCopied[k], copy));
 				} else
-					GPV_CUDA(cudaMemcpyAsync(sink->level2_inout + bb * n23, c->l2State.as<uint8_t>() + bb * n23, (size_t)((be - bb) * n23), cudaMemcpyDeviceToHost, c->copyStream));
+					GPV_CUDA(cudaMemcpyAsync(sink->level2_inout + bb * n23, c->l2State.as<uint8_t>() + bb * n23, (size_t)((be - bb) * n23), cudaMemcpyDeviceToHost, copy));
 			}
 		}
 		if (packHost) { packedChunks = nChunks; packedPer = per; packedCells = nRefine; }
@@ -650,7 +656,7 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		lio.cellList = nullptr;
 		lio.bBegin = 0; lio.nBoundary = (int)nB;
 	}
-	GPV_CUDA(cudaStreamWaitEvent(st, c->evJoin[1], 0)); // the parity-fill branch joins
+	GPV_CUDA(ev_wait(st, c->evJoin[1])); // the parity-fill branch joins
 	if (gather) { // completion flag behind this rank's last store; the gathering rank returns when every rank has signalled
 		k_gather_done<<<1, 1, 0, st>>>(c->gather.mail, c->gather.rank, epoch, dT);
 		launches++;
@@ -684,7 +690,7 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		expand_pool_end(pool);
 	}
 	GPV_CUDA(cudaStreamSynchronize(st));
-	if (sink) GPV_CUDA(cudaStreamSynchronize(c->copyStream));
+	if (sink && !serial) GPV_CUDA(cudaStreamSynchronize(c->copyStream));
 	GPV_CUDA(cudaGetLastError());
 	const Totals T2 = *c->hTotals;
 	if (reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(c->hTotals) + 128)[2] > kRayOverflowCap)
