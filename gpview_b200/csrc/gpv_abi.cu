@@ -3,21 +3,23 @@
 // Pipeline of gpv_voxelize_device (what Object::PerformVoxelization, src/Object.cpp:3077-3430, does between
 // CreateFlatTriangleData and SaveVoxelization, re-designed for one B200):
 //
-//   k_clear                 every counter of the call
+//   k_clear                 the small counters of the call (cellCount and the (triangle, column) bitmaps clean up after themselves)
 //   k_prepare               48 B triangle / ray / plane records, footprints, work-item counts, centre tables
 //   k_scan_offs3            balanced work spaces of the two triangle-parallel sweeps (two scans, one launch)
-//   k_bin<count>            K1 count sweep: cellCount, colCount(over), l1Hits
-//   k_cross<count>          K2a count sweep: crossCount
-//   k_scan<CELLS>           K3: prefix, boundaryIndex, bTriOff, bmask, per-column boundary-cell counts, nBoundary, triTotal
+//   k_bin<count>            K1 count sweep: cellCount, colCount, l1Hits               | side stream: k_cross<count>  K2a crossCount
+//   k_scan<CELLS>           K3: prefix, boundaryIndex, bTriOff, bmask, per-column boundary-cell counts (of the columns this rank owns)
 //   k_scan_offs3            column-list, crossing-list and column-cell offsets (three scans, one launch)
+//   k_ray_units             work list of the Level-2 parity rays: (column, <= 16 of its boundary cells), expensive units first
 //   ---- one 128-byte read-back (sizes of the variable-length buffers) ----
-//   k_bin<fill>, k_cross<fill>
-//   k_sort_segments / k_sort_long x2   canonical ascending cell lists; sorted + de-duplicated column lists
-//   k_fill_sweep            K2b: final Level-1 bytes + inside count
-//   k_l1_normals            (GPV_NORMALS)
-//   k_col_cells, k_l2_rays  K4a: boundary cells by column, Level-2 parity bits per sub-voxel column
-//   k_l2<n2>                K4: Level-2 SAT + final bytes + counts
-//   k_l2_normals            (GPV_NORMALS)
+//   k_bin<fill>             cell lists, column lists                                  | side stream: k_cross<fill>, k_fill_sweep K2b (final
+//   k_sort_segments / k_sort_long   (GPV_NORMALS / GPV_KEEP_LISTS) canonical order    |   Level-1 bytes + inside count), Level-1 streams to the
+//   k_l1_normals            (GPV_NORMALS)                                             |   host / the gathering rank, k_clear_bits
+//   k_col_cells, k_l2_rays, k_l2_rays_overflow   K4a: boundary cells by column, Level-2 parity bits per sub-voxel column
+//   k_l2<n2, out>           K4: Level-2 SAT + counts + the blocks as file bytes / staged bytes / 2 bits per sub-voxel (chunked with a host sink)
+//   k_scatter_blocks, k_l2_normals   (GPV_NORMALS)
+//   k_gather_begin / done / wait_rank + k_gather_expand / wait   (GPV_GATHER) mailbox flags, rank 0 expands the peers' 2-bit blocks
+// A small model (<= 1 M cells) runs all of it on the caller's stream alone (no fork / join events: the driver calls bound a dataset run).
+// gpv_collision_boxes / gpv_build_hierarchy (gpv_collision.cuh) work on the streams the last call left on the device.
 #include "../../include/gpview_b200.h"
 #include "gpv_internal.h"
 #include "gpv_kernels.cuh"

@@ -11,10 +11,13 @@
 //   k_scan<MODE,V>  K3  single-pass decoupled-look-back scan: boundary prefix sum / index compaction / per-column cell counts;
 //   k_scan_offs3        up to three CSR offset scans per launch
 //   k_sort_segments, k_sort_long   canonical (ascending) order of every cell / column list; de-duplicates column lists
-//   k_col_cells, k_l2_rays  K4a Level-2 parity rays per sub-voxel column of each Level-1 column (certified cell masks)
-//   k_l2<N2,GATHER> K4  Level-2 SAT hoisted along z per sub-voxel column, three stages over shared-memory queues, final bytes
+//   k_ray_units, k_col_cells, k_l2_rays, k_l2_rays_overflow   K4a Level-2 parity rays per sub-voxel column of each Level-1 column
+//                   (certified cell masks), over a work list of (column, <= 16 boundary cells) units
+//   k_l2<N2,OUT>    K4  Level-2 SAT hoisted along z per sub-voxel column, three stages over shared-memory queues; blocks leave as file
+//                   bytes, staged bytes per cell, or 2 bits per sub-voxel (NVLink / PCIe)
 //   k_l1_normals, k_l2_normals   K5 normals in the reference's uchar encoding
-//   k_gather_*      multi-GPU: slab streams written into the gathering rank's buffers over NVLink peer memory (8-byte mailbox)
+//   k_gather_*, k_scatter_blocks   multi-GPU: every rank's share written into the gathering rank's buffers over NVLink peer memory
+//                   (mailbox flags; the peers' 2-bit Level-2 blocks expanded on rank 0)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
