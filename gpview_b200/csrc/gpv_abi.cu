@@ -67,7 +67,7 @@ struct gpv_ctx {
 	int device = 0;
 	int smCount = 0;
 	gpv::DevBuf tri48, ray48, tabX, tabY, tabZ, cellCount, colCount, crossCount, prefix, bmask, boundaryIndex, bTriOff, cellTris,
-	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, aabbxy16, longList, colCursor, binBits, colCellCnt, colCellOff, colCellList, l2Par, cellMid, rayOver, rayOverflow, l2Packed, solidWords, occCount, occOff, occInv, occCenter, occExtent, hierMid, hierHalf, hierSolid, hierChild;
+	    colOff, colTris, crossOff, crossTri, l1State, l2State, l1Normal, l2Normal, desc, totals, scratch, crossFp, binCnt, binOff, crossCnt, crossWorkOff, plane16, aabbxy16, longList, colCursor, binBits, colCellCnt, colCellOff, colCellList, l2Par, cellMid, rayOver, rayOverflow, l2Packed, peerCells, solidWords, occCount, occOff, occInv, occCenter, occExtent, hierMid, hierHalf, hierSolid, hierChild;
 	gpv::Totals* hTotals = nullptr; // pinned
 	cudaEvent_t ev[GPV_PHASE_COUNT + 1] = {}, evEnd[GPV_PHASE_COUNT + 1] = {};
 	bool haveEvents = false;
@@ -183,7 +183,7 @@ extern "C" void gpv_destroy(gpv_ctx* c)
 	cudaSetDevice(c->device);
 	DevBuf* all[] = { &c->tri48, &c->ray48, &c->tabX, &c->tabY, &c->tabZ, &c->cellCount, &c->colCount, &c->crossCount, &c->prefix, &c->bmask,
 		              &c->boundaryIndex, &c->bTriOff, &c->cellTris, &c->colOff, &c->colTris, &c->crossOff, &c->crossTri, &c->l1State, &c->l2State,
-		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->aabbxy16, &c->longList, &c->colCursor, &c->binBits, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->rayOver, &c->rayOverflow, &c->l2Packed, &c->solidWords, &c->occCount, &c->occOff, &c->occInv, &c->occCenter, &c->occExtent, &c->hierMid, &c->hierHalf, &c->hierSolid, &c->hierChild, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
+		              &c->l1Normal, &c->l2Normal, &c->desc, &c->totals, &c->scratch, &c->crossFp, &c->binCnt, &c->binOff, &c->crossCnt, &c->crossWorkOff, &c->plane16, &c->aabbxy16, &c->longList, &c->colCursor, &c->binBits, &c->colCellCnt, &c->colCellOff, &c->colCellList, &c->l2Par, &c->cellMid, &c->rayOver, &c->rayOverflow, &c->l2Packed, &c->peerCells, &c->solidWords, &c->occCount, &c->occOff, &c->occInv, &c->occCenter, &c->occExtent, &c->hierMid, &c->hierHalf, &c->hierSolid, &c->hierChild, &c->gatherL1, &c->gatherPrefix, &c->gatherL2, &c->gatherMail };
 	gpv_gather_detach(c);
 	for (DevBuf* b : all) b->release();
 	if (c->hTotals) cudaFreeHost(c->hTotals);
@@ -569,11 +569,11 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		lio.colCellOff = c->colCellOff.as<unsigned>(); lio.colCellList = c->colCellList.as<int2>(); lio.l2Par = c->l2Par.as<unsigned>(); lio.cellMid = c->cellMid.as<float4>();
 		const L2K K = l2_constants(g.n2);
 		const int G = K.G;
+		const bool canPack = (n23 % 32) == 0; // the blocks can travel as 2 bits per sub-voxel
 		const size_t smem = (size_t)K.total;
 		// how the blocks leave k_l2 (L2_OUT_*): file bytes into local HBM; or 2 bits per sub-voxel -- to the gathering rank over NVLink
 		// (peers of a GPV_GATHER call; rank 0 expands them after the wait) or into the staging buffer of the host call (GPV_PACKED_L2;
 		// host threads expand); or, when n2^3 is not a multiple of 32, staged bytes for the peers of a gathering call
-		const bool canPack = (n23 % 32) == 0;
 		const bool packHost = sink && sink->level2_inout && (prm->flags & GPV_PACKED_L2) && canPack;
 		const bool packPeer = gather && c->gather.rank != 0 && canPack;
 		// (a peer that also computes normals keeps its blocks: they are written locally and copied to rank 0 by k_scatter_blocks)
@@ -599,8 +599,13 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		lio.l2Packed = (packHost || (packPeer && peerLocal)) ? c->l2Packed.as<unsigned char>() : packPeer ? c->gather.l2p : nullptr;
 		if (smem > 48 * 1024) return fail("k_l2: shared-memory layout exceeds 48 KB"); // cannot happen for n2 <= 32 (41 KB)
 		// K4a: boundary cells grouped by Level-1 column, then the parity bits of every sub-voxel column, one walk of the column list per column
+		// gathering rank: the cells of every peer, for the peer-by-peer expansion of their 2-bit blocks (counters in the totals block: zeroed by k_clear)
+		const bool peerLists = gather && c->gather.rank == 0 && c->gather.world > 1 && canPack;
+		unsigned* peerCount = reinterpret_cast<unsigned*>(c->totals.as<char>() + 144);
+		if (peerLists && c->peerCells.ensure((size_t)c->gather.world * nB * 4 + 32)) return 1;
+		const PeerLists pl{ peerLists ? c->peerCells.as<int>() : nullptr, peerCount, nB };
 		k_col_cells<<<(unsigned)((nB + 255) / 256), 256, 0, st>>>(lio.boundaryIndex, (int)nB, (int)ncol, g.nx, cx, cy, cz, lio.colCellOff, c->colCellCnt.as<int>(), c->colCellList.as<int2>(),
-		                                                        c->cellMid.as<float4>(), lio.colCount, lio.bTriOff, own, dT);
+		                                                        c->cellMid.as<float4>(), lio.colCount, lio.bTriOff, own, pl, dT);
 		const long long nUnits = (long long)T1.nRayHeavy + T1.nRayLight;
 		RayWork rw{ c->rayOver.as<int2>(), rayCap, dT, { c->rayOverflow.as<int4>(), reinterpret_cast<unsigned*>(c->totals.as<char>() + 128) + 2, kRayOverflowCap } }; // (counter zeroed by k_clear)
 		if (nUnits > 0) {
@@ -664,11 +669,12 @@ static int voxelize_body(gpv_ctx* c, const float* d_tris, int64_t n_tri, const f
 		launches++;
 		if (c->gather.rank == 0) {
 			if (wantL2 && nB > 0 && c->gather.world > 1 && (n23 % 32) == 0) { // the peers sent 2 bits per sub-voxel: the file bytes of their blocks, peer by peer as they finish
-				const long long nWords = nB * n23 / 32;
+				const unsigned* peerCount = reinterpret_cast<const unsigned*>(c->totals.as<char>() + 144);
+				const long long perPeer = (nB / c->gather.world + 1) * (n23 / 32); // grid: about one thread per word of a peer's share
 				for (int q = 1; q < c->gather.world; q++) {
 					k_gather_wait_rank<<<1, 1, 0, st>>>(c->gather.mail, q, epoch, c->gather.timeoutNs, dT);
-					k_gather_expand<<<(unsigned)std::min<long long>(c->smCount * 8, (nWords + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint2*>(c->gather.l2p), c->gather.l2, nWords, (int)(n23 / 32),
-					                                                                                                       c->boundaryIndex.as<int>(), (int)ncol, own, q);
+					k_gather_expand<<<(unsigned)std::min<long long>(c->smCount * 8, (perPeer + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint2*>(c->gather.l2p), c->gather.l2, (int)(n23 / 32),
+					                                                                                                        c->peerCells.as<int>() + (size_t)q * nB, peerCount + q);
 					launches += 2;
 				}
 			}
@@ -899,13 +905,13 @@ extern "C" int gpv_collision_boxes(gpv_ctx* c, void* stream, gpv_collision* out)
 	const size_t dsz = desc_bytes(nBlocks);
 	if (c->occCount.ensure((size_t)nBlocks * 4 + 32) || c->occOff.ensure((size_t)(nBlocks + 1) * 4 + 32) || c->desc.ensure(dsz + 32)) return 1;
 	GPV_CUDA(cudaMemsetAsync(c->desc.p, 0, dsz, st));
-	GPV_CUDA(cudaMemsetAsync(c->totals.as<char>() + 192, 0, 8, st));
+	GPV_CUDA(cudaMemsetAsync(c->totals.as<char>() + 208, 0, 8, st));
 	k_occupied_count<<<(unsigned)nBlocks, 256, 0, st>>>(c->l1State.as<unsigned char>(), cells, c->occCount.as<int>());
 	int64_t launches = 0;
-	const ScanReq r[1] = { { c->occCount.as<int>(), nBlocks, c->occOff.as<unsigned>(), reinterpret_cast<unsigned*>(c->totals.as<char>() + 192), nullptr, 0 } };
+	const ScanReq r[1] = { { c->occCount.as<int>(), nBlocks, c->occOff.as<unsigned>(), reinterpret_cast<unsigned*>(c->totals.as<char>() + 208), nullptr, 0 } };
 	launch_scans(c, st, r, 1, launches);
 	unsigned n = 0;
-	GPV_CUDA(cudaMemcpyAsync(&n, c->totals.as<char>() + 192, 4, cudaMemcpyDeviceToHost, st));
+	GPV_CUDA(cudaMemcpyAsync(&n, c->totals.as<char>() + 208, 4, cudaMemcpyDeviceToHost, st));
 	GPV_CUDA(cudaStreamSynchronize(st));
 	if (c->occInv.ensure((size_t)n * 4 + 32) || c->occCenter.ensure((size_t)n * 12 + 32) || c->occExtent.ensure((size_t)n * 12 + 32)) return 1;
 	if (n) k_occupied_write<<<(unsigned)nBlocks, 256, 0, st>>>(c->l1State.as<unsigned char>(), cells, c->occOff.as<unsigned>(), g.nx, g.ny, c->tabX.as<float>(), c->tabY.as<float>(),

@@ -781,9 +781,13 @@ __device__ __forceinline__ int fast_div(int a, float inv) { return __float2int_r
 // Boundary cells grouped by Level-1 column: slot by atomic decrement of the per-column count (left at 0; order inside a
 // column is irrelevant, every cell is refined independently).  Entry = (slab-local boundary rank, centre height of the cell).
 // Also the centre of every boundary cell by rank, so that k_l2 does not decode linear indices.
+// GPV_GATHER, gathering rank only: the boundary ranks of the cells every PEER refines (list[q * cap + i], i < count[q]), so that the
+// peers' 2-bit blocks can be expanded peer by peer as they finish without scanning the whole grid once per peer.
+struct PeerLists { int* list; unsigned* count; long long cap; };
+
 __global__ void k_col_cells(const int* __restrict__ boundaryIndex, int nBoundary, int plane, int nx, const float* __restrict__ cx, const float* __restrict__ cy,
                             const float* __restrict__ cz, const unsigned* __restrict__ colCellOff, int* colCellCnt, int2* colCellList, float4* cellMid,
-                            const int* __restrict__ colCount, const unsigned* __restrict__ bTriOff, Own own, Totals* totals)
+                            const int* __restrict__ colCount, const unsigned* __restrict__ bTriOff, Own own, PeerLists peers, Totals* totals)
 {
 	const int b = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned long long pairs = 0, tris = 0;
@@ -793,6 +797,7 @@ __global__ void k_col_cells(const int* __restrict__ boundaryIndex, int nBoundary
 		l1 = boundaryIndex[b]; kz = l1 / plane; col = l1 - kz * plane;
 		mine = own((unsigned)col);
 		if (mine) { pairs = (unsigned long long)colCount[col]; tris = bTriOff[b + 1] - bTriOff[b]; }
+		else if (peers.list) { const int q = own.owner((unsigned)col); peers.list[(long long)q * peers.cap + atomicAdd(peers.count + q, 1u)] = b; }
 	}
 	pairs = warp_sum(pairs); tris = warp_sum(tris);
 	if ((threadIdx.x & 31) == 0 && (pairs | tris)) { atomicAdd(&totals->l2ColPairs, pairs); atomicAdd(&totals->l2LocalTris, tris); }
@@ -1491,8 +1496,9 @@ __global__ void k_gather_done(GatherMail* mail, int rank, unsigned epoch, const 
 
 // Gathering rank: the peers sent their Level-2 blocks as 2 bits per sub-voxel (L2_OUT_PACKED); these two turn them into the file
 // bytes, peer by peer: a one-thread kernel waits for rank q's completion flag, then k_gather_expand expands the blocks of the
-// columns rank q owns (one thread per 32 sub-voxels: a uint2 in, two 128-bit stores out) -- the blocks of the ranks that finish
-// early are expanded while the later ones are still computing.  (A single resident grid whose threads spin on the flags was tried
+// cells rank q refined (listed per peer by k_col_cells; one thread per 32 sub-voxels: a uint2 in, two 128-bit stores out) -- the
+// blocks of the ranks that finish early are expanded while the later ones are still computing.  (Filtering the whole grid by owner
+// once per peer instead cost 47 us per peer: 0.33 ms of waiting and scanning on rank 0 at 8 ranks.)  (A single resident grid whose threads spin on the flags was tried
 // and dropped: with several ranks on ONE device, as in the tests, the spinning grid starves the ranks it waits for.)
 __global__ void k_gather_wait_rank(GatherMail* mail, int q, unsigned epoch, unsigned long long timeoutNs, Totals* totals)
 {
@@ -1501,11 +1507,13 @@ __global__ void k_gather_wait_rank(GatherMail* mail, int q, unsigned epoch, unsi
 		if (global_ns() - t0 > timeoutNs) { totals->gatherError = 2; return; }
 }
 
-__global__ void __launch_bounds__(256) k_gather_expand(const uint2* __restrict__ packed, unsigned char* __restrict__ bytes, long long nWords, int wordsPerCell,
-                                                        const int* __restrict__ boundaryIndex, int plane, Own own, int q)
+__global__ void __launch_bounds__(256) k_gather_expand(const uint2* __restrict__ packed, unsigned char* __restrict__ bytes, int wordsPerCell, const int* __restrict__ cells,
+                                                        const unsigned* __restrict__ nCells)
 {
-	for (long long w = (long long)blockIdx.x * 256 + threadIdx.x; w < nWords; w += (long long)gridDim.x * 256) {
-		if (own.owner((unsigned)(boundaryIndex[w / wordsPerCell] % plane)) != q) continue;
+	const long long nWords = (long long)*nCells * wordsPerCell; // the blocks rank q refined (k_col_cells listed them)
+	for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nWords; i += (long long)gridDim.x * 256) {
+		const long long c = i / wordsPerCell;
+		const long long w = (long long)cells[c] * wordsPerCell + (i - c * wordsPerCell);
 		const uint2 m = __ldcg(packed + w); // (written by a peer over NVLink: not through the read-only path)
 		unsigned o[8];
 #pragma unroll
