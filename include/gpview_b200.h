@@ -183,13 +183,16 @@ int gpv_voxelize_host(gpv_ctx* ctx, const gpv_mesh* mesh, const gpv_params* para
 
 /* ---- multi-GPU gather over NVLink peer memory (one process per GPU, one ctx per process).
  * The gathering rank (rank 0) allocates the whole-grid streams once and exports them as CUDA IPC handles; every other rank maps
- * them (peer access over NVLink / NVSwitch).  A call with GPV_GATHER then writes its share of the streams directly at their
- * final offsets in rank 0's memory from inside the kernels that produce them -- there is no separate collective and NO exchange
- * step on the data path: every rank runs Level 1 over the whole grid (the parity rays need whole column lists, cu:461-463), so
- * boundary ranks and prefix sums are global on every rank.  Shared out are
- *   - the Level1InOut bytes and prefix sums by z-slab: [z0,z1) of gpv_params, or an equal share of the layers when z1 <= 0;
- *   - the Level-2 refinement by Level-1 column: groups of max(1, 256/n2^2) consecutive columns are dealt to the ranks round-robin,
- *     so that every column list is walked by exactly one rank and neighbouring columns (similar cost) land on different ranks.
+ * them (peer access over NVLink / NVSwitch).  A call with GPV_GATHER then delivers its share of the streams directly at their
+ * final offsets in rank 0's memory -- there is no separate collective and NO exchange step on the data path: every rank runs
+ * Level 1 over the whole grid (the parity rays need whole column lists, cu:461-463), so boundary ranks and prefix sums are
+ * global on every rank.  Shared out are
+ *   - the Level1InOut bytes and prefix sums by z-slab: [z0,z1) of gpv_params, or an equal share of the layers when z1 <= 0; the
+ *     two contiguous ranges leave by the copy engines beside the Level-2 kernels;
+ *   - the Level-2 refinement by Level-1 column: groups of max(1, 256/n2^2) consecutive columns are dealt to the ranks round-robin
+ *     (skewed by the grid row), so that every column list is walked by exactly one rank and neighbouring columns (similar cost)
+ *     land on different ranks.  A peer's blocks are stored from inside k_l2 as 2 bits per sub-voxel (n2 a multiple of 4; file bytes
+ *     otherwise) and expanded into Level2InOut bytes on rank 0, peer by peer as they finish.
  * Completion flags and the ranks' shares of the counts travel through a mailbox in rank 0's memory (one-thread kernels on the
  * callers' streams); rank 0's call returns once every rank has signalled, with the whole grid's counts in its gpv_result (the
  * other ranks report their own share).  All ranks must issue their GPV_GATHER calls in the same order; a rank's call does not

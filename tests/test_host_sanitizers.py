@@ -91,3 +91,22 @@ def test_voxel_file_reader_under_sanitizers(driver, oracle, tmp_path_factory, tm
         (d / "Obj5VoxelConfig.txt").write_bytes(bytes(a))
     ok, refused = _run(driver, "voxels", str(tmp_path), str(n))
     assert ok >= 1 and refused > 50, (ok, refused)
+
+
+@pytest.mark.parametrize("sanitizer", ["thread", "address,undefined"])
+def test_expand_pool_under_sanitizers(tmp_path, sanitizer):
+    """The host-thread pool of the 2-bit Level-2 transfer (gpv_expand.cpp) driven like gpv_voxelize_host drives it -- begin, chunks
+    trickling in, end -- 2 x 40 calls from two client threads, every output byte checked: no data race (TSan), no stray write
+    (ASan), same bytes as the definition (tests/cpu_probe/expand_probe.cpp)."""
+    out = str(tmp_path / "expand_probe")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++17", "-O1", "-g", "-fsanitize=" + sanitizer, "-fno-omit-frame-pointer", "-pthread", "-o", out,
+           os.path.join(ROOT, "tests", "cpu_probe", "expand_probe.cpp"), os.path.join(ROOT, "gpview_b200", "csrc", "gpv_expand.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and ("tsan" in r.stderr or "asan" in r.stderr or "sanitize" in r.stderr):
+        pytest.skip("this toolchain has no sanitizer runtime")
+    assert r.returncode == 0, r.stderr[-2000:]
+    env = dict(os.environ, GPV_HOST_THREADS="5", ASAN_OPTIONS="detect_leaks=0", TSAN_OPTIONS="halt_on_error=1")   # (the pool lives as long as the process: not a leak)
+    r = subprocess.run([out, "40"], capture_output=True, text=True, env=env, timeout=900)
+    text = r.stdout + r.stderr
+    assert r.returncode == 0 and "ok" in r.stdout and "Sanitizer" not in text and "runtime error" not in text, text[-3000:]
