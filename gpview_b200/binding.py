@@ -76,7 +76,7 @@ class CBatchStats(C.Structure):
 NATIVE_SYMBOLS = ["gpv_last_error", "gpv_device_count", "gpv_create", "gpv_destroy", "gpv_stream", "gpv_load_obj", "gpv_load_off", "gpv_load_mesh", "gpv_load_mesh_ex",
                   "gpv_mesh_from_triangles", "gpv_free_mesh", "gpv_make_grid", "gpv_alloc_host", "gpv_free_host", "gpv_alloc_device",
                   "gpv_free_device", "gpv_memcpy_h2d", "gpv_memcpy_d2h", "gpv_stream_sync", "gpv_voxelize_device", "gpv_voxelize_host",
-                  "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_check_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_expand_packed_l2", "gpv_collision_boxes", "gpv_build_hierarchy", "gpv_voxelize_batch", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
+                  "gpv_save", "gpv_save_streams", "gpv_load_voxels", "gpv_check_voxels", "gpv_free_voxels", "gpv_expand_dense", "gpv_expand_packed_l2", "gpv_collision_boxes", "gpv_build_hierarchy", "gpv_voxelize_batch", "gpv_batch_release", "gpv_measure_fp32_peak", "gpv_measure_copy_peak",
                   "gpv_gather_create", "gpv_gather_create_ex", "gpv_gather_normals", "gpv_gather_attach", "gpv_gather_attach_local", "gpv_gather_detach", "gpv_gather_set_timeout", "gpv_gather_result"]
 COMPAT_SYMBOLS = ["CUDAClassifyTessellation", "CUDAClassifyTessellationLevel2", "CUDAClassifyInOutLevel2", "THRUSTDeviceFindMax"]
 
@@ -123,6 +123,7 @@ def lib():
         L.gpv_expand_packed_l2.argtypes = [vp, C.c_int64, vp]
         L.gpv_collision_boxes.argtypes = [vp, vp, C.POINTER(CCollision)]
         L.gpv_build_hierarchy.argtypes = [vp, vp, C.POINTER(CHierarchy)]
+        L.gpv_batch_release.argtypes = []; L.gpv_batch_release.restype = None
         L.gpv_measure_fp32_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         L.gpv_measure_copy_peak.argtypes = [vp, vp, C.POINTER(C.c_double)]
         L.gpv_gather_create.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(CGatherDesc)]

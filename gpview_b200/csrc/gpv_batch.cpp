@@ -18,6 +18,29 @@
 #include <vector>
 
 namespace {
+// Contexts are expensive to make (streams, events, ~50 pooled device buffers that grow with the first models) and cheap to keep:
+// a worker takes an idle context of its device from this cache and hands it back when the batch is done, so that the second batch
+// of a process -- and every later one -- starts with warm pools.  gpv_batch_release() frees them.
+struct CtxCache {
+	std::mutex mu;
+	std::vector<std::pair<int, gpv_ctx*>> idle;
+	gpv_ctx* take(int device)
+	{
+		std::lock_guard<std::mutex> g(mu);
+		for (size_t k = 0; k < idle.size(); k++)
+			if (idle[k].first == device) { gpv_ctx* c = idle[k].second; idle.erase(idle.begin() + (long)k); return c; }
+		return nullptr;
+	}
+	void give(int device, gpv_ctx* c) { std::lock_guard<std::mutex> g(mu); idle.emplace_back(device, c); }
+	void clear()
+	{
+		std::lock_guard<std::mutex> g(mu);
+		for (auto& e : idle) gpv_destroy(e.second);
+		idle.clear();
+	}
+};
+CtxCache& ctx_cache() { static CtxCache c; return c; }
+
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Pinned {
@@ -37,8 +60,9 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
 	double tParse = 0, tGpu = 0, tSave = 0;
 	const double t0 = now();
 	auto worker = [&](int w) {
-		gpv_ctx* ctx = nullptr;
-		if (gpv_create(devices[w % n_devices], &ctx)) { std::lock_guard<std::mutex> g(errMu); if (firstErr.empty()) firstErr = gpv_last_error(); return; }
+		const int device = devices[w % n_devices];
+		gpv_ctx* ctx = ctx_cache().take(device);
+		if (!ctx && gpv_create(device, &ctx)) { std::lock_guard<std::mutex> g(errMu); if (firstErr.empty()) firstErr = gpv_last_error(); return; }
 		Pinned l1, pre, bi, l2, n1, n2;
 		double parse = 0, gpu = 0, save = 0;
 		const bool wantN = (params->flags & GPV_NORMALS) != 0, wantL2 = !(params->flags & GPV_NO_LEVEL2) && params->voxel_count2 > 0;
@@ -84,7 +108,7 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
 			if (!ok) bail(); else done++;
 			gpv_free_mesh(&mesh);
 		}
-		gpv_destroy(ctx);
+		ctx_cache().give(device, ctx);
 		std::lock_guard<std::mutex> g(errMu);
 		tParse += parse; tGpu += gpu; tSave += save;
 	};
@@ -98,3 +122,5 @@ extern "C" int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, con
 	if (failed > 0 || (done == 0 && skipped == 0)) return gpv::fail(firstErr.empty() ? "gpv_voxelize_batch: no model processed" : firstErr);
 	return 0;
 }
+
+extern "C" void gpv_batch_release(void) { ctx_cache().clear(); }

@@ -149,6 +149,7 @@ ExpandPool* expand_pool_get()
 		int n = (int)std::thread::hardware_concurrency();
 		if (const char* e = getenv("GPV_HOST_THREADS")) n = atoi(e) + 1;
 		n = n > 1 ? n - 1 : 1;                 // the calling thread keeps a core for the CUDA events it waits on
+		if (!getenv("GPV_HOST_THREADS") && n > 15) n = 15; // streaming stores saturate the memory channels well before 32 cores do; more spinners only get in the way
 		if (n > 63) n = 63;
 		return new ExpandPool(n);             // lives as long as the process (worker threads sleep between calls)
 	}();

@@ -284,6 +284,8 @@ typedef struct {
 } gpv_batch_stats;
 int gpv_voxelize_batch(const char* const* paths, int64_t n_paths, const gpv_params* params, const int* devices, int n_devices, int threads,
                        const char* out_dir, int first_obj_id, int skip_existing, gpv_batch_stats* stats);
+/* The workers' contexts (streams, pooled device buffers) are kept for the next gpv_voxelize_batch call of the process; this frees them. */
+void gpv_batch_release(void);
 
 /* micro-benchmarks used for the roofline denominators (bench.py): achieved non-FMA FP32 lane-ops/s and copy GB/s */
 int gpv_measure_fp32_peak(gpv_ctx* ctx, void* stream, double* ops_per_s);
