@@ -30,6 +30,21 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("cessna Level1 64 + Level2 4^3")
+    # the workload description carries the same keys and numbers as the GPU arm's (derived there from the reference's own structures)
+    assert set(line["config"]) == {"workload", "l1", "l2", "mesh", "cache", "tri_box_tests_per_model", "triangles", "grid"}
+    if line["cpu_baseline"]["kind"] == "reference":
+        assert line["config"]["tri_box_tests_per_model"] == 38439 + 1668608 and line["config"]["triangles"] == 7446 and line["config"]["grid"] == [60, 16, 64]
+        assert "whole CPU path" in line["cpu_baseline"]["sample"] and line["ray_tests_per_step"] > 0
+        c1 = line["c1"]                                    # BASELINE.json configs[0]: cessna Level-1 64, brute-force fill + ClassifyTessellation
+        assert c1["fill_ray_tests"] == 60 * 16 * 64 * 7446 and c1["tri_box_tests"] == 38439 and c1["ms_per_model"] > 0
+
+
+def test_batch_reference_arm_prints_models_per_second():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--batch", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "models/s" and line["value"] > 0 and line["scaling"] == "weak"
+    assert line["config"]["l1"] == 64 and line["config"]["l2"] == 4 and "configs[4]" in line["config"]["workload"]
 
 
 def test_reference_arm_is_silent_on_other_ranks():
