@@ -364,6 +364,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:  # e2e leg: every rank expands its own slab's 2-bit Level-2 transfer; share the host cores instead of 15 spinning threads per rank
+        os.environ.setdefault("GPV_HOST_THREADS", str(max(2, (os.cpu_count() or 8) // world - 1)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- libgpview_b200 has no CPU fallback")
     torch.cuda.set_device(local)
