@@ -620,7 +620,7 @@ def main():
         dist.all_reduce(dsum)
     e2e = {"value": tests / (e2e_ms * 1e-3) / 1e9, "unit": "G tri-box tests/s", "ms_per_model": e2e_ms,
            "h2d_bytes_per_step": mesh.ntri * 36 * world, "d2h_bytes_per_step": int(dsum.item()),
-           "level2_transfer": "2 bits per sub-voxel over PCIe, expanded into the caller's bytes by %d host threads (GPV_PACKED_L2)" % ((os.cpu_count() or 2) - 1) if packed_wins else "file bytes by DMA",
+           "level2_transfer": "2 bits per sub-voxel over PCIe, expanded into the caller's bytes by %d host threads per rank (GPV_PACKED_L2)" % int(os.environ.get("GPV_HOST_THREADS", min(15, max(1, (os.cpu_count() or 2) - 1)))) if packed_wins else "file bytes by DMA",
            "ms_per_model_level2_as_bytes": e2e_bytes_ms, "ms_per_model_level2_packed": e2e_packed_ms,
            "timing": "host wall clock around gpv_voxelize_host, max over ranks (pinned buffers both ways; Level-2 D2H overlaps the refinement; "
                      "the call returns after the last byte has landed)"}
