@@ -14,6 +14,15 @@ is sharded, so cuts are balanced by the Level-2 cost per z-layer, not by layer c
 import numpy as np
 
 
+def column_owner(col, world, n2, nx):
+    """Which rank of a GPV_GATHER call refines Level-1 column `col` (numpy arrays welcome): the host-side statement of `struct Own`
+    in gpv_kernels.cuh.  Columns are dealt out in groups of max(1, 256 // n2**2) consecutive columns, group k of grid row j to rank
+    (k + j) % world -- neighbouring columns cost about the same, so this balances the Level-2 work without a cost model, and the skew
+    by the row keeps walls along x or y from landing on one rank."""
+    group = max(1, 256 // (n2 * n2))
+    return (col // group + col // nx) % world
+
+
 def plan_slabs(cost_per_layer, world):
     """Cut nz layers into `world` contiguous non-empty slabs of ~equal cost.  Deterministic: every rank computes the same
     cuts from the same replicated Level-1 pre-pass, no communication needed.  Returns world+1 cut positions."""

@@ -97,3 +97,37 @@ def test_rebalance_converges_on_a_skewed_cost():
         assert cuts[0] == 0 and cuts[-1] == nz and all(b > a for a, b in zip(cuts, cuts[1:]))
     t = np.array([true[cuts[r]:cuts[r + 1]].sum() for r in range(world)])
     assert t.max() < 1.25 * t.mean(), (cuts, t)
+
+
+def test_column_ownership_balances_level2_and_matches_the_measured_shares():
+    """GPV_GATHER shares the Level-2 refinement out by Level-1 column (struct Own in gpv_kernels.cuh; sharded.column_owner is its
+    host-side statement).  On the headline model (fixture boundary cells of cessna 256/16): every column has exactly one owner, the
+    ranks' shares of boundary cells and of (cell, triangle) pairs -- the two things Level 2 costs -- stay within a few percent of equal
+    at 2 / 4 / 8 ranks, and the cell counts are the ones the ranks of the committed 4- and 8-GPU runs reported."""
+    import json
+    import os
+    import numpy as np
+    from gpview_b200 import sharded
+    from util import ROOT, golden
+    info, z = golden("cessna_256_16")
+    nx, ny, nz = info["num_div"]
+    col = z["boundary_index"].astype(np.int64) % (nx * ny)
+    tris = z["tri_count_boundary"].astype(np.int64)
+    allcols = np.arange(nx * ny)
+    for world in (2, 4, 8):
+        own_all = sharded.column_owner(allcols, world, 16, nx)
+        assert own_all.min() == 0 and own_all.max() == world - 1
+        assert np.bincount(own_all, minlength=world).max() - np.bincount(own_all, minlength=world).min() <= ny      # columns: equal up to row ends
+        own = sharded.column_owner(col, world, 16, nx)
+        cells = np.bincount(own, minlength=world)
+        pairs = np.bincount(own, weights=tris, minlength=world)
+        assert cells.sum() == info["l1_boundary"]
+        assert cells.max() <= 1.03 * cells.mean() and pairs.max() <= 1.06 * pairs.mean(), (world, cells, pairs)
+        line = os.path.join(ROOT, "profiles", "r02_scale_n%d.json" % world)
+        if os.path.exists(line):   # the ranks' own reports of that run (bench.py: phase_ms_per_rank[r].l2_cells)
+            got = [r["l2_cells"] for r in json.loads(open(line).read().strip().splitlines()[-1])["phase_ms_per_rank"]]
+            assert got == [int(c) for c in cells], (world, got, cells)
+    # groups of 256 / n2^2 columns for smaller n2; one rank owns everything at world 1
+    assert sharded.column_owner(allcols, 1, 16, nx).max() == 0
+    g4 = sharded.column_owner(allcols, 4, 4, nx)
+    assert all(len(set(g4[k:k + 16])) == 1 for k in range(0, 16 * 10, 16))
