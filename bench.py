@@ -1,22 +1,28 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the voxelizer hot path (BASELINE.json: cessna Level-1 256 + Level-2 16^3).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--l1 256 --l2 16 --mesh cessna|sphere|torus|cad]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--l1 256 --l2 16 --mesh cessna|sphere|torus|cad] [--normals] [--batch M]
 
 One "step" = one full voxelization of the model (Level-1 SAT binning, parity fill, boundary compaction, Level-2
-refinement), triangles resident in HBM when the timed region starts, outputs resident in HBM when it ends (N > 1: gathered
-on rank 0 over NCCL).  Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+refinement), triangles resident in HBM when the timed region starts, outputs resident in HBM when it ends (N > 1: on rank 0,
+as file bytes).  Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   roofline      dominant kernel (k_l2): algorithmic tri-box FLOPs (124 per reference-equivalent test) over
                 its CUDA-event time (events recorded around the kernel on the launching stream, inside the timed steps),
-                against the non-FMA FP32 issue rate measured live by gpv_measure_fp32_peak
+                against the non-FMA FP32 issue rate measured live by gpv_measure_fp32_peak; beside the algorithmic `frac` the
+                utilisation figures `frac_executed` / `frac_issue_slots` from the committed ncu capture of the same command
+                (profiles/traffic.json, quoted only while the kernel sources hash to what it was captured from)
   roofline_hbm  the same launch's output bytes against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the reference's own TriBoxOverlap object code (oracle/_ref) -- or the oracle port when _ref is absent --
-                inside the Level-2 loop nest on a bounded sample of boundary cells, all host threads (rank 0, N = 1)
-  e2e           the same metric through gpv_voxelize_host: pinned HOST triangles in, HOST streams out, copies timed.
+  cpu_baseline  the reference's own object code (oracle/_ref) -- or the oracle port when _ref is absent -- through the WHOLE CPU
+                path (Level-1 tri-box loop, column lists, column-list fill, Level-2 rays + SAT) on a bounded sample of boundary
+                cells, all host threads (rank 0, N = 1); --impl reference prints the same as its own line, plus configs[0] (`c1`)
+  e2e           the same metric through gpv_voxelize_host: pinned HOST triangles in, HOST streams out, copies timed -- Level 2
+                over PCIe as bytes and as 2 bits per sub-voxel expanded by the library's host threads; the faster is the headline.
                 N > 1: every rank delivers the byte range of its z-slab to its own pinned host buffer over its own PCIe
                 link (ranges are disjoint and ordered, prefix sums made global with the all-gathered boundary counts)
-N > 1 (torchrun): the grid is cut into z-slabs balanced by Level-2 cost, one rank per GPU; the Level-1 passes are
-replicated (cheap), Level-2 is sharded.
+N > 1 (torchrun), GPV_GATHER: Level 1 is replicated (every rank needs whole column lists); every rank delivers a z-slab of the
+Level-1 bytes / prefix sums and the Level-2 blocks of the Level-1 columns it owns (interleaved groups) straight into rank 0's
+buffers over NVLink peer memory -- no collective; --gather nccl: the NCCL send/recv gather of cost-balanced z-slabs it replaces.
+--batch M: BASELINE.json configs[4], models/s through gpv_voxelize_batch (one rank per GPU, no collective).
 """
 import argparse
 import ctypes as C

@@ -1,5 +1,9 @@
 """z-slab sharding of one voxelization over the GPUs of a box -- torch.distributed plumbing only.
 
+(The recommended multi-GPU path is GPV_GATHER in the C ABI -- DESIGN.md 7: no collective, Level-2 shared out by Level-1 column,
+`column_owner` below is its ownership rule.  What follows is the NCCL send/recv gather of z-slabs it is measured against, and the
+slab plan the end-to-end leg of bench.py uses.)
+
 The linear cell index is z-major (idx = r*ny*nx + q*nx + p, cuda/CUDAClassifyTessellation.cu:393), so a slab [z0,z1) owns a
 contiguous byte range of Level1InOut / Level1BoundaryPrefixSum, and -- boundary cells being numbered in ascending index
 order -- a contiguous range of the Level-2 blocks.  Sharding is therefore: pick cuts, run the C ABI on each slab
