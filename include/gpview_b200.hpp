@@ -1,7 +1,8 @@
 // include/gpview_b200.hpp -- header-only C++ facade over the C ABI, shaped like the reference's Object / GLParameters so that
 // GPView-style callers port by recompiling (SURVEY.md 8b tier 3).  Same member names and argument meaning:
 //   Object::ReadObject / ReadOFFObject (src/Object.cpp:395, :171), CreateFlatTriangleData (:3496), PerformVoxelization (:3077),
-//   SaveVoxelization (:2934); GLParameters::voxelCount / voxelCount2 / level2Voxels / saveVoxels (src/GLParameters.cpp:28-69).
+//   SaveVoxelization (:2934), BuildHierarchy (:2790), CollisionInitCUDA (:3530); GLParameters::voxelCount / voxelCount2 / level2Voxels /
+//   saveVoxels (src/GLParameters.cpp:28-69).
 // Error behaviour: the reference abort()s on file errors and only prints CUDA errors; the facade throws gpview::Error.
 #pragma once
 #include "gpview_b200.h"
@@ -21,7 +22,14 @@ struct GLParameters {            // the voxelizer-relevant subset of the referen
 	bool level2Voxels = true;
 	bool saveVoxels = true;
 	bool normals = true;         // the reference always computes normals
+	bool packedTransfer = true;  // Level2InOut crosses PCIe as 2 bits per sub-voxel, expanded by host threads (GPV_PACKED_L2): same bytes, a quarter of the transfer
+	bool collision = false;      // keep what BuildHierarchy needs (the parity fill of the boundary cells, GPV_COLLISION)
 	int device = 0;
+};
+
+struct BBoxData {                // one box of the hierarchy: the reference's BBoxData without the per-cell triangle vectors (includes/Utilities.h:57-78)
+	float midPoint[3], halfSize[3];
+	int solid, childIndex1, childIndex2, index;
 };
 
 struct VoxelData {               // host copies of the streams, file encoding
@@ -30,6 +38,13 @@ struct VoxelData {               // host copies of the streams, file encoding (S
 	int64_t numLevel1InsideVoxels = 0, numLevel1BoundaryVoxels = 0, numLevel2InsideVoxels = 0, numLevel2BoundaryVoxels = 0;
 	std::vector<uint8_t> level1InOut, level1Normal, level2InOut, level2Normal;
 	std::vector<int32_t> boundaryPrefixSum, boundaryIndex;
+	// Object::CollisionInitCUDA: occupied cells (ascending) and their boxes; the two arrays stay on the device like the reference's
+	std::vector<int> invIndex;
+	const float* boxCenterCUDAData = nullptr; const float* boxExtentCUDAData = nullptr;
+	bool collisionInit = false;
+	// Object::BuildHierarchy
+	int numLevels = 0;
+	std::vector<BBoxData> bBoxHierarchy;
 	gpv_result result{};
 };
 
@@ -56,7 +71,8 @@ public:
 	void PerformVoxelization(const GLParameters* glParam, int /*bufferSize*/ = -1)
 	{
 		if (!ctx_) check(gpv_create(glParam->device, &ctx_));
-		gpv_params p{ glParam->voxelCount, glParam->voxelCount2, (glParam->normals ? GPV_NORMALS : 0) | (glParam->level2Voxels ? 0 : GPV_NO_LEVEL2), 0, 0 };
+		gpv_params p{ glParam->voxelCount, glParam->voxelCount2, (glParam->normals ? GPV_NORMALS : 0) | (glParam->level2Voxels ? 0 : GPV_NO_LEVEL2) |
+			                                                  (glParam->packedTransfer ? GPV_PACKED_L2 : 0) | (glParam->collision ? GPV_COLLISION : 0), 0, 0 };
 		gpv_grid g;
 		check(gpv_make_grid(mesh_.bbox_min, mesh_.bbox_max, mesh_.max_model_size, p.voxel_count, glParam->level2Voxels ? p.voxel_count2 : 1, &g));
 		VoxelData& v = voxelData;
@@ -64,7 +80,7 @@ public:
 		v.level1InOut.resize(cells); v.boundaryPrefixSum.resize(cells);
 		if (glParam->normals) v.level1Normal.resize(cells * 3);
 		// Level-2 sizes are only known after the Level-1 pass: run Level 1 alone first, then the full call into exact buffers
-		gpv_params p1 = p; p1.flags |= GPV_NO_LEVEL2; p1.flags &= ~GPV_NORMALS;
+		gpv_params p1 = p; p1.flags |= GPV_NO_LEVEL2; p1.flags &= ~(GPV_NORMALS | GPV_COLLISION);
 		gpv_host_streams none{};
 		check(gpv_voxelize_host(ctx_, &mesh_, &p1, nullptr, &v.result, &none));
 		const size_t nb = (size_t)v.result.n_boundary, n23 = (size_t)g.n2 * g.n2 * g.n2;
@@ -82,6 +98,42 @@ public:
 		v.numLevel2InsideVoxels = v.result.l2_inside; v.numLevel2BoundaryVoxels = v.result.l2_boundary;
 		voxelInit = true;
 		if (glParam->saveVoxels) SaveVoxelization(glParam);
+	}
+
+	// Object::CollisionInitCUDA (src/Object.cpp:3530-3572): the occupied cells of the last voxelization as an inverse index (host) and box
+	// centre / extent arrays (device, owned by the library, valid until the next voxelization of this object)
+	void CollisionInitCUDA(const GLParameters*)
+	{
+		if (!voxelInit) throw Error("CollisionInitCUDA before PerformVoxelization");
+		gpv_collision c;
+		check(gpv_collision_boxes(ctx_, nullptr, &c));
+		voxelData.invIndex.resize((size_t)c.count);
+		if (c.count) { check(gpv_memcpy_d2h(voxelData.invIndex.data(), c.d_inv_index, c.count * 4, nullptr)); check(gpv_stream_sync(nullptr)); }
+		voxelData.boxCenterCUDAData = c.d_center; voxelData.boxExtentCUDAData = c.d_extent;
+		voxelData.collisionInit = true;
+	}
+
+	// Object::BuildHierarchy (src/Object.cpp:2790-2867): needs GLParameters::collision = true at PerformVoxelization and a grid whose
+	// dimensions are powers of two (the reference's loop is not defined on others: Error)
+	void BuildHierarchy(const GLParameters*)
+	{
+		if (!voxelInit) throw Error("BuildHierarchy before PerformVoxelization");
+		gpv_hierarchy h;
+		check(gpv_build_hierarchy(ctx_, nullptr, &h));
+		const size_t n = (size_t)h.n_boxes;
+		std::vector<float> mid(n * 3), half(n * 3);
+		std::vector<uint8_t> solid(n);
+		std::vector<int32_t> child(n * 2);
+		check(gpv_memcpy_d2h(mid.data(), h.d_mid, (int64_t)n * 12, nullptr)); check(gpv_memcpy_d2h(half.data(), h.d_half, (int64_t)n * 12, nullptr));
+		check(gpv_memcpy_d2h(solid.data(), h.d_solid, (int64_t)n, nullptr)); check(gpv_memcpy_d2h(child.data(), h.d_child, (int64_t)n * 8, nullptr));
+		check(gpv_stream_sync(nullptr));
+		voxelData.numLevels = h.num_levels;
+		voxelData.bBoxHierarchy.resize(n);
+		for (size_t i = 0; i < n; i++) {
+			BBoxData& b = voxelData.bBoxHierarchy[i];
+			for (int a = 0; a < 3; a++) { b.midPoint[a] = mid[i * 3 + a]; b.halfSize[a] = half[i * 3 + a]; }
+			b.solid = solid[i]; b.childIndex1 = child[2 * i]; b.childIndex2 = child[2 * i + 1]; b.index = (int)i;
+		}
 	}
 
 	void SaveVoxelization(const GLParameters*, const char* dir = ".")

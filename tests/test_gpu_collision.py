@@ -59,3 +59,32 @@ def test_hierarchy_refuses_what_the_reference_cannot_do(product, ctx, tmp_path_f
     ctx.voxelize(sphere, product.Params(32, 4, product.GPV_COLLISION, 4, 12))  # a slab
     with pytest.raises(product.GpvError):
         ctx.build_hierarchy()
+
+
+def test_cli_facade_reports_the_oracle_hierarchy(product, oracle, tmp_path_factory, tmp_path):
+    """The Object-shaped C++ facade (include/gpview_b200.hpp: Object::CollisionInitCUDA / BuildHierarchy, same member names as the
+    reference) through the headless CLI: counts, levels and the root box the oracle computes; files still the oracle writer's."""
+    import filecmp, os, re, subprocess
+    from util import ROOT
+    exe = os.path.join(ROOT, "tools", "gpview_voxelize")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tools")])
+    path = mesh_path("sphere", tmp_path_factory.getbasetemp())
+    out = tmp_path / "cli"
+    out.mkdir()
+    log = subprocess.run([exe, "--l1", "32", "--l2", "4", "--collision", "--hierarchy", "--out", str(out), path], capture_output=True, text=True)
+    assert log.returncode == 0, log.stderr
+    want = oracle.OracleMesh(path).voxelize(32, 4, oracle.FILL_CERTIFIED, 4)
+    lv, mid, half, solid, child = want.build_hierarchy()
+    field = lambda name: re.search(name + r"\s*: (.*)", log.stdout).group(1)
+    assert int(field("Collision Boxes")) == want.counts[0] + want.counts[1]
+    assert int(field("Hierarchy Levels")) == lv and int(field("Hierarchy Boxes")) == want.cells - 1 and int(field("Solid Boxes")) == int(solid.sum())
+    root = [np.float32(x) for x in field("Root Box").replace("+-", " ").split()]
+    assert np.array_equal(np.array(root[:3], np.float32), mid[-1]) and np.array_equal(np.array(root[3:], np.float32), half[-1])
+    ref = tmp_path / "ora"
+    ref.mkdir()
+    want.save(-1, str(ref))
+    for n in sorted(os.listdir(ref)):
+        assert filecmp.cmp(ref / n, out / n, shallow=False), n      # (the facade moves Level 2 as 2 bits per sub-voxel by default)
+    bad = subprocess.run([exe, "--l1", "64", "--hierarchy", mesh_path("cessna", tmp_path_factory.getbasetemp())], capture_output=True, text=True, cwd=str(tmp_path))
+    assert bad.returncode == 1 and "power of two" in bad.stderr

@@ -2,8 +2,9 @@
 // voxelizer path: load every mesh named on the command line (type by the last three characters, like main()), voxelize, write
 // the six ObjN*.{txt,raw} files.  Build: make -C tools.  No GLEW / freeglut.
 //
-//   gpview_voxelize [--l1 N] [--l2 M] [--no-level2] [--no-normals] [--tolerant] [--obj-id K] [--out DIR] [--device D] mesh.obj|mesh.off ...
+//   gpview_voxelize [--l1 N] [--l2 M] [--no-level2] [--no-normals] [--tolerant] [--obj-id K] [--out DIR] [--device D] [--collision] [--hierarchy] mesh.obj|mesh.off ...
 //   --tolerant: polygons, free-form blanks, comments, relative indices (GPV_LOAD_TOLERANT, an extension to the reference's readers)
+//   --collision: also Object::CollisionInitCUDA (occupied boxes); --hierarchy: also Object::BuildHierarchy (power-of-two grids only)
 #include "../include/gpview_b200.hpp"
 #include <chrono>
 #include <cstdio>
@@ -15,7 +16,7 @@ int main(int argc, char** argv)
 	gpview::GLParameters gp;
 	gp.saveVoxels = false;
 	const char* out = ".";
-	bool tolerant = false;
+	bool tolerant = false, collision = false, hierarchy = false;
 	int objID = -1; // GPView numbers the first OBJ -1, the second 0, ... (dlID - 3, src/GPView.cpp:181)
 	std::vector<const char*> files;
 	for (int i = 1; i < argc; i++) {
@@ -24,6 +25,8 @@ int main(int argc, char** argv)
 		else if (!strcmp(argv[i], "--no-level2")) gp.level2Voxels = false;
 		else if (!strcmp(argv[i], "--no-normals")) gp.normals = false;
 		else if (!strcmp(argv[i], "--tolerant")) tolerant = true;
+		else if (!strcmp(argv[i], "--collision")) collision = true;
+		else if (!strcmp(argv[i], "--hierarchy")) { hierarchy = true; gp.collision = true; }
 		else if (!strcmp(argv[i], "--obj-id") && i + 1 < argc) objID = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
 		else if (!strcmp(argv[i], "--device") && i + 1 < argc) gp.device = atoi(argv[++i]);
@@ -52,6 +55,18 @@ int main(int argc, char** argv)
 			if (gp.level2Voxels)
 				printf("Voxels Level2          : %lld\nInside Voxels Level2   : %lld\nBoundary Voxels Level2 : %lld\n", (long long)(v.result.n_boundary * v.result.n23),
 				       (long long)v.numLevel2InsideVoxels, (long long)v.numLevel2BoundaryVoxels);
+			if (collision) {
+				o.CollisionInitCUDA(&gp);
+				printf("Collision Boxes        : %zu\n", v.invIndex.size());
+			}
+			if (hierarchy) {
+				o.BuildHierarchy(&gp);
+				size_t solid = 0;
+				for (const gpview::BBoxData& b : v.bBoxHierarchy) solid += b.solid != 0;
+				const gpview::BBoxData& root = v.bBoxHierarchy.back();
+				printf("Hierarchy Levels       : %d\nHierarchy Boxes        : %zu\nSolid Boxes            : %zu\nRoot Box               : %.9g %.9g %.9g +- %.9g %.9g %.9g\n", v.numLevels,
+				       v.bBoxHierarchy.size(), solid, root.midPoint[0], root.midPoint[1], root.midPoint[2], root.halfSize[0], root.halfSize[1], root.halfSize[2]);
+			}
 			printf("Load Time              : %g\nVoxelize Time          : %g\nSave Time              : %g\n\n", s(t0, t1), s(t1, t2), s(t2, t3));
 		}
 	} catch (const gpview::Error& e) {
